@@ -1,0 +1,73 @@
+"""Structured mesh generators mirroring the reference's Julia constructors (host logic, numpy only).
+
+`tri_grid`  follows src/MFEM/MFEM.jl:134-170  (`Mesh(m, n, h; version)`), 
+`tet_grid`  follows src/MFEM3/MFEM.jl:124-185 (`Mesh3(m, n, l, h)`, 5 tets per cube, parity-alternating).
+Returned connectivity is 0-based (the Julia arrays are 1-based).
+"""
+import numpy as np
+
+
+def tri_grid(m, n, h, version=1, rng=None):
+    """(m+1)(n+1) nodes, 2mn triangles. version 1/2 = the two diagonal directions, 3 = random per cell."""
+    jj, ii = np.meshgrid(np.arange(m, dtype=np.int64), np.arange(n, dtype=np.int64))   # ii: row (y), jj: col (x)
+    a = (ii * (m + 1) + jj).reshape(-1)
+    v1 = np.stack([np.stack([a, a + 1, a + m + 1], 1), np.stack([a + 1, a + m + 1, a + m + 2], 1)], 1)     # MFEM.jl:143-145
+    v2 = np.stack([np.stack([a, a + m + 2, a + m + 1], 1), np.stack([a, a + 1, a + m + 2], 1)], 1)         # MFEM.jl:146-148
+    if version == 1:
+        el = v1
+    elif version == 2:
+        el = v2
+    elif version == 3:
+        rng = np.random.default_rng(0) if rng is None else rng
+        pick = rng.random(m * n) > 0.5                                                                     # MFEM.jl:149-156
+        el = np.where(pick[:, None, None], v1, v2)
+    else:
+        raise ValueError("version must be 1, 2 or 3")
+    elems = el.reshape(2 * m * n, 3)
+    y, x = np.meshgrid(np.arange(n + 1) * float(h), np.arange(m + 1) * float(h), indexing="ij")
+    coords = np.stack([x.reshape(-1), y.reshape(-1)], 1)
+    return coords, elems
+
+
+_TE1 = np.array([[1, 2, 3, 5], [2, 3, 4, 8], [3, 5, 7, 8], [2, 3, 5, 8], [2, 5, 6, 8]]) - 1   # MFEM.jl:131-137
+_TE2 = np.array([[1, 2, 4, 6], [1, 5, 6, 7], [4, 6, 7, 8], [1, 4, 6, 7], [1, 3, 4, 7]]) - 1   # MFEM.jl:138-144
+
+
+def tet_grid(m, n, l, h):
+    """(m+1)(n+1)(l+1) nodes, 5mnl tets. Only consistent for m == n (reference quirk Q9)."""
+    # coords: for k; for j in 1:m+1; for i in 1:n+1  -> x=(i-1)h fastest
+    k, j, i = np.meshgrid(np.arange(l + 1), np.arange(m + 1), np.arange(n + 1), indexing="ij")
+    coords = np.stack([i.reshape(-1) * float(h), j.reshape(-1) * float(h), k.reshape(-1) * float(h)], 1)
+
+    def ID(i, j, k):   # 1-based in, 0-based out ; MFEM.jl:128-130
+        return (k - 1) * (n + 1) * (m + 1) + (j - 1) * (m + 1) + i - 1
+
+    ii, jj, kk = np.meshgrid(np.arange(1, n + 1, dtype=np.int64), np.arange(1, m + 1, dtype=np.int64),
+                             np.arange(1, l + 1, dtype=np.int64), indexing="ij")   # loops: for i; for j; for k
+    ii, jj, kk = ii.reshape(-1), jj.reshape(-1), kk.reshape(-1)
+    IDX = np.stack([ID(ii, jj, kk), ID(ii + 1, jj, kk), ID(ii, jj + 1, kk), ID(ii + 1, jj + 1, kk),
+                    ID(ii, jj, kk + 1), ID(ii + 1, jj, kk + 1), ID(ii, jj + 1, kk + 1), ID(ii + 1, jj + 1, kk + 1)], 1)
+    even = ((ii + jj + kk) % 2 == 0)
+    e1 = IDX[:, _TE1]          # ncell x 5 x 4
+    e2 = IDX[:, _TE2]
+    elems = np.where(even[:, None, None], e1, e2).reshape(-1, 4)
+    return coords, elems
+
+
+def jitter_unstructured(m, n, h, seed=2, jitter=0.3, permute=True):
+    """BASELINE config 4's synthetic unstructured mesh: structured grid, interior nodes jittered by
+    U(-jitter*h, jitter*h), per-cell random diagonal (version 3), random node + element renumbering."""
+    rng = np.random.default_rng(seed)
+    coords, elems = tri_grid(m, n, h, version=3, rng=rng)
+    ix = np.arange((m + 1) * (n + 1)) % (m + 1)
+    iy = np.arange((m + 1) * (n + 1)) // (m + 1)
+    interior = (ix > 0) & (ix < m) & (iy > 0) & (iy < n)
+    coords = coords + interior[:, None] * rng.uniform(-jitter * h, jitter * h, coords.shape)
+    if permute:
+        pn = rng.permutation(coords.shape[0])          # new id of old node i is inv[i]
+        inv = np.empty_like(pn)
+        inv[pn] = np.arange(len(pn))
+        coords = coords[pn]
+        elems = inv[elems]
+        elems = elems[rng.permutation(elems.shape[0])]
+    return coords, elems

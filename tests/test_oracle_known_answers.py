@@ -1,0 +1,324 @@
+"""Pins the CPU oracle against every known answer the reference's own tests hold for the path
+ plus hand-derivable goldens and mathematical invariants.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import adfem_jl_b200  # noqa: F401  (package shim)
+from adfem_jl_b200 import meshgen
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def csr(O, ind, vv, n):
+    rp, ci, v = O.canonical_csr(ind, vv, n)
+    return sp.csr_matrix((v, ci, rp), shape=(n, n))
+
+
+# ----------------------------------------------------------------------------- reference test values
+def test_mesh_2x2_reference_values(oracle):
+    """test/MFEM2.jl:7-27 — nodes, ngauss == 24, area == 0.125."""
+    c, e = meshgen.tri_grid(2, 2, 0.5)
+    assert np.allclose(c, [[0, 0], [.5, 0], [1, 0], [0, .5], [.5, .5], [1, .5], [0, 1], [.5, 1], [1, 1]])
+    M = oracle.Mesh2D(c, e)
+    assert M.ngauss == 24
+    assert np.allclose(M.area, np.ones(8) * 0.25 / 2, rtol=0, atol=1e-15)
+    # quirk Q3: second triangle of every cell is clockwise in the input and gets v0<->v1 swapped
+    assert M.elems[1].tolist() == [3, 1, 4] and M.elems[0].tolist() == [0, 1, 3]
+
+
+def test_segment_rule_reference_values(oracle):
+    """test/MFEM/MCore.jl:1-14 — lorder=6 gives the 4-point Gauss-Legendre rule, ascending."""
+    p, w = oracle.segment_rule(6)
+    assert len(p) == 4
+    vals = 5.0 * (1 - p) + 6.0 * p
+    assert np.allclose(vals, [5.069431844202973, 5.330009478207572, 5.669990521792428, 5.930568155797027], rtol=0, atol=1e-14)
+    assert abs(w.sum() - 1) < 1e-15
+
+
+def test_five_point_stencil_golden(oracle):
+    """Hand-derivable golden (SURVEY §8c vi): P1 Laplace on UnitSquareMesh(8,8,'left') == Mesh(8,8,1/8)
+    has interior rows [-1,-1,4,-1,-1] and structural zeros on the diagonal neighbours."""
+    c, e = meshgen.tri_grid(8, 8, 1 / 8)
+    M = oracle.Mesh2D(c, e)
+    A = csr(oracle, *M.laplace_fwd(np.ones(M.ngauss)), M.ndof)
+    i = 4 * 9 + 4
+    row = A.getrow(i)
+    cols = row.indices.tolist()
+    assert cols == [i - 9, i - 8, i - 1, i, i + 1, i + 8, i + 9]
+    dense = A.toarray()
+    assert np.allclose(dense[i, [i - 9, i - 1, i, i + 1, i + 9]], [-1, -1, 4, -1, -1], atol=1e-13)
+    assert abs(dense[i, i - 8]) < 1e-13 and abs(dense[i, i + 8]) < 1e-13     # 'left' diagonals: (i-8),(i+8) present, value 0
+    assert A[i, i - 8] == 0 and (i - 8) in cols and (i + 8) in cols          # structural zeros kept
+    assert np.allclose(dense, dense.T, atol=1e-13)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_source_equals_mass_times_ones(oracle, degree):
+    """deps/MFEM/FemSource1/ftest.jl:4-16."""
+    c, e = meshgen.tri_grid(8, 8, 1 / 8)
+    M = oracle.Mesh2D(c, e, degree=degree)
+    rng = np.random.default_rng(0)
+    coef = rng.random(M.ngauss)
+    C = csr(oracle, *M.mass_fwd(coef), M.ndof)
+    assert np.allclose(M.source_fwd(coef), C @ np.ones(M.ndof), rtol=0, atol=1e-15)
+
+
+# ----------------------------------------------------------------------------- invariants / exactness
+@pytest.mark.parametrize("degree", [1, 2])
+def test_2d_invariants_and_exactness(oracle, degree):
+    c, e = meshgen.jitter_unstructured(6, 5, 0.2, seed=5)
+    M = oracle.Mesh2D(c, e, degree=degree)
+    assert M.g == (3 if degree == 1 else 6) and M.elem_ndof == (3 if degree == 1 else 6)
+    assert M.ndof == M.nnode + (0 if degree == 1 else M.nedge)
+    assert M.nedge == M.nnode + M.nelem - 1                      # Euler, simply connected
+    area = 6 * 5 * 0.04
+    assert abs(M.area.sum() - area) < 1e-13 and abs(M.weights.sum() - area) < 1e-13
+    one = np.ones(M.ngauss)
+    K = csr(oracle, *M.laplace_fwd(one), M.ndof)
+    Mm = csr(oracle, *M.mass_fwd(one), M.ndof)
+    assert np.abs(K @ np.ones(M.ndof)).max() < 1e-12
+    assert abs(Mm.sum() - area) < 1e-13
+    assert abs(M.source_fwd(one).sum() - area) < 1e-13
+    # nodal interpolant of a polynomial of the element degree is exact
+    xy = np.zeros((M.ndof, 2))
+    xy[:M.nnode] = M.coords
+    if degree == 2:
+        xy[M.nnode:] = 0.5 * (M.coords[M.edges[:, 0]] + M.coords[M.edges[:, 1]])
+    x, y = xy[:, 0], xy[:, 1]
+    if degree == 1:
+        u = 2 * x - 3 * y + 1
+        exact_grad2 = 13 * area
+    else:
+        u = x * x + 2 * x * y - y + 0.5
+        # |grad u|^2 = (2x+2y)^2 + (2x-1)^2 integrated over [0,1.2]x[0,1.0]
+        a, b = 1.2, 1.0
+        exact_grad2 = (4 * (a ** 3 / 3 * b + 2 * (a ** 2 / 2) * (b ** 2 / 2) + a * b ** 3 / 3)
+                       + (4 * a ** 3 / 3 - 2 * a ** 2 + a) * b)
+    assert abs(u @ (K @ u) - exact_grad2) < 1e-11
+    # Gauss points lie inside their element and reproduce linear fields
+    gp = M.gauss.reshape(M.nelem, M.g, 2)
+    cent = M.coords[M.elems].mean(1)
+    assert np.allclose((gp * (M.weights.reshape(M.nelem, M.g, 1))).sum(1) / M.area[:, None], cent, atol=1e-13)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_3d_invariants_and_exactness(oracle, degree):
+    c, e = meshgen.tet_grid(3, 3, 2, 0.5)
+    M = oracle.Mesh3D(c, e, degree=degree)
+    assert M.g == (4 if degree == 1 else 11) and M.elem_ndof == (4 if degree == 1 else 10)
+    vol = 1.5 * 1.5 * 1.0
+    assert abs(M.volume.sum() - vol) < 1e-13 and abs(M.weights.sum() - vol) < 1e-13
+    assert (M.volume > 0).all()
+    one = np.ones(M.ngauss)
+    K = csr(oracle, *M.laplace_fwd(one), M.ndof)
+    Mm = csr(oracle, *M.mass_fwd(one), M.ndof)
+    assert np.abs(K @ np.ones(M.ndof)).max() < 1e-12
+    assert abs(Mm.sum() - vol) < 1e-12
+    assert np.allclose(M.source_fwd(one), Mm @ np.ones(M.ndof), atol=1e-15)
+    xyz = np.zeros((M.ndof, 3))
+    xyz[:M.nnode] = M.coords
+    if degree == 2:
+        xyz[M.nnode:] = 0.5 * (M.coords[M.edges[:, 0]] + M.coords[M.edges[:, 1]])
+    x, y, z = xyz.T
+    if degree == 1:
+        u = x - 2 * y + 3 * z
+        exact = 14 * vol
+    else:
+        u = x * x + y * z
+        # |grad u|^2 = 4x^2 + z^2 + y^2 over [0,1.5]^2 x [0,1]
+        exact = 4 * (1.5 ** 3 / 3) * 1.5 * 1.0 + 1.5 * 1.5 * (1 / 3) + 1.5 * (1.5 ** 3 / 3) * 1.0
+    assert abs(u @ (K @ u) - exact) < 1e-11
+    # 3-D elasticity extension (N2): rigid-body modes are in the null space, matrix symmetric for symmetric H
+    lam, mu = 1.3, 0.7
+    H = np.zeros((6, 6))
+    H[:3, :3] = lam
+    H[np.arange(3), np.arange(3)] += 2 * mu
+    H[np.arange(3, 6), np.arange(3, 6)] = mu
+    S = csr(oracle, *M.stiffness_fwd(np.tile(H.reshape(-1), M.ngauss)), 3 * M.ndof)
+    n = M.ndof
+    modes = [np.r_[np.ones(n), np.zeros(2 * n)], np.r_[np.zeros(n), np.ones(n), np.zeros(n)], np.r_[-y, x, np.zeros(n)],
+             np.r_[np.zeros(n), -z, y], np.r_[z, np.zeros(n), -x]]
+    for r in modes:
+        assert np.abs(S @ r).max() < 1e-11
+    assert abs(S - S.T).max() < 1e-12
+    # patch test: u = (x, 0, 0) has strain energy (lam+2mu)*vol
+    ux = np.r_[x, np.zeros(2 * n)]
+    assert abs(ux @ (S @ ux) - (lam + 2 * mu) * vol) < 1e-11
+
+
+def test_2d_elasticity_invariants(oracle):
+    c, e = meshgen.jitter_unstructured(4, 4, 0.25, seed=7)
+    for degree in (1, 2):
+        M = oracle.Mesh2D(c, e, degree=degree)
+        E, nu = 2.0, 0.3
+        H = E / ((1 + nu) * (1 - 2 * nu)) * np.array([[1 - nu, nu, 0], [nu, 1 - nu, 0], [0, 0, (1 - 2 * nu) / 2]])
+        S = csr(oracle, *M.stiffness_fwd(np.tile(H.reshape(-1), M.ngauss)), 2 * M.ndof)
+        n = M.ndof
+        xy = np.zeros((n, 2))
+        xy[:M.nnode] = M.coords
+        if degree == 2:
+            xy[M.nnode:] = 0.5 * (M.coords[M.edges[:, 0]] + M.coords[M.edges[:, 1]])
+        for r in (np.r_[np.ones(n), np.zeros(n)], np.r_[np.zeros(n), np.ones(n)], np.r_[-xy[:, 1], xy[:, 0]]):
+            assert np.abs(S @ r).max() < 1e-11
+        ux = np.r_[xy[:, 0], np.zeros(n)]
+        assert abs(ux @ (S @ ux) - H[0, 0] * 1.0) < 1e-11
+
+
+# ----------------------------------------------------------------------------- gradients (gradtest.jl idea)
+def _fd_check(fwd, bwd, x0, seed=0):
+    """Directional derivative of L = sum(w * out) vs <bwd(w), v>; ops are linear in the coefficient so
+    a single central difference is exact to rounding."""
+    rng = np.random.default_rng(seed)
+    out0 = fwd(x0)
+    wgt = rng.standard_normal(out0.shape)
+    v = rng.standard_normal(x0.shape)
+    g = bwd(wgt)
+    eps = 1e-3
+    fd = (np.sum(wgt * fwd(x0 + eps * v)) - np.sum(wgt * fwd(x0 - eps * v))) / (2 * eps)
+    assert abs(fd - g @ v) <= 1e-9 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_2d_adjoints(oracle, degree):
+    c, e = meshgen.jitter_unstructured(3, 4, 0.3, seed=11)
+    M = oracle.Mesh2D(c, e, degree=degree)
+    rng = np.random.default_rng(1)
+    _fd_check(lambda k: M.laplace_fwd(k)[1], M.laplace_bwd, rng.random(M.ngauss) + 1)
+    _fd_check(lambda k: M.mass_fwd(k)[1], M.mass_bwd, rng.random(M.ngauss) + 1)
+    _fd_check(lambda k: M.stiffness_fwd(k)[1], M.stiffness_bwd, rng.random(9 * M.ngauss))
+    _fd_check(M.source_fwd, M.source_bwd, rng.random(M.ngauss))
+    # PCL Jacobian (FemLaplaceScalar.h:65-92) is d vv / d kappa: column-major ngauss x N
+    J = M.laplace_jacobian()
+    k0 = rng.random(M.ngauss)
+    assert np.allclose(J.T @ k0, M.laplace_fwd(k0)[1], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_3d_adjoints(oracle, degree):
+    c, e = meshgen.tet_grid(2, 2, 2, 0.5)
+    M = oracle.Mesh3D(c, e, degree=degree)
+    rng = np.random.default_rng(2)
+    _fd_check(lambda k: M.laplace_fwd(k)[1], M.laplace_bwd, rng.random(M.ngauss) + 1)
+    _fd_check(lambda k: M.mass_fwd(k)[1], M.mass_bwd, rng.random(M.ngauss) + 1)
+    _fd_check(M.source_fwd, M.source_bwd, rng.random(M.ngauss))
+    if degree == 1:
+        _fd_check(lambda k: M.stiffness_fwd(k)[1], M.stiffness_bwd, rng.random(36 * M.ngauss))
+
+
+# ----------------------------------------------------------------------------- Dirichlet
+def test_dirichlet_matches_dense_julia_version(oracle):
+    """test/mfem.jl:78-88 — COO op == dense slicing version (src/MFEM/MUtils.jl:184-199)."""
+    rng = np.random.default_rng(3)
+    N = 7
+    A = rng.random((N, N))
+    ii, jj = np.nonzero(A)
+    order = rng.permutation(len(ii))       # arbitrary slot order, with duplicates below
+    ii, jj = ii[order], jj[order]
+    vv = A[ii, jj]
+    ii = np.r_[ii, ii[:5]]
+    jj = np.r_[jj, jj[:5]]
+    vv = np.r_[vv * 1.0, vv[:5] * 0.0 + 0.25]
+    A[ii[-5:], jj[-5:]] += 0.25
+    bd = np.array([4, 1, 2])
+    bdval = np.array([1.0, 2.0, 3.0])
+    rhs = rng.random(N)
+    oi, ov, orhs = oracle.impose_dirichlet_fwd(np.stack([ii, jj], 1), vv, bd, rhs, bdval)
+    idx = np.ones(N, bool)
+    idx[bd] = False
+    r = rhs.copy()
+    r[idx] = rhs[idx] - A[np.ix_(idx, bd)] @ bdval
+    r[bd] = bdval
+    B = np.zeros((N, N))
+    B[np.ix_(idx, idx)] = A[np.ix_(idx, idx)]
+    B[bd, bd] = 1.0
+    got = sp.coo_matrix((ov, (oi[:, 0], oi[:, 1])), shape=(N, N)).toarray()
+    assert np.allclose(got, B, atol=1e-14) and np.allclose(orhs, r, atol=1e-14)
+    # appended diagonals come in ascending dof order (std::map iteration, quirk Q11)
+    assert oi[-3:, 0].tolist() == [1, 2, 4] and np.all(ov[-3:] == 1.0)
+    # adjoint by finite differences on a random linear functional of (ov, orhs)
+    w1, w2 = rng.standard_normal(len(ov)), rng.standard_normal(N)
+    gv, gr, gb = oracle.impose_dirichlet_bwd(w1, w2, np.stack([ii, jj], 1), vv, bd, bdval, N)
+
+    def L(vv_, rhs_, bdval_):
+        _, a, b = oracle.impose_dirichlet_fwd(np.stack([ii, jj], 1), vv_, bd, rhs_, bdval_)
+        return w1 @ a + w2 @ b
+    eps = 1e-6
+    for (arr, g, which) in ((vv, gv, 0), (rhs, gr, 1), (bdval, gb, 2)):
+        d = rng.standard_normal(arr.shape)
+        args_p, args_m = [vv, rhs, bdval], [vv, rhs, bdval]
+        args_p[which] = arr + eps * d
+        args_m[which] = arr - eps * d
+        fd = (L(*args_p) - L(*args_m)) / (2 * eps)
+        assert abs(fd - g @ d) < 1e-7 * max(1, abs(fd))
+
+
+# ----------------------------------------------------------------------------- structured-grid ops
+def _julia_stiffness1(K, m, n, h):
+    """src/Core.jl:98-131 restated (independent pure-Julia implementation in the reference)."""
+    pts = [(-1 / np.sqrt(3) + 1) / 2, (1 / np.sqrt(3) + 1) / 2]
+    Om = np.zeros((4, 4))
+    for xi in pts:
+        for eta in pts:
+            B = np.array([[-1 / h * (1 - eta), 1 / h * (1 - eta), -1 / h * eta, 1 / h * eta],
+                          [-1 / h * (1 - xi), -1 / h * xi, 1 / h * (1 - xi), 1 / h * xi]])
+            Om += B.T @ K @ B * 0.25 * h * h
+    A = np.zeros(((m + 1) * (n + 1),) * 2)
+    for i in range(m):
+        for j in range(n):
+            kk = np.array([j * (m + 1) + i, j * (m + 1) + i + 1, (j + 1) * (m + 1) + i, (j + 1) * (m + 1) + i + 1])
+            A[np.ix_(kk, kk)] += Om
+    return A
+
+
+def test_structured_ops(oracle):
+    m, n, h = 4, 3, 0.5
+    rng = np.random.default_rng(4)
+    K = np.array([[2.0, 0.3], [0.3, 1.0]])
+    N = (m + 1) * (n + 1)
+    # constant K (Forward2) and the same K tiled per Gauss point (Forward_UFS) both equal the Julia version
+    for hm in (K, np.tile(K, (4 * m * n, 1, 1))):
+        ii, jj, vv = oracle.univariate_stiffness_fwd(hm, m, n, h)
+        assert ii.min() == 1 and ii.max() == N          # 1-based like the op
+        A = sp.coo_matrix((vv, (ii - 1, jj - 1)), shape=(N, N)).toarray()
+        assert np.allclose(A, _julia_stiffness1(K, m, n, h), atol=1e-13)
+    hm = rng.random((4 * m * n, 2, 2))
+    _fd_check(lambda x: oracle.univariate_stiffness_fwd(x.reshape(-1, 2, 2), m, n, h)[2],
+              lambda g: oracle.univariate_stiffness_bwd(g, m, n, h, True), hm.reshape(-1))
+    _fd_check(lambda x: oracle.univariate_stiffness_fwd(x.reshape(2, 2), m, n, h)[2],
+              lambda g: oracle.univariate_stiffness_bwd(g, m, n, h, False), K.reshape(-1))
+    # elasticity: constant H (FemStiffness) == per-Gauss H tiled (SpatialFemStiffness) after summing Gauss points
+    H = np.array([[3.0, 1.0, 0.2], [1.0, 2.5, 0.1], [0.2, 0.1, 0.8]])
+    ii, jj, vv = oracle.fem_stiffness_fwd(H, m, n, h)
+    A1 = sp.coo_matrix((vv, (ii - 1, jj - 1)), shape=(2 * N, 2 * N)).toarray()
+    ii, jj, vv = oracle.spatial_stiffness_fwd(np.tile(H, (4 * m * n, 1, 1)), m, n, h)
+    A2 = sp.coo_matrix((vv, (ii - 1, jj - 1)), shape=(2 * N, 2 * N)).toarray()
+    assert np.allclose(A1, A2, atol=1e-12)
+    x = np.tile(np.arange(m + 1) * h, n + 1)
+    y = np.repeat(np.arange(n + 1) * h, m + 1)
+    for r in (np.r_[np.ones(N), np.zeros(N)], np.r_[-y, x]):
+        assert np.abs(A1 @ r).max() < 1e-12
+    _fd_check(lambda xx: oracle.fem_stiffness_fwd(xx.reshape(3, 3), m, n, h)[2], lambda g: oracle.fem_stiffness_bwd(g, m, n, h),
+              rng.random(9))
+    _fd_check(lambda xx: oracle.spatial_stiffness_fwd(xx, m, n, h)[2], lambda g: oracle.spatial_stiffness_bwd(g, m, n, h),
+              rng.random(36 * m * n))
+    for t in (1, 2, 3):
+        mu = rng.random(4 * m * n * t)
+        hmat = oracle.svt_fwd(mu, m, n, t).reshape(-1, 2, 2)
+        assert np.allclose(hmat[:, 0, 0], mu[:4 * m * n])
+        assert np.allclose(hmat[:, 1, 1], mu[:4 * m * n] if t == 1 else mu[4 * m * n:8 * m * n])
+        assert np.allclose(hmat[:, 0, 1], 0 if t < 3 else mu[8 * m * n:]) and np.allclose(hmat[:, 0, 1], hmat[:, 1, 0])
+        _fd_check(lambda xx: oracle.svt_fwd(xx, m, n, t), lambda g: oracle.svt_bwd(g, m, n, t), mu)
+
+
+def test_config1_twoholes_fixture(oracle):
+    """BASELINE config 1 inputs: the README Poisson mesh; Euler characteristic of a domain with two holes."""
+    d = np.load(os.path.join(HERE, "golden", "twoholes_large.npz"))
+    M = oracle.Mesh2D(d["nodes"], d["elems"])
+    assert M.nelem == 2432 and M.ngauss == 3 * 2432
+    assert M.nnode - M.nedge + M.nelem == 1 - 2
+    assert M.ngauss * 9 == 65664                      # COO slots quoted in SURVEY §8a
+    K = csr(oracle, *M.laplace_fwd(np.sin(M.gauss[:, 0]) * (1 + M.gauss[:, 1] ** 2) + 1), M.ndof)
+    assert np.abs(K @ np.ones(M.ndof)).max() < 1e-10
