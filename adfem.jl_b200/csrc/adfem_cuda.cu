@@ -1,0 +1,713 @@
+// libadfem_cuda.so — mesh handle, symbolic phase, kernel dispatch and the C ABI of include/adfem_cuda.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/adfem_cuda.h"
+#include "host_mesh.h"
+#include "internal.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace adfem;
+
+namespace adfem {
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return 1; }
+}  // namespace adfem
+
+namespace {
+
+template <class T> cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v) {
+  cudaError_t e = b.alloc(v.size());
+  if (e != cudaSuccess) return e;
+  return v.empty() ? cudaSuccess : cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+struct FwdPlanDev {
+  TilePlan host;   // kept only when host_only (inspection); otherwise freed after upload
+  DevBuf<int> row_ptr, rows, elem_ptr, elems;
+  DevBuf<long long> soff_ptr, src_ptr;
+  DevBuf<uint16_t> src_off, src;
+  DevTilePlan dev{};
+  size_t bytes = 0;
+};
+struct AdjPlanDev {
+  AdjTilePlan host;
+  DevBuf<int> elem_ptr, elems, row_ptr, rows;
+  DevBuf<long long> gidx_ptr;
+  DevBuf<uint16_t> gidx;
+  DevAdjPlan dev{};
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct adfem_mesh {
+  HostMesh hm;
+  bool host_only = false;
+  int device = 0;
+  DevBuf<double> coords;
+  DevBuf<int> verts, conn;
+  DevMesh dm{};
+  // symbolic
+  bool has_pattern = false;
+  ScalarPattern pat;
+  DevBuf<long long> d_rowptr, d_adj_ptr;
+  DevBuf<int> d_colind, d_adj_elem;
+  DevBuf<uint8_t> d_adj_loc;
+  DevBuf<uint32_t> d_slot_nnz;
+  DevPattern dpat{};
+  std::map<int, std::unique_ptr<FwdPlanDev>> fwd_plans;   // keyed by S = (nc*d)^2
+  std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
+  // options
+  int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
+  int opt_smem_budget = 44 * 1024;
+  // scratch for the host-buffer calls
+  DevBuf<double> s_in, s_out;
+};
+
+namespace {
+
+#define CU_TRY(call)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+int need_device(const adfem_mesh* m) {
+  if (!m) return fail("null mesh handle");
+  if (m->host_only) return fail("mesh was created with ADFEM_HOST_ONLY: no device path (and there is no CPU fallback)");
+  cudaError_t e = cudaSetDevice(m->device);
+  if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_threads : default_threads(); }
+
+int ensure_pattern(adfem_mesh* m) {
+  if (m->has_pattern) return 0;
+  std::string err = m->pat.build(m->hm, nthreads_of(m));
+  if (!err.empty()) return fail("symbolic: " + err);
+  m->has_pattern = true;
+  if (!m->host_only) {
+    const HostMesh& h = m->hm;
+    const int dd = h.d * h.d;
+    CU_TRY(upload(m->d_rowptr, m->pat.rowptr));
+    CU_TRY(upload(m->d_colind, m->pat.colind));
+    CU_TRY(upload(m->d_adj_ptr, m->pat.adj_ptr));
+    CU_TRY(upload(m->d_adj_elem, m->pat.adj_elem));
+    CU_TRY(upload(m->d_adj_loc, m->pat.adj_loc));
+    std::vector<uint32_t> soa((size_t)h.ne * dd);
+    for (int e = 0; e < h.ne; e++)
+      for (int s = 0; s < dd; s++) soa[(size_t)s * h.ne + e] = m->pat.slot_nnz[(size_t)e * dd + s];
+    CU_TRY(upload(m->d_slot_nnz, soa));
+    m->dpat.n = m->pat.n; m->dpat.nnz = m->pat.nnz;
+    m->dpat.rowptr = m->d_rowptr.p; m->dpat.colind = m->d_colind.p; m->dpat.slot_nnz = m->d_slot_nnz.p;
+  }
+  return 0;
+}
+
+size_t fwd_smem_bytes(const TilePlan& tp, int S) {
+  return (size_t)8 * S * tp.max_elems + 8 * (size_t)tp.max_rows + 4 * ((size_t)tp.max_rows + 1) + 4 * (size_t)tp.max_rows + 2 * (size_t)tp.max_nnz + 16;
+}
+size_t adj_smem_bytes(const AdjTilePlan& ap, int nc) {
+  return (size_t)8 * nc * nc * ap.max_nnz + 8 * (size_t)ap.max_rows + 4 * ((size_t)ap.max_rows + 1) + 4 * (size_t)ap.max_rows + 2 * (size_t)ap.max_nnz + 16;
+}
+
+int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
+  if (int rc = ensure_pattern(m)) return rc;
+  const HostMesh& h = m->hm;
+  const int S = (nc * h.d) * (nc * h.d), dd = h.d * h.d;
+  auto it = m->fwd_plans.find(S);
+  if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
+  auto P = std::make_unique<FwdPlanDev>();
+  int budget = m->opt_smem_budget;
+  std::string err = "tile too large";
+  for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
+    int max_elems = std::max(4, std::min(65535 / dd, budget / (8 * S)));
+    double elems_per_row = (double)h.ne * h.d / std::max(1, h.ndof);     // average incident elements per dof
+    int R = m->opt_rows_per_tile > 0 ? m->opt_rows_per_tile : (int)(max_elems / std::max(1.0, elems_per_row) * h.d * 0.55);
+    R = std::max(4, std::min(R, 1024));
+    for (int tries = 0; tries < 12; tries++) {
+      err = P->host.build(h, m->pat, R, max_elems, nthreads_of(m));
+      if (err.empty() || R <= 4) break;
+      R = std::max(4, (int)(R * 0.7));
+    }
+  }
+  if (!err.empty()) return fail("forward tile plan: " + err);
+  TilePlan& tp = P->host;
+  P->bytes = 4 * (tp.row_ptr.size() + tp.rows.size() + tp.elem_ptr.size() + tp.elems.size()) + 8 * (tp.soff_ptr.size() + tp.src_ptr.size()) +
+             2 * (tp.src_off.size() + tp.src.size());
+  if (!m->host_only) {
+    CU_TRY(upload(P->row_ptr, tp.row_ptr)); CU_TRY(upload(P->rows, tp.rows));
+    CU_TRY(upload(P->elem_ptr, tp.elem_ptr)); CU_TRY(upload(P->elems, tp.elems));
+    CU_TRY(upload(P->soff_ptr, tp.soff_ptr)); CU_TRY(upload(P->src_off, tp.src_off));
+    CU_TRY(upload(P->src_ptr, tp.src_ptr)); CU_TRY(upload(P->src, tp.src));
+    P->dev = DevTilePlan{tp.ntiles, tp.max_rows, tp.max_elems, tp.max_nnz, P->row_ptr.p, P->rows.p, P->elem_ptr.p, P->elems.p,
+                         P->soff_ptr.p, P->src_off.p, P->src_ptr.p, P->src.p};
+    // the big arrays now live on the device
+    std::vector<int>().swap(tp.rows); std::vector<int>().swap(tp.elems);
+    std::vector<uint16_t>().swap(tp.src_off); std::vector<uint16_t>().swap(tp.src);
+  }
+  *out = P.get();
+  m->fwd_plans[S] = std::move(P);
+  return 0;
+}
+
+int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
+  if (int rc = ensure_pattern(m)) return rc;
+  const HostMesh& h = m->hm;
+  auto it = m->adj_plans.find(nc);
+  if (it != m->adj_plans.end()) { *out = it->second.get(); return 0; }
+  auto P = std::make_unique<AdjPlanDev>();
+  int budget = m->opt_smem_budget;
+  std::string err = "tile too large";
+  for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
+    int max_nnz = std::max(64, std::min(65535, budget / (8 * nc * nc + 2)));
+    double nnz_per_row = (double)m->pat.nnz / std::max(1, m->pat.n), rows_per_elem = (double)m->pat.n / std::max(1, h.ne);
+    int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(max_nnz / nnz_per_row / std::max(1e-9, rows_per_elem) * 0.6);
+    EPT = std::max(4, std::min(EPT, 2048));
+    for (int tries = 0; tries < 12; tries++) {
+      err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
+      if (err.empty() || EPT <= 4) break;
+      EPT = std::max(4, (int)(EPT * 0.7));
+    }
+  }
+  if (!err.empty()) return fail("adjoint tile plan: " + err);
+  AdjTilePlan& ap = P->host;
+  P->bytes = 4 * (ap.row_ptr.size() + ap.rows.size() + ap.elem_ptr.size() + ap.elems.size()) + 8 * ap.gidx_ptr.size() + 2 * ap.gidx.size();
+  if (!m->host_only) {
+    CU_TRY(upload(P->elem_ptr, ap.elem_ptr)); CU_TRY(upload(P->elems, ap.elems));
+    CU_TRY(upload(P->row_ptr, ap.row_ptr)); CU_TRY(upload(P->rows, ap.rows));
+    CU_TRY(upload(P->gidx_ptr, ap.gidx_ptr)); CU_TRY(upload(P->gidx, ap.gidx));
+    P->dev = DevAdjPlan{ap.ntiles, ap.max_rows, ap.max_elems, ap.max_nnz, P->elem_ptr.p, P->elems.p, P->row_ptr.p, P->rows.p, P->gidx_ptr.p, P->gidx.p};
+    std::vector<int>().swap(ap.rows); std::vector<int>().swap(ap.elems); std::vector<uint16_t>().swap(ap.gidx);
+  }
+  *out = P.get();
+  m->adj_plans[nc] = std::move(P);
+  return 0;
+}
+
+// ---- (dim, degree) dispatch ------------------------------------------------------------------------
+#define DISPATCH_ELEM(m, CALL)                                             \
+  do {                                                                     \
+    const int _dim = (m)->hm.dim, _deg = (m)->hm.degree;                   \
+    if (_dim == 2 && _deg == 1) { CALL(2, 1); }                            \
+    else if (_dim == 2 && _deg == 2) { CALL(2, 2); }                       \
+    else if (_dim == 3 && _deg == 1) { CALL(3, 1); }                       \
+    else { CALL(3, 2); }                                                   \
+  } while (0)
+
+inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <int DIM, int DEG, int OP>
+int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
+  constexpr int NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * ElemTraits<DIM, DEG>::D, S = Dt * Dt;
+  const size_t smem = fwd_smem_bytes(P->host, S);
+  auto kern = k_tile_fwd<DIM, DEG, OP>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<P->dev.ntiles, TILE_THREADS, smem, st>>>(m->dm, m->dpat, P->dev, coef, vals);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+template <int DIM, int DEG, int OP>
+int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
+  constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
+  if (m->opt_adjoint_tiled) {
+    AdjPlanDev* P = nullptr;
+    if (int rc = ensure_adj_plan(m, NC, &P)) return rc;
+    const size_t smem = adj_smem_bytes(P->host, NC);
+    auto kern = k_tile_adj<DIM, DEG, OP>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<P->dev.ntiles, TILE_THREADS, smem, st>>>(m->dm, m->dpat, P->dev, dvals, grad);
+  } else {
+    k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(m->dm, m->dpat, dvals, grad);
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int check_op(const adfem_mesh* m, int op) {
+  if (op < 0 || op > 2) return fail("unknown op");
+  (void)m;
+  return 0;
+}
+
+int coef_per_gauss(const adfem_mesh* m, int op) {
+  if (op != ADFEM_OP_STIFFNESS) return 1;
+  return m->hm.dim == 2 ? 9 : 36;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// handle API
+// ====================================================================================================
+extern "C" {
+
+const char* adfem_last_error(void) { return g_err.c_str(); }
+
+int adfem_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int vertex_stride, int nv, const int* elems, int ne,
+                      int order, int degree, int lorder, int flags) {
+  if (!out) return fail("null output");
+  *out = nullptr;
+  if (order == -1) order = degree == 1 ? 2 : 4;       // src/MFEM/MFEM.jl:71-77, src/MFEM3/MFEM.jl:49-55
+  if (lorder == -1) lorder = 6;                       // src/MFEM/MFEM.jl:79-85
+  auto m = std::make_unique<adfem_mesh>();
+  std::string err = m->hm.build(dim, vertices, vertex_stride, nv, elems, ne, order, degree, lorder);
+  if (!err.empty()) return fail(err);
+  m->host_only = (flags & ADFEM_HOST_ONLY) != 0;
+  if (!m->host_only) {
+    if (adfem_device_count() == 0) return fail("no CUDA device available (libadfem_cuda has no CPU fallback)");
+    CU_TRY(cudaGetDevice(&m->device));
+    const HostMesh& h = m->hm;
+    CU_TRY(upload(m->coords, h.coords));
+    const int nvl = h.dim + 1;
+    std::vector<int> vs((size_t)h.ne * nvl), cs((size_t)h.ne * h.d);
+    for (int e = 0; e < h.ne; e++) {
+      for (int k = 0; k < nvl; k++) vs[(size_t)k * h.ne + e] = h.verts[(size_t)e * nvl + k];
+      for (int k = 0; k < h.d; k++) cs[(size_t)k * h.ne + e] = h.conn[(size_t)e * h.d + k];
+    }
+    CU_TRY(upload(m->verts, vs));
+    CU_TRY(upload(m->conn, cs));
+    m->dm.dim = h.dim; m->dm.ne = h.ne; m->dm.nv = h.nv; m->dm.d = h.d; m->dm.g = h.g; m->dm.ndof = h.ndof;
+    m->dm.coords = m->coords.p; m->dm.verts = m->verts.p; m->dm.conn = m->conn.p; m->dm.rule = h.rule;
+  }
+  *out = m.release();
+  return 0;
+}
+
+void adfem_mesh_destroy(adfem_mesh* m) { delete m; }
+
+long long adfem_mesh_info(const adfem_mesh* m, int what) {
+  if (!m) return -1;
+  const HostMesh& h = m->hm;
+  switch (what) {
+    case ADFEM_INFO_DIM: return h.dim;
+    case ADFEM_INFO_NV: return h.nv;
+    case ADFEM_INFO_NE: return h.ne;
+    case ADFEM_INFO_NDOF: return h.ndof;
+    case ADFEM_INFO_NGAUSS: return (long long)h.ne * h.g;
+    case ADFEM_INFO_ELEM_NDOF: return h.d;
+    case ADFEM_INFO_NEDGES: return h.nedges;
+    case ADFEM_INFO_GAUSS_PER_ELEM: return h.g;
+    case ADFEM_INFO_NNZ_SCALAR: return m->has_pattern ? m->pat.nnz : -1;
+    case ADFEM_INFO_TILES_FWD: { long long t = 0; for (auto& kv : m->fwd_plans) t = kv.second->host.ntiles; return t; }
+    case ADFEM_INFO_TILES_ADJ: { long long t = 0; for (auto& kv : m->adj_plans) t = kv.second->host.ntiles; return t; }
+    case ADFEM_INFO_PLAN_BYTES: {
+      long long b = 0;
+      for (auto& kv : m->fwd_plans) b += (long long)kv.second->bytes;
+      for (auto& kv : m->adj_plans) b += (long long)kv.second->bytes;
+      return b;
+    }
+    default: return -1;
+  }
+}
+
+int adfem_mesh_edges(const adfem_mesh* m, long long* edges) {
+  if (!m) return fail("null mesh handle");
+  const long long ne = m->hm.nedges;
+  for (long long i = 0; i < ne; i++) { edges[i] = m->hm.edge_lo[i] + 1; edges[ne + i] = m->hm.edge_hi[i] + 1; }
+  return 0;
+}
+int adfem_mesh_connectivity(const adfem_mesh* m, long long* conn) {
+  if (!m) return fail("null mesh handle");
+  const size_t n = (size_t)m->hm.ne * m->hm.d;
+  for (size_t i = 0; i < n; i++) conn[i] = m->hm.conn[i] + 1;
+  return 0;
+}
+int adfem_mesh_element_to_vertices(const adfem_mesh* m, long long* elems) {
+  if (!m) return fail("null mesh handle");
+  const HostMesh& h = m->hm;
+  const int nvl = h.dim + 1;
+  for (int e = 0; e < h.ne; e++) for (int k = 0; k < nvl; k++) elems[(size_t)k * h.ne + e] = h.verts[(size_t)e * nvl + k] + 1;
+  return 0;
+}
+int adfem_mesh_gauss(const adfem_mesh* m, double* xyz) { if (!m) return fail("null mesh handle"); m->hm.gauss_points(xyz); return 0; }
+int adfem_mesh_gauss_weights(const adfem_mesh* m, double* w) { if (!m) return fail("null mesh handle"); m->hm.gauss_weights(w); return 0; }
+int adfem_mesh_measure(const adfem_mesh* m, double* a) { if (!m) return fail("null mesh handle"); m->hm.measure(a); return 0; }
+
+int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
+  if (!m || !key) return fail("null argument");
+  std::string k(key);
+  if (k == "rows_per_tile") { m->opt_rows_per_tile = (int)value; m->fwd_plans.clear(); }
+  else if (k == "elems_per_tile") { m->opt_elems_per_tile = (int)value; m->adj_plans.clear(); }
+  else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
+  else if (k == "host_threads") m->opt_threads = (int)value;
+  else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
+  else return fail("unknown option: " + k);
+  return 0;
+}
+
+int adfem_symbolic(adfem_mesh* m) {
+  if (!m) return fail("null mesh handle");
+  return ensure_pattern(m);
+}
+
+long long adfem_csr_nnz(adfem_mesh* m, int ncomp) {
+  if (!m || ensure_pattern(m)) return -1;
+  return m->pat.nnz * ncomp * ncomp;
+}
+
+int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr, int* colind) {
+  if (!m) return fail("null mesh handle");
+  if (int rc = ensure_pattern(m)) return rc;
+  const ScalarPattern& p = m->pat;
+  const long long n = p.n;
+  if ((long long)ncomp * n > 2147483647LL) return fail("ncomp*ndof exceeds 32-bit column ids");
+  for (int a = 0; a < ncomp; a++)
+    for (long long r = 0; r < n; r++) {
+      const long long rs = p.rowptr[r], len = p.rowptr[r + 1] - rs, base = ncomp * (a * p.nnz + rs);
+      rowptr[a * n + r] = base;
+      for (int b = 0; b < ncomp; b++)
+        for (long long j = 0; j < len; j++) colind[base + b * len + j] = (int)(p.colind[rs + j] + b * n);
+    }
+  rowptr[ncomp * n] = p.nnz * ncomp * ncomp;
+  return 0;
+}
+
+int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz) {
+  if (!m) return fail("null mesh handle");
+  if (int rc = ensure_pattern(m)) return rc;
+  memcpy(slot_nnz, m->pat.slot_nnz.data(), m->pat.slot_nnz.size() * sizeof(uint32_t));
+  return 0;
+}
+
+long long adfem_plan_array(adfem_mesh* m, int which_plan, int ncomp, int array_id, void* out) {
+  if (!m) { fail("null mesh handle"); return -1; }
+  if (!m->host_only) { fail("adfem_plan_array needs an ADFEM_HOST_ONLY handle (plans of device handles live on the device)"); return -1; }
+#define PLAN_ARR(vec)                                                                      \
+  { if (out) memcpy(out, (vec).data(), (vec).size() * sizeof((vec)[0])); return (long long)(vec).size(); }
+  if (which_plan == 0) {
+    FwdPlanDev* P = nullptr;
+    if (ensure_fwd_plan(m, ncomp, &P)) return -1;
+    const TilePlan& t = P->host;
+    switch (array_id) {
+      case 0: PLAN_ARR(t.row_ptr) case 1: PLAN_ARR(t.rows) case 2: PLAN_ARR(t.elem_ptr) case 3: PLAN_ARR(t.elems)
+      case 4: PLAN_ARR(t.soff_ptr) case 5: PLAN_ARR(t.src_off) case 6: PLAN_ARR(t.src_ptr) case 7: PLAN_ARR(t.src)
+    }
+  } else {
+    AdjPlanDev* P = nullptr;
+    if (ensure_adj_plan(m, ncomp, &P)) return -1;
+    const AdjTilePlan& t = P->host;
+    switch (array_id) {
+      case 0: PLAN_ARR(t.elem_ptr) case 1: PLAN_ARR(t.elems) case 2: PLAN_ARR(t.row_ptr) case 3: PLAN_ARR(t.rows)
+      case 4: PLAN_ARR(t.gidx_ptr) case 5: PLAN_ARR(t.gidx)
+    }
+  }
+#undef PLAN_ARR
+  fail("unknown plan array");
+  return -1;
+}
+
+int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
+  FwdPlanDev* P = nullptr;
+  if (int rc = ensure_fwd_plan(m, nc, &P)) return rc;
+#define CALL_FWD(DIM, DEG)                                                                                   \
+  switch (op) {                                                                                              \
+    case ADFEM_OP_LAPLACE: return launch_tile_fwd<DIM, DEG, OP_LAPLACE>(m, P, coef, vals, st);               \
+    case ADFEM_OP_MASS: return launch_tile_fwd<DIM, DEG, OP_MASS>(m, P, coef, vals, st);                     \
+    default: return launch_tile_fwd<DIM, DEG, OP_STIFFNESS>(m, P, coef, vals, st);                           \
+  }
+  DISPATCH_ELEM(m, CALL_FWD);
+#undef CALL_FWD
+  return 0;
+}
+
+int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, double* grad_coef, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  if (int rc = ensure_pattern(m)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL_ADJ(DIM, DEG)                                                                                   \
+  switch (op) {                                                                                              \
+    case ADFEM_OP_LAPLACE: return launch_adj<DIM, DEG, OP_LAPLACE>(m, dvals, grad_coef, st);                 \
+    case ADFEM_OP_MASS: return launch_adj<DIM, DEG, OP_MASS>(m, dvals, grad_coef, st);                       \
+    default: return launch_adj<DIM, DEG, OP_STIFFNESS>(m, dvals, grad_coef, st);                             \
+  }
+  DISPATCH_ELEM(m, CALL_ADJ);
+#undef CALL_ADJ
+  return 0;
+}
+
+long long adfem_coo_nslots(const adfem_mesh* m, int op) {
+  if (!m) return -1;
+  const HostMesh& h = m->hm;
+  const long long Dt = (op == ADFEM_OP_STIFFNESS ? h.dim : 1) * h.d;
+  if (op == ADFEM_OP_MASS && h.dim == 3) return (long long)h.ne * Dt * Dt;      // quirk Q5
+  return (long long)h.ne * h.g * Dt * Dt;
+}
+
+int adfem_coo_indices(adfem_mesh* m, int op, long long* indices, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
+  const int per_gauss = !(op == ADFEM_OP_MASS && m->hm.dim == 3);
+  const long long total = adfem_coo_nslots(m, op);
+  unsigned nb = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  k_coo_indices<<<std::max(1u, nb), 256, 0, (cudaStream_t)stream>>>(m->dm, nc, per_gauss, indices);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_assemble_coo(adfem_mesh* m, int op, const double* coef, double* vv, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const HostMesh& h = m->hm;
+  const long long G = (long long)h.ne * h.g;
+  if (op == ADFEM_OP_MASS && h.dim == 3) {
+    const long long n = (long long)h.ne * h.d;
+    if (h.degree == 1) k_coo_mass3_fwd<1><<<blocks_for(n, 128), 128, 0, st>>>(m->dm, coef, vv);
+    else k_coo_mass3_fwd<2><<<blocks_for(n, 128), 128, 0, st>>>(m->dm, coef, vv);
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
+#define CALL_COO(DIM, DEG)                                                                                   \
+  switch (op) {                                                                                              \
+    case ADFEM_OP_LAPLACE: k_coo_scalar_fwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break; \
+    case ADFEM_OP_MASS: k_coo_scalar_fwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break;       \
+    default: k_coo_stiff_fwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break;          \
+  }
+  DISPATCH_ELEM(m, CALL_COO);
+#undef CALL_COO
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, double* grad_coef, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const HostMesh& h = m->hm;
+  const long long G = (long long)h.ne * h.g;
+  if (op == ADFEM_OP_MASS && h.dim == 3) {
+    if (h.degree == 1) k_coo_mass3_bwd<1><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef);
+    else k_coo_mass3_bwd<2><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef);
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
+#define CALL_COOB(DIM, DEG)                                                                                  \
+  switch (op) {                                                                                              \
+    case ADFEM_OP_LAPLACE: k_coo_scalar_bwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break; \
+    case ADFEM_OP_MASS: k_coo_scalar_bwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break;       \
+    default: k_coo_stiff_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break; \
+  }
+  DISPATCH_ELEM(m, CALL_COOB);
+#undef CALL_COOB
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = ensure_pattern(m)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL_SRC(DIM, DEG) \
+  k_source_fwd<DIM, DEG><<<blocks_for(m->hm.ndof, 128), 128, 0, st>>>(m->dm, m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, f, rhs)
+  DISPATCH_ELEM(m, CALL_SRC);
+#undef CALL_SRC
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long G = (long long)m->hm.ne * m->hm.g;
+#define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_rhs, grad_f)
+  DISPATCH_ELEM(m, CALL_SRCB);
+#undef CALL_SRCB
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  const long long G = (long long)m->hm.ne * m->hm.g, nin = G * coef_per_gauss(m, op);
+  const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
+  const long long nout = adfem_csr_nnz(m, nc);
+  if (nout < 0) return 1;
+  if (m->s_in.n < (size_t)nin) CU_TRY(m->s_in.alloc(nin));
+  if (m->s_out.n < (size_t)nout) CU_TRY(m->s_out.alloc(nout));
+  CU_TRY(cudaMemcpyAsync(m->s_in.p, coef_host, nin * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (int rc = adfem_assemble_csr(m, op, m->s_in.p, m->s_out.p, nullptr)) return rc;
+  CU_TRY(cudaMemcpyAsync(vals_host, m->s_out.p, nout * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = check_op(m, op)) return rc;
+  const long long G = (long long)m->hm.ne * m->hm.g, nout = G * coef_per_gauss(m, op);
+  const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
+  const long long nin = adfem_csr_nnz(m, nc);
+  if (nin < 0) return 1;
+  if (m->s_out.n < (size_t)nin) CU_TRY(m->s_out.alloc(nin));
+  if (m->s_in.n < (size_t)nout) CU_TRY(m->s_in.alloc(nout));
+  CU_TRY(cudaMemcpyAsync(m->s_out.p, dvals_host, nin * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (int rc = adfem_assemble_csr_adjoint(m, op, m->s_out.p, m->s_in.p, nullptr)) return rc;
+  CU_TRY(cudaMemcpyAsync(grad_coef_host, m->s_in.p, nout * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return 0;
+}
+
+}  // extern "C"
+
+// ====================================================================================================
+// legacy symbols: global singletons + host pointers (deps/MFEM/API.cpp, deps/MFEM3/API.cpp and the
+// *_forward_Julia entry points).  `void` returns like the reference; failures print to stderr.
+// ====================================================================================================
+namespace {
+adfem_mesh* g_mesh2 = nullptr;
+adfem_mesh* g_mesh3 = nullptr;
+
+void legacy_fail(const char* where) { fprintf(stderr, "libadfem_cuda: %s failed: %s\n", where, adfem_last_error()); }
+
+long long* legacy_init(adfem_mesh*& slot, int dim, double* vertices, int nv, int* elems, int ne, int order, int lorder, int degree,
+                       long long* nedges) {
+  if (slot) { printf("WARNING: Internal mesh is being overwritten!\n"); adfem_mesh_destroy(slot); slot = nullptr; }   // API.cpp:6-10
+  if (adfem_mesh_create(&slot, dim, vertices, 3, nv, elems, ne, order, degree, lorder, 0)) { legacy_fail("init_nnfem_mesh"); return nullptr; }
+  *nedges = slot->hm.nedges;
+  long long* edges = (long long*)malloc(sizeof(long long) * 2 * (size_t)std::max<long long>(1, slot->hm.nedges));
+  adfem_mesh_edges(slot, edges);
+  return edges;
+}
+
+// host-pointer COO forward: indices + values
+void legacy_coo_fwd(adfem_mesh* m, int op, long long* indices, double* vv, const double* coef, const char* name) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long N = adfem_coo_nslots(m, op), nin = (long long)m->hm.ne * m->hm.g * coef_per_gauss(m, op);
+  DevBuf<double> dc, dv; DevBuf<long long> di;
+  bool ok = need_device(m) == 0 && dc.alloc(nin) == cudaSuccess && dv.alloc(N) == cudaSuccess &&
+            cudaMemcpy(dc.p, coef, nin * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+            adfem_assemble_coo(m, op, dc.p, dv.p, nullptr) == 0 &&
+            cudaMemcpy(vv, dv.p, N * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (ok && indices)
+    ok = di.alloc(2 * N) == cudaSuccess && adfem_coo_indices(m, op, di.p, nullptr) == 0 &&
+         cudaMemcpy(indices, di.p, 2 * N * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); }
+}
+void legacy_coo_bwd(adfem_mesh* m, int op, double* grad_coef, const double* grad_vv, const char* name) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long N = adfem_coo_nslots(m, op), nout = (long long)m->hm.ne * m->hm.g * coef_per_gauss(m, op);
+  DevBuf<double> dg, dv;
+  bool ok = need_device(m) == 0 && dg.alloc(nout) == cudaSuccess && dv.alloc(N) == cudaSuccess &&
+            cudaMemcpy(dv.p, grad_vv, N * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+            adfem_assemble_coo_adjoint(m, op, dv.p, dg.p, nullptr) == 0 &&
+            cudaMemcpy(grad_coef, dg.p, nout * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); }
+}
+void legacy_source_fwd(adfem_mesh* m, double* rhs, const double* f, const char* name) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long G = (long long)m->hm.ne * m->hm.g, n = m->hm.ndof;
+  DevBuf<double> df, dr;
+  std::vector<double> tmp(n);
+  bool ok = need_device(m) == 0 && df.alloc(G) == cudaSuccess && dr.alloc(n) == cudaSuccess &&
+            cudaMemcpy(df.p, f, G * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess && adfem_source(m, df.p, dr.p, nullptr) == 0 &&
+            cudaMemcpy(tmp.data(), dr.p, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); return; }
+  for (long long i = 0; i < n; i++) rhs[i] += tmp[i];      // the reference accumulates into a caller-zeroed rhs
+}
+void legacy_source_bwd(adfem_mesh* m, double* grad_f, const double* grad_rhs, const char* name) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long G = (long long)m->hm.ne * m->hm.g, n = m->hm.ndof;
+  DevBuf<double> df, dr;
+  bool ok = need_device(m) == 0 && df.alloc(G) == cudaSuccess && dr.alloc(n) == cudaSuccess &&
+            cudaMemcpy(dr.p, grad_rhs, n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+            adfem_source_adjoint(m, dr.p, df.p, nullptr) == 0 &&
+            cudaMemcpy(grad_f, df.p, G * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); }
+}
+void legacy_gauss(adfem_mesh* m, double** out) {
+  if (!m) return;
+  const size_t G = (size_t)m->hm.ne * m->hm.g;
+  std::vector<double> xyz(G * m->hm.dim);
+  m->hm.gauss_points(xyz.data());
+  for (int c = 0; c < m->hm.dim; c++) memcpy(out[c], xyz.data() + c * G, G * sizeof(double));
+}
+}  // namespace
+
+extern "C" {
+
+long long* init_nnfem_mesh(double* vertices, int num_vertices, int* element_indices, int num_elements, int order, int lorder,
+                           int degree, long long* nedges) {
+  if (degree == -1) { fprintf(stderr, "libadfem_cuda: BDM1 meshes (degree=-1) are outside the assembly path\n"); return nullptr; }
+  return legacy_init(g_mesh2, 2, vertices, num_vertices, element_indices, num_elements, order, lorder, degree, nedges);
+}
+int mfem_get_ngauss(void) { return g_mesh2 ? g_mesh2->hm.ne * g_mesh2->hm.g : 0; }
+void mfem_get_gauss(double* x, double* y) { double* o[2] = {x, y}; legacy_gauss(g_mesh2, o); }
+void mfem_get_gauss_weights(double* w) { if (g_mesh2) g_mesh2->hm.gauss_weights(w); }
+void mfem_get_area(double* a) { if (g_mesh2) g_mesh2->hm.measure(a); }
+int mfem_get_elem_ndof(void) { return g_mesh2 ? g_mesh2->hm.d : 0; }
+int mfem_get_ndof(void) { return g_mesh2 ? g_mesh2->hm.ndof : 0; }
+void mfem_get_connectivity(long long* conn) { if (g_mesh2) adfem_mesh_connectivity(g_mesh2, conn); }
+void mfem_get_element_to_vertices(long long* elems) { if (g_mesh2) adfem_mesh_element_to_vertices(g_mesh2, elems); }
+int get_LineIntegralN(void) { double p[64], w[64]; return segment_rule(g_mesh2 ? g_mesh2->hm.lorder : 6, p, w); }
+void get_LineIntegralPnW(double* p, double* w) { segment_rule(g_mesh2 ? g_mesh2->hm.lorder : 6, p, w); }
+
+long long* init_nnfem_mesh3(double* vertices, int num_vertices, int* element_indices, int num_elements, int order, int degree,
+                            long long* nedges) {
+  return legacy_init(g_mesh3, 3, vertices, num_vertices, element_indices, num_elements, order, -1, degree, nedges);
+}
+int mfem_get_ngauss3(void) { return g_mesh3 ? g_mesh3->hm.ne * g_mesh3->hm.g : 0; }
+void mfem_get_gauss3(double* x, double* y, double* z) { double* o[3] = {x, y, z}; legacy_gauss(g_mesh3, o); }
+void mfem_get_gauss_weights3(double* w) { if (g_mesh3) g_mesh3->hm.gauss_weights(w); }
+void mfem_get_volume3(double* v) { if (g_mesh3) g_mesh3->hm.measure(v); }
+int mfem_get_elem_ndof3(void) { return g_mesh3 ? g_mesh3->hm.d : 0; }
+int mfem_get_ndof3(void) { return g_mesh3 ? g_mesh3->hm.ndof : 0; }
+void mfem_get_connectivity3(long long* conn) { if (g_mesh3) adfem_mesh_connectivity(g_mesh3, conn); }
+void mfem_get_element_to_vertices3(long long* elems) { if (g_mesh3) adfem_mesh_element_to_vertices(g_mesh3, elems); }
+
+void FemLaplaceScalar_forward(long long* indices, double* vv, const double* kappa) { legacy_coo_fwd(g_mesh2, ADFEM_OP_LAPLACE, indices, vv, kappa, "FemLaplaceScalar_forward"); }
+void FemLaplaceScalar_forward_Julia(long long* indices, double* vv, const double* kappa) { FemLaplaceScalar_forward(indices, vv, kappa); }
+void FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv, const long long*, const double*, const double*) {
+  legacy_coo_bwd(g_mesh2, ADFEM_OP_LAPLACE, grad_kappa, grad_vv, "FemLaplaceScalar_backward");
+}
+void ComputeFemMassMatrix1_forward(long long* indices, double* vv, const double* rho) { legacy_coo_fwd(g_mesh2, ADFEM_OP_MASS, indices, vv, rho, "ComputeFemMassMatrix1_forward"); }
+void ComputeFemMassMatrix1_backward(double* grad_rho, const double* grad_vv, const double*, const double*) {
+  legacy_coo_bwd(g_mesh2, ADFEM_OP_MASS, grad_rho, grad_vv, "ComputeFemMassMatrix1_backward");
+}
+void ComputeFemStiffnessMatrixMfem_forward(long long* indices, double* vv, const double* hmat) {
+  legacy_coo_fwd(g_mesh2, ADFEM_OP_STIFFNESS, indices, vv, hmat, "ComputeFemStiffnessMatrixMfem_forward");
+}
+void ComputeFemStiffnessMatrixMfem_forward_Julia(long long* indices, double* vv, const double* hmat) { ComputeFemStiffnessMatrixMfem_forward(indices, vv, hmat); }
+void ComputeFemStiffnessMatrixMfem_backward(double* grad_hmat, const double* grad_vv) {
+  legacy_coo_bwd(g_mesh2, ADFEM_OP_STIFFNESS, grad_hmat, grad_vv, "ComputeFemStiffnessMatrixMfem_backward");
+}
+void FemSourceScalar_forward(double* rhs, const double* f) { legacy_source_fwd(g_mesh2, rhs, f, "FemSourceScalar_forward"); }
+void FemSourceScalar_forward_Julia(double* rhs, const double* f) { FemSourceScalar_forward(rhs, f); }
+void FemSourceScalar_backward(double* grad_f, const double* grad_rhs, const double*, const double*) { legacy_source_bwd(g_mesh2, grad_f, grad_rhs, "FemSourceScalar_backward"); }
+
+void FemLaplaceScalarT_forward(long long* indices, double* vv, const double* kappa) { legacy_coo_fwd(g_mesh3, ADFEM_OP_LAPLACE, indices, vv, kappa, "FemLaplaceScalarT_forward"); }
+void FemLaplaceScalarT_forward_Julia(long long* indices, double* vv, const double* kappa) { FemLaplaceScalarT_forward(indices, vv, kappa); }
+void FemLaplaceScalarT_backward(double* grad_kappa, const double* grad_vv, const long long*, const double*, const double*) {
+  legacy_coo_bwd(g_mesh3, ADFEM_OP_LAPLACE, grad_kappa, grad_vv, "FemLaplaceScalarT_backward");
+}
+void ComputeFemMassMatrixMfemT_forward(long long* indices, double* vv, const double* rho) { legacy_coo_fwd(g_mesh3, ADFEM_OP_MASS, indices, vv, rho, "ComputeFemMassMatrixMfemT_forward"); }
+void ComputeFemMassMatrixMfemT_backward(double* grad_rho, const double* grad_vv) { legacy_coo_bwd(g_mesh3, ADFEM_OP_MASS, grad_rho, grad_vv, "ComputeFemMassMatrixMfemT_backward"); }
+void FemSourceScalarT_forward(double* rhs, const double* f) { legacy_source_fwd(g_mesh3, rhs, f, "FemSourceScalarT_forward"); }
+void FemSourceScalarT_forward_Julia(double* rhs, const double* f) { FemSourceScalarT_forward(rhs, f); }
+void FemSourceScalarT_backward(double* grad_f, const double* grad_rhs, const double*, const double*) { legacy_source_bwd(g_mesh3, grad_f, grad_rhs, "FemSourceScalarT_backward"); }
+
+}  // extern "C"

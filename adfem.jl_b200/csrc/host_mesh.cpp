@@ -1,0 +1,144 @@
+#include "host_mesh.h"
+
+#include <cmath>
+
+namespace adfem {
+
+namespace {
+// local edges in MFEM geometry order (Geometry::Constants<TRIANGLE/TETRAHEDRON>::Edges)
+const int kTriEdges[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+const int kTetEdges[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+
+// Global edge ids in first-appearance order while walking elements 0..E-1 and their local edges in
+// geometry order — the numbering MFEM's GetElementToEdgeTable produces and the reference exposes
+// through `edges` and `dof[k+nv]` (deps/MFEM/Common.cpp:70-74,133-140).
+struct EdgeNumbering {
+  std::vector<int> head, next, hi, lo;
+  explicit EdgeNumbering(int nv) : head(nv, -1) {}
+  int id(int a, int b) {
+    int r = a <= b ? a : b, c = a <= b ? b : a;
+    for (int n = head[r]; n >= 0; n = next[n])
+      if (hi[n] == c) return n;
+    int i = (int)hi.size();
+    hi.push_back(c); lo.push_back(r); next.push_back(head[r]); head[r] = i;
+    return i;
+  }
+};
+}  // namespace
+
+std::string HostMesh::build(int dim_, const double* vertices, int vstride, int nv_, const int* elems, int ne_, int order_,
+                            int degree_, int lorder_) {
+  dim = dim_; nv = nv_; ne = ne_; order = order_; degree = degree_; lorder = lorder_;
+  if (dim != 2 && dim != 3) return "dim must be 2 or 3";
+  if (degree != 1 && degree != 2) return "degree must be equal to 1 or 2";   // deps/MFEM3/Common.cpp:52 (BDM1 is out of scope)
+  if (!(dim == 2 ? triangle_rule(order, rule) : tetrahedron_rule(order, rule))) return "unsupported quadrature order";
+  g = rule.n;
+  const int nvl = dim + 1, nel = dim == 2 ? 3 : 6;
+  d = degree == 1 ? nvl : nvl + nel;
+  coords.resize((size_t)nv * dim);
+  for (int i = 0; i < nv; i++)
+    for (int c = 0; c < dim; c++) coords[(size_t)i * dim + c] = vertices[(size_t)i * vstride + c];
+  verts.assign(elems, elems + (size_t)ne * nvl);
+  for (size_t i = 0; i < verts.size(); i++)
+    if (verts[i] < 0 || verts[i] >= nv) return "element vertex index out of range";
+  // orientation fix (quirk Q3)
+  for (int e = 0; e < ne; e++) {
+    int* vi = &verts[(size_t)e * nvl];
+    const double* X = coords.data();
+    double det;
+    if (dim == 2) {
+      const double *v0 = X + 2 * (size_t)vi[0], *v1 = X + 2 * (size_t)vi[1], *v2 = X + 2 * (size_t)vi[2];
+      det = (v1[0] - v0[0]) * (v2[1] - v0[1]) - (v1[1] - v0[1]) * (v2[0] - v0[0]);
+    } else {
+      const double *v0 = X + 3 * (size_t)vi[0], *v1 = X + 3 * (size_t)vi[1], *v2 = X + 3 * (size_t)vi[2], *v3 = X + 3 * (size_t)vi[3];
+      double a[3], b[3], c[3];
+      for (int k = 0; k < 3; k++) { a[k] = v1[k] - v0[k]; b[k] = v2[k] - v0[k]; c[k] = v3[k] - v0[k]; }
+      det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+    }
+    if (det < 0.0) { int t = vi[0]; vi[0] = vi[1]; vi[1] = t; }
+  }
+  // edges + connectivity
+  EdgeNumbering en(nv);
+  conn.resize((size_t)ne * d);
+  for (int e = 0; e < ne; e++) {
+    const int* vi = &verts[(size_t)e * nvl];
+    int* ce = &conn[(size_t)e * d];
+    for (int k = 0; k < nvl; k++) ce[k] = vi[k];
+    for (int j = 0; j < nel; j++) {
+      int a = dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0], b = dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1];
+      int id = en.id(vi[a], vi[b]);
+      if (degree == 2) ce[nvl + j] = nv + id;
+    }
+  }
+  nedges = (long long)en.hi.size();
+  edge_lo.swap(en.lo);
+  edge_hi.swap(en.hi);
+  long long nd = degree == 1 ? (long long)nv : (long long)nv + nedges;
+  if (nd > 2147483647LL) return "too many dofs for 32-bit dof ids";
+  ndof = (int)nd;
+  return "";
+}
+
+void HostMesh::dof_position(int dof, double* x) const {
+  if (dof < nv) {
+    for (int c = 0; c < dim; c++) x[c] = coords[(size_t)dof * dim + c];
+  } else {
+    int e = dof - nv;
+    for (int c = 0; c < dim; c++) x[c] = 0.5 * (coords[(size_t)edge_lo[e] * dim + c] + coords[(size_t)edge_hi[e] * dim + c]);
+  }
+}
+
+namespace {
+double tri_area_heron(const double* p1, const double* p2, const double* p3) {
+  double a = std::sqrt((p1[0] - p2[0]) * (p1[0] - p2[0]) + (p1[1] - p2[1]) * (p1[1] - p2[1]));
+  double b = std::sqrt((p3[0] - p2[0]) * (p3[0] - p2[0]) + (p3[1] - p2[1]) * (p3[1] - p2[1]));
+  double c = std::sqrt((p1[0] - p3[0]) * (p1[0] - p3[0]) + (p1[1] - p3[1]) * (p1[1] - p3[1]));
+  double s = (a + b + c) / 2.0;
+  return std::sqrt(s * (s - a) * (s - b) * (s - c));
+}
+double tet_volume(const double* v0, const double* v1, const double* v2, const double* v3) {
+  double J[3][3];
+  const double* V[3] = {v1, v2, v3};
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) J[r][c] = V[c][r] - v0[r];
+  double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  return det * (1. / 6.);
+}
+}  // namespace
+
+void HostMesh::measure(double* a) const {
+  const int nvl = dim + 1;
+  for (int e = 0; e < ne; e++) {
+    const int* vi = &verts[(size_t)e * nvl];
+    const double* X = coords.data();
+    a[e] = dim == 2 ? tri_area_heron(X + 2 * (size_t)vi[0], X + 2 * (size_t)vi[1], X + 2 * (size_t)vi[2])
+                    : tet_volume(X + 3 * (size_t)vi[0], X + 3 * (size_t)vi[1], X + 3 * (size_t)vi[2], X + 3 * (size_t)vi[3]);
+  }
+}
+
+void HostMesh::gauss_weights(double* w) const {
+  std::vector<double> a(ne);
+  measure(a.data());
+  for (int e = 0; e < ne; e++)
+    for (int k = 0; k < g; k++) w[(size_t)e * g + k] = dim == 2 ? rule.w[k] * a[e] / 0.5 : rule.w[k] * a[e] * 6.0;
+}
+
+void HostMesh::gauss_points(double* xyz) const {
+  const int nvl = dim + 1;
+  const size_t G = (size_t)ne * g;
+  for (int e = 0; e < ne; e++) {
+    const int* vi = &verts[(size_t)e * nvl];
+    for (int k = 0; k < g; k++) {
+      double L[4];
+      if (dim == 2) { L[0] = 1 - rule.x[k] - rule.y[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; }
+      else { L[0] = 1 - rule.x[k] - rule.y[k] - rule.z[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; L[3] = rule.z[k]; }
+      for (int c = 0; c < dim; c++) {
+        double s = 0;
+        for (int j = 0; j < nvl; j++) s += coords[(size_t)vi[j] * dim + c] * L[j];
+        xyz[c * G + (size_t)e * g + k] = s;
+      }
+    }
+  }
+}
+
+}  // namespace adfem

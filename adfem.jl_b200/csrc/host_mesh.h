@@ -1,0 +1,42 @@
+// Mesh-static host tables: what the reference builds in NNFEM_Mesh::init (deps/MFEM/Common.cpp:20-142)
+// and NNFEM_Mesh3::init (deps/MFEM3/Common.cpp:9-148), kept as flat arrays instead of one heap object
+// per element.  Everything here is computed once per mesh; the per-Gauss-point shape tables (h, hx, hy,
+// w) are NOT stored — the kernels recompute them from the vertex coordinates.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "quadrature.h"
+
+namespace adfem {
+
+struct HostMesh {
+  int dim = 0;          // 2 (triangles) or 3 (tetrahedra)
+  int nv = 0;           // vertices
+  int ne = 0;           // elements
+  int order = 0, degree = 0, lorder = 0;
+  int d = 0;            // dofs per element: 3/6 (tri P1/P2), 4/10 (tet P1/P2)
+  int g = 0;            // Gauss points per element
+  int ndof = 0;         // nv (P1) or nv + nedges (P2)
+  long long nedges = 0;
+  QuadRule rule;
+  std::vector<double> coords;     // nv x dim, packed
+  std::vector<int> verts;         // ne x (dim+1) after the orientation fix (det<0 => swap local 0,1)
+  std::vector<int> conn;          // ne x d, 0-based dofs: vertices then (P2) nv + edge id, geometry edge order
+  std::vector<int> edge_lo, edge_hi;   // edge i joins edge_lo[i] < edge_hi[i] (first-appearance numbering)
+
+  // builds all tables; returns "" or an error message
+  std::string build(int dim, const double* vertices, int vstride, int nv, const int* elems, int ne, int order,
+                    int degree, int lorder);
+
+  // physical position of a dof (vertex, or edge midpoint for P2 edge dofs)
+  void dof_position(int dof, double* x) const;
+
+  // setup-time getters (host arithmetic, same formulas as the kernels)
+  void gauss_points(double* xyz) const;     // dim blocks of ne*g values (column-major), deps/MFEM/Common.cpp:110-111
+  void gauss_weights(double* w) const;      // element-major, deps/MFEM/API.cpp:26-34
+  void measure(double* a) const;            // Heron area (Common.cpp:9-15) or tet volume (MFEM3/Common.cpp:88)
+};
+
+}  // namespace adfem

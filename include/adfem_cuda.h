@@ -1,0 +1,153 @@
+/* libadfem_cuda.so — C ABI of the B200-native differentiable FEM assembly path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) LEGACY symbols: byte-for-byte the signatures the reference's Julia side binds with `ccall`
+ *      (and the TF op shells call) for this path.  Host pointers in, host pointers out, one global
+ *      2-D mesh and one global 3-D mesh per process (reference quirk Q10), `void` returns.  They are
+ *      thin wrappers that copy to/from the device around the kernels of group (2).
+ *
+ *  (2) HANDLE API (`adfem_*`): mesh handles, the mesh-static symbolic phase, and device-pointer
+ *      assembly / adjoint calls on a caller-supplied CUDA stream.  Every function returns 0 on
+ *      success and a non-zero code otherwise; `adfem_last_error()` gives the message.
+ *
+ * There is no CPU fallback: every compute entry point fails (non-zero / error message) when no CUDA
+ * device is usable.  Index conventions are the reference's own and are stated per function.
+ *
+ * Reference paths below are relative to the kailaix/AdFem.jl checkout.
+ */
+#ifndef ADFEM_CUDA_H
+#define ADFEM_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================ (1) legacy symbols ============================================== */
+
+/* deps/MFEM/API.cpp:4-14.  vertices: 3*nv xyz-interleaved (z ignored); element_indices: 3*ne, 0-based.
+ * Returns malloc'ed edges[2*nedges] (edges[i] = min vertex + 1, edges[nedges+i] = max vertex + 1);
+ * the CALLER frees it (Julia: unsafe_wrap(..., own=true), src/MFEM/MFEM.jl:99).  degree -1 (BDM1) is
+ * out of scope and returns NULL. */
+long long* init_nnfem_mesh(double* vertices, int num_vertices, int* element_indices, int num_elements,
+                           int order, int lorder, int degree, long long* nedges);
+int  mfem_get_ngauss(void);                                  /* API.cpp:17-19 */
+void mfem_get_gauss(double* x, double* y);                   /* API.cpp:21-24 */
+void mfem_get_gauss_weights(double* w);                      /* API.cpp:26-34, element-major */
+void mfem_get_area(double* a);                               /* API.cpp:36-39 (Heron) */
+int  mfem_get_elem_ndof(void);                               /* API.cpp:41-43 */
+int  mfem_get_ndof(void);                                    /* API.cpp:45-47 */
+void mfem_get_connectivity(long long* conn);                 /* API.cpp:49-56, ne*d row-major, 1-based */
+void mfem_get_element_to_vertices(long long* elems);         /* API.cpp:58-65, column-major, 1-based */
+int  get_LineIntegralN(void);                                /* deps/MFEM/Common.cpp:350-352 */
+void get_LineIntegralPnW(double* p, double* w);              /* deps/MFEM/Common.cpp:354-362 */
+
+/* deps/MFEM3/API.cpp:4-67.  vertices: 3*nv; element_indices: 4*ne, 0-based. */
+long long* init_nnfem_mesh3(double* vertices, int num_vertices, int* element_indices, int num_elements,
+                            int order, int degree, long long* nedges);
+int  mfem_get_ngauss3(void);
+void mfem_get_gauss3(double* x, double* y, double* z);
+void mfem_get_gauss_weights3(double* w);
+void mfem_get_volume3(double* v);
+int  mfem_get_elem_ndof3(void);
+int  mfem_get_ndof3(void);
+void mfem_get_connectivity3(long long* conn);
+void mfem_get_element_to_vertices3(long long* elems);
+
+/* Eager op entry points (host pointers).  indices: 2*N interleaved (row, col), 0-based int64. */
+void FemLaplaceScalar_forward_Julia(long long* indices, double* vv, const double* kappa);      /* deps/MFEM/FemLaplace1/FemLaplaceScalar.h:59-61 */
+void FemSourceScalar_forward_Julia(double* rhs, const double* f);                              /* deps/MFEM/FemSource1/FemSourceScalar.h:35-37 (adds into rhs) */
+void ComputeFemStiffnessMatrixMfem_forward_Julia(long long* indices, double* vv, const double* hmat); /* deps/MFEM/ComputeFemStiffnessMatrixMfem/ComputeFemStiffnessMatrixMfem.h:84-88 */
+void FemLaplaceScalarT_forward_Julia(long long* indices, double* vv, const double* kappa);     /* deps/MFEM3/FemLaplace1/FemLaplaceScalarT.h:61-63 */
+void FemSourceScalarT_forward_Julia(double* rhs, const double* f);                             /* deps/MFEM3/FemSource/FemSourceScalarT.h:35-37 */
+
+/* The bodies the TF op shells call (namespace MFEM in the reference), exported with C linkage so a
+ * rebuilt op shell can link them.  Host pointers; same argument order as the reference functions. */
+void FemLaplaceScalar_forward(long long* indices, double* vv, const double* kappa);            /* FemLaplaceScalar.h:3-26 */
+void FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv, const long long* indices,
+                               const double* vv, const double* kappa);                        /* FemLaplaceScalar.h:28-54 */
+void ComputeFemMassMatrix1_forward(long long* indices, double* vv, const double* rho);         /* deps/MFEM/ComputeFemMassMatrix1/ComputeFemMassMatrixMfem.h:4-29 */
+void ComputeFemMassMatrix1_backward(double* grad_rho, const double* grad_vv, const double* vv,
+                                    const double* rho);                                       /* ComputeFemMassMatrixMfem.h:31-56 (overwrites grad_rho) */
+void ComputeFemStiffnessMatrixMfem_forward(long long* indices, double* vv, const double* hmat);/* ComputeFemStiffnessMatrixMfem.h:4-48 */
+void ComputeFemStiffnessMatrixMfem_backward(double* grad_hmat, const double* grad_vv);         /* ComputeFemStiffnessMatrixMfem.h:50-81 */
+void FemSourceScalar_forward(double* rhs, const double* f);                                    /* FemSourceScalar.h:4-15 (adds into rhs) */
+void FemSourceScalar_backward(double* grad_f, const double* grad_rhs, const double* rhs,
+                              const double* f);                                               /* FemSourceScalar.h:17-32 */
+void FemLaplaceScalarT_forward(long long* indices, double* vv, const double* kappa);           /* FemLaplaceScalarT.h:3-27 */
+void FemLaplaceScalarT_backward(double* grad_kappa, const double* grad_vv, const long long* indices,
+                                const double* vv, const double* kappa);                       /* FemLaplaceScalarT.h:29-56 */
+void ComputeFemMassMatrixMfemT_forward(long long* indices, double* vv, const double* rho);     /* deps/MFEM3/ComputeFemMassMatrixMfem3/ComputeFemMassMatrixMfemT.h:4-27, N = ne*d*d */
+void ComputeFemMassMatrixMfemT_backward(double* grad_rho, const double* grad_vv);              /* extension: the reference's Grad body is empty (…T.cpp:136-140) */
+void FemSourceScalarT_forward(double* rhs, const double* f);                                   /* FemSourceScalarT.h:4-15 */
+void FemSourceScalarT_backward(double* grad_f, const double* grad_rhs, const double* rhs,
+                               const double* f);                                              /* FemSourceScalarT.h:17-32 */
+
+/* ============================ (2) handle API ================================================= */
+typedef struct adfem_mesh adfem_mesh;
+
+const char* adfem_last_error(void);
+int adfem_device_count(void);          /* 0 when no usable CUDA device (never a fallback) */
+
+enum { ADFEM_HOST_ONLY = 1 };          /* flags: build host tables/plans only (inspection, CPU unit tests) */
+enum { ADFEM_OP_LAPLACE = 0, ADFEM_OP_MASS = 1, ADFEM_OP_STIFFNESS = 2 };
+enum { ADFEM_INFO_DIM = 0, ADFEM_INFO_NV, ADFEM_INFO_NE, ADFEM_INFO_NDOF, ADFEM_INFO_NGAUSS, ADFEM_INFO_ELEM_NDOF,
+       ADFEM_INFO_NEDGES, ADFEM_INFO_GAUSS_PER_ELEM, ADFEM_INFO_NNZ_SCALAR, ADFEM_INFO_TILES_FWD, ADFEM_INFO_TILES_ADJ,
+       ADFEM_INFO_PLAN_BYTES };
+
+/* Replaces init_nnfem_mesh / init_nnfem_mesh3 (deps/MFEM/API.cpp:4, deps/MFEM3/API.cpp:4) without the
+ * process-global singleton.  dim = 2|3; vertices: nv rows of `vertex_stride` doubles (first `dim` used);
+ * elems: ne*(dim+1), 0-based; degree 1|2; order/lorder as in the reference (-1 = reference defaults,
+ * src/MFEM/MFEM.jl:71-85, src/MFEM3/MFEM.jl:49-55). */
+int  adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int vertex_stride, int nv,
+                       const int* elems, int ne, int order, int degree, int lorder, int flags);
+void adfem_mesh_destroy(adfem_mesh* m);
+long long adfem_mesh_info(const adfem_mesh* m, int what);
+int adfem_mesh_edges(const adfem_mesh* m, long long* edges);                  /* 2*nedges, layout of init_nnfem_mesh */
+int adfem_mesh_connectivity(const adfem_mesh* m, long long* conn);            /* as mfem_get_connectivity */
+int adfem_mesh_element_to_vertices(const adfem_mesh* m, long long* elems);    /* as mfem_get_element_to_vertices */
+int adfem_mesh_gauss(const adfem_mesh* m, double* xyz);                       /* dim blocks of ngauss (column-major) */
+int adfem_mesh_gauss_weights(const adfem_mesh* m, double* w);
+int adfem_mesh_measure(const adfem_mesh* m, double* a);                       /* Heron area (2-D) / volume (3-D) */
+int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads" */
+
+/* Mesh-static symbolic phase (what Julia's sparse() / TF's sparse ops redo on every call downstream of the
+ * reference's COO, src/MFEM/MCore.jl:118-119).  ncomp = 1: scalar operators, n = ndof.  ncomp = dim: the
+ * elasticity operator, n = dim*ndof with component-blocked dofs (ComputeFemStiffnessMatrixMfem.h:31-34). */
+int adfem_symbolic(adfem_mesh* m);
+long long adfem_csr_nnz(adfem_mesh* m, int ncomp);
+int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr /* n+1 */, int* colind /* nnz */);   /* host out, 0-based */
+int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz /* ne*d*d, host out */);
+
+/* Inspection of the mesh-static tile plans (ADFEM_HOST_ONLY handles only; used by the CPU unit tests that
+ * replay a plan against the oracle).  which_plan 0 = forward row tiles {0 row_ptr:int32, 1 rows:int32,
+ * 2 elem_ptr:int32, 3 elems:int32, 4 soff_ptr:int64, 5 src_off:uint16, 6 src_ptr:int64, 7 src:uint16},
+ * 1 = adjoint element tiles {0 elem_ptr, 1 elems, 2 row_ptr, 3 rows: int32, 4 gidx_ptr:int64, 5 gidx:uint16}.
+ * Returns the element count (and copies when out != NULL), -1 on error. */
+long long adfem_plan_array(adfem_mesh* m, int which_plan, int ncomp, int array_id, void* out);
+
+/* CSR-mode assembly: coef and vals are DEVICE pointers, stream is a cudaStream_t.
+ * op LAPLACE/MASS: coef[ngauss]; STIFFNESS: coef[ngauss*ns*ns], ns = 3 (2-D) | 6 (3-D Voigt xx,yy,zz,yz,xz,xy).
+ * vals[nnz] in the order of adfem_csr_pattern: the canonical CSR of the reference op's COO output. */
+int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, void* stream);
+/* reverse mode: dvals[nnz] = d loss / d vals  ->  grad_coef (same shape as coef) */
+int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, double* grad_coef, void* stream);
+
+/* COO-compatible mode: exactly the reference ops' outputs (N = ngauss*D*D slots; 3-D mass: ne*d*d). */
+long long adfem_coo_nslots(const adfem_mesh* m, int op);
+int adfem_coo_indices(adfem_mesh* m, int op, long long* indices /* device, 2*N */, void* stream);
+int adfem_assemble_coo(adfem_mesh* m, int op, const double* coef, double* vv, void* stream);
+int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, double* grad_coef, void* stream);
+
+/* Source term (FemSourceScalar*): rhs[ndof] is OVERWRITTEN (no pre-zeroing needed). */
+int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream);
+int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, void* stream);
+
+/* Host-buffer convenience calls (synchronous; H2D + kernel + D2H).  Used for end-to-end timing. */
+int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host);
+int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,170 @@
+"""CPU tests of the product's host logic (no GPU): mesh tables, the symbolic CSR pattern and a replay of the
+forward / adjoint tile plans against the oracle.  The replay executes exactly the index arithmetic the CUDA
+kernels k_tile_fwd / k_tile_adj perform, with the oracle supplying the per-element local matrices."""
+import numpy as np
+import pytest
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import meshgen
+
+
+def _meshes():
+    out = {}
+    out["tri_struct"] = (2, *meshgen.tri_grid(7, 5, 0.25))
+    out["tri_unstruct"] = (2, *meshgen.jitter_unstructured(9, 8, 0.1, seed=3))
+    out["tet"] = (3, *meshgen.tet_grid(3, 3, 2, 0.5))
+    return out
+
+
+MESHES = _meshes()
+CASES = [(name, deg) for name in MESHES for deg in (1, 2)]
+
+
+def make(name, degree, oracle):
+    dim, c, e = MESHES[name]
+    if dim == 2:
+        return A.Mesh(c, e, degree=degree, host_only=True), oracle.Mesh2D(c, e, degree=degree)
+    return A.Mesh3(c, e, degree=degree, host_only=True), oracle.Mesh3D(c, e, degree=degree)
+
+
+@pytest.mark.parametrize("name,degree", CASES)
+def test_mesh_tables_match_oracle(oracle, name, degree):
+    m, o = make(name, degree, oracle)
+    assert (m.nnode, m.nelem, m.nedge, m.ndof, m.ngauss, m.elem_ndof) == (o.nnode, o.nelem, o.nedge, o.ndof, o.ngauss, o.elem_ndof)
+    assert np.array_equal(m.elems, o.elems)          # orientation fix
+    assert np.array_equal(m.edges, o.edges)          # first-appearance edge numbering
+    assert np.array_equal(m.conn, o.conn)
+    assert np.array_equal(A.gauss_nodes(m), o.gauss)
+    assert np.allclose(A.gauss_weights(m), o.weights, rtol=1e-15, atol=0)
+    assert np.allclose(A.get_area(m), o.area if m.dim == 2 else o.volume, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("name,degree", CASES)
+def test_csr_pattern_bit_exact(oracle, name, degree):
+    m, o = make(name, degree, oracle)
+    ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+    rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
+    rowptr, colind = m.csr_pattern(1)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+    # slot -> nnz map: the Gauss-point-0 block of every element lists its (row, col) pairs
+    g, dd = o.g, o.elem_ndof ** 2
+    s2n = m.slot_to_nnz().reshape(o.nelem, dd)
+    blk = ind.reshape(o.nelem, g, dd, 2)[:, 0]
+    rows_of_nnz = np.repeat(np.arange(o.ndof), np.diff(rp))
+    assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
+    # elasticity pattern (component-blocked dofs)
+    if degree == 1 or m.dim == 2:
+        ns = 3 if m.dim == 2 else 6
+        ind_e, vv_e = o.stiffness_fwd(np.tile(np.eye(ns).reshape(-1), o.ngauss))
+        rp_e, ci_e, _ = oracle.canonical_csr(ind_e, vv_e, m.dim * o.ndof)
+        rowptr_e, colind_e = m.csr_pattern(m.dim)
+        assert np.array_equal(rowptr_e, rp_e) and np.array_equal(colind_e, ci_e)
+
+
+def _fwd_replay(m, local, ncomp, n_out):
+    """local: [nelem, Dt*Dt] pre-summed local matrices. Mirrors k_tile_fwd."""
+    d = m.elem_ndof
+    dd, Dt = d * d, ncomp * d
+    rowptr, _ = m.csr_pattern(1)
+    nnz_s = rowptr[-1]
+    row_ptr = m.plan_array(0, ncomp, 0, np.int32); rows = m.plan_array(0, ncomp, 1, np.int32)
+    elem_ptr = m.plan_array(0, ncomp, 2, np.int32); elems = m.plan_array(0, ncomp, 3, np.int32)
+    soff_ptr = m.plan_array(0, ncomp, 4, np.int64); src_off = m.plan_array(0, ncomp, 5, np.uint16)
+    src_ptr = m.plan_array(0, ncomp, 6, np.int64); src = m.plan_array(0, ncomp, 7, np.uint16)
+    vals = np.full(n_out, np.nan)
+    written = np.zeros(n_out, dtype=np.int32)
+    for t in range(len(row_ptr) - 1):
+        trows = rows[row_ptr[t]:row_ptr[t + 1]]
+        tel = elems[elem_ptr[t]:elem_ptr[t + 1]]
+        loc = local[tel]                                      # [nel, S]
+        so = src_off[soff_ptr[t]:soff_ptr[t + 1]].astype(np.int64)
+        sr = src[src_ptr[t]:src_ptr[t + 1]].astype(np.int64)
+        i = 0
+        for r in trows:
+            rs, ln = rowptr[r], rowptr[r + 1] - rowptr[r]
+            for j in range(ln):
+                cs = sr[so[i]:so[i + 1]]
+                le, pq = cs // dd, cs % dd
+                p, q = pq // d, pq % d
+                for a in range(ncomp):
+                    for b in range(ncomp):
+                        v = 0.0
+                        for k in range(len(cs)):
+                            v += loc[le[k], ((a * d + p[k]) * Dt + b * d + q[k])]
+                        dest = ncomp * (a * nnz_s + rs) + b * ln + j
+                        vals[dest] = v
+                        written[dest] += 1
+                i += 1
+        assert i == len(so) - 1
+    assert (written == 1).all()                                # every CSR entry is produced exactly once
+    return vals
+
+
+def _close(a, b, rel=1e-12):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.all(np.abs(a - b) <= rel * np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3))
+
+
+@pytest.mark.parametrize("name,degree", CASES)
+def test_forward_plan_replay_scalar(oracle, name, degree):
+    m, o = make(name, degree, oracle)
+    m.set_option("rows_per_tile", 24)                          # several tiles even on these small meshes
+    rng = np.random.default_rng(0)
+    kappa = rng.random(o.ngauss) + 0.5
+    ind, vv = o.laplace_fwd(kappa)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+    dd = o.elem_ndof ** 2
+    local = vv.reshape(o.nelem, o.g, dd).sum(1)
+    vals = _fwd_replay(m, local, 1, len(ref))
+    assert _close(vals, ref)
+
+
+@pytest.mark.parametrize("name,degree", [("tri_unstruct", 1), ("tri_struct", 2), ("tet", 1)])
+def test_forward_plan_replay_elasticity(oracle, name, degree):
+    m, o = make(name, degree, oracle)
+    m.set_option("rows_per_tile", 16)
+    rng = np.random.default_rng(1)
+    ns = 3 if m.dim == 2 else 6
+    H = rng.random(o.ngauss * ns * ns)
+    ind, vv = o.stiffness_fwd(H)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, m.dim * o.ndof)
+    Dt = m.dim * o.elem_ndof
+    local = vv.reshape(o.nelem, o.g, Dt * Dt).sum(1)
+    vals = _fwd_replay(m, local, m.dim, len(ref))
+    assert _close(vals, ref)
+
+
+@pytest.mark.parametrize("name,degree", CASES)
+def test_adjoint_plan_replay(oracle, name, degree):
+    """Mirrors k_tile_adj: staged row segments + gidx must deliver dvals[slot_nnz[e,p,q]] to every owned element."""
+    m, o = make(name, degree, oracle)
+    m.set_option("elems_per_tile", 20)
+    d = o.elem_ndof
+    dd = d * d
+    rowptr, _ = m.csr_pattern(1)
+    s2n = m.slot_to_nnz().reshape(o.nelem, dd)
+    dvals = np.random.default_rng(2).standard_normal(rowptr[-1])
+    elem_ptr = m.plan_array(1, 1, 0, np.int32); elems = m.plan_array(1, 1, 1, np.int32)
+    row_ptr = m.plan_array(1, 1, 2, np.int32); rows = m.plan_array(1, 1, 3, np.int32)
+    gidx_ptr = m.plan_array(1, 1, 4, np.int64); gidx = m.plan_array(1, 1, 5, np.uint16)
+    seen = np.zeros(o.nelem, dtype=np.int32)
+    for t in range(len(elem_ptr) - 1):
+        trows = rows[row_ptr[t]:row_ptr[t + 1]]
+        staged = np.concatenate([dvals[rowptr[r]:rowptr[r + 1]] for r in trows])
+        tel = elems[elem_ptr[t]:elem_ptr[t + 1]]
+        gi = gidx[gidx_ptr[t]:gidx_ptr[t + 1]].reshape(len(tel), dd)
+        assert np.array_equal(staged[gi], dvals[s2n[tel]])
+        seen[tel] += 1
+    assert (seen == 1).all()
+
+
+def test_product_has_no_cpu_compute_path():
+    """A host-only handle (and any box without CUDA) must refuse to compute: no CPU fallback."""
+    import ctypes as C
+    m = A.Mesh(3, 3, 0.5, host_only=True)
+    L = A._lib.lib()
+    rc = L.adfem_assemble_csr(m.handle, 0, None, None, None)
+    assert rc != 0 and "no CPU fallback" in A._lib.last_error()
+    if L.adfem_device_count() == 0:
+        with pytest.raises(A._lib.AdfemError):
+            A.Mesh(3, 3, 0.5)
