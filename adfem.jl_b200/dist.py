@@ -1,0 +1,228 @@
+"""Multi-GPU assembly: element-block partition + interface-row exchange (one process per GPU).
+
+The reference has no parallelism at all; this is the new §8(e) design:
+
+  * each rank holds a contiguous block of ELEMENTS and a local mesh over the dofs they touch (local ids keep
+    the global order), so the coefficient arrays (`kappa`, `H`, `rho`, `f`: element-major, e*g+k) split with the
+    elements at zero cost and the assembly / adjoint kernels run unchanged and rank-local;
+  * a dof row touched by several ranks is OWNED by the lowest such rank.  Forward: a rank packs the CSR row
+    segments of the rows it does not own and one `all_to_all_single` (NCCL over NVLink) delivers them to the
+    owners, which add them into their rows — entries whose column the owner already has are summed in place,
+    entries with a ghost column form a small off-process block (`ghost_*`, like PETSc's MPIAIJ off-diagonal part);
+  * adjoint: the same lists run backwards (`replicate_interface`) so every rank sees d loss / d K for all entries
+    its own elements contributed to; the element-level adjoint then needs no reduction.
+
+Setup (numpy + one collective of index lists) is mesh-static.  The per-step exchange works on any
+`torch.distributed` backend: NCCL on the GPUs, gloo in the CPU unit tests (which inject oracle values).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import meshgen
+from .mesh import Mesh, Mesh3, bcedge, get_edge_dof
+
+
+def _boundary_faces(elems):
+    f = np.concatenate([elems[:, [0, 1, 2]], elems[:, [0, 1, 3]], elems[:, [0, 2, 3]], elems[:, [1, 2, 3]]], 0)
+    f = np.sort(f, 1)
+    u, cnt = np.unique(f, axis=0, return_counts=True)
+    return u[cnt == 1]
+
+
+class Partition:
+    """One rank's share of a distributed mesh.
+
+    coords/elems: the rank's own elements in LOCAL vertex numbering; gvid[i] = global id of local vertex i
+    (ascending); nv_global = number of global vertices.  `mesh_kwargs` go to Mesh/Mesh3 (degree, order, host_only)."""
+
+    def __init__(self, coords, elems, gvid, nv_global, rank, world, group=None, device=None, **mesh_kwargs):
+        self.rank, self.world, self.group = rank, world, group
+        dim = coords.shape[1]
+        self.mesh = (Mesh if dim == 2 else Mesh3)(coords, elems, **mesh_kwargs)
+        m = self.mesh
+        self.device = device if device is not None else (torch.device("cpu") if m.host_only else torch.device("cuda", torch.cuda.current_device()))
+        gvid = np.asarray(gvid, dtype=np.int64)
+        # globally consistent dof ids: vertices keep their global id; a P2 edge dof is keyed by its global end points
+        gid = np.empty(m.ndof, dtype=np.int64)
+        gid[:m.nnode] = gvid
+        if m.ndof > m.nnode:
+            lo, hi = gvid[m.edges[:, 0]], gvid[m.edges[:, 1]]
+            gid[m.nnode:] = nv_global + np.minimum(lo, hi) * np.int64(nv_global) + np.maximum(lo, hi)
+        self.gid = gid
+        self._gid_order = np.argsort(gid, kind="stable")
+        self._gid_sorted = gid[self._gid_order]
+        # dofs that can be shared: those on facets of the block boundary
+        if dim == 2:
+            bd = bcedge(m)
+            cand = np.unique(bd.reshape(-1))
+            if m.ndof > m.nnode:
+                cand = np.concatenate([cand, np.unique(get_edge_dof(bd, m)) + m.nnode])
+        else:
+            bf = _boundary_faces(m.elems)
+            cand = np.unique(bf.reshape(-1))
+            if m.ndof > m.nnode:
+                be = np.concatenate([bf[:, [0, 1]], bf[:, [0, 2]], bf[:, [1, 2]]], 0)
+                cand = np.concatenate([cand, np.unique(get_edge_dof(be, m)) + m.nnode])
+        cand_gid = np.sort(gid[cand])
+        all_cand = self._all_gather(cand_gid)
+        # owner of every local dof = lowest rank that has it
+        owner = np.full(m.ndof, rank, dtype=np.int64)
+        shared_with = {}
+        for q in range(world):
+            if q == rank or len(all_cand[q]) == 0:
+                continue
+            common = np.intersect1d(cand_gid, all_cand[q], assume_unique=True)
+            if len(common) == 0:
+                continue
+            loc = self.local_of_gid(common)
+            shared_with[q] = loc
+            owner[loc] = np.minimum(owner[loc], q)
+        self.owner = owner
+        self.owned = owner == rank
+        rowptr, colind = m.csr_pattern(1)
+        self.rowptr, self.colind = rowptr, colind
+        # ---- forward send lists: every entry of a row I do not own goes to its owner
+        send_pos, send_keys = [], []
+        for q in range(world):
+            rows = np.flatnonzero(owner == q) if q != rank else np.zeros(0, dtype=np.int64)
+            if len(rows):
+                lens = rowptr[rows + 1] - rowptr[rows]
+                pos = np.repeat(rowptr[rows] - np.cumsum(np.r_[0, lens[:-1]]), lens) + np.arange(lens.sum())
+                keys = np.stack([gid[np.repeat(rows, lens)], gid[colind[pos]]], 1)
+            else:
+                pos, keys = np.zeros(0, dtype=np.int64), np.zeros((0, 2), dtype=np.int64)
+            send_pos.append(pos)
+            send_keys.append(keys.reshape(-1))
+        self.send_counts = [len(p) for p in send_pos]
+        self.send_pos = torch.from_numpy(np.concatenate(send_pos)).to(self.device)
+        recv_keys = self._all_to_all([k for k in send_keys])
+        self.recv_counts = [len(k) // 2 for k in recv_keys]
+        rk = np.concatenate(recv_keys).reshape(-1, 2) if sum(self.recv_counts) else np.zeros((0, 2), dtype=np.int64)
+        # match received (global row, global col) against my local pattern
+        lrow = self.local_of_gid(rk[:, 0])
+        assert (lrow >= 0).all() and self.owned[lrow].all(), "received a row this rank does not own"
+        lcol = self.local_of_gid(rk[:, 1], missing_ok=True)
+        pos = np.full(len(rk), -1, dtype=np.int64)
+        have = lcol >= 0
+        if have.any():
+            urows = np.unique(lrow[have])
+            lens = rowptr[urows + 1] - rowptr[urows]
+            ent = np.repeat(rowptr[urows] - np.cumsum(np.r_[0, lens[:-1]]), lens) + np.arange(lens.sum())
+            key_have = np.repeat(urows, lens) * np.int64(m.ndof) + colind[ent]          # ascending (rows asc, cols asc)
+            q_keys = lrow[have] * np.int64(m.ndof) + lcol[have]
+            at = np.searchsorted(key_have, q_keys)
+            at = np.minimum(at, len(key_have) - 1)
+            hit = key_have[at] == q_keys
+            ph = np.full(have.sum(), -1, dtype=np.int64)
+            ph[hit] = ent[at[hit]]
+            pos[have] = ph
+        matched = pos >= 0
+        self.recv_match_idx = torch.from_numpy(np.flatnonzero(matched)).to(self.device)
+        self.recv_match_pos = torch.from_numpy(pos[matched]).to(self.device)
+        self.ghost_idx = torch.from_numpy(np.flatnonzero(~matched)).to(self.device)
+        self.ghost_rows = lrow[~matched]                       # local row ids (owned)
+        self.ghost_gcols = rk[~matched, 1]                     # global column ids
+        self.ghost_vals = torch.zeros(int((~matched).sum()), dtype=torch.float64, device=self.device)
+        self.interface_bytes = 8 * (sum(self.send_counts) + sum(self.recv_counts))
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def local_of_gid(self, g, missing_ok=False):
+        at = np.searchsorted(self._gid_sorted, g)
+        at = np.minimum(at, len(self._gid_sorted) - 1)
+        ok = self._gid_sorted[at] == g
+        out = np.where(ok, self._gid_order[at], -1)
+        if not missing_ok:
+            assert ok.all()
+        return out
+
+    def _all_gather(self, arr):
+        """all_gather of variable-length int64 arrays."""
+        if self.world == 1:
+            return [arr]
+        n = torch.tensor([len(arr)], dtype=torch.int64, device=self.device)
+        ns = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(ns, n, group=self.group)
+        mx = max(int(x.item()) for x in ns)
+        buf = torch.zeros(max(mx, 1), dtype=torch.int64, device=self.device)
+        buf[:len(arr)] = torch.from_numpy(arr).to(self.device)
+        bufs = [torch.zeros_like(buf) for _ in range(self.world)]
+        dist.all_gather(bufs, buf, group=self.group)
+        return [b[:int(k.item())].cpu().numpy() for b, k in zip(bufs, ns)]
+
+    def _all_to_all(self, arrs):
+        """all_to_all of variable-length int64 arrays (setup only)."""
+        if self.world == 1:
+            return [arrs[0]]
+        cnt = torch.tensor([len(a) for a in arrs], dtype=torch.int64, device=self.device)
+        rc = torch.zeros_like(cnt)
+        dist.all_to_all_single(rc, cnt, group=self.group)
+        rcl = [int(x) for x in rc.cpu()]
+        send = torch.from_numpy(np.concatenate(arrs) if sum(len(a) for a in arrs) else np.zeros(0, dtype=np.int64)).to(self.device)
+        recv = torch.zeros(sum(rcl), dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=rcl, input_split_sizes=[len(a) for a in arrs], group=self.group)
+        out, o = [], 0
+        r = recv.cpu().numpy()
+        for c in rcl:
+            out.append(r[o:o + c])
+            o += c
+        return out
+
+    # ---- per-step exchanges ------------------------------------------------------------------------
+    def reduce_interface(self, vals):
+        """Forward: sum the partial interface rows into their owners (in place on `vals`, ghost-column part into
+        `self.ghost_vals`).  Rows this rank does not own keep their partial sums (they are not part of its result)."""
+        if self.world == 1:
+            return vals
+        send = vals.index_select(0, self.send_pos)
+        recv = torch.empty(sum(self.recv_counts), dtype=vals.dtype, device=vals.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts, group=self.group)
+        vals.index_add_(0, self.recv_match_pos, recv.index_select(0, self.recv_match_idx))
+        self.ghost_vals = recv.index_select(0, self.ghost_idx)
+        return vals
+
+    def replicate_interface(self, dvals, dghost=None):
+        """Adjoint: owners send d loss / d K of the interface entries back, so `dvals` becomes valid on every entry
+        this rank's elements contribute to (rows it does not own included)."""
+        if self.world == 1:
+            return dvals
+        back = torch.empty(sum(self.recv_counts), dtype=dvals.dtype, device=dvals.device)
+        back.index_copy_(0, self.recv_match_idx, dvals.index_select(0, self.recv_match_pos))
+        if len(self.ghost_idx):
+            back.index_copy_(0, self.ghost_idx, dghost if dghost is not None else torch.zeros_like(self.ghost_vals))
+        got = torch.empty(sum(self.send_counts), dtype=dvals.dtype, device=dvals.device)
+        dist.all_to_all_single(got, back, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=self.group)
+        dvals.index_copy_(0, self.send_pos, got)
+        return dvals
+
+    def owned_rows_coo(self, vals):
+        """(global row, global col, value) triplets of the rows this rank owns — for tests / hand-off to a solver."""
+        rows = np.repeat(np.arange(self.mesh.ndof), np.diff(self.rowptr))
+        keep = self.owned[rows]
+        v = vals.detach().cpu().numpy()
+        gr = np.concatenate([self.gid[rows[keep]], self.gid[self.ghost_rows]])
+        gc = np.concatenate([self.gid[self.colind[keep]], self.ghost_gcols])
+        gv = np.concatenate([v[keep], self.ghost_vals.cpu().numpy()])
+        return gr, gc, gv
+
+
+def partition_elements(coords, elems, rank, world, **kw):
+    """Element-block partition of a global mesh given as arrays (setup helper for moderately sized meshes)."""
+    ne = elems.shape[0]
+    e0, e1 = ne * rank // world, ne * (rank + 1) // world
+    own = np.asarray(elems[e0:e1])
+    gv = np.unique(own.reshape(-1))
+    loc = np.searchsorted(gv, own)
+    return Partition(np.asarray(coords)[gv], loc, gv, coords.shape[0], rank, world, **kw), (e0, e1)
+
+
+def structured_slab(m, n_total, h, rank, world, **kw):
+    """Rank `rank`'s row slab of Mesh(m, n_total, h) (src/MFEM/MFEM.jl:134-170) without ever forming the global mesh:
+    element blocks of the row-major cell numbering are slabs of n_total/world cell rows."""
+    assert n_total % world == 0
+    nl = n_total // world
+    j0 = rank * nl
+    coords, elems = meshgen.tri_grid(m, nl, h)
+    coords[:, 1] += j0 * h
+    gvid = np.arange(coords.shape[0], dtype=np.int64) + j0 * (m + 1)
+    return Partition(coords, elems, gvid, (m + 1) * (n_total + 1), rank, world, **kw)
