@@ -32,19 +32,17 @@ template <class T> cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v) {
 }
 
 struct FwdPlanDev {
-  TilePlan host;   // kept only when host_only (inspection); otherwise freed after upload
-  DevBuf<int> row_ptr, rows, elem_ptr, elems;
-  DevBuf<long long> soff_ptr, src_ptr;
-  DevBuf<uint16_t> src_off, src;
-  DevTilePlan dev{};
+  FwdTiles host;   // blob kept on the host only for ADFEM_HOST_ONLY handles (inspection)
+  DevBuf<long long> blob_ptr;
+  DevBuf<uint8_t> blob;
+  DevTiles dev{};
   size_t bytes = 0;
 };
 struct AdjPlanDev {
-  AdjTilePlan host;
-  DevBuf<int> elem_ptr, elems, row_ptr, rows;
-  DevBuf<long long> gidx_ptr;
-  DevBuf<uint16_t> gidx;
-  DevAdjPlan dev{};
+  AdjTiles host;
+  DevBuf<long long> blob_ptr;
+  DevBuf<uint8_t> blob;
+  DevTiles dev{};
   size_t bytes = 0;
 };
 
@@ -69,7 +67,9 @@ struct adfem_mesh {
   std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
-  int opt_smem_budget = 44 * 1024;
+  int opt_smem_budget = 52 * 1024;          // blob + local-matrix staging per CTA (4 CTAs per SM)
+  int opt_tile_threads = 256;
+  int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // scratch for the host-buffer calls
   DevBuf<double> s_in, s_out;
 };
@@ -115,50 +115,45 @@ int ensure_pattern(adfem_mesh* m) {
   return 0;
 }
 
-size_t fwd_smem_bytes(const TilePlan& tp, int S) {
-  return (size_t)8 * S * tp.max_elems + 8 * (size_t)tp.max_rows + 4 * ((size_t)tp.max_rows + 1) + 4 * (size_t)tp.max_rows + 2 * (size_t)tp.max_nnz + 16;
-}
-size_t adj_smem_bytes(const AdjTilePlan& ap, int nc) {
-  return (size_t)8 * nc * nc * ap.max_nnz + 8 * (size_t)ap.max_rows + 4 * ((size_t)ap.max_rows + 1) + 4 * (size_t)ap.max_rows + 2 * (size_t)ap.max_nnz + 16;
-}
+int slots_of(const HostMesh& h, int nc) { return nc == 1 ? h.d * (h.d + 1) / 2 : (nc * h.d) * (nc * h.d); }
+
+size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return align16(tp.max_blob) + (size_t)8 * slots * tp.max_elems; }
+size_t adj_smem_bytes(const AdjTiles& ap, int nc) { return align16(ap.max_blob) + (size_t)8 * nc * nc * ap.max_nnz; }
 
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (int rc = ensure_pattern(m)) return rc;
   const HostMesh& h = m->hm;
-  const int S = (nc * h.d) * (nc * h.d), dd = h.d * h.d;
-  auto it = m->fwd_plans.find(S);
+  const int slots = slots_of(h, nc), dd = h.d * h.d;
+  auto it = m->fwd_plans.find(nc);
   if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
   auto P = std::make_unique<FwdPlanDev>();
   int budget = m->opt_smem_budget;
   std::string err = "tile too large";
   for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
-    int max_elems = std::max(4, std::min(65535 / dd, budget / (8 * S)));
-    double elems_per_row = (double)h.ne * h.d / std::max(1, h.ndof);     // average incident elements per dof
-    int R = m->opt_rows_per_tile > 0 ? m->opt_rows_per_tile : (int)(max_elems / std::max(1.0, elems_per_row) * h.d * 0.55);
-    R = std::max(4, std::min(R, 1024));
-    for (int tries = 0; tries < 12; tries++) {
-      err = P->host.build(h, m->pat, R, max_elems, nthreads_of(m));
+    // per tile element: local matrix + its share of the blob (ids, vertices, sources)
+    const double per_elem = 8.0 * slots + 4 + 2 * (h.dim + 1) + 8 * h.dim * 0.6 + 2.0 * dd * 1.2;
+    int max_elems = std::max(4, std::min(65535 / std::max(slots, dd), (int)(budget / per_elem)));
+    double elems_per_row = (double)h.ne * h.d / std::max(1, h.ndof);
+    int R = m->opt_rows_per_tile > 0 ? m->opt_rows_per_tile : (int)(max_elems / std::max(1.0, elems_per_row) * h.d * 0.8);
+    R = std::max(4, std::min(R, 4096));
+    for (int tries = 0; tries < 16; tries++) {
+      err = P->host.build(h, m->pat, R, max_elems, nc == 1 ? 1 : 0, nthreads_of(m));
+      if (err.empty() && fwd_smem_bytes(P->host, slots) > (size_t)std::max(budget, 200 * 1024)) err = "tile too large";
       if (err.empty() || R <= 4) break;
-      R = std::max(4, (int)(R * 0.7));
+      R = std::max(4, (int)(R * 0.75));
     }
   }
   if (!err.empty()) return fail("forward tile plan: " + err);
-  TilePlan& tp = P->host;
-  P->bytes = 4 * (tp.row_ptr.size() + tp.rows.size() + tp.elem_ptr.size() + tp.elems.size()) + 8 * (tp.soff_ptr.size() + tp.src_ptr.size()) +
-             2 * (tp.src_off.size() + tp.src.size());
+  FwdTiles& tp = P->host;
+  P->bytes = tp.blob.size() + 8 * tp.blob_ptr.size();
   if (!m->host_only) {
-    CU_TRY(upload(P->row_ptr, tp.row_ptr)); CU_TRY(upload(P->rows, tp.rows));
-    CU_TRY(upload(P->elem_ptr, tp.elem_ptr)); CU_TRY(upload(P->elems, tp.elems));
-    CU_TRY(upload(P->soff_ptr, tp.soff_ptr)); CU_TRY(upload(P->src_off, tp.src_off));
-    CU_TRY(upload(P->src_ptr, tp.src_ptr)); CU_TRY(upload(P->src, tp.src));
-    P->dev = DevTilePlan{tp.ntiles, tp.max_rows, tp.max_elems, tp.max_nnz, P->row_ptr.p, P->rows.p, P->elem_ptr.p, P->elems.p,
-                         P->soff_ptr.p, P->src_off.p, P->src_ptr.p, P->src.p};
-    // the big arrays now live on the device
-    std::vector<int>().swap(tp.rows); std::vector<int>().swap(tp.elems);
-    std::vector<uint16_t>().swap(tp.src_off); std::vector<uint16_t>().swap(tp.src);
+    CU_TRY(upload(P->blob_ptr, tp.blob_ptr));
+    CU_TRY(upload(P->blob, tp.blob));
+    P->dev = DevTiles{tp.ntiles, tp.sym, tp.lrow16, (unsigned)align16(tp.max_blob), tp.max_elems, tp.max_nnz, P->blob_ptr.p, P->blob.p};
+    std::vector<uint8_t>().swap(tp.blob);
   }
   *out = P.get();
-  m->fwd_plans[S] = std::move(P);
+  m->fwd_plans[nc] = std::move(P);
   return 0;
 }
 
@@ -171,25 +166,28 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
   int budget = m->opt_smem_budget;
   std::string err = "tile too large";
   for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
-    int max_nnz = std::max(64, std::min(65535, budget / (8 * nc * nc + 2)));
+    const int dd = h.d * h.d;
     double nnz_per_row = (double)m->pat.nnz / std::max(1, m->pat.n), rows_per_elem = (double)m->pat.n / std::max(1, h.ne);
-    int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(max_nnz / nnz_per_row / std::max(1e-9, rows_per_elem) * 0.6);
-    EPT = std::max(4, std::min(EPT, 2048));
-    for (int tries = 0; tries < 12; tries++) {
+    // bytes per owned element: staged gradients + row tables + its share of the blob
+    const double per_elem = rows_per_elem * 1.3 * (nnz_per_row * (8.0 * nc * nc + 2) + 10) + 4 + 2 * (h.dim + 1) + 8 * h.dim * rows_per_elem + 2.0 * dd;
+    int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(budget / per_elem);
+    EPT = std::max(4, std::min(EPT, 4096));
+    const int max_nnz = 65535;
+    for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
+      if (err.empty() && adj_smem_bytes(P->host, nc) > (size_t)std::max(budget, 200 * 1024)) err = "tile too large";
       if (err.empty() || EPT <= 4) break;
-      EPT = std::max(4, (int)(EPT * 0.7));
+      EPT = std::max(4, (int)(EPT * 0.75));
     }
   }
   if (!err.empty()) return fail("adjoint tile plan: " + err);
-  AdjTilePlan& ap = P->host;
-  P->bytes = 4 * (ap.row_ptr.size() + ap.rows.size() + ap.elem_ptr.size() + ap.elems.size()) + 8 * ap.gidx_ptr.size() + 2 * ap.gidx.size();
+  AdjTiles& ap = P->host;
+  P->bytes = ap.blob.size() + 8 * ap.blob_ptr.size();
   if (!m->host_only) {
-    CU_TRY(upload(P->elem_ptr, ap.elem_ptr)); CU_TRY(upload(P->elems, ap.elems));
-    CU_TRY(upload(P->row_ptr, ap.row_ptr)); CU_TRY(upload(P->rows, ap.rows));
-    CU_TRY(upload(P->gidx_ptr, ap.gidx_ptr)); CU_TRY(upload(P->gidx, ap.gidx));
-    P->dev = DevAdjPlan{ap.ntiles, ap.max_rows, ap.max_elems, ap.max_nnz, P->elem_ptr.p, P->elems.p, P->row_ptr.p, P->rows.p, P->gidx_ptr.p, P->gidx.p};
-    std::vector<int>().swap(ap.rows); std::vector<int>().swap(ap.elems); std::vector<uint16_t>().swap(ap.gidx);
+    CU_TRY(upload(P->blob_ptr, ap.blob_ptr));
+    CU_TRY(upload(P->blob, ap.blob));
+    P->dev = DevTiles{ap.ntiles, 0, 1, (unsigned)align16(ap.max_blob), ap.max_elems, ap.max_nnz, P->blob_ptr.p, P->blob.p};
+    std::vector<uint8_t>().swap(ap.blob);
   }
   *out = P.get();
   m->adj_plans[nc] = std::move(P);
@@ -208,13 +206,15 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+DevMesh dev_mesh(const adfem_mesh* m, int heron) { DevMesh d = m->dm; d.heron = heron; return d; }
+
 template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
-  constexpr int NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * ElemTraits<DIM, DEG>::D, S = Dt * Dt;
-  const size_t smem = fwd_smem_bytes(P->host, S);
+  constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
+  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
   auto kern = k_tile_fwd<DIM, DEG, OP>;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<P->dev.ntiles, TILE_THREADS, smem, st>>>(m->dm, m->dpat, P->dev, coef, vals);
+  kern<<<P->dev.ntiles, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -227,9 +227,9 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
     const size_t smem = adj_smem_bytes(P->host, NC);
     auto kern = k_tile_adj<DIM, DEG, OP>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<P->dev.ntiles, TILE_THREADS, smem, st>>>(m->dm, m->dpat, P->dev, dvals, grad);
+    kern<<<P->dev.ntiles, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
   } else {
-    k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(m->dm, m->dpat, dvals, grad);
+    k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
   CU_TRY(cudaGetLastError());
   return 0;
@@ -349,6 +349,9 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
+  else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); m->opt_tile_threads = (int)value; }
+  else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
+  else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);
   return 0;
 }
@@ -390,26 +393,19 @@ int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz) {
 long long adfem_plan_array(adfem_mesh* m, int which_plan, int ncomp, int array_id, void* out) {
   if (!m) { fail("null mesh handle"); return -1; }
   if (!m->host_only) { fail("adfem_plan_array needs an ADFEM_HOST_ONLY handle (plans of device handles live on the device)"); return -1; }
-#define PLAN_ARR(vec)                                                                      \
-  { if (out) memcpy(out, (vec).data(), (vec).size() * sizeof((vec)[0])); return (long long)(vec).size(); }
+  const std::vector<long long>* ptr = nullptr;
+  const std::vector<uint8_t>* blob = nullptr;
   if (which_plan == 0) {
     FwdPlanDev* P = nullptr;
     if (ensure_fwd_plan(m, ncomp, &P)) return -1;
-    const TilePlan& t = P->host;
-    switch (array_id) {
-      case 0: PLAN_ARR(t.row_ptr) case 1: PLAN_ARR(t.rows) case 2: PLAN_ARR(t.elem_ptr) case 3: PLAN_ARR(t.elems)
-      case 4: PLAN_ARR(t.soff_ptr) case 5: PLAN_ARR(t.src_off) case 6: PLAN_ARR(t.src_ptr) case 7: PLAN_ARR(t.src)
-    }
+    ptr = &P->host.blob_ptr; blob = &P->host.blob;
   } else {
     AdjPlanDev* P = nullptr;
     if (ensure_adj_plan(m, ncomp, &P)) return -1;
-    const AdjTilePlan& t = P->host;
-    switch (array_id) {
-      case 0: PLAN_ARR(t.elem_ptr) case 1: PLAN_ARR(t.elems) case 2: PLAN_ARR(t.row_ptr) case 3: PLAN_ARR(t.rows)
-      case 4: PLAN_ARR(t.gidx_ptr) case 5: PLAN_ARR(t.gidx)
-    }
+    ptr = &P->host.blob_ptr; blob = &P->host.blob;
   }
-#undef PLAN_ARR
+  if (array_id == 0) { if (out) memcpy(out, ptr->data(), ptr->size() * sizeof(long long)); return (long long)ptr->size(); }
+  if (array_id == 1) { if (out) memcpy(out, blob->data(), blob->size()); return (long long)blob->size(); }
   fail("unknown plan array");
   return -1;
 }
@@ -476,16 +472,16 @@ int adfem_assemble_coo(adfem_mesh* m, int op, const double* coef, double* vv, vo
   const long long G = (long long)h.ne * h.g;
   if (op == ADFEM_OP_MASS && h.dim == 3) {
     const long long n = (long long)h.ne * h.d;
-    if (h.degree == 1) k_coo_mass3_fwd<1><<<blocks_for(n, 128), 128, 0, st>>>(m->dm, coef, vv);
-    else k_coo_mass3_fwd<2><<<blocks_for(n, 128), 128, 0, st>>>(m->dm, coef, vv);
+    if (h.degree == 1) k_coo_mass3_fwd<1><<<blocks_for(n, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), coef, vv);
+    else k_coo_mass3_fwd<2><<<blocks_for(n, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), coef, vv);
     CU_TRY(cudaGetLastError());
     return 0;
   }
 #define CALL_COO(DIM, DEG)                                                                                   \
   switch (op) {                                                                                              \
-    case ADFEM_OP_LAPLACE: k_coo_scalar_fwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break; \
-    case ADFEM_OP_MASS: k_coo_scalar_fwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break;       \
-    default: k_coo_stiff_fwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, coef, vv); break;          \
+    case ADFEM_OP_LAPLACE: k_coo_scalar_fwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), coef, vv); break; \
+    case ADFEM_OP_MASS: k_coo_scalar_fwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), coef, vv); break;       \
+    default: k_coo_stiff_fwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), coef, vv); break;          \
   }
   DISPATCH_ELEM(m, CALL_COO);
 #undef CALL_COO
@@ -500,16 +496,16 @@ int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, dou
   const HostMesh& h = m->hm;
   const long long G = (long long)h.ne * h.g;
   if (op == ADFEM_OP_MASS && h.dim == 3) {
-    if (h.degree == 1) k_coo_mass3_bwd<1><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef);
-    else k_coo_mass3_bwd<2><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef);
+    if (h.degree == 1) k_coo_mass3_bwd<1><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_vv, grad_coef);
+    else k_coo_mass3_bwd<2><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_vv, grad_coef);
     CU_TRY(cudaGetLastError());
     return 0;
   }
 #define CALL_COOB(DIM, DEG)                                                                                  \
   switch (op) {                                                                                              \
-    case ADFEM_OP_LAPLACE: k_coo_scalar_bwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break; \
-    case ADFEM_OP_MASS: k_coo_scalar_bwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break;       \
-    default: k_coo_stiff_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_vv, grad_coef); break; \
+    case ADFEM_OP_LAPLACE: k_coo_scalar_bwd<DIM, DEG, OP_LAPLACE><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_vv, grad_coef); break; \
+    case ADFEM_OP_MASS: k_coo_scalar_bwd<DIM, DEG, OP_MASS><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_vv, grad_coef); break;       \
+    default: k_coo_stiff_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_vv, grad_coef); break; \
   }
   DISPATCH_ELEM(m, CALL_COOB);
 #undef CALL_COOB
@@ -522,7 +518,7 @@ int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL_SRC(DIM, DEG) \
-  k_source_fwd<DIM, DEG><<<blocks_for(m->hm.ndof, 128), 128, 0, st>>>(m->dm, m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, f, rhs)
+  k_source_fwd<DIM, DEG><<<blocks_for(m->hm.ndof, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, f, rhs)
   DISPATCH_ELEM(m, CALL_SRC);
 #undef CALL_SRC
   CU_TRY(cudaGetLastError());
@@ -533,7 +529,7 @@ int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, 
   if (int rc = need_device(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long G = (long long)m->hm.ne * m->hm.g;
-#define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(m->dm, grad_rhs, grad_f)
+#define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_rhs, grad_f)
   DISPATCH_ELEM(m, CALL_SRCB);
 #undef CALL_SRCB
   CU_TRY(cudaGetLastError());

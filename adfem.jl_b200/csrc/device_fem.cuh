@@ -14,6 +14,7 @@ namespace adfem {
 
 struct DevMesh {            // passed by value to kernels
   int dim, ne, nv, d, g, ndof;
+  int heron;                // 2-D weight scale: 1 = Heron area like the reference, 0 = det/2
   const double* coords;     // nv x dim packed
   const int* verts;         // [(dim+1)][ne]  struct-of-arrays, post orientation fix
   const int* conn;          // [d][ne]        struct-of-arrays dof ids
@@ -42,31 +43,30 @@ template <int DIM> __device__ __forceinline__ void load_verts(const DevMesh& m, 
   for (int k = 0; k <= DIM; k++) v[k] = ldg(m.verts + (size_t)k * m.ne + e);
 }
 
-// Geometry of a triangle: gradients as MFEM's CalcPhysDShape (adj(J)/det), weight scale from the
-// Heron area exactly as deps/MFEM/Common.cpp:9-15,83,116 (w = ip.weight * area / 0.5).
-__device__ __forceinline__ void geom_from_verts(const DevMesh& m, const int v[3], Geom<2>& G) {
-  const double2* X = reinterpret_cast<const double2*>(m.coords);
-  const double2 p1 = __ldg(X + v[0]), p2 = __ldg(X + v[1]), p3 = __ldg(X + v[2]);
+// Geometry of a triangle from its (orientation-fixed) vertices: gradients of the barycentric coordinates
+// as MFEM's CalcPhysDShape (adj(J)/det).  Weight scale: the reference uses w = ip.weight * area / 0.5 with the
+// HERON area (deps/MFEM/Common.cpp:9-15,83,116); `heron` = 0 uses area = det/2 instead (identical up to the
+// rounding of Heron's formula, 4 sqrt cheaper).
+__device__ __forceinline__ void geom_tri(const double2 p1, const double2 p2, const double2 p3, int heron, Geom<2>& G) {
   const double det = (p2.x - p1.x) * (p3.y - p1.y) - (p3.x - p1.x) * (p2.y - p1.y);
-  G.gL[1][0] = (p3.y - p1.y) / det;  G.gL[1][1] = -(p3.x - p1.x) / det;
-  G.gL[2][0] = -(p2.y - p1.y) / det; G.gL[2][1] = (p2.x - p1.x) / det;
+  const double inv = 1.0 / det;
+  G.gL[1][0] = (p3.y - p1.y) * inv;  G.gL[1][1] = -(p3.x - p1.x) * inv;
+  G.gL[2][0] = -(p2.y - p1.y) * inv; G.gL[2][1] = (p2.x - p1.x) * inv;
   G.gL[0][0] = -G.gL[1][0] - G.gL[2][0]; G.gL[0][1] = -G.gL[1][1] - G.gL[2][1];
-  const double a = sqrt((p1.x - p2.x) * (p1.x - p2.x) + (p1.y - p2.y) * (p1.y - p2.y));
-  const double b = sqrt((p3.x - p2.x) * (p3.x - p2.x) + (p3.y - p2.y) * (p3.y - p2.y));
-  const double c = sqrt((p1.x - p3.x) * (p1.x - p3.x) + (p1.y - p3.y) * (p1.y - p3.y));
-  const double s = (a + b + c) / 2.0;
-  const double area = sqrt(s * (s - a) * (s - b) * (s - c));
-  G.wscale = area / 0.5;
+  if (heron) {
+    const double a = sqrt((p1.x - p2.x) * (p1.x - p2.x) + (p1.y - p2.y) * (p1.y - p2.y));
+    const double b = sqrt((p3.x - p2.x) * (p3.x - p2.x) + (p3.y - p2.y) * (p3.y - p2.y));
+    const double c = sqrt((p1.x - p3.x) * (p1.x - p3.x) + (p1.y - p3.y) * (p1.y - p3.y));
+    const double s = (a + b + c) / 2.0;
+    G.wscale = sqrt(s * (s - a) * (s - b) * (s - c)) / 0.5;
+  } else {
+    G.wscale = det;
+  }
 }
 
 // Geometry of a tetrahedron: volume = det/6 (Mesh::GetElementVolume), w = ip.weight * volume * 6
 // (deps/MFEM3/Common.cpp:88,117).
-__device__ __forceinline__ void geom_from_verts(const DevMesh& m, const int v[4], Geom<3>& G) {
-  double X[4][3];
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) X[k][c] = ldg(m.coords + (size_t)v[k] * 3 + c);
+__device__ __forceinline__ void geom_tet(const double X[4][3], Geom<3>& G) {
   double J[3][3];
 #pragma unroll
   for (int r = 0; r < 3; r++)
@@ -74,19 +74,45 @@ __device__ __forceinline__ void geom_from_verts(const DevMesh& m, const int v[4]
     for (int c = 0; c < 3; c++) J[r][c] = X[c + 1][r] - X[0][r];
   const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
                      J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-  G.gL[1][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; G.gL[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; G.gL[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-  G.gL[2][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; G.gL[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; G.gL[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-  G.gL[3][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; G.gL[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; G.gL[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  const double inv = 1.0 / det;
+  G.gL[1][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * inv; G.gL[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * inv; G.gL[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv;
+  G.gL[2][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * inv; G.gL[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * inv; G.gL[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * inv;
+  G.gL[3][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * inv; G.gL[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * inv; G.gL[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv;
 #pragma unroll
   for (int c = 0; c < 3; c++) G.gL[0][c] = -G.gL[1][c] - G.gL[2][c] - G.gL[3][c];
-  const double vol = det * (1. / 6.);
-  G.wscale = vol * 6.0;
+  G.wscale = det * (1. / 6.) * 6.0;
 }
 
-template <int DIM> __device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<DIM>& G) {
-  int v[DIM + 1];
-  load_verts<DIM>(m, e, v);
-  geom_from_verts(m, v, G);
+// geometry of element e from the global vertex / coordinate arrays
+__device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<2>& G) {
+  int v[3]; load_verts<2>(m, e, v);
+  const double2* X = reinterpret_cast<const double2*>(m.coords);
+  geom_tri(__ldg(X + v[0]), __ldg(X + v[1]), __ldg(X + v[2]), m.heron, G);
+}
+__device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<3>& G) {
+  int v[4]; load_verts<3>(m, e, v);
+  double X[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[k][c] = ldg(m.coords + (size_t)v[k] * 3 + c);
+  geom_tet(X, G);
+}
+// geometry of tile element `le` from a tile blob staged in shared memory: tv = k-major tile-local vertex ids,
+// xy = coordinates of the tile-local vertices
+__device__ __forceinline__ void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int heron, Geom<2>& G) {
+  const double2* X = reinterpret_cast<const double2*>(xy);
+  geom_tri(X[tv[le]], X[tv[nel + le]], X[tv[2 * nel + le]], heron, G);
+}
+__device__ __forceinline__ void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int, Geom<3>& G) {
+  double X[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double* p = xy + 3 * (int)tv[k * nel + le];
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[k][c] = p[c];
+  }
+  geom_tet(X, G);
 }
 
 template <int DIM> __device__ __forceinline__ void bary(const QuadRule& r, int k, double L[DIM + 1]) {

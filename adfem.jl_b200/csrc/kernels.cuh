@@ -11,7 +11,7 @@
 
 namespace adfem {
 
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_MAX_THREADS = 512;
 
 struct DevPattern {
   int n; long long nnz;
@@ -19,16 +19,12 @@ struct DevPattern {
   const int* colind;              // nnz
   const uint32_t* slot_nnz;       // [d*d][ne] struct-of-arrays
 };
-struct DevTilePlan {
-  int ntiles, max_rows, max_elems, max_nnz;
-  const int *row_ptr, *rows, *elem_ptr, *elems;
-  const long long* soff_ptr; const uint16_t* src_off;
-  const long long* src_ptr;  const uint16_t* src;
-};
-struct DevAdjPlan {
-  int ntiles, max_rows, max_elems, max_nnz;
-  const int *elem_ptr, *elems, *row_ptr, *rows;
-  const long long* gidx_ptr; const uint16_t* gidx;
+struct DevTiles {                  // forward (FwdTiles) or adjoint (AdjTiles) blobs on the device
+  int ntiles, sym, lrow16;
+  unsigned max_blob;               // bytes, multiple of 16
+  int max_elems, max_nnz;
+  const long long* blob_ptr;
+  const unsigned char* blob;
 };
 
 // ==================================================================================================
@@ -41,7 +37,7 @@ __global__ void k_coo_scalar_fwd(DevMesh m, const double* __restrict__ coef, dou
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
+  Geom<DIM> G; load_geom(m, e, G);
   double L[DIM + 1]; bary<DIM>(m.rule, k, L);
   const double c = coef[t], w = m.rule.w[k] * G.wscale;
   double* out = vv + t * (D * D);
@@ -66,7 +62,7 @@ __global__ void k_coo_scalar_bwd(DevMesh m, const double* __restrict__ grad_vv, 
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
+  Geom<DIM> G; load_geom(m, e, G);
   double L[DIM + 1]; bary<DIM>(m.rule, k, L);
   const double w = m.rule.w[k] * G.wscale;
   const double* gin = grad_vv + t * (D * D);
@@ -94,7 +90,7 @@ __global__ void k_coo_mass3_fwd(DevMesh m, const double* __restrict__ rho, doubl
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * D) return;
   const int e = (int)(t / D), p = (int)(t % D);
-  Geom<3> G; load_geom<3>(m, e, G);
+  Geom<3> G; load_geom(m, e, G);
   double acc[D];
 #pragma unroll
   for (int q = 0; q < D; q++) acc[q] = 0.0;
@@ -118,7 +114,7 @@ __global__ void k_coo_mass3_bwd(DevMesh m, const double* __restrict__ grad_vv, d
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<3> G; load_geom<3>(m, e, G);
+  Geom<3> G; load_geom(m, e, G);
   double L[4]; bary<3>(m.rule, k, L);
   double phi[D]; basis_val<3, DEG>(L, phi);
   const double w = m.rule.w[k] * G.wscale;
@@ -137,7 +133,7 @@ __global__ void k_coo_stiff_fwd(DevMesh m, const double* __restrict__ hmat, doub
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
+  Geom<DIM> G; load_geom(m, e, G);
   double L[DIM + 1]; bary<DIM>(m.rule, k, L);
   double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
   const double w = m.rule.w[k] * G.wscale;
@@ -165,7 +161,7 @@ __global__ void k_coo_stiff_bwd(DevMesh m, const double* __restrict__ grad_vv, d
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
+  Geom<DIM> G; load_geom(m, e, G);
   double L[DIM + 1]; bary<DIM>(m.rule, k, L);
   double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
   const double w = m.rule.w[k] * G.wscale;
@@ -225,7 +221,7 @@ __global__ void k_source_fwd(DevMesh m, const long long* __restrict__ adj_ptr, c
   double acc = 0.0;
   for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
     const int e = adj_elem[a], p = adj_loc[a];
-    Geom<DIM> G; load_geom<DIM>(m, e, G);
+    Geom<DIM> G; load_geom(m, e, G);
     for (int k = 0; k < m.g; k++) {
       double L[DIM + 1]; bary<DIM>(m.rule, k, L);
       double phi[D]; basis_val<DIM, DEG>(L, phi);
@@ -244,7 +240,7 @@ __global__ void k_source_bwd(DevMesh m, const double* __restrict__ grad_rhs, dou
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)m.ne * m.g) return;
   const int e = (int)(t / m.g), k = (int)(t % m.g);
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
+  Geom<DIM> G; load_geom(m, e, G);
   double L[DIM + 1]; bary<DIM>(m.rule, k, L);
   double phi[D]; basis_val<DIM, DEG>(L, phi);
   const double w = m.rule.w[k] * G.wscale;
@@ -257,44 +253,46 @@ __global__ void k_source_bwd(DevMesh m, const double* __restrict__ grad_rhs, dou
 // ==================================================================================================
 // CSR fast path
 // ==================================================================================================
-// Exclusive scan of n ints in shared memory by the whole CTA; out[n] = total. tmp = 32 ints of smem.
-__device__ __forceinline__ void block_exclusive_scan(const int* in, int* out, int n, int* tmp) {
-  const int nth = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int ipt = (n + nth - 1) / nth, b = min(n, tid * ipt), e = min(n, b + ipt);
-  int s = 0;
-  for (int i = b; i < e; i++) s += in[i];
-  int x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) tmp[w] = x;
-  __syncthreads();
-  if (w == 0) {
-    int v = lane < (nth >> 5) ? tmp[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
-    tmp[lane] = v;
-  }
-  __syncthreads();
-  int base = (w > 0 ? tmp[w - 1] : 0) + x - s;
-  for (int i = b; i < e; i++) { out[i] = base; base += in[i]; }
-  if (tid == 0) out[n] = tmp[(nth >> 5) - 1];
-  __syncthreads();
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one contiguous global -> shared bulk copy (SASS: UBLKCP), completion signalled on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
 
-// Local element matrix summed over Gauss points, handed to `put(slot, value)` with slot = l*Dt + s.
+// Local element matrix summed over Gauss points, handed to `put(slot, value)`.
+//   scalar ops (symmetric): slot = index in the packed upper triangle (p <= q, row-major)
+//   stiffness (H may be unsymmetric): slot = l*Dt + s; P2 accumulates over Gauss points through put(-slot-1, v)
 template <int DIM, int DEG, int OP, typename Put>
-__device__ __forceinline__ void local_matrix(const DevMesh& m, int e, const double* __restrict__ coef, Put put) {
+__device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& G, int e, const double* __restrict__ coef, Put put) {
   constexpr int D = ElemTraits<DIM, DEG>::D;
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
   if (OP == OP_LAPLACE && DEG == 1) {
     double c = 0.0;                                   // gradients are constant: sum the coefficients first
     for (int k = 0; k < m.g; k++) c += coef[(size_t)e * m.g + k] * (m.rule.w[k] * G.wscale);
+    int i = 0;
 #pragma unroll
     for (int p = 0; p < D; p++)
 #pragma unroll
-      for (int q = p; q < D; q++) { const double v = dotg<DIM>(G.gL[p], G.gL[q]) * c; put(p * D + q, v); if (q != p) put(q * D + p, v); }
+      for (int q = p; q < D; q++) put(i++, dotg<DIM>(G.gL[p], G.gL[q]) * c);
   } else if (OP == OP_LAPLACE || OP == OP_MASS) {
-    constexpr int NA = D * (D + 1) / 2;                // symmetric accumulators
+    constexpr int NA = D * (D + 1) / 2;
     double acc[NA];
 #pragma unroll
     for (int i = 0; i < NA; i++) acc[i] = 0.0;
@@ -317,12 +315,9 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, int e, const doub
           for (int q = p; q < D; q++) acc[i++] += phi[p] * phi[q] * c;
       }
     }
-    int i = 0;
 #pragma unroll
-    for (int p = 0; p < D; p++)
-#pragma unroll
-      for (int q = p; q < D; q++) { put(p * D + q, acc[i]); if (q != p) put(q * D + p, acc[i]); i++; }
-  } else {   // OP_STIFFNESS (H may be unsymmetric: keep the full block)
+    for (int i = 0; i < NA; i++) put(i, acc[i]);
+  } else {
     constexpr int NS = Voigt<DIM>::NS, Dt = DIM * D;
     if (DEG == 1) {
       double H[NS * NS];                               // constant B: sum H_k w_k first
@@ -347,8 +342,6 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, int e, const doub
             for (int pl = 0; pl < D; pl++) put((cl * D + pl) * Dt + cs * D + ps, bdot<DIM>(cl, G.gL[pl], hb));
         }
     } else {
-      // P2: Dt*Dt accumulators do not fit in registers; the caller's put() must accumulate
-      // (first Gauss point stores, later ones add) — signalled through negative slot offset.
       for (int k = 0; k < m.g; k++) {
         double L[DIM + 1]; bary<DIM>(m.rule, k, L);
         double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
@@ -373,79 +366,76 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, int e, const doub
   }
 }
 
-// Forward: one CTA per row tile.  Phase A evaluates the local matrices of every element touching the
-// tile's rows into shared memory; phase B lets each CSR entry of those rows sum its contributions in a
-// fixed (column, element) order and writes it once.
+// Forward: one CTA per row tile.  The tile's mesh-static blob (index lists + vertex coordinates) arrives by ONE
+// TMA bulk copy; phase A evaluates the local matrices of every element touching the tile's rows into shared
+// memory; phase B lets each CSR entry sum its contributions in a fixed (column, element) order and writes it once.
 template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile_fwd(DevMesh m, DevPattern pat, DevTilePlan tp, const double* __restrict__ coef,
-                                                           double* __restrict__ vals) {
-  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, S = Dt * Dt, dd = D * D;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int scan_tmp[32];
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const int r0 = tp.row_ptr[t], nrows = tp.row_ptr[t + 1] - r0;
-  const int e0 = tp.elem_ptr[t], nel = tp.elem_ptr[t + 1] - e0;
-  const long long so0 = tp.soff_ptr[t];
-  const int nnz_t = (int)(tp.soff_ptr[t + 1] - so0) - 1;
-  const uint16_t* __restrict__ soff = tp.src_off + so0;
-  const uint16_t* __restrict__ src = tp.src + tp.src_ptr[t];
-  double* loc = reinterpret_cast<double*>(smem_raw);                                   // S x nel
-  long long* rstart = reinterpret_cast<long long*>(loc + (size_t)S * tp.max_elems);    // max_rows
-  int* roff = reinterpret_cast<int*>(rstart + tp.max_rows);                            // max_rows + 1
-  int* rlen = roff + tp.max_rows + 1;                                                  // max_rows
-  unsigned short* lrow = reinterpret_cast<unsigned short*>(rlen + tp.max_rows);        // max_nnz
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
+                                                               double* __restrict__ vals) {
+  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const long long b0 = tp.blob_ptr[t];
+  const uint32_t bytes = (uint32_t)(tp.blob_ptr[t + 1] - b0);
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(smem, tp.blob + b0, bytes, &mbar); }
+  mbar_wait(&mbar, 0);
+  const int* hdr = reinterpret_cast<const int*>(smem);
+  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
+  unsigned o = 32;
+  const long long* rstart = reinterpret_cast<const long long*>(smem + o); o += a16(8u * nrows);
+  const unsigned short* roff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nrows + 1));
+  const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
+  const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
+  const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
+  const unsigned char* lrow8 = smem + o;
+  const unsigned short* lrow16 = reinterpret_cast<const unsigned short*>(smem + o); o += a16((tp.lrow16 ? 2u : 1u) * nnz_t);
+  const unsigned short* soff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nnz_t + 1));
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(smem + o);
+  double* loc = reinterpret_cast<double*>(smem + tp.max_blob);
 
-  for (int lr = tid; lr < nrows; lr += TILE_THREADS) {
-    const int r = tp.rows[r0 + lr];
-    const long long a = pat.rowptr[r], b = pat.rowptr[r + 1];
-    rstart[lr] = a; rlen[lr] = (int)(b - a);
-  }
-  for (int le = tid; le < nel; le += TILE_THREADS) {
-    const int e = tp.elems[e0 + le];
-    local_matrix<DIM, DEG, OP>(m, e, coef, [&](int slot, double v) {
-      if (slot >= 0) loc[(size_t)slot * nel + le] = v; else loc[(size_t)(-slot - 1) * nel + le] += v;
+  for (int le = tid; le < nel; le += nth) {
+    Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);
+    local_matrix<DIM, DEG, OP>(m, G, elems[le], coef, [&](int slot, double v) {
+      if (slot >= 0) loc[slot * nel + le] = v; else loc[(-slot - 1) * nel + le] += v;
     });
   }
   __syncthreads();
-  block_exclusive_scan(rlen, roff, nrows, scan_tmp);
-  for (int lr = tid; lr < nrows; lr += TILE_THREADS) {
-    const int o = roff[lr], n = rlen[lr];
-    for (int j = 0; j < n; j++) lrow[o + j] = (unsigned short)lr;
-  }
-  __syncthreads();
-  for (int i = tid; i < nnz_t; i += TILE_THREADS) {
-    const int lr = lrow[i], j = i - roff[lr];
+  for (int i = tid; i < nnz_t; i += nth) {
+    const int lr = tp.lrow16 ? (int)lrow16[i] : (int)lrow8[i];
+    const int j = i - roff[lr];
     const int sb = soff[i], se = soff[i + 1];
     if (NC == 1) {
       double v = 0.0;
-      for (int s = sb; s < se; s++) { const int c = src[s]; v += loc[(size_t)(c % dd) * nel + c / dd]; }
+      for (int s = sb; s < se; s++) v += loc[src[s]];
       vals[rstart[lr] + j] = v;
     } else {
       double v[NC * NC];
 #pragma unroll
       for (int ab = 0; ab < NC * NC; ab++) v[ab] = 0.0;
       for (int s = sb; s < se; s++) {
-        const int c = src[s], le = c / dd, pq = c % dd, p = pq / D, q = pq % D;
+        const int c = src[s], le = c / dd, pq = c - le * dd, p = pq / D, q = pq - p * D;
 #pragma unroll
         for (int a = 0; a < NC; a++)
 #pragma unroll
-          for (int b = 0; b < NC; b++) v[a * NC + b] += loc[(size_t)((a * D + p) * Dt + b * D + q) * nel + le];
+          for (int b = 0; b < NC; b++) v[a * NC + b] += loc[((a * D + p) * Dt + b * D + q) * nel + le];
       }
-      const long long len = rlen[lr];
+      const long long len = roff[lr + 1] - roff[lr], rs = rstart[lr];
 #pragma unroll
       for (int a = 0; a < NC; a++)
 #pragma unroll
-        for (int b = 0; b < NC; b++) vals[NC * (a * pat.nnz + rstart[lr]) + b * len + j] = v[a * NC + b];
+        for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
     }
   }
 }
 
-// Contract the D*D (or Dt*Dt) upstream gradients `g(l, s)` of one element with its shape tables:
-// writes grad_coef for every Gauss point of the element.
+// Contract the upstream gradients `g(l, s)` of one element's local matrix with its shape tables: writes
+// grad_coef for every Gauss point of the element.
 template <int DIM, int DEG, int OP, typename Get>
-__device__ __forceinline__ void local_adjoint(const DevMesh& m, int e, Get g, double* __restrict__ grad_coef) {
+__device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>& G, int e, Get g, double* __restrict__ grad_coef) {
   constexpr int D = ElemTraits<DIM, DEG>::D;
-  Geom<DIM> G; load_geom<DIM>(m, e, G);
   if (OP == OP_LAPLACE && DEG == 1) {
     double s = 0.0;
 #pragma unroll
@@ -528,10 +518,11 @@ __global__ void k_csr_adj_gather(DevMesh m, DevPattern pat, const double* __rest
   constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m.ne) return;
+  Geom<DIM> G; load_geom(m, e, G);
   if (NC == 1) {
-    local_adjoint<DIM, DEG, OP>(m, e, [&](int p, int q) { return dvals[pat.slot_nnz[(size_t)(p * D + q) * m.ne + e]]; }, grad_coef);
+    local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return dvals[pat.slot_nnz[(size_t)(p * D + q) * m.ne + e]]; }, grad_coef);
   } else {
-    local_adjoint<DIM, DEG, OP>(m, e, [&](int l, int s) {
+    local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
       const int a = l / D, p = l % D, b = s / D, q = s % D;
       const int r = ldg(m.conn + (size_t)p * m.ne + e);
       const long long rs = pat.rowptr[r], len = pat.rowptr[r + 1] - rs;
@@ -541,55 +532,53 @@ __global__ void k_csr_adj_gather(DevMesh m, DevPattern pat, const double* __rest
   }
 }
 
-// Adjoint, tiled version: one CTA per element tile stages the CSR rows its elements touch into shared
-// memory with coalesced loads, then every element gathers its upstream gradients from there.
+// Adjoint, tiled version: one CTA per element tile.  One TMA bulk copy brings the tile blob; the CSR rows the
+// tile's elements touch are staged into shared memory with coalesced loads; every element then gathers its
+// upstream gradients from shared memory and contracts them with its shape tables.
 template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile_adj(DevMesh m, DevPattern pat, DevAdjPlan ap, const double* __restrict__ dvals,
-                                                           double* __restrict__ grad_coef) {
-  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, dd = D * D;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int scan_tmp[32];
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const int r0 = ap.row_ptr[t], nrows = ap.row_ptr[t + 1] - r0;
-  const int e0 = ap.elem_ptr[t], nel = ap.elem_ptr[t + 1] - e0;
-  const uint16_t* __restrict__ gidx = ap.gidx + ap.gidx_ptr[t];
-  double* sd = reinterpret_cast<double*>(smem_raw);                                             // NC*NC x max_nnz
-  long long* rstart = reinterpret_cast<long long*>(sd + (size_t)NC * NC * ap.max_nnz);          // max_rows
-  int* roff = reinterpret_cast<int*>(rstart + ap.max_rows);                                     // max_rows + 1
-  int* rlen = roff + ap.max_rows + 1;                                                           // max_rows
-  unsigned short* lrow = reinterpret_cast<unsigned short*>(rlen + ap.max_rows);                 // max_nnz
-  for (int lr = tid; lr < nrows; lr += TILE_THREADS) {
-    const int r = ap.rows[r0 + lr];
-    const long long a = pat.rowptr[r], b = pat.rowptr[r + 1];
-    rstart[lr] = a; rlen[lr] = (int)(b - a);
-  }
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, const double* __restrict__ dvals,
+                                                               double* __restrict__ grad_coef) {
+  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, dd = D * D, NVL = DIM + 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const long long b0 = ap.blob_ptr[t];
+  const uint32_t bytes = (uint32_t)(ap.blob_ptr[t + 1] - b0);
+  if (tid == 0) mbar_init(&mbar, 1);
   __syncthreads();
-  block_exclusive_scan(rlen, roff, nrows, scan_tmp);
-  const int nnz_t = roff[nrows];
-  for (int lr = tid; lr < nrows; lr += TILE_THREADS) {
-    const int o = roff[lr], n = rlen[lr];
-    for (int j = 0; j < n; j++) lrow[o + j] = (unsigned short)lr;
-  }
-  __syncthreads();
-  for (int i = tid; i < nnz_t; i += TILE_THREADS) {
+  if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(smem, ap.blob + b0, bytes, &mbar); }
+  mbar_wait(&mbar, 0);
+  const int* hdr = reinterpret_cast<const int*>(smem);
+  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
+  unsigned o = 32;
+  const long long* rstart = reinterpret_cast<const long long*>(smem + o); o += a16(8u * nrows);
+  const unsigned short* roff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nrows + 1));
+  const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
+  const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
+  const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
+  const unsigned short* lrow = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * nnz_t);
+  const unsigned short* gidx = reinterpret_cast<const unsigned short*>(smem + o);
+  double* sd = reinterpret_cast<double*>(smem + ap.max_blob);                       // NC*NC x nnz_t staged upstream gradients
+
+  for (int i = tid; i < nnz_t; i += nth) {
     const int lr = lrow[i], j = i - roff[lr];
     if (NC == 1) sd[i] = dvals[rstart[lr] + j];
     else {
-      const long long len = rlen[lr];
+      const long long len = roff[lr + 1] - roff[lr], rs = rstart[lr];
 #pragma unroll
       for (int a = 0; a < NC; a++)
 #pragma unroll
-        for (int b = 0; b < NC; b++) sd[(size_t)(a * NC + b) * nnz_t + i] = dvals[NC * (a * pat.nnz + rstart[lr]) + b * len + j];
+        for (int b = 0; b < NC; b++) sd[(a * NC + b) * nnz_t + i] = dvals[NC * (a * nnz_s + rs) + b * len + j];
     }
   }
   __syncthreads();
-  for (int le = tid; le < nel; le += TILE_THREADS) {
-    const int e = ap.elems[e0 + le];
-    const uint16_t* __restrict__ gi = gidx + (size_t)le * dd;
-    if (NC == 1) local_adjoint<DIM, DEG, OP>(m, e, [&](int p, int q) { return sd[gi[p * D + q]]; }, grad_coef);
-    else local_adjoint<DIM, DEG, OP>(m, e, [&](int l, int s) {
+  for (int le = tid; le < nel; le += nth) {
+    Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);
+    const int e = elems[le];
+    if (NC == 1) local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[gidx[(p * D + q) * nel + le]]; }, grad_coef);
+    else local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
       const int a = l / D, p = l % D, b = s / D, q = s % D;
-      return sd[(size_t)(a * NC + b) * nnz_t + gi[p * D + q]];
+      return sd[(a * NC + b) * nnz_t + gidx[(p * D + q) * nel + le]];
     }, grad_coef);
   }
 }

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <thread>
 #include <utility>
@@ -153,82 +154,135 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------------------------
-std::string TilePlan::build(const HostMesh& m, const ScalarPattern& pat, int R, int max_tile_elems, int nthreads) {
-  rows_per_tile = R;
+namespace {
+struct BlobWriter {
+  std::vector<uint8_t>& out;
+  size_t base;
+  explicit BlobWriter(std::vector<uint8_t>& o) : out(o), base(o.size()) {}
+  template <class T> void section(const T* data, size_t count) {
+    size_t at = out.size(), bytes = count * sizeof(T), padded = align16(bytes);
+    out.resize(at + padded, 0);
+    if (bytes) memcpy(out.data() + at, data, bytes);
+  }
+  template <class T> void section(const std::vector<T>& v) { section(v.data(), v.size()); }
+  size_t size() const { return out.size() - base; }
+};
+
+// vertices (post orientation fix) used by a sorted element list, and the k-major local ids
+void tile_vertices(const HostMesh& m, const std::vector<int>& te, std::vector<int>& tvert, std::vector<uint16_t>& tv, std::vector<double>& xy) {
+  const int nvl = m.dim + 1, nel = (int)te.size();
+  tvert.clear();
+  for (int e : te) for (int k = 0; k < nvl; k++) tvert.push_back(m.verts[(size_t)e * nvl + k]);
+  std::sort(tvert.begin(), tvert.end());
+  tvert.erase(std::unique(tvert.begin(), tvert.end()), tvert.end());
+  tv.resize((size_t)nvl * nel);
+  for (int le = 0; le < nel; le++)
+    for (int k = 0; k < nvl; k++)
+      tv[(size_t)k * nel + le] = (uint16_t)(std::lower_bound(tvert.begin(), tvert.end(), m.verts[(size_t)te[le] * nvl + k]) - tvert.begin());
+  xy.resize(tvert.size() * m.dim);
+  for (size_t i = 0; i < tvert.size(); i++)
+    for (int c = 0; c < m.dim; c++) xy[i * m.dim + c] = m.coords[(size_t)tvert[i] * m.dim + c];
+}
+
+struct PartOut { std::vector<uint8_t> blob; std::vector<long long> sizes; std::string err; int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0; long long tot_a = 0; };
+
+template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<PartOut>& parts, F per_tile) {
+  int nparts = std::max(1, std::min(nthreads, ntiles));
+  parts.assign(nparts, PartOut());
+  std::vector<long long> pcut(nparts + 1);
+  for (int i = 0; i <= nparts; i++) pcut[i] = (long long)ntiles * i / nparts;
+  std::vector<std::thread> th;
+  for (int pi = 0; pi < nparts; pi++) th.emplace_back([&, pi] {
+    PartOut& P = parts[pi];
+    for (long long t = pcut[pi]; t < pcut[pi + 1] && P.err.empty(); t++) {
+      size_t before = P.blob.size();
+      per_tile((int)t, P);
+      P.sizes.push_back((long long)(P.blob.size() - before));
+    }
+  });
+  for (auto& t : th) t.join();
+  for (auto& P : parts) if (!P.err.empty()) return P.err;
+  return "";
+}
+}  // namespace
+
+std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, int max_tile_elems, int sym_, int nthreads) {
+  rows_per_tile = R; sym = sym_;
   const int d = m.d, dd = d * d, n = pat.n;
+  const int nslot = sym ? d * (d + 1) / 2 : dd;
+  lrow16 = R > 256;
   Morton mc(m);
   std::vector<int> order;
   morton_order(n, nthreads, [&](long long i) { double x[3]; m.dof_position((int)i, x); return mc.code(x); }, order);
   ntiles = (n + R - 1) / R;
-  row_ptr.resize(ntiles + 1);
+  std::vector<int> row_ptr(ntiles + 1);
   for (int t = 0; t <= ntiles; t++) row_ptr[t] = (int)std::min<long long>((long long)t * R, n);
-  rows = order;
+  std::vector<int>& rows = order;
   parallel_for(ntiles, nthreads, [&](long long b, long long e, int) {
     for (long long t = b; t < e; t++) std::sort(rows.begin() + row_ptr[t], rows.begin() + row_ptr[t + 1]);
   });
+  std::vector<int> symidx(dd);
+  for (int p = 0; p < d; p++) for (int q = 0; q < d; q++) { int a = std::min(p, q), b = std::max(p, q); symidx[p * d + q] = a * d - a * (a - 1) / 2 + (b - a); }
 
-  struct Part { std::vector<int> elems, elem_cnt; std::vector<uint16_t> soff, src; std::vector<long long> soff_cnt, src_cnt; std::string err; };
-  int nparts = std::max(1, std::min(nthreads, ntiles));
-  std::vector<Part> parts(nparts);
-  std::vector<long long> pcut(nparts + 1);
-  for (int i = 0; i <= nparts; i++) pcut[i] = (long long)ntiles * i / nparts;
-  {
-    std::vector<std::thread> th;
-    for (int pi = 0; pi < nparts; pi++) th.emplace_back([&, pi] {
-      Part& P = parts[pi];
-      std::vector<ColSlot> ps;
-      std::vector<int> te;
-      for (long long t = pcut[pi]; t < pcut[pi + 1]; t++) {
-        te.clear();
-        for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) { int r = rows[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
-        std::sort(te.begin(), te.end());
-        te.erase(std::unique(te.begin(), te.end()), te.end());
-        if ((long long)te.size() > max_tile_elems || (long long)te.size() * dd > 65535) { P.err = "tile too large"; return; }
-        P.elem_cnt.push_back((int)te.size());
-        P.elems.insert(P.elems.end(), te.begin(), te.end());
-        size_t s0 = P.src.size(), o0 = P.soff.size();
-        for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) {
-          row_pairs(m, pat, rows[i], ps);
-          for (size_t k = 0; k < ps.size(); k++) {
-            if (k == 0 || ps[k].first != ps[k - 1].first) P.soff.push_back((uint16_t)(P.src.size() - s0));
-            int el = (int)(ps[k].second / dd), pq = (int)(ps[k].second % dd);
-            int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
-            P.src.push_back((uint16_t)(le * dd + pq));
-          }
-        }
-        if (P.src.size() - s0 > 65535) { P.err = "tile too large"; return; }
-        P.soff.push_back((uint16_t)(P.src.size() - s0));
-        P.soff_cnt.push_back((long long)(P.soff.size() - o0));
-        P.src_cnt.push_back((long long)(P.src.size() - s0));
+  std::vector<PartOut> parts;
+  std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
+    std::vector<ColSlot> ps;
+    std::vector<int> te, tvert;
+    std::vector<uint16_t> tv, roff, soff, src, lrow2;
+    std::vector<uint8_t> lrow1;
+    std::vector<double> xy;
+    std::vector<long long> rstart;
+    const int nrows = row_ptr[t + 1] - row_ptr[t];
+    for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) { int r = rows[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
+    std::sort(te.begin(), te.end());
+    te.erase(std::unique(te.begin(), te.end()), te.end());
+    const int nel = (int)te.size();
+    if (nel > max_tile_elems || (long long)nel * (sym ? nslot : dd) > 65535) { P.err = "tile too large"; return; }
+    tile_vertices(m, te, tvert, tv, xy);
+    if (tvert.size() > 65535) { P.err = "tile too large"; return; }
+    roff.push_back(0);
+    for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) {
+      const int r = rows[i], lr = i - row_ptr[t];
+      rstart.push_back(pat.rowptr[r]);
+      row_pairs(m, pat, r, ps);
+      for (size_t k = 0; k < ps.size(); k++) {
+        if (k == 0 || ps[k].first != ps[k - 1].first) { soff.push_back((uint16_t)src.size()); lrow1.push_back((uint8_t)lr); lrow2.push_back((uint16_t)lr); }
+        int el = (int)(ps[k].second / dd), pq = (int)(ps[k].second % dd);
+        int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
+        src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
       }
-    });
-    for (auto& t : th) t.join();
-  }
-  for (auto& P : parts) if (!P.err.empty()) return P.err;
-  elem_ptr.assign(1, 0); soff_ptr.assign(1, 0); src_ptr.assign(1, 0);
-  elems.clear(); src_off.clear(); src.clear();
-  max_rows = max_elems = max_nnz = max_src = 0;
-  for (auto& P : parts) {
-    for (size_t i = 0; i < P.elem_cnt.size(); i++) {
-      elem_ptr.push_back(elem_ptr.back() + P.elem_cnt[i]);
-      soff_ptr.push_back(soff_ptr.back() + P.soff_cnt[i]);
-      src_ptr.push_back(src_ptr.back() + P.src_cnt[i]);
-      max_elems = std::max(max_elems, P.elem_cnt[i]);
-      max_nnz = std::max<int>(max_nnz, (int)P.soff_cnt[i] - 1);
-      max_src = std::max<int>(max_src, (int)P.src_cnt[i]);
+      if (src.size() > 65535 || soff.size() > 65534) { P.err = "tile too large"; return; }
+      roff.push_back((uint16_t)soff.size());
     }
-    elems.insert(elems.end(), P.elems.begin(), P.elems.end());
-    src_off.insert(src_off.end(), P.soff.begin(), P.soff.end());
-    src.insert(src.end(), P.src.begin(), P.src.end());
-    P = Part();
+    const int nnz_t = (int)soff.size();
+    soff.push_back((uint16_t)src.size());
+    int hdr[8] = {nrows, nel, (int)tvert.size(), nnz_t, (int)src.size(), 0, 0, 0};
+    BlobWriter w(P.blob);
+    w.section(hdr, 8); w.section(rstart); w.section(roff); w.section(te); w.section(tv); w.section(xy);
+    if (lrow16) w.section(lrow2); else w.section(lrow1);
+    w.section(soff); w.section(src);
+    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, nnz_t);
+    P.max_src = std::max(P.max_src, (int)src.size()); P.max_verts = std::max(P.max_verts, (int)tvert.size());
+    P.tot_a += nel;
+  });
+  if (!err.empty()) return err;
+  blob_ptr.assign(1, 0); blob.clear();
+  max_rows = max_elems = max_nnz = max_src = max_verts = 0; max_blob = 0;
+  long long tot = 0;
+  for (auto& P : parts) {
+    for (long long sz : P.sizes) { blob_ptr.push_back(blob_ptr.back() + sz); max_blob = std::max(max_blob, (size_t)sz); }
+    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
+    max_rows = std::max(max_rows, P.max_rows); max_elems = std::max(max_elems, P.max_elems); max_nnz = std::max(max_nnz, P.max_nnz);
+    max_src = std::max(max_src, P.max_src); max_verts = std::max(max_verts, P.max_verts);
+    tot += P.tot_a;
+    P = PartOut();
   }
-  for (int t = 0; t < ntiles; t++) max_rows = std::max(max_rows, row_ptr[t + 1] - row_ptr[t]);
-  elem_redundancy = m.ne > 0 ? (double)elems.size() / m.ne : 0;
+  elem_redundancy = m.ne > 0 ? (double)tot / m.ne : 0;
   return "";
 }
 
 // ------------------------------------------------------------------------------------------------
-std::string AdjTilePlan::build(const HostMesh& m, const ScalarPattern& pat, int EPT, int max_tile_nnz, int nthreads) {
+std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT, int max_tile_nnz, int nthreads) {
   elems_per_tile = EPT;
   const int d = m.d, dd = d * d, nvl = m.dim + 1;
   Morton mc(m);
@@ -240,67 +294,66 @@ std::string AdjTilePlan::build(const HostMesh& m, const ScalarPattern& pat, int 
     return mc.code(c);
   }, order);
   ntiles = (m.ne + EPT - 1) / EPT;
-  elem_ptr.resize(ntiles + 1);
+  std::vector<int> elem_ptr(ntiles + 1);
   for (int t = 0; t <= ntiles; t++) elem_ptr[t] = (int)std::min<long long>((long long)t * EPT, m.ne);
-  elems = order;
+  std::vector<int>& elems = order;
   parallel_for(ntiles, nthreads, [&](long long b, long long e, int) {
     for (long long t = b; t < e; t++) std::sort(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]);
   });
-  struct Part { std::vector<int> rows, row_cnt; std::vector<uint16_t> gidx; std::vector<int> nnz_cnt; std::string err; };
-  int nparts = std::max(1, std::min(nthreads, ntiles));
-  std::vector<Part> parts(nparts);
-  std::vector<long long> pcut(nparts + 1);
-  for (int i = 0; i <= nparts; i++) pcut[i] = (long long)ntiles * i / nparts;
-  {
-    std::vector<std::thread> th;
-    for (int pi = 0; pi < nparts; pi++) th.emplace_back([&, pi] {
-      Part& P = parts[pi];
-      std::vector<int> tr;
-      std::vector<long long> roff;
-      for (long long t = pcut[pi]; t < pcut[pi + 1]; t++) {
-        tr.clear();
-        for (int i = elem_ptr[t]; i < elem_ptr[t + 1]; i++) { const int* ce = &m.conn[(size_t)elems[i] * d]; tr.insert(tr.end(), ce, ce + d); }
-        std::sort(tr.begin(), tr.end());
-        tr.erase(std::unique(tr.begin(), tr.end()), tr.end());
-        roff.assign(tr.size() + 1, 0);
-        for (size_t i = 0; i < tr.size(); i++) roff[i + 1] = roff[i] + (pat.rowptr[tr[i] + 1] - pat.rowptr[tr[i]]);
-        if (roff.back() > max_tile_nnz || roff.back() > 65535) { P.err = "tile too large"; return; }
-        P.row_cnt.push_back((int)tr.size());
-        P.nnz_cnt.push_back((int)roff.back());
-        P.rows.insert(P.rows.end(), tr.begin(), tr.end());
-        for (int i = elem_ptr[t]; i < elem_ptr[t + 1]; i++) {
-          int e = elems[i];
-          const int* ce = &m.conn[(size_t)e * d];
-          for (int p = 0; p < d; p++) {
-            int lr = (int)(std::lower_bound(tr.begin(), tr.end(), ce[p]) - tr.begin());
-            for (int q = 0; q < d; q++) {
-              long long pos = pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]];
-              P.gidx.push_back((uint16_t)(roff[lr] + pos));
-            }
-          }
+  std::vector<PartOut> parts;
+  std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
+    std::vector<int> tr, te(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]), tvert;
+    std::vector<uint16_t> tv, roff, lrow, gidx;
+    std::vector<double> xy;
+    std::vector<long long> rstart;
+    const int nel = (int)te.size();
+    for (int e : te) { const int* ce = &m.conn[(size_t)e * d]; tr.insert(tr.end(), ce, ce + d); }
+    std::sort(tr.begin(), tr.end());
+    tr.erase(std::unique(tr.begin(), tr.end()), tr.end());
+    const int nrows = (int)tr.size();
+    long long acc = 0;
+    roff.push_back(0);
+    for (int lr = 0; lr < nrows; lr++) {
+      const long long rs = pat.rowptr[tr[lr]], len = pat.rowptr[tr[lr] + 1] - rs;
+      rstart.push_back(rs);
+      acc += len;
+      if (acc > max_tile_nnz || acc > 65535 || nrows > 65535) { P.err = "tile too large"; return; }
+      for (long long j = 0; j < len; j++) lrow.push_back((uint16_t)lr);
+      roff.push_back((uint16_t)acc);
+    }
+    tile_vertices(m, te, tvert, tv, xy);
+    gidx.resize((size_t)dd * nel);
+    for (int le = 0; le < nel; le++) {
+      const int e = te[le];
+      const int* ce = &m.conn[(size_t)e * d];
+      for (int p = 0; p < d; p++) {
+        const int lr = (int)(std::lower_bound(tr.begin(), tr.end(), ce[p]) - tr.begin());
+        for (int q = 0; q < d; q++) {
+          const long long pos = (long long)pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]];
+          gidx[(size_t)(p * d + q) * nel + le] = (uint16_t)(roff[lr] + pos);
         }
       }
-    });
-    for (auto& t : th) t.join();
-  }
-  for (auto& P : parts) if (!P.err.empty()) return P.err;
-  row_ptr.assign(1, 0); gidx_ptr.assign(1, 0);
-  rows.clear(); gidx.clear();
-  max_rows = max_elems = max_nnz = 0;
-  int t = 0;
-  for (auto& P : parts) {
-    for (size_t i = 0; i < P.row_cnt.size(); i++, t++) {
-      row_ptr.push_back(row_ptr.back() + P.row_cnt[i]);
-      gidx_ptr.push_back(gidx_ptr.back() + (long long)(elem_ptr[t + 1] - elem_ptr[t]) * dd);
-      max_rows = std::max(max_rows, P.row_cnt[i]);
-      max_nnz = std::max(max_nnz, P.nnz_cnt[i]);
-      max_elems = std::max(max_elems, elem_ptr[t + 1] - elem_ptr[t]);
     }
-    rows.insert(rows.end(), P.rows.begin(), P.rows.end());
-    gidx.insert(gidx.end(), P.gidx.begin(), P.gidx.end());
-    P = Part();
+    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)acc, 0, 0, 0, 0};
+    BlobWriter w(P.blob);
+    w.section(hdr, 8); w.section(rstart); w.section(roff); w.section(te); w.section(tv); w.section(xy); w.section(lrow); w.section(gidx);
+    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)acc);
+    P.max_verts = std::max(P.max_verts, (int)tvert.size());
+    P.tot_a += nrows;
+  });
+  if (!err.empty()) return err;
+  blob_ptr.assign(1, 0); blob.clear();
+  max_rows = max_elems = max_nnz = max_verts = 0; max_blob = 0;
+  long long tot = 0;
+  for (auto& P : parts) {
+    for (long long sz : P.sizes) { blob_ptr.push_back(blob_ptr.back() + sz); max_blob = std::max(max_blob, (size_t)sz); }
+    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
+    max_rows = std::max(max_rows, P.max_rows); max_elems = std::max(max_elems, P.max_elems); max_nnz = std::max(max_nnz, P.max_nnz);
+    max_verts = std::max(max_verts, P.max_verts);
+    tot += P.tot_a;
+    P = PartOut();
   }
-  row_redundancy = pat.n > 0 ? (double)rows.size() / pat.n : 0;
+  row_redundancy = pat.n > 0 ? (double)tot / pat.n : 0;
   return "";
 }
 

@@ -7,9 +7,14 @@
 //    reference's component-blocked dof layout (deps/MFEM/ComputeFemStiffnessMatrixMfem/
 //    ComputeFemStiffnessMatrixMfem.h:31-34) entry (r + a*n, c + b*n) lives at
 //        nc * (a * nnz + rowptr[r]) + b * rowlen(r) + j,        j = position of c in row r.
-//  * TilePlan — partition of the rows into spatially compact tiles (Morton order of the dof positions);
-//    a CTA computes the local matrices of every element touching its rows into shared memory and then
+//  * FwdTiles — partition of the rows into spatially compact tiles (Morton order of the dof positions).
+//    A CTA evaluates the local matrices of every element touching its rows into shared memory, then
 //    each CSR entry gathers its contributions in a fixed order: no atomics, no global intermediate.
+//  * AdjTiles — partition of the ELEMENTS into compact tiles; a CTA stages the CSR rows its elements
+//    touch (coalesced) and each element gathers its upstream gradients from shared memory.
+//
+// Every tile's mesh-static data (index lists AND the coordinates of the vertices it needs) is packed
+// into ONE contiguous, 16-byte aligned blob so that a single TMA bulk copy brings it on chip.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -31,30 +36,45 @@ struct ScalarPattern {
   std::string build(const HostMesh& m, int nthreads);
 };
 
-struct TilePlan {
-  int ntiles = 0;
-  int rows_per_tile = 0;
-  int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0;
-  std::vector<int> row_ptr, rows;           // ntiles+1 ; tile rows (global dof ids, ascending inside a tile)
-  std::vector<int> elem_ptr, elems;         // ntiles+1 ; elements a tile evaluates (ascending)
-  std::vector<long long> soff_ptr;          // ntiles+1 ; offsets into src_off (tile nnz + 1 entries per tile)
-  std::vector<uint16_t> src_off;            // per tile-nnz start into the tile's source list
-  std::vector<long long> src_ptr;           // ntiles+1 ; offsets into src
-  std::vector<uint16_t> src;                // local_elem * d*d + p*d + q
-  double elem_redundancy = 0;               // sum(tile elems) / ne
-  std::string build(const HostMesh& m, const ScalarPattern& pat, int rows_per_tile, int max_tile_elems, int nthreads);
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ---- forward tile blob -----------------------------------------------------------------------------
+// sections, each starting on a 16-byte boundary, in this order:
+//   hdr    int32[8]            {nrows, nel, nvt, nnz, nsrc, 0, 0, 0}
+//   rstart int64[nrows]        CSR offset of the first entry of each tile row (scalar pattern)
+//   roff   uint16[nrows+1]     exclusive prefix of the row lengths inside the tile
+//   elems  int32[nel]          global element ids evaluated by the tile (ascending) — coefficient index
+//   tv     uint16[nvl*nel]     tile-local vertex ids, k-major (tv[k*nel+le]), post orientation fix
+//   xy     double[dim*nvt]     coordinates of the tile-local vertices
+//   lrow   uint8|uint16[nnz]   tile row of every tile entry (uint8 when max rows per tile <= 256)
+//   soff   uint16[nnz+1]       start of every entry's source list
+//   src    uint16[nsrc]        scalar plans (sym=1): shared-memory index  sym(p,q)*nel + le  of a local-matrix
+//                              value, sym(p,q) = index in the packed upper triangle; vector plans: le*d*d + p*d + q
+struct FwdTiles {
+  int ntiles = 0, rows_per_tile = 0, sym = 1, lrow16 = 0;
+  int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0;
+  size_t max_blob = 0;
+  std::vector<long long> blob_ptr;    // ntiles+1 byte offsets
+  std::vector<uint8_t> blob;
+  double elem_redundancy = 0;
+  std::string build(const HostMesh& m, const ScalarPattern& pat, int rows_per_tile, int max_tile_elems, int sym, int nthreads);
 };
 
-// adjoint tiles: a CTA owns a compact set of ELEMENTS, stages every CSR row they touch in shared memory
-// (coalesced), and each element gathers its d*d upstream gradients from there.
-struct AdjTilePlan {
-  int ntiles = 0;
-  int elems_per_tile = 0;
-  int max_rows = 0, max_elems = 0, max_nnz = 0;
-  std::vector<int> elem_ptr, elems;         // owned elements
-  std::vector<int> row_ptr, rows;           // rows staged by the tile (ascending)
-  std::vector<long long> gidx_ptr;          // ntiles+1 ; offsets into gidx (d*d per owned element)
-  std::vector<uint16_t> gidx;               // position of slot (e,p,q) inside the tile's staged nnz
+// ---- adjoint tile blob -----------------------------------------------------------------------------
+//   hdr    int32[8]            {nrows, nel, nvt, nnz, 0, 0, 0, 0}
+//   rstart int64[nrows]        CSR offset of each staged row
+//   roff   uint16[nrows+1]
+//   elems  int32[nel]          owned elements (ascending)
+//   tv     uint16[nvl*nel]
+//   xy     double[dim*nvt]
+//   lrow   uint16[nnz]         staged row of every staged entry
+//   gidx   uint16[d*d*nel]     pq-major: position of slot (le,p,q) inside the staged entries
+struct AdjTiles {
+  int ntiles = 0, elems_per_tile = 0;
+  int max_rows = 0, max_elems = 0, max_nnz = 0, max_verts = 0;
+  size_t max_blob = 0;
+  std::vector<long long> blob_ptr;
+  std::vector<uint8_t> blob;
   double row_redundancy = 0;
   std::string build(const HostMesh& m, const ScalarPattern& pat, int elems_per_tile, int max_tile_nnz, int nthreads);
 };

@@ -131,6 +131,8 @@ def main():
     ap.add_argument("--rows-per-tile", type=int, default=0)
     ap.add_argument("--elems-per-tile", type=int, default=0)
     ap.add_argument("--adjoint-tiled", type=int, default=1)
+    ap.add_argument("--tile-threads", type=int, default=0)
+    ap.add_argument("--smem-budget", type=int, default=0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -165,6 +167,10 @@ def main():
     if args.elems_per_tile:
         mesh.set_option("elems_per_tile", args.elems_per_tile)
     mesh.set_option("adjoint_tiled", args.adjoint_tiled)
+    if args.tile_threads:
+        mesh.set_option("tile_threads", args.tile_threads)
+    if args.smem_budget:
+        mesh.set_option("smem_budget", args.smem_budget)
     rowptr, colind = mesh.csr_pattern(1)
     nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
     xy = A.gauss_nodes(mesh)

@@ -109,7 +109,7 @@ int adfem_mesh_element_to_vertices(const adfem_mesh* m, long long* elems);    /*
 int adfem_mesh_gauss(const adfem_mesh* m, double* xyz);                       /* dim blocks of ngauss (column-major) */
 int adfem_mesh_gauss_weights(const adfem_mesh* m, double* w);
 int adfem_mesh_measure(const adfem_mesh* m, double* a);                       /* Heron area (2-D) / volume (3-D) */
-int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads" */
+int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads", "smem_budget", "tile_threads", "area_formula_csr", "area_formula_coo" */
 
 /* Mesh-static symbolic phase (what Julia's sparse() / TF's sparse ops redo on every call downstream of the
  * reference's COO, src/MFEM/MCore.jl:118-119).  ncomp = 1: scalar operators, n = ndof.  ncomp = dim: the
@@ -120,9 +120,9 @@ int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr /* n+1 */, int
 int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz /* ne*d*d, host out */);
 
 /* Inspection of the mesh-static tile plans (ADFEM_HOST_ONLY handles only; used by the CPU unit tests that
- * replay a plan against the oracle).  which_plan 0 = forward row tiles {0 row_ptr:int32, 1 rows:int32,
- * 2 elem_ptr:int32, 3 elems:int32, 4 soff_ptr:int64, 5 src_off:uint16, 6 src_ptr:int64, 7 src:uint16},
- * 1 = adjoint element tiles {0 elem_ptr, 1 elems, 2 row_ptr, 3 rows: int32, 4 gidx_ptr:int64, 5 gidx:uint16}.
+ * replay a plan against the oracle).  which_plan 0 = forward row tiles, 1 = adjoint element tiles; array_id 0 =
+ * blob_ptr (int64[ntiles+1] byte offsets), 1 = the concatenated per-tile blobs (bytes; layout documented in
+ * adfem.jl_b200/csrc/plan.h — it is exactly what one TMA bulk copy brings into shared memory per CTA).
  * Returns the element count (and copies when out != NULL), -1 on error. */
 long long adfem_plan_array(adfem_mesh* m, int which_plan, int ncomp, int array_id, void* out);
 

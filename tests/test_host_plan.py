@@ -61,29 +61,91 @@ def test_csr_pattern_bit_exact(oracle, name, degree):
         assert np.array_equal(rowptr_e, rp_e) and np.array_equal(colind_e, ci_e)
 
 
-def _fwd_replay(m, local, ncomp, n_out):
+def a16(x):
+    return (x + 15) & ~15
+
+
+def parse_blob(buf, dim, d, fwd, lrow16):
+    """Decode one tile blob exactly as the kernels do (layout: adfem.jl_b200/csrc/plan.h)."""
+    hdr = np.frombuffer(buf, dtype=np.int32, count=8)
+    nrows, nel, nvt, nnz, nsrc = (int(x) for x in hdr[:5])
+    o = 32
+    out = {"nrows": nrows, "nel": nel, "nvt": nvt, "nnz": nnz, "nsrc": nsrc}
+
+    def take(dtype, count):
+        nonlocal o
+        a = np.frombuffer(buf, dtype=dtype, count=count, offset=o)
+        o += a16(count * np.dtype(dtype).itemsize)
+        return a
+    out["rstart"] = take(np.int64, nrows)
+    out["roff"] = take(np.uint16, nrows + 1)
+    out["elems"] = take(np.int32, nel)
+    out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
+    out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
+    if fwd:
+        out["lrow"] = take(np.uint16 if lrow16 else np.uint8, nnz)
+        out["soff"] = take(np.uint16, nnz + 1)
+        out["src"] = take(np.uint16, nsrc)
+    else:
+        out["lrow"] = take(np.uint16, nnz)
+        out["gidx"] = take(np.uint16, d * d * nel).reshape(d * d, nel)
+    assert o == len(buf)
+    return out
+
+
+def tiles_of(m, which, ncomp, rows_per_tile=None):
+    ptr = m.plan_array(which, ncomp, 0, np.int64)
+    blob = m.plan_array(which, ncomp, 1, np.uint8).tobytes()
+    tiles = []
+    for lrow16 in (False, True):      # the planner may shrink the requested tile; the row-id width follows the final size
+        try:
+            tiles = [parse_blob(blob[ptr[t]:ptr[t + 1]], m.dim, m.elem_ndof, which == 0, lrow16) for t in range(len(ptr) - 1)]
+            break
+        except (AssertionError, ValueError):
+            continue
+    assert len(tiles) == len(ptr) - 1
+    for t in range(len(ptr) - 1):
+        assert ptr[t] % 16 == 0 and (ptr[t + 1] - ptr[t]) % 16 == 0          # TMA bulk copy alignment rules
+    assert max(T["nrows"] for T in tiles) <= (65535 if lrow16 else 256)
+    return tiles
+
+
+def _check_tile_geometry(m, T):
+    """tv/xy must reproduce the (orientation-fixed) vertex coordinates of the tile's elements."""
+    assert np.array_equal(T["xy"][T["tv"].T], m.nodes[m.elems[T["elems"]]])
+
+
+def _fwd_replay(m, local, ncomp, n_out, R):
     """local: [nelem, Dt*Dt] pre-summed local matrices. Mirrors k_tile_fwd."""
     d = m.elem_ndof
     dd, Dt = d * d, ncomp * d
     rowptr, _ = m.csr_pattern(1)
     nnz_s = rowptr[-1]
-    row_ptr = m.plan_array(0, ncomp, 0, np.int32); rows = m.plan_array(0, ncomp, 1, np.int32)
-    elem_ptr = m.plan_array(0, ncomp, 2, np.int32); elems = m.plan_array(0, ncomp, 3, np.int32)
-    soff_ptr = m.plan_array(0, ncomp, 4, np.int64); src_off = m.plan_array(0, ncomp, 5, np.uint16)
-    src_ptr = m.plan_array(0, ncomp, 6, np.int64); src = m.plan_array(0, ncomp, 7, np.uint16)
+    sym = {}
+    i = 0
+    for p in range(d):
+        for q in range(p, d):
+            sym[i] = (p, q)
+            i += 1
     vals = np.full(n_out, np.nan)
     written = np.zeros(n_out, dtype=np.int32)
-    for t in range(len(row_ptr) - 1):
-        trows = rows[row_ptr[t]:row_ptr[t + 1]]
-        tel = elems[elem_ptr[t]:elem_ptr[t + 1]]
-        loc = local[tel]                                      # [nel, S]
-        so = src_off[soff_ptr[t]:soff_ptr[t + 1]].astype(np.int64)
-        sr = src[src_ptr[t]:src_ptr[t + 1]].astype(np.int64)
-        i = 0
-        for r in trows:
-            rs, ln = rowptr[r], rowptr[r + 1] - rowptr[r]
-            for j in range(ln):
-                cs = sr[so[i]:so[i + 1]]
+    for T in tiles_of(m, 0, ncomp, R):
+        _check_tile_geometry(m, T)
+        nel = T["nel"]
+        loc = local[T["elems"]]                               # [nel, S]
+        for i in range(T["nnz"]):
+            lr = int(T["lrow"][i]); j = i - int(T["roff"][lr]); ln = int(T["roff"][lr + 1]) - int(T["roff"][lr]); rs = int(T["rstart"][lr])
+            cs = T["src"][int(T["soff"][i]):int(T["soff"][i + 1])].astype(np.int64)
+            if ncomp == 1:
+                v = 0.0
+                for c in cs:
+                    s, le = divmod(int(c), nel)
+                    p, q = sym[s]
+                    assert abs(loc[le, p * d + q] - loc[le, q * d + p]) <= 1e-14 * abs(loc[le]).max()
+                    v += loc[le, p * d + q]
+                vals[rs + j] = v
+                written[rs + j] += 1
+            else:
                 le, pq = cs // dd, cs % dd
                 p, q = pq // d, pq % d
                 for a in range(ncomp):
@@ -94,8 +156,6 @@ def _fwd_replay(m, local, ncomp, n_out):
                         dest = ncomp * (a * nnz_s + rs) + b * ln + j
                         vals[dest] = v
                         written[dest] += 1
-                i += 1
-        assert i == len(so) - 1
     assert (written == 1).all()                                # every CSR entry is produced exactly once
     return vals
 
@@ -105,17 +165,18 @@ def _close(a, b, rel=1e-12):
     return np.all(np.abs(a - b) <= rel * np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3))
 
 
+@pytest.mark.parametrize("R", [24, 300])
 @pytest.mark.parametrize("name,degree", CASES)
-def test_forward_plan_replay_scalar(oracle, name, degree):
+def test_forward_plan_replay_scalar(oracle, name, degree, R):
     m, o = make(name, degree, oracle)
-    m.set_option("rows_per_tile", 24)                          # several tiles even on these small meshes
+    m.set_option("rows_per_tile", R)                           # several tiles even on these small meshes
     rng = np.random.default_rng(0)
     kappa = rng.random(o.ngauss) + 0.5
     ind, vv = o.laplace_fwd(kappa)
     rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
     dd = o.elem_ndof ** 2
     local = vv.reshape(o.nelem, o.g, dd).sum(1)
-    vals = _fwd_replay(m, local, 1, len(ref))
+    vals = _fwd_replay(m, local, 1, len(ref), R)
     assert _close(vals, ref)
 
 
@@ -130,7 +191,7 @@ def test_forward_plan_replay_elasticity(oracle, name, degree):
     rp, ci, ref = oracle.canonical_csr(ind, vv, m.dim * o.ndof)
     Dt = m.dim * o.elem_ndof
     local = vv.reshape(o.nelem, o.g, Dt * Dt).sum(1)
-    vals = _fwd_replay(m, local, m.dim, len(ref))
+    vals = _fwd_replay(m, local, m.dim, len(ref), 16)
     assert _close(vals, ref)
 
 
@@ -144,16 +205,15 @@ def test_adjoint_plan_replay(oracle, name, degree):
     rowptr, _ = m.csr_pattern(1)
     s2n = m.slot_to_nnz().reshape(o.nelem, dd)
     dvals = np.random.default_rng(2).standard_normal(rowptr[-1])
-    elem_ptr = m.plan_array(1, 1, 0, np.int32); elems = m.plan_array(1, 1, 1, np.int32)
-    row_ptr = m.plan_array(1, 1, 2, np.int32); rows = m.plan_array(1, 1, 3, np.int32)
-    gidx_ptr = m.plan_array(1, 1, 4, np.int64); gidx = m.plan_array(1, 1, 5, np.uint16)
     seen = np.zeros(o.nelem, dtype=np.int32)
-    for t in range(len(elem_ptr) - 1):
-        trows = rows[row_ptr[t]:row_ptr[t + 1]]
-        staged = np.concatenate([dvals[rowptr[r]:rowptr[r + 1]] for r in trows])
-        tel = elems[elem_ptr[t]:elem_ptr[t + 1]]
-        gi = gidx[gidx_ptr[t]:gidx_ptr[t + 1]].reshape(len(tel), dd)
-        assert np.array_equal(staged[gi], dvals[s2n[tel]])
+    for T in tiles_of(m, 1, 1):
+        _check_tile_geometry(m, T)
+        staged = np.concatenate([dvals[rs:rs + ln] for rs, ln in zip(T["rstart"], np.diff(T["roff"].astype(int)))])
+        assert len(staged) == T["nnz"]
+        lr = T["lrow"].astype(int)
+        assert np.array_equal(staged, dvals[T["rstart"][lr] + np.arange(T["nnz"]) - T["roff"][lr].astype(int)])   # the kernel's staging loop
+        tel = T["elems"]
+        assert np.array_equal(staged[T["gidx"].T.astype(int)], dvals[s2n[tel]])
         seen[tel] += 1
     assert (seen == 1).all()
 
