@@ -149,7 +149,7 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (!m->host_only) {
     CU_TRY(upload(P->blob_ptr, tp.blob_ptr));
     CU_TRY(upload(P->blob, tp.blob));
-    P->dev = DevTiles{tp.ntiles, tp.sym, tp.lrow16, (unsigned)align16(tp.max_blob), tp.max_elems, tp.max_nnz, P->blob_ptr.p, P->blob.p};
+    P->dev = DevTiles{tp.ntiles, tp.sym, (unsigned)align16(tp.max_blob), tp.max_elems, tp.max_nnz, P->blob_ptr.p, P->blob.p};
     std::vector<uint8_t>().swap(tp.blob);
   }
   *out = P.get();
@@ -186,7 +186,7 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
   if (!m->host_only) {
     CU_TRY(upload(P->blob_ptr, ap.blob_ptr));
     CU_TRY(upload(P->blob, ap.blob));
-    P->dev = DevTiles{ap.ntiles, 0, 1, (unsigned)align16(ap.max_blob), ap.max_elems, ap.max_nnz, P->blob_ptr.p, P->blob.p};
+    P->dev = DevTiles{ap.ntiles, 0, (unsigned)align16(ap.max_blob), ap.max_elems, ap.max_nnz, P->blob_ptr.p, P->blob.p};
     std::vector<uint8_t>().swap(ap.blob);
   }
   *out = P.get();

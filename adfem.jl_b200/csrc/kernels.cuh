@@ -20,7 +20,7 @@ struct DevPattern {
   const uint32_t* slot_nnz;       // [d*d][ne] struct-of-arrays
 };
 struct DevTiles {                  // forward (FwdTiles) or adjoint (AdjTiles) blobs on the device
-  int ntiles, sym, lrow16;
+  int ntiles, sym;
   unsigned max_blob;               // bytes, multiple of 16
   int max_elems, max_nnz;
   const long long* blob_ptr;
@@ -276,6 +276,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 __device__ __forceinline__ unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
+// asynchronous 8-byte global -> shared copy (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Local element matrix summed over Gauss points, handed to `put(slot, value)`.
 //   scalar ops (symmetric): slot = index in the packed upper triangle (p <= q, row-major)
@@ -383,19 +389,27 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(smem, tp.blob + b0, bytes, &mbar); }
   mbar_wait(&mbar, 0);
   const int* hdr = reinterpret_cast<const int*>(smem);
-  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
+  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3], nsrc = hdr[4], ncls = hdr[5], ent32 = hdr[6];
   unsigned o = 32;
-  const long long* rstart = reinterpret_cast<const long long*>(smem + o); o += a16(8u * nrows);
-  const unsigned short* roff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nrows + 1));
+  const unsigned* rstart = reinterpret_cast<const unsigned*>(smem + o); o += a16(4u * nrows);
+  const unsigned short* rlen = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * nrows);
   const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
   const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
   const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
-  const unsigned char* lrow8 = smem + o;
-  const unsigned short* lrow16 = reinterpret_cast<const unsigned short*>(smem + o); o += a16((tp.lrow16 ? 2u : 1u) * nnz_t);
-  const unsigned short* soff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nnz_t + 1));
+  const int* cls = reinterpret_cast<const int*>(smem + o); o += a16(16u * ncls);
+  const unsigned char* ent = smem + o; o += a16((ent32 ? 4u : 2u) * nnz_t);
   const unsigned short* src = reinterpret_cast<const unsigned short*>(smem + o);
+  (void)nsrc; (void)rlen;
   double* loc = reinterpret_cast<double*>(smem + tp.max_blob);
 
+  {  // warm the coefficient lines of all of this thread's elements before the first use (non-blocking)
+    const int cpe = m.g * (OP == OP_STIFFNESS ? Voigt<DIM>::NS * Voigt<DIM>::NS : 1);
+    for (int le = tid; le < nel; le += nth) {
+      const double* p = coef + (size_t)elems[le] * cpe;
+      for (int b = 0; b < cpe; b += 16) prefetch_l1(p + b);
+      prefetch_l1(p + cpe - 1);
+    }
+  }
   for (int le = tid; le < nel; le += nth) {
     Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);
     local_matrix<DIM, DEG, OP>(m, G, elems[le], coef, [&](int slot, double v) {
@@ -403,30 +417,60 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     });
   }
   __syncthreads();
-  for (int i = tid; i < nnz_t; i += nth) {
-    const int lr = tp.lrow16 ? (int)lrow16[i] : (int)lrow8[i];
-    const int j = i - roff[lr];
-    const int sb = soff[i], se = soff[i + 1];
+  for (int c = 0; c < ncls; c++) {
+    const int cnt = cls[4 * c], n = cls[4 * c + 1];
+    const unsigned short* sc = src + cls[4 * c + 2];
+    const int e0 = cls[4 * c + 3];
+    auto dest = [&](int i, int& lr, int& j) {
+      if (ent32) { const unsigned v = reinterpret_cast<const unsigned*>(ent)[e0 + i]; lr = v & 0xffffu; j = v >> 16; }
+      else { const unsigned v = reinterpret_cast<const unsigned short*>(ent)[e0 + i]; lr = v & 0xffu; j = v >> 8; }
+    };
     if (NC == 1) {
-      double v = 0.0;
-      for (int s = sb; s < se; s++) v += loc[src[s]];
-      vals[rstart[lr] + j] = v;
+      // every entry of the class has `cnt` sources: the same unrolled gather in every lane
+#define ADFEM_GATHER_CLASS(C)                                                              \
+      for (int i = tid; i < n; i += nth) {                                                 \
+        double v = 0.0;                                                                    \
+        _Pragma("unroll") for (int k = 0; k < C; k++) v += loc[sc[k * n + i]];           \
+        int lr, j; dest(i, lr, j);                                                         \
+        vals[(size_t)rstart[lr] + j] = v;                                                  \
+      }
+      switch (cnt) {
+        case 1: ADFEM_GATHER_CLASS(1) break;
+        case 2: ADFEM_GATHER_CLASS(2) break;
+        case 3: ADFEM_GATHER_CLASS(3) break;
+        case 4: ADFEM_GATHER_CLASS(4) break;
+        case 5: ADFEM_GATHER_CLASS(5) break;
+        case 6: ADFEM_GATHER_CLASS(6) break;
+        case 7: ADFEM_GATHER_CLASS(7) break;
+        case 8: ADFEM_GATHER_CLASS(8) break;
+        default:
+          for (int i = tid; i < n; i += nth) {
+            double v = 0.0;
+            for (int k = 0; k < cnt; k++) v += loc[sc[k * n + i]];
+            int lr, j; dest(i, lr, j);
+            vals[(size_t)rstart[lr] + j] = v;
+          }
+      }
+#undef ADFEM_GATHER_CLASS
     } else {
-      double v[NC * NC];
+      for (int i = tid; i < n; i += nth) {
+        double v[NC * NC];
 #pragma unroll
-      for (int ab = 0; ab < NC * NC; ab++) v[ab] = 0.0;
-      for (int s = sb; s < se; s++) {
-        const int c = src[s], le = c / dd, pq = c - le * dd, p = pq / D, q = pq - p * D;
+        for (int ab = 0; ab < NC * NC; ab++) v[ab] = 0.0;
+        for (int k = 0; k < cnt; k++) {
+          const int cc = sc[k * n + i], le = cc / dd, pq = cc - le * dd, p = pq / D, q = pq - p * D;
+#pragma unroll
+          for (int a = 0; a < NC; a++)
+#pragma unroll
+            for (int b = 0; b < NC; b++) v[a * NC + b] += loc[((a * D + p) * Dt + b * D + q) * nel + le];
+        }
+        int lr, j; dest(i, lr, j);
+        const long long len = rlen[lr], rs = rstart[lr];
 #pragma unroll
         for (int a = 0; a < NC; a++)
 #pragma unroll
-          for (int b = 0; b < NC; b++) v[a * NC + b] += loc[((a * D + p) * Dt + b * D + q) * nel + le];
+          for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
       }
-      const long long len = roff[lr + 1] - roff[lr], rs = rstart[lr];
-#pragma unroll
-      for (int a = 0; a < NC; a++)
-#pragma unroll
-        for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
     }
   }
 }
@@ -551,7 +595,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
   const int* hdr = reinterpret_cast<const int*>(smem);
   const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
   unsigned o = 32;
-  const long long* rstart = reinterpret_cast<const long long*>(smem + o); o += a16(8u * nrows);
+  const unsigned* rstart = reinterpret_cast<const unsigned*>(smem + o); o += a16(4u * nrows);
   const unsigned short* roff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nrows + 1));
   const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
   const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
@@ -560,17 +604,20 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
   const unsigned short* gidx = reinterpret_cast<const unsigned short*>(smem + o);
   double* sd = reinterpret_cast<double*>(smem + ap.max_blob);                       // NC*NC x nnz_t staged upstream gradients
 
+  // stage the upstream gradients with asynchronous 8-byte copies (LDGSTS): every thread fires all of its
+  // copies back to back, nothing waits on a register
   for (int i = tid; i < nnz_t; i += nth) {
     const int lr = lrow[i], j = i - roff[lr];
-    if (NC == 1) sd[i] = dvals[rstart[lr] + j];
+    if (NC == 1) cp_async8(sd + i, dvals + ((size_t)rstart[lr] + j));
     else {
       const long long len = roff[lr + 1] - roff[lr], rs = rstart[lr];
 #pragma unroll
       for (int a = 0; a < NC; a++)
 #pragma unroll
-        for (int b = 0; b < NC; b++) sd[(a * NC + b) * nnz_t + i] = dvals[NC * (a * nnz_s + rs) + b * len + j];
+        for (int b = 0; b < NC; b++) cp_async8(sd + (a * NC + b) * nnz_t + i, dvals + (NC * (a * nnz_s + rs) + b * len + j));
     }
   }
+  cp_async_wait_all();
   __syncthreads();
   for (int le = tid; le < nel; le += nth) {
     Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);

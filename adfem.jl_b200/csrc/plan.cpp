@@ -210,7 +210,6 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   rows_per_tile = R; sym = sym_;
   const int d = m.d, dd = d * d, n = pat.n;
   const int nslot = sym ? d * (d + 1) / 2 : dd;
-  lrow16 = R > 256;
   Morton mc(m);
   std::vector<int> order;
   morton_order(n, nthreads, [&](long long i) { double x[3]; m.dof_position((int)i, x); return mc.code(x); }, order);
@@ -221,6 +220,10 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   parallel_for(ntiles, nthreads, [&](long long b, long long e, int) {
     for (long long t = b; t < e; t++) std::sort(rows.begin() + row_ptr[t], rows.begin() + row_ptr[t + 1]);
   });
+  // entries are (row, position) packed into 16 bits when both fit in a byte, else 32 bits
+  int max_len = 0;
+  for (int r = 0; r < n; r++) max_len = std::max<int>(max_len, (int)(pat.rowptr[r + 1] - pat.rowptr[r]));
+  ent32 = (R > 256 || max_len > 256) ? 1 : 0;
   std::vector<int> symidx(dd);
   for (int p = 0; p < d; p++) for (int q = 0; q < d; q++) { int a = std::min(p, q), b = std::max(p, q); symidx[p * d + q] = a * d - a * (a - 1) / 2 + (b - a); }
 
@@ -228,10 +231,11 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
     std::vector<ColSlot> ps;
     std::vector<int> te, tvert;
-    std::vector<uint16_t> tv, roff, soff, src, lrow2;
-    std::vector<uint8_t> lrow1;
+    std::vector<uint16_t> tv, rlen;
     std::vector<double> xy;
-    std::vector<long long> rstart;
+    std::vector<uint32_t> rstart;
+    struct Entry { int lr, j; std::vector<uint16_t> src; };
+    std::vector<Entry> ents;
     const int nrows = row_ptr[t + 1] - row_ptr[t];
     for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) { int r = rows[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
     std::sort(te.begin(), te.end());
@@ -240,28 +244,48 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     if (nel > max_tile_elems || (long long)nel * (sym ? nslot : dd) > 65535) { P.err = "tile too large"; return; }
     tile_vertices(m, te, tvert, tv, xy);
     if (tvert.size() > 65535) { P.err = "tile too large"; return; }
-    roff.push_back(0);
+    size_t nsrc = 0;
     for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) {
       const int r = rows[i], lr = i - row_ptr[t];
-      rstart.push_back(pat.rowptr[r]);
+      rstart.push_back((uint32_t)pat.rowptr[r]);
+      rlen.push_back((uint16_t)(pat.rowptr[r + 1] - pat.rowptr[r]));
       row_pairs(m, pat, r, ps);
+      int j = -1;
       for (size_t k = 0; k < ps.size(); k++) {
-        if (k == 0 || ps[k].first != ps[k - 1].first) { soff.push_back((uint16_t)src.size()); lrow1.push_back((uint8_t)lr); lrow2.push_back((uint16_t)lr); }
+        if (k == 0 || ps[k].first != ps[k - 1].first) { j++; ents.push_back(Entry{lr, j, {}}); }
         int el = (int)(ps[k].second / dd), pq = (int)(ps[k].second % dd);
         int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
-        src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
+        ents.back().src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
+        nsrc++;
       }
-      if (src.size() > 65535 || soff.size() > 65534) { P.err = "tile too large"; return; }
-      roff.push_back((uint16_t)soff.size());
     }
-    const int nnz_t = (int)soff.size();
-    soff.push_back((uint16_t)src.size());
-    int hdr[8] = {nrows, nel, (int)tvert.size(), nnz_t, (int)src.size(), 0, 0, 0};
+    if (nsrc > 65535 * 4 || ents.size() > 65535) { P.err = "tile too large"; return; }
+    // classes of equal source count, ascending; original entry order kept inside a class (coalesced stores)
+    std::vector<int> ord(ents.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return ents[a].src.size() < ents[b].src.size(); });
+    std::vector<int> cls;            // {count, entries, src offset, entry offset} per class
+    std::vector<uint16_t> src, ent16;
+    std::vector<uint32_t> ent32v;
+    for (size_t a = 0; a < ord.size();) {
+      size_t b = a;
+      const int cnt = (int)ents[ord[a]].src.size();
+      while (b < ord.size() && (int)ents[ord[b]].src.size() == cnt) b++;
+      const int nc = (int)(b - a);
+      cls.push_back(cnt); cls.push_back(nc); cls.push_back((int)src.size()); cls.push_back((int)a);
+      for (int k = 0; k < cnt; k++) for (size_t i = a; i < b; i++) src.push_back(ents[ord[i]].src[k]);
+      for (size_t i = a; i < b; i++) {
+        const Entry& E = ents[ord[i]];
+        if (ent32) ent32v.push_back((uint32_t)E.lr | (uint32_t)E.j << 16); else ent16.push_back((uint16_t)(E.lr | E.j << 8));
+      }
+      a = b;
+    }
+    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)ents.size(), (int)src.size(), (int)cls.size() / 4, ent32, 0};
     BlobWriter w(P.blob);
-    w.section(hdr, 8); w.section(rstart); w.section(roff); w.section(te); w.section(tv); w.section(xy);
-    if (lrow16) w.section(lrow2); else w.section(lrow1);
-    w.section(soff); w.section(src);
-    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, nnz_t);
+    w.section(hdr, 8); w.section(rstart); w.section(rlen); w.section(te); w.section(tv); w.section(xy); w.section(cls);
+    if (ent32) w.section(ent32v); else w.section(ent16);
+    w.section(src);
+    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)ents.size());
     P.max_src = std::max(P.max_src, (int)src.size()); P.max_verts = std::max(P.max_verts, (int)tvert.size());
     P.tot_a += nel;
   });
@@ -305,7 +329,7 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     std::vector<int> tr, te(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]), tvert;
     std::vector<uint16_t> tv, roff, lrow, gidx;
     std::vector<double> xy;
-    std::vector<long long> rstart;
+    std::vector<uint32_t> rstart;
     const int nel = (int)te.size();
     for (int e : te) { const int* ce = &m.conn[(size_t)e * d]; tr.insert(tr.end(), ce, ce + d); }
     std::sort(tr.begin(), tr.end());
@@ -315,7 +339,7 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     roff.push_back(0);
     for (int lr = 0; lr < nrows; lr++) {
       const long long rs = pat.rowptr[tr[lr]], len = pat.rowptr[tr[lr] + 1] - rs;
-      rstart.push_back(rs);
+      rstart.push_back((uint32_t)rs);
       acc += len;
       if (acc > max_tile_nnz || acc > 65535 || nrows > 65535) { P.err = "tile too large"; return; }
       for (long long j = 0; j < len; j++) lrow.push_back((uint16_t)lr);

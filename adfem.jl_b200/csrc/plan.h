@@ -40,18 +40,21 @@ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // ---- forward tile blob -----------------------------------------------------------------------------
 // sections, each starting on a 16-byte boundary, in this order:
-//   hdr    int32[8]            {nrows, nel, nvt, nnz, nsrc, 0, 0, 0}
-//   rstart int64[nrows]        CSR offset of the first entry of each tile row (scalar pattern)
-//   roff   uint16[nrows+1]     exclusive prefix of the row lengths inside the tile
+//   hdr    int32[8]            {nrows, nel, nvt, nnz, nsrc, ncls, ent32, 0}
+//   rstart uint32[nrows]       CSR offset of the first entry of each tile row (scalar pattern)
+//   rlen   uint16[nrows]       row lengths
 //   elems  int32[nel]          global element ids evaluated by the tile (ascending) — coefficient index
 //   tv     uint16[nvl*nel]     tile-local vertex ids, k-major (tv[k*nel+le]), post orientation fix
 //   xy     double[dim*nvt]     coordinates of the tile-local vertices
-//   lrow   uint8|uint16[nnz]   tile row of every tile entry (uint8 when max rows per tile <= 256)
-//   soff   uint16[nnz+1]       start of every entry's source list
-//   src    uint16[nsrc]        scalar plans (sym=1): shared-memory index  sym(p,q)*nel + le  of a local-matrix
-//                              value, sym(p,q) = index in the packed upper triangle; vector plans: le*d*d + p*d + q
+//   cls    int32[4*ncls]       entry classes {source count, entries, first source, first entry}: entries with the same
+//                              number of contributions are processed together so that every lane of a warp runs the
+//                              same fully unrolled gather (no divergence); ascending count, tile order inside a class
+//   ent    uint16|uint32[nnz]  destination of each entry in class order: tile row | position-in-row << 8 (or << 16)
+//   src    uint16[nsrc]        class-major, k-major inside a class: src[first + k*entries + i].  Scalar plans (sym=1):
+//                              shared-memory index sym(p,q)*nel + le of a local-matrix value (packed upper triangle);
+//                              vector plans: le*d*d + p*d + q
 struct FwdTiles {
-  int ntiles = 0, rows_per_tile = 0, sym = 1, lrow16 = 0;
+  int ntiles = 0, rows_per_tile = 0, sym = 1, ent32 = 0;
   int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0;
   size_t max_blob = 0;
   std::vector<long long> blob_ptr;    // ntiles+1 byte offsets
@@ -62,7 +65,7 @@ struct FwdTiles {
 
 // ---- adjoint tile blob -----------------------------------------------------------------------------
 //   hdr    int32[8]            {nrows, nel, nvt, nnz, 0, 0, 0, 0}
-//   rstart int64[nrows]        CSR offset of each staged row
+//   rstart uint32[nrows]       CSR offset of each staged row
 //   roff   uint16[nrows+1]
 //   elems  int32[nel]          owned elements (ascending)
 //   tv     uint16[nvl*nel]

@@ -65,10 +65,10 @@ def a16(x):
     return (x + 15) & ~15
 
 
-def parse_blob(buf, dim, d, fwd, lrow16):
+def parse_blob(buf, dim, d, fwd):
     """Decode one tile blob exactly as the kernels do (layout: adfem.jl_b200/csrc/plan.h)."""
     hdr = np.frombuffer(buf, dtype=np.int32, count=8)
-    nrows, nel, nvt, nnz, nsrc = (int(x) for x in hdr[:5])
+    nrows, nel, nvt, nnz, nsrc, ncls, ent32 = (int(x) for x in hdr[:7])
     o = 32
     out = {"nrows": nrows, "nel": nel, "nvt": nvt, "nnz": nnz, "nsrc": nsrc}
 
@@ -77,15 +77,20 @@ def parse_blob(buf, dim, d, fwd, lrow16):
         a = np.frombuffer(buf, dtype=dtype, count=count, offset=o)
         o += a16(count * np.dtype(dtype).itemsize)
         return a
-    out["rstart"] = take(np.int64, nrows)
-    out["roff"] = take(np.uint16, nrows + 1)
+    out["rstart"] = take(np.uint32, nrows).astype(np.int64)
+    if fwd:
+        out["rlen"] = take(np.uint16, nrows).astype(np.int64)
+    else:
+        out["roff"] = take(np.uint16, nrows + 1)
     out["elems"] = take(np.int32, nel)
     out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
     out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
     if fwd:
-        out["lrow"] = take(np.uint16 if lrow16 else np.uint8, nnz)
-        out["soff"] = take(np.uint16, nnz + 1)
-        out["src"] = take(np.uint16, nsrc)
+        out["cls"] = take(np.int32, 4 * ncls).reshape(ncls, 4)
+        e = take(np.uint32 if ent32 else np.uint16, nnz).astype(np.int64)
+        out["ent_lr"], out["ent_j"] = (e & 0xffff, e >> 16) if ent32 else (e & 0xff, e >> 8)
+        out["src"] = take(np.uint16, nsrc).astype(np.int64)
+        assert ent32 or nrows <= 256
     else:
         out["lrow"] = take(np.uint16, nnz)
         out["gidx"] = take(np.uint16, d * d * nel).reshape(d * d, nel)
@@ -93,21 +98,12 @@ def parse_blob(buf, dim, d, fwd, lrow16):
     return out
 
 
-def tiles_of(m, which, ncomp, rows_per_tile=None):
+def tiles_of(m, which, ncomp):
     ptr = m.plan_array(which, ncomp, 0, np.int64)
     blob = m.plan_array(which, ncomp, 1, np.uint8).tobytes()
-    tiles = []
-    for lrow16 in (False, True):      # the planner may shrink the requested tile; the row-id width follows the final size
-        try:
-            tiles = [parse_blob(blob[ptr[t]:ptr[t + 1]], m.dim, m.elem_ndof, which == 0, lrow16) for t in range(len(ptr) - 1)]
-            break
-        except (AssertionError, ValueError):
-            continue
-    assert len(tiles) == len(ptr) - 1
     for t in range(len(ptr) - 1):
         assert ptr[t] % 16 == 0 and (ptr[t + 1] - ptr[t]) % 16 == 0          # TMA bulk copy alignment rules
-    assert max(T["nrows"] for T in tiles) <= (65535 if lrow16 else 256)
-    return tiles
+    return [parse_blob(blob[ptr[t]:ptr[t + 1]], m.dim, m.elem_ndof, which == 0) for t in range(len(ptr) - 1)]
 
 
 def _check_tile_geometry(m, T):
@@ -115,7 +111,7 @@ def _check_tile_geometry(m, T):
     assert np.array_equal(T["xy"][T["tv"].T], m.nodes[m.elems[T["elems"]]])
 
 
-def _fwd_replay(m, local, ncomp, n_out, R):
+def _fwd_replay(m, local, ncomp, n_out):
     """local: [nelem, Dt*Dt] pre-summed local matrices. Mirrors k_tile_fwd."""
     d = m.elem_ndof
     dd, Dt = d * d, ncomp * d
@@ -129,35 +125,42 @@ def _fwd_replay(m, local, ncomp, n_out, R):
             i += 1
     vals = np.full(n_out, np.nan)
     written = np.zeros(n_out, dtype=np.int32)
-    for T in tiles_of(m, 0, ncomp, R):
+    ntiles = 0
+    for T in tiles_of(m, 0, ncomp):
+        ntiles += 1
         _check_tile_geometry(m, T)
         nel = T["nel"]
         loc = local[T["elems"]]                               # [nel, S]
-        for i in range(T["nnz"]):
-            lr = int(T["lrow"][i]); j = i - int(T["roff"][lr]); ln = int(T["roff"][lr + 1]) - int(T["roff"][lr]); rs = int(T["rstart"][lr])
-            cs = T["src"][int(T["soff"][i]):int(T["soff"][i + 1])].astype(np.int64)
-            if ncomp == 1:
-                v = 0.0
-                for c in cs:
-                    s, le = divmod(int(c), nel)
-                    p, q = sym[s]
-                    assert abs(loc[le, p * d + q] - loc[le, q * d + p]) <= 1e-14 * abs(loc[le]).max()
-                    v += loc[le, p * d + q]
-                vals[rs + j] = v
-                written[rs + j] += 1
-            else:
-                le, pq = cs // dd, cs % dd
-                p, q = pq // d, pq % d
-                for a in range(ncomp):
-                    for b in range(ncomp):
-                        v = 0.0
-                        for k in range(len(cs)):
-                            v += loc[le[k], ((a * d + p[k]) * Dt + b * d + q[k])]
-                        dest = ncomp * (a * nnz_s + rs) + b * ln + j
-                        vals[dest] = v
-                        written[dest] += 1
+        assert np.array_equal(T["rlen"], rowptr[1:][np.searchsorted(rowptr[:-1], T["rstart"])] - T["rstart"])
+        assert T["cls"][:, 1].sum() == T["nnz"] and (np.diff(T["cls"][:, 0]) > 0).all()
+        for cnt, n, so, eo in T["cls"]:
+            for i in range(n):
+                cs = T["src"][so + np.arange(cnt) * n + i]
+                lr, j = int(T["ent_lr"][eo + i]), int(T["ent_j"][eo + i])
+                rs, ln = int(T["rstart"][lr]), int(T["rlen"][lr])
+                assert j < ln
+                if ncomp == 1:
+                    v = 0.0
+                    for c in cs:
+                        s, le = divmod(int(c), nel)
+                        p, q = sym[s]
+                        assert abs(loc[le, p * d + q] - loc[le, q * d + p]) <= 1e-14 * abs(loc[le]).max()
+                        v += loc[le, p * d + q]
+                    vals[rs + j] = v
+                    written[rs + j] += 1
+                else:
+                    le, pq = cs // dd, cs % dd
+                    p, q = pq // d, pq % d
+                    for a in range(ncomp):
+                        for b in range(ncomp):
+                            v = 0.0
+                            for k in range(len(cs)):
+                                v += loc[le[k], ((a * d + p[k]) * Dt + b * d + q[k])]
+                            dest = ncomp * (a * nnz_s + rs) + b * ln + j
+                            vals[dest] = v
+                            written[dest] += 1
     assert (written == 1).all()                                # every CSR entry is produced exactly once
-    return vals
+    return vals, ntiles
 
 
 def _close(a, b, rel=1e-12):
@@ -176,7 +179,8 @@ def test_forward_plan_replay_scalar(oracle, name, degree, R):
     rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
     dd = o.elem_ndof ** 2
     local = vv.reshape(o.nelem, o.g, dd).sum(1)
-    vals = _fwd_replay(m, local, 1, len(ref), R)
+    vals, ntiles = _fwd_replay(m, local, 1, len(ref))
+    assert ntiles >= (2 if R == 24 else 1)
     assert _close(vals, ref)
 
 
@@ -191,7 +195,7 @@ def test_forward_plan_replay_elasticity(oracle, name, degree):
     rp, ci, ref = oracle.canonical_csr(ind, vv, m.dim * o.ndof)
     Dt = m.dim * o.elem_ndof
     local = vv.reshape(o.nelem, o.g, Dt * Dt).sum(1)
-    vals = _fwd_replay(m, local, m.dim, len(ref), 16)
+    vals, _ = _fwd_replay(m, local, m.dim, len(ref))
     assert _close(vals, ref)
 
 
