@@ -1,0 +1,179 @@
+// Algebraic Dirichlet boundary conditions on a COO matrix — deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-93.
+//
+// The reference walks the COO slots with two std::map lookups per slot, pushes the kept triplets into
+// std::vectors and appends one (b, b, 1.0) per boundary dof in ascending dof order.  Here: a dof -> bd-index
+// table replaces the map (last duplicate wins, like map assignment), the kept slots and the boundary dofs are
+// compacted with exclusive prefix sums (stable: input order kept, ascending dof order for the diagonal, quirk
+// Q11), and the right-hand-side correction rhs[i] -= v * u_B[j] is accumulated with fp64 atomics on the VECTOR
+// (matrix values are never touched by an atomic).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include <string>
+
+#include "../../include/adfem_cuda.h"
+#include "internal.h"
+
+using namespace adfem;
+
+namespace {
+
+#define CU_TRY(call)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+__global__ void k_fill_i32(int* p, long long n, int v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+// bmap[dof] = largest index i with bd[i]-1 == dof  (std::map assignment: the last duplicate wins)
+__global__ void k_bd_map(const long long* __restrict__ bd, long long bdN, long long N, int* __restrict__ bmap, int* __restrict__ err) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= bdN) return;
+  const long long dof = bd[i] - 1;                                   // bd is 1-based (ImposeDirichlet.h:32)
+  if (dof < 0 || dof >= N) { *err = 1; return; }
+  atomicMax(&bmap[dof], (int)i);
+}
+__global__ void k_flags(const long long* __restrict__ indices, long long sN, long long N, const int* __restrict__ bmap,
+                        int* __restrict__ keep, int* __restrict__ isbd, int* __restrict__ err) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < sN) {
+    const long long i = indices[2 * k], j = indices[2 * k + 1];
+    if (i < 0 || i >= N || j < 0 || j >= N) { *err = 2; keep[k] = 0; }
+    else keep[k] = (bmap[i] < 0 && bmap[j] < 0) ? 1 : 0;
+  }
+  if (k < N) isbd[k] = bmap[k] >= 0 ? 1 : 0;
+}
+__global__ void k_copy(const double* __restrict__ a, double* __restrict__ b, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+__global__ void k_dirichlet_fwd(const long long* __restrict__ indices, const double* __restrict__ vv, long long sN, long long N,
+                                const int* __restrict__ bmap, const double* __restrict__ bdval, const int* __restrict__ kpos,
+                                const int* __restrict__ bpos, long long nkeep, long long* __restrict__ oindices, double* __restrict__ ov,
+                                double* __restrict__ orhs) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < sN) {
+    const long long i = indices[2 * k], j = indices[2 * k + 1];
+    const int bi = bmap[i], bj = bmap[j];
+    if (bi < 0 && bj < 0) { const long long z = kpos[k]; oindices[2 * z] = i; oindices[2 * z + 1] = j; ov[z] = vv[k]; }     // :35-39
+    else if (bi < 0 && bj >= 0) atomicAdd(&orhs[i], -vv[k] * bdval[bj]);                                                  // :41-43
+  }
+  if (k < N && bmap[k] >= 0) {                                                                                             // :45-50
+    const long long z = nkeep + bpos[k];
+    oindices[2 * z] = k; oindices[2 * z + 1] = k; ov[z] = 1.0;
+  }
+}
+__global__ void k_dirichlet_rhs_bd(long long N, const int* __restrict__ bmap, const double* __restrict__ bdval, double* __restrict__ orhs) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < N && bmap[k] >= 0) orhs[k] = bdval[bmap[k]];
+}
+__global__ void k_dirichlet_bwd(const long long* __restrict__ indices, const double* __restrict__ vv, long long sN, long long N,
+                                const int* __restrict__ bmap, const double* __restrict__ bdval, const int* __restrict__ kpos,
+                                const double* __restrict__ grad_ov, const double* __restrict__ grad_orhs, double* __restrict__ grad_vv,
+                                double* __restrict__ grad_rhs, double* __restrict__ grad_bdval) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < sN) {
+    const long long i = indices[2 * k], j = indices[2 * k + 1];
+    const int bi = bmap[i], bj = bmap[j];
+    double g = 0.0;
+    if (bi < 0 && bj < 0) g = grad_ov[kpos[k]];                                                                            // :73-75
+    else if (bi < 0 && bj >= 0) { g = -bdval[bj] * grad_orhs[i]; atomicAdd(&grad_bdval[bj], -vv[k] * grad_orhs[i]); }      // :77-81
+    grad_vv[k] = g;
+  }
+  if (k < N) {
+    const int b = bmap[k];
+    grad_rhs[k] = b < 0 ? grad_orhs[k] : 0.0;                                                                             // :83-87
+    if (b >= 0) atomicAdd(&grad_bdval[b], grad_orhs[k]);                                                                  // :88-90
+  }
+}
+
+struct Work {
+  int *bmap = nullptr, *keep = nullptr, *isbd = nullptr, *kpos = nullptr, *bpos = nullptr, *err = nullptr;
+  void* tmp = nullptr;
+  cudaStream_t st;
+  explicit Work(cudaStream_t s) : st(s) {}
+  ~Work() { for (void* p : {(void*)bmap, (void*)keep, (void*)isbd, (void*)kpos, (void*)bpos, (void*)err, tmp}) if (p) cudaFreeAsync(p, st); }
+};
+
+inline unsigned nblk(long long n) { return (unsigned)((n > 0 ? n : 1) + 255) / 256; }
+
+// builds bmap, keep/isbd flags and their exclusive scans; returns counts
+int prepare(Work& W, const long long* indices, long long sN, const long long* bd, long long bdN, long long N, long long* nkeep, long long* nbd) {
+  if (sN > 2147483647LL || N > 2147483647LL || bdN > 2147483647LL) return fail("ImposeDirichlet: sizes exceed 32-bit");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { cudaGetLastError(); return fail("no CUDA device available (libadfem_cuda has no CPU fallback)"); }
+  cudaStream_t st = W.st;
+  const long long M = sN > N ? sN : N;
+  CU_TRY(cudaMallocAsync((void**)&W.bmap, sizeof(int) * (N + 1), st));
+  CU_TRY(cudaMallocAsync((void**)&W.keep, sizeof(int) * (sN + 1), st));
+  CU_TRY(cudaMallocAsync((void**)&W.isbd, sizeof(int) * (N + 1), st));
+  CU_TRY(cudaMallocAsync((void**)&W.kpos, sizeof(int) * (sN + 1), st));
+  CU_TRY(cudaMallocAsync((void**)&W.bpos, sizeof(int) * (N + 1), st));
+  CU_TRY(cudaMallocAsync((void**)&W.err, sizeof(int), st));
+  CU_TRY(cudaMemsetAsync(W.err, 0, sizeof(int), st));
+  k_fill_i32<<<std::min(nblk(N), 4096u), 256, 0, st>>>(W.bmap, N, -1);
+  if (bdN > 0) k_bd_map<<<nblk(bdN), 256, 0, st>>>(bd, bdN, N, W.bmap, W.err);
+  CU_TRY(cudaMemsetAsync(W.keep + sN, 0, sizeof(int), st));
+  CU_TRY(cudaMemsetAsync(W.isbd + N, 0, sizeof(int), st));
+  k_flags<<<nblk(M), 256, 0, st>>>(indices, sN, N, W.bmap, W.keep, W.isbd, W.err);
+  size_t b1 = 0, b2 = 0;
+  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b1, W.keep, W.kpos, (int)(sN + 1), st));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b2, W.isbd, W.bpos, (int)(N + 1), st));
+  size_t tb = b1 > b2 ? b1 : b2;
+  CU_TRY(cudaMallocAsync(&W.tmp, tb > 0 ? tb : 16, st));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(W.tmp, b1, W.keep, W.kpos, (int)(sN + 1), st));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(W.tmp, b2, W.isbd, W.bpos, (int)(N + 1), st));
+  int h[3] = {0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(&h[0], W.kpos + sN, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&h[1], W.bpos + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&h[2], W.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (h[2] == 1) return fail("ImposeDirichlet: boundary dof out of range");
+  if (h[2] == 2) return fail("ImposeDirichlet: COO index out of range");
+  *nkeep = h[0]; *nbd = h[1];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long adfem_impose_dirichlet_count(const long long* indices, long long sN, const long long* bd, long long bdN, long long N, void* stream) {
+  Work W((cudaStream_t)stream);
+  long long nkeep = 0, nbd = 0;
+  if (prepare(W, indices, sN, bd, bdN, N, &nkeep, &nbd)) return -1;
+  return nkeep + nbd;
+}
+
+int adfem_impose_dirichlet(const long long* indices, const double* vv, long long sN, const long long* bd, const double* bdval, long long bdN,
+                           const double* rhs, long long N, long long* oindices, double* ov, double* orhs, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Work W(st);
+  long long nkeep = 0, nbd = 0;
+  if (int rc = prepare(W, indices, sN, bd, bdN, N, &nkeep, &nbd)) return rc;
+  const long long M = sN > N ? sN : N;
+  if (N > 0) k_copy<<<nblk(N), 256, 0, st>>>(rhs, orhs, N);
+  k_dirichlet_fwd<<<nblk(M), 256, 0, st>>>(indices, vv, sN, N, W.bmap, bdval, W.kpos, W.bpos, nkeep, oindices, ov, orhs);
+  k_dirichlet_rhs_bd<<<nblk(N), 256, 0, st>>>(N, W.bmap, bdval, orhs);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_impose_dirichlet_grad(const double* grad_ov, const double* grad_orhs, const long long* indices, const double* vv, long long sN,
+                                const long long* bd, const double* bdval, long long bdN, long long N, double* grad_vv, double* grad_rhs,
+                                double* grad_bdval, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Work W(st);
+  long long nkeep = 0, nbd = 0;
+  if (int rc = prepare(W, indices, sN, bd, bdN, N, &nkeep, &nbd)) return rc;
+  const long long M = sN > N ? sN : N;
+  if (bdN > 0) CU_TRY(cudaMemsetAsync(grad_bdval, 0, sizeof(double) * bdN, st));
+  k_dirichlet_bwd<<<nblk(M), 256, 0, st>>>(indices, vv, sN, N, W.bmap, bdval, W.kpos, grad_ov, grad_orhs, grad_vv, grad_rhs, grad_bdval);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

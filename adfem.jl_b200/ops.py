@@ -201,3 +201,171 @@ def compute_fem_source_term(f1, f2, mesh):
     """src/MFEM/MCore.jl:87-89."""
     a, b = compute_fem_source_term1(f1, mesh), compute_fem_source_term1(f2, mesh)
     return np.concatenate([a, b]) if isinstance(a, np.ndarray) else torch.cat([a, b])
+
+
+# =====================================================================================================
+# Structured-grid Q1 operators (src/InvCore.jl:67-110, 206-211) and the algebraic Dirichlet step
+# =====================================================================================================
+class _QuadOp(torch.autograd.Function):
+    """kind 0: UnivariateFemStiffness, 1: FemStiffness / SpatialFemStiffness."""
+
+    @staticmethod
+    def forward(ctx, hmat, kind, m, n, h):
+        hm = hmat.contiguous()
+        if kind == 0:
+            flag, nslot = int(hm.dim() == 3), 64 * m * n
+            fn = lib().adfem_quad_stiffness1
+        else:
+            flag, nslot = int(hm.dim() == 3), (256 if hm.dim() == 3 else 64) * m * n
+            fn = lib().adfem_quad_elasticity
+        vv = torch.empty(nslot, dtype=torch.float64, device=hm.device)
+        check(fn(_ptr(hm), C.c_int(flag), C.c_int(m), C.c_int(n), C.c_double(h), None, None, _ptr(vv), _stream()))
+        ctx.args = (kind, flag, m, n, h, hm.shape)
+        return vv
+
+    @staticmethod
+    def backward(ctx, grad_vv):
+        kind, flag, m, n, h, shape = ctx.args
+        g = torch.empty(shape, dtype=torch.float64, device=grad_vv.device)
+        fn = lib().adfem_quad_stiffness1_grad if kind == 0 else lib().adfem_quad_elasticity_grad
+        check(fn(_ptr(grad_vv.contiguous()), C.c_int(flag), C.c_int(m), C.c_int(n), C.c_double(h), _ptr(g), _stream()))
+        return g, None, None, None, None
+
+
+def _quad_indices(kind, flag, m, n, h, device):
+    nslot = (64 if kind == 0 or not flag else 256) * m * n
+    ii = torch.empty(nslot, dtype=torch.int64, device=device)
+    jj = torch.empty(nslot, dtype=torch.int64, device=device)
+    vv = torch.empty(nslot, dtype=torch.float64, device=device)
+    dummy = torch.zeros((4 * m * n, 2, 2) if kind == 0 else ((4 * m * n, 3, 3) if flag else (3, 3)), dtype=torch.float64, device=device)
+    fn = lib().adfem_quad_stiffness1 if kind == 0 else lib().adfem_quad_elasticity
+    check(fn(_ptr(dummy), C.c_int(1 if kind == 0 else flag), C.c_int(m), C.c_int(n), C.c_double(h), _ptr(ii), _ptr(jj), _ptr(vv), _stream()))
+    return torch.stack([ii - 1, jj - 1], 1)              # the ops emit 1-based ii/jj; SparseTensor here is 0-based
+
+
+def _quad(hmat, kind, m, n, h, ncomp):
+    N = ncomp * (m + 1) * (n + 1)
+    as_numpy = isinstance(hmat, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(hmat, dtype=np.float64)).cuda() if as_numpy else hmat
+    if t.dtype != torch.float64 or not t.is_cuda:
+        raise TypeError("hmat must be float64 (numpy array or CUDA tensor)")
+    vv = _QuadOp.apply(t, kind, int(m), int(n), float(h))
+    idx = _quad_indices(kind, int(t.dim() == 3), int(m), int(n), float(h), t.device)
+    S = SparseTensor(idx, vv, N, N)
+    return S.to_scipy() if as_numpy else S
+
+
+def compute_fem_stiffness_matrix1(hmat, m, n, h):
+    """Scalar anisotropic stiffness `∫(K∇u)·∇v` on an m×n Q1 grid — src/InvCore.jl:67-76 (op UnivariateFemStiffness).
+    `hmat` is 2×2 (constant) or 4mn×2×2 (per Gauss point)."""
+    if hmat.ndim not in (2, 3):
+        raise ValueError("Only 4mn x 2 x 2 or 2 x 2 `hmat` is supported.")       # InvCore.jl:68-70
+    assert hmat.shape[-1] == 2 and hmat.shape[-2] == 2
+    assert hmat.ndim == 2 or hmat.shape[0] == 4 * m * n
+    return _quad(hmat, 0, m, n, h, 1)
+
+
+def compute_fem_stiffness_matrix_grid(hmat, m, n, h):
+    """Q1 elasticity stiffness on an m×n grid — src/InvCore.jl:84-110 (`compute_fem_stiffness_matrix(hmat, m, n, h)`):
+    3×3 constant H → op FemStiffness, 4mn×3×3 → op SpatialFemStiffness."""
+    if hmat.ndim not in (2, 3):
+        raise ValueError("size hmat not valid")                                 # InvCore.jl:92
+    assert hmat.shape[-1] == 3 and hmat.shape[-2] == 3
+    assert hmat.ndim == 2 or hmat.shape[0] == 4 * m * n
+    return _quad(hmat, 1, m, n, h, 2)
+
+
+_mfem_stiffness = compute_fem_stiffness_matrix
+
+
+def compute_fem_stiffness_matrix(*args, **kw):     # noqa: F811  (Julia dispatches on argument types; so do we)
+    """`compute_fem_stiffness_matrix(kappa, mesh)` (src/MFEM/MCore.jl:275-315) or
+    `compute_fem_stiffness_matrix(hmat, m, n, h)` (src/InvCore.jl:84-110)."""
+    if len(args) == 4:
+        return compute_fem_stiffness_matrix_grid(*args)
+    return _mfem_stiffness(*args, **kw)
+
+
+class _SVT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, m, n, type_):
+        mu = mu.contiguous()
+        out = torch.empty((4 * m * n, 2, 2), dtype=torch.float64, device=mu.device)
+        check(lib().adfem_svt(_ptr(mu), C.c_longlong(m), C.c_longlong(n), C.c_int(type_), _ptr(out), _stream()))
+        ctx.args = (m, n, type_, mu.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        m, n, type_, shape = ctx.args
+        out = torch.empty(shape, dtype=torch.float64, device=g.device)
+        check(lib().adfem_svt_grad(_ptr(g.contiguous()), C.c_longlong(m), C.c_longlong(n), C.c_int(type_), _ptr(out), _stream()))
+        return out, None, None, None
+
+
+def compute_space_varying_tangent_elasticity_matrix(mu, m, n, h, type=1):   # noqa: A002  (the reference's argument name)
+    """4mn×2×2 tangent matrices from `mu` — src/InvCore.jl:206-211 (op SpatialVaryingTangentElastic)."""
+    as_numpy = isinstance(mu, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(mu, dtype=np.float64)).cuda() if as_numpy else mu
+    assert t.numel() == 4 * m * n * type
+    out = _SVT.apply(t.view(-1), int(m), int(n), int(type))
+    return out.cpu().numpy() if as_numpy else out
+
+
+class _Dirichlet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vv, rhs, bdval, indices, bd1):
+        vv, rhs, bdval = vv.contiguous(), rhs.contiguous(), bdval.contiguous()
+        sN, N, bdN = vv.numel(), rhs.numel(), bd1.numel()
+        L = lib()
+        L.adfem_impose_dirichlet_count.restype = C.c_longlong
+        S = L.adfem_impose_dirichlet_count(_ptr(indices), C.c_longlong(sN), _ptr(bd1), C.c_longlong(bdN), C.c_longlong(N), _stream())
+        if S < 0:
+            raise _lib.AdfemError(_lib.last_error())
+        oind = torch.empty((S, 2), dtype=torch.int64, device=vv.device)
+        ov = torch.empty(S, dtype=torch.float64, device=vv.device)
+        orhs = torch.empty(N, dtype=torch.float64, device=vv.device)
+        check(L.adfem_impose_dirichlet(_ptr(indices), _ptr(vv), C.c_longlong(sN), _ptr(bd1), _ptr(bdval), C.c_longlong(bdN), _ptr(rhs),
+                                       C.c_longlong(N), _ptr(oind), _ptr(ov), _ptr(orhs), _stream()))
+        ctx.save_for_backward(vv, bdval, indices, bd1)
+        ctx.N = N
+        ctx.mark_non_differentiable(oind)
+        return ov, orhs, oind
+
+    @staticmethod
+    def backward(ctx, g_ov, g_orhs, _g_ind):
+        vv, bdval, indices, bd1 = ctx.saved_tensors
+        sN, N, bdN = vv.numel(), ctx.N, bd1.numel()
+        g_ov = torch.zeros(0, dtype=torch.float64, device=vv.device) if g_ov is None else g_ov.contiguous()
+        g_orhs = torch.zeros(N, dtype=torch.float64, device=vv.device) if g_orhs is None else g_orhs.contiguous()
+        gv, gr, gb = (torch.empty(k, dtype=torch.float64, device=vv.device) for k in (sN, N, bdN))
+        check(lib().adfem_impose_dirichlet_grad(_ptr(g_ov), _ptr(g_orhs), _ptr(indices), _ptr(vv), C.c_longlong(sN), _ptr(bd1), _ptr(bdval),
+                                                C.c_longlong(bdN), C.c_longlong(N), _ptr(gv), _ptr(gr), _ptr(gb), _stream()))
+        return gv, gr, gb, None, None
+
+
+def impose_Dirichlet_boundary_conditions(A, rhs=None, bdnode=None, bdval=None):
+    """Algebraic Dirichlet conditions — src/MFEM/MUtils.jl:184-225 (op ImposeDirichlet).  `A` is a `SparseTensor`
+    (device, differentiable) or a scipy sparse matrix / dense array (eager); `bdnode` holds 0-based dofs here.
+    `impose_Dirichlet_boundary_conditions(A, bdnode)` is the homogeneous helper of MUtils.jl:220-225."""
+    if bdnode is None:                                                     # helper form: (A, bdnode)
+        bdnode, rhs = rhs, None
+    eager = not isinstance(A, SparseTensor)
+    if eager:
+        M = sp.coo_matrix(A)
+        dev_ = torch.device("cuda")
+        A = SparseTensor(torch.from_numpy(np.stack([M.row, M.col], 1).astype(np.int64)).to(dev_), torch.from_numpy(M.data.astype(np.float64)).to(dev_),
+                         *M.shape)
+    dev_ = A.values.device
+    N = A.shape[0]
+    assert A.shape[0] == A.shape[1]
+    bd = torch.as_tensor(np.asarray(bdnode), dtype=torch.int64, device=dev_)
+    helper = rhs is None
+    rhs_t = torch.zeros(N, dtype=torch.float64, device=dev_) if helper else torch.as_tensor(rhs, dtype=torch.float64, device=dev_)
+    bdval_t = torch.zeros(bd.numel(), dtype=torch.float64, device=dev_) if bdval is None else torch.as_tensor(bdval, dtype=torch.float64, device=dev_)
+    assert rhs_t.numel() == N and bdval_t.numel() == bd.numel() and bd.numel() <= N            # MUtils.jl:205-207
+    ov, orhs, oind = _Dirichlet.apply(A.values, rhs_t, bdval_t, A.indices.contiguous(), (bd + 1).contiguous())
+    B = SparseTensor(oind, ov, N, N)
+    if eager:
+        B, orhs = B.to_scipy(), orhs.cpu().numpy()
+    return B if helper else (B, orhs)

@@ -143,6 +143,33 @@ int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, dou
 int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream);
 int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, void* stream);
 
+/* Algebraic Dirichlet conditions on a COO matrix — the ImposeDirichlet op (deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-93,
+ * op signature ImposeDirichlet.cpp:14-57).  All pointers are DEVICE pointers.  indices: sN x 2 (row, col) 0-based; bd: bdN
+ * boundary dofs, 1-BASED like the reference (ImposeDirichlet.h:32); duplicates in bd: the last bdval wins.  Output: the kept
+ * slots in input order followed by one (b, b, 1.0) per boundary dof in ascending order; orhs[N].  The output length is data
+ * dependent: call _count first (as the op shell runs forward before allocating, ImposeDirichlet.cpp:104-110). */
+long long adfem_impose_dirichlet_count(const long long* indices, long long sN, const long long* bd, long long bdN, long long N, void* stream);
+int adfem_impose_dirichlet(const long long* indices, const double* vv, long long sN, const long long* bd, const double* bdval,
+                           long long bdN, const double* rhs, long long N, long long* oindices, double* ov, double* orhs, void* stream);
+/* ImposeDirichletGrad (ImposeDirichlet.h:63-93): grad_vv[sN], grad_rhs[N], grad_bdval[bdN] are overwritten. */
+int adfem_impose_dirichlet_grad(const double* grad_ov, const double* grad_orhs, const long long* indices, const double* vv,
+                                long long sN, const long long* bd, const double* bdval, long long bdN, long long N,
+                                double* grad_vv, double* grad_rhs, double* grad_bdval, void* stream);
+
+/* Structured-grid Q1 operators on an m x n grid of h x h cells (device pointers; ii/jj are 1-BASED int64 like the ops and may
+ * both be NULL to skip the mesh-static indices).
+ *  adfem_quad_stiffness1: UnivariateFemStiffness (deps/FemStiffness1/UnivariateFemStiffness.h:7-196) = compute_fem_stiffness_matrix1
+ *    (src/InvCore.jl:67-76); hmat [4mn,2,2] (rank3=1) or [2,2] (rank3=0); 64mn slots.
+ *  adfem_quad_elasticity: per_gauss=0 FemStiffness (deps/FemStiffness/FemStiffness.h:7-70, hmat [3,3], 64mn slots),
+ *    per_gauss=1 SpatialFemStiffness (deps/SpatialFemStiffness/SpatialFemStiffness.h:7-81, hmat [4mn,3,3], 256mn slots).
+ *  adfem_svt: SpatialVaryingTangentElastic (deps/SpatialVaryingTangentElastic/SpatialVaryingTangentElastic.h:1-70), type 1|2|3. */
+int adfem_quad_stiffness1(const double* hmat, int rank3, int m, int n, double h, long long* ii, long long* jj, double* vv, void* stream);
+int adfem_quad_stiffness1_grad(const double* grad_vv, int rank3, int m, int n, double h, double* grad_hmat, void* stream);
+int adfem_quad_elasticity(const double* hmat, int per_gauss, int m, int n, double h, long long* ii, long long* jj, double* vv, void* stream);
+int adfem_quad_elasticity_grad(const double* grad_vv, int per_gauss, int m, int n, double h, double* grad_hmat, void* stream);
+int adfem_svt(const double* mu, long long m, long long n, int type, double* hmat, void* stream);
+int adfem_svt_grad(const double* grad_hmat, long long m, long long n, int type, double* grad_mu, void* stream);
+
 /* Host-buffer convenience calls (synchronous; H2D + kernel + D2H).  Used for end-to-end timing. */
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host);
 int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host);
