@@ -69,6 +69,8 @@ struct adfem_mesh {
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
   int opt_smem_budget = 52 * 1024;          // blob + local-matrix staging per CTA (4 CTAs per SM)
   int opt_tile_threads = 256;
+  int opt_pipeline = 2;                     // blob buffers per CTA: 2 = prefetch the next tile while processing this one
+  int num_sms = 0;
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // scratch for the host-buffer calls
   DevBuf<double> s_in, s_out;
@@ -117,8 +119,11 @@ int ensure_pattern(adfem_mesh* m) {
 
 int slots_of(const HostMesh& h, int nc) { return nc == 1 ? h.d * (h.d + 1) / 2 : (nc * h.d) * (nc * h.d); }
 
-size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return align16(tp.max_blob) + (size_t)8 * slots * tp.max_elems; }
-size_t adj_smem_bytes(const AdjTiles& ap, int nc) { return align16(ap.max_blob) + (size_t)8 * nc * nc * ap.max_nnz; }
+size_t fwd_smem_bytes(const FwdTiles& tp, int slots, int nbuf = 1) { return nbuf * align16(tp.max_blob) + (size_t)8 * slots * tp.max_elems; }
+size_t adj_smem_bytes(const AdjTiles& ap, int nc, int nbuf = 1) { return nbuf * align16(ap.max_blob) + (size_t)8 * nc * nc * ap.max_nnz; }
+
+// persistent launch: as many CTAs as fit on the device at this shared-memory footprint (0 = one CTA per tile)
+template <class K> int persistent_grid(adfem_mesh* m, K kern, int threads, size_t smem, int ntiles, int* grid);
 
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (int rc = ensure_pattern(m)) return rc;
@@ -206,15 +211,27 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+template <class K> int persistent_grid(adfem_mesh* m, K kern, int threads, size_t smem, int ntiles, int* grid) {
+  if (m->opt_pipeline == 0) { *grid = ntiles; return 0; }             // one CTA per tile (no persistence)
+  if (m->num_sms == 0) CU_TRY(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  *grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * m->num_sms));
+  return 0;
+}
+
 DevMesh dev_mesh(const adfem_mesh* m, int heron) { DevMesh d = m->dm; d.heron = heron; return d; }
 
 template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
-  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
   auto kern = k_tile_fwd<DIM, DEG, OP>;
+  int nbuf = m->opt_pipeline >= 2 ? 2 : 1, grid = 0;
+  size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC), nbuf);
+  if (smem > 200 * 1024) { nbuf = 1; smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC), 1); }
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<P->dev.ntiles, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
+  if (int rc = persistent_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
+  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, nbuf, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -224,10 +241,13 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
   if (m->opt_adjoint_tiled) {
     AdjPlanDev* P = nullptr;
     if (int rc = ensure_adj_plan(m, NC, &P)) return rc;
-    const size_t smem = adj_smem_bytes(P->host, NC);
     auto kern = k_tile_adj<DIM, DEG, OP>;
+    int nbuf = m->opt_pipeline >= 2 ? 2 : 1, grid = 0;
+    size_t smem = adj_smem_bytes(P->host, NC, nbuf);
+    if (smem > 200 * 1024) { nbuf = 1; smem = adj_smem_bytes(P->host, NC, 1); }
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<P->dev.ntiles, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
+    if (int rc = persistent_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
+    kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, nbuf, dvals, grad);
   } else {
     k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
@@ -350,6 +370,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); m->opt_tile_threads = (int)value; }
+  else if (k == "pipeline") { if (value < 0 || value > 2) return fail("pipeline must be 0 (CTA per tile), 1 (persistent) or 2 (persistent, double-buffered)"); m->opt_pipeline = (int)value; }
   else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
   else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);

@@ -372,22 +372,46 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& 
   }
 }
 
-// Forward: one CTA per row tile.  The tile's mesh-static blob (index lists + vertex coordinates) arrives by ONE
-// TMA bulk copy; phase A evaluates the local matrices of every element touching the tile's rows into shared
-// memory; phase B lets each CSR entry sum its contributions in a fixed (column, element) order and writes it once.
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Forward: persistent CTAs walk the row tiles (tile = blockIdx.x + k*gridDim.x).  A tile's mesh-static blob (index
+// lists + vertex coordinates) arrives by ONE TMA bulk copy; with nbuf = 2 the copy of the NEXT tile is issued before
+// the current one is processed and, once it has landed, the coefficient lines of the next tile are prefetched into
+// L2, so neither latency sits on the critical path.  Phase A evaluates the local matrices of every element touching
+// the tile's rows into shared memory; phase B lets each CSR entry sum its contributions in a fixed (column, element)
+// order and writes it once.
 template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, int nbuf, const double* __restrict__ coef,
                                                                double* __restrict__ vals) {
   constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mbar;
-  const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-  const long long b0 = tp.blob_ptr[t];
-  const uint32_t bytes = (uint32_t)(tp.blob_ptr[t + 1] - b0);
-  if (tid == 0) mbar_init(&mbar, 1);
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* loc = reinterpret_cast<double*>(smem_all + (size_t)nbuf * tp.max_blob);
+  const int cpe = m.g * (OP == OP_STIFFNESS ? Voigt<DIM>::NS * Voigt<DIM>::NS : 1);      // coefficients per element
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
-  if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(smem, tp.blob + b0, bytes, &mbar); }
-  mbar_wait(&mbar, 0);
+  auto issue = [&](int t, int buf) {
+    const long long b0 = tp.blob_ptr[t];
+    const uint32_t bytes = (uint32_t)(tp.blob_ptr[t + 1] - b0);
+    mbar_expect_tx(&mbar[buf], bytes);
+    tma_bulk_g2s(smem_all + (size_t)buf * tp.max_blob, tp.blob + b0, bytes, &mbar[buf]);
+  };
+  if (nbuf == 2 && tid == 0 && (int)blockIdx.x < tp.ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, it++) {
+  const int sbuf = nbuf == 2 ? (it & 1) : 0, tn = t + gridDim.x;
+  const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+  if (tid == 0) { if (nbuf == 1) issue(t, 0); else if (tn < tp.ntiles) issue(tn, sbuf ^ 1); }
+  unsigned char* smem = smem_all + (size_t)sbuf * tp.max_blob;
+  mbar_wait(&mbar[sbuf], parity);
   const int* hdr = reinterpret_cast<const int*>(smem);
   const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3], nsrc = hdr[4], ncls = hdr[5], ent32 = hdr[6];
   unsigned o = 32;
@@ -400,10 +424,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   const unsigned char* ent = smem + o; o += a16((ent32 ? 4u : 2u) * nnz_t);
   const unsigned short* src = reinterpret_cast<const unsigned short*>(smem + o);
   (void)nsrc; (void)rlen;
-  double* loc = reinterpret_cast<double*>(smem + tp.max_blob);
 
-  {  // warm the coefficient lines of all of this thread's elements before the first use (non-blocking)
-    const int cpe = m.g * (OP == OP_STIFFNESS ? Voigt<DIM>::NS * Voigt<DIM>::NS : 1);
+  if (nbuf == 1 || it == 0) {  // warm the coefficient lines of this thread's elements before the first use (non-blocking)
     for (int le = tid; le < nel; le += nth) {
       const double* p = coef + (size_t)elems[le] * cpe;
       for (int b = 0; b < cpe; b += 16) prefetch_l1(p + b);
@@ -415,6 +437,17 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     local_matrix<DIM, DEG, OP>(m, G, elems[le], coef, [&](int slot, double v) {
       if (slot >= 0) loc[slot * nel + le] = v; else loc[(-slot - 1) * nel + le] += v;
     });
+  }
+  if (nbuf == 2 && tn < tp.ntiles && mbar_test(&mbar[sbuf ^ 1], ((it + 1) >> 1) & 1)) {
+    // the next tile's blob has landed: pull its coefficient lines into L2 while this tile finishes
+    const unsigned char* nb = smem_all + (size_t)(sbuf ^ 1) * tp.max_blob;
+    const int* nh = reinterpret_cast<const int*>(nb);
+    const int* nel_ids = reinterpret_cast<const int*>(nb + 32 + a16(4u * nh[0]) + a16(2u * nh[0]));
+    for (int le = tid; le < nh[1]; le += nth) {
+      const double* p = coef + (size_t)nel_ids[le] * cpe;
+      for (int b = 0; b < cpe; b += 4) prefetch_l2(p + b);
+      prefetch_l2(p + cpe - 1);
+    }
   }
   __syncthreads();
   for (int c = 0; c < ncls; c++) {
@@ -472,6 +505,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
           for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
       }
     }
+  }
+  __syncthreads();   // loc and this blob buffer are free again
   }
 }
 
@@ -576,22 +611,35 @@ __global__ void k_csr_adj_gather(DevMesh m, DevPattern pat, const double* __rest
   }
 }
 
-// Adjoint, tiled version: one CTA per element tile.  One TMA bulk copy brings the tile blob; the CSR rows the
-// tile's elements touch are staged into shared memory with coalesced loads; every element then gathers its
-// upstream gradients from shared memory and contracts them with its shape tables.
+// Adjoint, tiled version: persistent CTAs walk the element tiles.  One TMA bulk copy brings a tile blob (double
+// buffered: the next tile's copy is in flight while this one is processed, and once it has landed the CSR rows it
+// will stage are prefetched into L2); the CSR rows the tile's elements touch are staged into shared memory with
+// asynchronous copies; every element then gathers its upstream gradients from shared memory and contracts them
+// with its shape tables.
 template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, const double* __restrict__ dvals,
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, int nbuf, const double* __restrict__ dvals,
                                                                double* __restrict__ grad_coef) {
   constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, dd = D * D, NVL = DIM + 1;
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mbar;
-  const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-  const long long b0 = ap.blob_ptr[t];
-  const uint32_t bytes = (uint32_t)(ap.blob_ptr[t + 1] - b0);
-  if (tid == 0) mbar_init(&mbar, 1);
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* sd = reinterpret_cast<double*>(smem_all + (size_t)nbuf * ap.max_blob);       // NC*NC x nnz_t staged upstream gradients
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
-  if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(smem, ap.blob + b0, bytes, &mbar); }
-  mbar_wait(&mbar, 0);
+  auto issue = [&](int t, int buf) {
+    const long long b0 = ap.blob_ptr[t];
+    const uint32_t bytes = (uint32_t)(ap.blob_ptr[t + 1] - b0);
+    mbar_expect_tx(&mbar[buf], bytes);
+    tma_bulk_g2s(smem_all + (size_t)buf * ap.max_blob, ap.blob + b0, bytes, &mbar[buf]);
+  };
+  if (nbuf == 2 && tid == 0 && (int)blockIdx.x < ap.ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < ap.ntiles; t += gridDim.x, it++) {
+  const int sbuf = nbuf == 2 ? (it & 1) : 0, tn = t + gridDim.x;
+  const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+  if (tid == 0) { if (nbuf == 1) issue(t, 0); else if (tn < ap.ntiles) issue(tn, sbuf ^ 1); }
+  unsigned char* smem = smem_all + (size_t)sbuf * ap.max_blob;
+  mbar_wait(&mbar[sbuf], parity);
   const int* hdr = reinterpret_cast<const int*>(smem);
   const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
   unsigned o = 32;
@@ -602,7 +650,6 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
   const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
   const unsigned short* lrow = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * nnz_t);
   const unsigned short* gidx = reinterpret_cast<const unsigned short*>(smem + o);
-  double* sd = reinterpret_cast<double*>(smem + ap.max_blob);                       // NC*NC x nnz_t staged upstream gradients
 
   // stage the upstream gradients with asynchronous 8-byte copies (LDGSTS): every thread fires all of its
   // copies back to back, nothing waits on a register
@@ -617,6 +664,20 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
         for (int b = 0; b < NC; b++) cp_async8(sd + (a * NC + b) * nnz_t + i, dvals + (NC * (a * nnz_s + rs) + b * len + j));
     }
   }
+  if (nbuf == 2 && tn < ap.ntiles && mbar_test(&mbar[sbuf ^ 1], ((it + 1) >> 1) & 1)) {
+    // the next tile's blob has landed: pull the CSR rows it will stage into L2 (scalar layout; rows are <= a few sectors)
+    const unsigned char* nb = smem_all + (size_t)(sbuf ^ 1) * ap.max_blob;
+    const int* nh = reinterpret_cast<const int*>(nb);
+    const unsigned* nrs = reinterpret_cast<const unsigned*>(nb + 32);
+    const unsigned short* nro = reinterpret_cast<const unsigned short*>(nb + 32 + a16(4u * nh[0]));
+    if (NC == 1)
+      for (int lr = tid; lr < nh[0]; lr += nth) {
+        const double* p = dvals + nrs[lr];
+        const int len = nro[lr + 1] - nro[lr];
+        for (int b = 0; b < len; b += 4) prefetch_l2(p + b);
+        prefetch_l2(p + len - 1);
+      }
+  }
   cp_async_wait_all();
   __syncthreads();
   for (int le = tid; le < nel; le += nth) {
@@ -627,6 +688,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
       const int a = l / D, p = l % D, b = s / D, q = s % D;
       return sd[(a * NC + b) * nnz_t + gidx[(p * D + q) * nel + le]];
     }, grad_coef);
+  }
+  __syncthreads();   // sd and this blob buffer are free again
   }
 }
 

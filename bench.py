@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--adjoint-tiled", type=int, default=1)
     ap.add_argument("--tile-threads", type=int, default=0)
     ap.add_argument("--smem-budget", type=int, default=0)
+    ap.add_argument("--pipeline", type=int, default=-1)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -171,6 +172,8 @@ def main():
         mesh.set_option("tile_threads", args.tile_threads)
     if args.smem_budget:
         mesh.set_option("smem_budget", args.smem_budget)
+    if args.pipeline >= 0:
+        mesh.set_option("pipeline", args.pipeline)
     rowptr, colind = mesh.csr_pattern(1)
     nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
     xy = A.gauss_nodes(mesh)

@@ -1,0 +1,135 @@
+"""GPU parity tests of the boundary-row and structured-grid kernels against the oracle."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import meshgen
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rel=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3)
+    assert err.size == 0 or err.max() <= rel, f"max rel err {err.max():.3e}"
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------------------------------ ImposeDirichlet
+@pytest.mark.parametrize("dup", [False, True])
+def test_impose_dirichlet_coo(oracle, dup):
+    """Op-level parity incl. output ORDER (kept slots in input order, then boundary diagonals ascending, quirk Q11),
+    unordered / duplicated `bd` (last value wins) and the three gradients."""
+    c, e = meshgen.jitter_unstructured(11, 9, 0.1, seed=2)
+    m, o = A.Mesh(c, e, degree=2), oracle.Mesh2D(c, e, degree=2)
+    rng = np.random.default_rng(0)
+    kappa = rng.random(o.ngauss) + 0.5
+    ind, vv = o.laplace_fwd(kappa)
+    rhs = rng.standard_normal(o.ndof)
+    bd = rng.permutation(A.bcnode(m))                       # bcnode is unordered in the reference (Q12)
+    if dup:
+        bd = np.concatenate([bd, bd[:7]])
+    bdval = rng.standard_normal(len(bd))
+    oi, ov, orhs = oracle.impose_dirichlet_fwd(ind, vv, bd, rhs, bdval)
+    K = A.compute_fem_laplace_matrix1(dev(kappa), m)         # COO SparseTensor straight from the assembly op
+    v_t, r_t, b_t = K.values.detach().clone().requires_grad_(True), dev(rhs).requires_grad_(True), dev(bdval).requires_grad_(True)
+    B, r2 = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(K.indices, v_t, *K.shape), r_t, bd, b_t)
+    assert np.array_equal(B.indices.cpu().numpy(), oi)       # bit-exact indices and order
+    assert np.array_equal(B.values.detach().cpu().numpy(), ov)   # values are copies (or exactly 1.0)
+    close(r2.detach().cpu().numpy(), orhs)
+    w1, w2 = rng.standard_normal(len(ov)), rng.standard_normal(o.ndof)
+    gv, gr, gb = torch.autograd.grad([B.values, r2], [v_t, r_t, b_t], [dev(w1), dev(w2)])
+    egv, egr, egb = oracle.impose_dirichlet_bwd(w1, w2, ind, vv, bd, bdval, o.ndof)
+    close(gv.cpu().numpy(), egv); close(gr.cpu().numpy(), egr); close(gb.cpu().numpy(), egb)
+
+
+def test_impose_dirichlet_eager_matches_dense_julia_version():
+    """test/mfem.jl:78-88: the op equals the dense slicing implementation (src/MFEM/MUtils.jl:184-199)."""
+    rng = np.random.default_rng(1)
+    N = 9
+    Am = rng.random((N, N))
+    bd, bdval, rhs = np.array([4, 1, 2]), np.array([1.0, 2.0, 3.0]), rng.random(N)
+    B, r = A.impose_Dirichlet_boundary_conditions(sp.csr_matrix(Am), rhs, bd, bdval)
+    idx = np.ones(N, bool); idx[bd] = False
+    r0 = rhs.copy(); r0[idx] = rhs[idx] - Am[np.ix_(idx, bd)] @ bdval; r0[bd] = bdval
+    B0 = np.zeros((N, N)); B0[np.ix_(idx, idx)] = Am[np.ix_(idx, idx)]; B0[bd, bd] = 1.0
+    assert np.allclose(B.toarray(), B0, atol=1e-15) and np.allclose(r, r0, atol=1e-14)
+    Bh = A.impose_Dirichlet_boundary_conditions(sp.csr_matrix(Am), bd)      # homogeneous helper (MUtils.jl:220-225)
+    assert np.allclose(Bh.toarray(), B0, atol=1e-15)
+
+
+def test_impose_dirichlet_edge_cases(oracle):
+    ind = np.array([[0, 0], [0, 1], [1, 0], [1, 1], [2, 2], [0, 0]])
+    vv = np.arange(1.0, 7.0)
+    rhs = np.array([1.0, 2.0, 3.0])
+    for bd in (np.zeros(0, dtype=np.int64), np.array([0, 1, 2]), np.array([1])):      # no boundary, everything boundary, one dof
+        bdval = np.arange(len(bd), dtype=float) + 0.5
+        oi, ov, orhs = oracle.impose_dirichlet_fwd(ind, vv, bd, rhs, bdval)
+        B, r = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), dev(vv), 3, 3), dev(rhs), bd, dev(bdval))
+        assert np.array_equal(B.indices.cpu().numpy().reshape(-1, 2), oi) and np.array_equal(B.values.cpu().numpy(), ov)
+        close(r.cpu().numpy(), orhs)
+    with pytest.raises(A.AdfemError):
+        A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), dev(vv), 3, 3), dev(rhs), np.array([7]), dev(np.ones(1)))
+
+
+# ------------------------------------------------------------------------------------------ structured quads
+@pytest.mark.parametrize("m,n", [(5, 3), (1, 1), (16, 37)])
+def test_univariate_stiffness(oracle, m, n):
+    h = 0.3
+    rng = np.random.default_rng(2)
+    for hm in (rng.random((4 * m * n, 2, 2)), rng.random((2, 2))):
+        ii, jj, vv = oracle.univariate_stiffness_fwd(hm, m, n, h)
+        t = dev(hm).requires_grad_(True)
+        S = A.compute_fem_stiffness_matrix1(t, m, n, h)
+        assert np.array_equal(S.indices.cpu().numpy(), np.stack([ii - 1, jj - 1], 1))
+        close(S.values.detach().cpu().numpy(), vv)
+        gv = rng.standard_normal(len(vv))
+        (g,) = torch.autograd.grad(S.values, t, dev(gv))
+        close(g.cpu().numpy().reshape(-1), oracle.univariate_stiffness_bwd(gv, m, n, h, hm.ndim == 3))
+        Se = A.compute_fem_stiffness_matrix1(hm, m, n, h)                              # eager numpy path
+        ref = sp.coo_matrix((vv, (ii - 1, jj - 1)), shape=Se.shape).tocsr()
+        assert abs(Se - ref).max() < 1e-12 * abs(vv).max()
+
+
+@pytest.mark.parametrize("m,n", [(4, 6), (1, 2), (23, 9)])
+def test_grid_elasticity_and_svt(oracle, m, n):
+    h = 0.25
+    rng = np.random.default_rng(3)
+    for hm, fwd, bwd in ((rng.random((3, 3)), oracle.fem_stiffness_fwd, oracle.fem_stiffness_bwd),
+                         (rng.random((4 * m * n, 3, 3)), oracle.spatial_stiffness_fwd, oracle.spatial_stiffness_bwd)):
+        ii, jj, vv = fwd(hm, m, n, h)
+        t = dev(hm).requires_grad_(True)
+        S = A.compute_fem_stiffness_matrix(t, m, n, h)
+        assert S.shape == (2 * (m + 1) * (n + 1),) * 2
+        assert np.array_equal(S.indices.cpu().numpy(), np.stack([ii - 1, jj - 1], 1))
+        close(S.values.detach().cpu().numpy(), vv)
+        gv = rng.standard_normal(len(vv))
+        (g,) = torch.autograd.grad(S.values, t, dev(gv))
+        close(g.cpu().numpy().reshape(-1), bwd(gv, m, n, h))
+        if hm.ndim == 2:      # constant-H adjoint is a fixed-order reduction: bit-reproducible
+            (g2,) = torch.autograd.grad(A.compute_fem_stiffness_matrix(t, m, n, h).values, t, dev(gv))
+            assert torch.equal(g, g2)
+    for type_ in (1, 2, 3):
+        mu = rng.random(4 * m * n * type_)
+        t = dev(mu).requires_grad_(True)
+        H = A.compute_space_varying_tangent_elasticity_matrix(t, m, n, h, type_)
+        assert tuple(H.shape) == (4 * m * n, 2, 2)
+        assert np.array_equal(H.detach().cpu().numpy().reshape(-1), oracle.svt_fwd(mu, m, n, type_))
+        gh = rng.standard_normal(16 * m * n)
+        (g,) = torch.autograd.grad(H, t, dev(gh).view(-1, 2, 2))
+        assert np.array_equal(g.cpu().numpy(), oracle.svt_bwd(gh, m, n, type_))
+    # config 3's structured variant: SVT type 1 feeding compute_fem_stiffness_matrix1, gradient through both ops
+    mu = dev(rng.random(4 * m * n) + 0.5).requires_grad_(True)
+    S = A.compute_fem_stiffness_matrix1(A.compute_space_varying_tangent_elasticity_matrix(mu, m, n, h, 1), m, n, h)
+    (g,) = torch.autograd.grad((S.values ** 2).sum(), mu)
+    hm = oracle.svt_fwd(mu.detach().cpu().numpy(), m, n, 1).reshape(-1, 2, 2)
+    _, _, vv = oracle.univariate_stiffness_fwd(hm, m, n, h)
+    expect = oracle.svt_bwd(oracle.univariate_stiffness_bwd(2 * vv, m, n, h, True), m, n, 1)
+    close(g.cpu().numpy(), expect)

@@ -117,16 +117,19 @@ def _csr_check(m, o, oracle, op, coef, ofwd, obwd, ncomp, tiles):
     rng = np.random.default_rng(5)
     dv = rng.standard_normal(len(ref))
     expect = obwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, n))
-    for tiled, heron, threads in ((1, 0, 256), (0, 0, 256), (1, 1, 128), (1, 0, 512)):   # tiled / direct-gather adjoint, both area formulas
+    # tiled / direct-gather adjoint, both area formulas, CTA sizes, CTA-per-tile / persistent / double-buffered launches
+    for tiled, heron, threads, pipe in ((1, 0, 256, 2), (0, 0, 256, 2), (1, 1, 128, 1), (1, 0, 512, 0), (1, 0, 96, 2)):
         m.set_option("adjoint_tiled", tiled)
         m.set_option("area_formula_csr", heron)
         m.set_option("tile_threads", threads)
+        m.set_option("pipeline", pipe)
         T2 = fn(k, m, mode="csr")
         close(T2.values.detach().cpu().numpy(), ref)
         (g,) = torch.autograd.grad(T2.values, k, dev(dv))
         close(g.cpu().numpy().reshape(-1), expect)
     m.set_option("area_formula_csr", 0)
     m.set_option("tile_threads", 256)
+    m.set_option("pipeline", 2)
     # eager numpy path returns the same matrix as a scipy CSR
     S = fn(coef, m)
     assert np.array_equal(S.indptr, rp) and np.array_equal(S.indices, ci)
