@@ -68,8 +68,9 @@ struct adfem_mesh {
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
   int opt_smem_budget = 52 * 1024;          // blob + local-matrix staging per CTA (4 CTAs per SM)
-  int opt_tile_threads = 256;
-  int opt_pipeline = 2;                     // blob buffers per CTA: 2 = prefetch the next tile while processing this one
+  int opt_tile_threads = 320;               // measured best on config 2 (scripts/gpu_sweep.sh)
+  int opt_pipeline = 0;                     // 0 = one CTA per tile, 1 = persistent CTAs, 2 = persistent + double-buffered blobs
+                                            // (measured on B200: 2 loses more occupancy than it hides latency, 0 ~ 1)
   int num_sms = 0;
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // scratch for the host-buffer calls

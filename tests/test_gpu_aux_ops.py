@@ -39,7 +39,8 @@ def test_impose_dirichlet_coo(oracle, dup):
     bdval = rng.standard_normal(len(bd))
     oi, ov, orhs = oracle.impose_dirichlet_fwd(ind, vv, bd, rhs, bdval)
     K = A.compute_fem_laplace_matrix1(dev(kappa), m)         # COO SparseTensor straight from the assembly op
-    v_t, r_t, b_t = K.values.detach().clone().requires_grad_(True), dev(rhs).requires_grad_(True), dev(bdval).requires_grad_(True)
+    assert np.array_equal(K.indices.cpu().numpy(), ind)
+    v_t, r_t, b_t = dev(vv).requires_grad_(True), dev(rhs).requires_grad_(True), dev(bdval).requires_grad_(True)   # oracle values in: kept slots are exact copies
     B, r2 = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(K.indices, v_t, *K.shape), r_t, bd, b_t)
     assert np.array_equal(B.indices.cpu().numpy(), oi)       # bit-exact indices and order
     assert np.array_equal(B.values.detach().cpu().numpy(), ov)   # values are copies (or exactly 1.0)
