@@ -67,10 +67,12 @@ struct adfem_mesh {
   std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
-  int opt_smem_budget = 52 * 1024;          // blob + local-matrix staging per CTA (4 CTAs per SM)
-  int opt_tile_threads = 320;               // measured best on config 2 (scripts/gpu_sweep.sh)
-  int opt_pipeline = 0;                     // 0 = one CTA per tile, 1 = persistent CTAs, 2 = persistent + double-buffered blobs
-                                            // (measured on B200: 2 loses more occupancy than it hides latency, 0 ~ 1)
+  int opt_smem_budget = 72 * 1024;          // dynamic shared memory per CTA (3 head + 2 body buffers + staging): 3 CTAs per SM
+  int opt_tile_threads = 320;
+  int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
+  int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
+  int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
+  bool adj_untileable = false;              // a CSR row has more than 255 entries: adjoint uses the direct gather kernel
   int num_sms = 0;
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // scratch for the host-buffer calls
@@ -120,11 +122,10 @@ int ensure_pattern(adfem_mesh* m) {
 
 int slots_of(const HostMesh& h, int nc) { return nc == 1 ? h.d * (h.d + 1) / 2 : (nc * h.d) * (nc * h.d); }
 
-size_t fwd_smem_bytes(const FwdTiles& tp, int slots, int nbuf = 1) { return nbuf * align16(tp.max_blob) + (size_t)8 * slots * tp.max_elems; }
-size_t adj_smem_bytes(const AdjTiles& ap, int nc, int nbuf = 1) { return nbuf * align16(ap.max_blob) + (size_t)8 * nc * nc * ap.max_nnz; }
-
-// persistent launch: as many CTAs as fit on the device at this shared-memory footprint (0 = one CTA per tile)
-template <class K> int persistent_grid(adfem_mesh* m, K kern, int threads, size_t smem, int ntiles, int* grid);
+// dynamic shared memory of the tile kernels: 3 head buffers + 2 body buffers + local matrices / 2 staging buffers
+size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return 3 * align16(tp.max_head) + 2 * align16(tp.max_body) + (size_t)8 * slots * tp.max_elems; }
+size_t adj_smem_bytes(const AdjTiles& ap, int nc) { return 3 * align16(ap.max_head) + 2 * align16(ap.max_body) + (size_t)2 * 8 * nc * nc * ap.max_nnz; }
+constexpr size_t SMEM_LIMIT = 220 * 1024;
 
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (int rc = ensure_pattern(m)) return rc;
@@ -133,20 +134,20 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   auto it = m->fwd_plans.find(nc);
   if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
   auto P = std::make_unique<FwdPlanDev>();
-  int budget = m->opt_smem_budget;
+  size_t budget = (size_t)m->opt_smem_budget;
   std::string err = "tile too large";
-  for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
-    // per tile element: local matrix + its share of the blob (ids, vertices, sources)
-    const double per_elem = 8.0 * slots + 4 + 2 * (h.dim + 1) + 8 * h.dim * 0.6 + 2.0 * dd * 1.2;
+  for (int attempt = 0; attempt < 4 && !err.empty(); attempt++, budget = std::min(SMEM_LIMIT, budget * 2)) {
+    // bytes per tile element: local matrix + 3 head copies of its id + 2 body copies of (vertex ids, vertices, sources, destinations)
+    const double per_elem = 8.0 * slots + 3 * 4 + 2 * (2 * (h.dim + 1) + 8 * h.dim * 0.6 + 2.0 * dd * (nc == 1 ? 0.7 : 1.1) + 4);
     int max_elems = std::max(4, std::min(65535 / std::max(slots, dd), (int)(budget / per_elem)));
     double elems_per_row = (double)h.ne * h.d / std::max(1, h.ndof);
     int R = m->opt_rows_per_tile > 0 ? m->opt_rows_per_tile : (int)(max_elems / std::max(1.0, elems_per_row) * h.d * 0.8);
     R = std::max(4, std::min(R, 4096));
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, R, max_elems, nc == 1 ? 1 : 0, nthreads_of(m));
-      if (err.empty() && fwd_smem_bytes(P->host, slots) > (size_t)std::max(budget, 200 * 1024)) err = "tile too large";
+      if (err.empty() && fwd_smem_bytes(P->host, slots) > std::max(budget, m->opt_rows_per_tile > 0 ? SMEM_LIMIT : budget)) err = "tile too large";
       if (err.empty() || R <= 4) break;
-      R = std::max(4, (int)(R * 0.75));
+      R = std::max(4, (int)(R * 0.8));
     }
   }
   if (!err.empty()) return fail("forward tile plan: " + err);
@@ -155,7 +156,7 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (!m->host_only) {
     CU_TRY(upload(P->blob_ptr, tp.blob_ptr));
     CU_TRY(upload(P->blob, tp.blob));
-    P->dev = DevTiles{tp.ntiles, tp.sym, (unsigned)align16(tp.max_blob), tp.max_elems, tp.max_nnz, P->blob_ptr.p, P->blob.p};
+    P->dev = DevTiles{tp.ntiles, tp.sym, (unsigned)align16(tp.max_head), (unsigned)align16(tp.max_body), tp.max_elems, tp.max_nnz, P->blob_ptr.p, P->blob.p};
     std::vector<uint8_t>().swap(tp.blob);
   }
   *out = P.get();
@@ -163,27 +164,31 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   return 0;
 }
 
+// *out stays null (rc 0) when the mesh has rows the tiled adjoint cannot index (> 255 entries): the caller uses the gather kernel
 int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
+  *out = nullptr;
   if (int rc = ensure_pattern(m)) return rc;
   const HostMesh& h = m->hm;
   auto it = m->adj_plans.find(nc);
   if (it != m->adj_plans.end()) { *out = it->second.get(); return 0; }
+  if (m->adj_untileable) return 0;
   auto P = std::make_unique<AdjPlanDev>();
-  int budget = m->opt_smem_budget;
+  size_t budget = (size_t)m->opt_smem_budget;
   std::string err = "tile too large";
-  for (int attempt = 0; attempt < 3 && !err.empty(); attempt++, budget = std::min(200 * 1024, budget * 2)) {
+  for (int attempt = 0; attempt < 4 && !err.empty(); attempt++, budget = std::min(SMEM_LIMIT, budget * 2)) {
     const int dd = h.d * h.d;
     double nnz_per_row = (double)m->pat.nnz / std::max(1, m->pat.n), rows_per_elem = (double)m->pat.n / std::max(1, h.ne);
-    // bytes per owned element: staged gradients + row tables + its share of the blob
-    const double per_elem = rows_per_elem * 1.3 * (nnz_per_row * (8.0 * nc * nc + 2) + 10) + 4 + 2 * (h.dim + 1) + 8 * h.dim * rows_per_elem + 2.0 * dd;
+    // bytes per owned element: 2 staging buffers + 3 head copies (row tables) + 2 body copies (ids, vertices, positions)
+    const double per_elem = rows_per_elem * 1.3 * (nnz_per_row * (2 * 8.0 * nc * nc + 3 * 1) + 3 * 6) + 2 * (4 + 2 * (h.dim + 1) + 8 * h.dim * rows_per_elem + 1.0 * dd + (h.degree == 2 ? 2 * h.d : 0));
     int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(budget / per_elem);
     EPT = std::max(4, std::min(EPT, 4096));
     const int max_nnz = 65535;
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
-      if (err.empty() && adj_smem_bytes(P->host, nc) > (size_t)std::max(budget, 200 * 1024)) err = "tile too large";
+      if (err == "row longer than 255 entries") { m->adj_untileable = true; return 0; }
+      if (err.empty() && adj_smem_bytes(P->host, nc) > std::max(budget, m->opt_elems_per_tile > 0 ? SMEM_LIMIT : budget)) err = "tile too large";
       if (err.empty() || EPT <= 4) break;
-      EPT = std::max(4, (int)(EPT * 0.75));
+      EPT = std::max(4, (int)(EPT * 0.8));
     }
   }
   if (!err.empty()) return fail("adjoint tile plan: " + err);
@@ -192,7 +197,7 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
   if (!m->host_only) {
     CU_TRY(upload(P->blob_ptr, ap.blob_ptr));
     CU_TRY(upload(P->blob, ap.blob));
-    P->dev = DevTiles{ap.ntiles, 0, (unsigned)align16(ap.max_blob), ap.max_elems, ap.max_nnz, P->blob_ptr.p, P->blob.p};
+    P->dev = DevTiles{ap.ntiles, 0, (unsigned)align16(ap.max_head), (unsigned)align16(ap.max_body), ap.max_elems, ap.max_nnz, P->blob_ptr.p, P->blob.p};
     std::vector<uint8_t>().swap(ap.blob);
   }
   *out = P.get();
@@ -212,43 +217,54 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-template <class K> int persistent_grid(adfem_mesh* m, K kern, int threads, size_t smem, int ntiles, int* grid) {
-  if (m->opt_pipeline == 0) { *grid = ntiles; return 0; }             // one CTA per tile (no persistence)
+// grid of a tile kernel: persistent (resident CTAs per SM x SMs, never more than the tiles) or one CTA per tile
+template <class K> int tile_grid(adfem_mesh* m, K kern, int threads, size_t smem, int ntiles, int* grid) {
+  if (m->opt_pipeline == 0) { *grid = ntiles; return 0; }
   if (m->num_sms == 0) CU_TRY(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
   int per_sm = 0;
   CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  *grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * m->num_sms));
+  if (per_sm < 1) return fail("tile kernel does not fit on an SM (threads / shared memory)");
+  *grid = std::max(1, std::min(ntiles, per_sm * m->num_sms));
+  if (m->opt_grid_limit > 0) *grid = std::min(*grid, m->opt_grid_limit);
   return 0;
 }
 
 DevMesh dev_mesh(const adfem_mesh* m, int heron) { DevMesh d = m->dm; d.heron = heron; return d; }
 
+template <class K>
+int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, const double* coef, double* vals, cudaStream_t st) {
+  int grid = 0;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = tile_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
+  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
-  auto kern = k_tile_fwd<DIM, DEG, OP>;
-  int nbuf = m->opt_pipeline >= 2 ? 2 : 1, grid = 0;
-  size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC), nbuf);
-  if (smem > 200 * 1024) { nbuf = 1; smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC), 1); }
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (int rc = persistent_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
-  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, nbuf, coef, vals);
-  CU_TRY(cudaGetLastError());
-  return 0;
+  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
+  if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
+  if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
+    // register prefetch of the next tile's coefficients
+    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * m->opt_tile_threads)
+      return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true>, P, smem, coef, vals, st);
+  }
+  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false>, P, smem, coef, vals, st);
 }
 template <int DIM, int DEG, int OP>
 int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
-  if (m->opt_adjoint_tiled) {
-    AdjPlanDev* P = nullptr;
-    if (int rc = ensure_adj_plan(m, NC, &P)) return rc;
+  AdjPlanDev* P = nullptr;
+  if (m->opt_adjoint_tiled) { if (int rc = ensure_adj_plan(m, NC, &P)) return rc; }
+  const size_t smem = P ? adj_smem_bytes(P->host, NC) : 0;
+  if (P && smem <= SMEM_LIMIT) {
     auto kern = k_tile_adj<DIM, DEG, OP>;
-    int nbuf = m->opt_pipeline >= 2 ? 2 : 1, grid = 0;
-    size_t smem = adj_smem_bytes(P->host, NC, nbuf);
-    if (smem > 200 * 1024) { nbuf = 1; smem = adj_smem_bytes(P->host, NC, 1); }
+    int grid = 0;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = persistent_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
-    kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, nbuf, dvals, grad);
+    if (int rc = tile_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
+    kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
   } else {
     k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
@@ -371,7 +387,9 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); m->opt_tile_threads = (int)value; }
-  else if (k == "pipeline") { if (value < 0 || value > 2) return fail("pipeline must be 0 (CTA per tile), 1 (persistent) or 2 (persistent, double-buffered)"); m->opt_pipeline = (int)value; }
+  else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
+  else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;
+  else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
   else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);

@@ -21,9 +21,9 @@ struct DevPattern {
 };
 struct DevTiles {                  // forward (FwdTiles) or adjoint (AdjTiles) blobs on the device
   int ntiles, sym;
-  unsigned max_blob;               // bytes, multiple of 16
+  unsigned max_head, max_body;     // bytes, multiples of 16
   int max_elems, max_nnz;
-  const long long* blob_ptr;
+  const long long* blob_ptr;       // 2*ntiles+1: head offset, body offset per tile, then the end
   const unsigned char* blob;
 };
 
@@ -283,28 +283,37 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Local element matrix summed over Gauss points, handed to `put(slot, value)`.
-//   scalar ops (symmetric): slot = index in the packed upper triangle (p <= q, row-major)
-//   stiffness (H may be unsymmetric): slot = l*Dt + s; P2 accumulates over Gauss points through put(-slot-1, v)
-template <int DIM, int DEG, int OP, typename Put>
-__device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& G, int e, const double* __restrict__ coef, Put put) {
+// loop over the Gauss points of an element; GMAX > 0 unrolls (k < g <= GMAX) so that per-point data can live in registers
+template <int GMAX, class F> __device__ __forceinline__ void for_gauss(int g, F f) {
+  if constexpr (GMAX > 0) {
+#pragma unroll
+    for (int k = 0; k < GMAX; k++) if (k < g) f(k);
+  } else {
+    for (int k = 0; k < g; k++) f(k);
+  }
+}
+
+// Scalar operators (Laplace / mass): local matrix summed over Gauss points, packed upper triangle (p <= q, row-major)
+// handed to `put(index, value)`.  `cf(k)` is the coefficient at Gauss point k of this element.
+template <int DIM, int DEG, int OP, int GMAX, typename Coef, typename Put>
+__device__ __forceinline__ void local_matrix_scalar(const DevMesh& m, const Geom<DIM>& G, Coef cf, Put put) {
   constexpr int D = ElemTraits<DIM, DEG>::D;
   if (OP == OP_LAPLACE && DEG == 1) {
     double c = 0.0;                                   // gradients are constant: sum the coefficients first
-    for (int k = 0; k < m.g; k++) c += coef[(size_t)e * m.g + k] * (m.rule.w[k] * G.wscale);
+    for_gauss<GMAX>(m.g, [&](int k) { c += cf(k) * (m.rule.w[k] * G.wscale); });
     int i = 0;
 #pragma unroll
     for (int p = 0; p < D; p++)
 #pragma unroll
       for (int q = p; q < D; q++) put(i++, dotg<DIM>(G.gL[p], G.gL[q]) * c);
-  } else if (OP == OP_LAPLACE || OP == OP_MASS) {
+  } else {
     constexpr int NA = D * (D + 1) / 2;
     double acc[NA];
 #pragma unroll
     for (int i = 0; i < NA; i++) acc[i] = 0.0;
-    for (int k = 0; k < m.g; k++) {
+    for_gauss<GMAX>(m.g, [&](int k) {
       double L[DIM + 1]; bary<DIM>(m.rule, k, L);
-      const double c = coef[(size_t)e * m.g + k] * (m.rule.w[k] * G.wscale);
+      const double c = cf(k) * (m.rule.w[k] * G.wscale);
       if (OP == OP_LAPLACE) {
         double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
         int i = 0;
@@ -320,9 +329,21 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& 
 #pragma unroll
           for (int q = p; q < D; q++) acc[i++] += phi[p] * phi[q] * c;
       }
-    }
+    });
 #pragma unroll
     for (int i = 0; i < NA; i++) put(i, acc[i]);
+  }
+}
+
+// Local element matrix summed over Gauss points, handed to `put(slot, value)`.
+//   scalar ops (symmetric): slot = index in the packed upper triangle (p <= q, row-major)
+//   stiffness (H may be unsymmetric): slot = l*Dt + s; P2 accumulates over Gauss points through put(-slot-1, v)
+template <int DIM, int DEG, int OP, typename Put>
+__device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& G, int e, const double* __restrict__ coef, Put put) {
+  constexpr int D = ElemTraits<DIM, DEG>::D;
+  if (OP == OP_LAPLACE || OP == OP_MASS) {
+    const double* ce = coef + (size_t)e * m.g;
+    local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return ce[k]; }, put);
   } else {
     constexpr int NS = Voigt<DIM>::NS, Dt = DIM * D;
     if (DEG == 1) {
@@ -372,143 +393,7 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& 
   }
 }
 
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-               : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return done != 0;
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Forward: persistent CTAs walk the row tiles (tile = blockIdx.x + k*gridDim.x).  A tile's mesh-static blob (index
-// lists + vertex coordinates) arrives by ONE TMA bulk copy; with nbuf = 2 the copy of the NEXT tile is issued before
-// the current one is processed and, once it has landed, the coefficient lines of the next tile are prefetched into
-// L2, so neither latency sits on the critical path.  Phase A evaluates the local matrices of every element touching
-// the tile's rows into shared memory; phase B lets each CSR entry sum its contributions in a fixed (column, element)
-// order and writes it once.
-template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, int nbuf, const double* __restrict__ coef,
-                                                               double* __restrict__ vals) {
-  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
-  extern __shared__ __align__(128) unsigned char smem_all[];
-  __shared__ __align__(8) uint64_t mbar[2];
-  const int tid = threadIdx.x, nth = blockDim.x;
-  double* loc = reinterpret_cast<double*>(smem_all + (size_t)nbuf * tp.max_blob);
-  const int cpe = m.g * (OP == OP_STIFFNESS ? Voigt<DIM>::NS * Voigt<DIM>::NS : 1);      // coefficients per element
-  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-  __syncthreads();
-  auto issue = [&](int t, int buf) {
-    const long long b0 = tp.blob_ptr[t];
-    const uint32_t bytes = (uint32_t)(tp.blob_ptr[t + 1] - b0);
-    mbar_expect_tx(&mbar[buf], bytes);
-    tma_bulk_g2s(smem_all + (size_t)buf * tp.max_blob, tp.blob + b0, bytes, &mbar[buf]);
-  };
-  if (nbuf == 2 && tid == 0 && (int)blockIdx.x < tp.ntiles) issue(blockIdx.x, 0);
-  int it = 0;
-  for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, it++) {
-  const int sbuf = nbuf == 2 ? (it & 1) : 0, tn = t + gridDim.x;
-  const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-  if (tid == 0) { if (nbuf == 1) issue(t, 0); else if (tn < tp.ntiles) issue(tn, sbuf ^ 1); }
-  unsigned char* smem = smem_all + (size_t)sbuf * tp.max_blob;
-  mbar_wait(&mbar[sbuf], parity);
-  const int* hdr = reinterpret_cast<const int*>(smem);
-  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3], nsrc = hdr[4], ncls = hdr[5], ent32 = hdr[6];
-  unsigned o = 32;
-  const unsigned* rstart = reinterpret_cast<const unsigned*>(smem + o); o += a16(4u * nrows);
-  const unsigned short* rlen = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * nrows);
-  const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
-  const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
-  const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
-  const int* cls = reinterpret_cast<const int*>(smem + o); o += a16(16u * ncls);
-  const unsigned char* ent = smem + o; o += a16((ent32 ? 4u : 2u) * nnz_t);
-  const unsigned short* src = reinterpret_cast<const unsigned short*>(smem + o);
-  (void)nsrc; (void)rlen;
-
-  if (nbuf == 1 || it == 0) {  // warm the coefficient lines of this thread's elements before the first use (non-blocking)
-    for (int le = tid; le < nel; le += nth) {
-      const double* p = coef + (size_t)elems[le] * cpe;
-      for (int b = 0; b < cpe; b += 16) prefetch_l1(p + b);
-      prefetch_l1(p + cpe - 1);
-    }
-  }
-  for (int le = tid; le < nel; le += nth) {
-    Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);
-    local_matrix<DIM, DEG, OP>(m, G, elems[le], coef, [&](int slot, double v) {
-      if (slot >= 0) loc[slot * nel + le] = v; else loc[(-slot - 1) * nel + le] += v;
-    });
-  }
-  if (nbuf == 2 && tn < tp.ntiles && mbar_test(&mbar[sbuf ^ 1], ((it + 1) >> 1) & 1)) {
-    // the next tile's blob has landed: pull its coefficient lines into L2 while this tile finishes
-    const unsigned char* nb = smem_all + (size_t)(sbuf ^ 1) * tp.max_blob;
-    const int* nh = reinterpret_cast<const int*>(nb);
-    const int* nel_ids = reinterpret_cast<const int*>(nb + 32 + a16(4u * nh[0]) + a16(2u * nh[0]));
-    for (int le = tid; le < nh[1]; le += nth) {
-      const double* p = coef + (size_t)nel_ids[le] * cpe;
-      for (int b = 0; b < cpe; b += 4) prefetch_l2(p + b);
-      prefetch_l2(p + cpe - 1);
-    }
-  }
-  __syncthreads();
-  for (int c = 0; c < ncls; c++) {
-    const int cnt = cls[4 * c], n = cls[4 * c + 1];
-    const unsigned short* sc = src + cls[4 * c + 2];
-    const int e0 = cls[4 * c + 3];
-    auto dest = [&](int i, int& lr, int& j) {
-      if (ent32) { const unsigned v = reinterpret_cast<const unsigned*>(ent)[e0 + i]; lr = v & 0xffffu; j = v >> 16; }
-      else { const unsigned v = reinterpret_cast<const unsigned short*>(ent)[e0 + i]; lr = v & 0xffu; j = v >> 8; }
-    };
-    if (NC == 1) {
-      // every entry of the class has `cnt` sources: the same unrolled gather in every lane
-#define ADFEM_GATHER_CLASS(C)                                                              \
-      for (int i = tid; i < n; i += nth) {                                                 \
-        double v = 0.0;                                                                    \
-        _Pragma("unroll") for (int k = 0; k < C; k++) v += loc[sc[k * n + i]];           \
-        int lr, j; dest(i, lr, j);                                                         \
-        vals[(size_t)rstart[lr] + j] = v;                                                  \
-      }
-      switch (cnt) {
-        case 1: ADFEM_GATHER_CLASS(1) break;
-        case 2: ADFEM_GATHER_CLASS(2) break;
-        case 3: ADFEM_GATHER_CLASS(3) break;
-        case 4: ADFEM_GATHER_CLASS(4) break;
-        case 5: ADFEM_GATHER_CLASS(5) break;
-        case 6: ADFEM_GATHER_CLASS(6) break;
-        case 7: ADFEM_GATHER_CLASS(7) break;
-        case 8: ADFEM_GATHER_CLASS(8) break;
-        default:
-          for (int i = tid; i < n; i += nth) {
-            double v = 0.0;
-            for (int k = 0; k < cnt; k++) v += loc[sc[k * n + i]];
-            int lr, j; dest(i, lr, j);
-            vals[(size_t)rstart[lr] + j] = v;
-          }
-      }
-#undef ADFEM_GATHER_CLASS
-    } else {
-      for (int i = tid; i < n; i += nth) {
-        double v[NC * NC];
-#pragma unroll
-        for (int ab = 0; ab < NC * NC; ab++) v[ab] = 0.0;
-        for (int k = 0; k < cnt; k++) {
-          const int cc = sc[k * n + i], le = cc / dd, pq = cc - le * dd, p = pq / D, q = pq - p * D;
-#pragma unroll
-          for (int a = 0; a < NC; a++)
-#pragma unroll
-            for (int b = 0; b < NC; b++) v[a * NC + b] += loc[((a * D + p) * Dt + b * D + q) * nel + le];
-        }
-        int lr, j; dest(i, lr, j);
-        const long long len = rlen[lr], rs = rstart[lr];
-#pragma unroll
-        for (int a = 0; a < NC; a++)
-#pragma unroll
-          for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
-      }
-    }
-  }
-  __syncthreads();   // loc and this blob buffer are free again
-  }
-}
 
 // Contract the upstream gradients `g(l, s)` of one element's local matrix with its shape tables: writes
 // grad_coef for every Gauss point of the element.
@@ -611,85 +496,299 @@ __global__ void k_csr_adj_gather(DevMesh m, DevPattern pat, const double* __rest
   }
 }
 
-// Adjoint, tiled version: persistent CTAs walk the element tiles.  One TMA bulk copy brings a tile blob (double
-// buffered: the next tile's copy is in flight while this one is processed, and once it has landed the CSR rows it
-// will stage are prefetched into L2); the CSR rows the tile's elements touch are staged into shared memory with
-// asynchronous copies; every element then gathers its upstream gradients from shared memory and contracts them
-// with its shape tables.
-template <int DIM, int DEG, int OP>
-__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, int nbuf, const double* __restrict__ dvals,
-                                                               double* __restrict__ grad_coef) {
-  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, dd = D * D, NVL = DIM + 1;
-  extern __shared__ __align__(128) unsigned char smem_all[];
-  __shared__ __align__(8) uint64_t mbar[2];
-  const int tid = threadIdx.x, nth = blockDim.x;
-  double* sd = reinterpret_cast<double*>(smem_all + (size_t)nbuf * ap.max_blob);       // NC*NC x nnz_t staged upstream gradients
-  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-  __syncthreads();
-  auto issue = [&](int t, int buf) {
-    const long long b0 = ap.blob_ptr[t];
-    const uint32_t bytes = (uint32_t)(ap.blob_ptr[t + 1] - b0);
-    mbar_expect_tx(&mbar[buf], bytes);
-    tma_bulk_g2s(smem_all + (size_t)buf * ap.max_blob, ap.blob + b0, bytes, &mbar[buf]);
-  };
-  if (nbuf == 2 && tid == 0 && (int)blockIdx.x < ap.ntiles) issue(blockIdx.x, 0);
-  int it = 0;
-  for (int t = blockIdx.x; t < ap.ntiles; t += gridDim.x, it++) {
-  const int sbuf = nbuf == 2 ? (it & 1) : 0, tn = t + gridDim.x;
-  const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-  if (tid == 0) { if (nbuf == 1) issue(t, 0); else if (tn < ap.ntiles) issue(tn, sbuf ^ 1); }
-  unsigned char* smem = smem_all + (size_t)sbuf * ap.max_blob;
-  mbar_wait(&mbar[sbuf], parity);
-  const int* hdr = reinterpret_cast<const int*>(smem);
-  const int nrows = hdr[0], nel = hdr[1], nvt = hdr[2], nnz_t = hdr[3];
-  unsigned o = 32;
-  const unsigned* rstart = reinterpret_cast<const unsigned*>(smem + o); o += a16(4u * nrows);
-  const unsigned short* roff = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * (nrows + 1));
-  const int* elems = reinterpret_cast<const int*>(smem + o); o += a16(4u * nel);
-  const unsigned short* tv = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * NVL * nel);
-  const double* xy = reinterpret_cast<const double*>(smem + o); o += a16(8u * DIM * nvt);
-  const unsigned short* lrow = reinterpret_cast<const unsigned short*>(smem + o); o += a16(2u * nnz_t);
-  const unsigned short* gidx = reinterpret_cast<const unsigned short*>(smem + o);
 
-  // stage the upstream gradients with asynchronous 8-byte copies (LDGSTS): every thread fires all of its
-  // copies back to back, nothing waits on a register
-  for (int i = tid; i < nnz_t; i += nth) {
-    const int lr = lrow[i], j = i - roff[lr];
-    if (NC == 1) cp_async8(sd + i, dvals + ((size_t)rstart[lr] + j));
-    else {
-      const long long len = roff[lr + 1] - roff[lr], rs = rstart[lr];
-#pragma unroll
-      for (int a = 0; a < NC; a++)
-#pragma unroll
-        for (int b = 0; b < NC; b++) cp_async8(sd + (a * NC + b) * nnz_t + i, dvals + (NC * (a * nnz_s + rs) + b * len + j));
+// --------------------------------------------------------------------------------------------------
+// Tile kernels.  Persistent CTAs walk tiles t_i = blockIdx.x + i*gridDim.x (gridDim.x == ntiles gives one CTA per tile).
+// Software pipeline, per CTA:  heads in a ring of 3 buffers, bodies in a ring of 2, each filled by ONE TMA bulk copy
+// (UBLKCP) signalled on its own mbarrier.  While tile i is processed
+//   * body(i+1) and head(i+2) are already in flight (requested when tile i-1 finished), and
+//   * as soon as head(i+1) has landed the data-dependent loads of tile i+1 are started — coefficient loads into
+//     registers (forward) or asynchronous copies of the CSR rows into shared memory (adjoint) — so they are in flight
+//     during the whole second half / all of tile i.
+// In steady state no thread waits on a global load.
+// --------------------------------------------------------------------------------------------------
+struct TileRing {
+  unsigned char *heads, *bodies;
+  uint64_t* mbar;                  // [0..2] heads, [3..4] bodies
+  unsigned max_head, max_body;
+  const long long* blob_ptr; const unsigned char* blob;
+  int first, stride, count;        // tiles of this CTA: first + i*stride, i < count
+  __device__ __forceinline__ unsigned char* head(int i) const { return heads + (size_t)(i % 3) * max_head; }
+  __device__ __forceinline__ unsigned char* body(int i) const { return bodies + (size_t)(i & 1) * max_body; }
+  __device__ __forceinline__ void issue_head(int i) const {
+    const long long t = first + (long long)i * stride, b0 = blob_ptr[2 * t];
+    const uint32_t bytes = (uint32_t)(blob_ptr[2 * t + 1] - b0);
+    mbar_expect_tx(&mbar[i % 3], bytes);
+    tma_bulk_g2s(head(i), blob + b0, bytes, &mbar[i % 3]);
+  }
+  __device__ __forceinline__ void issue_body(int i) const {
+    const long long t = first + (long long)i * stride, b0 = blob_ptr[2 * t + 1];
+    const uint32_t bytes = (uint32_t)(blob_ptr[2 * t + 2] - b0);
+    mbar_expect_tx(&mbar[3 + (i & 1)], bytes);
+    tma_bulk_g2s(body(i), blob + b0, bytes, &mbar[3 + (i & 1)]);
+  }
+  __device__ __forceinline__ void wait_head(int i) const { mbar_wait(&mbar[i % 3], (i / 3) & 1); }
+  __device__ __forceinline__ void wait_body(int i) const { mbar_wait(&mbar[3 + (i & 1)], (i >> 1) & 1); }
+  // called by ONE thread after the CTA-wide barrier that ends tile i: its body buffer and head buffer are free
+  __device__ __forceinline__ void refill_after(int i) const {
+    if (i + 2 < count) issue_body(i + 2);
+    if (i + 3 < count) issue_head(i + 3);
+  }
+  __device__ __forceinline__ void prologue() const {
+    for (int i = 0; i < 3 && i < count; i++) issue_head(i);
+    for (int i = 0; i < 2 && i < count; i++) issue_body(i);
+  }
+};
+
+// decoded view of a forward tile (layout: plan.h)
+struct FwdView {
+  int nrows, nel, nvt, ncls, ent32;
+  const int* elems;
+  const unsigned* rstart; const unsigned short* rlen; const unsigned short* tv; const double* xy;
+  const int* cls; const unsigned char* dst; const unsigned short* src;
+  __device__ __forceinline__ FwdView(const unsigned char* head, const unsigned char* body, int nvl, int dim, bool has_rlen) {
+    const int* hdr = reinterpret_cast<const int*>(head);
+    nrows = hdr[0]; nel = hdr[1]; nvt = hdr[2]; ncls = hdr[5]; ent32 = hdr[6] & 1;
+    const int ndst = hdr[3];
+    elems = reinterpret_cast<const int*>(head + 32);
+    unsigned o = 0;
+    rstart = reinterpret_cast<const unsigned*>(body + o); o += a16(4u * nrows);
+    rlen = reinterpret_cast<const unsigned short*>(body + o); if (has_rlen) o += a16(2u * nrows);
+    tv = reinterpret_cast<const unsigned short*>(body + o); o += a16(2u * nvl * nel);
+    xy = reinterpret_cast<const double*>(body + o); o += a16(8u * dim * nvt);
+    cls = reinterpret_cast<const int*>(body + o); o += a16(16u * ncls);
+    dst = body + o; o += a16((ent32 ? 4u : 2u) * ndst);
+    src = reinterpret_cast<const unsigned short*>(body + o);
+  }
+  __device__ __forceinline__ void dest(int i, int& lr, int& j) const {
+    if (ent32) { const unsigned v = reinterpret_cast<const unsigned*>(dst)[i]; lr = v & 0xffffu; j = v >> 16; }
+    else { const unsigned v = reinterpret_cast<const unsigned short*>(dst)[i]; lr = v & 0xffu; j = v >> 8; }
+  }
+};
+
+// phase B of the scalar forward: every gather item sums its sources in a fixed order and is written once (twice for a
+// paired item: the (r,c) and (c,r) entries of a symmetric local-matrix sum)
+__device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double* __restrict__ loc, double* __restrict__ vals, int tid, int nth) {
+  for (int c = 0; c < V.ncls; c++) {
+    const int key = V.cls[4 * c], cnt = key & 0xffff, paired = key >> 16, n = V.cls[4 * c + 1];
+    const unsigned short* sc = V.src + V.cls[4 * c + 2];
+    const int d0 = V.cls[4 * c + 3];
+    auto put = [&](int i, double v) {
+      int lr, j; V.dest(d0 + i, lr, j);
+      vals[(size_t)V.rstart[lr] + j] = v;
+      if (paired) { V.dest(d0 + n + i, lr, j); vals[(size_t)V.rstart[lr] + j] = v; }
+    };
+#define ADFEM_GATHER_CLASS(C)                                                              \
+    for (int i = tid; i < n; i += nth) {                                                   \
+      double v = 0.0;                                                                      \
+      _Pragma("unroll") for (int k = 0; k < C; k++) v += loc[sc[k * n + i]];             \
+      put(i, v);                                                                           \
     }
+    switch (cnt) {
+      case 1: ADFEM_GATHER_CLASS(1) break;
+      case 2: ADFEM_GATHER_CLASS(2) break;
+      case 3: ADFEM_GATHER_CLASS(3) break;
+      case 4: ADFEM_GATHER_CLASS(4) break;
+      case 5: ADFEM_GATHER_CLASS(5) break;
+      case 6: ADFEM_GATHER_CLASS(6) break;
+      case 7: ADFEM_GATHER_CLASS(7) break;
+      case 8: ADFEM_GATHER_CLASS(8) break;
+      default:
+        for (int i = tid; i < n; i += nth) {
+          double v = 0.0;
+          for (int k = 0; k < cnt; k++) v += loc[sc[k * n + i]];
+          put(i, v);
+        }
+    }
+#undef ADFEM_GATHER_CLASS
   }
-  if (nbuf == 2 && tn < ap.ntiles && mbar_test(&mbar[sbuf ^ 1], ((it + 1) >> 1) & 1)) {
-    // the next tile's blob has landed: pull the CSR rows it will stage into L2 (scalar layout; rows are <= a few sectors)
-    const unsigned char* nb = smem_all + (size_t)(sbuf ^ 1) * ap.max_blob;
-    const int* nh = reinterpret_cast<const int*>(nb);
-    const unsigned* nrs = reinterpret_cast<const unsigned*>(nb + 32);
-    const unsigned short* nro = reinterpret_cast<const unsigned short*>(nb + 32 + a16(4u * nh[0]));
-    if (NC == 1)
-      for (int lr = tid; lr < nh[0]; lr += nth) {
-        const double* p = dvals + nrs[lr];
-        const int len = nro[lr + 1] - nro[lr];
-        for (int b = 0; b < len; b += 4) prefetch_l2(p + b);
-        prefetch_l2(p + len - 1);
-      }
-  }
-  cp_async_wait_all();
+}
+
+// Forward.  Phase A evaluates the local matrices of every element touching the tile's rows into shared memory; phase B
+// lets each CSR entry sum its contributions in a fixed (column, element) order and writes it once.  KPRE (P1 scalar
+// operators, g <= PIPE_GMAX Gauss points, at most PIPE_EPT tile elements per thread): the coefficients of the NEXT tile
+// are loaded into registers before phase B of the current one; otherwise they are prefetched into L2 at that point.
+constexpr int PIPE_GMAX = 4, PIPE_EPT = 2;
+template <int DIM, int DEG, int OP, bool KPRE>
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
+                                                               double* __restrict__ vals) {
+  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
+  static_assert(!KPRE || (DEG == 1 && OP != OP_STIFFNESS), "register prefetch is for P1 scalar operators");
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ __align__(8) uint64_t mbar[5];
+  const int tid = threadIdx.x, nth = blockDim.x, g = m.g;
+  const int cpe = g * (OP == OP_STIFFNESS ? Voigt<DIM>::NS * Voigt<DIM>::NS : 1);      // coefficients per element
+  TileRing R{smem_all, smem_all + (size_t)3 * tp.max_head, mbar, tp.max_head, tp.max_body, tp.blob_ptr, tp.blob,
+             (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < tp.ntiles) ? (tp.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
+  double* loc = reinterpret_cast<double*>(R.bodies + (size_t)2 * tp.max_body);
+  if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
-  for (int le = tid; le < nel; le += nth) {
-    Geom<DIM> G; tile_geom(tv, xy, nel, le, m.heron, G);
-    const int e = elems[le];
-    if (NC == 1) local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[gidx[(p * D + q) * nel + le]]; }, grad_coef);
-    else local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
-      const int a = l / D, p = l % D, b = s / D, q = s % D;
-      return sd[(a * NC + b) * nnz_t + gidx[(p * D + q) * nel + le]];
-    }, grad_coef);
+  if (R.count == 0) return;
+  if (tid == 0) R.prologue();
+  double kr[KPRE ? PIPE_EPT : 1][KPRE ? PIPE_GMAX : 1];
+  auto fetch_coef = [&](const unsigned char* head) {      // coefficients of this thread's elements of the tile with this head
+    const int* hdr = reinterpret_cast<const int*>(head);
+    const int nel = hdr[1];
+    const int* elems = hdr + 8;
+    if constexpr (KPRE) {
+#pragma unroll
+      for (int s = 0; s < PIPE_EPT; s++) {
+        const int le = tid + s * nth;
+        if (le < nel) {
+          const double* p = coef + (size_t)elems[le] * g;
+#pragma unroll
+          for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
+        }
+      }
+    } else {
+      for (int le = tid; le < nel; le += nth) {
+        const double* p = coef + (size_t)elems[le] * cpe;
+        for (int b = 0; b < cpe; b += 4) prefetch_l2(p + b);
+        prefetch_l2(p + cpe - 1);
+      }
+    }
+  };
+  R.wait_head(0);
+  fetch_coef(R.head(0));
+  for (int i = 0; i < R.count; i++) {
+    R.wait_body(i);
+    const FwdView V(R.head(i), R.body(i), NVL, DIM, NC > 1);
+    // ---- phase A
+    if constexpr (KPRE) {
+#pragma unroll
+      for (int s = 0; s < PIPE_EPT; s++) {
+        const int le = tid + s * nth;
+        if (le < V.nel) {
+          Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+          local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+        }
+      }
+    } else {
+      for (int le = tid; le < V.nel; le += nth) {
+        Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+        local_matrix<DIM, DEG, OP>(m, G, V.elems[le], coef, [&](int slot, double v) {
+          if (slot >= 0) loc[slot * V.nel + le] = v; else loc[(-slot - 1) * V.nel + le] += v;
+        });
+      }
+    }
+    __syncthreads();
+    if (i + 1 < R.count) { R.wait_head(i + 1); fetch_coef(R.head(i + 1)); }
+    // ---- phase B
+    if constexpr (NC == 1) {
+      fwd_gather_scalar(V, loc, vals, tid, nth);
+    } else {
+      for (int c = 0; c < V.ncls; c++) {
+        const int cnt = V.cls[4 * c] & 0xffff, n = V.cls[4 * c + 1];
+        const unsigned short* sc = V.src + V.cls[4 * c + 2];
+        const int d0 = V.cls[4 * c + 3];
+        for (int it = tid; it < n; it += nth) {
+          double v[NC * NC];
+#pragma unroll
+          for (int ab = 0; ab < NC * NC; ab++) v[ab] = 0.0;
+          for (int k = 0; k < cnt; k++) {
+            const int cc = sc[k * n + it], le = cc / dd, pq = cc - le * dd, p = pq / D, q = pq - p * D;
+#pragma unroll
+            for (int a = 0; a < NC; a++)
+#pragma unroll
+              for (int b = 0; b < NC; b++) v[a * NC + b] += loc[((a * D + p) * Dt + b * D + q) * V.nel + le];
+          }
+          int lr, j; V.dest(d0 + it, lr, j);
+          const long long len = V.rlen[lr], rs = V.rstart[lr];
+#pragma unroll
+          for (int a = 0; a < NC; a++)
+#pragma unroll
+            for (int b = 0; b < NC; b++) vals[NC * (a * nnz_s + rs) + b * len + j] = v[a * NC + b];
+        }
+      }
+    }
+    __syncthreads();                                       // loc and the buffers of tile i are free again
+    if (tid == 0) R.refill_after(i);
   }
-  __syncthreads();   // sd and this blob buffer are free again
+}
+
+// decoded view of an adjoint tile
+struct AdjView {
+  int nrows, nel, nvt, nnz_t, lrow16;
+  const unsigned* rstart; const unsigned short* roff; const unsigned char* lrow;
+  const int* elems; const unsigned short* tv; const double* xy; const unsigned short* td; const unsigned char* gpos;
+  __device__ __forceinline__ void set_head(const unsigned char* head) {
+    const int* hdr = reinterpret_cast<const int*>(head);
+    nrows = hdr[0]; nel = hdr[1]; nvt = hdr[2]; nnz_t = hdr[3]; lrow16 = hdr[4] & 1;
+    unsigned o = 32;
+    rstart = reinterpret_cast<const unsigned*>(head + o); o += a16(4u * nrows);
+    roff = reinterpret_cast<const unsigned short*>(head + o); o += a16(2u * (nrows + 1));
+    lrow = head + o;
+  }
+  __device__ __forceinline__ void set_body(const unsigned char* head, const unsigned char* body, int nvl, int dim, int d) {
+    const int has_td = (reinterpret_cast<const int*>(head)[4] >> 1) & 1;
+    unsigned o = 0;
+    elems = reinterpret_cast<const int*>(body + o); o += a16(4u * nel);
+    tv = reinterpret_cast<const unsigned short*>(body + o); o += a16(2u * nvl * nel);
+    xy = reinterpret_cast<const double*>(body + o); o += a16(8u * dim * nvt);
+    td = has_td ? reinterpret_cast<const unsigned short*>(body + o) : tv; if (has_td) o += a16(2u * d * nel);
+    gpos = body + o;
+  }
+};
+
+// Adjoint.  The CSR rows the tile's elements touch are staged into shared memory with asynchronous copies (LDGSTS) one
+// tile ahead; every element then gathers its d*d upstream gradients from shared memory (row base roff[td_p] + position
+// gpos) and contracts them with its shape tables.
+template <int DIM, int DEG, int OP>
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, const double* __restrict__ dvals,
+                                                               double* __restrict__ grad_coef) {
+  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, NVL = DIM + 1;
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ __align__(8) uint64_t mbar[5];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  TileRing R{smem_all, smem_all + (size_t)3 * ap.max_head, mbar, ap.max_head, ap.max_body, ap.blob_ptr, ap.blob,
+             (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < ap.ntiles) ? (ap.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
+  double* sd_all = reinterpret_cast<double*>(R.bodies + (size_t)2 * ap.max_body);
+  const size_t sd_stride = (size_t)NC * NC * ap.max_nnz;
+  if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
+  __syncthreads();
+  if (R.count == 0) return;
+  if (tid == 0) R.prologue();
+  auto stage = [&](const unsigned char* head, double* sd) {   // request the CSR row segments of the tile with this head
+    AdjView H; H.set_head(head);
+    for (int i = tid; i < H.nnz_t; i += nth) {
+      const int lr = H.lrow16 ? (int)reinterpret_cast<const unsigned short*>(H.lrow)[i] : (int)H.lrow[i];
+      const int j = i - H.roff[lr];
+      if (NC == 1) cp_async8(sd + i, dvals + ((size_t)H.rstart[lr] + j));
+      else {
+        const long long len = H.roff[lr + 1] - H.roff[lr], rs = H.rstart[lr];
+#pragma unroll
+        for (int a = 0; a < NC; a++)
+#pragma unroll
+          for (int b = 0; b < NC; b++) cp_async8(sd + (a * NC + b) * H.nnz_t + i, dvals + (NC * (a * nnz_s + rs) + b * len + j));
+      }
+    }
+  };
+  R.wait_head(0);
+  stage(R.head(0), sd_all);
+  for (int i = 0; i < R.count; i++) {
+    const double* sd = sd_all + (i & 1) * sd_stride;
+    cp_async_wait_all();
+    __syncthreads();                                       // sd[i&1] complete and visible to every thread
+    if (i + 1 < R.count) { R.wait_head(i + 1); stage(R.head(i + 1), sd_all + ((i + 1) & 1) * sd_stride); }
+    R.wait_body(i);
+    AdjView V; V.set_head(R.head(i)); V.set_body(R.head(i), R.body(i), NVL, DIM, D);
+    for (int le = tid; le < V.nel; le += nth) {
+      Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+      const int e = V.elems[le];
+      if constexpr (NC == 1) {
+        int rb[D];
+#pragma unroll
+        for (int p = 0; p < D; p++) rb[p] = V.roff[V.td[p * V.nel + le]];
+        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[rb[p] + V.gpos[(p * D + q) * V.nel + le]]; }, grad_coef);
+      } else {
+        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
+          const int a = l / D, p = l % D, b = s / D, q = s % D;
+          return sd[(a * NC + b) * V.nnz_t + V.roff[V.td[p * V.nel + le]] + V.gpos[(p * D + q) * V.nel + le]];
+        }, grad_coef);
+      }
+    }
+    __syncthreads();                                       // sd[i&1] and the buffers of tile i are free again
+    if (tid == 0) R.refill_after(i);
   }
 }
 

@@ -186,6 +186,7 @@ void tile_vertices(const HostMesh& m, const std::vector<int>& te, std::vector<in
 
 struct PartOut { std::vector<uint8_t> blob; std::vector<long long> sizes; std::string err; int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0; long long tot_a = 0; };
 
+// per_tile appends the tile's head and body to P.blob and pushes their two sizes to P.sizes
 template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<PartOut>& parts, F per_tile) {
   int nparts = std::max(1, std::min(nthreads, ntiles));
   parts.assign(nparts, PartOut());
@@ -194,15 +195,28 @@ template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<P
   std::vector<std::thread> th;
   for (int pi = 0; pi < nparts; pi++) th.emplace_back([&, pi] {
     PartOut& P = parts[pi];
-    for (long long t = pcut[pi]; t < pcut[pi + 1] && P.err.empty(); t++) {
-      size_t before = P.blob.size();
-      per_tile((int)t, P);
-      P.sizes.push_back((long long)(P.blob.size() - before));
-    }
+    for (long long t = pcut[pi]; t < pcut[pi + 1] && P.err.empty(); t++) per_tile((int)t, P);
   });
   for (auto& t : th) t.join();
   for (auto& P : parts) if (!P.err.empty()) return P.err;
   return "";
+}
+
+// concatenate the per-thread outputs: blob, blob_ptr (2 offsets per tile + end), largest head / body
+void merge_parts(std::vector<PartOut>& parts, std::vector<long long>& blob_ptr, std::vector<uint8_t>& blob, size_t& max_head, size_t& max_body) {
+  blob_ptr.assign(1, 0); blob.clear(); max_head = max_body = 0;
+  size_t total = 0;
+  for (auto& P : parts) total += P.blob.size();
+  blob.reserve(total);
+  for (auto& P : parts) {
+    for (size_t i = 0; i < P.sizes.size(); i++) {
+      blob_ptr.push_back(blob_ptr.back() + P.sizes[i]);
+      size_t& mx = (i & 1) ? max_body : max_head;
+      mx = std::max(mx, (size_t)P.sizes[i]);
+    }
+    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
+    std::vector<uint8_t>().swap(P.blob);
+  }
 }
 }  // namespace
 
@@ -220,7 +234,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   parallel_for(ntiles, nthreads, [&](long long b, long long e, int) {
     for (long long t = b; t < e; t++) std::sort(rows.begin() + row_ptr[t], rows.begin() + row_ptr[t + 1]);
   });
-  // entries are (row, position) packed into 16 bits when both fit in a byte, else 32 bits
+  // destinations are (row, position) packed into 16 bits when both fit in a byte, else 32 bits
   int max_len = 0;
   for (int r = 0; r < n; r++) max_len = std::max<int>(max_len, (int)(pat.rowptr[r + 1] - pat.rowptr[r]));
   ent32 = (R > 256 || max_len > 256) ? 1 : 0;
@@ -234,73 +248,98 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     std::vector<uint16_t> tv, rlen;
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
-    struct Entry { int lr, j; std::vector<uint16_t> src; };
-    std::vector<Entry> ents;
+    struct Item { uint32_t d0, d1; int paired; std::vector<uint16_t> src; };
+    std::vector<Item> items;
+    const int* trow = rows.data() + row_ptr[t];
     const int nrows = row_ptr[t + 1] - row_ptr[t];
-    for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) { int r = rows[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
+    for (int i = 0; i < nrows; i++) { int r = trow[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
     std::sort(te.begin(), te.end());
     te.erase(std::unique(te.begin(), te.end()), te.end());
     const int nel = (int)te.size();
     if (nel > max_tile_elems || (long long)nel * (sym ? nslot : dd) > 65535) { P.err = "tile too large"; return; }
     tile_vertices(m, te, tvert, tv, xy);
     if (tvert.size() > 65535) { P.err = "tile too large"; return; }
-    size_t nsrc = 0;
-    for (int i = row_ptr[t]; i < row_ptr[t + 1]; i++) {
-      const int r = rows[i], lr = i - row_ptr[t];
+    auto code = [&](int lr, int j) { return ent32 ? ((uint32_t)lr | (uint32_t)j << 16) : ((uint32_t)lr | (uint32_t)j << 8); };
+    size_t nsrc = 0, nnz_t = 0;
+    for (int lr = 0; lr < nrows; lr++) {
+      const int r = trow[lr];
       rstart.push_back((uint32_t)pat.rowptr[r]);
       rlen.push_back((uint16_t)(pat.rowptr[r + 1] - pat.rowptr[r]));
+      nnz_t += rlen.back();
       row_pairs(m, pat, r, ps);
       int j = -1;
+      bool skip = false;
       for (size_t k = 0; k < ps.size(); k++) {
-        if (k == 0 || ps[k].first != ps[k - 1].first) { j++; ents.push_back(Entry{lr, j, {}}); }
+        if (k == 0 || ps[k].first != ps[k - 1].first) {
+          j++;
+          const int c = ps[k].first;
+          skip = false;
+          int paired = 0; uint32_t d1 = 0;
+          if (sym && c != r) {                       // is the mirrored entry (c, r) produced by this tile too?
+            const int* it = std::lower_bound(trow, trow + nrows, c);
+            if (it != trow + nrows && *it == c) {
+              const int lc = (int)(it - trow);
+              if (lc < lr) skip = true;               // already emitted from the other side
+              else {
+                const int* cb = &pat.colind[pat.rowptr[c]];
+                const int* ce = &pat.colind[pat.rowptr[c + 1]];
+                paired = 1; d1 = code(lc, (int)(std::lower_bound(cb, ce, r) - cb));
+              }
+            }
+          }
+          if (!skip) items.push_back(Item{code(lr, j), d1, paired, {}});
+        }
+        if (skip) continue;
         int el = (int)(ps[k].second / dd), pq = (int)(ps[k].second % dd);
         int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
-        ents.back().src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
+        items.back().src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
         nsrc++;
       }
     }
-    if (nsrc > 65535 * 4 || ents.size() > 65535) { P.err = "tile too large"; return; }
-    // classes of equal source count, ascending; original entry order kept inside a class (coalesced stores)
-    std::vector<int> ord(ents.size());
+    if (nsrc > 65535 * 4 || nnz_t > 65535) { P.err = "tile too large"; return; }
+    // classes of equal (source count, paired), ascending; tile order kept inside a class (coalesced stores)
+    std::vector<int> ord(items.size());
     for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return ents[a].src.size() < ents[b].src.size(); });
-    std::vector<int> cls;            // {count, entries, src offset, entry offset} per class
-    std::vector<uint16_t> src, ent16;
-    std::vector<uint32_t> ent32v;
+    auto key = [&](int a) { return (int)items[a].src.size() | items[a].paired << 16; };
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key(a) < key(b); });
+    std::vector<int> cls;            // {count | paired << 16, items, src offset, dst offset} per class
+    std::vector<uint16_t> src, dst16;
+    std::vector<uint32_t> dst32;
+    auto push_dst = [&](uint32_t v) { if (ent32) dst32.push_back(v); else dst16.push_back((uint16_t)v); };
     for (size_t a = 0; a < ord.size();) {
       size_t b = a;
-      const int cnt = (int)ents[ord[a]].src.size();
-      while (b < ord.size() && (int)ents[ord[b]].src.size() == cnt) b++;
-      const int nc = (int)(b - a);
-      cls.push_back(cnt); cls.push_back(nc); cls.push_back((int)src.size()); cls.push_back((int)a);
-      for (int k = 0; k < cnt; k++) for (size_t i = a; i < b; i++) src.push_back(ents[ord[i]].src[k]);
-      for (size_t i = a; i < b; i++) {
-        const Entry& E = ents[ord[i]];
-        if (ent32) ent32v.push_back((uint32_t)E.lr | (uint32_t)E.j << 16); else ent16.push_back((uint16_t)(E.lr | E.j << 8));
-      }
+      const int kk = key(ord[a]), cnt = kk & 0xffff;
+      while (b < ord.size() && key(ord[b]) == kk) b++;
+      cls.push_back(kk); cls.push_back((int)(b - a)); cls.push_back((int)src.size()); cls.push_back((int)(ent32 ? dst32.size() : dst16.size()));
+      for (int k = 0; k < cnt; k++) for (size_t i = a; i < b; i++) src.push_back(items[ord[i]].src[k]);
+      for (size_t i = a; i < b; i++) push_dst(items[ord[i]].d0);
+      if (kk >> 16) for (size_t i = a; i < b; i++) push_dst(items[ord[i]].d1);
       a = b;
     }
-    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)ents.size(), (int)src.size(), (int)cls.size() / 4, ent32, 0};
+    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)(ent32 ? dst32.size() : dst16.size()), (int)src.size(), (int)cls.size() / 4, ent32, (int)nnz_t};
+    const size_t at0 = P.blob.size();
     BlobWriter w(P.blob);
-    w.section(hdr, 8); w.section(rstart); w.section(rlen); w.section(te); w.section(tv); w.section(xy); w.section(cls);
-    if (ent32) w.section(ent32v); else w.section(ent16);
+    w.section(hdr, 8); w.section(te);
+    const size_t at1 = P.blob.size();
+    w.section(rstart);
+    if (!sym) w.section(rlen);
+    w.section(tv); w.section(xy); w.section(cls);
+    if (ent32) w.section(dst32); else w.section(dst16);
     w.section(src);
-    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)ents.size());
+    P.sizes.push_back((long long)(at1 - at0)); P.sizes.push_back((long long)(P.blob.size() - at1));
+    P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)nnz_t);
     P.max_src = std::max(P.max_src, (int)src.size()); P.max_verts = std::max(P.max_verts, (int)tvert.size());
     P.tot_a += nel;
   });
   if (!err.empty()) return err;
-  blob_ptr.assign(1, 0); blob.clear();
-  max_rows = max_elems = max_nnz = max_src = max_verts = 0; max_blob = 0;
+  max_rows = max_elems = max_nnz = max_src = max_verts = 0;
   long long tot = 0;
   for (auto& P : parts) {
-    for (long long sz : P.sizes) { blob_ptr.push_back(blob_ptr.back() + sz); max_blob = std::max(max_blob, (size_t)sz); }
-    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
     max_rows = std::max(max_rows, P.max_rows); max_elems = std::max(max_elems, P.max_elems); max_nnz = std::max(max_nnz, P.max_nnz);
     max_src = std::max(max_src, P.max_src); max_verts = std::max(max_verts, P.max_verts);
     tot += P.tot_a;
-    P = PartOut();
   }
+  merge_parts(parts, blob_ptr, blob, max_head, max_body);
   elem_redundancy = m.ne > 0 ? (double)tot / m.ne : 0;
   return "";
 }
@@ -309,6 +348,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
 std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT, int max_tile_nnz, int nthreads) {
   elems_per_tile = EPT;
   const int d = m.d, dd = d * d, nvl = m.dim + 1;
+  for (int r = 0; r < pat.n; r++) if (pat.rowptr[r + 1] - pat.rowptr[r] > 255) return "row longer than 255 entries";
   Morton mc(m);
   std::vector<int> order;
   morton_order(m.ne, nthreads, [&](long long e) {
@@ -327,7 +367,8 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
   std::vector<PartOut> parts;
   std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
     std::vector<int> tr, te(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]), tvert;
-    std::vector<uint16_t> tv, roff, lrow, gidx;
+    std::vector<uint16_t> tv, roff, lrow16, td;
+    std::vector<uint8_t> lrow8, gpos;
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
     const int nel = (int)te.size();
@@ -335,6 +376,7 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     std::sort(tr.begin(), tr.end());
     tr.erase(std::unique(tr.begin(), tr.end()), tr.end());
     const int nrows = (int)tr.size();
+    const int lrow_wide = nrows > 256;
     long long acc = 0;
     roff.push_back(0);
     for (int lr = 0; lr < nrows; lr++) {
@@ -342,41 +384,45 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
       rstart.push_back((uint32_t)rs);
       acc += len;
       if (acc > max_tile_nnz || acc > 65535 || nrows > 65535) { P.err = "tile too large"; return; }
-      for (long long j = 0; j < len; j++) lrow.push_back((uint16_t)lr);
+      for (long long j = 0; j < len; j++) { if (lrow_wide) lrow16.push_back((uint16_t)lr); else lrow8.push_back((uint8_t)lr); }
       roff.push_back((uint16_t)acc);
     }
     tile_vertices(m, te, tvert, tv, xy);
-    gidx.resize((size_t)dd * nel);
+    td.resize((size_t)d * nel); gpos.resize((size_t)dd * nel);
     for (int le = 0; le < nel; le++) {
       const int e = te[le];
       const int* ce = &m.conn[(size_t)e * d];
       for (int p = 0; p < d; p++) {
-        const int lr = (int)(std::lower_bound(tr.begin(), tr.end(), ce[p]) - tr.begin());
-        for (int q = 0; q < d; q++) {
-          const long long pos = (long long)pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]];
-          gidx[(size_t)(p * d + q) * nel + le] = (uint16_t)(roff[lr] + pos);
-        }
+        td[(size_t)p * nel + le] = (uint16_t)(std::lower_bound(tr.begin(), tr.end(), ce[p]) - tr.begin());
+        for (int q = 0; q < d; q++)
+          gpos[(size_t)(p * d + q) * nel + le] = (uint8_t)((long long)pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]]);
       }
     }
-    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)acc, 0, 0, 0, 0};
+    // P1: the staged rows are the tile vertices in the same order, so td == tv and is not stored
+    const int has_td = !(d == nvl && td == tv);
+    int hdr[8] = {nrows, nel, (int)tvert.size(), (int)acc, lrow_wide | has_td << 1, 0, 0, 0};
+    const size_t at0 = P.blob.size();
     BlobWriter w(P.blob);
-    w.section(hdr, 8); w.section(rstart); w.section(roff); w.section(te); w.section(tv); w.section(xy); w.section(lrow); w.section(gidx);
+    w.section(hdr, 8); w.section(rstart); w.section(roff);
+    if (lrow_wide) w.section(lrow16); else w.section(lrow8);
+    const size_t at1 = P.blob.size();
+    w.section(te); w.section(tv); w.section(xy);
+    if (has_td) w.section(td);
+    w.section(gpos);
+    P.sizes.push_back((long long)(at1 - at0)); P.sizes.push_back((long long)(P.blob.size() - at1));
     P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)acc);
     P.max_verts = std::max(P.max_verts, (int)tvert.size());
     P.tot_a += nrows;
   });
   if (!err.empty()) return err;
-  blob_ptr.assign(1, 0); blob.clear();
-  max_rows = max_elems = max_nnz = max_verts = 0; max_blob = 0;
+  max_rows = max_elems = max_nnz = max_verts = 0;
   long long tot = 0;
   for (auto& P : parts) {
-    for (long long sz : P.sizes) { blob_ptr.push_back(blob_ptr.back() + sz); max_blob = std::max(max_blob, (size_t)sz); }
-    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
     max_rows = std::max(max_rows, P.max_rows); max_elems = std::max(max_elems, P.max_elems); max_nnz = std::max(max_nnz, P.max_nnz);
     max_verts = std::max(max_verts, P.max_verts);
     tot += P.tot_a;
-    P = PartOut();
   }
+  merge_parts(parts, blob_ptr, blob, max_head, max_body);
   row_redundancy = pat.n > 0 ? (double)tot / pat.n : 0;
   return "";
 }

@@ -14,7 +14,7 @@
 //    touch (coalesced) and each element gathers its upstream gradients from shared memory.
 //
 // Every tile's mesh-static data (index lists AND the coordinates of the vertices it needs) is packed
-// into ONE contiguous, 16-byte aligned blob so that a single TMA bulk copy brings it on chip.
+// into one contiguous, 16-byte aligned blob that TMA bulk copies bring on chip (two copies: head, body).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -38,45 +38,57 @@ struct ScalarPattern {
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Every tile blob is split into a small HEAD (what the kernel needs one pipeline stage early: the element ids whose
+// coefficients are prefetched / the row segments whose upstream gradients are staged) and a BODY (everything else).
+// Head and body of tile t are contiguous: blob_ptr[2t] = head offset, blob_ptr[2t+1] = body offset, blob_ptr[2t+2] = end.
+// Every section starts on a 16-byte boundary (TMA bulk copy alignment rule).
+//
 // ---- forward tile blob -----------------------------------------------------------------------------
-// sections, each starting on a 16-byte boundary, in this order:
-//   hdr    int32[8]            {nrows, nel, nvt, nnz, nsrc, ncls, ent32, 0}
-//   rstart uint32[nrows]       CSR offset of the first entry of each tile row (scalar pattern)
-//   rlen   uint16[nrows]       row lengths
+// HEAD
+//   hdr    int32[8]            {nrows, nel, nvt, ndst, nsrc, ncls, flags (bit0: 32-bit destinations), nnz}
 //   elems  int32[nel]          global element ids evaluated by the tile (ascending) — coefficient index
+// BODY
+//   rstart uint32[nrows]       CSR offset of the first entry of each tile row (scalar pattern)
+//   rlen   uint16[nrows]       row lengths — vector plans (sym = 0) only
 //   tv     uint16[nvl*nel]     tile-local vertex ids, k-major (tv[k*nel+le]), post orientation fix
 //   xy     double[dim*nvt]     coordinates of the tile-local vertices
-//   cls    int32[4*ncls]       entry classes {source count, entries, first source, first entry}: entries with the same
-//                              number of contributions are processed together so that every lane of a warp runs the
-//                              same fully unrolled gather (no divergence); ascending count, tile order inside a class
-//   ent    uint16|uint32[nnz]  destination of each entry in class order: tile row | position-in-row << 8 (or << 16)
-//   src    uint16[nsrc]        class-major, k-major inside a class: src[first + k*entries + i].  Scalar plans (sym=1):
+//   cls    int32[4*ncls]       gather classes {source count | paired << 16, items, first source, first destination}: items
+//                              with the same number of contributions are processed together so that every lane of a warp
+//                              runs the same fully unrolled gather (no divergence).  A PAIRED item (scalar plans only) is an
+//                              off-diagonal pair (r,c),(c,r) with both rows in the tile: the local matrices are symmetric, so
+//                              the sum is formed once and stored to both destinations (dst[first+i], dst[first+items+i]).
+//   dst    uint16|uint32[...]  destinations: tile row | position-in-row << 8 (or << 16)
+//   src    uint16[nsrc]        class-major, k-major inside a class: src[first + k*items + i].  Scalar plans (sym=1):
 //                              shared-memory index sym(p,q)*nel + le of a local-matrix value (packed upper triangle);
 //                              vector plans: le*d*d + p*d + q
 struct FwdTiles {
   int ntiles = 0, rows_per_tile = 0, sym = 1, ent32 = 0;
   int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0;
-  size_t max_blob = 0;
-  std::vector<long long> blob_ptr;    // ntiles+1 byte offsets
+  size_t max_head = 0, max_body = 0;
+  std::vector<long long> blob_ptr;    // 2*ntiles+1 byte offsets
   std::vector<uint8_t> blob;
   double elem_redundancy = 0;
   std::string build(const HostMesh& m, const ScalarPattern& pat, int rows_per_tile, int max_tile_elems, int sym, int nthreads);
 };
 
 // ---- adjoint tile blob -----------------------------------------------------------------------------
-//   hdr    int32[8]            {nrows, nel, nvt, nnz, 0, 0, 0, 0}
+// HEAD
+//   hdr    int32[8]            {nrows, nel, nvt, nnz, flags (bit0: 16-bit lrow, bit1: td present), 0, 0, 0}
 //   rstart uint32[nrows]       CSR offset of each staged row
-//   roff   uint16[nrows+1]
+//   roff   uint16[nrows+1]     offset of each staged row inside the staging buffer
+//   lrow   uint8|uint16[nnz]   staged row of every staged entry
+// BODY
 //   elems  int32[nel]          owned elements (ascending)
 //   tv     uint16[nvl*nel]
 //   xy     double[dim*nvt]
-//   lrow   uint16[nnz]         staged row of every staged entry
-//   gidx   uint16[d*d*nel]     pq-major: position of slot (le,p,q) inside the staged entries
+//   td     uint16[d*nel]       staged row of each local dof, k-major — only when it differs from tv (P2); for P1 the staged
+//                              rows ARE the tile vertices in the same (ascending) order
+//   gpos   uint8[d*d*nel]      pq-major: position of slot (le,p,q) inside its CSR row; the staged entry is roff[td_p] + gpos
 struct AdjTiles {
   int ntiles = 0, elems_per_tile = 0;
   int max_rows = 0, max_elems = 0, max_nnz = 0, max_verts = 0;
-  size_t max_blob = 0;
-  std::vector<long long> blob_ptr;
+  size_t max_head = 0, max_body = 0;
+  std::vector<long long> blob_ptr;    // 2*ntiles+1
   std::vector<uint8_t> blob;
   double row_redundancy = 0;
   std::string build(const HostMesh& m, const ScalarPattern& pat, int elems_per_tile, int max_tile_nnz, int nthreads);

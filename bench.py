@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--tile-threads", type=int, default=0)
     ap.add_argument("--smem-budget", type=int, default=0)
     ap.add_argument("--pipeline", type=int, default=-1)
+    ap.add_argument("--coef-prefetch", type=int, default=-1)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -174,6 +175,8 @@ def main():
         mesh.set_option("smem_budget", args.smem_budget)
     if args.pipeline >= 0:
         mesh.set_option("pipeline", args.pipeline)
+    if args.coef_prefetch >= 0:
+        mesh.set_option("coef_prefetch", args.coef_prefetch)
     rowptr, colind = mesh.csr_pattern(1)
     nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
     xy = A.gauss_nodes(mesh)

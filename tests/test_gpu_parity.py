@@ -117,19 +117,26 @@ def _csr_check(m, o, oracle, op, coef, ofwd, obwd, ncomp, tiles):
     rng = np.random.default_rng(5)
     dv = rng.standard_normal(len(ref))
     expect = obwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, n))
-    # tiled / direct-gather adjoint, both area formulas, CTA sizes, CTA-per-tile / persistent / double-buffered launches
-    for tiled, heron, threads, pipe in ((1, 0, 256, 2), (0, 0, 256, 2), (1, 1, 128, 1), (1, 0, 512, 0), (1, 0, 96, 2)):
+    # tiled / direct-gather adjoint, both area formulas, CTA sizes, persistent (software-pipelined) / one-CTA-per-tile launches,
+    # coefficient prefetch into registers on / off
+    # grid_limit: 0 = every tile gets its own CTA on these small meshes; 1/2/3/5 CTAs walk ALL tiles (ring wrap-around of the pipeline)
+    for tiled, heron, threads, pipe, kpre, glim in ((1, 0, 256, 1, 1, 0), (0, 0, 256, 1, 0, 0), (1, 1, 128, 0, 1, 0), (1, 0, 512, 0, 0, 0), (1, 0, 96, 1, 1, 1),
+                                                    (1, 1, 64, 1, 0, 2), (1, 0, 512, 1, 1, 3), (1, 0, 320, 1, 1, 5), (1, 0, 320, 1, 0, 5)):
+        m.set_option("grid_limit", glim)
         m.set_option("adjoint_tiled", tiled)
         m.set_option("area_formula_csr", heron)
         m.set_option("tile_threads", threads)
         m.set_option("pipeline", pipe)
+        m.set_option("coef_prefetch", kpre)
         T2 = fn(k, m, mode="csr")
         close(T2.values.detach().cpu().numpy(), ref)
         (g,) = torch.autograd.grad(T2.values, k, dev(dv))
         close(g.cpu().numpy().reshape(-1), expect)
     m.set_option("area_formula_csr", 0)
     m.set_option("tile_threads", 320)
-    m.set_option("pipeline", 0)
+    m.set_option("pipeline", 1)
+    m.set_option("coef_prefetch", 1)
+    m.set_option("grid_limit", 0)
     # eager numpy path returns the same matrix as a scipy CSR
     S = fn(coef, m)
     assert np.array_equal(S.indptr, rp) and np.array_equal(S.indices, ci)

@@ -65,35 +65,48 @@ def a16(x):
     return (x + 15) & ~15
 
 
-def parse_blob(buf, dim, d, fwd):
-    """Decode one tile blob exactly as the kernels do (layout: adfem.jl_b200/csrc/plan.h)."""
-    hdr = np.frombuffer(buf, dtype=np.int32, count=8)
-    nrows, nel, nvt, nnz, nsrc, ncls, ent32 = (int(x) for x in hdr[:7])
-    o = 32
-    out = {"nrows": nrows, "nel": nel, "nvt": nvt, "nnz": nnz, "nsrc": nsrc}
+def parse_blob(head, body, dim, d, fwd, sym):
+    """Decode one tile (head + body) exactly as the kernels do (layout: adfem.jl_b200/csrc/plan.h)."""
+    hdr = np.frombuffer(head, dtype=np.int32, count=8)
+    nrows, nel, nvt = (int(x) for x in hdr[:3])
+    out = {"nrows": nrows, "nel": nel, "nvt": nvt}
+    o, buf = 32, head
 
     def take(dtype, count):
         nonlocal o
         a = np.frombuffer(buf, dtype=dtype, count=count, offset=o)
         o += a16(count * np.dtype(dtype).itemsize)
         return a
-    out["rstart"] = take(np.uint32, nrows).astype(np.int64)
     if fwd:
-        out["rlen"] = take(np.uint16, nrows).astype(np.int64)
-    else:
-        out["roff"] = take(np.uint16, nrows + 1)
-    out["elems"] = take(np.int32, nel)
-    out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
-    out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
-    if fwd:
+        ndst, nsrc, ncls, ent32, nnz = int(hdr[3]), int(hdr[4]), int(hdr[5]), int(hdr[6]) & 1, int(hdr[7])
+        out.update(nnz=nnz, nsrc=nsrc)
+        out["elems"] = take(np.int32, nel)
+        assert o == len(head)
+        o, buf = 0, body
+        out["rstart"] = take(np.uint32, nrows).astype(np.int64)
+        if not sym:
+            out["rlen"] = take(np.uint16, nrows).astype(np.int64)
+        out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
+        out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
         out["cls"] = take(np.int32, 4 * ncls).reshape(ncls, 4)
-        e = take(np.uint32 if ent32 else np.uint16, nnz).astype(np.int64)
-        out["ent_lr"], out["ent_j"] = (e & 0xffff, e >> 16) if ent32 else (e & 0xff, e >> 8)
+        e = take(np.uint32 if ent32 else np.uint16, ndst).astype(np.int64)
+        out["dst_lr"], out["dst_j"] = (e & 0xffff, e >> 16) if ent32 else (e & 0xff, e >> 8)
         out["src"] = take(np.uint16, nsrc).astype(np.int64)
         assert ent32 or nrows <= 256
     else:
-        out["lrow"] = take(np.uint16, nnz)
-        out["gidx"] = take(np.uint16, d * d * nel).reshape(d * d, nel)
+        nnz, flags = int(hdr[3]), int(hdr[4])
+        out["nnz"] = nnz
+        out["rstart"] = take(np.uint32, nrows).astype(np.int64)
+        out["roff"] = take(np.uint16, nrows + 1)
+        out["lrow"] = take(np.uint16 if flags & 1 else np.uint8, nnz)
+        assert (flags & 1) or nrows <= 256
+        assert o == len(head)
+        o, buf = 0, body
+        out["elems"] = take(np.int32, nel)
+        out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
+        out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
+        out["td"] = take(np.uint16, d * nel).reshape(d, nel) if flags & 2 else out["tv"]
+        out["gpos"] = take(np.uint8, d * d * nel).reshape(d * d, nel)
     assert o == len(buf)
     return out
 
@@ -101,9 +114,11 @@ def parse_blob(buf, dim, d, fwd):
 def tiles_of(m, which, ncomp):
     ptr = m.plan_array(which, ncomp, 0, np.int64)
     blob = m.plan_array(which, ncomp, 1, np.uint8).tobytes()
-    for t in range(len(ptr) - 1):
-        assert ptr[t] % 16 == 0 and (ptr[t + 1] - ptr[t]) % 16 == 0          # TMA bulk copy alignment rules
-    return [parse_blob(blob[ptr[t]:ptr[t + 1]], m.dim, m.elem_ndof, which == 0) for t in range(len(ptr) - 1)]
+    assert len(ptr) % 2 == 1
+    assert (ptr % 16 == 0).all()                                              # TMA bulk copy alignment rules (address and size)
+    nt = (len(ptr) - 1) // 2
+    return [parse_blob(blob[ptr[2 * t]:ptr[2 * t + 1]], blob[ptr[2 * t + 1]:ptr[2 * t + 2]], m.dim, m.elem_ndof, which == 0, ncomp == 1)
+            for t in range(nt)]
 
 
 def _check_tile_geometry(m, T):
@@ -125,20 +140,23 @@ def _fwd_replay(m, local, ncomp, n_out):
             i += 1
     vals = np.full(n_out, np.nan)
     written = np.zeros(n_out, dtype=np.int32)
-    ntiles = 0
+    ntiles = npaired = 0
     for T in tiles_of(m, 0, ncomp):
         ntiles += 1
         _check_tile_geometry(m, T)
         nel = T["nel"]
         loc = local[T["elems"]]                               # [nel, S]
-        assert np.array_equal(T["rlen"], rowptr[1:][np.searchsorted(rowptr[:-1], T["rstart"])] - T["rstart"])
-        assert T["cls"][:, 1].sum() == T["nnz"] and (np.diff(T["cls"][:, 0]) > 0).all()
-        for cnt, n, so, eo in T["cls"]:
+        rlen = rowptr[1:][np.searchsorted(rowptr[:-1], T["rstart"])] - T["rstart"]
+        if ncomp > 1:
+            assert np.array_equal(T["rlen"], rlen)
+        assert rlen.sum() == T["nnz"] and (np.diff(T["cls"][:, 0]) > 0).all()
+        for key, n, so, do in T["cls"]:
+            cnt, paired = key & 0xffff, key >> 16
+            assert not (paired and ncomp > 1)
             for i in range(n):
                 cs = T["src"][so + np.arange(cnt) * n + i]
-                lr, j = int(T["ent_lr"][eo + i]), int(T["ent_j"][eo + i])
-                rs, ln = int(T["rstart"][lr]), int(T["rlen"][lr])
-                assert j < ln
+                dests = [do + i] + ([do + n + i] if paired else [])
+                npaired += paired
                 if ncomp == 1:
                     v = 0.0
                     for c in cs:
@@ -146,9 +164,15 @@ def _fwd_replay(m, local, ncomp, n_out):
                         p, q = sym[s]
                         assert abs(loc[le, p * d + q] - loc[le, q * d + p]) <= 1e-14 * abs(loc[le]).max()
                         v += loc[le, p * d + q]
-                    vals[rs + j] = v
-                    written[rs + j] += 1
+                    for dk in dests:
+                        lr, j = int(T["dst_lr"][dk]), int(T["dst_j"][dk])
+                        assert j < rlen[lr]
+                        vals[T["rstart"][lr] + j] = v
+                        written[T["rstart"][lr] + j] += 1
                 else:
+                    lr, j = int(T["dst_lr"][do + i]), int(T["dst_j"][do + i])
+                    rs, ln = int(T["rstart"][lr]), int(rlen[lr])
+                    assert j < ln
                     le, pq = cs // dd, cs % dd
                     p, q = pq // d, pq % d
                     for a in range(ncomp):
@@ -160,6 +184,7 @@ def _fwd_replay(m, local, ncomp, n_out):
                             vals[dest] = v
                             written[dest] += 1
     assert (written == 1).all()                                # every CSR entry is produced exactly once
+    assert ncomp > 1 or npaired > 0                            # symmetric pairs are really merged
     return vals, ntiles
 
 
@@ -217,7 +242,11 @@ def test_adjoint_plan_replay(oracle, name, degree):
         lr = T["lrow"].astype(int)
         assert np.array_equal(staged, dvals[T["rstart"][lr] + np.arange(T["nnz"]) - T["roff"][lr].astype(int)])   # the kernel's staging loop
         tel = T["elems"]
-        assert np.array_equal(staged[T["gidx"].T.astype(int)], dvals[s2n[tel]])
+        # the kernel's gather: staged[roff[td_p] + gpos[p*d+q]]
+        idx = T["roff"].astype(int)[T["td"].astype(int)][np.repeat(np.arange(d), d)] + T["gpos"].astype(int)      # [dd, nel]
+        assert np.array_equal(staged[idx.T], dvals[s2n[tel]])
+        if degree == 1:
+            assert T["td"] is T["tv"]                          # P1: the staged rows are the tile vertices (no td section)
         seen[tel] += 1
     assert (seen == 1).all()
 
