@@ -19,7 +19,7 @@ c_ip = C.POINTER(C.c_int)
 OP_LAPLACE, OP_MASS, OP_STIFFNESS = 0, 1, 2
 HOST_ONLY = 1
 (INFO_DIM, INFO_NV, INFO_NE, INFO_NDOF, INFO_NGAUSS, INFO_ELEM_NDOF, INFO_NEDGES, INFO_GAUSS_PER_ELEM, INFO_NNZ_SCALAR,
- INFO_TILES_FWD, INFO_TILES_ADJ, INFO_PLAN_BYTES) = range(12)
+ INFO_TILES_FWD, INFO_TILES_ADJ, INFO_PLAN_BYTES, INFO_STRUCTURED) = range(13)
 
 
 class AdfemError(RuntimeError):

@@ -15,6 +15,7 @@
 #include "internal.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "tri_grid.cuh"
 
 using namespace adfem;
 
@@ -70,11 +71,16 @@ struct adfem_mesh {
   int opt_smem_budget = 72 * 1024;          // dynamic shared memory per CTA (3 head + 2 body buffers + staging): 3 CTAs per SM
   int opt_tile_threads = 320;
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
+  int opt_variant = 0;                      // forward tuning bits: 1 = rotate gather chunks over the warps, 2 = balanced phase A mapping
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
   bool adj_untileable = false;              // a CSR row has more than 255 entries: adjoint uses the direct gather kernel
   int num_sms = 0;
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
+  // structured triangulation Mesh(m, n, h) (tri_grid.cuh): detected from the arrays, no mesh-static index data is read
+  bool grid_ok = false;
+  int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0;
+  DevBuf<double> grid_xs, grid_ys;
   // scratch for the host-buffer calls
   DevBuf<double> s_in, s_out;
 };
@@ -95,6 +101,42 @@ int need_device(const adfem_mesh* m) {
   return 0;
 }
 
+// Is this the reference's structured triangulation (src/MFEM/MFEM.jl:134-146, version 1) on rectilinear coordinates?
+bool detect_tri_grid(const HostMesh& h, int& m, int& n, std::vector<double>& xs, std::vector<double>& ys) {
+  if (h.dim != 2 || h.degree != 1 || h.g != 3 || h.ne < 2 || h.nv < 4) return false;
+  const int* v = h.verts.data();
+  if (v[0] != 0 || v[1] != 1 || v[2] < 2) return false;
+  m = v[2] - 1;
+  if (h.ne % (2 * m) != 0) return false;
+  n = h.ne / (2 * m);
+  if ((long long)(m + 1) * (n + 1) != h.nv) return false;
+  for (int ci = 0; ci < n; ci++)
+    for (int cj = 0; cj < m; cj++) {
+      const int a = ci * (m + 1) + cj;
+      const int* t = v + 6 * ((size_t)ci * m + cj);
+      if (t[0] != a || t[1] != a + 1 || t[2] != a + m + 1 || t[3] != a + m + 1 || t[4] != a + 1 || t[5] != a + m + 2) return false;
+    }
+  xs.resize(m + 1); ys.resize(n + 1);
+  for (int j = 0; j <= m; j++) xs[j] = h.coords[2 * (size_t)j];
+  for (int i = 0; i <= n; i++) ys[i] = h.coords[2 * (size_t)i * (m + 1) + 1];
+  for (int j = 0; j < m; j++) if (!(xs[j] < xs[j + 1])) return false;
+  for (int i = 0; i < n; i++) if (!(ys[i] < ys[i + 1])) return false;
+  for (int i = 0; i <= n; i++)
+    for (int j = 0; j <= m; j++) {
+      const double* c = &h.coords[2 * ((size_t)i * (m + 1) + j)];
+      if (c[0] != xs[j] || c[1] != ys[i]) return false;       // bitwise: the kernels recompute nothing, they index xs / ys
+    }
+  return true;
+}
+
+// the closed-form row pointers of tri_grid.cuh must reproduce the symbolic pattern exactly
+bool grid_pattern_matches(const ScalarPattern& pat, int m, int n) {
+  if (pat.n != (m + 1) * (n + 1)) return false;
+  for (int i = 0; i <= n; i++)
+    for (int j = 0; j <= m; j++) if (pat.rowptr[(size_t)i * (m + 1) + j] != grid_rowptr(i, j, m, n)) return false;
+  return pat.nnz == grid_rowptr(n, m + 1, m, n);
+}
+
 int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_threads : default_threads(); }
 
 int ensure_pattern(adfem_mesh* m) {
@@ -102,6 +144,7 @@ int ensure_pattern(adfem_mesh* m) {
   std::string err = m->pat.build(m->hm, nthreads_of(m));
   if (!err.empty()) return fail("symbolic: " + err);
   m->has_pattern = true;
+  if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;
   if (!m->host_only) {
     const HostMesh& h = m->hm;
     const int dd = h.d * h.d;
@@ -182,6 +225,8 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
     const double per_elem = rows_per_elem * 1.3 * (nnz_per_row * (2 * 8.0 * nc * nc + 3 * 1) + 3 * 6) + 2 * (4 + 2 * (h.dim + 1) + 8 * h.dim * rows_per_elem + 1.0 * dd + (h.degree == 2 ? 2 * h.d : 0));
     int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(budget / per_elem);
     EPT = std::max(4, std::min(EPT, 4096));
+    // every thread of the CTA gets the same number of elements
+    if (m->opt_elems_per_tile <= 0 && EPT >= m->opt_tile_threads) EPT -= EPT % m->opt_tile_threads;
     const int max_nnz = 65535;
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
@@ -236,7 +281,8 @@ int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, const d
   int grid = 0;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (int rc = tile_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
-  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
+  DevTiles dt = P->dev; dt.sym |= m->opt_variant << 1;
+  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, dt, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -248,7 +294,8 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
   if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
   if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
     // register prefetch of the next tile's coefficients
-    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * m->opt_tile_threads)
+    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * m->opt_tile_threads &&
+        (!(m->opt_variant & 2) || ((((P->host.max_elems + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31) <= m->opt_tile_threads))
       return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true>, P, smem, coef, vals, st);
   }
   return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false>, P, smem, coef, vals, st);
@@ -268,6 +315,31 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
   } else {
     k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+bool use_grid(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }
+
+int grid_rows_per_warp(const adfem_mesh* m, int strips, int rows) {
+  if (m->opt_grid_rows > 0) return m->opt_grid_rows;
+  const int want_chunks = std::max(1, 8192 / std::max(1, strips));      // ~8k warps on the device
+  return std::max(8, (rows + want_chunks - 1) / want_chunks);
+}
+
+template <int OP> int launch_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st) {
+  GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
+  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n + 1), chunks = (gt.n + 1 + H - 1) / H;
+  const long long warps = (long long)strips * chunks;
+  k_grid_fwd<OP><<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
+  GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
+  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n), chunks = (gt.n + H - 1) / H;
+  const long long warps = (long long)strips * chunks;
+  k_grid_adj<OP><<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -308,6 +380,8 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
   std::string err = m->hm.build(dim, vertices, vertex_stride, nv, elems, ne, order, degree, lorder);
   if (!err.empty()) return fail(err);
   m->host_only = (flags & ADFEM_HOST_ONLY) != 0;
+  std::vector<double> grid_xs, grid_ys;
+  m->grid_ok = detect_tri_grid(m->hm, m->grid_m, m->grid_n, grid_xs, grid_ys);
   if (!m->host_only) {
     if (adfem_device_count() == 0) return fail("no CUDA device available (libadfem_cuda has no CPU fallback)");
     CU_TRY(cudaGetDevice(&m->device));
@@ -323,6 +397,7 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
     CU_TRY(upload(m->conn, cs));
     m->dm.dim = h.dim; m->dm.ne = h.ne; m->dm.nv = h.nv; m->dm.d = h.d; m->dm.g = h.g; m->dm.ndof = h.ndof;
     m->dm.coords = m->coords.p; m->dm.verts = m->verts.p; m->dm.conn = m->conn.p; m->dm.rule = h.rule;
+    if (m->grid_ok) { CU_TRY(upload(m->grid_xs, grid_xs)); CU_TRY(upload(m->grid_ys, grid_ys)); }
   }
   *out = m.release();
   return 0;
@@ -351,6 +426,7 @@ long long adfem_mesh_info(const adfem_mesh* m, int what) {
       for (auto& kv : m->adj_plans) b += (long long)kv.second->bytes;
       return b;
     }
+    case ADFEM_INFO_STRUCTURED: return m->grid_ok ? 1 : 0;
     default: return -1;
   }
 }
@@ -386,10 +462,13 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
-  else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); m->opt_tile_threads = (int)value; }
+  else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
   else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
+  else if (k == "variant") m->opt_variant = (int)value & 3;
+  else if (k == "structured") m->opt_structured = value != 0;
+  else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
   else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);
@@ -455,6 +534,9 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   if (int rc = check_op(m, op)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
+  if (op != ADFEM_OP_STIFFNESS && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
+  if (op != ADFEM_OP_STIFFNESS && use_grid(m))
+    return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   FwdPlanDev* P = nullptr;
   if (int rc = ensure_fwd_plan(m, nc, &P)) return rc;
 #define CALL_FWD(DIM, DEG)                                                                                   \
@@ -473,6 +555,8 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
   if (int rc = check_op(m, op)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (op != ADFEM_OP_STIFFNESS && use_grid(m))
+    return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
 #define CALL_ADJ(DIM, DEG)                                                                                   \
   switch (op) {                                                                                              \
     case ADFEM_OP_LAPLACE: return launch_adj<DIM, DEG, OP_LAPLACE>(m, dvals, grad_coef, st);                 \

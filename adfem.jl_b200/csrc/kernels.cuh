@@ -20,7 +20,7 @@ struct DevPattern {
   const uint32_t* slot_nnz;       // [d*d][ne] struct-of-arrays
 };
 struct DevTiles {                  // forward (FwdTiles) or adjoint (AdjTiles) blobs on the device
-  int ntiles, sym;
+  int ntiles, sym;                 // sym doubles as a tuning bit mask in the kernels: bit1 = rotate gather chunks, bit2 = balanced phase A
   unsigned max_head, max_body;     // bytes, multiples of 16
   int max_elems, max_nnz;
   const long long* blob_ptr;       // 2*ntiles+1: head offset, body offset per tile, then the end
@@ -395,10 +395,10 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& 
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Contract the upstream gradients `g(l, s)` of one element's local matrix with its shape tables: writes
-// grad_coef for every Gauss point of the element.
-template <int DIM, int DEG, int OP, typename Get>
-__device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>& G, int e, Get g, double* __restrict__ grad_coef) {
+// Scalar operators: contract the upstream gradients `g(p, q)` of one element's local matrix with its shape tables and
+// hand the gradient w.r.t. the coefficient at Gauss point k to `out(k, value)`.  GMAX as in for_gauss.
+template <int DIM, int DEG, int OP, int GMAX, typename Get, typename Out>
+__device__ __forceinline__ void local_adjoint_scalar(const DevMesh& m, const Geom<DIM>& G, Get g, Out out) {
   constexpr int D = ElemTraits<DIM, DEG>::D;
   if (OP == OP_LAPLACE && DEG == 1) {
     double s = 0.0;
@@ -406,8 +406,8 @@ __device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>&
     for (int p = 0; p < D; p++)
 #pragma unroll
       for (int q = 0; q < D; q++) s += g(p, q) * dotg<DIM>(G.gL[p], G.gL[q]);
-    for (int k = 0; k < m.g; k++) grad_coef[(size_t)e * m.g + k] = s * (m.rule.w[k] * G.wscale);
-  } else if (OP == OP_LAPLACE || OP == OP_MASS) {
+    for_gauss<GMAX>(m.g, [&](int k) { out(k, s * (m.rule.w[k] * G.wscale)); });
+  } else {
     constexpr int NA = D * (D + 1) / 2;     // only the symmetric part of g matters
     double gs[NA];
     { int i = 0;
@@ -415,7 +415,7 @@ __device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>&
       for (int p = 0; p < D; p++)
 #pragma unroll
         for (int q = p; q < D; q++) gs[i++] = (q == p) ? g(p, p) : g(p, q) + g(q, p); }
-    for (int k = 0; k < m.g; k++) {
+    for_gauss<GMAX>(m.g, [&](int k) {
       double L[DIM + 1]; bary<DIM>(m.rule, k, L);
       double v = 0.0;
       if (OP == OP_LAPLACE) {
@@ -433,8 +433,19 @@ __device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>&
 #pragma unroll
           for (int q = p; q < D; q++) v += gs[i++] * phi[p] * phi[q];
       }
-      grad_coef[(size_t)e * m.g + k] = v * (m.rule.w[k] * G.wscale);
-    }
+      out(k, v * (m.rule.w[k] * G.wscale));
+    });
+  }
+}
+
+// Contract the upstream gradients `g(l, s)` of one element's local matrix with its shape tables: writes
+// grad_coef for every Gauss point of the element.
+template <int DIM, int DEG, int OP, typename Get>
+__device__ __forceinline__ void local_adjoint(const DevMesh& m, const Geom<DIM>& G, int e, Get g, double* __restrict__ grad_coef) {
+  constexpr int D = ElemTraits<DIM, DEG>::D;
+  if (OP == OP_LAPLACE || OP == OP_MASS) {
+    double* ge = grad_coef + (size_t)e * m.g;
+    local_adjoint_scalar<DIM, DEG, OP, 0>(m, G, g, [&](int k, double v) { ge[k] = v; });
   } else {
     constexpr int NS = Voigt<DIM>::NS;
     for (int k = 0; k < m.g; k++) {
@@ -568,18 +579,23 @@ struct FwdView {
 
 // phase B of the scalar forward: every gather item sums its sources in a fixed order and is written once (twice for a
 // paired item: the (r,c) and (c,r) entries of a symmetric local-matrix sum)
-__device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double* __restrict__ loc, double* __restrict__ vals, int tid, int nth) {
+__device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double* __restrict__ loc, double* __restrict__ vals, int tid, int nth, bool rotate) {
+  // 32-item chunks of every class are dealt to the warps round-robin, continuing across classes, so that no warp idles through
+  // a small class while others work: `first` is the lane offset of this thread's first item in the current class
+  int rot = 0;
   for (int c = 0; c < V.ncls; c++) {
     const int key = V.cls[4 * c], cnt = key & 0xffff, paired = key >> 16, n = V.cls[4 * c + 1];
     const unsigned short* sc = V.src + V.cls[4 * c + 2];
     const int d0 = V.cls[4 * c + 3];
+    int first = tid - rot; if (first < 0) first += nth;
+    if (rotate) rot = (rot + ((n + 31) & ~31)) % nth;
     auto put = [&](int i, double v) {
       int lr, j; V.dest(d0 + i, lr, j);
       vals[(size_t)V.rstart[lr] + j] = v;
       if (paired) { V.dest(d0 + n + i, lr, j); vals[(size_t)V.rstart[lr] + j] = v; }
     };
 #define ADFEM_GATHER_CLASS(C)                                                              \
-    for (int i = tid; i < n; i += nth) {                                                   \
+    for (int i = first; i < n; i += nth) {                                                 \
       double v = 0.0;                                                                      \
       _Pragma("unroll") for (int k = 0; k < C; k++) v += loc[sc[k * n + i]];             \
       put(i, v);                                                                           \
@@ -594,7 +610,7 @@ __device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double
       case 7: ADFEM_GATHER_CLASS(7) break;
       case 8: ADFEM_GATHER_CLASS(8) break;
       default:
-        for (int i = tid; i < n; i += nth) {
+        for (int i = first; i < n; i += nth) {
           double v = 0.0;
           for (int k = 0; k < cnt; k++) v += loc[sc[k * n + i]];
           put(i, v);
@@ -609,6 +625,8 @@ __device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double
 // operators, g <= PIPE_GMAX Gauss points, at most PIPE_EPT tile elements per thread): the coefficients of the NEXT tile
 // are loaded into registers before phase B of the current one; otherwise they are prefetched into L2 at that point.
 constexpr int PIPE_GMAX = 4, PIPE_EPT = 2;
+// a thread owns tile elements tid + s*part, s < PIPE_EPT: every active thread gets the same number of elements (whole warps)
+__device__ __forceinline__ int pipe_part(int nel) { return (((nel + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31; }
 template <int DIM, int DEG, int OP, bool KPRE>
 __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
                                                                double* __restrict__ vals) {
@@ -631,10 +649,11 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     const int nel = hdr[1];
     const int* elems = hdr + 8;
     if constexpr (KPRE) {
+      const int part = (tp.sym & 4) ? pipe_part(nel) : nth;
 #pragma unroll
       for (int s = 0; s < PIPE_EPT; s++) {
-        const int le = tid + s * nth;
-        if (le < nel) {
+        const int le = tid + s * part;
+        if (tid < part && le < nel) {
           const double* p = coef + (size_t)elems[le] * g;
 #pragma unroll
           for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
@@ -655,10 +674,11 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     const FwdView V(R.head(i), R.body(i), NVL, DIM, NC > 1);
     // ---- phase A
     if constexpr (KPRE) {
+      const int part = (tp.sym & 4) ? pipe_part(V.nel) : nth;
 #pragma unroll
       for (int s = 0; s < PIPE_EPT; s++) {
-        const int le = tid + s * nth;
-        if (le < V.nel) {
+        const int le = tid + s * part;
+        if (tid < part && le < V.nel) {
           Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
           local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
         }
@@ -675,7 +695,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     if (i + 1 < R.count) { R.wait_head(i + 1); fetch_coef(R.head(i + 1)); }
     // ---- phase B
     if constexpr (NC == 1) {
-      fwd_gather_scalar(V, loc, vals, tid, nth);
+      fwd_gather_scalar(V, loc, vals, tid, nth, (tp.sym & 2) != 0);
     } else {
       for (int c = 0; c < V.ncls; c++) {
         const int cnt = V.cls[4 * c] & 0xffff, n = V.cls[4 * c + 1];
@@ -709,13 +729,13 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
 // decoded view of an adjoint tile
 struct AdjView {
   int nrows, nel, nvt, nnz_t, lrow16;
-  const unsigned* rstart; const unsigned short* roff; const unsigned char* lrow;
-  const int* elems; const unsigned short* tv; const double* xy; const unsigned short* td; const unsigned char* gpos;
+  const unsigned* delta; const unsigned short* roff; const unsigned char* lrow;
+  const int* elems; const unsigned short* tv; const double* xy; const unsigned short* td; const unsigned* gpk;
   __device__ __forceinline__ void set_head(const unsigned char* head) {
     const int* hdr = reinterpret_cast<const int*>(head);
     nrows = hdr[0]; nel = hdr[1]; nvt = hdr[2]; nnz_t = hdr[3]; lrow16 = hdr[4] & 1;
     unsigned o = 32;
-    rstart = reinterpret_cast<const unsigned*>(head + o); o += a16(4u * nrows);
+    delta = reinterpret_cast<const unsigned*>(head + o); o += a16(4u * nrows);
     roff = reinterpret_cast<const unsigned short*>(head + o); o += a16(2u * (nrows + 1));
     lrow = head + o;
   }
@@ -726,17 +746,17 @@ struct AdjView {
     tv = reinterpret_cast<const unsigned short*>(body + o); o += a16(2u * nvl * nel);
     xy = reinterpret_cast<const double*>(body + o); o += a16(8u * dim * nvt);
     td = has_td ? reinterpret_cast<const unsigned short*>(body + o) : tv; if (has_td) o += a16(2u * d * nel);
-    gpos = body + o;
+    gpk = reinterpret_cast<const unsigned*>(body + o);
   }
 };
 
 // Adjoint.  The CSR rows the tile's elements touch are staged into shared memory with asynchronous copies (LDGSTS) one
-// tile ahead; every element then gathers its d*d upstream gradients from shared memory (row base roff[td_p] + position
-// gpos) and contracts them with its shape tables.
+// tile ahead; every element then gathers its d*d upstream gradients from shared memory (row base roff[td_p] + 8-bit
+// position, four positions per 32-bit word) and contracts them with its shape tables.  One CTA-wide barrier per tile.
 template <int DIM, int DEG, int OP>
 __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long long nnz_s, DevTiles ap, const double* __restrict__ dvals,
                                                                double* __restrict__ grad_coef) {
-  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, NVL = DIM + 1;
+  constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, NVL = DIM + 1, W = (D + 3) / 4;
   extern __shared__ __align__(128) unsigned char smem_all[];
   __shared__ __align__(8) uint64_t mbar[5];
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -752,10 +772,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
     AdjView H; H.set_head(head);
     for (int i = tid; i < H.nnz_t; i += nth) {
       const int lr = H.lrow16 ? (int)reinterpret_cast<const unsigned short*>(H.lrow)[i] : (int)H.lrow[i];
-      const int j = i - H.roff[lr];
-      if (NC == 1) cp_async8(sd + i, dvals + ((size_t)H.rstart[lr] + j));
+      if (NC == 1) cp_async8(sd + i, dvals + (unsigned)(i + H.delta[lr]));
       else {
-        const long long len = H.roff[lr + 1] - H.roff[lr], rs = H.rstart[lr];
+        const long long len = H.roff[lr + 1] - H.roff[lr], rs = (unsigned)(H.roff[lr] + H.delta[lr]), j = i - H.roff[lr];
 #pragma unroll
         for (int a = 0; a < NC; a++)
 #pragma unroll
@@ -765,10 +784,11 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
   };
   R.wait_head(0);
   stage(R.head(0), sd_all);
+  cp_async_wait_all();
+  __syncthreads();
   for (int i = 0; i < R.count; i++) {
+    // here: sd[i&1] is complete and visible; every thread is done with tile i-1
     const double* sd = sd_all + (i & 1) * sd_stride;
-    cp_async_wait_all();
-    __syncthreads();                                       // sd[i&1] complete and visible to every thread
     if (i + 1 < R.count) { R.wait_head(i + 1); stage(R.head(i + 1), sd_all + ((i + 1) & 1) * sd_stride); }
     R.wait_body(i);
     AdjView V; V.set_head(R.head(i)); V.set_body(R.head(i), R.body(i), NVL, DIM, D);
@@ -776,18 +796,24 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
       Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
       const int e = V.elems[le];
       if constexpr (NC == 1) {
-        int rb[D];
+        unsigned pk[D][W]; int rb[D];
 #pragma unroll
-        for (int p = 0; p < D; p++) rb[p] = V.roff[V.td[p * V.nel + le]];
-        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[rb[p] + V.gpos[(p * D + q) * V.nel + le]]; }, grad_coef);
+        for (int p = 0; p < D; p++) {
+          rb[p] = V.roff[V.td[p * V.nel + le]];
+#pragma unroll
+          for (int w = 0; w < W; w++) pk[p][w] = V.gpk[(p * W + w) * V.nel + le];
+        }
+        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[rb[p] + ((pk[p][q >> 2] >> (8 * (q & 3))) & 0xffu)]; }, grad_coef);
       } else {
         local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
           const int a = l / D, p = l % D, b = s / D, q = s % D;
-          return sd[(a * NC + b) * V.nnz_t + V.roff[V.td[p * V.nel + le]] + V.gpos[(p * D + q) * V.nel + le]];
+          const unsigned pos = (V.gpk[(p * W + (q >> 2)) * V.nel + le] >> (8 * (q & 3))) & 0xffu;
+          return sd[(a * NC + b) * V.nnz_t + V.roff[V.td[p * V.nel + le]] + pos];
         }, grad_coef);
       }
     }
-    __syncthreads();                                       // sd[i&1] and the buffers of tile i are free again
+    cp_async_wait_all();
+    __syncthreads();                                       // tile i is finished everywhere AND sd[(i+1)&1] is complete and visible
     if (tid == 0) R.refill_after(i);
   }
 }

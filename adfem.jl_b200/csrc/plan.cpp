@@ -368,7 +368,8 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
   std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
     std::vector<int> tr, te(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]), tvert;
     std::vector<uint16_t> tv, roff, lrow16, td;
-    std::vector<uint8_t> lrow8, gpos;
+    std::vector<uint8_t> lrow8;
+    std::vector<uint32_t> gpk, delta;
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
     const int nel = (int)te.size();
@@ -382,20 +383,24 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     for (int lr = 0; lr < nrows; lr++) {
       const long long rs = pat.rowptr[tr[lr]], len = pat.rowptr[tr[lr] + 1] - rs;
       rstart.push_back((uint32_t)rs);
+      delta.push_back((uint32_t)rs - (uint32_t)acc);      // global offset of staged entry i of this row = i + delta
       acc += len;
       if (acc > max_tile_nnz || acc > 65535 || nrows > 65535) { P.err = "tile too large"; return; }
       for (long long j = 0; j < len; j++) { if (lrow_wide) lrow16.push_back((uint16_t)lr); else lrow8.push_back((uint8_t)lr); }
       roff.push_back((uint16_t)acc);
     }
     tile_vertices(m, te, tvert, tv, xy);
-    td.resize((size_t)d * nel); gpos.resize((size_t)dd * nel);
+    const int W = (d + 3) / 4;                    // 32-bit words holding the d 8-bit positions of one local row
+    td.resize((size_t)d * nel); gpk.assign((size_t)d * W * nel, 0);
     for (int le = 0; le < nel; le++) {
       const int e = te[le];
       const int* ce = &m.conn[(size_t)e * d];
       for (int p = 0; p < d; p++) {
         td[(size_t)p * nel + le] = (uint16_t)(std::lower_bound(tr.begin(), tr.end(), ce[p]) - tr.begin());
-        for (int q = 0; q < d; q++)
-          gpos[(size_t)(p * d + q) * nel + le] = (uint8_t)((long long)pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]]);
+        for (int q = 0; q < d; q++) {
+          const uint32_t pos = (uint32_t)((long long)pat.slot_nnz[((size_t)e * d + p) * d + q] - pat.rowptr[ce[p]]);
+          gpk[(size_t)(p * W + q / 4) * nel + le] |= pos << (8 * (q % 4));
+        }
       }
     }
     // P1: the staged rows are the tile vertices in the same order, so td == tv and is not stored
@@ -403,12 +408,12 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     int hdr[8] = {nrows, nel, (int)tvert.size(), (int)acc, lrow_wide | has_td << 1, 0, 0, 0};
     const size_t at0 = P.blob.size();
     BlobWriter w(P.blob);
-    w.section(hdr, 8); w.section(rstart); w.section(roff);
+    w.section(hdr, 8); w.section(delta); w.section(roff);
     if (lrow_wide) w.section(lrow16); else w.section(lrow8);
     const size_t at1 = P.blob.size();
     w.section(te); w.section(tv); w.section(xy);
     if (has_td) w.section(td);
-    w.section(gpos);
+    w.section(gpk);
     P.sizes.push_back((long long)(at1 - at0)); P.sizes.push_back((long long)(P.blob.size() - at1));
     P.max_rows = std::max(P.max_rows, nrows); P.max_elems = std::max(P.max_elems, nel); P.max_nnz = std::max(P.max_nnz, (int)acc);
     P.max_verts = std::max(P.max_verts, (int)tvert.size());

@@ -74,7 +74,8 @@ struct FwdTiles {
 // ---- adjoint tile blob -----------------------------------------------------------------------------
 // HEAD
 //   hdr    int32[8]            {nrows, nel, nvt, nnz, flags (bit0: 16-bit lrow, bit1: td present), 0, 0, 0}
-//   rstart uint32[nrows]       CSR offset of each staged row
+//   delta  uint32[nrows]       CSR offset of each staged row minus its offset in the staging buffer (mod 2^32): staged entry i
+//                              of that row is global entry i + delta
 //   roff   uint16[nrows+1]     offset of each staged row inside the staging buffer
 //   lrow   uint8|uint16[nnz]   staged row of every staged entry
 // BODY
@@ -83,7 +84,8 @@ struct FwdTiles {
 //   xy     double[dim*nvt]
 //   td     uint16[d*nel]       staged row of each local dof, k-major — only when it differs from tv (P2); for P1 the staged
 //                              rows ARE the tile vertices in the same (ascending) order
-//   gpos   uint8[d*d*nel]      pq-major: position of slot (le,p,q) inside its CSR row; the staged entry is roff[td_p] + gpos
+//   gpk    uint32[d*W*nel]     W = ceil(d/4); word (p*W + q/4)*nel + le, byte q%4: position of slot (le,p,q) inside its CSR row;
+//                              the staged entry is roff[td_p] + position
 struct AdjTiles {
   int ntiles = 0, elems_per_tile = 0;
   int max_rows = 0, max_elems = 0, max_nnz = 0, max_verts = 0;

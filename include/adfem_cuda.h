@@ -93,7 +93,9 @@ enum { ADFEM_HOST_ONLY = 1 };          /* flags: build host tables/plans only (i
 enum { ADFEM_OP_LAPLACE = 0, ADFEM_OP_MASS = 1, ADFEM_OP_STIFFNESS = 2 };
 enum { ADFEM_INFO_DIM = 0, ADFEM_INFO_NV, ADFEM_INFO_NE, ADFEM_INFO_NDOF, ADFEM_INFO_NGAUSS, ADFEM_INFO_ELEM_NDOF,
        ADFEM_INFO_NEDGES, ADFEM_INFO_GAUSS_PER_ELEM, ADFEM_INFO_NNZ_SCALAR, ADFEM_INFO_TILES_FWD, ADFEM_INFO_TILES_ADJ,
-       ADFEM_INFO_PLAN_BYTES };
+       ADFEM_INFO_PLAN_BYTES,
+       ADFEM_INFO_STRUCTURED /* 1: the mesh is the structured triangulation Mesh(m,n,h) v1 on rectilinear nodes and the scalar CSR
+                                operators use the index-free kernels of csrc/tri_grid.cuh (option "structured" = 0 disables) */ };
 
 /* Replaces init_nnfem_mesh / init_nnfem_mesh3 (deps/MFEM/API.cpp:4, deps/MFEM3/API.cpp:4) without the
  * process-global singleton.  dim = 2|3; vertices: nv rows of `vertex_stride` doubles (first `dim` used);
@@ -109,7 +111,7 @@ int adfem_mesh_element_to_vertices(const adfem_mesh* m, long long* elems);    /*
 int adfem_mesh_gauss(const adfem_mesh* m, double* xyz);                       /* dim blocks of ngauss (column-major) */
 int adfem_mesh_gauss_weights(const adfem_mesh* m, double* w);
 int adfem_mesh_measure(const adfem_mesh* m, double* a);                       /* Heron area (2-D) / volume (3-D) */
-int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads", "smem_budget", "tile_threads", "area_formula_csr", "area_formula_coo" */
+int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads", "smem_budget", "tile_threads", "pipeline", "coef_prefetch", "structured", "grid_rows", "grid_limit", "area_formula_csr", "area_formula_coo" */
 
 /* Mesh-static symbolic phase (what Julia's sparse() / TF's sparse ops redo on every call downstream of the
  * reference's COO, src/MFEM/MCore.jl:118-119).  ncomp = 1: scalar operators, n = ndof.  ncomp = dim: the

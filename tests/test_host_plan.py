@@ -96,8 +96,9 @@ def parse_blob(head, body, dim, d, fwd, sym):
     else:
         nnz, flags = int(hdr[3]), int(hdr[4])
         out["nnz"] = nnz
-        out["rstart"] = take(np.uint32, nrows).astype(np.int64)
+        out["delta"] = take(np.uint32, nrows)
         out["roff"] = take(np.uint16, nrows + 1)
+        out["rstart"] = ((out["delta"].astype(np.uint64) + out["roff"][:-1]) & 0xffffffff).astype(np.int64)
         out["lrow"] = take(np.uint16 if flags & 1 else np.uint8, nnz)
         assert (flags & 1) or nrows <= 256
         assert o == len(head)
@@ -106,7 +107,9 @@ def parse_blob(head, body, dim, d, fwd, sym):
         out["tv"] = take(np.uint16, (dim + 1) * nel).reshape(dim + 1, nel)
         out["xy"] = take(np.float64, dim * nvt).reshape(nvt, dim)
         out["td"] = take(np.uint16, d * nel).reshape(d, nel) if flags & 2 else out["tv"]
-        out["gpos"] = take(np.uint8, d * d * nel).reshape(d * d, nel)
+        W = (d + 3) // 4
+        gpk = take(np.uint32, d * W * nel).reshape(d, W, nel)
+        out["gpos"] = np.stack([(gpk[p, q // 4] >> (8 * (q % 4))) & 0xff for p in range(d) for q in range(d)])      # [dd, nel]
     assert o == len(buf)
     return out
 
@@ -240,7 +243,7 @@ def test_adjoint_plan_replay(oracle, name, degree):
         staged = np.concatenate([dvals[rs:rs + ln] for rs, ln in zip(T["rstart"], np.diff(T["roff"].astype(int)))])
         assert len(staged) == T["nnz"]
         lr = T["lrow"].astype(int)
-        assert np.array_equal(staged, dvals[T["rstart"][lr] + np.arange(T["nnz"]) - T["roff"][lr].astype(int)])   # the kernel's staging loop
+        assert np.array_equal(staged, dvals[(np.arange(T["nnz"], dtype=np.uint64) + T["delta"][lr]) & 0xffffffff])   # the kernel's staging loop
         tel = T["elems"]
         # the kernel's gather: staged[roff[td_p] + gpos[p*d+q]]
         idx = T["roff"].astype(int)[T["td"].astype(int)][np.repeat(np.arange(d), d)] + T["gpos"].astype(int)      # [dd, nel]

@@ -1,0 +1,126 @@
+"""Structured triangulation fast path (adfem.jl_b200/csrc/tri_grid.cuh): detection + closed-form row pointers on the CPU,
+parity of the index-free kernels against the oracle and against the general tile kernels on the GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import _lib, meshgen
+
+
+def _info(m, what):
+    return int(_lib.lib().adfem_mesh_info(m.handle, what))
+
+
+def rectilinear(m, n, seed):
+    """Mesh(m, n, h) connectivity on non-uniform rectilinear nodes, optionally shifted (a slab of a larger grid)."""
+    rng = np.random.default_rng(seed)
+    c, e = meshgen.tri_grid(m, n, 1.0)
+    xs = np.cumsum(rng.uniform(0.5, 1.5, m + 1)) - 3.0
+    ys = np.cumsum(rng.uniform(0.5, 1.5, n + 1)) + 7.0
+    c = np.stack([xs[c[:, 0].astype(int)], ys[c[:, 1].astype(int)]], 1)
+    return c, e
+
+
+GRIDS = [(1, 1), (2, 1), (1, 3), (5, 4), (31, 2), (32, 3), (63, 5), (70, 33)]
+
+
+@pytest.mark.parametrize("m,n", GRIDS)
+def test_detection_and_closed_form_rowptr(m, n):
+    for c, e in (meshgen.tri_grid(m, n, 0.1), rectilinear(m, n, 1)):
+        M = A.Mesh(c, e, host_only=True)
+        assert _info(M, _lib.INFO_STRUCTURED) == 1
+        M.csr_pattern(1)                       # builds the symbolic pattern, which validates the closed-form row pointers
+        assert _info(M, _lib.INFO_STRUCTURED) == 1
+
+
+def test_not_structured():
+    c, e = meshgen.tri_grid(6, 5, 0.1, version=2)                # other diagonal
+    assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
+    c, e = meshgen.tri_grid(6, 5, 0.1)
+    c2 = c.copy(); c2[9, 0] += 1e-13                             # one node off the rectilinear grid
+    assert _info(A.Mesh(c2, e, host_only=True), _lib.INFO_STRUCTURED) == 0
+    assert _info(A.Mesh(c, e[::-1].copy(), host_only=True), _lib.INFO_STRUCTURED) == 0      # renumbered elements
+    assert _info(A.Mesh(c, e, degree=2, host_only=True), _lib.INFO_STRUCTURED) == 0          # P2
+    c, e = meshgen.jitter_unstructured(6, 5, 0.1)
+    assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _close(a, b, rel=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3)
+    assert err.max() <= rel, f"max rel err {err.max():.3e} at {err.argmax()}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+@pytest.mark.parametrize("m,n", GRIDS)
+def test_structured_parity(oracle, m, n, kind):
+    import torch
+    from adfem_jl_b200 import ops
+    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else rectilinear(m, n, 2)
+    M, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    assert _info(M, _lib.INFO_STRUCTURED) == 1
+    rng = np.random.default_rng(7)
+    coef = rng.random(o.ngauss) + 0.5
+    rowptr, colind = M.csr_pattern(1)
+    for fn, ofwd, obwd in ((ops.compute_fem_laplace_matrix1, o.laplace_fwd, o.laplace_bwd), (ops.compute_fem_mass_matrix1, o.mass_fwd, o.mass_bwd)):
+        ind, vv = ofwd(coef)
+        rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+        assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+        dv = rng.standard_normal(len(ref))
+        expect = obwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, o.ndof))
+        out = {}
+        for structured, rows, heron in ((1, 0, 0), (1, 3, 1), (1, 1, 0), (0, 0, 0)):
+            M.set_option("structured", structured)
+            M.set_option("grid_rows", rows)
+            M.set_option("area_formula_csr", heron)
+            k = torch.from_numpy(coef).cuda().requires_grad_(True)
+            T = fn(k, M, mode="csr")
+            vals = T.values.detach().cpu().numpy()
+            (g,) = torch.autograd.grad(T.values, k, torch.from_numpy(dv).cuda())
+            _close(vals, ref)
+            _close(g.cpu().numpy(), expect)
+            out[(structured, rows, heron)] = (vals, g.cpu().numpy())
+        # same per-entry summation order as the general tile kernels: agreement far below the parity bar
+        _close(out[(1, 0, 0)][0], out[(0, 0, 0)][0], rel=1e-14)
+        _close(out[(1, 0, 0)][1], out[(0, 0, 0)][1], rel=1e-14)
+        assert np.array_equal(out[(1, 0, 0)][0], out[(1, 1, 0)][0])          # independent of the row chunking
+        M.set_option("structured", 1); M.set_option("grid_rows", 0); M.set_option("area_formula_csr", 0)
+
+
+@pytest.mark.gpu
+def test_structured_large_properties():
+    """Config-2-like size (not square, not a multiple of the strip width): K·1 = 0, symmetry, Σ M = area, adjoint identity, and
+    bit-identical repeat; the general tile kernels on the same mesh agree to 1e-13."""
+    import scipy.sparse as sp
+    import torch
+    from adfem_jl_b200 import ops
+    m, n = 1500, 1111
+    M = A.Mesh(m, n, 1.0 / 1024)
+    assert _info(M, _lib.INFO_STRUCTURED) == 1
+    G = M.ngauss
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    k1 = torch.rand(G, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    rowptr, colind = M.csr_pattern(1)
+    v1 = ops.compute_fem_laplace_matrix1(k1, M, mode="csr").values
+    assert torch.equal(v1, ops.compute_fem_laplace_matrix1(k1, M, mode="csr").values)
+    K = sp.csr_matrix((v1.cpu().numpy(), colind, rowptr), shape=(M.ndof, M.ndof))
+    assert np.abs(K @ np.ones(M.ndof)).max() < 1e-10
+    assert abs(K - K.T).max() < 1e-12
+    Mv = ops.compute_fem_mass_matrix1(torch.ones(G, dtype=torch.float64, device="cuda"), M, mode="csr").values
+    area = m * n / 1024.0 ** 2
+    assert abs(Mv.sum().item() - area) < 1e-11 * area
+    dK = torch.randn(v1.numel(), dtype=torch.float64, device="cuda", generator=gen)
+    kk = k1.clone().requires_grad_(True)
+    (g,) = torch.autograd.grad(ops.compute_fem_laplace_matrix1(kk, M, mode="csr").values, kk, dK)
+    lhs, rhs = (dK * v1).sum().item(), (g * k1).sum().item()
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), 1.0)
+    M.set_option("structured", 0)
+    v0 = ops.compute_fem_laplace_matrix1(k1, M, mode="csr").values
+    (g0,) = torch.autograd.grad(ops.compute_fem_laplace_matrix1(kk, M, mode="csr").values, kk, dK)
+    assert (v0 - v1).abs().max().item() <= 1e-13 * v1.abs().max().item()
+    assert (g0 - g).abs().max().item() <= 1e-13 * g.abs().max().item()
