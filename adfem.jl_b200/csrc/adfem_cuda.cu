@@ -79,7 +79,7 @@ struct adfem_mesh {
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // structured triangulation Mesh(m, n, h) (tri_grid.cuh): detected from the arrays, no mesh-static index data is read
   bool grid_ok = false;
-  int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0;
+  int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   DevBuf<double> grid_xs, grid_ys;
   // scratch for the host-buffer calls
   DevBuf<double> s_in, s_out;
@@ -321,27 +321,34 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
 
 bool use_grid(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }
 
-int grid_rows_per_warp(const adfem_mesh* m, int strips, int rows) {
+int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
   if (m->opt_grid_rows > 0) return m->opt_grid_rows;
-  const int want_chunks = std::max(1, 8192 / std::max(1, strips));      // ~8k warps on the device
+  // ~8 full waves of resident CTAs (2 per SM): short enough tails, long enough marches (one extra cell row per chunk is recomputed)
+  if (m->num_sms == 0 && cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) m->num_sms = 148;
+  const long long want_warps = 8LL * std::max(2, std::min(3, m->opt_grid_occupancy)) * m->num_sms * GRID_WARPS;
+  const int want_chunks = (int)std::max<long long>(1, want_warps / std::max(1, strips));
   return std::max(8, (rows + want_chunks - 1) / want_chunks);
 }
 
+template <class K> int launch_grid(K kern, int smem, long long warps, cudaStream_t st, const DevMesh& dm, const GridTri& gt, int H, const double* in, double* out) {
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, smem, st>>>(dm, gt, H, in, out);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
 template <int OP> int launch_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n + 1), chunks = (gt.n + 1 + H - 1) / H;
   const long long warps = (long long)strips * chunks;
-  k_grid_fwd<OP><<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
-  CU_TRY(cudaGetLastError());
-  return 0;
+  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_fwd<OP, 3>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
+  return launch_grid(k_grid_fwd<OP, 2>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
 }
 template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n), chunks = (gt.n + H - 1) / H;
   const long long warps = (long long)strips * chunks;
-  k_grid_adj<OP><<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
-  CU_TRY(cudaGetLastError());
-  return 0;
+  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_adj<OP, 3>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
+  return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
 }
 
 int check_op(const adfem_mesh* m, int op) {
@@ -469,6 +476,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "variant") m->opt_variant = (int)value & 3;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
+  else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;
   else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
   else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);

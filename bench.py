@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--structured", type=int, default=1, help="0: force the general tile kernels on the structured mesh")
     ap.add_argument("--general-steps", type=int, default=20, help="extra timed steps of the general (unstructured-mesh) tile kernels, N=1 only")
     ap.add_argument("--grid-rows", type=int, default=0)
+    ap.add_argument("--grid-occupancy", type=int, default=0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -186,6 +187,8 @@ def main():
     mesh.set_option("structured", args.structured)
     if args.grid_rows:
         mesh.set_option("grid_rows", args.grid_rows)
+    if args.grid_occupancy:
+        mesh.set_option("grid_occupancy", args.grid_occupancy)
     structured = bool(args.structured) and L.adfem_mesh_info(mesh.handle, _lib.INFO_STRUCTURED) == 1
     rowptr, colind = mesh.csr_pattern(1)
     nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
