@@ -81,7 +81,14 @@ struct adfem_mesh {
   bool grid_ok = false;
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   DevBuf<double> grid_xs, grid_ys;
-  // scratch for the host-buffer calls
+  // scratch and streams for the host-buffer calls (H2D, kernels, D2H)
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t hev[2] = {nullptr, nullptr};
+  int opt_host_chunks = 16;
+  ~adfem_mesh() {
+    for (auto& s : hs) if (s) cudaStreamDestroy(s);
+    for (auto& e : hev) if (e) cudaEventDestroy(e);
+  }
   DevBuf<double> s_in, s_out;
 };
 
@@ -319,6 +326,13 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
   return 0;
 }
 
+int ensure_host_streams(adfem_mesh* m) {
+  if (m->hs[0]) return 0;
+  for (auto& s : m->hs) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto& e : m->hev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return 0;
+}
+
 bool use_grid(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }
 
 int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
@@ -330,25 +344,30 @@ int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
   return std::max(8, (rows + want_chunks - 1) / want_chunks);
 }
 
-template <class K> int launch_grid(K kern, int smem, long long warps, cudaStream_t st, const DevMesh& dm, const GridTri& gt, int H, const double* in, double* out) {
+template <class K> int launch_grid(K kern, int smem, long long warps, cudaStream_t st, const DevMesh& dm, const GridTri& gt, int r0, int r1, int H, const double* in,
+                                   double* out) {
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, smem, st>>>(dm, gt, H, in, out);
+  kern<<<(unsigned)((warps + GRID_WARPS - 1) / GRID_WARPS), GRID_WARPS * 32, smem, st>>>(dm, gt, r0, r1, H, in, out);
   CU_TRY(cudaGetLastError());
   return 0;
 }
-template <int OP> int launch_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st) {
+// node rows [r0, r1) of the structured forward (r1 < 0: all rows)
+template <int OP> int launch_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st, int r0 = 0, int r1 = -1) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
-  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n + 1), chunks = (gt.n + 1 + H - 1) / H;
+  if (r1 < 0) r1 = gt.n + 1;
+  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, r1 - r0), chunks = (r1 - r0 + H - 1) / H;
   const long long warps = (long long)strips * chunks;
-  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_fwd<OP, 3>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
-  return launch_grid(k_grid_fwd<OP, 2>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, coef, vals);
+  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_fwd<OP, 3>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, coef, vals);
+  return launch_grid(k_grid_fwd<OP, 2>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, coef, vals);
 }
-template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
+// cell rows [r0, r1) of the structured adjoint (r1 < 0: all rows)
+template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st, int r0 = 0, int r1 = -1) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
-  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, gt.n), chunks = (gt.n + H - 1) / H;
+  if (r1 < 0) r1 = gt.n;
+  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, r1 - r0), chunks = (r1 - r0 + H - 1) / H;
   const long long warps = (long long)strips * chunks;
-  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_adj<OP, 3>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
-  return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, H, dvals, grad);
+  if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_adj<OP, 3>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
+  return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
 }
 
 int check_op(const adfem_mesh* m, int op) {
@@ -477,6 +496,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;
+  else if (k == "host_chunks") m->opt_host_chunks = (int)value;
   else if (k == "area_formula_csr") m->opt_area_csr = value != 0;
   else if (k == "area_formula_coo") m->opt_area_coo = value != 0;
   else return fail("unknown option: " + k);
@@ -677,6 +697,28 @@ int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, doub
   if (nout < 0) return 1;
   if (m->s_in.n < (size_t)nin) CU_TRY(m->s_in.alloc(nin));
   if (m->s_out.n < (size_t)nout) CU_TRY(m->s_out.alloc(nout));
+  if (op != ADFEM_OP_STIFFNESS && use_grid(m) && m->opt_host_chunks > 1) {
+    // structured mesh: node-row chunks flow through three streams, so the H2D copy of chunk c+1, the kernel of chunk c and the
+    // D2H copy of chunk c-1 overlap (PCIe is full duplex).  Chunk c needs the coefficients of cell rows < R[c+1] and writes the
+    // contiguous CSR range of node rows [R[c], R[c+1]).
+    if (int rc = ensure_host_streams(m)) return rc;
+    const int gm = m->grid_m, gn = m->grid_n, C = std::min(m->opt_host_chunks, gn + 1);
+    for (int c = 0; c < C; c++) {
+      const int ra = (int)((long long)(gn + 1) * c / C), rb = (int)((long long)(gn + 1) * (c + 1) / C);
+      const long long k0 = 6LL * gm * std::min(ra, gn), k1 = 6LL * gm * std::min(rb, gn);
+      if (k1 > k0) CU_TRY(cudaMemcpyAsync(m->s_in.p + k0, coef_host + k0, (k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, m->hs[0]));
+      CU_TRY(cudaEventRecord(m->hev[0], m->hs[0]));
+      CU_TRY(cudaStreamWaitEvent(m->hs[1], m->hev[0], 0));
+      if (int rc = op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, m->s_in.p, m->s_out.p, m->hs[1], ra, rb)
+                                          : launch_grid_fwd<OP_MASS>(m, m->s_in.p, m->s_out.p, m->hs[1], ra, rb)) return rc;
+      CU_TRY(cudaEventRecord(m->hev[1], m->hs[1]));
+      CU_TRY(cudaStreamWaitEvent(m->hs[2], m->hev[1], 0));
+      const long long v0 = grid_rowptr(ra, 0, gm, gn), v1 = rb > gn ? nout : grid_rowptr(rb, 0, gm, gn);
+      CU_TRY(cudaMemcpyAsync(vals_host + v0, m->s_out.p + v0, (v1 - v0) * sizeof(double), cudaMemcpyDeviceToHost, m->hs[2]));
+    }
+    CU_TRY(cudaStreamSynchronize(m->hs[2]));
+    return 0;
+  }
   CU_TRY(cudaMemcpyAsync(m->s_in.p, coef_host, nin * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (int rc = adfem_assemble_csr(m, op, m->s_in.p, m->s_out.p, nullptr)) return rc;
   CU_TRY(cudaMemcpyAsync(vals_host, m->s_out.p, nout * sizeof(double), cudaMemcpyDeviceToHost, 0));
@@ -693,6 +735,28 @@ int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_h
   if (nin < 0) return 1;
   if (m->s_out.n < (size_t)nin) CU_TRY(m->s_out.alloc(nin));
   if (m->s_in.n < (size_t)nout) CU_TRY(m->s_in.alloc(nout));
+  if (op != ADFEM_OP_STIFFNESS && use_grid(m) && m->opt_host_chunks > 1) {
+    // cell-row chunks [C[c], C[c+1]) need the upstream CSR rows of node rows <= C[c+1] and write a contiguous gradient range
+    if (int rc = ensure_host_streams(m)) return rc;
+    const int gm = m->grid_m, gn = m->grid_n, C = std::min(m->opt_host_chunks, gn);
+    long long sent = 0;
+    for (int c = 0; c < C; c++) {
+      const int ca = (int)((long long)gn * c / C), cb = (int)((long long)gn * (c + 1) / C);
+      const long long v1 = cb + 1 > gn ? nin : grid_rowptr(cb + 1, 0, gm, gn);
+      if (v1 > sent) CU_TRY(cudaMemcpyAsync(m->s_out.p + sent, dvals_host + sent, (v1 - sent) * sizeof(double), cudaMemcpyHostToDevice, m->hs[0]));
+      sent = std::max(sent, v1);
+      CU_TRY(cudaEventRecord(m->hev[0], m->hs[0]));
+      CU_TRY(cudaStreamWaitEvent(m->hs[1], m->hev[0], 0));
+      if (int rc = op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, m->s_out.p, m->s_in.p, m->hs[1], ca, cb)
+                                          : launch_grid_adj<OP_MASS>(m, m->s_out.p, m->s_in.p, m->hs[1], ca, cb)) return rc;
+      CU_TRY(cudaEventRecord(m->hev[1], m->hs[1]));
+      CU_TRY(cudaStreamWaitEvent(m->hs[2], m->hev[1], 0));
+      const long long g0 = 6LL * gm * ca, g1 = 6LL * gm * cb;
+      CU_TRY(cudaMemcpyAsync(grad_coef_host + g0, m->s_in.p + g0, (g1 - g0) * sizeof(double), cudaMemcpyDeviceToHost, m->hs[2]));
+    }
+    CU_TRY(cudaStreamSynchronize(m->hs[2]));
+    return 0;
+  }
   CU_TRY(cudaMemcpyAsync(m->s_out.p, dvals_host, nin * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (int rc = adfem_assemble_csr_adjoint(m, op, m->s_out.p, m->s_in.p, nullptr)) return rc;
   CU_TRY(cudaMemcpyAsync(grad_coef_host, m->s_in.p, nout * sizeof(double), cudaMemcpyDeviceToHost, 0));

@@ -94,19 +94,19 @@ constexpr int GRID_FWD_WARP_DOUBLES = GRID_STRIP * 7 + 1;
 constexpr int GRID_FWD_SMEM = GRID_WARPS * GRID_FWD_WARP_DOUBLES * 8;
 
 // Forward: vals[nnz] of the scalar operator OP on the structured triangulation (3 Gauss points per element).
-// grid: ceil(strips * chunks / GRID_WARPS) CTAs of GRID_WARPS warps; `rows_per_warp` node rows per warp.
+// Node rows [r0, r1); grid: ceil(strips * chunks / GRID_WARPS) CTAs of GRID_WARPS warps; `rows_per_warp` node rows per warp.
 // The coefficients of cell row i+2 are loaded into registers while row i is processed (three rotating buffers).
 template <int OP, int MINB>
-__global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, GridTri gt, int rows_per_warp, const double* __restrict__ coef,
-                                                                 double* __restrict__ vals) {
+__global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp,
+                                                                    const double* __restrict__ coef, double* __restrict__ vals) {
   extern __shared__ __align__(16) double grid_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, chunks = (gt.n + 1 + rows_per_warp - 1) / rows_per_warp;
+  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, chunks = (r1 - r0 + rows_per_warp - 1) / rows_per_warp;   // node rows [r0, r1)
   const long long gw = (long long)blockIdx.x * GRID_WARPS + wib;
   if (gw >= (long long)strips * chunks) return;
   const int strip = (int)(gw % strips), chunk = (int)(gw / strips);
   const int j0 = strip * GRID_STRIP, cj = j0 - 1 + lane;            // this lane's cell column = its node column
-  const int i0 = chunk * rows_per_warp, i1 = min(i0 + rows_per_warp, gt.n + 1);
+  const int i0 = r0 + chunk * rows_per_warp, i1 = min(i0 + rows_per_warp, r1);
   double* stage = grid_smem + (size_t)wib * GRID_FWD_WARP_DOUBLES;
   const bool colok = cj >= 0 && cj < gt.m;                           // this lane's cell column exists
   const double x0 = colok ? __ldg(gt.xs + cj) : 0.0, x1 = colok ? __ldg(gt.xs + cj + 1) : 1.0;
@@ -219,16 +219,16 @@ constexpr int GRID_ADJ_SMEM = GRID_WARPS * GRID_ADJ_WARP_DOUBLES * 8;
 // its left neighbour) and cell column j0+l for l < 31.  The CSR entries of node row ci+3 (one contiguous run per strip) are
 // requested with asynchronous copies while cell row ci is processed.
 template <int OP, int MINB>
-__global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, GridTri gt, int rows_per_warp, const double* __restrict__ dvals,
-                                                                 double* __restrict__ grad_coef) {
+__global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp,
+                                                                    const double* __restrict__ dvals, double* __restrict__ grad_coef) {
   extern __shared__ __align__(16) double grid_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, chunks = (gt.n + rows_per_warp - 1) / rows_per_warp;   // over CELLS
+  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, chunks = (r1 - r0 + rows_per_warp - 1) / rows_per_warp;   // cell rows [r0, r1)
   const long long gw = (long long)blockIdx.x * GRID_WARPS + wib;
   if (gw >= (long long)strips * chunks) return;
   const int strip = (int)(gw % strips), chunk = (int)(gw / strips);
   const int j0 = strip * GRID_STRIP, j = j0 + lane;                  // node column == cell column of this lane
-  const int c0 = chunk * rows_per_warp, c1 = min(c0 + rows_per_warp, gt.n);
+  const int c0 = r0 + chunk * rows_per_warp, c1 = min(c0 + rows_per_warp, r1);
   double* ring = grid_smem + (size_t)wib * GRID_ADJ_WARP_DOUBLES;    // ring[slot][32*7]
   double* stage = ring + 3 * 32 * 7;
   const bool node_ok = j <= gt.m, cell_ok = lane < GRID_STRIP && j < gt.m;

@@ -46,14 +46,18 @@ SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 
 
 def short(name):
+    """'void adfem::k_tile_fwd<(int)2, (int)1, (int)0, (bool)1>(...)' -> 'k_tile_fwd<2,1,LAPLACE,1>' (the names bench.py uses)."""
     m = re.match(r"(?:void )?(?:adfem::)?(\w+)<([^>]*)>", name)
     if not m:
         return name.split("(")[0]
     ops = {"0": "LAPLACE", "1": "MASS", "2": "STIFFNESS"}
-    a = [x.strip() for x in m.group(2).split(",")]
-    if len(a) == 3:
+    a = [re.sub(r"\((?:int|bool)\)", "", x).strip() for x in m.group(2).split(",")]
+    kname = m.group(1)
+    if kname.startswith("k_grid"):            # <OP, MINB>
+        a = [ops.get(a[0], a[0])]
+    elif len(a) >= 3:                         # <DIM, DEG, OP[, KPRE]>
         a[2] = ops.get(a[2], a[2])
-    return "%s<%s>" % (m.group(1), ",".join(a))
+    return "%s<%s>" % (kname, ",".join(a))
 
 
 def main():

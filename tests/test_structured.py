@@ -124,3 +124,31 @@ def test_structured_large_properties():
     (g0,) = torch.autograd.grad(ops.compute_fem_laplace_matrix1(kk, M, mode="csr").values, kk, dK)
     assert (v0 - v1).abs().max().item() <= 1e-13 * v1.abs().max().item()
     assert (g0 - g).abs().max().item() <= 1e-13 * g.abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 4), (63, 5), (70, 33)])
+def test_structured_host_buffer_pipeline(m, n):
+    """adfem_assemble_csr_host / _adjoint_host on a structured mesh stream node-row chunks through three CUDA streams; any chunking
+    must give exactly the device-pointer result."""
+    import torch
+    from adfem_jl_b200 import ops
+    c, e = rectilinear(m, n, 3)
+    M = A.Mesh(c, e)
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    rowptr, _ = M.csr_pattern(1)
+    nnz = int(rowptr[-1])
+    for op, fn in ((0, ops.compute_fem_laplace_matrix1), (1, ops.compute_fem_mass_matrix1)):
+        coef = rng.random(M.ngauss) + 0.5
+        dv = rng.standard_normal(nnz)
+        k = torch.from_numpy(coef).cuda().requires_grad_(True)
+        T = fn(k, M, mode="csr")
+        (g,) = torch.autograd.grad(T.values, k, torch.from_numpy(dv).cuda())
+        ref_v, ref_g = T.values.detach().cpu().numpy(), g.cpu().numpy()
+        for chunks in (1, 2, 3, 16, 1000):
+            M.set_option("host_chunks", chunks)
+            vals, grad = np.full(nnz, np.nan), np.full(M.ngauss, np.nan)
+            _lib.check(L.adfem_assemble_csr_host(M.handle, C.c_int(op), coef.ctypes.data_as(_lib.c_dp), vals.ctypes.data_as(_lib.c_dp)))
+            _lib.check(L.adfem_assemble_csr_adjoint_host(M.handle, C.c_int(op), dv.ctypes.data_as(_lib.c_dp), grad.ctypes.data_as(_lib.c_dp)))
+            assert np.array_equal(vals, ref_v) and np.array_equal(grad, ref_g)
