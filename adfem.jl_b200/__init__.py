@@ -6,4 +6,5 @@ from .mesh import (P1, P2, Mesh, Mesh3, bcedge, bcnode, fem_nodes, gauss_nodes, 
                    get_edge_dof, get_ngauss, get_volume, read_mesh_file)
 from .ops import (CSRTensor, SparseTensor, compute_fem_laplace_matrix1, compute_fem_mass_matrix1,  # noqa: F401,E402
                   compute_fem_source_term, compute_fem_source_term1, compute_fem_stiffness_matrix, compute_fem_stiffness_matrix1,
-                  compute_space_varying_tangent_elasticity_matrix, coo_indices, impose_Dirichlet_boundary_conditions)
+                  compute_space_varying_tangent_elasticity_matrix, coo_indices, impose_Dirichlet_boundary_conditions,
+                  pcl_compute_fem_laplace_matrix1, pcl_impose_Dirichlet_boundary_conditions)

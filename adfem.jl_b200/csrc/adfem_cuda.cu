@@ -665,6 +665,16 @@ int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, dou
   return 0;
 }
 
+int adfem_pcl_laplace_jacobian(adfem_mesh* m, double* H, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  const long long G = (long long)m->hm.ne * m->hm.g;
+#define CALL_PCL(DIM, DEG) k_pcl_laplace<DIM, DEG><<<blocks_for(G, 128), 128, 0, (cudaStream_t)stream>>>(dev_mesh(m, m->opt_area_coo), H)
+  DISPATCH_ELEM(m, CALL_PCL);
+#undef CALL_PCL
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
@@ -873,6 +883,21 @@ void mfem_get_element_to_vertices3(long long* elems) { if (g_mesh3) adfem_mesh_e
 
 void FemLaplaceScalar_forward(long long* indices, double* vv, const double* kappa) { legacy_coo_fwd(g_mesh2, ADFEM_OP_LAPLACE, indices, vv, kappa, "FemLaplaceScalar_forward"); }
 void FemLaplaceScalar_forward_Julia(long long* indices, double* vv, const double* kappa) { FemLaplaceScalar_forward(indices, vv, kappa); }
+// Dense G x (G*d*d) column-major Jacobian into a caller-zeroed HOST array: only the structural entries are written, from the
+// COO values of kappa == 1 (FemLaplaceScalar.h:65-92 evaluates exactly N = D D^T w).
+void pcl_FemLaplaceScalar_Jacobian(double* H) {
+  adfem_mesh* m = g_mesh2;
+  if (!m) { fprintf(stderr, "libadfem_cuda: pcl_FemLaplaceScalar_Jacobian called before the mesh was initialised\n"); return; }
+  const long long G = (long long)m->hm.ne * m->hm.g, dd = (long long)m->hm.d * m->hm.d, N = G * dd;
+  std::vector<double> ones((size_t)G, 1.0), vv((size_t)N);
+  DevBuf<double> dc, dv;
+  const bool ok = need_device(m) == 0 && dc.alloc(G) == cudaSuccess && dv.alloc(N) == cudaSuccess &&
+                  cudaMemcpy(dc.p, ones.data(), G * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  adfem_assemble_coo(m, ADFEM_OP_LAPLACE, dc.p, dv.p, nullptr) == 0 &&
+                  cudaMemcpy(vv.data(), dv.p, N * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail("pcl_FemLaplaceScalar_Jacobian"); return; }
+  for (long long nz = 0; nz < N; nz++) H[nz / dd + nz * G] = vv[nz];
+}
 void FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv, const long long*, const double*, const double*) {
   legacy_coo_bwd(g_mesh2, ADFEM_OP_LAPLACE, grad_kappa, grad_vv, "FemLaplaceScalar_backward");
 }

@@ -10,7 +10,9 @@
 
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
+#include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/adfem_cuda.h"
 #include "internal.h"
@@ -137,6 +139,12 @@ int prepare(Work& W, const long long* indices, long long sN, const long long* bd
   return 0;
 }
 
+// J[k + kpos[k]*sN] = 1 for every kept slot k (pcl_ImposeDirichlet, ImposeDirichlet.h:98-112)
+__global__ void k_pcl_dirichlet(long long sN, const int* __restrict__ keep, const int* __restrict__ kpos, double* __restrict__ J) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < sN && keep[k]) J[k + (long long)kpos[k] * sN] = 1.0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -174,6 +182,45 @@ int adfem_impose_dirichlet_grad(const double* grad_ov, const double* grad_orhs, 
   k_dirichlet_bwd<<<nblk(M), 256, 0, st>>>(indices, vv, sN, N, W.bmap, bdval, W.kpos, grad_ov, grad_orhs, grad_vv, grad_rhs, grad_bdval);
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+int adfem_pcl_impose_dirichlet(const long long* indices, long long sN, const long long* bd, long long bdN, long long N, double* J, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Work W(st);
+  long long nkeep = 0, nbd = 0;
+  if (int rc = prepare(W, indices, sN, bd, bdN, N, &nkeep, &nbd)) return rc;
+  if (sN > 0) k_pcl_dirichlet<<<nblk(sN), 256, 0, st>>>(sN, W.keep, W.kpos, J);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Legacy symbol (host pointers): J is sN x outdof column-major and caller-zeroed; indices are 1-BASED and column-major
+// (indices[k] = row, indices[k + sN] = col), bd 1-based — exactly the reference's arguments (ImposeDirichlet.h:98-112, src/pcl.jl:15-22).
+void pcl_ImposeDirichlet(double* J, const long long* indices, const long long* bd, int bdN, int sN) {
+  long long N = 0;
+  std::vector<long long> ind((size_t)2 * sN);
+  for (int k = 0; k < sN; k++) {
+    ind[2 * (size_t)k] = indices[k] - 1; ind[2 * (size_t)k + 1] = indices[k + (size_t)sN] - 1;
+    N = std::max(N, std::max(indices[k], indices[k + (size_t)sN]));
+  }
+  for (int i = 0; i < bdN; i++) N = std::max(N, bd[i]);
+  long long *d_ind = nullptr, *d_bd = nullptr;
+  std::vector<int> keep((size_t)sN + 1), kpos((size_t)sN + 1);
+  bool ok = cudaMalloc((void**)&d_ind, sizeof(long long) * std::max(1, 2 * sN)) == cudaSuccess &&
+            cudaMalloc((void**)&d_bd, sizeof(long long) * std::max(1, bdN)) == cudaSuccess &&
+            cudaMemcpy(d_ind, ind.data(), sizeof(long long) * 2 * sN, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(d_bd, bd, sizeof(long long) * bdN, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    Work W(nullptr);
+    long long nkeep = 0, nbd = 0;
+    ok = prepare(W, d_ind, sN, d_bd, bdN, N, &nkeep, &nbd) == 0 &&
+         cudaMemcpy(keep.data(), W.keep, sizeof(int) * sN, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(kpos.data(), W.kpos, sizeof(int) * sN, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  if (d_ind) cudaFree(d_ind);
+  if (d_bd) cudaFree(d_bd);
+  if (!ok) { fprintf(stderr, "libadfem_cuda: pcl_ImposeDirichlet failed: %s\n", adfem_last_error()); return; }
+  for (int k = 0; k < sN; k++) if (keep[k]) J[k + (size_t)kpos[k] * sN] = 1.0;
 }
 
 }  // extern "C"

@@ -192,6 +192,24 @@ __global__ void k_coo_stiff_bwd(DevMesh m, const double* __restrict__ grad_vv, d
 #pragma unroll
   for (int i = 0; i < NS * NS; i++) grad_hmat[t * (NS * NS) + i] = gH[i] * w;
 }
+// pcl_FemLaplaceScalar_Jacobian (deps/MFEM/FemLaplace1/FemLaplaceScalar.h:65-92): d vv[slot] / d kappa[t], a G x N column-major
+// dense matrix whose only structural non-zeros are H[t + slot*G] = (grad phi_p . grad phi_q) w for the d*d slots of Gauss point t.
+// One thread per Gauss point; the caller zero-fills H (as the reference's Julia wrapper does, src/pcl.jl:35-39).
+template <int DIM, int DEG>
+__global__ void k_pcl_laplace(DevMesh m, double* __restrict__ H) {
+  constexpr int D = ElemTraits<DIM, DEG>::D;
+  const long long G = (long long)m.ne * m.g, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= G) return;
+  const int e = (int)(t / m.g), k = (int)(t % m.g);
+  Geom<DIM> Gm; load_geom(m, e, Gm);
+  double L[DIM + 1]; bary<DIM>(m.rule, k, L);
+  double gp[D][DIM]; basis_grad<DIM, DEG>(Gm, L, gp);
+  const double w = m.rule.w[k] * Gm.wscale;
+#pragma unroll
+  for (int p = 0; p < D; p++)
+#pragma unroll
+    for (int q = 0; q < D; q++) H[t + (t * (D * D) + p * D + q) * G] = dotg<DIM>(gp[p], gp[q]) * w;
+}
 // mesh-static COO indices, 0-based interleaved (row, col) int64 pairs; NC = 1 (scalar) or DIM (elasticity)
 __global__ void k_coo_indices(DevMesh m, int nc, int per_gauss, long long* __restrict__ indices) {
   const int d = m.d, Dt = nc * d;

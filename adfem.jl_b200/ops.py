@@ -369,3 +369,28 @@ def impose_Dirichlet_boundary_conditions(A, rhs=None, bdnode=None, bdval=None):
     if eager:
         B, orhs = B.to_scipy(), orhs.cpu().numpy()
     return B if helper else (B, orhs)
+
+
+# ------------------------------------------------------------------------------------------ PCL Jacobians (src/pcl.jl)
+def pcl_compute_fem_laplace_matrix1(mesh):
+    """`pcl_compute_fem_laplace_matrix1(mmesh)` — src/pcl.jl:35-39 (kernel pcl_FemLaplaceScalar_Jacobian,
+    deps/MFEM/FemLaplace1/FemLaplaceScalar.h:65-92): dense J[t, slot] = d values[slot] / d kappa[t] of the COO output of
+    `compute_fem_laplace_matrix1`, shape (ngauss, elem_ndof^2 * ngauss), as a device tensor."""
+    G = mesh.ngauss
+    N = G * mesh.elem_ndof ** 2
+    Ht = torch.zeros(N, G, dtype=torch.float64, device="cuda")            # column-major G x N == row-major N x G
+    check(lib().adfem_pcl_laplace_jacobian(mesh.handle, _ptr(Ht), _stream()))
+    return Ht.t()
+
+
+def pcl_impose_Dirichlet_boundary_conditions(indices, bdnode, outdof):
+    """`pcl_impose_Dirichlet_boundary_conditions(indices, bdnode, outdof)` — src/pcl.jl:15-22 (kernel pcl_ImposeDirichlet,
+    deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:98-112): J[i, j] = d (v_B)_j / d (v_A)_i, shape (n_A, outdof).  `indices` (n_A x 2) and
+    `bdnode` are 0-based here (1-based in Julia)."""
+    ind = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device="cuda").contiguous()
+    bd = torch.as_tensor(np.asarray(bdnode), dtype=torch.int64, device="cuda") + 1
+    sN = ind.shape[0]
+    N = int(max(ind.max().item() if sN else -1, (bd.max().item() - 1) if bd.numel() else -1)) + 1
+    Jt = torch.zeros(int(outdof), sN, dtype=torch.float64, device="cuda")  # column-major sN x outdof
+    check(lib().adfem_pcl_impose_dirichlet(_ptr(ind), C.c_longlong(sN), _ptr(bd), C.c_longlong(bd.numel()), C.c_longlong(N), _ptr(Jt), _stream()))
+    return Jt.t()

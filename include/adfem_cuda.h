@@ -54,6 +54,13 @@ int  mfem_get_ndof3(void);
 void mfem_get_connectivity3(long long* conn);
 void mfem_get_element_to_vertices3(long long* elems);
 
+/* Physics-constrained-learning Jacobians (src/pcl.jl), host pointers, dense column-major, CALLER-ZEROED like Julia's zeros(...):
+ *  pcl_FemLaplaceScalar_Jacobian: H[G x G*d*d], H[t + slot*G] = d vv[slot] / d kappa[t]     (deps/MFEM/FemLaplace1/FemLaplaceScalar.h:65-92)
+ *  pcl_ImposeDirichlet: J[sN x outdof], J[k + s*sN] = 1 for the s-th kept slot k; indices 1-based column-major, bd 1-based
+ *                                                                                          (deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:98-112) */
+void pcl_FemLaplaceScalar_Jacobian(double* H);
+void pcl_ImposeDirichlet(double* J, const long long* indices, const long long* bd, int bdN, int sN);
+
 /* Eager op entry points (host pointers).  indices: 2*N interleaved (row, col), 0-based int64. */
 void FemLaplaceScalar_forward_Julia(long long* indices, double* vv, const double* kappa);      /* deps/MFEM/FemLaplace1/FemLaplaceScalar.h:59-61 */
 void FemSourceScalar_forward_Julia(double* rhs, const double* f);                              /* deps/MFEM/FemSource1/FemSourceScalar.h:35-37 (adds into rhs) */
@@ -157,6 +164,11 @@ int adfem_impose_dirichlet(const long long* indices, const double* vv, long long
 int adfem_impose_dirichlet_grad(const double* grad_ov, const double* grad_orhs, const long long* indices, const double* vv,
                                 long long sN, const long long* bd, const double* bdval, long long bdN, long long N,
                                 double* grad_vv, double* grad_rhs, double* grad_bdval, void* stream);
+
+/* Device versions of the two PCL Jacobians: H / J are DEVICE pointers, caller-zeroed; indices 0-based interleaved like adfem_impose_dirichlet. */
+int adfem_pcl_laplace_jacobian(adfem_mesh* m, double* H /* G x G*d*d column-major */, void* stream);
+int adfem_pcl_impose_dirichlet(const long long* indices, long long sN, const long long* bd, long long bdN, long long N, double* J /* sN x S column-major */,
+                               void* stream);
 
 /* Structured-grid Q1 operators on an m x n grid of h x h cells (device pointers; ii/jj are 1-BASED int64 like the ops and may
  * both be NULL to skip the mesh-static indices).

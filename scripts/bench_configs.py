@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Single-GPU timings of BASELINE.json configs 3-5 (and the source term of config 2) at sizes whose host-side symbolic phase
+finishes in about a minute.  These are NOT bench.py lines (bench.py measures config 2); they record where the general tile
+kernels stand on the other operator / element families.  One JSON line per case on stdout.
+
+  python scripts/bench_configs.py [--steps 20] [--cases 3,4l,4m,5,src]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import _lib, meshgen
+
+
+def timed(fn, steps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[steps]) / steps
+
+
+def run_csr(name, mesh, op, c_per_gauss, steps, note):
+    L = _lib.lib()
+    ncomp = mesh.dim if op == 2 else 1
+    t0 = time.perf_counter()
+    rowptr, _ = mesh.csr_pattern(ncomp)
+    nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    coef = torch.rand(G * c_per_gauss, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    dK = torch.rand(nnz, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    vals = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    grad = torch.empty(G * c_per_gauss, dtype=torch.float64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = mesh.handle
+    pk, pv, pd, pg = (C.c_void_p(t.data_ptr()) for t in (coef, vals, dK, grad))
+    fwd = lambda: _lib.check(L.adfem_assemble_csr(h, op, pk, pv, st))
+    adj = lambda: _lib.check(L.adfem_assemble_csr_adjoint(h, op, pd, pg, st))
+    fwd(); adj()
+    torch.cuda.synchronize()
+    setup = time.perf_counter() - t0
+    tf, ta = timed(fwd, steps), timed(adj, steps)
+    d, dim, g = mesh.elem_ndof, mesh.dim, mesh.gauss_per_elem
+    # conn + coords + coefficients + values, per element and direction
+    b = 4 * d + 8 * dim * mesh.nnode / E + 8 * c_per_gauss * g + 8 * nnz / E
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    line = {"case": name, "note": note, "elements": E, "ndof": mesh.ndof, "nnz": nnz, "fwd_ms": tf, "adj_ms": ta,
+            "Melem_per_s": E / ((tf + ta) * 1e-3) / 1e6, "alg_bytes_per_elem_per_direction": b,
+            "fwd_GBps": b * E / (tf * 1e-3) / 1e9, "adj_GBps": b * E / (ta * 1e-3) / 1e9, "peak_GBps": peak,
+            "step_frac": 2 * b * E / ((tf + ta) * 1e-3) / 1e9 / peak, "setup_s": round(setup, 1),
+            "plan_bytes_per_elem": L.adfem_mesh_info(h, _lib.INFO_PLAN_BYTES) / E,
+            "structured_path": bool(L.adfem_mesh_info(h, _lib.INFO_STRUCTURED)) and op != 2}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--cases", default="3,4l,4m,5,src")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every mesh edge count by this factor (smoke runs)")
+    args = ap.parse_args()
+    cases = args.cases.split(",")
+    s = args.scale
+    torch.cuda.set_device(0)
+    if "3" in cases:
+        m = A.Mesh(int(4096 * s), int(2048 * s), 1.0 / int(4096 * s))
+        run_csr("config3_elasticity_P1_tri", m, 2, 9, args.steps, "Mesh(4096,2048,h) P1, per-Gauss-point 3x3 H, CSR fwd + H-adjoint (general tile kernels)")
+        del m
+    if "4l" in cases or "4m" in cases:
+        n = int(1000 * s)
+        c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)
+        m = A.Mesh(c, e, degree=2)
+        if "4l" in cases:
+            run_csr("config4_laplace_P2_unstructured", m, 0, 1, args.steps, "jittered, randomly renumbered triangulation, P2 (d=6, g=6), %dx%d cells" % (n, n))
+        if "4m" in cases:
+            run_csr("config4_mass_P2_unstructured", m, 1, 1, args.steps, "same mesh, mass matrix")
+        del m
+    if "5" in cases:
+        n = int(64 * s)
+        c, e = meshgen.tet_grid(n, n, n, 1.0 / n)
+        m = A.Mesh3(c, e)
+        run_csr("config5_elasticity_P1_tet", m, 2, 36, args.steps, "Mesh3(%d,%d,%d,h) P1 tets, per-Gauss-point 6x6 Voigt H (3-D extension N2)" % (n, n, n))
+        del m
+    if "src" in cases:
+        L = _lib.lib()
+        n = int(4096 * s)
+        m = A.Mesh(n, n, 1.0 / n)
+        G = m.ngauss
+        f = torch.rand(G, dtype=torch.float64, device="cuda")
+        rhs = torch.empty(m.ndof, dtype=torch.float64, device="cuda")
+        gr = torch.rand(m.ndof, dtype=torch.float64, device="cuda")
+        gf = torch.empty(G, dtype=torch.float64, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        fwd = lambda: _lib.check(L.adfem_source(m.handle, C.c_void_p(f.data_ptr()), C.c_void_p(rhs.data_ptr()), st))
+        adj = lambda: _lib.check(L.adfem_source_adjoint(m.handle, C.c_void_p(gr.data_ptr()), C.c_void_p(gf.data_ptr()), st))
+        tf, ta = timed(fwd, args.steps), timed(adj, args.steps)
+        b = 12 + 8 * 2 * m.nnode / m.nelem + 24 + 8 * m.ndof / m.nelem
+        print(json.dumps({"case": "config2_source_term_P1_tri", "elements": m.nelem, "fwd_ms": tf, "adj_ms": ta, "alg_bytes_per_elem_per_direction": b,
+                          "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,7 +4,7 @@ import pytest
 import scipy.sparse as sp
 
 import adfem_jl_b200 as A
-from adfem_jl_b200 import meshgen
+from adfem_jl_b200 import meshgen, ops
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -134,3 +134,59 @@ def test_grid_elasticity_and_svt(oracle, m, n):
     _, _, vv = oracle.univariate_stiffness_fwd(hm, m, n, h)
     expect = oracle.svt_bwd(oracle.univariate_stiffness_bwd(2 * vv, m, n, h, True), m, n, 1)
     close(g.cpu().numpy(), expect)
+
+
+# ------------------------------------------------------------------------------------------ PCL Jacobians (src/pcl.jl, test/pcl.jl)
+@pytest.mark.parametrize("degree", [1, 2])
+def test_pcl_laplace_jacobian(oracle, degree):
+    """pcl_compute_fem_laplace_matrix1 == the oracle's restatement of pcl_FemLaplaceScalar_Jacobian, == autograd of the COO op (the check
+    test/pcl.jl:34-50 makes with finite differences), through the device API and through the legacy host symbol."""
+    import ctypes as C
+    c, e = meshgen.jitter_unstructured(4, 3, 0.25, seed=5)
+    m, o = A.Mesh(c, e, degree=degree), oracle.Mesh2D(c, e, degree=degree)
+    J = ops.pcl_compute_fem_laplace_matrix1(m)
+    ref = o.laplace_jacobian()
+    assert tuple(J.shape) == ref.shape == (o.ngauss, o.ngauss * o.elem_ndof ** 2)
+    close(J.cpu().numpy(), ref)
+    k = torch.rand(o.ngauss, dtype=torch.float64, device="cuda").requires_grad_(True)
+    vv = ops.compute_fem_laplace_matrix1(k, m, mode="coo").values
+    Ja = torch.autograd.functional.jacobian(lambda kk: ops.compute_fem_laplace_matrix1(kk, m, mode="coo").values, k)     # [N, G]
+    close(J.cpu().numpy(), Ja.t().cpu().numpy())
+    assert vv.numel() == J.shape[1]
+    # legacy symbol on the global 2-D mesh: host pointer, caller-zeroed, column-major
+    L = A._lib.lib()
+    v3 = np.zeros((c.shape[0], 3)); v3[:, :2] = c
+    ne = C.c_longlong()
+    L.init_nnfem_mesh(np.ascontiguousarray(v3).ctypes.data_as(A._lib.c_dp), c.shape[0], np.ascontiguousarray(e, dtype=np.int32).ctypes.data_as(A._lib.c_ip),
+                      e.shape[0], 2 if degree == 1 else 4, 6, degree, C.byref(ne))
+    H = np.zeros(ref.size)
+    L.pcl_FemLaplaceScalar_Jacobian(H.ctypes.data_as(A._lib.c_dp))
+    close(H.reshape(ref.shape[1], ref.shape[0]).T, ref)
+
+
+def test_pcl_impose_dirichlet(oracle):
+    """pcl_impose_Dirichlet_boundary_conditions: J[i, j] = d (v_B)_j / d (v_A)_i is the 0/1 selection of the kept slots, in order —
+    checked against autograd of the ImposeDirichlet op and through the legacy host symbol (1-based, column-major indices)."""
+    import ctypes as C
+    c, e = meshgen.tri_grid(4, 3, 0.25)
+    m = A.Mesh(c, e)
+    k = torch.rand(m.ngauss, dtype=torch.float64, device="cuda")
+    K = ops.compute_fem_laplace_matrix1(k, m, mode="coo")
+    bd = A.bcnode(m)
+    B = ops.impose_Dirichlet_boundary_conditions(K, bd)
+    ind = K.indices.cpu().numpy()
+    J = ops.pcl_impose_Dirichlet_boundary_conditions(ind, bd, B.values.numel())
+    Ja = torch.autograd.functional.jacobian(lambda v: ops.impose_Dirichlet_boundary_conditions(ops.SparseTensor(K.indices, v, m.ndof, m.ndof), bd).values,
+                                            K.values.detach().clone())                                                  # [outdof, sN]
+    assert np.array_equal(J.cpu().numpy(), Ja.t().cpu().numpy())
+    isbd = np.zeros(m.ndof, dtype=bool); isbd[np.asarray(bd)] = True
+    kept = np.flatnonzero(~isbd[ind[:, 0]] & ~isbd[ind[:, 1]])
+    Jr = np.zeros(J.shape); Jr[kept, np.arange(len(kept))] = 1.0
+    assert np.array_equal(J.cpu().numpy(), Jr)
+    L = A._lib.lib()
+    sN = ind.shape[0]
+    ind1 = np.ascontiguousarray((ind + 1).T.reshape(-1), dtype=np.int64)          # column-major sN x 2, 1-based
+    bd1 = np.ascontiguousarray(np.asarray(bd) + 1, dtype=np.int64)
+    Jh = np.zeros(sN * J.shape[1])
+    L.pcl_ImposeDirichlet(Jh.ctypes.data_as(A._lib.c_dp), ind1.ctypes.data_as(A._lib.c_lp), bd1.ctypes.data_as(A._lib.c_lp), C.c_int(len(bd1)), C.c_int(sN))
+    assert np.array_equal(Jh.reshape(J.shape[1], sN).T, Jr)
