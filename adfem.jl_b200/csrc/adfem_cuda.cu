@@ -68,8 +68,8 @@ struct adfem_mesh {
   std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
-  int opt_smem_budget = 72 * 1024;          // dynamic shared memory per CTA (3 head + 2 body buffers + staging): 3 CTAs per SM
-  int opt_tile_threads = 320;
+  int opt_smem_budget = 0;                  // dynamic shared memory per CTA (3 head + 2 body buffers + staging); 0 = per-operator default
+  int opt_tile_threads = 0;                 // threads per CTA of the tile kernels; 0 = per-operator default
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
   int opt_variant = 0;                      // forward tuning bits: 1 = rotate gather chunks over the warps, 2 = balanced phase A mapping
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
@@ -146,6 +146,12 @@ bool grid_pattern_matches(const ScalarPattern& pat, int m, int n) {
 
 int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_threads : default_threads(); }
 
+// Tile-kernel launch shape.  Measured on B200 (scripts/gpu_sweep*.sh, scripts/gpu_cfg_sweep.sh): scalar operators and 2-D elasticity run best
+// with 3 CTAs of 320 threads per SM (72 KB each); 3-D elasticity keeps (3*4)^2 = 144 doubles per tile element in shared memory and wants
+// the larger tiles of 2 CTAs x 512 threads (110 KB each).
+int tile_threads_of(const adfem_mesh* m, int nc) { return m->opt_tile_threads > 0 ? m->opt_tile_threads : ((nc > 1 && m->hm.dim == 3) ? 512 : 320); }
+size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : ((nc > 1 && m->hm.dim == 3) ? 110 * 1024 : 72 * 1024); }
+
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
   std::string err = m->pat.build(m->hm, nthreads_of(m));
@@ -170,11 +176,22 @@ int ensure_pattern(adfem_mesh* m) {
   return 0;
 }
 
-int slots_of(const HostMesh& h, int nc) { return nc == 1 ? h.d * (h.d + 1) / 2 : (nc * h.d) * (nc * h.d); }
+// doubles of shared memory per tile element in the forward kernel: the local matrix (packed symmetric for scalar operators), plus the
+// Gauss-summed NS x NS coefficient matrix for P1 elasticity (cooperative coefficient load)
+int slots_of(const HostMesh& h, int nc) {
+  if (nc == 1) return h.d * (h.d + 1) / 2;
+  const int ns = h.dim == 2 ? 3 : 6;
+  (void)ns;
+  return (nc * h.d) * (nc * h.d);
+}
 
 // dynamic shared memory of the tile kernels: 3 head buffers + 2 body buffers + local matrices / 2 staging buffers
 size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return 3 * align16(tp.max_head) + 2 * align16(tp.max_body) + (size_t)8 * slots * tp.max_elems; }
-size_t adj_smem_bytes(const AdjTiles& ap, int nc) { return 3 * align16(ap.max_head) + 2 * align16(ap.max_body) + (size_t)2 * 8 * nc * nc * ap.max_nnz; }
+// ns2: NS*NS for P1 elasticity (gradient matrices parked in shared memory for the coalesced store), else 0
+size_t adj_smem_bytes(const AdjTiles& ap, int nc, int ns2) {
+  return 3 * align16(ap.max_head) + 2 * align16(ap.max_body) + (size_t)2 * 8 * nc * nc * ap.max_nnz + (size_t)8 * ns2 * ap.max_elems;
+}
+int adj_ns2(const HostMesh& h, int nc) { return (nc > 1 && h.degree == 1) ? (h.dim == 2 ? 9 : 36) : 0; }
 constexpr size_t SMEM_LIMIT = 220 * 1024;
 
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
@@ -184,7 +201,7 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   auto it = m->fwd_plans.find(nc);
   if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
   auto P = std::make_unique<FwdPlanDev>();
-  size_t budget = (size_t)m->opt_smem_budget;
+  size_t budget = smem_budget_of(m, nc);
   std::string err = "tile too large";
   for (int attempt = 0; attempt < 4 && !err.empty(); attempt++, budget = std::min(SMEM_LIMIT, budget * 2)) {
     // bytes per tile element: local matrix + 3 head copies of its id + 2 body copies of (vertex ids, vertices, sources, destinations)
@@ -223,7 +240,7 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
   if (it != m->adj_plans.end()) { *out = it->second.get(); return 0; }
   if (m->adj_untileable) return 0;
   auto P = std::make_unique<AdjPlanDev>();
-  size_t budget = (size_t)m->opt_smem_budget;
+  size_t budget = smem_budget_of(m, nc);
   std::string err = "tile too large";
   for (int attempt = 0; attempt < 4 && !err.empty(); attempt++, budget = std::min(SMEM_LIMIT, budget * 2)) {
     const int dd = h.d * h.d;
@@ -233,12 +250,12 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
     int EPT = m->opt_elems_per_tile > 0 ? m->opt_elems_per_tile : (int)(budget / per_elem);
     EPT = std::max(4, std::min(EPT, 4096));
     // every thread of the CTA gets the same number of elements
-    if (m->opt_elems_per_tile <= 0 && EPT >= m->opt_tile_threads) EPT -= EPT % m->opt_tile_threads;
+    if (m->opt_elems_per_tile <= 0 && EPT >= tile_threads_of(m, nc)) EPT -= EPT % tile_threads_of(m, nc);
     const int max_nnz = 65535;
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
       if (err == "row longer than 255 entries") { m->adj_untileable = true; return 0; }
-      if (err.empty() && adj_smem_bytes(P->host, nc) > std::max(budget, m->opt_elems_per_tile > 0 ? SMEM_LIMIT : budget)) err = "tile too large";
+      if (err.empty() && adj_smem_bytes(P->host, nc, adj_ns2(h, nc)) > std::max(budget, m->opt_elems_per_tile > 0 ? SMEM_LIMIT : budget)) err = "tile too large";
       if (err.empty() || EPT <= 4) break;
       EPT = std::max(4, (int)(EPT * 0.8));
     }
@@ -284,12 +301,12 @@ template <class K> int tile_grid(adfem_mesh* m, K kern, int threads, size_t smem
 DevMesh dev_mesh(const adfem_mesh* m, int heron) { DevMesh d = m->dm; d.heron = heron; return d; }
 
 template <class K>
-int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, const double* coef, double* vals, cudaStream_t st) {
+int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int threads, const double* coef, double* vals, cudaStream_t st) {
   int grid = 0;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (int rc = tile_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
+  if (int rc = tile_grid(m, kern, threads, smem, P->dev.ntiles, &grid)) return rc;
   DevTiles dt = P->dev; dt.sym |= m->opt_variant << 1;
-  kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, dt, coef, vals);
+  kern<<<grid, threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, dt, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -298,27 +315,28 @@ template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
   const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
+  const int threads = tile_threads_of(m, NC);
   if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
   if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
     // register prefetch of the next tile's coefficients
-    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * m->opt_tile_threads &&
-        (!(m->opt_variant & 2) || ((((P->host.max_elems + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31) <= m->opt_tile_threads))
-      return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true>, P, smem, coef, vals, st);
+    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads &&
+        (!(m->opt_variant & 2) || ((((P->host.max_elems + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31) <= threads))
+      return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true>, P, smem, threads, coef, vals, st);
   }
-  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false>, P, smem, coef, vals, st);
+  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false>, P, smem, threads, coef, vals, st);
 }
 template <int DIM, int DEG, int OP>
 int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
   AdjPlanDev* P = nullptr;
   if (m->opt_adjoint_tiled) { if (int rc = ensure_adj_plan(m, NC, &P)) return rc; }
-  const size_t smem = P ? adj_smem_bytes(P->host, NC) : 0;
+  const size_t smem = P ? adj_smem_bytes(P->host, NC, adj_ns2(m->hm, NC)) : 0;
   if (P && smem <= SMEM_LIMIT) {
     auto kern = k_tile_adj<DIM, DEG, OP>;
     int grid = 0;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = tile_grid(m, kern, m->opt_tile_threads, smem, P->dev.ntiles, &grid)) return rc;
-    kern<<<grid, m->opt_tile_threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
+    if (int rc = tile_grid(m, kern, tile_threads_of(m, NC), smem, P->dev.ntiles, &grid)) return rc;
+    kern<<<grid, tile_threads_of(m, NC), smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
   } else {
     k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
@@ -488,6 +506,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
+  else if (k == "tile_threads" && value == 0) { m->opt_tile_threads = 0; m->adj_plans.clear(); }          // back to the per-operator default
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
   else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;

@@ -353,6 +353,31 @@ __device__ __forceinline__ void local_matrix_scalar(const DevMesh& m, const Geom
   }
 }
 
+// Adjoint of the P1 elasticity local matrix B^T H B (constant B): gH = sum_{l,s} dK(l,s) col(l) (x) col(s), l = a*D+p, s = b*D+q,
+// col(c, g) = column of B for component c (device_fem.cuh).  Unweighted: grad H_k = w_k gH.
+template <int DIM, typename Get>
+__device__ __forceinline__ void stiffness_p1_adjoint(const Geom<DIM>& G, Get g, double* gH) {
+  constexpr int D = DIM + 1, NS = Voigt<DIM>::NS;
+#pragma unroll
+  for (int i = 0; i < NS * NS; i++) gH[i] = 0.0;
+  for (int cl = 0; cl < DIM; cl++)
+    for (int pl = 0; pl < D; pl++) {
+      double tl[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) tl[i] = 0.0;
+      for (int cs = 0; cs < DIM; cs++)
+        for (int ps = 0; ps < D; ps++) badd<DIM>(cs, G.gL[ps], g(cl * D + pl, cs * D + ps), tl);
+      double bl[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) bl[i] = 0.0;
+      badd<DIM>(cl, G.gL[pl], 1.0, bl);
+#pragma unroll
+      for (int i = 0; i < NS; i++)
+#pragma unroll
+        for (int j = 0; j < NS; j++) gH[i * NS + j] += bl[i] * tl[j];
+    }
+}
+
 // Local element matrix summed over Gauss points, handed to `put(slot, value)`.
 //   scalar ops (symmetric): slot = index in the packed upper triangle (p <= q, row-major)
 //   stiffness (H may be unsymmetric): slot = l*Dt + s; P2 accumulates over Gauss points through put(-slot-1, v)
@@ -782,6 +807,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
              (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < ap.ntiles) ? (ap.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
   double* sd_all = reinterpret_cast<double*>(R.bodies + (size_t)2 * ap.max_body);
   const size_t sd_stride = (size_t)NC * NC * ap.max_nnz;
+  double* gacc = sd_all + 2 * sd_stride;                   // P1 elasticity only: [NS*NS][nel] gradient matrices of the tile's elements
+  (void)gacc;
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
@@ -823,11 +850,33 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
         }
         local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[rb[p] + ((pk[p][q >> 2] >> (8 * (q & 3))) & 0xffu)]; }, grad_coef);
       } else {
-        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int l, int s) {
+        auto dK = [&](int l, int s) {
           const int a = l / D, p = l % D, b = s / D, q = s % D;
           const unsigned pos = (V.gpk[(p * W + (q >> 2)) * V.nel + le] >> (8 * (q & 3))) & 0xffu;
           return sd[(a * NC + b) * V.nnz_t + V.roff[V.td[p * V.nel + le]] + pos];
-        }, grad_coef);
+        };
+        if constexpr (DEG == 1) {
+          // P1: one gradient matrix per element (times w_k).  A thread writing the NS*NS*g gradients of ITS element touches 32
+          // different sectors per warp store, so the matrix is parked in shared memory and written by consecutive lanes below.
+          constexpr int NS2 = Voigt<DIM>::NS * Voigt<DIM>::NS;
+          double gH[NS2];
+          stiffness_p1_adjoint<DIM>(G, dK, gH);
+#pragma unroll
+          for (int c = 0; c < NS2; c++) gacc[c * V.nel + le] = gH[c] * G.wscale;
+        } else {
+          local_adjoint<DIM, DEG, OP>(m, G, e, dK, grad_coef);
+        }
+      }
+    }
+    if constexpr (NC > 1 && DEG == 1) {
+      // flat index (element, entry): consecutive threads write consecutive entries of consecutive elements
+      constexpr int NS2 = Voigt<DIM>::NS * Voigt<DIM>::NS;
+      __syncthreads();
+      for (int idx = tid; idx < V.nel * NS2; idx += nth) {
+        const int le = idx / NS2, c = idx - le * NS2;
+        double* ge = grad_coef + (size_t)V.elems[le] * m.g * NS2 + c;
+        const double v = gacc[c * V.nel + le];
+        for (int k = 0; k < m.g; k++) ge[k * NS2] = v * m.rule.w[k];
       }
     }
     cp_async_wait_all();

@@ -35,8 +35,13 @@ def timed(fn, steps):
     return ev[0].elapsed_time(ev[steps]) / steps
 
 
+OPTS = {}
+
+
 def run_csr(name, mesh, op, c_per_gauss, steps, note):
     L = _lib.lib()
+    for k, v in OPTS.items():
+        mesh.set_option(k, v)
     ncomp = mesh.dim if op == 2 else 1
     t0 = time.perf_counter()
     rowptr, _ = mesh.csr_pattern(ncomp)
@@ -64,7 +69,8 @@ def run_csr(name, mesh, op, c_per_gauss, steps, note):
             "fwd_GBps": b * E / (tf * 1e-3) / 1e9, "adj_GBps": b * E / (ta * 1e-3) / 1e9, "peak_GBps": peak,
             "step_frac": 2 * b * E / ((tf + ta) * 1e-3) / 1e9 / peak, "setup_s": round(setup, 1),
             "plan_bytes_per_elem": L.adfem_mesh_info(h, _lib.INFO_PLAN_BYTES) / E,
-            "structured_path": bool(L.adfem_mesh_info(h, _lib.INFO_STRUCTURED)) and op != 2}
+            "structured_path": bool(L.adfem_mesh_info(h, _lib.INFO_STRUCTURED)) and op != 2, "options": dict(OPTS),
+            "tiles": [int(L.adfem_mesh_info(h, _lib.INFO_TILES_FWD)), int(L.adfem_mesh_info(h, _lib.INFO_TILES_ADJ))]}
     print(json.dumps(line), flush=True)
 
 
@@ -73,8 +79,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--cases", default="3,4l,4m,5,src")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every mesh edge count by this factor (smoke runs)")
+    ap.add_argument("--smem-budget", type=int, default=0)
+    ap.add_argument("--tile-threads", type=int, default=0)
     args = ap.parse_args()
     cases = args.cases.split(",")
+    if args.smem_budget:
+        OPTS["smem_budget"] = args.smem_budget
+    if args.tile_threads:
+        OPTS["tile_threads"] = args.tile_threads
     s = args.scale
     torch.cuda.set_device(0)
     if "3" in cases:

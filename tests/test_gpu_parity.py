@@ -133,7 +133,7 @@ def _csr_check(m, o, oracle, op, coef, ofwd, obwd, ncomp, tiles):
         (g,) = torch.autograd.grad(T2.values, k, dev(dv))
         close(g.cpu().numpy().reshape(-1), expect)
     m.set_option("area_formula_csr", 0)
-    m.set_option("tile_threads", 320)
+    m.set_option("tile_threads", 0)
     m.set_option("pipeline", 1)
     m.set_option("coef_prefetch", 1)
     m.set_option("grid_limit", 0)
