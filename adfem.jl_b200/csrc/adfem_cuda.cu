@@ -388,6 +388,18 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
   return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
 }
 
+int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
+  GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
+  const int rows = adjoint ? gt.n : gt.n + 1;
+  const int strips = adjoint ? (gt.m + GRID_STRIP - 1) / GRID_STRIP : (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP;
+  const int H = grid_rows_per_warp(m, strips, rows), chunks = (rows + H - 1) / H;
+  const unsigned blocks = (unsigned)(((long long)strips * chunks + GRID_WARPS - 1) / GRID_WARPS);
+  if (adjoint) k_grid_source_adj<<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+  else k_grid_source_fwd<<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int check_op(const adfem_mesh* m, int op) {
   if (op < 0 || op > 2) return fail("unknown op");
   (void)m;
@@ -698,6 +710,7 @@ int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_grid(m)) return launch_grid_source(m, false, f, rhs, st);
 #define CALL_SRC(DIM, DEG) \
   k_source_fwd<DIM, DEG><<<blocks_for(m->hm.ndof, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, f, rhs)
   DISPATCH_ELEM(m, CALL_SRC);
@@ -709,6 +722,8 @@ int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
 int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, void* stream) {
   if (int rc = need_device(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }
+  if (use_grid(m)) return launch_grid_source(m, true, grad_rhs, grad_f, st);
   const long long G = (long long)m->hm.ne * m->hm.g;
 #define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_rhs, grad_f)
   DISPATCH_ELEM(m, CALL_SRCB);

@@ -317,6 +317,135 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
   }
 }
 
+// ---- source term on the structured triangulation (FemSourceScalar_forward/_backward, deps/MFEM/FemSource1/FemSourceScalar.h:4-32) -------------
+// per-vertex load integrals of both triangles of a VALID cell: v[r] = sum_k f_k lambda_r(x_k) w_k
+__device__ __forceinline__ void grid_cell_loads(const DevMesh& m, double x0, double x1, double y0, double y1, const double f[6], double T0[3], double T1[3]) {
+  const double2 BL = make_double2(x0, y0), BR = make_double2(x1, y0), TL = make_double2(x0, y1), TR = make_double2(x1, y1);
+  Geom<2> G0, G1;
+  geom_tri(BL, BR, TL, m.heron, G0);
+  geom_tri(TL, BR, TR, m.heron, G1);
+#pragma unroll
+  for (int r = 0; r < 3; r++) T0[r] = T1[r] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double L[3]; bary<2>(m.rule, k, L);
+    const double w0 = f[k] * (m.rule.w[k] * G0.wscale), w1 = f[3 + k] * (m.rule.w[k] * G1.wscale);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { T0[r] += L[r] * w0; T1[r] += L[r] * w1; }
+  }
+}
+
+// rhs[node] for node rows [r0, r1): lane l owns cell column / node column j0-1+l as in k_grid_fwd; one value per node, so
+// consecutive lanes write consecutive addresses and no transpose is needed
+__global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp, const double* __restrict__ f,
+                                                                     double* __restrict__ rhs) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, chunks = (r1 - r0 + rows_per_warp - 1) / rows_per_warp;
+  const long long gw = (long long)blockIdx.x * GRID_WARPS + wib;
+  if (gw >= (long long)strips * chunks) return;
+  const int strip = (int)(gw % strips), chunk = (int)(gw / strips);
+  const int j0 = strip * GRID_STRIP, cj = j0 - 1 + lane;
+  const int i0 = r0 + chunk * rows_per_warp, i1 = min(i0 + rows_per_warp, r1);
+  const bool colok = cj >= 0 && cj < gt.m, has_node = lane >= 1 && cj <= gt.m;
+  const double x0 = colok ? __ldg(gt.xs + cj) : 0.0, x1 = colok ? __ldg(gt.xs + cj + 1) : 1.0;
+  const size_t kstride = (size_t)6 * gt.m;
+  const double* kcol = f + 6 * (size_t)max(cj, 0);
+  auto load = [&](int ci, double k[6]) {
+    if (colok && ci >= 0 && ci < gt.n) {
+      const double2* p = reinterpret_cast<const double2*>(kcol + (size_t)ci * kstride);
+      const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+      k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y; k[4] = c.x; k[5] = c.y;
+    }
+  };
+  double kA[6], kB[6], kC[6], pT0[3], pT1[3], cT0[3], cT1[3];
+#pragma unroll
+  for (int s = 0; s < 6; s++) kA[s] = kB[s] = kC[s] = 0.0;
+#pragma unroll
+  for (int s = 0; s < 3; s++) pT0[s] = pT1[s] = 0.0;
+  double ya = __ldg(gt.ys + i0), yb = __ldg(gt.ys + min(i0 + 1, gt.n));
+  if (i0 > 0) {
+    load(i0 - 1, kC);
+    if (colok) grid_cell_loads(m, x0, x1, __ldg(gt.ys + i0 - 1), ya, kC, pT0, pT1);
+  }
+  load(i0, kA);
+  if (i0 + 1 < i1) load(i0 + 1, kB);
+  auto row = [&](int i, const double kcur[6], double kfill[6]) {
+    if (i + 2 < i1) load(i + 2, kfill);
+    const double yc = __ldg(gt.ys + min(i + 2, gt.n));
+    if (colok && i < gt.n) grid_cell_loads(m, x0, x1, ya, yb, kcur, cT0, cT1);
+    else {
+#pragma unroll
+      for (int s = 0; s < 3; s++) cT0[s] = cT1[s] = 0.0;
+    }
+    // incident (cell, triangle, local vertex) in ascending element order: (i-1,j-1).T1.2, (i-1,j).T0.2, (i-1,j).T1.0, (i,j-1).T0.1, (i,j-1).T1.1, (i,j).T0.0
+    const double l_p = shfl_up1(pT1[2]), l_c0 = shfl_up1(cT0[1]), l_c1 = shfl_up1(cT1[1]);
+    const double v = ((((l_p + pT0[2]) + pT1[0]) + l_c0) + l_c1) + cT0[0];
+    if (has_node) rhs[(size_t)i * (gt.m + 1) + cj] = v;
+    ya = yb; yb = yc;
+#pragma unroll
+    for (int s = 0; s < 3; s++) { pT0[s] = cT0[s]; pT1[s] = cT1[s]; }
+  };
+  for (int i = i0; i < i1; i += 3) {
+    row(i, kA, kC);
+    if (i + 1 < i1) row(i + 1, kB, kA);
+    if (i + 2 < i1) row(i + 2, kC, kB);
+  }
+}
+
+// grad_f[e*3 + k] = sum_r lambda_r(x_k) w_k grad_rhs[node_r] for cell rows [r0, r1): lane l owns node column = cell column j0+l (l < 31)
+__global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_adj(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp, const double* __restrict__ grad_rhs,
+                                                                     double* __restrict__ grad_f) {
+  __shared__ double stage_all[GRID_WARPS][GRID_STRIP * 7];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, chunks = (r1 - r0 + rows_per_warp - 1) / rows_per_warp;
+  const long long gw = (long long)blockIdx.x * GRID_WARPS + wib;
+  if (gw >= (long long)strips * chunks) return;
+  const int strip = (int)(gw % strips), chunk = (int)(gw / strips);
+  const int j0 = strip * GRID_STRIP, j = j0 + lane;
+  const int c0 = r0 + chunk * rows_per_warp, c1 = min(c0 + rows_per_warp, r1);
+  double* stage = stage_all[wib];
+  const bool node_ok = j <= gt.m, cell_ok = lane < GRID_STRIP && j < gt.m;
+  const double x0 = cell_ok ? __ldg(gt.xs + j) : 0.0, x1 = cell_ok ? __ldg(gt.xs + j + 1) : 1.0;
+  const int ncell6 = 6 * min(GRID_STRIP, gt.m - j0);
+  auto node = [&](int i) { return (node_ok && i <= gt.n) ? __ldg(grad_rhs + (size_t)i * (gt.m + 1) + j) : 0.0; };
+  double glo = node(c0), ghi = node(c0 + 1), gnx = node(c0 + 2);     // node rows ci, ci+1, ci+2 (one row ahead)
+  double ya = __ldg(gt.ys + c0), yb = __ldg(gt.ys + c0 + 1);
+  double* out = grad_f + 6 * ((size_t)c0 * gt.m + j0) + lane;
+  const size_t ostride = (size_t)6 * gt.m;
+  for (int ci = c0; ci < c1; ci++, out += ostride) {
+    const double gn2 = node(ci + 3), yc = __ldg(gt.ys + min(ci + 2, gt.n));
+    const double g_br = shfl_down1(glo), g_tr = shfl_down1(ghi);
+    double gk[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++) gk[s] = 0.0;
+    if (cell_ok) {
+      const double2 BL = make_double2(x0, ya), BR = make_double2(x1, ya), TL = make_double2(x0, yb), TR = make_double2(x1, yb);
+      Geom<2> G0, G1;
+      geom_tri(BL, BR, TL, m.heron, G0);
+      geom_tri(TL, BR, TR, m.heron, G1);
+      const double t0[3] = {glo, g_br, ghi}, t1[3] = {ghi, g_br, g_tr};   // T0 = [BL, BR, TL], T1 = [TL, BR, TR]
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double L[3]; bary<2>(m.rule, k, L);
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { a += L[r] * (m.rule.w[k] * G0.wscale) * t0[r]; b += L[r] * (m.rule.w[k] * G1.wscale) * t1[r]; }
+        gk[k] = a; gk[3 + k] = b;
+      }
+    }
+    __syncwarp();
+    if (lane < GRID_STRIP) {
+#pragma unroll
+      for (int s = 0; s < 6; s++) stage[lane * 7 + s] = gk[s];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const int t = lane + 32 * k; if (t < ncell6) out[32 * k] = stage[(t / 6) * 7 + t % 6]; }
+    glo = ghi; ghi = gnx; gnx = gn2;
+    ya = yb; yb = yc;
+  }
+}
+
 #undef S00
 #undef S01
 #undef S02

@@ -152,3 +152,31 @@ def test_structured_host_buffer_pipeline(m, n):
             _lib.check(L.adfem_assemble_csr_host(M.handle, C.c_int(op), coef.ctypes.data_as(_lib.c_dp), vals.ctypes.data_as(_lib.c_dp)))
             _lib.check(L.adfem_assemble_csr_adjoint_host(M.handle, C.c_int(op), dv.ctypes.data_as(_lib.c_dp), grad.ctypes.data_as(_lib.c_dp)))
             assert np.array_equal(vals, ref_v) and np.array_equal(grad, ref_g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+@pytest.mark.parametrize("m,n", GRIDS)
+def test_structured_source_term(oracle, m, n, kind):
+    """compute_fem_source_term1 and its adjoint on the structured path vs the oracle and vs the general kernels."""
+    import torch
+    from adfem_jl_b200 import ops
+    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else rectilinear(m, n, 4)
+    M, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    rng = np.random.default_rng(13)
+    f, gr = rng.standard_normal(o.ngauss), rng.standard_normal(o.ndof)
+    out = {}
+    for structured, rows in ((1, 0), (1, 2), (0, 0)):
+        M.set_option("structured", structured)
+        M.set_option("grid_rows", rows)
+        ft = torch.from_numpy(f).cuda().requires_grad_(True)
+        rhs = ops.compute_fem_source_term1(ft, M)
+        (g,) = torch.autograd.grad(rhs, ft, torch.from_numpy(gr).cuda())
+        _close(rhs.detach().cpu().numpy(), o.source_fwd(f))
+        _close(g.cpu().numpy(), o.source_bwd(gr))
+        out[(structured, rows)] = (rhs.detach().cpu().numpy(), g.cpu().numpy())
+    _close(out[(1, 0)][0], out[(0, 0)][0], rel=1e-13)
+    _close(out[(1, 0)][1], out[(0, 0)][1], rel=1e-13)
+    _close(out[(1, 0)][0], out[(1, 2)][0], rel=1e-14)             # row chunking only changes which inlined copy of the cell code runs
+    _close(out[(1, 0)][1], out[(1, 2)][1], rel=1e-14)
+    M.set_option("structured", 1); M.set_option("grid_rows", 0)
