@@ -146,11 +146,12 @@ bool grid_pattern_matches(const ScalarPattern& pat, int m, int n) {
 
 int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_threads : default_threads(); }
 
-// Tile-kernel launch shape.  Measured on B200 (scripts/gpu_sweep*.sh, scripts/gpu_cfg_sweep.sh): scalar operators and 2-D elasticity run best
-// with 3 CTAs of 320 threads per SM (72 KB each); 3-D elasticity keeps (3*4)^2 = 144 doubles per tile element in shared memory and wants
-// the larger tiles of 2 CTAs x 512 threads (110 KB each).
-int tile_threads_of(const adfem_mesh* m, int nc) { return m->opt_tile_threads > 0 ? m->opt_tile_threads : ((nc > 1 && m->hm.dim == 3) ? 512 : 320); }
-size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : ((nc > 1 && m->hm.dim == 3) ? 110 * 1024 : 72 * 1024); }
+// Tile-kernel launch shape.  P1 scalar operators and 2-D P1 elasticity compile to <= 64 registers: 3 CTAs of 320 threads per SM, 72 KB of
+// shared memory each (scripts/gpu_sweep*.sh).  The P2 and the 3-D elasticity kernels need 116-128 registers; at 320 threads only ONE CTA
+// fits the register file (seen in ncu: occupancy limit 1, 15 % achieved), so they run 256 threads x 2 CTAs with 110 KB tiles.
+bool heavy_kernel(const adfem_mesh* m, int nc) { return m->hm.degree == 2 || (nc > 1 && m->hm.dim == 3); }
+int tile_threads_of(const adfem_mesh* m, int nc) { return m->opt_tile_threads > 0 ? m->opt_tile_threads : (heavy_kernel(m, nc) ? 256 : 320); }
+size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : (heavy_kernel(m, nc) ? 110 * 1024 : 72 * 1024); }
 
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
