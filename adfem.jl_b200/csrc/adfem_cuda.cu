@@ -177,10 +177,11 @@ int ensure_pattern(adfem_mesh* m) {
   return 0;
 }
 
-// doubles of shared memory per tile element in the forward kernel: the local matrix (packed symmetric for scalar operators), plus the
-// Gauss-summed NS x NS coefficient matrix for P1 elasticity (cooperative coefficient load)
+// doubles of shared memory per tile element in the forward kernel: the local matrix (packed symmetric for scalar operators) plus, for the
+// scalar operators that stage their coefficients asynchronously, two buffers of g coefficients
+bool coef_staged(const HostMesh& h) { return h.degree != 1 || h.g > PIPE_GMAX; }       // scalar operators that cannot use the register prefetch
 int slots_of(const HostMesh& h, int nc) {
-  if (nc == 1) return h.d * (h.d + 1) / 2;
+  if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? 2 * h.g : 0);            // + two staging buffers of g coefficients
   const int ns = h.dim == 2 ? 3 : 6;
   (void)ns;
   return (nc * h.d) * (nc * h.d);
@@ -322,9 +323,12 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
     // register prefetch of the next tile's coefficients
     if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads &&
         (!(m->opt_variant & 2) || ((((P->host.max_elems + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31) <= threads))
-      return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true>, P, smem, threads, coef, vals, st);
+      return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true, false>, P, smem, threads, coef, vals, st);
   }
-  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false>, P, smem, threads, coef, vals, st);
+  if constexpr (OP != OP_STIFFNESS) {
+    if (coef_staged(m->hm) && m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st);
+  }
+  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, false>, P, smem, threads, coef, vals, st);
 }
 template <int DIM, int DEG, int OP>
 int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {

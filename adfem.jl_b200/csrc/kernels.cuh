@@ -666,15 +666,17 @@ __device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double
 // Forward.  Phase A evaluates the local matrices of every element touching the tile's rows into shared memory; phase B
 // lets each CSR entry sum its contributions in a fixed (column, element) order and writes it once.  KPRE (P1 scalar
 // operators, g <= PIPE_GMAX Gauss points, at most PIPE_EPT tile elements per thread): the coefficients of the NEXT tile
-// are loaded into registers before phase B of the current one; otherwise they are prefetched into L2 at that point.
+// are loaded into registers before phase B of the current one.  CST (other scalar operators: P2, or more Gauss points): they are
+// copied asynchronously (LDGSTS) into a shared-memory staging buffer instead.  Elasticity: prefetched into L2 at that point.
 constexpr int PIPE_GMAX = 4, PIPE_EPT = 2;
 // a thread owns tile elements tid + s*part, s < PIPE_EPT: every active thread gets the same number of elements (whole warps)
 __device__ __forceinline__ int pipe_part(int nel) { return (((nel + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31; }
-template <int DIM, int DEG, int OP, bool KPRE>
+template <int DIM, int DEG, int OP, bool KPRE, bool CST>
 __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
                                                                double* __restrict__ vals) {
   constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
   static_assert(!KPRE || (DEG == 1 && OP != OP_STIFFNESS), "register prefetch is for P1 scalar operators");
+  static_assert(!CST || (!KPRE && OP != OP_STIFFNESS), "coefficient staging is for scalar operators without register prefetch");
   extern __shared__ __align__(128) unsigned char smem_all[];
   __shared__ __align__(8) uint64_t mbar[5];
   const int tid = threadIdx.x, nth = blockDim.x, g = m.g;
@@ -682,12 +684,15 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   TileRing R{smem_all, smem_all + (size_t)3 * tp.max_head, mbar, tp.max_head, tp.max_body, tp.blob_ptr, tp.blob,
              (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < tp.ntiles) ? (tp.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
   double* loc = reinterpret_cast<double*>(R.bodies + (size_t)2 * tp.max_body);
+  // CST: two staging buffers [g][nel] behind the local matrices; a thread copies (cp.async) and later reads only ITS elements' coefficients
+  double* cst_all = loc + (size_t)(D * (D + 1) / 2) * tp.max_elems;
+  const size_t cst_stride = (size_t)g * tp.max_elems;
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
   if (tid == 0) R.prologue();
   double kr[KPRE ? PIPE_EPT : 1][KPRE ? PIPE_GMAX : 1];
-  auto fetch_coef = [&](const unsigned char* head) {      // coefficients of this thread's elements of the tile with this head
+  auto fetch_coef = [&](const unsigned char* head, int buf) {      // coefficients of this thread's elements of the tile with this head
     const int* hdr = reinterpret_cast<const int*>(head);
     const int nel = hdr[1];
     const int* elems = hdr + 8;
@@ -702,6 +707,12 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
           for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
         }
       }
+    } else if constexpr (CST) {
+      double* dst = cst_all + buf * cst_stride;
+      for (int le = tid; le < nel; le += nth) {
+        const double* p = coef + (size_t)elems[le] * g;
+        for (int k = 0; k < g; k++) cp_async8(dst + k * nel + le, p + k);
+      }
     } else {
       for (int le = tid; le < nel; le += nth) {
         const double* p = coef + (size_t)elems[le] * cpe;
@@ -709,9 +720,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
         prefetch_l2(p + cpe - 1);
       }
     }
+    (void)buf;
   };
   R.wait_head(0);
-  fetch_coef(R.head(0));
+  fetch_coef(R.head(0), 0);
   for (int i = 0; i < R.count; i++) {
     R.wait_body(i);
     const FwdView V(R.head(i), R.body(i), NVL, DIM, NC > 1);
@@ -726,6 +738,13 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
           local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
         }
       }
+    } else if constexpr (CST) {
+      cp_async_wait_all();                                 // this thread's copies of tile i (requested one tile ago) have landed
+      const double* cs = cst_all + (i & 1) * cst_stride;
+      for (int le = tid; le < V.nel; le += nth) {
+        Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+        local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+      }
     } else {
       for (int le = tid; le < V.nel; le += nth) {
         Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
@@ -735,7 +754,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
       }
     }
     __syncthreads();
-    if (i + 1 < R.count) { R.wait_head(i + 1); fetch_coef(R.head(i + 1)); }
+    if (i + 1 < R.count) { R.wait_head(i + 1); fetch_coef(R.head(i + 1), (i + 1) & 1); }
     // ---- phase B
     if constexpr (NC == 1) {
       fwd_gather_scalar(V, loc, vals, tid, nth, (tp.sym & 2) != 0);
