@@ -181,7 +181,7 @@ int ensure_pattern(adfem_mesh* m) {
 // scalar operators that stage their coefficients asynchronously, two buffers of g coefficients
 bool coef_staged(const HostMesh& h) { return h.degree != 1 || h.g > PIPE_GMAX; }       // scalar operators that cannot use the register prefetch
 int slots_of(const HostMesh& h, int nc) {
-  if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? 2 * h.g : 0);            // + two staging buffers of g coefficients
+  if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? h.g : 0);                // + a staging buffer of g coefficients
   const int ns = h.dim == 2 ? 3 : 6;
   (void)ns;
   return (nc * h.d) * (nc * h.d);

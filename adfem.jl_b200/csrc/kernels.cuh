@@ -684,9 +684,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   TileRing R{smem_all, smem_all + (size_t)3 * tp.max_head, mbar, tp.max_head, tp.max_body, tp.blob_ptr, tp.blob,
              (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < tp.ntiles) ? (tp.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
   double* loc = reinterpret_cast<double*>(R.bodies + (size_t)2 * tp.max_body);
-  // CST: two staging buffers [g][nel] behind the local matrices; a thread copies (cp.async) and later reads only ITS elements' coefficients
+  // CST: a staging buffer [g][nel] behind the local matrices; a thread copies (cp.async) and later reads only ITS elements' coefficients,
+  // and the copies for tile i+1 are issued after the barrier that ends phase A of tile i, so one buffer suffices
   double* cst_all = loc + (size_t)(D * (D + 1) / 2) * tp.max_elems;
-  const size_t cst_stride = (size_t)g * tp.max_elems;
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
@@ -708,10 +708,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
         }
       }
     } else if constexpr (CST) {
-      double* dst = cst_all + buf * cst_stride;
       for (int le = tid; le < nel; le += nth) {
         const double* p = coef + (size_t)elems[le] * g;
-        for (int k = 0; k < g; k++) cp_async8(dst + k * nel + le, p + k);
+        for (int k = 0; k < g; k++) cp_async8(cst_all + k * nel + le, p + k);
       }
     } else {
       for (int le = tid; le < nel; le += nth) {
@@ -740,7 +739,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
       }
     } else if constexpr (CST) {
       cp_async_wait_all();                                 // this thread's copies of tile i (requested one tile ago) have landed
-      const double* cs = cst_all + (i & 1) * cst_stride;
+      const double* cs = cst_all;
       for (int le = tid; le < V.nel; le += nth) {
         Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
         local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
