@@ -118,6 +118,36 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and the pinned host buffers it allocates afterwards, first touch) to the NUMA node its GPU hangs off, so that the
+    end-to-end host<->device copies of several ranks do not cross sockets.  Best effort: silently skipped when sysfs has no answer."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            import pynvml as nv
+            nv.nvmlInit()
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(local)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = str(bus).lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +187,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libadfem_cuda has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
@@ -287,7 +318,7 @@ def main():
         gf = sum(e[0].elapsed_time(e[1]) for e in gev) / len(gev)
         ga = sum(e[1].elapsed_time(e[2]) for e in gev) / len(gev)
         general = {"fwd_ms": gf, "adj_ms": ga, "ms_per_step": gf + ga, "value": E / ((gf + ga) * 1e-3) / 1e6, "unit": UNIT,
-                   "kernels": ["k_tile_fwd<2,1,LAPLACE,1>", "k_tile_adj<2,1,LAPLACE>"],
+                   "kernels": ["k_tile_fwd<2,1,LAPLACE,1,0>", "k_tile_adj<2,1,LAPLACE>"],
                    "plan_bytes_per_elem": L.adfem_mesh_info(h, _lib.INFO_PLAN_BYTES) / E}
         mesh.set_option("structured", 1)
 
@@ -329,7 +360,7 @@ def main():
         bf = ba = 8 * 3 + 8 * nnz / E
     else:
         bf, ba = bf72, ba72
-    fname = "k_grid_fwd<LAPLACE>" if structured else "k_tile_fwd<2,1,LAPLACE,1>"
+    fname = "k_grid_fwd<LAPLACE>" if structured else "k_tile_fwd<2,1,LAPLACE,1,0>"
     aname = "k_grid_adj<LAPLACE>" if structured else ("k_tile_adj<2,1,LAPLACE>" if args.adjoint_tiled else "k_csr_adj_gather<2,1,LAPLACE>")
     kern = {"fwd": {"name": fname, "ms": fwd_ms, "alg_bytes": bf * E, "GBps": bf * E / (fwd_ms * 1e-3) / 1e9},
             "adj": {"name": aname, "ms": adj_ms, "alg_bytes": ba * E, "GBps": ba * E / (adj_ms * 1e-3) / 1e9}}
@@ -365,7 +396,7 @@ def main():
             "config": {"workload": f"config 2: structured P1 Laplace fwd+adjoint (CSR mode), Mesh({n},{n},1/{n}) per GPU",
                        "elements_per_gpu": E, "nodes_per_gpu": mesh.nnode, "nnz_per_gpu": nnz, "gauss_points_per_gpu": G,
                        "l2_policy": "inputs larger than L2 (kappa %.2f GB, values %.2f GB per pass; no flush needed)" % (8 * G / 1e9, 8 * nnz / 1e9),
-                       "setup_s_untimed": round(t_setup, 1),
+                       "setup_s_untimed": round(t_setup, 1), "numa_node_rank0": numa,
                        "path": "structured triangulation kernels (tri_grid.cuh): no mesh-static index data" if structured else "general tile kernels",
                        "plan_bytes_per_elem": 0.0 if structured else L.adfem_mesh_info(h, _lib.INFO_PLAN_BYTES) / E,
                        "parallelism": "element slabs; NCCL all_to_all of interface rows on a side stream (reduce(vals) overlaps the adjoint kernel, "
