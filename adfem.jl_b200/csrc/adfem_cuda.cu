@@ -183,8 +183,8 @@ bool coef_staged(const HostMesh& h) { return h.degree != 1 || h.g > PIPE_GMAX; }
 int slots_of(const HostMesh& h, int nc) {
   if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? h.g : 0);                // + a staging buffer of g coefficients
   const int ns = h.dim == 2 ? 3 : 6;
-  (void)ns;
-  return (nc * h.d) * (nc * h.d);
+  // 2-D P1 elasticity stages the raw coefficient blocks (ns*ns*g doubles per element) asynchronously
+  return (nc * h.d) * (nc * h.d) + ((h.dim == 2 && h.degree == 1) ? ns * ns * h.g : 0);
 }
 
 // dynamic shared memory of the tile kernels: 3 head buffers + 2 body buffers + local matrices / 2 staging buffers
@@ -327,6 +327,9 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
   }
   if constexpr (OP != OP_STIFFNESS) {
     if (coef_staged(m->hm) && m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st);
+  }
+  if constexpr (OP == OP_STIFFNESS && DIM == 2 && DEG == 1) {
+    if (m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st);
   }
   return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, false>, P, smem, threads, coef, vals, st);
 }

@@ -353,6 +353,25 @@ __device__ __forceinline__ void local_matrix_scalar(const DevMesh& m, const Geom
   }
 }
 
+// P1 elasticity: the (DIM*D)^2 local matrix B^T H B from the Gauss-summed, weighted coefficient matrix H (NS x NS, row-major);
+// slot = l*Dt + s with l = c*D + p (component-blocked, deps/MFEM/ComputeFemStiffnessMatrixMfem/ComputeFemStiffnessMatrixMfem.h:18-34)
+template <int DIM, typename Put>
+__device__ __forceinline__ void stiffness_p1_blocks(const Geom<DIM>& G, const double* H, Put put) {
+  constexpr int D = DIM + 1, NS = Voigt<DIM>::NS, Dt = DIM * D;
+#pragma unroll
+  for (int cs = 0; cs < DIM; cs++)
+#pragma unroll
+    for (int ps = 0; ps < D; ps++) {
+      double hb[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) hb[i] = bdot<DIM>(cs, G.gL[ps], &H[i * NS]);
+#pragma unroll
+      for (int cl = 0; cl < DIM; cl++)
+#pragma unroll
+        for (int pl = 0; pl < D; pl++) put((cl * D + pl) * Dt + cs * D + ps, bdot<DIM>(cl, G.gL[pl], hb));
+    }
+}
+
 // Adjoint of the P1 elasticity local matrix B^T H B (constant B): gH = sum_{l,s} dK(l,s) col(l) (x) col(s), l = a*D+p, s = b*D+q,
 // col(c, g) = column of B for component c (device_fem.cuh).  Unweighted: grad H_k = w_k gH.
 template <int DIM, typename Get>
@@ -676,7 +695,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
                                                                double* __restrict__ vals) {
   constexpr int D = ElemTraits<DIM, DEG>::D, NC = OP == OP_STIFFNESS ? DIM : 1, Dt = NC * D, dd = D * D, NVL = DIM + 1;
   static_assert(!KPRE || (DEG == 1 && OP != OP_STIFFNESS), "register prefetch is for P1 scalar operators");
-  static_assert(!CST || (!KPRE && OP != OP_STIFFNESS), "coefficient staging is for scalar operators without register prefetch");
+  static_assert(!CST || (!KPRE && (OP != OP_STIFFNESS || DEG == 1)), "coefficient staging: scalar operators without register prefetch, P1 elasticity");
   extern __shared__ __align__(128) unsigned char smem_all[];
   __shared__ __align__(8) uint64_t mbar[5];
   const int tid = threadIdx.x, nth = blockDim.x, g = m.g;
@@ -686,7 +705,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   double* loc = reinterpret_cast<double*>(R.bodies + (size_t)2 * tp.max_body);
   // CST: a staging buffer [g][nel] behind the local matrices; a thread copies (cp.async) and later reads only ITS elements' coefficients,
   // and the copies for tile i+1 are issued after the barrier that ends phase A of tile i, so one buffer suffices
-  double* cst_all = loc + (size_t)(D * (D + 1) / 2) * tp.max_elems;
+  // P1 elasticity (CST): the raw coefficient blocks [nel][cpe] of the tile, copied with a flat (coalesced) index by all threads.
+  double* cst_all = loc + (size_t)(OP == OP_STIFFNESS ? Dt * Dt : D * (D + 1) / 2) * tp.max_elems;
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
@@ -706,6 +726,12 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
 #pragma unroll
           for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
         }
+      }
+    } else if constexpr (CST && OP == OP_STIFFNESS) {
+      // flat index over (element, coefficient): consecutive threads copy consecutive doubles of consecutive elements
+      for (int idx = tid; idx < nel * cpe; idx += nth) {
+        const int le = idx / cpe, c = idx - le * cpe;
+        cp_async8(cst_all + idx, coef + (size_t)elems[le] * cpe + c);
       }
     } else if constexpr (CST) {
       for (int le = tid; le < nel; le += nth) {
@@ -736,6 +762,23 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
           Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
           local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
         }
+      }
+    } else if constexpr (CST && OP == OP_STIFFNESS) {
+      constexpr int NS2 = Voigt<DIM>::NS * Voigt<DIM>::NS;
+      cp_async_wait_all();
+      __syncthreads();                                     // the copies of every thread have landed
+      for (int le = tid; le < V.nel; le += nth) {
+        Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+        const double* he = cst_all + (size_t)le * cpe;
+        double H[NS2];
+#pragma unroll
+        for (int c = 0; c < NS2; c++) H[c] = 0.0;
+        for (int k = 0; k < g; k++) {
+          const double w = m.rule.w[k] * G.wscale;
+#pragma unroll
+          for (int c = 0; c < NS2; c++) H[c] += he[k * NS2 + c] * w;
+        }
+        stiffness_p1_blocks<DIM>(G, H, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
       }
     } else if constexpr (CST) {
       cp_async_wait_all();                                 // this thread's copies of tile i (requested one tile ago) have landed
