@@ -732,8 +732,7 @@ int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, 
   cudaStream_t st = (cudaStream_t)stream;
   if (m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }
   if (use_grid(m)) return launch_grid_source(m, true, grad_rhs, grad_f, st);
-  const long long G = (long long)m->hm.ne * m->hm.g;
-#define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(G, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_rhs, grad_f)
+#define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_rhs, grad_f)
   DISPATCH_ELEM(m, CALL_SRCB);
 #undef CALL_SRCB
   CU_TRY(cudaGetLastError());

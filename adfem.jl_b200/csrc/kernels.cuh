@@ -251,21 +251,26 @@ __global__ void k_source_fwd(DevMesh m, const long long* __restrict__ adj_ptr, c
   }
   rhs[r] = acc;
 }
-// FemSourceScalar_backward: pure gather
+// FemSourceScalar_backward: pure gather.  One thread per ELEMENT: geometry, connectivity and the D upstream values are loaded once
+// and reused for all Gauss points.
 template <int DIM, int DEG>
 __global__ void k_source_bwd(DevMesh m, const double* __restrict__ grad_rhs, double* __restrict__ grad_f) {
   constexpr int D = ElemTraits<DIM, DEG>::D;
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= (long long)m.ne * m.g) return;
-  const int e = (int)(t / m.g), k = (int)(t % m.g);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.ne) return;
   Geom<DIM> G; load_geom(m, e, G);
-  double L[DIM + 1]; bary<DIM>(m.rule, k, L);
-  double phi[D]; basis_val<DIM, DEG>(L, phi);
-  const double w = m.rule.w[k] * G.wscale;
-  double v = 0.0;
+  double gr[D];
 #pragma unroll
-  for (int r = 0; r < D; r++) v += phi[r] * w * grad_rhs[ldg(m.conn + (size_t)r * m.ne + e)];
-  grad_f[t] = v;
+  for (int r = 0; r < D; r++) gr[r] = grad_rhs[ldg(m.conn + (size_t)r * m.ne + e)];
+  for (int k = 0; k < m.g; k++) {
+    double L[DIM + 1]; bary<DIM>(m.rule, k, L);
+    double phi[D]; basis_val<DIM, DEG>(L, phi);
+    const double w = m.rule.w[k] * G.wscale;
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; r++) v += phi[r] * w * gr[r];
+    grad_f[(size_t)e * m.g + k] = v;
+  }
 }
 
 // ==================================================================================================
