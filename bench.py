@@ -238,7 +238,7 @@ def main():
     # d loss / d K of the interface rows back, input of the adjoint) overlaps the forward kernel; reduce(vals) (interface-row partial
     # sums to their owners) overlaps the adjoint kernel.  Streams join at the start of every step.
     main = torch.cuda.current_stream()
-    side = torch.cuda.Stream() if part is not None else None
+    side = torch.cuda.Stream(priority=-1) if part is not None else None      # high priority: its small kernels slip in between the CTAs of the big ones
 
     def step(ev=None):
         if part is not None:
