@@ -71,7 +71,6 @@ struct adfem_mesh {
   int opt_smem_budget = 0;                  // dynamic shared memory per CTA (3 head + 2 body buffers + staging); 0 = per-operator default
   int opt_tile_threads = 0;                 // threads per CTA of the tile kernels; 0 = per-operator default
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
-  int opt_variant = 0;                      // forward tuning bits: 1 = rotate gather chunks over the warps, 2 = balanced phase A mapping
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
   bool adj_untileable = false;              // a CSR row has more than 255 entries: adjoint uses the direct gather kernel
@@ -307,8 +306,7 @@ int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int thr
   int grid = 0;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (int rc = tile_grid(m, kern, threads, smem, P->dev.ntiles, &grid)) return rc;
-  DevTiles dt = P->dev; dt.sym |= m->opt_variant << 1;
-  kern<<<grid, threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, dt, coef, vals);
+  kern<<<grid, threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -321,8 +319,7 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
   if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
   if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
     // register prefetch of the next tile's coefficients
-    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads &&
-        (!(m->opt_variant & 2) || ((((P->host.max_elems + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31) <= threads))
+    if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads)
       return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, true, false>, P, smem, threads, coef, vals, st);
   }
   if constexpr (OP != OP_STIFFNESS) {
@@ -531,7 +528,6 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
   else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
-  else if (k == "variant") m->opt_variant = (int)value & 3;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;

@@ -20,7 +20,7 @@ struct DevPattern {
   const uint32_t* slot_nnz;       // [d*d][ne] struct-of-arrays
 };
 struct DevTiles {                  // forward (FwdTiles) or adjoint (AdjTiles) blobs on the device
-  int ntiles, sym;                 // sym doubles as a tuning bit mask in the kernels: bit1 = rotate gather chunks, bit2 = balanced phase A
+  int ntiles, sym;
   unsigned max_head, max_body;     // bytes, multiples of 16
   int max_elems, max_nnz;
   const long long* blob_ptr;       // 2*ntiles+1: head offset, body offset per tile, then the end
@@ -646,23 +646,18 @@ struct FwdView {
 
 // phase B of the scalar forward: every gather item sums its sources in a fixed order and is written once (twice for a
 // paired item: the (r,c) and (c,r) entries of a symmetric local-matrix sum)
-__device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double* __restrict__ loc, double* __restrict__ vals, int tid, int nth, bool rotate) {
-  // 32-item chunks of every class are dealt to the warps round-robin, continuing across classes, so that no warp idles through
-  // a small class while others work: `first` is the lane offset of this thread's first item in the current class
-  int rot = 0;
+__device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double* __restrict__ loc, double* __restrict__ vals, int tid, int nth) {
   for (int c = 0; c < V.ncls; c++) {
     const int key = V.cls[4 * c], cnt = key & 0xffff, paired = key >> 16, n = V.cls[4 * c + 1];
     const unsigned short* sc = V.src + V.cls[4 * c + 2];
     const int d0 = V.cls[4 * c + 3];
-    int first = tid - rot; if (first < 0) first += nth;
-    if (rotate) rot = (rot + ((n + 31) & ~31)) % nth;
     auto put = [&](int i, double v) {
       int lr, j; V.dest(d0 + i, lr, j);
       vals[(size_t)V.rstart[lr] + j] = v;
       if (paired) { V.dest(d0 + n + i, lr, j); vals[(size_t)V.rstart[lr] + j] = v; }
     };
 #define ADFEM_GATHER_CLASS(C)                                                              \
-    for (int i = first; i < n; i += nth) {                                                 \
+    for (int i = tid; i < n; i += nth) {                                                 \
       double v = 0.0;                                                                      \
       _Pragma("unroll") for (int k = 0; k < C; k++) v += loc[sc[k * n + i]];             \
       put(i, v);                                                                           \
@@ -677,7 +672,7 @@ __device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double
       case 7: ADFEM_GATHER_CLASS(7) break;
       case 8: ADFEM_GATHER_CLASS(8) break;
       default:
-        for (int i = first; i < n; i += nth) {
+        for (int i = tid; i < n; i += nth) {
           double v = 0.0;
           for (int k = 0; k < cnt; k++) v += loc[sc[k * n + i]];
           put(i, v);
@@ -693,8 +688,6 @@ __device__ __forceinline__ void fwd_gather_scalar(const FwdView& V, const double
 // are loaded into registers before phase B of the current one.  CST (other scalar operators: P2, or more Gauss points): they are
 // copied asynchronously (LDGSTS) into a shared-memory staging buffer instead.  Elasticity: prefetched into L2 at that point.
 constexpr int PIPE_GMAX = 4, PIPE_EPT = 2;
-// a thread owns tile elements tid + s*part, s < PIPE_EPT: every active thread gets the same number of elements (whole warps)
-__device__ __forceinline__ int pipe_part(int nel) { return (((nel + PIPE_EPT - 1) / PIPE_EPT) + 31) & ~31; }
 template <int DIM, int DEG, int OP, bool KPRE, bool CST>
 __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
                                                                double* __restrict__ vals) {
@@ -722,11 +715,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     const int nel = hdr[1];
     const int* elems = hdr + 8;
     if constexpr (KPRE) {
-      const int part = (tp.sym & 4) ? pipe_part(nel) : nth;
 #pragma unroll
       for (int s = 0; s < PIPE_EPT; s++) {
-        const int le = tid + s * part;
-        if (tid < part && le < nel) {
+        const int le = tid + s * nth;
+        if (le < nel) {
           const double* p = coef + (size_t)elems[le] * g;
 #pragma unroll
           for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
@@ -759,11 +751,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     const FwdView V(R.head(i), R.body(i), NVL, DIM, NC > 1);
     // ---- phase A
     if constexpr (KPRE) {
-      const int part = (tp.sym & 4) ? pipe_part(V.nel) : nth;
 #pragma unroll
       for (int s = 0; s < PIPE_EPT; s++) {
-        const int le = tid + s * part;
-        if (tid < part && le < V.nel) {
+        const int le = tid + s * nth;
+        if (le < V.nel) {
           Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
           local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
         }
@@ -804,7 +795,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
     if (i + 1 < R.count) { R.wait_head(i + 1); fetch_coef(R.head(i + 1), (i + 1) & 1); }
     // ---- phase B
     if constexpr (NC == 1) {
-      fwd_gather_scalar(V, loc, vals, tid, nth, (tp.sym & 2) != 0);
+      fwd_gather_scalar(V, loc, vals, tid, nth);
     } else {
       for (int c = 0; c < V.ncls; c++) {
         const int cnt = V.cls[4 * c] & 0xffff, n = V.cls[4 * c + 1];

@@ -165,7 +165,6 @@ def main():
     ap.add_argument("--smem-budget", type=int, default=0)
     ap.add_argument("--pipeline", type=int, default=-1)
     ap.add_argument("--coef-prefetch", type=int, default=-1)
-    ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--structured", type=int, default=1, help="0: force the general tile kernels on the structured mesh")
     ap.add_argument("--general-steps", type=int, default=20, help="extra timed steps of the general (unstructured-mesh) tile kernels, N=1 only")
     ap.add_argument("--grid-rows", type=int, default=0)
@@ -213,8 +212,6 @@ def main():
         mesh.set_option("pipeline", args.pipeline)
     if args.coef_prefetch >= 0:
         mesh.set_option("coef_prefetch", args.coef_prefetch)
-    if args.variant >= 0:
-        mesh.set_option("variant", args.variant)
     mesh.set_option("structured", args.structured)
     if args.grid_rows:
         mesh.set_option("grid_rows", args.grid_rows)
