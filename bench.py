@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--general-steps", type=int, default=20, help="extra timed steps of the general (unstructured-mesh) tile kernels, N=1 only")
     ap.add_argument("--grid-rows", type=int, default=0)
     ap.add_argument("--grid-occupancy", type=int, default=0)
+    ap.add_argument("--host-chunks", type=int, default=0, help="node-row chunks of the pipelined host-buffer calls (end-to-end path)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -217,6 +218,8 @@ def main():
         mesh.set_option("grid_rows", args.grid_rows)
     if args.grid_occupancy:
         mesh.set_option("grid_occupancy", args.grid_occupancy)
+    if args.host_chunks:
+        mesh.set_option("host_chunks", args.host_chunks)
     structured = bool(args.structured) and L.adfem_mesh_info(mesh.handle, _lib.INFO_STRUCTURED) == 1
     rowptr, colind = mesh.csr_pattern(1)
     nnz, G, E = int(rowptr[-1]), mesh.ngauss, mesh.nelem
