@@ -565,6 +565,14 @@ int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr, int* colind) 
   return 0;
 }
 
+int adfem_csr_pattern_device(adfem_mesh* m, const long long** rowptr, const int** colind) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = ensure_pattern(m)) return rc;
+  if (rowptr) *rowptr = m->d_rowptr.p;
+  if (colind) *colind = m->d_colind.p;
+  return 0;
+}
+
 int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz) {
   if (!m) return fail("null mesh handle");
   if (int rc = ensure_pattern(m)) return rc;

@@ -127,6 +127,11 @@ int adfem_symbolic(adfem_mesh* m);
 long long adfem_csr_nnz(adfem_mesh* m, int ncomp);
 int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr /* n+1 */, int* colind /* nnz */);   /* host out, 0-based */
 int adfem_slot_to_nnz(adfem_mesh* m, unsigned int* slot_nnz /* ne*d*d, host out */);
+/* DEVICE pointers of the scalar pattern (rowptr int64[ndof+1], colind int32[nnz], 0-based), owned by the handle: together with the values
+ * written by adfem_assemble_csr this is a device-resident CSR matrix that a GPU solver (cuDSS / cuSPARSE / AMGX) can take without a host
+ * round trip — the hand-off SURVEY 8(f) ranks first after the assembly path itself. */
+int adfem_csr_pattern_device(adfem_mesh* m, const long long** rowptr, const int** colind);
+
 
 /* Inspection of the mesh-static tile plans (ADFEM_HOST_ONLY handles only; used by the CPU unit tests that
  * replay a plan against the oracle).  which_plan 0 = forward row tiles, 1 = adjoint element tiles; array_id 0 =

@@ -320,3 +320,26 @@ def test_empty_and_tiny_meshes(oracle):
             S = ops.compute_fem_laplace_matrix1(kappa, m)
             assert np.array_equal(S.indptr, rp) and np.array_equal(S.indices, ci)
             close(S.data, ref)
+
+
+def test_device_resident_csr_pattern():
+    """adfem_csr_pattern_device hands out the handle's device copies of rowptr / colind (solver hand-off): identical to the
+    host pattern, and together with adfem_assemble_csr's values a complete device CSR matrix."""
+    import ctypes as C
+
+    class _Dev:                                    # wrap a raw device pointer for torch (CUDA array interface)
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    c, e = meshgen.jitter_unstructured(13, 11, 0.1, seed=9)
+    m = A.Mesh(c, e)
+    rowptr, colind = m.csr_pattern(1)
+    prp, pci = C.c_void_p(), C.c_void_p()
+    A._lib.check(A._lib.lib().adfem_csr_pattern_device(m.handle, C.byref(prp), C.byref(pci)))
+    d_rp = torch.as_tensor(_Dev(prp.value, len(rowptr), "<i8"), device="cuda")
+    d_ci = torch.as_tensor(_Dev(pci.value, len(colind), "<i4"), device="cuda")
+    assert np.array_equal(d_rp.cpu().numpy(), rowptr) and np.array_equal(d_ci.cpu().numpy(), colind)
+    k = torch.rand(m.ngauss, dtype=torch.float64, device="cuda") + 0.5
+    T = ops.compute_fem_laplace_matrix1(k, m, mode="csr")
+    K = torch.sparse_csr_tensor(d_rp, d_ci.to(torch.int64), T.values, size=(m.ndof, m.ndof))
+    assert (K.to_dense() @ torch.ones(m.ndof, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-10       # K 1 = 0
