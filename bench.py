@@ -103,8 +103,11 @@ def cpu_reference_run(size, reps):
 def run_reference(args, rank):
     if rank != 0:
         return
-    size = args.cpu_size
-    nelem, times = cpu_reference_run(size, args.warmup + args.steps)
+    # bounded sample: the oracle port needs 0.25-0.5 us per triangle and step on one core; keep the whole run (warm-up + steps) within
+    # about two minutes whatever K the caller asks for
+    reps = max(1, args.warmup + args.steps)
+    size = min(args.cpu_size, max(128, int((120.0 / reps / 0.5e-6 / 2) ** 0.5)))
+    nelem, times = cpu_reference_run(size, reps)
     t = times[args.warmup:]
     ms = 1e3 * sum(t) / len(t)
     val = nelem / (ms * 1e-3) / 1e6
