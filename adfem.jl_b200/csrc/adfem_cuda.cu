@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/adfem_cuda.h"
+#include "gauss_ops.h"
 #include "host_mesh.h"
 #include "internal.h"
 #include "kernels.cuh"
@@ -743,6 +744,83 @@ int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, 
   return 0;
 }
 
+// ---- Gauss-point operators (gauss_ops.cu) ---------------------------------------------------------------------
+namespace {
+struct GpKind { int basis; bool weighted, scatter_fwd; };     // forward = gather (dof -> Gauss points) unless scatter_fwd
+bool gp_kind(int kind, GpKind& k) {
+  switch (kind) {
+    case ADFEM_GP_FEM_TO_GAUSS: k = {0 /* GB_P1SHAPE */, false, false}; return true;
+    case ADFEM_GP_DOF_TO_GAUSS: k = {1 /* GB_SHAPE */, false, false}; return true;
+    case ADFEM_GP_GRAD: k = {2 /* GB_GRAD */, false, false}; return true;
+    case ADFEM_GP_STRAIN: k = {3 /* GB_STRAIN */, false, false}; return true;
+    case ADFEM_GP_STRAIN_ENERGY: k = {3, true, true}; return true;
+    default: return false;
+  }
+}
+DofAdjacency dof_adjacency(const adfem_mesh* m) { return DofAdjacency{m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p}; }
+// one direction of a Gauss-point operator: to_gauss = dof values -> Gauss points (gather), else the transposed scatter
+int gp_apply(adfem_mesh* m, const GpKind& k, bool to_gauss, const double* in, double* out, cudaStream_t st) {
+  if (to_gauss) return launch_gp_gather(dev_mesh(m, m->opt_area_coo), m->hm.degree, k.basis, k.weighted, in, out, st);
+  if (int rc = ensure_pattern(m)) return rc;
+  return launch_gp_scatter(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), k.basis, k.weighted, in, out, st);
+}
+}  // namespace
+
+long long adfem_gauss_op_len(const adfem_mesh* m, int kind, int output) {
+  GpKind k;
+  if (!m || !gp_kind(kind, k)) { fail(m ? "unknown Gauss-point operator" : "null mesh handle"); return -1; }
+  const long long G = (long long)m->hm.ne * m->hm.g, dim = m->hm.dim, ns = dim == 2 ? 3 : 6;
+  long long ndofs, ngauss;
+  switch (kind) {
+    case ADFEM_GP_FEM_TO_GAUSS: ndofs = m->hm.nv; ngauss = G; break;
+    case ADFEM_GP_DOF_TO_GAUSS: ndofs = m->hm.ndof; ngauss = G; break;
+    case ADFEM_GP_GRAD: ndofs = m->hm.ndof; ngauss = G * dim; break;
+    default: ndofs = dim * m->hm.ndof; ngauss = G * ns; break;
+  }
+  return (output != 0) == k.scatter_fwd ? ndofs : ngauss;
+}
+
+int adfem_gauss_op(adfem_mesh* m, int kind, const double* in, double* out, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  GpKind k;
+  if (!gp_kind(kind, k)) return fail("unknown Gauss-point operator");
+  return gp_apply(m, k, !k.scatter_fwd, in, out, (cudaStream_t)stream);
+}
+
+int adfem_gauss_op_adjoint(adfem_mesh* m, int kind, const double* grad_out, double* grad_in, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  GpKind k;
+  if (!gp_kind(kind, k)) return fail("unknown Gauss-point operator");
+  return gp_apply(m, k, k.scatter_fwd, grad_out, grad_in, (cudaStream_t)stream);
+}
+
+int adfem_laplace_term(adfem_mesh* m, const double* nu, const double* u, double* out, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = ensure_pattern(m)) return rc;
+  return launch_laplace_term(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), nu, u, out, (cudaStream_t)stream);
+}
+
+int adfem_laplace_term_adjoint(adfem_mesh* m, const double* nu, const double* u, const double* grad_out, double* grad_nu, double* grad_u,
+                               void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (int rc = ensure_pattern(m)) return rc;
+  const DevMesh dm = dev_mesh(m, m->opt_area_coo);
+  if (grad_nu) { if (int rc = launch_laplace_term_grad_nu(dm, m->hm.degree, u, grad_out, grad_nu, (cudaStream_t)stream)) return rc; }
+  // the term is symmetric in (u, v): d/du of grad_out . K(nu) u is K(nu) grad_out
+  if (grad_u) { if (int rc = launch_laplace_term(dm, m->hm.degree, dof_adjacency(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc; }
+  return 0;
+}
+
+int adfem_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H, void* stream) {
+  if (adfem_device_count() <= 0) return fail("no usable CUDA device (there is no CPU fallback)");
+  return launch_plane_matrix(mode, n, E, nu, H, (cudaStream_t)stream);
+}
+int adfem_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
+                            void* stream) {
+  if (adfem_device_count() <= 0) return fail("no usable CUDA device (there is no CPU fallback)");
+  return launch_plane_matrix_grad(mode, n, E, nu, grad_H, grad_E, grad_nu, (cudaStream_t)stream);
+}
+
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host) {
   if (int rc = need_device(m)) return rc;
   if (int rc = check_op(m, op)) return rc;
@@ -886,6 +964,79 @@ void legacy_source_bwd(adfem_mesh* m, double* grad_f, const double* grad_rhs, co
             cudaMemcpy(grad_f, df.p, G * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
   if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); }
 }
+// Host-pointer wrapper of a device call with one or two inputs and up to two outputs: copies in, runs `call`, copies out.  `accumulate`
+// adds the result into the host array (the reference's `+=` into a caller-zeroed buffer), otherwise it overwrites.
+struct HostArg { const double* in; long long n; };
+struct HostOut { double* out; long long n; bool accumulate; };
+template <class F> void legacy_call(adfem_mesh* m, const char* name, std::initializer_list<HostArg> ins, std::initializer_list<HostOut> outs, F call) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  if (need_device(m)) { legacy_fail(name); return; }
+  std::vector<DevBuf<double>> din(ins.size()), dout(outs.size());
+  std::vector<const double*> pi; std::vector<double*> po;
+  bool ok = true;
+  size_t i = 0;
+  for (const HostArg& a : ins) {
+    ok = ok && din[i].alloc(std::max<long long>(a.n, 1)) == cudaSuccess &&
+         (a.n == 0 || cudaMemcpy(din[i].p, a.in, a.n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess);
+    pi.push_back(din[i].p); i++;
+  }
+  i = 0;
+  for (const HostOut& o : outs) { ok = ok && (o.out == nullptr || dout[i].alloc(std::max<long long>(o.n, 1)) == cudaSuccess); po.push_back(o.out ? dout[i].p : nullptr); i++; }
+  ok = ok && call(pi, po) == 0 && cudaStreamSynchronize(nullptr) == cudaSuccess;
+  i = 0;
+  std::vector<double> tmp;
+  for (const HostOut& o : outs) {
+    if (ok && o.out && o.n > 0) {
+      if (o.accumulate) {
+        tmp.resize(o.n);
+        ok = cudaMemcpy(tmp.data(), dout[i].p, o.n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok) for (long long j = 0; j < o.n; j++) o.out[j] += tmp[j];
+      } else {
+        ok = cudaMemcpy(o.out, dout[i].p, o.n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+    }
+    i++;
+  }
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); legacy_fail(name); }
+}
+void legacy_gp(adfem_mesh* m, const char* name, int kind, bool adjoint, const double* in, double* out, bool accumulate) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long nin = adfem_gauss_op_len(m, kind, adjoint ? 1 : 0), nout = adfem_gauss_op_len(m, kind, adjoint ? 0 : 1);
+  legacy_call(m, name, {{in, nin}}, {{out, nout, accumulate}}, [&](const std::vector<const double*>& pi, const std::vector<double*>& po) {
+    return adjoint ? adfem_gauss_op_adjoint(m, kind, pi[0], po[0], nullptr) : adfem_gauss_op(m, kind, pi[0], po[0], nullptr);
+  });
+}
+void legacy_laplace_term(adfem_mesh* m, const char* name, double* out, const double* nu, const double* u) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long G = (long long)m->hm.ne * m->hm.g, n = m->hm.ndof;
+  legacy_call(m, name, {{nu, G}, {u, n}}, {{out, n, true}}, [&](const std::vector<const double*>& pi, const std::vector<double*>& po) {
+    return adfem_laplace_term(m, pi[0], pi[1], po[0], nullptr);
+  });
+}
+void legacy_laplace_term_bwd(adfem_mesh* m, const char* name, double* grad_nu, double* grad_u, const double* grad_out, const double* nu, const double* u) {
+  if (!m) { fprintf(stderr, "libadfem_cuda: %s called before the mesh was initialised\n", name); return; }
+  const long long G = (long long)m->hm.ne * m->hm.g, n = m->hm.ndof;
+  legacy_call(m, name, {{nu, G}, {u, n}, {grad_out, n}}, {{grad_nu, G, true}, {grad_u, n, true}},
+              [&](const std::vector<const double*>& pi, const std::vector<double*>& po) {
+                return adfem_laplace_term_adjoint(m, pi[0], pi[1], pi[2], po[0], po[1], nullptr);
+              });
+}
+void legacy_plane(const char* name, int mode, bool backward, double* o1, double* o2, const double* g, const double* E, const double* nu, int N) {
+  DevBuf<double> dE, dnu, dH, d1, d2;
+  const size_t n = (size_t)std::max(N, 0);
+  bool ok = adfem_device_count() > 0 && dE.alloc(n + 1) == cudaSuccess && dnu.alloc(n + 1) == cudaSuccess && dH.alloc(9 * n + 1) == cudaSuccess &&
+            cudaMemcpy(dE.p, E, n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(dnu.p, nu, n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok && !backward) {
+    ok = adfem_plane_matrix(mode, N, dE.p, dnu.p, dH.p, nullptr) == 0 && cudaMemcpy(o1, dH.p, 9 * n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+  } else if (ok) {
+    ok = d1.alloc(n + 1) == cudaSuccess && d2.alloc(n + 1) == cudaSuccess && cudaMemcpy(dH.p, g, 9 * n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         adfem_plane_matrix_grad(mode, N, dE.p, dnu.p, dH.p, d1.p, d2.p, nullptr) == 0 &&
+         cudaMemcpy(o1, d1.p, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&      // o1 = grad_E
+         cudaMemcpy(o2, d2.p, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;        // o2 = grad_nu
+  }
+  if (!ok) { if (g_err.empty()) g_err = cudaGetErrorString(cudaGetLastError()); if (adfem_device_count() <= 0) g_err = "no usable CUDA device (there is no CPU fallback)"; legacy_fail(name); }
+}
 void legacy_gauss(adfem_mesh* m, double** out) {
   if (!m) return;
   const size_t G = (size_t)m->hm.ne * m->hm.g;
@@ -971,5 +1122,51 @@ void ComputeFemMassMatrixMfemT_backward(double* grad_rho, const double* grad_vv)
 void FemSourceScalarT_forward(double* rhs, const double* f) { legacy_source_fwd(g_mesh3, rhs, f, "FemSourceScalarT_forward"); }
 void FemSourceScalarT_forward_Julia(double* rhs, const double* f) { FemSourceScalarT_forward(rhs, f); }
 void FemSourceScalarT_backward(double* grad_f, const double* grad_rhs, const double*, const double*) { legacy_source_bwd(g_mesh3, grad_f, grad_rhs, "FemSourceScalarT_backward"); }
+
+// Gauss-point operators and matrix-free terms (gauss_ops.cu)
+void FemToGaussPointsMfem_forward(double* out, const double* u) { legacy_gp(g_mesh2, "FemToGaussPointsMfem_forward", ADFEM_GP_FEM_TO_GAUSS, false, u, out, false); }
+void FemToGaussPointsMfem_Julia(double* out, const double* u) { FemToGaussPointsMfem_forward(out, u); }
+void FemToGaussPointsMfem_backward(double* grad_u, const double* grad_out, const double*, const double*) {
+  legacy_gp(g_mesh2, "FemToGaussPointsMfem_backward", ADFEM_GP_FEM_TO_GAUSS, true, grad_out, grad_u, true);
+}
+void DofToGaussPointsMfem_forward(double* out, const double* u) { legacy_gp(g_mesh2, "DofToGaussPointsMfem_forward", ADFEM_GP_DOF_TO_GAUSS, false, u, out, false); }
+void DofToGaussPointsMfem_forward_Julia(double* out, const double* u) { DofToGaussPointsMfem_forward(out, u); }
+void DofToGaussPointsMfem_backward(double* grad_u, const double* grad_out, const double*, const double*) {
+  legacy_gp(g_mesh2, "DofToGaussPointsMfem_backward", ADFEM_GP_DOF_TO_GAUSS, true, grad_out, grad_u, true);
+}
+void FemGradMfem_forward(double* out, const double* u) { legacy_gp(g_mesh2, "FemGradMfem_forward", ADFEM_GP_GRAD, false, u, out, false); }
+void FemGradMfem_backward(double* grad_u, const double* grad_out, const double*, const double*) {
+  legacy_gp(g_mesh2, "FemGradMfem_backward", ADFEM_GP_GRAD, true, grad_out, grad_u, true);
+}
+void EvalStrainOnGaussPts_forward(double* epsilon, const double* u) { legacy_gp(g_mesh2, "EvalStrainOnGaussPts_forward", ADFEM_GP_STRAIN, false, u, epsilon, true); }
+void EvalStrainOnGaussPts_forward_Julia(double* epsilon, const double* u) { EvalStrainOnGaussPts_forward(epsilon, u); }
+void EvalStrainOnGaussPts_backward(double* grad_u, const double* grad_epsilon) {
+  legacy_gp(g_mesh2, "EvalStrainOnGaussPts_backward", ADFEM_GP_STRAIN, true, grad_epsilon, grad_u, true);
+}
+void ComputeStrainEnergyTermMfem_forward(double* out, const double* sigma) {
+  legacy_gp(g_mesh2, "ComputeStrainEnergyTermMfem_forward", ADFEM_GP_STRAIN_ENERGY, false, sigma, out, true);
+}
+void ComputeStrainEnergyTermMfem_forward_Julia(double* out, const double* sigma) { ComputeStrainEnergyTermMfem_forward(out, sigma); }
+void ComputeStrainEnergyTermMfem_backward(double* grad_sigma, const double* grad_out) {
+  legacy_gp(g_mesh2, "ComputeStrainEnergyTermMfem_backward", ADFEM_GP_STRAIN_ENERGY, true, grad_out, grad_sigma, true);
+}
+void ComputeLaplaceTermMfem_forward(double* out, const double* nu, const double* u) { legacy_laplace_term(g_mesh2, "ComputeLaplaceTermMfem_forward", out, nu, u); }
+void ComputeLaplaceTermMfem_forward_Julia(double* out, const double* nu, const double* u) { ComputeLaplaceTermMfem_forward(out, nu, u); }
+void ComputeLaplaceTermMfem_backward(double* grad_nu, double* grad_u, const double* grad_out, const double*, const double* nu, const double* u) {
+  legacy_laplace_term_bwd(g_mesh2, "ComputeLaplaceTermMfem_backward", grad_nu, grad_u, grad_out, nu, u);
+}
+void ComputeLaplaceTermMfemT_forward(double* out, const double* nu, const double* u) { legacy_laplace_term(g_mesh3, "ComputeLaplaceTermMfemT_forward", out, nu, u); }
+void ComputeLaplaceTermMfem3_forward_Julia(double* out, const double* nu, const double* u) { ComputeLaplaceTermMfemT_forward(out, nu, u); }
+void ComputeLaplaceTermMfemT_backward(double* grad_nu, double* grad_u, const double* grad_out, const double*, const double* nu, const double* u) {
+  legacy_laplace_term_bwd(g_mesh3, "ComputeLaplaceTermMfemT_backward", grad_nu, grad_u, grad_out, nu, u);
+}
+void PlaneStrainMatrix_forward(double* out, const double* E, const double* nu, int N) { legacy_plane("PlaneStrainMatrix_forward", 0, false, out, nullptr, nullptr, E, nu, N); }
+void PlaneStrainMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N) {
+  legacy_plane("PlaneStrainMatrix_backward", 0, true, grad_E, grad_nu, grad_out, E, nu, N);
+}
+void PlaneStressMatrix_forward(double* out, const double* E, const double* nu, int N) { legacy_plane("PlaneStressMatrix_forward", 1, false, out, nullptr, nullptr, E, nu, N); }
+void PlaneStressMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N) {
+  legacy_plane("PlaneStressMatrix_backward", 1, true, grad_E, grad_nu, grad_out, E, nu, N);
+}
 
 }  // extern "C"

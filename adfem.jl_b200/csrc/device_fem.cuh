@@ -34,11 +34,21 @@ template <int DIM> struct Geom {
   double wscale;             // w_k = rule.w[k] * wscale
 };
 
-__device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
-__device__ __forceinline__ int ldg(const int* p) { return __ldg(p); }
+// Host + device: the per-element arithmetic below is also compiled for the host by the test-only emulation harness
+// (tests/host_emul/), which runs the kernel BODIES in plain loops against the oracle on machines without a GPU.
+#define ADFEM_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+ADFEM_HD double ldg(const double* p) { return __ldg(p); }
+ADFEM_HD int ldg(const int* p) { return __ldg(p); }
+ADFEM_HD double2 ldg(const double2* p) { return __ldg(p); }
+#else
+ADFEM_HD double ldg(const double* p) { return *p; }
+ADFEM_HD int ldg(const int* p) { return *p; }
+ADFEM_HD double2 ldg(const double2* p) { return *p; }
+#endif
 
 // vertex ids of element e
-template <int DIM> __device__ __forceinline__ void load_verts(const DevMesh& m, int e, int v[DIM + 1]) {
+template <int DIM> ADFEM_HD void load_verts(const DevMesh& m, int e, int v[DIM + 1]) {
 #pragma unroll
   for (int k = 0; k <= DIM; k++) v[k] = ldg(m.verts + (size_t)k * m.ne + e);
 }
@@ -47,7 +57,7 @@ template <int DIM> __device__ __forceinline__ void load_verts(const DevMesh& m, 
 // as MFEM's CalcPhysDShape (adj(J)/det).  Weight scale: the reference uses w = ip.weight * area / 0.5 with the
 // HERON area (deps/MFEM/Common.cpp:9-15,83,116); `heron` = 0 uses area = det/2 instead (identical up to the
 // rounding of Heron's formula, 4 sqrt cheaper).
-__device__ __forceinline__ void geom_tri(const double2 p1, const double2 p2, const double2 p3, int heron, Geom<2>& G) {
+ADFEM_HD void geom_tri(const double2 p1, const double2 p2, const double2 p3, int heron, Geom<2>& G) {
   const double det = (p2.x - p1.x) * (p3.y - p1.y) - (p3.x - p1.x) * (p2.y - p1.y);
   const double inv = 1.0 / det;
   G.gL[1][0] = (p3.y - p1.y) * inv;  G.gL[1][1] = -(p3.x - p1.x) * inv;
@@ -66,7 +76,7 @@ __device__ __forceinline__ void geom_tri(const double2 p1, const double2 p2, con
 
 // Geometry of a tetrahedron: volume = det/6 (Mesh::GetElementVolume), w = ip.weight * volume * 6
 // (deps/MFEM3/Common.cpp:88,117).
-__device__ __forceinline__ void geom_tet(const double X[4][3], Geom<3>& G) {
+ADFEM_HD void geom_tet(const double X[4][3], Geom<3>& G) {
   double J[3][3];
 #pragma unroll
   for (int r = 0; r < 3; r++)
@@ -84,12 +94,12 @@ __device__ __forceinline__ void geom_tet(const double X[4][3], Geom<3>& G) {
 }
 
 // geometry of element e from the global vertex / coordinate arrays
-__device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<2>& G) {
+ADFEM_HD void load_geom(const DevMesh& m, int e, Geom<2>& G) {
   int v[3]; load_verts<2>(m, e, v);
   const double2* X = reinterpret_cast<const double2*>(m.coords);
-  geom_tri(__ldg(X + v[0]), __ldg(X + v[1]), __ldg(X + v[2]), m.heron, G);
+  geom_tri(ldg(X + v[0]), ldg(X + v[1]), ldg(X + v[2]), m.heron, G);
 }
-__device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<3>& G) {
+ADFEM_HD void load_geom(const DevMesh& m, int e, Geom<3>& G) {
   int v[4]; load_verts<3>(m, e, v);
   double X[4][3];
 #pragma unroll
@@ -100,11 +110,11 @@ __device__ __forceinline__ void load_geom(const DevMesh& m, int e, Geom<3>& G) {
 }
 // geometry of tile element `le` from a tile blob staged in shared memory: tv = k-major tile-local vertex ids,
 // xy = coordinates of the tile-local vertices
-__device__ __forceinline__ void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int heron, Geom<2>& G) {
+ADFEM_HD void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int heron, Geom<2>& G) {
   const double2* X = reinterpret_cast<const double2*>(xy);
   geom_tri(X[tv[le]], X[tv[nel + le]], X[tv[2 * nel + le]], heron, G);
 }
-__device__ __forceinline__ void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int, Geom<3>& G) {
+ADFEM_HD void tile_geom(const unsigned short* tv, const double* xy, int nel, int le, int, Geom<3>& G) {
   double X[4][3];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -115,19 +125,19 @@ __device__ __forceinline__ void tile_geom(const unsigned short* tv, const double
   geom_tet(X, G);
 }
 
-template <int DIM> __device__ __forceinline__ void bary(const QuadRule& r, int k, double L[DIM + 1]) {
+template <int DIM> ADFEM_HD void bary(const QuadRule& r, int k, double L[DIM + 1]) {
   if (DIM == 2) { L[0] = 1 - r.x[k] - r.y[k]; L[1] = r.x[k]; L[2] = r.y[k]; }
   else { L[0] = 1 - r.x[k] - r.y[k] - r.z[k]; L[1] = r.x[k]; L[2] = r.y[k]; L[DIM] = r.z[k]; }
 }
 
 // local edge (a,b) of edge function j, MFEM geometry order
-template <int DIM> __device__ __forceinline__ void edge_ends(int j, int& a, int& b) {
+template <int DIM> ADFEM_HD void edge_ends(int j, int& a, int& b) {
   if (DIM == 2) { a = j; b = j == 2 ? 0 : j + 1; }                        // (0,1) (1,2) (2,0)
   else { a = j < 3 ? 0 : (j < 5 ? 1 : 2); b = j < 3 ? j + 1 : (j < 5 ? j - 1 : 3); }   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
 }
 
 // nodal H1 basis values at barycentric point L (H1_TriangleElement / H1_TetrahedronElement, p = DEG)
-template <int DIM, int DEG> __device__ __forceinline__ void basis_val(const double L[DIM + 1], double phi[]) {
+template <int DIM, int DEG> ADFEM_HD void basis_val(const double L[DIM + 1], double phi[]) {
   constexpr int NV = DIM + 1;
   if (DEG == 1) {
 #pragma unroll
@@ -141,7 +151,7 @@ template <int DIM, int DEG> __device__ __forceinline__ void basis_val(const doub
 }
 
 // physical gradients of the basis at barycentric point L
-template <int DIM, int DEG> __device__ __forceinline__ void basis_grad(const Geom<DIM>& G, const double L[DIM + 1], double gphi[][DIM]) {
+template <int DIM, int DEG> ADFEM_HD void basis_grad(const Geom<DIM>& G, const double L[DIM + 1], double gphi[][DIM]) {
   constexpr int NV = DIM + 1;
   if (DEG == 1) {
 #pragma unroll
@@ -162,7 +172,7 @@ template <int DIM, int DEG> __device__ __forceinline__ void basis_grad(const Geo
   }
 }
 
-template <int DIM> __device__ __forceinline__ double dotg(const double* a, const double* b) {
+template <int DIM> ADFEM_HD double dotg(const double* a, const double* b) {
   double s = a[0] * b[0] + a[1] * b[1];
   if (DIM == 3) s += a[2] * b[2];
   return s;
@@ -175,18 +185,18 @@ template <int DIM> __device__ __forceinline__ double dotg(const double* a, const
 template <int DIM> struct Voigt { static constexpr int NS = DIM == 2 ? 3 : 6; };
 
 // b(c,g) . v
-template <int DIM> __device__ __forceinline__ double bdot(int c, const double* g, const double* v) {
+template <int DIM> ADFEM_HD double bdot(int c, const double* g, const double* v) {
   if (DIM == 2) return c == 0 ? g[0] * v[0] + g[1] * v[2] : g[1] * v[1] + g[0] * v[2];
   return c == 0 ? g[0] * v[0] + g[2] * v[4] + g[1] * v[5] : (c == 1 ? g[1] * v[1] + g[2] * v[3] + g[0] * v[5] : g[2] * v[2] + g[1] * v[3] + g[0] * v[4]);
 }
 // strided variant: b(c,g) . v[0], v[stride], ...
-template <int DIM> __device__ __forceinline__ double bdot_s(int c, const double* g, const double* v, int st) {
+template <int DIM> ADFEM_HD double bdot_s(int c, const double* g, const double* v, int st) {
   if (DIM == 2) return c == 0 ? g[0] * v[0] + g[1] * v[2 * st] : g[1] * v[st] + g[0] * v[2 * st];
   return c == 0 ? g[0] * v[0] + g[2] * v[4 * st] + g[1] * v[5 * st]
                 : (c == 1 ? g[1] * v[st] + g[2] * v[3 * st] + g[0] * v[5 * st] : g[2] * v[2 * st] + g[1] * v[3 * st] + g[0] * v[4 * st]);
 }
 // v += s * b(c,g)
-template <int DIM> __device__ __forceinline__ void badd(int c, const double* g, double s, double* v) {
+template <int DIM> ADFEM_HD void badd(int c, const double* g, double s, double* v) {
   if (DIM == 2) {
     if (c == 0) { v[0] += s * g[0]; v[2] += s * g[1]; } else { v[1] += s * g[1]; v[2] += s * g[0]; }
   } else {

@@ -1,0 +1,29 @@
+// Launchers of the Gauss-point operator kernels (gauss_ops.cu); the C-ABI wrappers live in adfem_cuda.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_fem.cuh"
+
+namespace adfem {
+
+// dof -> (element, local dof) adjacency of the symbolic phase, device pointers
+struct DofAdjacency {
+  const long long* ptr;
+  const int* elem;
+  const uint8_t* loc;
+};
+
+// Every launcher returns 0 or records an error (adfem_last_error) and returns 1.
+// basis: GpBasis (gauss_ops.cuh); weighted: multiply by the Gauss weights w_k.
+int launch_gp_gather(const DevMesh& dm, int degree, int basis, bool weighted, const double* in, double* out, cudaStream_t st);
+int launch_gp_scatter(const DevMesh& dm, int degree, const DofAdjacency& adj, int basis, bool weighted, const double* in, double* out,
+                      cudaStream_t st);
+int launch_laplace_term(const DevMesh& dm, int degree, const DofAdjacency& adj, const double* nu, const double* u, double* out, cudaStream_t st);
+int launch_laplace_term_grad_nu(const DevMesh& dm, int degree, const double* u, const double* grad_out, double* grad_nu, cudaStream_t st);
+int launch_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H, cudaStream_t st);
+int launch_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
+                             cudaStream_t st);
+
+}  // namespace adfem

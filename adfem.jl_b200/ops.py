@@ -204,6 +204,155 @@ def compute_fem_source_term(f1, f2, mesh):
 
 
 # =====================================================================================================
+# Gauss-point operators and matrix-free terms (csrc/gauss_ops.cu)
+# =====================================================================================================
+GP_FEM_TO_GAUSS, GP_DOF_TO_GAUSS, GP_GRAD, GP_STRAIN, GP_STRAIN_ENERGY = range(5)
+
+
+def _gp_len(mesh, kind, output):
+    n = lib().adfem_gauss_op_len(mesh.handle, C.c_int(kind), C.c_int(output))
+    if n < 0:
+        raise _lib.AdfemError(_lib.last_error())
+    return n
+
+
+class _GaussOp(torch.autograd.Function):
+    """A linear dof <-> Gauss-point map and its transpose (adfem_gauss_op / adfem_gauss_op_adjoint)."""
+
+    @staticmethod
+    def forward(ctx, x, mesh, kind):
+        if x.dtype != torch.float64 or not x.is_cuda:
+            raise TypeError("input must be a float64 CUDA tensor")
+        x = x.contiguous().view(-1)
+        if x.numel() != _gp_len(mesh, kind, 0):
+            raise AssertionError(f"input length {x.numel()} != {_gp_len(mesh, kind, 0)}")      # the reference @asserts the lengths
+        out = torch.empty(_gp_len(mesh, kind, 1), dtype=torch.float64, device=x.device)
+        check(lib().adfem_gauss_op(mesh.handle, C.c_int(kind), _ptr(x), _ptr(out), _stream()))
+        ctx.mesh, ctx.kind = mesh, kind
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad_out = grad_out.contiguous()
+        g = torch.empty(_gp_len(ctx.mesh, ctx.kind, 0), dtype=torch.float64, device=grad_out.device)
+        check(lib().adfem_gauss_op_adjoint(ctx.mesh.handle, C.c_int(ctx.kind), _ptr(grad_out), _ptr(g), _stream()))
+        return g, None, None
+
+
+def _gauss_op(x, mesh, kind):
+    if isinstance(x, np.ndarray):          # the reference's eager `Array` methods
+        return _GaussOp.apply(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(-1)).cuda(), mesh, kind).cpu().numpy()
+    return _GaussOp.apply(x, mesh, kind)
+
+
+def fem_to_gauss_points(u, mesh):
+    """Vertex values -> Gauss points with the linear shapes — src/MFEM/MUtils.jl:231-248 (op FemToGaussPointsMfem,
+    deps/MFEM/FemToGaussPoints/FemToGaussPointsMfem.h:6-35).  Only the first nnode entries of `u` are read, like the reference."""
+    nv = _gp_len(mesh, GP_FEM_TO_GAUSS, 0)
+    u = u.reshape(-1)
+    assert u.shape[0] >= nv
+    return _gauss_op(u[:nv], mesh, GP_FEM_TO_GAUSS)
+
+
+def dof_to_gauss_points(u, mesh):
+    """All dof values (edge dofs included for P2) -> Gauss points — src/MFEM/MUtils.jl:256-270 (op DofToGaussPointsMfem)."""
+    return _gauss_op(u, mesh, GP_DOF_TO_GAUSS)
+
+
+def eval_grad_on_gauss_pts1(u, mesh):
+    """Gradient of a scalar dof field at the Gauss points, ngauss x dim — src/MFEM/MCore.jl:239-246 (op FemGradMfem)."""
+    return _gauss_op(u, mesh, GP_GRAD).reshape(mesh.ngauss, mesh.dim)
+
+
+def eval_strain_on_gauss_pts(u, mesh):
+    """Strain (exx, eyy, gxy) of a displacement field `u` (2 ndof, component-blocked) at the Gauss points, ngauss x 3 —
+    src/MFEM/MCore.jl:834-849 (op EvalStrainOnGaussPts).  3-D meshes (extension): ngauss x 6, Voigt xx, yy, zz, yz, xz, xy."""
+    return _gauss_op(u, mesh, GP_STRAIN).reshape(mesh.ngauss, 3 if mesh.dim == 2 else 6)
+
+
+def compute_strain_energy_term(Sigma, mesh):
+    """`∫ σ : ε(δu)` for `Sigma` = ngauss x 3 rows (σ11, σ22, σ12); length 2 ndof — src/MFEM/MCore.jl:804-823
+    (op ComputeStrainEnergyTermMfem)."""
+    ns = 3 if mesh.dim == 2 else 6
+    assert tuple(Sigma.shape) == (mesh.ngauss, ns)
+    return _gauss_op(Sigma.reshape(-1), mesh, GP_STRAIN_ENERGY)
+
+
+class _LaplaceTerm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, nu, mesh):
+        if u.dtype != torch.float64 or nu.dtype != torch.float64 or not u.is_cuda or not nu.is_cuda:
+            raise TypeError("u and nu must be float64 CUDA tensors")
+        u, nu = u.contiguous().view(-1), nu.contiguous().view(-1)
+        assert u.numel() == mesh.ndof and nu.numel() == mesh.ngauss                             # src/MFEM/MCore.jl:741-742
+        out = torch.empty(mesh.ndof, dtype=torch.float64, device=u.device)
+        check(lib().adfem_laplace_term(mesh.handle, _ptr(nu), _ptr(u), _ptr(out), _stream()))
+        ctx.mesh = mesh
+        ctx.save_for_backward(u, nu)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        u, nu = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gu, gnu = torch.empty_like(u), torch.empty_like(nu)
+        check(lib().adfem_laplace_term_adjoint(ctx.mesh.handle, _ptr(nu), _ptr(u), _ptr(grad_out), _ptr(gnu), _ptr(gu), _stream()))
+        return gu, gnu, None
+
+
+def compute_fem_laplace_term1(u, nu, mesh):
+    """`∫ ν ∇u·∇δu` (the action of the Laplace matrix without forming it) — src/MFEM/MCore.jl:740-763, 3-D
+    src/MFEM3/MCore.jl:6-20 (ops ComputeLaplaceTermMfem / ComputeLaplaceTermMfemT)."""
+    if isinstance(u, np.ndarray) and isinstance(nu, np.ndarray):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).cuda()
+        return _LaplaceTerm.apply(t(u), t(nu), mesh).cpu().numpy()
+    dev = u.device if torch.is_tensor(u) else nu.device
+    t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev)
+    return _LaplaceTerm.apply(t(u), t(nu), mesh)
+
+
+class _PlaneMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, nu, mode):
+        if E.dtype != torch.float64 or nu.dtype != torch.float64 or not E.is_cuda or not nu.is_cuda:
+            raise TypeError("E and nu must be float64 CUDA tensors")
+        E, nu = E.contiguous().view(-1), nu.contiguous().view(-1)
+        assert E.numel() == nu.numel()                                                          # src/Core.jl:780
+        H = torch.empty((E.numel(), 3, 3), dtype=torch.float64, device=E.device)
+        check(lib().adfem_plane_matrix(C.c_int(mode), C.c_longlong(E.numel()), _ptr(E), _ptr(nu), _ptr(H), _stream()))
+        ctx.mode = mode
+        ctx.save_for_backward(E, nu)
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        E, nu = ctx.saved_tensors
+        gE, gnu = torch.empty_like(E), torch.empty_like(nu)
+        check(lib().adfem_plane_matrix_grad(C.c_int(ctx.mode), C.c_longlong(E.numel()), _ptr(E), _ptr(nu), _ptr(gH.contiguous()), _ptr(gE),
+                                            _ptr(gnu), _stream()))
+        return gE, gnu, None
+
+
+def _plane(E, nu, mode):
+    if isinstance(E, np.ndarray) and isinstance(nu, np.ndarray):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).cuda()
+        return _PlaneMatrix.apply(t(E), t(nu), mode).cpu().numpy()
+    dev = E.device if torch.is_tensor(E) else nu.device
+    t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev)
+    return _PlaneMatrix.apply(t(E), t(nu), mode)
+
+
+def compute_plane_strain_matrix(E, nu):
+    """Pointwise N x 3 x 3 tangent, the reference's `PlaneStrainMatrix` (op PlaneStrainAndStress, mode 0) — src/Core.jl:777-786."""
+    return _plane(E, nu, 0)
+
+
+def compute_plane_stress_matrix(E, nu):
+    """Pointwise N x 3 x 3 tangent, the reference's `PlaneStressMatrix` (op PlaneStrainAndStress, mode 1) — src/Core.jl:794-803."""
+    return _plane(E, nu, 1)
+
+
+# =====================================================================================================
 # Structured-grid Q1 operators (src/InvCore.jl:67-110, 206-211) and the algebraic Dirichlet step
 # =====================================================================================================
 class _QuadOp(torch.autograd.Function):

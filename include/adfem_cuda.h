@@ -90,6 +90,38 @@ void FemSourceScalarT_forward(double* rhs, const double* f);                    
 void FemSourceScalarT_backward(double* grad_f, const double* grad_rhs, const double* rhs,
                                const double* f);                                              /* FemSourceScalarT.h:17-32 */
 
+/* Gauss-point operators and matrix-free terms on the same element tables.  Host pointers, the global 2-D mesh
+ * (`…T` / `…3`: the global 3-D mesh); same argument order as the reference bodies.  Where the reference ACCUMULATES into a
+ * caller-zeroed array (every `+=` below) these wrappers add into the host array as well. */
+void FemToGaussPointsMfem_Julia(double* out, const double* u);                                    /* deps/MFEM/FemToGaussPoints/FemToGaussPointsMfem.h:38-49: out[G] = */
+void FemToGaussPointsMfem_forward(double* out, const double* u);                                  /* …h:6-18 */
+void FemToGaussPointsMfem_backward(double* grad_u, const double* grad_out, const double* out, const double* u);   /* …h:20-35: grad_u[node] += */
+void DofToGaussPointsMfem_forward_Julia(double* out, const double* u);                            /* deps/MFEM/DofToGaussPoints/DofToGaussPointsMfem.h:37-39 */
+void DofToGaussPointsMfem_forward(double* out, const double* u);                                  /* …h:6-18: out[G] = */
+void DofToGaussPointsMfem_backward(double* grad_u, const double* grad_out, const double* out, const double* u);   /* …h:20-34: grad_u[ndof] += */
+void FemGradMfem_forward(double* out, const double* u);                                           /* deps/MFEM/FemGrad/FemGradMfem.h:8-23: out[2G] = (du/dx, du/dy) interleaved */
+void FemGradMfem_backward(double* grad_u, const double* grad_out, const double* out, const double* u);            /* …h:25-42: grad_u[ndof] += */
+void EvalStrainOnGaussPts_forward_Julia(double* epsilon, const double* u);                        /* deps/MFEM/EvalStrainOnGaussPtsMfem/EvalStrainOnGaussPts.h:32-34 */
+void EvalStrainOnGaussPts_forward(double* epsilon, const double* u);                              /* …h:4-16: epsilon[3G] += (exx, eyy, gxy); u[2 ndof] component-blocked */
+void EvalStrainOnGaussPts_backward(double* grad_u, const double* grad_epsilon);                   /* …h:18-29: grad_u[2 ndof] += */
+void ComputeStrainEnergyTermMfem_forward_Julia(double* out, const double* sigma);                 /* deps/MFEM/ComputeStrainEnergyTermMfem/ComputeStrainEnergyTermMfem.h:38-40 */
+void ComputeStrainEnergyTermMfem_forward(double* out, const double* sigma);                       /* …h:4-19: out[2 ndof] += int sigma : eps(v); sigma[3G] = (s11, s22, s12) */
+void ComputeStrainEnergyTermMfem_backward(double* grad_sigma, const double* grad_out);            /* …h:21-35: grad_sigma[3G] += */
+void ComputeLaplaceTermMfem_forward_Julia(double* out, const double* nu, const double* u);        /* deps/MFEM/ComputeLaplaceTermMfem/ComputeLaplaceTermMfem.h:42-44 */
+void ComputeLaplaceTermMfem_forward(double* out, const double* nu, const double* u);              /* …h:4-17: out[ndof] += int nu grad u . grad v */
+void ComputeLaplaceTermMfem_backward(double* grad_nu, double* grad_u, const double* grad_out, const double* out,
+                                     const double* nu, const double* u);                          /* …h:19-39: both += */
+void ComputeLaplaceTermMfem3_forward_Julia(double* out, const double* nu, const double* u);       /* deps/MFEM3/ComputeLaplaceTermMfem/ComputeLaplaceTermMfemT.h:48-50 */
+void ComputeLaplaceTermMfemT_forward(double* out, const double* nu, const double* u);                 /* …T.h:4-22 */
+void ComputeLaplaceTermMfemT_backward(double* grad_nu, double* grad_u, const double* grad_out, const double* out,
+                                      const double* nu, const double* u);                         /* …T.h:24-46 */
+/* deps/MFEM/PlaneStrainAndStress/PlaneStrainAndStress.h:5-78 (the op's mode 0 / mode 1): out[9N] row-major 3x3 per point; the
+ * backward OVERWRITES grad_nu[N], grad_E[N] (note the reference's argument order: grad_nu first). */
+void PlaneStrainMatrix_forward(double* out, const double* E, const double* nu, int N);
+void PlaneStrainMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N);
+void PlaneStressMatrix_forward(double* out, const double* E, const double* nu, int N);
+void PlaneStressMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N);
+
 /* ============================ (2) handle API ================================================= */
 typedef struct adfem_mesh adfem_mesh;
 
@@ -156,6 +188,31 @@ int adfem_assemble_coo_adjoint(adfem_mesh* m, int op, const double* grad_vv, dou
 /* Source term (FemSourceScalar*): rhs[ndof] is OVERWRITTEN (no pre-zeroing needed). */
 int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream);
 int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, void* stream);
+
+/* Gauss-point operators: dof <-> Gauss-point transfers on the element tables.  DEVICE pointers; outputs are
+ * OVERWRITTEN (no pre-zeroing).  Layouts are the reference's: Gauss-point arrays element-major with NQ interleaved values per point
+ * ((e*g + k)*NQ + i), dof vectors component-blocked (dof + c*ndof).
+ *   kind                      forward: in -> out                                    reference op
+ *   ADFEM_GP_FEM_TO_GAUSS     u[nv]        -> [G]       P1 shapes, vertex values     FemToGaussPointsMfem
+ *   ADFEM_GP_DOF_TO_GAUSS     u[ndof]      -> [G]       all shape functions          DofToGaussPointsMfem
+ *   ADFEM_GP_GRAD             u[ndof]      -> [G*dim]   physical gradient            FemGradMfem
+ *   ADFEM_GP_STRAIN           u[dim*ndof]  -> [G*ns]    (exx, eyy, gxy); 3-D Voigt   EvalStrainOnGaussPts (3-D: extension)
+ *   ADFEM_GP_STRAIN_ENERGY    sigma[G*ns]  -> [dim*ndof] int sigma : eps(v)          ComputeStrainEnergyTermMfem
+ * adfem_gauss_op_len(m, kind, 0|1) = input | output length.  _adjoint maps grad_out (output-shaped) to grad_in (input-shaped). */
+enum { ADFEM_GP_FEM_TO_GAUSS = 0, ADFEM_GP_DOF_TO_GAUSS = 1, ADFEM_GP_GRAD = 2, ADFEM_GP_STRAIN = 3, ADFEM_GP_STRAIN_ENERGY = 4 };
+long long adfem_gauss_op_len(const adfem_mesh* m, int kind, int output);
+int adfem_gauss_op(adfem_mesh* m, int kind, const double* in, double* out, void* stream);
+int adfem_gauss_op_adjoint(adfem_mesh* m, int kind, const double* grad_out, double* grad_in, void* stream);
+/* ComputeLaplaceTermMfem / ...T: out[ndof] = int nu grad u . grad v (nu[G], u[ndof]); the adjoint gives grad_nu[G] and grad_u[ndof]
+ * (either may be NULL to skip it). */
+int adfem_laplace_term(adfem_mesh* m, const double* nu, const double* u, double* out, void* stream);
+int adfem_laplace_term_adjoint(adfem_mesh* m, const double* nu, const double* u, const double* grad_out, double* grad_nu, double* grad_u,
+                               void* stream);
+/* PlaneStrainAndStress op: mode 0 = PlaneStrainMatrix, 1 = PlaneStressMatrix (the reference's names and formulas,
+ * deps/MFEM/PlaneStrainAndStress/PlaneStrainAndStress.h); E[n], nu[n] -> H[9n]; the gradient overwrites grad_E[n], grad_nu[n]. */
+int adfem_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H, void* stream);
+int adfem_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
+                            void* stream);
 
 /* Algebraic Dirichlet conditions on a COO matrix — the ImposeDirichlet op (deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-93,
  * op signature ImposeDirichlet.cpp:14-57).  All pointers are DEVICE pointers.  indices: sN x 2 (row, col) 0-based; bd: bdN

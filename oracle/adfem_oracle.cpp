@@ -578,6 +578,227 @@ void oracle_FemSourceScalar_backward(double* grad_f, const double* grad_rhs) {
 }
 
 // =====================================================================================
+// Gauss-point operators and matrix-free terms on the 2-D tables.  Like the reference bodies these
+// ACCUMULATE where the reference writes `+=` (the callers zero-fill) and assign where it writes `=`.
+// =====================================================================================
+// deps/MFEM/FemToGaussPoints/FemToGaussPointsMfem.h:6-18
+void oracle_FemToGaussPointsMfem_forward(double* out, const double* u) {
+  size_t k = 0;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      out[k] = u[elem->node[0]] * elem->hs[0 * g + j] + u[elem->node[1]] * elem->hs[1 * g + j] + u[elem->node[2]] * elem->hs[2 * g + j];
+      k++;
+    }
+  }
+}
+// FemToGaussPointsMfem.h:20-35
+void oracle_FemToGaussPointsMfem_backward(double* grad_u, const double* grad_out) {
+  size_t k = 0;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      grad_u[elem->node[0]] += grad_out[k] * elem->hs[0 * g + j];
+      grad_u[elem->node[1]] += grad_out[k] * elem->hs[1 * g + j];
+      grad_u[elem->node[2]] += grad_out[k] * elem->hs[2 * g + j];
+      k++;
+    }
+  }
+}
+// deps/MFEM/DofToGaussPoints/DofToGaussPointsMfem.h:6-18
+void oracle_DofToGaussPointsMfem_forward(double* out, const double* u) {
+  size_t k = 0;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      out[k] = 0.0;
+      for (int r = 0; r < elem->ndof; r++) out[k] += u[elem->dof[r]] * elem->h[r * g + j];
+      k++;
+    }
+  }
+}
+// DofToGaussPointsMfem.h:20-34
+void oracle_DofToGaussPointsMfem_backward(double* grad_u, const double* grad_out) {
+  size_t k = 0;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      for (int r = 0; r < elem->ndof; r++) grad_u[elem->dof[r]] += grad_out[k] * elem->h[r * g + j];
+      k++;
+    }
+  }
+}
+// deps/MFEM/FemGrad/FemGradMfem.h:8-23
+void oracle_FemGradMfem_forward(double* out, const double* u) {
+  size_t k = 0;
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      out[k] = 0.0;
+      for (int r = 0; r < d; r++) out[k] += u[elem->dof[r]] * elem->hx[r * g + j];
+      k++;
+      out[k] = 0.0;
+      for (int r = 0; r < d; r++) out[k] += u[elem->dof[r]] * elem->hy[r * g + j];
+      k++;
+    }
+  }
+}
+// FemGradMfem.h:25-42
+void oracle_FemGradMfem_backward(double* grad_u, const double* grad_out) {
+  size_t k = 0;
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      for (int r = 0; r < d; r++) grad_u[elem->dof[r]] += grad_out[k] * elem->hx[r * g + j];
+      k++;
+      for (int r = 0; r < d; r++) grad_u[elem->dof[r]] += grad_out[k] * elem->hy[r * g + j];
+      k++;
+    }
+  }
+}
+// deps/MFEM/EvalStrainOnGaussPtsMfem/EvalStrainOnGaussPts.h:4-16
+void oracle_EvalStrainOnGaussPts_forward(double* epsilon, const double* u) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++)
+      for (int p = 0; p < d; p++) {
+        epsilon[((size_t)i * g + j) * 3] += elem->hx[p * g + j] * u[elem->dof[p]];
+        epsilon[((size_t)i * g + j) * 3 + 1] += elem->hy[p * g + j] * u[elem->dof[p] + mmesh.ndof];
+        epsilon[((size_t)i * g + j) * 3 + 2] += elem->hy[p * g + j] * u[elem->dof[p]] + elem->hx[p * g + j] * u[elem->dof[p] + mmesh.ndof];
+      }
+  }
+}
+// EvalStrainOnGaussPts.h:18-29
+void oracle_EvalStrainOnGaussPts_backward(double* grad_u, const double* grad_epsilon) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++)
+      for (int p = 0; p < d; p++) {
+        const double* ge = grad_epsilon + ((size_t)i * g + j) * 3;
+        grad_u[elem->dof[p]] += elem->hx[p * g + j] * ge[0] + elem->hy[p * g + j] * ge[2];
+        grad_u[elem->dof[p] + mmesh.ndof] += elem->hy[p * g + j] * ge[1] + elem->hx[p * g + j] * ge[2];
+      }
+  }
+}
+// deps/MFEM/ComputeStrainEnergyTermMfem/ComputeStrainEnergyTermMfem.h:4-19
+void oracle_ComputeStrainEnergyTermMfem_forward(double* out, const double* sigma) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      const double s11 = sigma[3 * ((size_t)i * g + j)], s22 = sigma[3 * ((size_t)i * g + j) + 1], s12 = sigma[3 * ((size_t)i * g + j) + 2];
+      for (int p = 0; p < d; p++) {
+        out[elem->dof[p]] += s11 * elem->hx[p * g + j] * elem->w[j];
+        out[elem->dof[p] + mmesh.ndof] += s22 * elem->hy[p * g + j] * elem->w[j];
+        out[elem->dof[p]] += s12 * elem->hy[p * g + j] * elem->w[j];
+        out[elem->dof[p] + mmesh.ndof] += s12 * elem->hx[p * g + j] * elem->w[j];
+      }
+    }
+  }
+}
+// ComputeStrainEnergyTermMfem.h:21-35
+void oracle_ComputeStrainEnergyTermMfem_backward(double* grad_sigma, const double* grad_out) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++)
+      for (int p = 0; p < d; p++) {
+        double* gs = grad_sigma + 3 * ((size_t)i * g + j);
+        gs[0] += elem->hx[p * g + j] * elem->w[j] * grad_out[elem->dof[p]];
+        gs[1] += elem->hy[p * g + j] * elem->w[j] * grad_out[elem->dof[p] + mmesh.ndof];
+        gs[2] += elem->hy[p * g + j] * elem->w[j] * grad_out[elem->dof[p]] + elem->hx[p * g + j] * elem->w[j] * grad_out[elem->dof[p] + mmesh.ndof];
+      }
+  }
+}
+// deps/MFEM/ComputeLaplaceTermMfem/ComputeLaplaceTermMfem.h:4-17
+void oracle_ComputeLaplaceTermMfem_forward(double* out, const double* nu, const double* u) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      const double nu_val = nu[(size_t)i * g + j];
+      for (int p = 0; p < d; p++)
+        for (int q = 0; q < d; q++)
+          out[elem->dof[p]] += nu_val * (elem->hx[p * g + j] * elem->hx[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                         elem->hy[p * g + j] * elem->hy[q * g + j] * u[elem->dof[q]] * elem->w[j]);
+    }
+  }
+}
+// ComputeLaplaceTermMfem.h:19-39
+void oracle_ComputeLaplaceTermMfem_backward(double* grad_nu, double* grad_u, const double* grad_out, const double* nu, const double* u) {
+  const int d = mmesh.elem_ndof;
+  for (int i = 0; i < mmesh.nelem; i++) {
+    Element2* elem = mmesh.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      const double nu_val = nu[(size_t)i * g + j];
+      for (int p = 0; p < d; p++)
+        for (int q = 0; q < d; q++) {
+          grad_nu[(size_t)i * g + j] += grad_out[elem->dof[p]] * (elem->hx[p * g + j] * elem->hx[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                                                  elem->hy[p * g + j] * elem->hy[q * g + j] * u[elem->dof[q]] * elem->w[j]);
+          grad_u[elem->dof[q]] += grad_out[elem->dof[p]] * nu_val * elem->hx[p * g + j] * elem->hx[q * g + j] * elem->w[j];
+          grad_u[elem->dof[q]] += grad_out[elem->dof[p]] * nu_val * elem->hy[p * g + j] * elem->hy[q * g + j] * elem->w[j];
+        }
+    }
+  }
+}
+// deps/MFEM/PlaneStrainAndStress/PlaneStrainAndStress.h:5-19 (mode 0) and :46-60 (mode 1)
+void oracle_PlaneMatrix_forward(double* out, const double* E, const double* nu, int N, int mode) {
+  for (int i = 0; i < N; i++) {
+    if (mode == 0) {
+      double s = E[i] * (1 - nu[i]) / (1 + nu[i]) / (1 - 2 * nu[i]);
+      for (int k = 0; k < 9; k++) out[9 * i + k] = (k % 4 == 0) ? s : s * nu[i] / (1 - nu[i]);
+    } else {
+      double s = E[i] / (1 + nu[i]) / (1 - 2 * nu[i]);
+      out[9 * i] = s * (1 - nu[i]); out[9 * i + 1] = s * nu[i]; out[9 * i + 2] = 0.0;
+      out[9 * i + 3] = s * nu[i]; out[9 * i + 4] = s * (1 - nu[i]); out[9 * i + 5] = 0.0;
+      out[9 * i + 6] = 0.0; out[9 * i + 7] = 0.0; out[9 * i + 8] = s * (1 - 2 * nu[i]) / 2.0;
+    }
+  }
+}
+// PlaneStrainAndStress.h:21-44, 62-78.  The reference runs a reverse-mode tape (`had`, not vendored) over the forward expressions;
+// restated here as forward-mode dual numbers over the SAME expressions (one pass per input), which yields the same derivatives.
+struct Dual { double v, d; };
+static inline Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+static inline Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+static inline Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+static inline Dual operator/(Dual a, Dual b) { return {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; }
+static inline Dual cst(double c) { return {c, 0.0}; }
+static Dual plane_L(Dual Ei, Dual nui, const double* go, int mode) {
+  if (mode == 0) {
+    Dual s = Ei * (cst(1) - nui) / (cst(1) + nui) / (cst(1) - cst(2) * nui);
+    Dual t = s * nui / (cst(1) - nui);
+    Dual L = cst(0);
+    for (int k = 0; k < 9; k++) L = L + cst(go[k]) * ((k % 4 == 0) ? s : t);
+    return L;
+  }
+  Dual s = Ei / (cst(1) + nui) / (cst(1) - cst(2) * nui);
+  return cst(go[0]) * s * (cst(1) - nui) + cst(go[1]) * s * nui + cst(go[3]) * s * nui + cst(go[4]) * s * (cst(1) - nui) +
+         cst(go[8]) * s * (cst(1) - cst(2) * nui) / cst(2.0);
+}
+void oracle_PlaneMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N, int mode) {
+  for (int i = 0; i < N; i++) {
+    grad_E[i] = plane_L({E[i], 1.0}, {nu[i], 0.0}, grad_out + 9 * i, mode).d;
+    grad_nu[i] = plane_L({E[i], 0.0}, {nu[i], 1.0}, grad_out + 9 * i, mode).d;
+  }
+}
+
+// =====================================================================================
 // ImposeDirichlet — deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-93
 // =====================================================================================
 // forward, two calls like the op shell (ImposeDirichlet.cpp:104-128): count, then copy
@@ -768,6 +989,54 @@ void oracle_ComputeFemStiffnessMatrixMfemT_backward(double* grad_hmat, const dou
         grad_hmat[k0++] = a * elem->w[j];
       }
     }
+  }
+}
+
+// deps/MFEM3/ComputeLaplaceTermMfem/ComputeLaplaceTermMfemT.h:4-22
+void oracle_ComputeLaplaceTermMfemT_forward(double* out, const double* nu, const double* u) {
+  const int d = mmesh3.elem_ndof;
+  for (int i = 0; i < mmesh3.nelem; i++) {
+    Element3* elem = mmesh3.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      const double nu_val = nu[(size_t)i * g + j];
+      for (int p = 0; p < d; p++)
+        for (int q = 0; q < d; q++)
+          out[elem->dof[p]] += nu_val * (elem->hx[p * g + j] * elem->hx[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                         elem->hy[p * g + j] * elem->hy[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                         elem->hz[p * g + j] * elem->hz[q * g + j] * u[elem->dof[q]] * elem->w[j]);
+    }
+  }
+}
+// ComputeLaplaceTermMfemT.h:24-46
+void oracle_ComputeLaplaceTermMfemT_backward(double* grad_nu, double* grad_u, const double* grad_out, const double* nu, const double* u) {
+  const int d = mmesh3.elem_ndof;
+  for (int i = 0; i < mmesh3.nelem; i++) {
+    Element3* elem = mmesh3.elements[i];
+    const int g = elem->ngauss;
+    for (int j = 0; j < g; j++) {
+      const double nu_val = nu[(size_t)i * g + j];
+      for (int p = 0; p < d; p++)
+        for (int q = 0; q < d; q++) {
+          grad_nu[(size_t)i * g + j] += grad_out[elem->dof[p]] * (elem->hx[p * g + j] * elem->hx[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                                                  elem->hy[p * g + j] * elem->hy[q * g + j] * u[elem->dof[q]] * elem->w[j] +
+                                                                  elem->hz[p * g + j] * elem->hz[q * g + j] * u[elem->dof[q]] * elem->w[j]);
+          grad_u[elem->dof[q]] += grad_out[elem->dof[p]] * nu_val * elem->hx[p * g + j] * elem->hx[q * g + j] * elem->w[j];
+          grad_u[elem->dof[q]] += grad_out[elem->dof[p]] * nu_val * elem->hy[p * g + j] * elem->hy[q * g + j] * elem->w[j];
+          grad_u[elem->dof[q]] += grad_out[elem->dof[p]] * nu_val * elem->hz[p * g + j] * elem->hz[q * g + j] * elem->w[j];
+        }
+    }
+  }
+}
+// Extension (no 3-D twin in the reference): shape tables of Element3 at the Gauss points, exported so that the tests can check the 3-D
+// Gauss-point gathers of libadfem_cuda against the oracle's own h / hx / hy / hz (layout [r*g + k] per element, elements concatenated).
+void oracle_shape_tables3(double* h, double* hx, double* hy, double* hz) {
+  size_t o = 0;
+  for (int i = 0; i < mmesh3.nelem; i++) {
+    Element3* elem = mmesh3.elements[i];
+    const size_t n = (size_t)elem->ndof * elem->ngauss;
+    for (size_t k = 0; k < n; k++) { h[o + k] = elem->h[k]; hx[o + k] = elem->hx[k]; hy[o + k] = elem->hy[k]; hz[o + k] = elem->hz[k]; }
+    o += n;
   }
 }
 

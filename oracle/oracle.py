@@ -167,6 +167,53 @@ class Mesh2D(_MeshBase):
         lib().oracle_FemSourceScalar_backward(_d(g), _d(_f64(grad_rhs)))
         return g
 
+    # --- Gauss-point operators / matrix-free terms ------------------------
+    def _vec(self, name, nout, *ins):
+        """Calls `name(out, *ins)` on a zero-filled output (the reference's callers zero-fill where the body accumulates)."""
+        self._activate()
+        out = np.zeros(nout)
+        getattr(lib(), name)(_d(out), *[_d(_f64(a)) for a in ins])
+        return out
+
+    def fem_to_gauss_fwd(self, u):
+        return self._vec("oracle_FemToGaussPointsMfem_forward", self.ngauss, u)
+
+    def fem_to_gauss_bwd(self, grad_out):
+        return self._vec("oracle_FemToGaussPointsMfem_backward", self.nnode, grad_out)
+
+    def dof_to_gauss_fwd(self, u):
+        return self._vec("oracle_DofToGaussPointsMfem_forward", self.ngauss, u)
+
+    def dof_to_gauss_bwd(self, grad_out):
+        return self._vec("oracle_DofToGaussPointsMfem_backward", self.ndof, grad_out)
+
+    def grad_fwd(self, u):
+        return self._vec("oracle_FemGradMfem_forward", 2 * self.ngauss, u)
+
+    def grad_bwd(self, grad_out):
+        return self._vec("oracle_FemGradMfem_backward", self.ndof, grad_out)
+
+    def strain_fwd(self, u):
+        return self._vec("oracle_EvalStrainOnGaussPts_forward", 3 * self.ngauss, u)
+
+    def strain_bwd(self, grad_eps):
+        return self._vec("oracle_EvalStrainOnGaussPts_backward", 2 * self.ndof, grad_eps)
+
+    def strain_energy_fwd(self, sigma):
+        return self._vec("oracle_ComputeStrainEnergyTermMfem_forward", 2 * self.ndof, sigma)
+
+    def strain_energy_bwd(self, grad_out):
+        return self._vec("oracle_ComputeStrainEnergyTermMfem_backward", 3 * self.ngauss, grad_out)
+
+    def laplace_term_fwd(self, nu, u):
+        return self._vec("oracle_ComputeLaplaceTermMfem_forward", self.ndof, nu, u)
+
+    def laplace_term_bwd(self, grad_out, nu, u):
+        self._activate()
+        gnu, gu = np.zeros(self.ngauss), np.zeros(self.ndof)
+        lib().oracle_ComputeLaplaceTermMfem_backward(_d(gnu), _d(gu), _d(_f64(grad_out)), _d(_f64(nu)), _d(_f64(u)))
+        return gnu, gu
+
 
 class Mesh3D(_MeshBase):
     """3-D tetrahedral mesh tables: deps/MFEM3/Common.cpp:9-148."""
@@ -255,6 +302,26 @@ class Mesh3D(_MeshBase):
         lib().oracle_FemSourceScalarT_backward(_d(g), _d(_f64(grad_rhs)))
         return g
 
+    def laplace_term_fwd(self, nu, u):
+        self._activate()
+        out = np.zeros(self.ndof)
+        lib().oracle_ComputeLaplaceTermMfemT_forward(_d(out), _d(_f64(nu)), _d(_f64(u)))
+        return out
+
+    def laplace_term_bwd(self, grad_out, nu, u):
+        self._activate()
+        gnu, gu = np.zeros(self.ngauss), np.zeros(self.ndof)
+        lib().oracle_ComputeLaplaceTermMfemT_backward(_d(gnu), _d(gu), _d(_f64(grad_out)), _d(_f64(nu)), _d(_f64(u)))
+        return gnu, gu
+
+    def shape_tables(self):
+        """h, hx, hy, hz of every element, each [nelem, elem_ndof, g] (extension helper, see oracle_shape_tables3)."""
+        self._activate()
+        n = self.nelem * self.elem_ndof * self.g
+        t = [np.zeros(n) for _ in range(4)]
+        lib().oracle_shape_tables3(*[_d(a) for a in t])
+        return [a.reshape(self.nelem, self.elem_ndof, self.g) for a in t]
+
 
 # --- mesh-free ops -----------------------------------------------------------------------
 def impose_dirichlet_fwd(indices, vv, bd0, rhs, bdval):
@@ -277,6 +344,21 @@ def impose_dirichlet_bwd(grad_ov, grad_orhs, indices, vv, bd0, bdval, N):
     lib().oracle_ImposeDirichlet_backward(_d(gv), _d(gr), _d(gb), _d(grad_ov), _d(grad_orhs), _l(indices), _d(vv), _l(bd), _d(bdval),
                                           C.c_int(N), C.c_int(len(bd)), C.c_int(len(vv)))
     return gv, gr, gb
+
+
+def plane_matrix_fwd(E, nu, mode):
+    """deps/MFEM/PlaneStrainAndStress/PlaneStrainAndStress.h: mode 0 = PlaneStrainMatrix, 1 = PlaneStressMatrix; [N,3,3]."""
+    E, nu = _f64(E), _f64(nu)
+    out = np.zeros(9 * len(E))
+    lib().oracle_PlaneMatrix_forward(_d(out), _d(E), _d(nu), C.c_int(len(E)), C.c_int(mode))
+    return out.reshape(-1, 3, 3)
+
+
+def plane_matrix_bwd(grad_out, E, nu, mode):
+    E, nu, grad_out = _f64(E), _f64(nu), _f64(grad_out)
+    gnu, gE = np.zeros(len(E)), np.zeros(len(E))
+    lib().oracle_PlaneMatrix_backward(_d(gnu), _d(gE), _d(grad_out), _d(E), _d(nu), C.c_int(len(E)), C.c_int(mode))
+    return gE, gnu
 
 
 def _quad(fn_name, nslot, hmat, m, n, h, extra=()):

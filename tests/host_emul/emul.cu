@@ -1,0 +1,117 @@
+// tests/host_emul/emul.cu — TEST INFRASTRUCTURE ONLY (never linked into libadfem_cuda.so, never imported by the package).
+//
+// The kernel bodies of adfem.jl_b200/csrc/gauss_ops.cuh are `__host__ __device__`; this file compiles them for the HOST and runs
+// them in plain loops that mirror the kernels of gauss_ops.cu (same indexing of inputs and outputs), so that the arithmetic the GPU
+// executes can be checked against the oracle on a machine without a GPU (tests/test_host_emulation.py).  It is a checker of the
+// device code, not a CPU path of the product: the product's entry points still fail without a CUDA device.
+#include <cstdint>
+
+#include "gauss_ops.cuh"
+
+using namespace adfem;
+
+namespace {
+
+DevMesh make_mesh(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn, bool& ok) {
+  DevMesh m{};
+  m.dim = dim; m.ne = ne; m.nv = nv; m.ndof = ndof; m.heron = 1;
+  m.d = dim == 2 ? (degree == 1 ? 3 : 6) : (degree == 1 ? 4 : 10);
+  m.coords = coords; m.verts = verts; m.conn = conn;
+  ok = dim == 2 ? triangle_rule(order, m.rule) : tetrahedron_rule(order, m.rule);
+  m.g = m.rule.n;
+  return m;
+}
+
+template <int DIM, int DEG, int B, bool W>
+void run_gather(const DevMesh& m, const double* in, double* out) {
+  for (int e = 0; e < m.ne; e++) gp_gather_body<DIM, DEG, B, W>(m, e, in, out);      // k_gp_gather
+}
+template <int DIM, int DEG, int B, bool W>
+void run_scatter(const DevMesh& m, const long long* ap, const int* ae, const uint8_t* al, const double* in, double* out) {
+  constexpr int NC = GpShape<DIM, DEG, B>::NC;
+  const int nrows = B == GB_P1SHAPE ? m.nv : m.ndof;                                   // launch_gp_scatter
+  for (int r = 0; r < nrows; r++) {                                                    // k_gp_scatter
+    double acc[NC];
+    gp_scatter_row<DIM, DEG, B, W>(m, ap, ae, al, r, in, acc);
+    for (int c = 0; c < NC; c++) out[r + (size_t)c * nrows] = acc[c];
+  }
+}
+template <int DIM, int DEG>
+int run_kind(const DevMesh& m, const long long* ap, const int* ae, const uint8_t* al, int basis, bool weighted, bool to_gauss, const double* in,
+             double* out) {
+  if (to_gauss) {
+    switch (basis) {
+      case GB_P1SHAPE: run_gather<DIM, DEG, GB_P1SHAPE, false>(m, in, out); return 0;
+      case GB_SHAPE: run_gather<DIM, DEG, GB_SHAPE, false>(m, in, out); return 0;
+      case GB_GRAD: run_gather<DIM, DEG, GB_GRAD, false>(m, in, out); return 0;
+      case GB_STRAIN: if (weighted) run_gather<DIM, DEG, GB_STRAIN, true>(m, in, out); else run_gather<DIM, DEG, GB_STRAIN, false>(m, in, out); return 0;
+    }
+    return 1;
+  }
+  switch (basis) {
+    case GB_P1SHAPE: run_scatter<DIM, DEG, GB_P1SHAPE, false>(m, ap, ae, al, in, out); return 0;
+    case GB_SHAPE: run_scatter<DIM, DEG, GB_SHAPE, false>(m, ap, ae, al, in, out); return 0;
+    case GB_GRAD: run_scatter<DIM, DEG, GB_GRAD, false>(m, ap, ae, al, in, out); return 0;
+    case GB_STRAIN: if (weighted) run_scatter<DIM, DEG, GB_STRAIN, true>(m, ap, ae, al, in, out); else run_scatter<DIM, DEG, GB_STRAIN, false>(m, ap, ae, al, in, out); return 0;
+  }
+  return 1;
+}
+
+#define EMUL_DISPATCH(dim, degree, CALL)          \
+  do {                                            \
+    if (dim == 2 && degree == 1) { CALL(2, 1); }  \
+    else if (dim == 2) { CALL(2, 2); }            \
+    else if (degree == 1) { CALL(3, 1); }         \
+    else { CALL(3, 2); }                          \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+// kind / adjoint as adfem_gauss_op / adfem_gauss_op_adjoint (include/adfem_cuda.h); the kind -> (basis, weighted, direction) table is the one
+// of gp_kind() in adfem_cuda.cu
+int emul_gauss_op(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn,
+                  const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, int kind, int adjoint, const double* in, double* out) {
+  bool ok;
+  const DevMesh m = make_mesh(dim, degree, order, nv, ne, ndof, coords, verts, conn, ok);
+  if (!ok || kind < 0 || kind > 4) return 1;
+  const int basis = kind == 4 ? GB_STRAIN : kind;
+  const bool weighted = kind == 4, scatter_fwd = kind == 4;
+  const bool to_gauss = adjoint ? scatter_fwd : !scatter_fwd;
+  int rc = 1;
+#define CALL_K(DIM, DEG) rc = run_kind<DIM, DEG>(m, adj_ptr, adj_elem, adj_loc, basis, weighted, to_gauss, in, out)
+  EMUL_DISPATCH(dim, degree, CALL_K);
+#undef CALL_K
+  return rc;
+}
+
+int emul_laplace_term(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn,
+                      const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, const double* nu, const double* u, double* out) {
+  bool ok;
+  const DevMesh m = make_mesh(dim, degree, order, nv, ne, ndof, coords, verts, conn, ok);
+  if (!ok) return 1;
+#define CALL_L(DIM, DEG) for (int r = 0; r < m.ndof; r++) out[r] = laplace_term_row<DIM, DEG>(m, adj_ptr, adj_elem, adj_loc, r, nu, u)
+  EMUL_DISPATCH(dim, degree, CALL_L);
+#undef CALL_L
+  return 0;
+}
+
+int emul_laplace_term_grad_nu(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn,
+                              const double* u, const double* go, double* grad_nu) {
+  bool ok;
+  const DevMesh m = make_mesh(dim, degree, order, nv, ne, ndof, coords, verts, conn, ok);
+  if (!ok) return 1;
+#define CALL_G(DIM, DEG) for (int e = 0; e < m.ne; e++) laplace_term_grad_nu_body<DIM, DEG>(m, e, u, go, grad_nu)
+  EMUL_DISPATCH(dim, degree, CALL_G);
+#undef CALL_G
+  return 0;
+}
+
+void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {
+  for (long long i = 0; i < n; i++) plane_matrix_body(mode, E[i], nu[i], H + 9 * i);
+}
+void emul_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* gH, double* gE, double* gnu) {
+  for (long long i = 0; i < n; i++) plane_matrix_grad_body(mode, E[i], nu[i], gH + 9 * i, gE + i, gnu + i);
+}
+}

@@ -1,0 +1,199 @@
+"""CPU tests of the Gauss-point operator KERNEL BODIES (adfem.jl_b200/csrc/gauss_ops.cuh) against the oracle.
+
+The bodies are `__host__ __device__`; tests/host_emul/emul.cu compiles them for the host (nvcc, no GPU needed) and runs them in loops
+that mirror the kernels of gauss_ops.cu.  This checks the arithmetic the GPU executes where no GPU exists; the GPU parity tests proper
+(through the C ABI) are in tests/test_widen_gauss_ops.py.  The harness is test infrastructure: nothing in the package can reach it.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import meshgen
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "host_emul", "emul.cu")
+SO = os.path.join(HERE, "host_emul", "_build", "libadfem_emul.so")
+CSRC = os.path.join(ROOT, "adfem.jl_b200", "csrc")
+
+FEM_TO_GAUSS, DOF_TO_GAUSS, GRAD, STRAIN, STRAIN_ENERGY = range(5)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "device_fem.cuh", "quadrature.h")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                               "-shared", "-Xcompiler", "-fPIC", "-I", CSRC, SRC, "-o", SO])
+    return C.CDLL(SO)
+
+
+def close(a, b, rel=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3)
+    assert err.size == 0 or err.max() <= rel, f"max rel err {err.max():.3e}"
+
+
+class HostTables:
+    """What the device sees of a mesh (struct-of-arrays connectivity, packed coordinates, dof -> (element, local) adjacency in ascending
+    element order), built here from the ORACLE's tables — the harness shares no mesh code with the product."""
+
+    def __init__(self, o):
+        self.o = o
+        self.dim = o.dim
+        self.coords = np.ascontiguousarray(o.coords[:, :o.dim], dtype=np.float64)
+        self.verts = np.ascontiguousarray(o.elems.T, dtype=np.int32)         # [dim+1][ne], post orientation fix
+        self.conn = np.ascontiguousarray(o.conn.T, dtype=np.int32)           # [d][ne]
+        ne, d = o.conn.shape
+        dof = o.conn.reshape(-1)
+        order = np.argsort(dof, kind="stable")                                 # stable: ascending element, then local index
+        self.adj_elem = np.ascontiguousarray(order // d, dtype=np.int32)
+        self.adj_loc = np.ascontiguousarray(order % d, dtype=np.uint8)
+        self.adj_ptr = np.zeros(o.ndof + 1, dtype=np.int64)
+        np.cumsum(np.bincount(dof, minlength=o.ndof), out=self.adj_ptr[1:])
+
+    def _mesh_args(self):
+        o = self.o
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        return (C.c_int(o.dim), C.c_int(o.degree), C.c_int(o.order), C.c_int(o.nnode), C.c_int(o.nelem), C.c_int(o.ndof),
+                p(self.coords, C.c_double), p(self.verts, C.c_int), p(self.conn, C.c_int))
+
+    def _adj_args(self):
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        return (p(self.adj_ptr, C.c_longlong), p(self.adj_elem, C.c_int), p(self.adj_loc, C.c_ubyte))
+
+    def gauss_op(self, L, kind, adjoint, x, nout):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.full(nout, np.nan)                 # the kernels overwrite: no zero fill
+        rc = L.emul_gauss_op(*self._mesh_args(), *self._adj_args(), C.c_int(kind), C.c_int(int(adjoint)),
+                             x.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        return out
+
+    def laplace_term(self, L, nu, u):
+        nu, u = np.ascontiguousarray(nu, dtype=np.float64), np.ascontiguousarray(u, dtype=np.float64)
+        out = np.full(self.o.ndof, np.nan)
+        d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert L.emul_laplace_term(*self._mesh_args(), *self._adj_args(), d(nu), d(u), d(out)) == 0
+        return out
+
+    def laplace_term_grad_nu(self, L, u, go):
+        u, go = np.ascontiguousarray(u, dtype=np.float64), np.ascontiguousarray(go, dtype=np.float64)
+        out = np.full(self.o.ngauss, np.nan)
+        d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert L.emul_laplace_term_grad_nu(*self._mesh_args(), d(u), d(go), d(out)) == 0
+        return out
+
+
+def mesh2(oracle, degree):
+    c, e = meshgen.jitter_unstructured(9, 7, 0.1, seed=3)
+    return oracle.Mesh2D(c, e, degree=degree)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_gauss_ops_2d_match_oracle(emul, oracle, degree):
+    o = mesh2(oracle, degree)
+    T = HostTables(o)
+    rng = np.random.default_rng(degree)
+    G, n, nv = o.ngauss, o.ndof, o.nnode
+    u, u2 = rng.standard_normal(n), rng.standard_normal(2 * n)
+    cases = [   # kind, forward input, forward output length, oracle forward, oracle adjoint, adjoint output length
+        (FEM_TO_GAUSS, u[:nv], G, o.fem_to_gauss_fwd, o.fem_to_gauss_bwd, nv),
+        (DOF_TO_GAUSS, u, G, o.dof_to_gauss_fwd, o.dof_to_gauss_bwd, n),
+        (GRAD, u, 2 * G, o.grad_fwd, o.grad_bwd, n),
+        (STRAIN, u2, 3 * G, o.strain_fwd, o.strain_bwd, 2 * n),
+        (STRAIN_ENERGY, rng.standard_normal(3 * G), 2 * n, o.strain_energy_fwd, o.strain_energy_bwd, 3 * G),
+    ]
+    for kind, x, nout, fwd, bwd, nin in cases:
+        x_full = np.concatenate([x, np.zeros(n - nv)]) if kind == FEM_TO_GAUSS else x     # the oracle indexes u by node: any length >= nnode
+        close(T.gauss_op(emul, kind, False, x, nout), fwd(x_full))
+        w = rng.standard_normal(nout)
+        close(T.gauss_op(emul, kind, True, w, nin), bwd(w))
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_laplace_term_2d_matches_oracle(emul, oracle, degree):
+    o = mesh2(oracle, degree)
+    T = HostTables(o)
+    rng = np.random.default_rng(10 + degree)
+    nu, u, go = rng.random(o.ngauss) + 0.5, rng.standard_normal(o.ndof), rng.standard_normal(o.ndof)
+    close(T.laplace_term(emul, nu, u), o.laplace_term_fwd(nu, u))
+    gnu, gu = o.laplace_term_bwd(go, nu, u)
+    close(T.laplace_term_grad_nu(emul, u, go), gnu)
+    close(T.laplace_term(emul, nu, go), gu)         # adfem_laplace_term_adjoint: grad_u = term(nu, grad_out)
+    # second opinion: the term is the assembled Laplace matrix applied to u
+    import scipy.sparse as sp
+    ind, vv = o.laplace_fwd(nu)
+    K = sp.coo_matrix((vv, (ind[:, 0], ind[:, 1])), shape=(o.ndof, o.ndof)).tocsr()
+    close(T.laplace_term(emul, nu, u), K @ u, rel=1e-10)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_ops_3d(emul, oracle, degree):
+    c, e = meshgen.tet_grid(3, 3, 2, 0.25)
+    rng = np.random.default_rng(5)
+    c = c + rng.uniform(-0.03, 0.03, c.shape)
+    o = oracle.Mesh3D(c, e, degree=degree)
+    T = HostTables(o)
+    nu, u, go = rng.random(o.ngauss) + 0.5, rng.standard_normal(o.ndof), rng.standard_normal(o.ndof)
+    close(T.laplace_term(emul, nu, u), o.laplace_term_fwd(nu, u))
+    gnu, gu = o.laplace_term_bwd(go, nu, u)
+    close(T.laplace_term_grad_nu(emul, u, go), gnu)
+    close(T.laplace_term(emul, nu, go), gu)
+    # 3-D transfers (no reference twin): against the oracle's own shape tables
+    h, hx, hy, hz = o.shape_tables()                       # [ne, d, g]
+    ul = u[o.conn]                                         # [ne, d]
+    G = o.ngauss
+    close(T.gauss_op(emul, DOF_TO_GAUSS, False, u, G), np.einsum("ed,edk->ek", ul, h).reshape(-1))
+    grad = np.stack([np.einsum("ed,edk->ek", ul, t) for t in (hx, hy, hz)], axis=2).reshape(-1)
+    close(T.gauss_op(emul, GRAD, False, u, 3 * G), grad)
+    # adjoints: <A x, w> == <x, A^T w>
+    for kind, nin, nout in ((FEM_TO_GAUSS, o.nnode, G), (DOF_TO_GAUSS, o.ndof, G), (GRAD, o.ndof, 3 * G), (STRAIN, 3 * o.ndof, 6 * G),
+                            (STRAIN_ENERGY, 6 * G, 3 * o.ndof)):
+        x, w = rng.standard_normal(nin), rng.standard_normal(nout)
+        lhs = T.gauss_op(emul, kind, False, x, nout) @ w
+        rhs = x @ T.gauss_op(emul, kind, True, w, nin)
+        assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0)
+    # 3-D strain (Voigt xx, yy, zz, yz, xz, xy; engineering shears) of a linear displacement field is exact
+    Agrad = rng.standard_normal((3, 3))
+    pos = np.zeros((o.ndof, 3)); pos[:o.nnode] = c
+    if degree == 2:
+        pos[o.nnode:] = 0.5 * (c[o.edges[:, 0]] + c[o.edges[:, 1]])
+    disp = pos @ Agrad.T                                   # u_i = A_ij x_j
+    eps = T.gauss_op(emul, STRAIN, False, disp.T.reshape(-1), 6 * G).reshape(G, 6)
+    ref = np.array([Agrad[0, 0], Agrad[1, 1], Agrad[2, 2], Agrad[1, 2] + Agrad[2, 1], Agrad[0, 2] + Agrad[2, 0], Agrad[0, 1] + Agrad[1, 0]])
+    assert np.abs(eps - ref).max() < 1e-11
+
+
+def test_plane_matrix(emul, oracle):
+    rng = np.random.default_rng(7)
+    N = 257
+    E, nu = rng.random(N) + 0.5, rng.random(N) * 0.45
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for mode in (0, 1):
+        H = np.full(9 * N, np.nan)
+        emul.emul_plane_matrix(C.c_int(mode), C.c_longlong(N), d(E), d(nu), d(H))
+        ref = oracle.plane_matrix_fwd(E, nu, mode)
+        assert np.array_equal(H.reshape(N, 3, 3), ref)                    # same expressions: bit-exact
+        g = rng.standard_normal(9 * N)
+        gE, gnu = np.full(N, np.nan), np.full(N, np.nan)
+        emul.emul_plane_matrix_grad(C.c_int(mode), C.c_longlong(N), d(E), d(nu), d(g), d(gE), d(gnu))
+        rE, rnu = oracle.plane_matrix_bwd(g, E, nu, mode)
+        close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)
+    # the documented closed forms (src/Core.jl:742-768)
+    E0, n0 = 2.0, 0.3
+    ref0 = E0 * (1 - n0) / (1 + n0) / (1 - 2 * n0) * np.array([[1, n0 / (1 - n0), n0 / (1 - n0)], [n0 / (1 - n0), 1, n0 / (1 - n0)], [n0 / (1 - n0), n0 / (1 - n0), 1]])
+    ref1 = E0 / (1 + n0) / (1 - 2 * n0) * np.array([[1 - n0, n0, 0], [n0, 1 - n0, 0], [0, 0, (1 - 2 * n0) / 2]])
+    assert np.allclose(oracle.plane_matrix_fwd([E0], [n0], 0)[0], ref0, rtol=1e-15)
+    assert np.allclose(oracle.plane_matrix_fwd([E0], [n0], 1)[0], ref1, rtol=1e-15)

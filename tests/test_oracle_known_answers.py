@@ -322,3 +322,62 @@ def test_config1_twoholes_fixture(oracle):
     assert M.ngauss * 9 == 65664                      # COO slots quoted in SURVEY §8a
     K = csr(oracle, *M.laplace_fwd(np.sin(M.gauss[:, 0]) * (1 + M.gauss[:, 1] ** 2) + 1), M.ndof)
     assert np.abs(K @ np.ones(M.ndof)).max() < 1e-10
+
+
+# ----------------------------------------------------------------------------- Gauss-point operators
+@pytest.mark.parametrize("degree", [1, 2])
+def test_gauss_point_operators_reference_test_ideas(oracle, degree):
+    """The checks the reference's own scripts make for these ops, applied to the oracle restatements."""
+    c, e = meshgen.tri_grid(10, 10, 0.1)
+    M = oracle.Mesh2D(c, e, degree=degree)
+    rng = np.random.default_rng(degree)
+    n, G = M.ndof, M.ngauss
+    pos = np.zeros((n, 2)); pos[:M.nnode] = c
+    if degree == 2:
+        pos[M.nnode:] = 0.5 * (c[M.edges[:, 0]] + c[M.edges[:, 1]])
+    gx, gy = M.gauss[:, 0], M.gauss[:, 1]
+    # deps/MFEM/ComputeLaplaceTermMfem/ftest.jl:8-15: term(u, nu) == K(nu) u
+    nu, u = rng.random(G) + 0.5, rng.random(n)
+    K = csr(oracle, *M.laplace_fwd(nu), n)
+    assert np.abs(M.laplace_term_fwd(nu, u) - K @ u).max() < 1e-12 * np.abs(K @ u).max() * 100
+    # deps/MFEM/ComputeStrainEnergyTermMfem/ftest.jl:6-18: strain_energy(K eps(u)) == Q(K) u
+    u2 = rng.random(2 * n)
+    Kc = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 0.5]])
+    eps = M.strain_fwd(u2).reshape(G, 3)
+    e1 = M.strain_energy_fwd((eps @ Kc.T).reshape(-1))
+    Q = csr(oracle, *M.stiffness_fwd(np.tile(Kc.reshape(-1), G)), 2 * n)
+    assert np.abs(e1 - Q @ u2).max() < 1e-11 * np.abs(Q @ u2).max()
+    # deps/MFEM/FemGrad/TestFemGrad.jl:7-30: gradient of 3x + 14y is (3, 14) at every Gauss point
+    g = M.grad_fwd(3 * pos[:, 0] + 14 * pos[:, 1]).reshape(G, 2)
+    assert np.abs(g - [3.0, 14.0]).max() < 1e-11
+    # deps/MFEM/FemToGaussPoints/TestFemToGaussPoints.jl:7-19: vertex interpolation reproduces linear functions at the Gauss points;
+    # dof_to_gauss_points (all dofs) also reproduces 2x^2 + y for degree 2
+    f_lin = 2 * pos[:, 0] - 0.5 * pos[:, 1] + 1
+    assert np.abs(M.fem_to_gauss_fwd(f_lin) - (2 * gx - 0.5 * gy + 1)).max() < 1e-13
+    assert np.abs(M.dof_to_gauss_fwd(f_lin) - (2 * gx - 0.5 * gy + 1)).max() < 1e-13
+    if degree == 2:
+        assert np.abs(M.dof_to_gauss_fwd(2 * pos[:, 0] ** 2 + pos[:, 1]) - (2 * gx ** 2 + gy)).max() < 1e-13
+    # adjoints are the transposes (gradtest.jl of each op checks this by finite differences)
+    for fwd, bwd, nin, nout in ((M.fem_to_gauss_fwd, M.fem_to_gauss_bwd, M.nnode, G), (M.dof_to_gauss_fwd, M.dof_to_gauss_bwd, n, G),
+                                (M.grad_fwd, M.grad_bwd, n, 2 * G), (M.strain_fwd, M.strain_bwd, 2 * n, 3 * G),
+                                (M.strain_energy_fwd, M.strain_energy_bwd, 3 * G, 2 * n)):
+        x, w = rng.standard_normal(nin), rng.standard_normal(nout)
+        xin = np.concatenate([x, np.zeros(n - nin)]) if nin == M.nnode and nin != n else x
+        lhs, rhs = fwd(xin) @ w, x @ bwd(w)
+        assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0)
+    go = rng.standard_normal(n)
+    gnu, gu = M.laplace_term_bwd(go, nu, u)
+    dnu, du = rng.standard_normal(G) * 1e-6, rng.standard_normal(n) * 1e-6
+    fd = go @ (M.laplace_term_fwd(nu + dnu, u + du) - M.laplace_term_fwd(nu - dnu, u - du)) / 2
+    assert abs(fd - (gnu @ dnu + gu @ du)) <= 1e-6 * abs(fd) + 1e-14
+
+
+def test_laplace_term_3d_equals_matrix_action(oracle):
+    """3-D twin (deps/MFEM3/ComputeLaplaceTermMfem): term(u, nu) == K(nu) u with K from FemLaplaceScalarT."""
+    c, e = meshgen.tet_grid(3, 3, 3, 1 / 3)
+    for degree in (1, 2):
+        M = oracle.Mesh3D(c, e, degree=degree)
+        rng = np.random.default_rng(3)
+        nu, u = rng.random(M.ngauss) + 0.5, rng.random(M.ndof)
+        K = csr(oracle, *M.laplace_fwd(nu), M.ndof)
+        assert np.abs(M.laplace_term_fwd(nu, u) - K @ u).max() < 1e-11 * np.abs(K @ u).max()

@@ -1,0 +1,192 @@
+"""GPU parity tests of the Gauss-point operators and matrix-free terms (csrc/gauss_ops.cu) against the oracle,
+through the C ABI (handle API via the Python mirror, and the reference's legacy host-pointer symbols).
+
+The file name sorts after the core parity files on purpose: `pytest -x` reaches these widening rows (8(f)) only after rows (a)-(e).
+The kernel bodies tested here are also run on the host by tests/test_host_emulation.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import adfem_jl_b200 as A
+from adfem_jl_b200 import meshgen
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rel=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale * 1e-3)
+    assert err.size == 0 or err.max() <= rel, f"max rel err {err.max():.3e}"
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_gauss_ops_2d(oracle, degree):
+    c, e = meshgen.jitter_unstructured(23, 17, 0.05, seed=4)
+    m, o = A.Mesh(c, e, degree=degree), oracle.Mesh2D(c, e, degree=degree)
+    rng = np.random.default_rng(degree)
+    G, n, nv = o.ngauss, o.ndof, o.nnode
+    u, u2, sig = rng.standard_normal(n), rng.standard_normal(2 * n), rng.standard_normal((G, 3))
+    cases = [   # public function, input, oracle forward, oracle adjoint
+        (A.fem_to_gauss_points, u, o.fem_to_gauss_fwd, lambda w: np.concatenate([o.fem_to_gauss_bwd(w), np.zeros(n - nv)])),
+        (A.dof_to_gauss_points, u, o.dof_to_gauss_fwd, o.dof_to_gauss_bwd),
+        (A.eval_grad_on_gauss_pts1, u, o.grad_fwd, o.grad_bwd),
+        (A.eval_strain_on_gauss_pts, u2, o.strain_fwd, o.strain_bwd),
+        (A.compute_strain_energy_term, sig, o.strain_energy_fwd, lambda w: o.strain_energy_bwd(w).reshape(G, 3)),
+    ]
+    for fn, x, fwd, bwd in cases:
+        xt = dev(x).requires_grad_(True)
+        out = fn(xt, m)
+        close(npy(out).reshape(-1), fwd(x.reshape(-1)))
+        w = rng.standard_normal(tuple(out.shape))
+        (g,) = torch.autograd.grad(out, xt, dev(w))
+        close(npy(g), bwd(w.reshape(-1)))
+        close(fn(x, m).reshape(-1), fwd(x.reshape(-1)))          # numpy in -> numpy out (the reference's eager methods)
+
+
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_laplace_term(oracle, dim, degree):
+    rng = np.random.default_rng(10 * dim + degree)
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(19, 14, 0.05, seed=5)
+        m, o = A.Mesh(c, e, degree=degree), oracle.Mesh2D(c, e, degree=degree)
+    else:
+        c, e = meshgen.tet_grid(4, 4, 3, 0.25)
+        c = c + rng.uniform(-0.03, 0.03, c.shape)
+        m, o = A.Mesh3(c, e, degree=degree), oracle.Mesh3D(c, e, degree=degree)
+    nu, u, go = rng.random(o.ngauss) + 0.5, rng.standard_normal(o.ndof), rng.standard_normal(o.ndof)
+    ut, nt = dev(u).requires_grad_(True), dev(nu).requires_grad_(True)
+    out = A.compute_fem_laplace_term1(ut, nt, m)
+    close(npy(out), o.laplace_term_fwd(nu, u))
+    gu, gnu = torch.autograd.grad(out, [ut, nt], dev(go))
+    rnu, ru = o.laplace_term_bwd(go, nu, u)
+    close(npy(gnu), rnu); close(npy(gu), ru)
+    close(A.compute_fem_laplace_term1(u, nu, m), o.laplace_term_fwd(nu, u))
+    # deps/MFEM/ComputeLaplaceTermMfem/ftest.jl:8-15: the term equals the assembled matrix applied to u
+    K = A.compute_fem_laplace_matrix1(nu, m)
+    close(npy(out), K @ u, rel=1e-10)
+
+
+def test_gauss_ops_3d(oracle):
+    """3-D transfers have no reference twin: checked against the oracle's shape tables and by transposition."""
+    rng = np.random.default_rng(6)
+    c, e = meshgen.tet_grid(4, 4, 3, 0.25)
+    c = c + rng.uniform(-0.03, 0.03, c.shape)
+    for degree in (1, 2):
+        m, o = A.Mesh3(c, e, degree=degree), oracle.Mesh3D(c, e, degree=degree)
+        h, hx, hy, hz = o.shape_tables()
+        u = rng.standard_normal(o.ndof)
+        ul = u[o.conn]
+        close(A.dof_to_gauss_points(u, m), np.einsum("ed,edk->ek", ul, h).reshape(-1))
+        close(A.eval_grad_on_gauss_pts1(u, m), np.stack([np.einsum("ed,edk->ek", ul, t) for t in (hx, hy, hz)], axis=2).reshape(-1, 3))
+        for fn, nin in ((A.fem_to_gauss_points, o.nnode), (A.dof_to_gauss_points, o.ndof), (A.eval_grad_on_gauss_pts1, o.ndof),
+                        (A.eval_strain_on_gauss_pts, 3 * o.ndof), (A.compute_strain_energy_term, (o.ngauss, 6))):
+            x = dev(rng.standard_normal(nin)).requires_grad_(True)
+            out = fn(x, m)
+            w = dev(rng.standard_normal(tuple(out.shape)))
+            (g,) = torch.autograd.grad(out, x, w)
+            lhs, rhs = float((out * w).sum()), float((x * g).sum())
+            assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_plane_matrices(oracle):
+    rng = np.random.default_rng(8)
+    N = 1000
+    E, nu = rng.random(N) + 0.5, rng.random(N) * 0.45
+    for mode, fn in ((0, A.compute_plane_strain_matrix), (1, A.compute_plane_stress_matrix)):
+        Et, nt = dev(E).requires_grad_(True), dev(nu).requires_grad_(True)
+        H = fn(Et, nt)
+        close(npy(H), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-15)
+        g = rng.standard_normal((N, 3, 3))
+        gE, gnu = torch.autograd.grad(H, [Et, nt], dev(g))
+        rE, rnu = oracle.plane_matrix_bwd(g, E, nu, mode)
+        close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
+        close(fn(E, nu), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-15)
+    # fused pre-step + assembly: H(E, nu) feeds the stiffness operator and the gradient reaches E
+    c, e = meshgen.jitter_unstructured(9, 8, 0.1, seed=1)
+    m, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    E, nu = rng.random(o.ngauss) + 0.5, rng.random(o.ngauss) * 0.4
+    Et = dev(E).requires_grad_(True)
+    Kt = A.compute_fem_stiffness_matrix(A.compute_plane_stress_matrix(Et, dev(nu)), m, mode="coo")
+    w = rng.standard_normal(Kt.values.numel())
+    (gE,) = torch.autograd.grad(Kt.values, Et, dev(w))
+    rE, _ = oracle.plane_matrix_bwd(o.stiffness_bwd(w), E, nu, 1)
+    close(npy(gE), rE, rel=1e-11)
+
+
+def test_legacy_symbols_gauss_ops(oracle):
+    """The reference's eager ccall targets (src/MFEM/MUtils.jl:241-270, MCore.jl:740-750, 804-840) on the global 2-D mesh, incl. their
+    accumulate-into-the-caller's-array behaviour."""
+    L = A._lib.lib()
+    c, e = meshgen.jitter_unstructured(10, 8, 0.1, seed=11)
+    o = oracle.Mesh2D(c, e, degree=2)
+    c3 = np.zeros((c.shape[0], 3)); c3[:, :2] = c
+    e32 = np.ascontiguousarray(e, dtype=np.int32)
+    ned = C.c_longlong(0)
+    p = L.init_nnfem_mesh(c3.ctypes.data_as(A._lib.c_dp), C.c_int(c.shape[0]), e32.ctypes.data_as(A._lib.c_ip), C.c_int(e.shape[0]),
+                          C.c_int(4), C.c_int(6), C.c_int(2), C.byref(ned))
+    C.CDLL(None).free(C.cast(p, C.c_void_p))
+    d = lambda a: a.ctypes.data_as(A._lib.c_dp)
+    rng = np.random.default_rng(12)
+    G, n = o.ngauss, o.ndof
+    u, u2, nu, sig = rng.standard_normal(n), rng.standard_normal(2 * n), rng.random(G) + 0.5, rng.standard_normal(3 * G)
+    out = np.full(G, 7.0); L.FemToGaussPointsMfem_Julia(d(out), d(u)); close(out, o.fem_to_gauss_fwd(u))            # assigns
+    out = np.full(G, 7.0); L.DofToGaussPointsMfem_forward_Julia(d(out), d(u)); close(out, o.dof_to_gauss_fwd(u))   # assigns
+    out = np.full(2 * G, 7.0); L.FemGradMfem_forward(d(out), d(u)); close(out, o.grad_fwd(u))
+    base = rng.standard_normal(3 * G)
+    out = base.copy(); L.EvalStrainOnGaussPts_forward_Julia(d(out), d(u2)); close(out, base + o.strain_fwd(u2))    # accumulates
+    base = rng.standard_normal(2 * n)
+    out = base.copy(); L.ComputeStrainEnergyTermMfem_forward_Julia(d(out), d(sig)); close(out, base + o.strain_energy_fwd(sig))
+    base = rng.standard_normal(n)
+    out = base.copy(); L.ComputeLaplaceTermMfem_forward_Julia(d(out), d(nu), d(u)); close(out, base + o.laplace_term_fwd(nu, u))
+    go = rng.standard_normal(n)
+    gnu, gu = np.zeros(G), np.zeros(n)
+    L.ComputeLaplaceTermMfem_backward(d(gnu), d(gu), d(go), None, d(nu), d(u))
+    rnu, ru = o.laplace_term_bwd(go, nu, u)
+    close(gnu, rnu); close(gu, ru)
+    w = rng.standard_normal(G)
+    g = np.zeros(n); L.DofToGaussPointsMfem_backward(d(g), d(w), None, None); close(g, o.dof_to_gauss_bwd(w))
+    g = np.zeros(n); L.FemToGaussPointsMfem_backward(d(g), d(w), None, None); close(g[:o.nnode], o.fem_to_gauss_bwd(w)); assert not g[o.nnode:].any()
+    w2 = rng.standard_normal(2 * G)
+    g = np.zeros(n); L.FemGradMfem_backward(d(g), d(w2), None, None); close(g, o.grad_bwd(w2))
+    w3 = rng.standard_normal(3 * G)
+    g = np.zeros(2 * n); L.EvalStrainOnGaussPts_backward(d(g), d(w3)); close(g, o.strain_bwd(w3))
+    w4 = rng.standard_normal(2 * n)
+    g = np.zeros(3 * G); L.ComputeStrainEnergyTermMfem_backward(d(g), d(w4)); close(g, o.strain_energy_bwd(w4))
+    N = 50
+    E, pr = rng.random(N) + 0.5, rng.random(N) * 0.45
+    H = np.zeros(9 * N); L.PlaneStrainMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 0), rel=1e-15)
+    H = np.zeros(9 * N); L.PlaneStressMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 1), rel=1e-15)
+    gH = rng.standard_normal(9 * N)
+    gn, gE = np.zeros(N), np.zeros(N)
+    L.PlaneStressMatrix_backward(d(gn), d(gE), d(gH), d(E), d(pr), C.c_int(N))
+    rE, rn = oracle.plane_matrix_bwd(gH, E, pr, 1)
+    close(gE, rE, rel=1e-11); close(gn, rn, rel=1e-11)
+
+
+def test_laplace_term_3d_legacy(oracle):
+    L = A._lib.lib()
+    c, e = meshgen.tet_grid(3, 3, 3, 0.3)
+    o = oracle.Mesh3D(c, e, degree=1)
+    e32, cc = np.ascontiguousarray(e, dtype=np.int32), np.ascontiguousarray(c)
+    ned = C.c_longlong(0)
+    p = L.init_nnfem_mesh3(cc.ctypes.data_as(A._lib.c_dp), C.c_int(c.shape[0]), e32.ctypes.data_as(A._lib.c_ip), C.c_int(e.shape[0]),
+                           C.c_int(2), C.c_int(1), C.byref(ned))
+    C.CDLL(None).free(C.cast(p, C.c_void_p))
+    rng = np.random.default_rng(13)
+    nu, u = rng.random(o.ngauss) + 0.5, rng.standard_normal(o.ndof)
+    out = np.zeros(o.ndof)
+    d = lambda a: a.ctypes.data_as(A._lib.c_dp)
+    L.ComputeLaplaceTermMfem3_forward_Julia(d(out), d(nu), d(u))
+    close(out, o.laplace_term_fwd(nu, u))
