@@ -74,6 +74,9 @@ struct adfem_mesh {
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
+  int opt_coef_presum = 0;                  // P1 elasticity: reduce the g coefficient blocks of an element to one in a streaming pre-pass (and expand the
+                                            // adjoint's per-element block afterwards), so the tile kernels move NS*NS instead of g*NS*NS doubles per element
+  DevBuf<double> presum_buf;                // ne * NS*NS doubles of scratch for it
   bool adj_untileable = false;              // a CSR row has more than 255 entries: adjoint uses the direct gather kernel
   int num_sms = 0;
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
@@ -301,19 +304,33 @@ template <class K> int tile_grid(adfem_mesh* m, K kern, int threads, size_t smem
 }
 
 DevMesh dev_mesh(const adfem_mesh* m, int heron) { DevMesh d = m->dm; d.heron = heron; return d; }
+// the mesh as the tile kernels see it when the coefficients are already summed over the Gauss points (option "coef_presum"): one
+// "Gauss point" per element with reference weight 1 (P1: the position is irrelevant)
+DevMesh dev_mesh_presum(const adfem_mesh* m, int heron) {
+  DevMesh d = dev_mesh(m, heron);
+  d.g = 1; d.rule.n = 1; d.rule.w[0] = 1.0;
+  return d;
+}
+bool use_presum(const adfem_mesh* m, int op) { return m->opt_coef_presum && op == ADFEM_OP_STIFFNESS && m->hm.degree == 1 && m->hm.g > 1; }
+int ensure_presum_buf(adfem_mesh* m) {
+  const size_t n = (size_t)m->hm.ne * (m->hm.dim == 2 ? 9 : 36);
+  if (m->presum_buf.n >= n) return 0;
+  CU_TRY(m->presum_buf.alloc(n));
+  return 0;
+}
 
 template <class K>
-int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int threads, const double* coef, double* vals, cudaStream_t st) {
+int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int threads, const double* coef, double* vals, cudaStream_t st, bool presum = false) {
   int grid = 0;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (int rc = tile_grid(m, kern, threads, smem, P->dev.ntiles, &grid)) return rc;
-  kern<<<grid, threads, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
+  kern<<<grid, threads, smem, st>>>(presum ? dev_mesh_presum(m, m->opt_area_csr) : dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, coef, vals);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
 template <int DIM, int DEG, int OP>
-int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st) {
+int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st, bool presum = false) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
   const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
   const int threads = tile_threads_of(m, NC);
@@ -327,12 +344,12 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
     if (coef_staged(m->hm) && m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st);
   }
   if constexpr (OP == OP_STIFFNESS && DIM == 2 && DEG == 1) {
-    if (m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st);
+    if (m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st, presum);
   }
-  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, false>, P, smem, threads, coef, vals, st);
+  return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, false>, P, smem, threads, coef, vals, st, presum);
 }
 template <int DIM, int DEG, int OP>
-int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
+int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st, bool presum = false) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
   AdjPlanDev* P = nullptr;
   if (m->opt_adjoint_tiled) { if (int rc = ensure_adj_plan(m, NC, &P)) return rc; }
@@ -342,9 +359,9 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
     int grid = 0;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int rc = tile_grid(m, kern, tile_threads_of(m, NC), smem, P->dev.ntiles, &grid)) return rc;
-    kern<<<grid, tile_threads_of(m, NC), smem, st>>>(dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
+    kern<<<grid, tile_threads_of(m, NC), smem, st>>>(presum ? dev_mesh_presum(m, m->opt_area_csr) : dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
   } else {
-    k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
+    k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(presum ? dev_mesh_presum(m, m->opt_area_csr) : dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
   CU_TRY(cudaGetLastError());
   return 0;
@@ -528,6 +545,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
   else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;
+  else if (k == "coef_presum") m->opt_coef_presum = value != 0;
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
@@ -611,11 +629,17 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   FwdPlanDev* P = nullptr;
   if (int rc = ensure_fwd_plan(m, nc, &P)) return rc;
+  const bool presum = use_presum(m, op);
+  if (presum) {
+    if (int rc = ensure_presum_buf(m)) return rc;
+    if (int rc = launch_presum_coef(dev_mesh(m, m->opt_area_csr), coef_per_gauss(m, op), coef, m->presum_buf.p, st)) return rc;
+    coef = m->presum_buf.p;
+  }
 #define CALL_FWD(DIM, DEG)                                                                                   \
   switch (op) {                                                                                              \
     case ADFEM_OP_LAPLACE: return launch_tile_fwd<DIM, DEG, OP_LAPLACE>(m, P, coef, vals, st);               \
     case ADFEM_OP_MASS: return launch_tile_fwd<DIM, DEG, OP_MASS>(m, P, coef, vals, st);                     \
-    default: return launch_tile_fwd<DIM, DEG, OP_STIFFNESS>(m, P, coef, vals, st);                           \
+    default: return launch_tile_fwd<DIM, DEG, OP_STIFFNESS>(m, P, coef, vals, st, presum);                   \
   }
   DISPATCH_ELEM(m, CALL_FWD);
 #undef CALL_FWD
@@ -629,6 +653,16 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
   cudaStream_t st = (cudaStream_t)stream;
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
+  if (use_presum(m, op)) {
+    // one gradient block per element from the tile kernel, expanded to the g Gauss points by a streaming pass
+    if (int rc = ensure_presum_buf(m)) return rc;
+    int rc = 0;
+#define CALL_ADJP(DIM, DEG) rc = launch_adj<DIM, DEG, OP_STIFFNESS>(m, dvals, m->presum_buf.p, st, true)
+    DISPATCH_ELEM(m, CALL_ADJP);
+#undef CALL_ADJP
+    if (rc) return rc;
+    return launch_expand_grad(dev_mesh(m, m->opt_area_csr), coef_per_gauss(m, op), m->presum_buf.p, grad_coef, st);
+  }
 #define CALL_ADJ(DIM, DEG)                                                                                   \
   switch (op) {                                                                                              \
     case ADFEM_OP_LAPLACE: return launch_adj<DIM, DEG, OP_LAPLACE>(m, dvals, grad_coef, st);                 \

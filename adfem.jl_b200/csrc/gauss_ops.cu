@@ -56,6 +56,15 @@ __global__ void k_plane_matrix_grad(int mode, long long n, const double* __restr
   if (i < n) plane_matrix_grad_body(mode, E[i], nu[i], gH + 9 * i, gE + i, gnu + i);
 }
 
+__global__ void k_presum_coef(DevMesh m, int ns2, long long n, const double* __restrict__ coef, double* __restrict__ hbar) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) hbar[i] = presum_coef_body(m.rule, m.g, ns2, i, coef);
+}
+__global__ void k_expand_grad(DevMesh m, int ns2, long long n, const double* __restrict__ gbar, double* __restrict__ grad) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) grad[i] = expand_grad_body(m.rule, m.g, ns2, i, gbar);
+}
+
 int launched(const char* what) {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail(std::string(what) + ": " + cudaGetErrorString(e));
@@ -136,6 +145,19 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
   if (n <= 0) return 0;
   k_plane_matrix_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mode, n, E, nu, grad_H, grad_E, grad_nu);
   return launched("plane matrix gradient kernel");
+}
+
+int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st) {
+  const long long n = (long long)dm.ne * ns2;
+  if (n <= 0) return 0;
+  k_presum_coef<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, ns2, n, coef, hbar);
+  return launched("coefficient pre-sum kernel");
+}
+int launch_expand_grad(const DevMesh& dm, int ns2, const double* gbar, double* grad, cudaStream_t st) {
+  const long long n = (long long)dm.ne * dm.g * ns2;
+  if (n <= 0) return 0;
+  k_expand_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, ns2, n, gbar, grad);
+  return launched("gradient expansion kernel");
 }
 
 }  // namespace adfem

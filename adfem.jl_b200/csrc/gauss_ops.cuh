@@ -191,6 +191,27 @@ ADFEM_HD void laplace_term_grad_nu_body(const DevMesh& m, int e, const double* u
   }
 }
 
+// ---- Gauss-summed coefficients for P1 elasticity (option "coef_presum") ------------------------------------------------------
+// For P1 elements B is constant per element, so the stiffness block only needs Hbar_e = sum_k w_k H_k (reference weights w_k of the
+// quadrature rule; the geometric scale is applied by the tile kernel).  A streaming pre-pass reduces the g blocks of an element to one,
+// so that the row-tile kernel — which re-evaluates halo elements — gathers NS*NS instead of g*NS*NS doubles per element evaluation.
+// The adjoint runs the other way: one block per element from the tile kernel, expanded to the g Gauss points here.
+// idx = e*ns2 + c (flat over the reduced array)
+ADFEM_HD double presum_coef_body(const QuadRule& rule, int g, int ns2, long long idx, const double* coef) {
+  const long long e = idx / ns2;
+  const int c = (int)(idx - e * ns2);
+  const double* p = coef + (e * g) * ns2 + c;
+  double s = 0.0;
+  for (int k = 0; k < g; k++) s += ldg(p + (size_t)k * ns2) * rule.w[k];
+  return s;
+}
+// idx = (e*g + k)*ns2 + c (flat over the per-Gauss-point gradient)
+ADFEM_HD double expand_grad_body(const QuadRule& rule, int g, int ns2, long long idx, const double* gbar) {
+  const long long t = idx / ns2;                 // e*g + k
+  const int c = (int)(idx - t * ns2), k = (int)(t % g);
+  return ldg(gbar + (t / g) * ns2 + c) * rule.w[k];
+}
+
 // ---- constitutive pre-step (SURVEY §8 f, rank 3): per-point 3x3 tangent from (E, nu) -----------------------------------------
 // deps/MFEM/PlaneStrainAndStress/PlaneStrainAndStress.h:5-19 (mode 0, `PlaneStrainMatrix`: s on the diagonal, s nu/(1-nu) in
 // ALL six off-diagonal entries) and :46-60 (mode 1, `PlaneStressMatrix`: E/((1+nu)(1-2nu)) [[1-nu,nu,0],[nu,1-nu,0],[0,0,(1-2nu)/2]]).

@@ -26,4 +26,8 @@ int launch_plane_matrix(int mode, long long n, const double* E, const double* nu
 int launch_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
                              cudaStream_t st);
 
+// option "coef_presum" (P1 elasticity): hbar[ne*ns2] = sum_k w_k coef[(e*g+k)*ns2 + c]; grad[(e*g+k)*ns2 + c] = w_k gbar[e*ns2 + c]
+int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st);
+int launch_expand_grad(const DevMesh& dm, int ns2, const double* gbar, double* grad, cudaStream_t st);
+
 }  // namespace adfem

@@ -3,7 +3,7 @@
 finishes in about a minute.  These are NOT bench.py lines (bench.py measures config 2); they record where the general tile
 kernels stand on the other operator / element families.  One JSON line per case on stdout.
 
-  python scripts/bench_configs.py [--steps 20] [--cases 3,4l,4m,5,src]
+  python scripts/bench_configs.py [--steps 20] [--cases 3,4l,4m,5,src,gp] [--opt coef_presum=1]
 """
 import argparse
 import ctypes as C
@@ -81,7 +81,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every mesh edge count by this factor (smoke runs)")
     ap.add_argument("--smem-budget", type=int, default=0)
     ap.add_argument("--tile-threads", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="adfem_set_option on every mesh, e.g. --opt coef_presum=1")
     args = ap.parse_args()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        OPTS[k] = int(v)
     cases = args.cases.split(",")
     if args.smem_budget:
         OPTS["smem_budget"] = args.smem_budget
@@ -124,6 +128,38 @@ def main():
         b = 12 + 8 * 2 * m.nnode / m.nelem + 24 + 8 * m.ndof / m.nelem
         print(json.dumps({"case": "config2_source_term_P1_tri", "elements": m.nelem, "fwd_ms": tf, "adj_ms": ta, "alg_bytes_per_elem_per_direction": b,
                           "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9}), flush=True)
+    if "gp" in cases:
+        # Gauss-point operators on the config-4-like unstructured P2 mesh and on Mesh(2048,2048) P1 (general kernels)
+        L = _lib.lib()
+        L.adfem_gauss_op_len.restype = C.c_longlong
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n = int(1000 * s)
+        c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)
+        for tag, m in (("P2_unstructured", A.Mesh(c, e, degree=2)), ("P1_grid", A.Mesh(int(2048 * s), int(2048 * s), 1.0 / int(2048 * s)))):
+            for kind, name in enumerate(("fem_to_gauss", "dof_to_gauss", "grad", "strain", "strain_energy")):
+                nin, nout = L.adfem_gauss_op_len(m.handle, kind, 0), L.adfem_gauss_op_len(m.handle, kind, 1)
+                x = torch.rand(nin, dtype=torch.float64, device="cuda")
+                y = torch.empty(nout, dtype=torch.float64, device="cuda")
+                w = torch.rand(nout, dtype=torch.float64, device="cuda")
+                gx = torch.empty(nin, dtype=torch.float64, device="cuda")
+                fwd = lambda: _lib.check(L.adfem_gauss_op(m.handle, kind, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), st))
+                adj = lambda: _lib.check(L.adfem_gauss_op_adjoint(m.handle, kind, C.c_void_p(w.data_ptr()), C.c_void_p(gx.data_ptr()), st))
+                tf, ta = timed(fwd, args.steps), timed(adj, args.steps)
+                b = 4 * m.elem_ndof + 8 * m.dim * m.nnode / m.nelem + 8 * (nin + nout) / m.nelem      # connectivity + coordinates + vectors
+                print(json.dumps({"case": "gauss_op_%s_%s" % (name, tag), "elements": m.nelem, "fwd_ms": tf, "adj_ms": ta, "alg_bytes_per_elem_per_direction": b,
+                                  "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9}), flush=True)
+            nu = torch.rand(m.ngauss, dtype=torch.float64, device="cuda") + 0.5
+            u = torch.rand(m.ndof, dtype=torch.float64, device="cuda")
+            go = torch.rand(m.ndof, dtype=torch.float64, device="cuda")
+            out, gu, gnu = torch.empty_like(u), torch.empty_like(u), torch.empty_like(nu)
+            p = lambda t: C.c_void_p(t.data_ptr())
+            fwd = lambda: _lib.check(L.adfem_laplace_term(m.handle, p(nu), p(u), p(out), st))
+            adj = lambda: _lib.check(L.adfem_laplace_term_adjoint(m.handle, p(nu), p(u), p(go), p(gnu), p(gu), st))
+            tf, ta = timed(fwd, args.steps), timed(adj, args.steps)
+            b = 4 * m.elem_ndof + 8 * m.dim * m.nnode / m.nelem + 8 * m.gauss_per_elem + 16 * m.ndof / m.nelem
+            print(json.dumps({"case": "laplace_term_%s" % tag, "elements": m.nelem, "fwd_ms": tf, "adj_ms": ta, "alg_bytes_per_elem_fwd": b,
+                              "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9}), flush=True)
+            del m
 
 
 if __name__ == "__main__":

@@ -108,6 +108,20 @@ int emul_laplace_term_grad_nu(int dim, int degree, int order, int nv, int ne, in
   return 0;
 }
 
+// option "coef_presum": k_presum_coef / k_expand_grad of gauss_ops.cu
+int emul_presum_coef(int dim, int order, long long ne, int ns2, const double* coef, double* hbar) {
+  QuadRule r;
+  if (!(dim == 2 ? triangle_rule(order, r) : tetrahedron_rule(order, r))) return 1;
+  for (long long i = 0; i < ne * ns2; i++) hbar[i] = presum_coef_body(r, r.n, ns2, i, coef);
+  return 0;
+}
+int emul_expand_grad(int dim, int order, long long ne, int ns2, const double* gbar, double* grad) {
+  QuadRule r;
+  if (!(dim == 2 ? triangle_rule(order, r) : tetrahedron_rule(order, r))) return 1;
+  for (long long i = 0; i < ne * r.n * ns2; i++) grad[i] = expand_grad_body(r, r.n, ns2, i, gbar);
+  return 0;
+}
+
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {
   for (long long i = 0; i < n; i++) plane_matrix_body(mode, E[i], nu[i], H + 9 * i);
 }

@@ -197,3 +197,35 @@ def test_plane_matrix(emul, oracle):
     ref1 = E0 / (1 + n0) / (1 - 2 * n0) * np.array([[1 - n0, n0, 0], [n0, 1 - n0, 0], [0, 0, (1 - 2 * n0) / 2]])
     assert np.allclose(oracle.plane_matrix_fwd([E0], [n0], 0)[0], ref0, rtol=1e-15)
     assert np.allclose(oracle.plane_matrix_fwd([E0], [n0], 1)[0], ref1, rtol=1e-15)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_coef_presum_bodies(emul, oracle, dim):
+    """Option "coef_presum": for P1 elements the stiffness blocks of (sum_k w_k H_k at ONE point of weight 1) equal those of the g-point
+    rule, and the per-Gauss-point gradient is w_k times the one-point gradient — checked with the oracle's own stiffness ops."""
+    rng = np.random.default_rng(dim)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(6, 5, 0.1, seed=1)
+        o, o1 = oracle.Mesh2D(c, e), oracle.Mesh2D(c, e, order=1)
+        ns2, wsum = 9, 0.5
+    else:
+        c, e = meshgen.tet_grid(2, 2, 2, 0.5)
+        o, o1 = oracle.Mesh3D(c, e), oracle.Mesh3D(c, e, order=1)
+        ns2, wsum = 36, 1.0 / 6.0
+    assert o1.g == 1 and o.g > 1
+    H = rng.random(o.ngauss * ns2)
+    hbar = np.full(o.nelem * ns2, np.nan)
+    assert emul.emul_presum_coef(C.c_int(dim), C.c_int(o.order), C.c_longlong(o.nelem), C.c_int(ns2), d(H), d(hbar)) == 0
+    # the tile kernel applies weight 1 to hbar; the oracle's one-point rule has weight wsum, so feed it hbar / wsum
+    _, vv = o.stiffness_fwd(H)
+    _, vv1 = o1.stiffness_fwd(hbar / wsum)
+    D2 = (dim * o.elem_ndof) ** 2
+    close(vv.reshape(o.nelem, o.g, D2).sum(1), vv1.reshape(o.nelem, D2), rel=1e-11)
+    # adjoint: per-element gradient (one-point rule, weight 1 => oracle gradient / wsum) expanded with w_k
+    gvv_e = rng.standard_normal((o.nelem, D2))
+    gbar = o1.stiffness_bwd(gvv_e.reshape(-1)) / wsum
+    grad = np.full(o.ngauss * ns2, np.nan)
+    assert emul.emul_expand_grad(C.c_int(dim), C.c_int(o.order), C.c_longlong(o.nelem), C.c_int(ns2), d(np.ascontiguousarray(gbar)), d(grad)) == 0
+    ref = o.stiffness_bwd(np.repeat(gvv_e[:, None, :], o.g, axis=1).reshape(-1))       # every Gauss-point block of an element gets the same upstream
+    close(grad, ref, rel=1e-11)
