@@ -1,0 +1,21 @@
+# First GPU call of round 2: validates everything that was written in the GPU-less tail of round 1 and takes the A/B numbers those changes
+# were written for.  Usage: gpurun --timeout 2400 -- 'bash scripts/gpu_round2_first.sh r2a'.  Everything lands in gpurun_out/.
+TAG=${1:-r2a}
+mkdir -p gpurun_out
+(time python -c "import __graft_entry__ as g; g.smoke()") > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
+# core parity first (rows a-e), then the widening rows; --timeout per test, no -x so that one failing new test does not hide the others
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_$TAG.log 2>&1
+echo "pytest rc=$?"; tail -15 gpurun_out/pytest_$TAG.log
+timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+echo "bench rc=$?"; python scripts/bench_line.py $TAG < gpurun_out/bench_$TAG.json
+# configs 3 / 5 with and without the Gauss-summed coefficients (option coef_presum), then the Gauss-point operators
+for P in 0 1; do
+  timeout 600 python scripts/bench_configs.py --cases 3,5 --steps 10 --opt coef_presum=$P > gpurun_out/cfg35_presum${P}_$TAG.jsonl 2> gpurun_out/cfg35_presum${P}_$TAG.err
+  echo "configs 3,5 coef_presum=$P rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg35_presum${P}_$TAG.jsonl
+done
+timeout 600 python scripts/bench_configs.py --cases gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
+echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
+# one full capture of the new kernels (scatter / Laplace term are the ones expected to need work)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gp_scatter|k_laplace_term|k_presum|k_expand" -c 8 -f -o gpurun_out/prof_gp_$TAG \
+  python scripts/bench_configs.py --cases gp --steps 1 --scale 0.5 > gpurun_out/prof_gp_$TAG.log 2>&1
+echo "ncu (gauss-point kernels) rc=$?"
