@@ -14,6 +14,7 @@
 
 #include "../../include/adfem_cuda.h"
 #include "internal.h"
+#include "quad_ops.cuh"
 
 using namespace adfem;
 
@@ -237,6 +238,25 @@ int reduce_cells(const double* grad_vv, long long ncell, int mode, double h, dou
   return 0;
 }
 
+// ---- FemLaplace / FemMass / FemSource (quad_ops.cuh): one thread per (cell, Gauss point), one per node for the source gather ------
+__global__ void k_quad_scalar_fwd(int op, const double* __restrict__ coef, int m, long long total, double h, long long* __restrict__ ii,
+                                  long long* __restrict__ jj, double* __restrict__ vv) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < total) quad_scalar_fwd_body(op, t, coef, m, h, ii, jj, vv);
+}
+__global__ void k_quad_scalar_bwd(int op, const double* __restrict__ grad_vv, long long total, double h, double* __restrict__ grad_coef) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < total) grad_coef[t] = quad_scalar_bwd_body(op, t, grad_vv, h);
+}
+__global__ void k_quad_source_fwd(const double* __restrict__ f, int m, int n, double h, double* __restrict__ rhs) {
+  const long long node = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (node < (long long)(m + 1) * (n + 1)) rhs[node] = quad_source_node(node, f, m, n, h);
+}
+__global__ void k_quad_source_bwd(const double* __restrict__ grad_rhs, int m, long long total, double h, double* __restrict__ grad_f) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < total) grad_f[t] = quad_source_bwd_body(t, grad_rhs, m, h);
+}
+
 }  // namespace
 
 extern "C" {
@@ -285,6 +305,34 @@ int adfem_svt_grad(const double* grad_hmat, long long m, long long n, int type, 
   if (type < 1 || type > 3) return fail("SpatialVaryingTangentElastic: type must be 1, 2 or 3");
   if (int rc = check_grid((int)m, (int)n, 1.0)) return rc;
   k_svt_bwd<<<nblk(4 * m * n, 256), 256, 0, (cudaStream_t)stream>>>(grad_hmat, 4 * m * n, type, grad_mu);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_quad_scalar(int op, const double* coef, long long m, long long n, double h, long long* ii, long long* jj, double* vv, void* stream) {
+  if (op != 0 && op != 1) return fail("adfem_quad_scalar: op must be 0 (FemLaplace) or 1 (FemMass)");
+  if (int rc = check_grid((int)m, (int)n, h)) return rc;
+  if ((ii == nullptr) != (jj == nullptr)) return fail("ii and jj must both be given or both be NULL");
+  k_quad_scalar_fwd<<<nblk(4 * m * n, 128), 128, 0, (cudaStream_t)stream>>>(op, coef, (int)m, 4 * m * n, h, ii, jj, vv);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int adfem_quad_scalar_grad(int op, const double* grad_vv, long long m, long long n, double h, double* grad_coef, void* stream) {
+  if (op != 0 && op != 1) return fail("adfem_quad_scalar_grad: op must be 0 (FemLaplace) or 1 (FemMass)");
+  if (int rc = check_grid((int)m, (int)n, h)) return rc;
+  k_quad_scalar_bwd<<<nblk(4 * m * n, 128), 128, 0, (cudaStream_t)stream>>>(op, grad_vv, 4 * m * n, h, grad_coef);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int adfem_quad_source(const double* f, long long m, long long n, double h, double* rhs, void* stream) {
+  if (int rc = check_grid((int)m, (int)n, h)) return rc;
+  k_quad_source_fwd<<<nblk((m + 1) * (n + 1), 128), 128, 0, (cudaStream_t)stream>>>(f, (int)m, (int)n, h, rhs);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int adfem_quad_source_grad(const double* grad_rhs, long long m, long long n, double h, double* grad_f, void* stream) {
+  if (int rc = check_grid((int)m, (int)n, h)) return rc;
+  k_quad_source_bwd<<<nblk(4 * m * n, 128), 128, 0, (cudaStream_t)stream>>>(grad_rhs, (int)m, 4 * m * n, h, grad_f);
   CU_TRY(cudaGetLastError());
   return 0;
 }

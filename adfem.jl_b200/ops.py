@@ -156,13 +156,19 @@ def _assemble(coef, mesh, op, mode):
     raise ValueError("mode must be 'coo' or 'csr'")
 
 
-def compute_fem_laplace_matrix1(kappa, mesh, mode="coo"):
-    """`∫ κ ∇u·∇v` — src/MFEM/MCore.jl:100-120 (2-D), src/MFEM3/MCore.jl (3-D). `kappa` has one value per Gauss point."""
+def compute_fem_laplace_matrix1(kappa, mesh, *grid, mode="coo"):
+    """`∫ κ ∇u·∇v` — src/MFEM/MCore.jl:100-120 (2-D), src/MFEM3/MCore.jl (3-D). `kappa` has one value per Gauss point.
+    `compute_fem_laplace_matrix1(K, m, n, h)` is the structured Q1 sibling (src/InvCore.jl:443-449, op FemLaplace)."""
+    if grid:
+        return _quad_scalar(kappa, 0, mesh, *grid)
     return _assemble(kappa, mesh, OP_LAPLACE, mode)
 
 
-def compute_fem_mass_matrix1(rho, mesh=None, mode="coo"):
-    """`∫ ρ u v` — src/MFEM/MCore.jl:170-181. `compute_fem_mass_matrix1(mesh)` uses ρ ≡ 1 like the reference."""
+def compute_fem_mass_matrix1(rho, mesh=None, *grid, mode="coo"):
+    """`∫ ρ u v` — src/MFEM/MCore.jl:170-181. `compute_fem_mass_matrix1(mesh)` uses ρ ≡ 1 like the reference.
+    `compute_fem_mass_matrix1(rho, m, n, h)` is the structured Q1 sibling (src/InvCore.jl:364-369, op FemMass)."""
+    if grid:
+        return _quad_scalar(rho, 1, mesh, *grid)
     if mesh is None:
         mesh, rho = rho, None
     if rho is None:
@@ -188,8 +194,11 @@ def compute_fem_stiffness_matrix(kappa, mesh, mode="coo"):
     return _assemble(kappa, mesh, OP_STIFFNESS, mode)
 
 
-def compute_fem_source_term1(f, mesh):
-    """`∫ f v` — src/MFEM/MCore.jl:65-82."""
+def compute_fem_source_term1(f, mesh, *grid):
+    """`∫ f v` — src/MFEM/MCore.jl:65-82.  `compute_fem_source_term1(f, m, n, h)` is the structured Q1 sibling
+    (src/InvCore.jl:307-312, op FemSource)."""
+    if grid:
+        return _quad_source(f, mesh, *grid)
     if isinstance(f, np.ndarray):
         f = np.ascontiguousarray(f, dtype=np.float64)
         assert f.size == mesh.ngauss
@@ -379,6 +388,74 @@ class _QuadOp(torch.autograd.Function):
         fn = lib().adfem_quad_stiffness1_grad if kind == 0 else lib().adfem_quad_elasticity_grad
         check(fn(_ptr(grad_vv.contiguous()), C.c_int(flag), C.c_int(m), C.c_int(n), C.c_double(h), _ptr(g), _stream()))
         return g, None, None, None, None
+
+
+class _QuadScalar(torch.autograd.Function):
+    """FemLaplace (op 0) / FemMass (op 1) on an m x n grid: coef [4mn] -> vv [64mn]."""
+
+    @staticmethod
+    def forward(ctx, coef, op, m, n, h):
+        if coef.dtype != torch.float64 or not coef.is_cuda:
+            raise TypeError("coefficients must be a float64 CUDA tensor")
+        coef = coef.contiguous().view(-1)
+        assert coef.numel() == 4 * m * n
+        vv = torch.empty(64 * m * n, dtype=torch.float64, device=coef.device)
+        check(lib().adfem_quad_scalar(C.c_int(op), _ptr(coef), C.c_longlong(m), C.c_longlong(n), C.c_double(h), None, None, _ptr(vv), _stream()))
+        ctx.args = (op, m, n, h)
+        return vv
+
+    @staticmethod
+    def backward(ctx, grad_vv):
+        op, m, n, h = ctx.args
+        g = torch.empty(4 * m * n, dtype=torch.float64, device=grad_vv.device)
+        check(lib().adfem_quad_scalar_grad(C.c_int(op), _ptr(grad_vv.contiguous()), C.c_longlong(m), C.c_longlong(n), C.c_double(h), _ptr(g), _stream()))
+        return g, None, None, None, None
+
+
+class _QuadSource(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, m, n, h):
+        if f.dtype != torch.float64 or not f.is_cuda:
+            raise TypeError("f must be a float64 CUDA tensor")
+        f = f.contiguous().view(-1)
+        assert f.numel() == 4 * m * n
+        rhs = torch.empty((m + 1) * (n + 1), dtype=torch.float64, device=f.device)
+        check(lib().adfem_quad_source(_ptr(f), C.c_longlong(m), C.c_longlong(n), C.c_double(h), _ptr(rhs), _stream()))
+        ctx.args = (m, n, h)
+        return rhs
+
+    @staticmethod
+    def backward(ctx, grad_rhs):
+        m, n, h = ctx.args
+        g = torch.empty(4 * m * n, dtype=torch.float64, device=grad_rhs.device)
+        check(lib().adfem_quad_source_grad(_ptr(grad_rhs.contiguous()), C.c_longlong(m), C.c_longlong(n), C.c_double(h), _ptr(g), _stream()))
+        return g, None, None, None
+
+
+def _quad_scalar_indices(op, m, n, h, device):
+    ii = torch.empty(64 * m * n, dtype=torch.int64, device=device)
+    jj = torch.empty_like(ii)
+    vv = torch.empty(64 * m * n, dtype=torch.float64, device=device)
+    dummy = torch.zeros(4 * m * n, dtype=torch.float64, device=device)
+    check(lib().adfem_quad_scalar(C.c_int(op), _ptr(dummy), C.c_longlong(m), C.c_longlong(n), C.c_double(h), _ptr(ii), _ptr(jj), _ptr(vv), _stream()))
+    return torch.stack([ii, jj], 1)                      # these ops emit 0-based indices already
+
+
+def _quad_scalar(coef, op, m, n, h):
+    m, n, h = int(m), int(n), float(h)
+    N = (m + 1) * (n + 1)
+    as_numpy = isinstance(coef, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(coef, dtype=np.float64).reshape(-1)).cuda() if as_numpy else coef
+    vv = _QuadScalar.apply(t, op, m, n, h)
+    S = SparseTensor(_quad_scalar_indices(op, m, n, h, vv.device), vv, N, N)
+    return S.to_scipy() if as_numpy else S
+
+
+def _quad_source(f, m, n, h):
+    m, n, h = int(m), int(n), float(h)
+    if isinstance(f, np.ndarray):
+        return _QuadSource.apply(torch.from_numpy(np.ascontiguousarray(f, dtype=np.float64).reshape(-1)).cuda(), m, n, h).cpu().numpy()
+    return _QuadSource.apply(f, m, n, h)
 
 
 def _quad_indices(kind, flag, m, n, h, device):

@@ -246,6 +246,18 @@ int adfem_quad_elasticity_grad(const double* grad_vv, int per_gauss, int m, int 
 int adfem_svt(const double* mu, long long m, long long n, int type, double* hmat, void* stream);
 int adfem_svt_grad(const double* grad_hmat, long long m, long long n, int type, double* grad_mu, void* stream);
 
+/* Structured-grid Q1 scalar siblings, device pointers.  Cell (i,j) = id j*m+i, Gauss point k = 2q+p at (pts[p], pts[q]),
+ * coefficients [4mn] indexed 4*cell+k, slot (4*cell+k)*16 + 4a + b; ii/jj are 0-BASED int64 like these ops emit them (the Julia wrappers add
+ * 1, src/InvCore.jl:368,448) and may both be NULL; m, n are int64 as in the ops' signatures.
+ *  adfem_quad_scalar op 0: FemLaplace (deps/FemLaplace/FemLaplace.h:11-49) = compute_fem_laplace_matrix1(K, m, n, h);
+ *                    op 1: FemMass (deps/FemMass/FemMass.h:10-43) = compute_fem_mass_matrix1(rho, m, n, h); 64mn slots.
+ *  adfem_quad_source: FemSource (deps/FemSource/FemSource.h:8-26) = compute_fem_source_term1(f, m, n, h); rhs[(m+1)(n+1)] is OVERWRITTEN.
+ *  The _grad calls overwrite grad_coef / grad_f [4mn] (FemLaplace.h:51-82, FemMass.h:45-79, FemSource.h:30-47). */
+int adfem_quad_scalar(int op, const double* coef, long long m, long long n, double h, long long* ii, long long* jj, double* vv, void* stream);
+int adfem_quad_scalar_grad(int op, const double* grad_vv, long long m, long long n, double h, double* grad_coef, void* stream);
+int adfem_quad_source(const double* f, long long m, long long n, double h, double* rhs, void* stream);
+int adfem_quad_source_grad(const double* grad_rhs, long long m, long long n, double h, double* grad_f, void* stream);
+
 /* Host-buffer convenience calls (synchronous; H2D + kernel + D2H).  Used for end-to-end timing. */
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host);
 int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host);

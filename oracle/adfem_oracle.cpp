@@ -1186,4 +1186,100 @@ void oracle_SVT_backward(double* grad_mu, const double* grad_hmat, long long m, 
   }
 }
 
+// =====================================================================================
+// Structured-grid Q1 scalar siblings; ii / jj 0-based as these ops emit them
+// =====================================================================================
+// the four B0^T B0 h^2/4 matrices, k = 2q + p with xi = pts[p], eta = pts[q] — deps/FemLaplace/FemLaplace.h:13-23
+static void make_laplace_locals(double h, double B[4][4][4]) {
+  for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++) {
+    const int k = q * 2 + p;
+    const double xi = pts[p], eta = pts[q];
+    const double B0[2][4] = {{-1 / h * (1 - eta), 1 / h * (1 - eta), -1 / h * eta, 1 / h * eta},
+                             {-1 / h * (1 - xi), -1 / h * xi, 1 / h * (1 - xi), 1 / h * xi}};
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) B[k][a][b] = (B0[0][a] * B0[0][b] + B0[1][a] * B0[1][b]) * 0.25 * h * h;
+  }
+}
+// the four A A^T h^2/4 matrices — deps/FemMass/FemMass.h:12-20
+static void make_mass_locals(double h, double Me[4][4][4]) {
+  for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++) {
+    const double xi = pts[p], eta = pts[q];
+    const double A[4] = {(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta};
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) Me[q * 2 + p][a][b] = A[a] * A[b] * 0.25 * h * h;
+  }
+}
+// deps/FemLaplace/FemLaplace.h:11-49
+void oracle_FemLaplace_forward(int64* ii, int64* jj, double* vv, const double* K, int m, int n, double h) {
+  double B[4][4][4]; make_laplace_locals(h, B);
+  size_t k_gauss = 0, k = 0;
+  for (int j = 0; j < n; j++) for (int i = 0; i < m; i++) {
+    const int idx[4] = {j * (m + 1) + i, j * (m + 1) + i + 1, (j + 1) * (m + 1) + i, (j + 1) * (m + 1) + i + 1};
+    for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++) {
+      const double kv = K[k_gauss++];
+      for (int i_ = 0; i_ < 4; i_++) for (int j_ = 0; j_ < 4; j_++) { ii[k] = idx[i_]; jj[k] = idx[j_]; vv[k] = kv * B[2 * q + p][i_][j_]; k++; }
+    }
+  }
+}
+// FemLaplace.h:51-82 (accumulates; the op shell zero-fills)
+void oracle_FemLaplace_backward(double* grad_K, const double* grad_vv, int m, int n, double h) {
+  double B[4][4][4]; make_laplace_locals(h, B);
+  size_t k_gauss = 0, k = 0;
+  for (int j = 0; j < n; j++) for (int i = 0; i < m; i++)
+    for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++) {
+      for (int i_ = 0; i_ < 4; i_++) for (int j_ = 0; j_ < 4; j_++) { grad_K[k_gauss] += B[2 * q + p][i_][j_] * grad_vv[k]; k++; }
+      k_gauss++;
+    }
+}
+// deps/FemMass/FemMass.h:10-43
+void oracle_FemMass_forward(int64* ii, int64* jj, double* vv, const double* rho, int m, int n, double h) {
+  double Me[4][4][4]; make_mass_locals(h, Me);
+  size_t k = 0;
+  for (int j = 0; j < n; j++) for (int i = 0; i < m; i++) {
+    const size_t elem_idx = (size_t)j * m + i;
+    const int idx[4] = {j * (m + 1) + i, j * (m + 1) + i + 1, (j + 1) * (m + 1) + i, (j + 1) * (m + 1) + i + 1};
+    for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++) {
+      const double rho_ = rho[elem_idx * 4 + 2 * q + p];
+      for (int i_ = 0; i_ < 4; i_++) for (int j_ = 0; j_ < 4; j_++) { ii[k] = idx[i_]; jj[k] = idx[j_]; vv[k] = rho_ * Me[2 * q + p][i_][j_]; k++; }
+    }
+  }
+}
+// FemMass.h:45-79
+void oracle_FemMass_backward(double* grad_rho, const double* grad_vv, int m, int n, double h) {
+  double Me[4][4][4]; make_mass_locals(h, Me);
+  size_t k = 0;
+  for (int j = 0; j < n; j++) for (int i = 0; i < m; i++) {
+    const size_t elem_idx = (size_t)j * m + i;
+    for (int q = 0; q < 2; q++) for (int p = 0; p < 2; p++)
+      for (int i_ = 0; i_ < 4; i_++) for (int j_ = 0; j_ < 4; j_++) { grad_rho[elem_idx * 4 + 2 * q + p] += grad_vv[k] * Me[2 * q + p][i_][j_]; k++; }
+  }
+}
+// deps/FemSource/FemSource.h:8-26 (cell loop i outer, j inner; accumulates into a zero-filled rhs)
+void oracle_FemSource_forward(double* rhs, const double* f, int m, int n, double h) {
+  for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) {
+    const size_t idx = (size_t)j * m + i;
+    for (int p = 0; p < 2; p++) for (int q = 0; q < 2; q++) {
+      const double xi = pts[p], eta = pts[q];
+      const size_t k = idx * 4 + 2 * q + p;
+      const double val1 = f[k] * h * h * 0.25;
+      rhs[j * (m + 1) + i] += val1 * (1 - xi) * (1 - eta);
+      rhs[j * (m + 1) + i + 1] += val1 * xi * (1 - eta);
+      rhs[(j + 1) * (m + 1) + i] += val1 * (1 - xi) * eta;
+      rhs[(j + 1) * (m + 1) + i + 1] += val1 * xi * eta;
+    }
+  }
+}
+// FemSource.h:30-47
+void oracle_FemSource_backward(double* grad_f, const double* grad_rhs, int m, int n, double h) {
+  for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) {
+    const size_t idx = (size_t)j * m + i;
+    for (int p = 0; p < 2; p++) for (int q = 0; q < 2; q++) {
+      const double xi = pts[p], eta = pts[q];
+      const size_t k = idx * 4 + 2 * q + p;
+      grad_f[k] += h * h * 0.25 * (1 - xi) * (1 - eta) * grad_rhs[j * (m + 1) + i];
+      grad_f[k] += h * h * 0.25 * xi * (1 - eta) * grad_rhs[j * (m + 1) + i + 1];
+      grad_f[k] += h * h * 0.25 * (1 - xi) * eta * grad_rhs[(j + 1) * (m + 1) + i];
+      grad_f[k] += h * h * 0.25 * xi * eta * grad_rhs[(j + 1) * (m + 1) + i + 1];
+    }
+  }
+}
+
 }  // extern "C"

@@ -443,3 +443,42 @@ def csr_adjoint_to_slots(rowptr, colind, dvals, indices, n):
     key = np.asarray(indices[:, 0], dtype=np.int64) * np.int64(n) + indices[:, 1]
     pos = np.searchsorted(key_nnz, key)
     return np.asarray(dvals)[pos]
+
+
+def _quad_scalar(name, coef, m, n, h):
+    """FemLaplace / FemMass (deps/FemLaplace/FemLaplace.h, deps/FemMass/FemMass.h): coef [4mn]; ii / jj 0-based like the ops emit them."""
+    N = 64 * m * n
+    ii, jj, vv = np.zeros(N, dtype=np.int64), np.zeros(N, dtype=np.int64), np.zeros(N)
+    getattr(lib(), name)(_l(ii), _l(jj), _d(vv), _d(_f64(coef)), C.c_int(m), C.c_int(n), C.c_double(h))
+    return ii, jj, vv
+
+
+def _quad_vec(name, x, nout, m, n, h):
+    out = np.zeros(nout)
+    getattr(lib(), name)(_d(out), _d(_f64(x)), C.c_int(m), C.c_int(n), C.c_double(h))
+    return out
+
+
+def quad_laplace_fwd(K, m, n, h):
+    return _quad_scalar("oracle_FemLaplace_forward", K, m, n, h)
+
+
+def quad_laplace_bwd(grad_vv, m, n, h):
+    return _quad_vec("oracle_FemLaplace_backward", grad_vv, 4 * m * n, m, n, h)
+
+
+def quad_mass_fwd(rho, m, n, h):
+    return _quad_scalar("oracle_FemMass_forward", rho, m, n, h)
+
+
+def quad_mass_bwd(grad_vv, m, n, h):
+    return _quad_vec("oracle_FemMass_backward", grad_vv, 4 * m * n, m, n, h)
+
+
+def quad_source_fwd(f, m, n, h):
+    """deps/FemSource/FemSource.h:8-26."""
+    return _quad_vec("oracle_FemSource_forward", f, (m + 1) * (n + 1), m, n, h)
+
+
+def quad_source_bwd(grad_rhs, m, n, h):
+    return _quad_vec("oracle_FemSource_backward", grad_rhs, 4 * m * n, m, n, h)

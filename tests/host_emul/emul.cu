@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "gauss_ops.cuh"
+#include "quad_ops.cuh"
 
 using namespace adfem;
 
@@ -120,6 +121,20 @@ int emul_expand_grad(int dim, int order, long long ne, int ns2, const double* gb
   if (!(dim == 2 ? triangle_rule(order, r) : tetrahedron_rule(order, r))) return 1;
   for (long long i = 0; i < ne * r.n * ns2; i++) grad[i] = expand_grad_body(r, r.n, ns2, i, gbar);
   return 0;
+}
+
+// structured Q1 scalar siblings: k_quad_scalar_fwd / _bwd, k_quad_source_fwd / _bwd of grid_ops.cu
+void emul_quad_scalar(int op, const double* coef, int m, int n, double h, long long* ii, long long* jj, double* vv) {
+  for (long long t = 0; t < 4LL * m * n; t++) quad_scalar_fwd_body(op, t, coef, m, h, ii, jj, vv);
+}
+void emul_quad_scalar_grad(int op, const double* grad_vv, int m, int n, double h, double* grad_coef) {
+  for (long long t = 0; t < 4LL * m * n; t++) grad_coef[t] = quad_scalar_bwd_body(op, t, grad_vv, h);
+}
+void emul_quad_source(const double* f, int m, int n, double h, double* rhs) {
+  for (long long node = 0; node < (long long)(m + 1) * (n + 1); node++) rhs[node] = quad_source_node(node, f, m, n, h);
+}
+void emul_quad_source_grad(const double* grad_rhs, int m, int n, double h, double* grad_f) {
+  for (long long t = 0; t < 4LL * m * n; t++) grad_f[t] = quad_source_bwd_body(t, grad_rhs, m, h);
 }
 
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {

@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -229,3 +229,30 @@ def test_coef_presum_bodies(emul, oracle, dim):
     assert emul.emul_expand_grad(C.c_int(dim), C.c_int(o.order), C.c_longlong(o.nelem), C.c_int(ns2), d(np.ascontiguousarray(gbar)), d(grad)) == 0
     ref = o.stiffness_bwd(np.repeat(gvv_e[:, None, :], o.g, axis=1).reshape(-1))       # every Gauss-point block of an element gets the same upstream
     close(grad, ref, rel=1e-11)
+
+
+def test_quad_scalar_siblings(emul, oracle):
+    """FemLaplace / FemMass / FemSource bodies (csrc/quad_ops.cuh) against the oracle: indices bit-exact (0-based), values within 1e-12."""
+    rng = np.random.default_rng(11)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    l = lambda a: a.ctypes.data_as(C.POINTER(C.c_longlong))
+    for m, n, h in ((5, 3, 0.1), (1, 1, 2.0), (2, 7, 0.37)):
+        coef = rng.random(4 * m * n) + 0.5
+        N = 64 * m * n
+        for op, fwd, bwd in ((0, oracle.quad_laplace_fwd, oracle.quad_laplace_bwd), (1, oracle.quad_mass_fwd, oracle.quad_mass_bwd)):
+            ii, jj, vv = np.full(N, -1, dtype=np.int64), np.full(N, -1, dtype=np.int64), np.full(N, np.nan)
+            emul.emul_quad_scalar(C.c_int(op), d(coef), C.c_int(m), C.c_int(n), C.c_double(h), l(ii), l(jj), d(vv))
+            ri, rj, rv = fwd(coef, m, n, h)
+            assert np.array_equal(ii, ri) and np.array_equal(jj, rj)
+            close(vv, rv)
+            g = rng.standard_normal(N)
+            out = np.full(4 * m * n, np.nan)
+            emul.emul_quad_scalar_grad(C.c_int(op), d(g), C.c_int(m), C.c_int(n), C.c_double(h), d(out))
+            close(out, bwd(g, m, n, h))
+        rhs = np.full((m + 1) * (n + 1), np.nan)
+        emul.emul_quad_source(d(coef), C.c_int(m), C.c_int(n), C.c_double(h), d(rhs))
+        close(rhs, oracle.quad_source_fwd(coef, m, n, h))
+        w = rng.standard_normal((m + 1) * (n + 1))
+        gf = np.full(4 * m * n, np.nan)
+        emul.emul_quad_source_grad(d(w), C.c_int(m), C.c_int(n), C.c_double(h), d(gf))
+        close(gf, oracle.quad_source_bwd(w, m, n, h))

@@ -381,3 +381,38 @@ def test_laplace_term_3d_equals_matrix_action(oracle):
         nu, u = rng.random(M.ngauss) + 0.5, rng.random(M.ndof)
         K = csr(oracle, *M.laplace_fwd(nu), M.ndof)
         assert np.abs(M.laplace_term_fwd(nu, u) - K @ u).max() < 1e-11 * np.abs(K @ u).max()
+
+
+def test_quad_scalar_siblings_known_answers(oracle):
+    """Structured Q1 FemLaplace / FemMass / FemSource: invariants and an independent numpy assembly
+    (the reference's own tests compare these kernels with the pure-Julia loops of src/Core.jl, test/invkernel.jl:149-160)."""
+    rng = np.random.default_rng(4)
+    m, n, h = 6, 4, 0.25
+    N = (m + 1) * (n + 1)
+    K, f = rng.random(4 * m * n) + 0.5, rng.standard_normal(4 * m * n)
+    ii, jj, vv = oracle.quad_laplace_fwd(K, m, n, h)
+    L = sp.coo_matrix((vv, (ii, jj)), shape=(N, N)).tocsr()
+    assert np.abs(L @ np.ones(N)).max() < 1e-13                               # constants are in the kernel
+    assert np.abs((L - L.T)).max() < 1e-15
+    ii, jj, vv = oracle.quad_mass_fwd(K, m, n, h)
+    M = sp.coo_matrix((vv, (ii, jj)), shape=(N, N)).tocsr()
+    assert abs(M.sum() - K.sum() * h * h / 4) < 1e-13                         # partition of unity
+    rhs = oracle.quad_source_fwd(f, m, n, h)
+    assert abs(rhs.sum() - f.sum() * h * h / 4) < 1e-13
+    assert np.abs(rhs - sp.coo_matrix((oracle.quad_mass_fwd(f, m, n, h)[2], (ii, jj)), shape=(N, N)).tocsr() @ np.ones(N)).max() < 1e-14   # source(c) == mass(c) 1
+    # independent numpy assembly: x-linear field u = x has energy sum K h^2/4 (|grad u|^2 = 1)
+    x = np.tile(np.arange(m + 1) * h, n + 1)
+    assert abs(x @ (L @ x) - K.sum() * h * h / 4) < 1e-12
+    # with K = 1 the matrix is the classic Q1 stencil: centre 8/3, every neighbour -1/3
+    ii, jj, vv = oracle.quad_laplace_fwd(np.ones(4 * m * n), m, n, h)
+    L1 = sp.coo_matrix((vv, (ii, jj)), shape=(N, N)).toarray()
+    c = 2 * (m + 1) + 3                                                      # an interior node
+    assert abs(L1[c, c] - 8 / 3) < 1e-13
+    for dn in (-1, 1, -(m + 1), m + 1, -(m + 2), -m, m, m + 2):
+        assert abs(L1[c, c + dn] + 1 / 3) < 1e-13
+    # adjoints are transposes
+    g = rng.standard_normal(64 * m * n)
+    assert abs(oracle.quad_laplace_bwd(g, m, n, h) @ K - g @ oracle.quad_laplace_fwd(K, m, n, h)[2]) < 1e-12
+    assert abs(oracle.quad_mass_bwd(g, m, n, h) @ K - g @ oracle.quad_mass_fwd(K, m, n, h)[2]) < 1e-12
+    w = rng.standard_normal(N)
+    assert abs(oracle.quad_source_bwd(w, m, n, h) @ f - w @ rhs) < 1e-12

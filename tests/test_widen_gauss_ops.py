@@ -223,3 +223,33 @@ def test_coef_presum_option(oracle, dim):
         close(npy(T.values), ref)
         (g,) = torch.autograd.grad(T.values, k, dev(dv))
         close(npy(g).reshape(-1), expect)
+
+
+def test_quad_scalar_siblings(oracle):
+    """Structured Q1 FemLaplace / FemMass / FemSource through the reference-style signatures (coef, m, n, h)."""
+    rng = np.random.default_rng(31)
+    for m, n, h in ((13, 9, 0.1), (1, 1, 2.0), (64, 33, 1 / 64)):
+        coef = rng.random(4 * m * n) + 0.5
+        for fn, fwd, bwd in ((A.compute_fem_laplace_matrix1, oracle.quad_laplace_fwd, oracle.quad_laplace_bwd),
+                             (A.compute_fem_mass_matrix1, oracle.quad_mass_fwd, oracle.quad_mass_bwd)):
+            ri, rj, rv = fwd(coef, m, n, h)
+            k = dev(coef).requires_grad_(True)
+            S = fn(k, m, n, h)
+            idx = npy(S.indices)
+            assert np.array_equal(idx[:, 0], ri) and np.array_equal(idx[:, 1], rj)        # 0-based, bit-exact
+            close(npy(S.values), rv)
+            g = rng.standard_normal(len(rv))
+            (gk,) = torch.autograd.grad(S.values, k, dev(g))
+            close(npy(gk), bwd(g, m, n, h))
+            import scipy.sparse as sp
+            N = (m + 1) * (n + 1)
+            ref = sp.coo_matrix((rv, (ri, rj)), shape=(N, N)).tocsr()
+            assert abs(fn(coef, m, n, h) - ref).max() <= 1e-12 * abs(ref).max()             # numpy in -> scipy out
+        f = rng.standard_normal(4 * m * n)
+        ft = dev(f).requires_grad_(True)
+        rhs = A.compute_fem_source_term1(ft, m, n, h)
+        close(npy(rhs), oracle.quad_source_fwd(f, m, n, h))
+        w = rng.standard_normal((m + 1) * (n + 1))
+        (gf,) = torch.autograd.grad(rhs, ft, dev(w))
+        close(npy(gf), oracle.quad_source_bwd(w, m, n, h))
+        close(A.compute_fem_source_term1(f, m, n, h), oracle.quad_source_fwd(f, m, n, h))
