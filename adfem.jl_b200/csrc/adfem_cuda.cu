@@ -855,6 +855,29 @@ int adfem_plane_matrix_grad(int mode, long long n, const double* E, const double
   return launch_plane_matrix_grad(mode, n, E, nu, grad_H, grad_E, grad_nu, (cudaStream_t)stream);
 }
 
+// Fused constitutive pre-step + elasticity assembly for P1 triangles: the per-Gauss-point tangent H(E, nu) is never
+// written to memory — a streaming pass forms sum_k w_k H_k per element straight from the moduli and the row-tile kernel takes it from there.
+int adfem_assemble_csr_plane(adfem_mesh* m, int mode, const double* E, const double* nu, double* vals, void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (m->hm.dim != 2 || m->hm.degree != 1) return fail("adfem_assemble_csr_plane: P1 triangles only (use adfem_plane_matrix + adfem_assemble_csr otherwise)");
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdPlanDev* P = nullptr;
+  if (int rc = ensure_fwd_plan(m, 2, &P)) return rc;
+  if (int rc = ensure_presum_buf(m)) return rc;
+  if (int rc = launch_presum_plane(dev_mesh(m, m->opt_area_csr), mode, E, nu, m->presum_buf.p, st)) return rc;
+  return launch_tile_fwd<2, 1, OP_STIFFNESS>(m, P, m->presum_buf.p, vals, st, true);
+}
+int adfem_assemble_csr_plane_adjoint(adfem_mesh* m, int mode, const double* E, const double* nu, const double* dvals, double* grad_E, double* grad_nu,
+                                     void* stream) {
+  if (int rc = need_device(m)) return rc;
+  if (m->hm.dim != 2 || m->hm.degree != 1) return fail("adfem_assemble_csr_plane_adjoint: P1 triangles only");
+  if (int rc = ensure_pattern(m)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = ensure_presum_buf(m)) return rc;
+  if (int rc = launch_adj<2, 1, OP_STIFFNESS>(m, dvals, m->presum_buf.p, st, true)) return rc;
+  return launch_expand_plane_grad(dev_mesh(m, m->opt_area_csr), mode, E, nu, m->presum_buf.p, grad_E, grad_nu, st);
+}
+
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host) {
   if (int rc = need_device(m)) return rc;
   if (int rc = check_op(m, op)) return rc;

@@ -65,6 +65,16 @@ __global__ void k_expand_grad(DevMesh m, int ns2, long long n, const double* __r
   if (i < n) grad[i] = expand_grad_body(m.rule, m.g, ns2, i, gbar);
 }
 
+__global__ void k_presum_plane(DevMesh m, int mode, long long n, const double* __restrict__ E, const double* __restrict__ nu, double* __restrict__ hbar) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) hbar[i] = presum_plane_body(m.rule, m.g, mode, i, E, nu);
+}
+__global__ void k_expand_plane_grad(DevMesh m, int mode, long long n, const double* __restrict__ E, const double* __restrict__ nu,
+                                    const double* __restrict__ gbar, double* __restrict__ gE, double* __restrict__ gnu) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) expand_plane_grad_body(m.rule, m.g, mode, t, E, nu, gbar, gE, gnu);
+}
+
 int launched(const char* what) {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail(std::string(what) + ": " + cudaGetErrorString(e));
@@ -158,6 +168,22 @@ int launch_expand_grad(const DevMesh& dm, int ns2, const double* gbar, double* g
   if (n <= 0) return 0;
   k_expand_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, ns2, n, gbar, grad);
   return launched("gradient expansion kernel");
+}
+
+int launch_presum_plane(const DevMesh& dm, int mode, const double* E, const double* nu, double* hbar, cudaStream_t st) {
+  if (mode != 0 && mode != 1) return fail("plane matrix: mode must be 0 (PlaneStrainMatrix) or 1 (PlaneStressMatrix)");
+  const long long n = (long long)dm.ne * 9;
+  if (n <= 0) return 0;
+  k_presum_plane<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, mode, n, E, nu, hbar);
+  return launched("fused plane-matrix pre-sum kernel");
+}
+int launch_expand_plane_grad(const DevMesh& dm, int mode, const double* E, const double* nu, const double* gbar, double* grad_E, double* grad_nu,
+                             cudaStream_t st) {
+  if (mode != 0 && mode != 1) return fail("plane matrix: mode must be 0 (PlaneStrainMatrix) or 1 (PlaneStressMatrix)");
+  const long long n = (long long)dm.ne * dm.g;
+  if (n <= 0) return 0;
+  k_expand_plane_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, mode, n, E, nu, gbar, grad_E, grad_nu);
+  return launched("fused plane-matrix gradient kernel");
 }
 
 }  // namespace adfem

@@ -242,4 +242,32 @@ ADFEM_HD void plane_matrix_grad_body(int mode, double E, double nu, const double
   }
 }
 
+// ---- constitutive pre-step FUSED with the Gauss sum (SURVEY §8 f rank 3: H is never materialised) ----------------------------
+// P1 triangles: hbar[e*9 + c] = sum_k w_k H(E[e*g+k], nu[e*g+k])[c] straight from the moduli (16 B per Gauss point in instead of 72),
+// and on the way back (dE, dnu)[e*g+k] = dH/d(E,nu)^T (w_k gbar[e]).  idx = e*9 + c.
+ADFEM_HD double presum_plane_body(const QuadRule& rule, int g, int mode, long long idx, const double* E, const double* nu) {
+  const long long e = idx / 9;
+  const int c = (int)(idx - e * 9);
+  double s = 0.0;
+  for (int k = 0; k < g; k++) {
+    double H[9];
+    plane_matrix_body(mode, ldg(E + e * g + k), ldg(nu + e * g + k), H);
+    double hc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) hc = (i == c) ? H[i] : hc;
+    s += hc * rule.w[k];
+  }
+  return s;
+}
+// t = e*g + k
+ADFEM_HD void expand_plane_grad_body(const QuadRule& rule, int g, int mode, long long t, const double* E, const double* nu, const double* gbar,
+                                     double* grad_E, double* grad_nu) {
+  const long long e = t / g;
+  const double w = rule.w[(int)(t - e * g)];
+  double gk[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) gk[i] = ldg(gbar + e * 9 + i) * w;
+  plane_matrix_grad_body(mode, ldg(E + t), ldg(nu + t), gk, grad_E + t, grad_nu + t);
+}
+
 }  // namespace adfem

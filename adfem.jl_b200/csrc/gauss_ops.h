@@ -29,5 +29,9 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
 // option "coef_presum" (P1 elasticity): hbar[ne*ns2] = sum_k w_k coef[(e*g+k)*ns2 + c]; grad[(e*g+k)*ns2 + c] = w_k gbar[e*ns2 + c]
 int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st);
 int launch_expand_grad(const DevMesh& dm, int ns2, const double* gbar, double* grad, cudaStream_t st);
+// fused constitutive pre-step (P1 triangles): hbar[ne*9] from E[G], nu[G]; (grad_E, grad_nu)[G] from gbar[ne*9]
+int launch_presum_plane(const DevMesh& dm, int mode, const double* E, const double* nu, double* hbar, cudaStream_t st);
+int launch_expand_plane_grad(const DevMesh& dm, int mode, const double* E, const double* nu, const double* gbar, double* grad_E, double* grad_nu,
+                             cudaStream_t st);
 
 }  // namespace adfem

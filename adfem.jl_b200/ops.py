@@ -351,6 +351,43 @@ def _plane(E, nu, mode):
     return _PlaneMatrix.apply(t(E), t(nu), mode)
 
 
+class _AssemblePlane(torch.autograd.Function):
+    """CSR elasticity values straight from the moduli (adfem_assemble_csr_plane): H(E, nu) is never materialised."""
+
+    @staticmethod
+    def forward(ctx, E, nu, mesh, mode):
+        if E.dtype != torch.float64 or nu.dtype != torch.float64 or not E.is_cuda or not nu.is_cuda:
+            raise TypeError("E and nu must be float64 CUDA tensors")
+        E, nu = E.contiguous().view(-1), nu.contiguous().view(-1)
+        assert E.numel() == mesh.ngauss and nu.numel() == mesh.ngauss
+        nnz = lib().adfem_csr_nnz(mesh.handle, C.c_int(mesh.dim))
+        if nnz < 0:
+            raise _lib.AdfemError(_lib.last_error())
+        vals = torch.empty(nnz, dtype=torch.float64, device=E.device)
+        check(lib().adfem_assemble_csr_plane(mesh.handle, C.c_int(mode), _ptr(E), _ptr(nu), _ptr(vals), _stream()))
+        ctx.mesh, ctx.mode = mesh, mode
+        ctx.save_for_backward(E, nu)
+        return vals
+
+    @staticmethod
+    def backward(ctx, dvals):
+        E, nu = ctx.saved_tensors
+        gE, gnu = torch.empty_like(E), torch.empty_like(nu)
+        check(lib().adfem_assemble_csr_plane_adjoint(ctx.mesh.handle, C.c_int(ctx.mode), _ptr(E), _ptr(nu), _ptr(dvals.contiguous()), _ptr(gE),
+                                                     _ptr(gnu), _stream()))
+        return gE, gnu, None, None
+
+
+def compute_fem_stiffness_matrix_from_moduli(E, nu, mesh, plane="stress"):
+    """`compute_fem_stiffness_matrix(compute_plane_stress_matrix(E, nu), mesh)` (or `..._strain_...`) in one fused device pass for P1
+    triangle meshes: E, nu are CUDA tensors with one value per Gauss point; returns a `CSRTensor` whose values are
+    differentiable with respect to both."""
+    mode = {"strain": 0, "stress": 1}[plane]
+    vals = _AssemblePlane.apply(E, nu, mesh, mode)
+    rowptr, colind = mesh.csr_pattern(mesh.dim)
+    return CSRTensor(rowptr, colind, vals, mesh.dim * mesh.ndof)
+
+
 def compute_plane_strain_matrix(E, nu):
     """Pointwise N x 3 x 3 tangent, the reference's `PlaneStrainMatrix` (op PlaneStrainAndStress, mode 0) — src/Core.jl:777-786."""
     return _plane(E, nu, 0)

@@ -214,6 +214,13 @@ int adfem_plane_matrix(int mode, long long n, const double* E, const double* nu,
 int adfem_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
                             void* stream);
 
+/* Fused pre-step + assembly (P1 triangles): CSR values of the elasticity operator with H = plane matrix(E, nu) per Gauss point, and the
+ * gradient with respect to E and nu, WITHOUT materialising H (16 B instead of 72 B of coefficients per Gauss point).  Same values as
+ * adfem_plane_matrix followed by adfem_assemble_csr(ADFEM_OP_STIFFNESS); E[G], nu[G], vals / dvals [4*nnz]. */
+int adfem_assemble_csr_plane(adfem_mesh* m, int mode, const double* E, const double* nu, double* vals, void* stream);
+int adfem_assemble_csr_plane_adjoint(adfem_mesh* m, int mode, const double* E, const double* nu, const double* dvals, double* grad_E, double* grad_nu,
+                                     void* stream);
+
 /* Algebraic Dirichlet conditions on a COO matrix — the ImposeDirichlet op (deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-93,
  * op signature ImposeDirichlet.cpp:14-57).  All pointers are DEVICE pointers.  indices: sN x 2 (row, col) 0-based; bd: bdN
  * boundary dofs, 1-BASED like the reference (ImposeDirichlet.h:32); duplicates in bd: the last bdval wins.  Output: the kept

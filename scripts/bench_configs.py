@@ -97,6 +97,27 @@ def main():
         m = A.Mesh(int(4096 * s), int(2048 * s), 1.0 / int(4096 * s))
         run_csr("config3_elasticity_P1_tri", m, 2, 9, args.steps, "Mesh(4096,2048,h) P1, per-Gauss-point 3x3 H, CSR fwd + H-adjoint (general tile kernels)")
         del m
+    if "3f" in cases:
+        # config 3 with the constitutive pre-step fused: E, nu per Gauss point in, H never materialised
+        L = _lib.lib()
+        m = A.Mesh(int(4096 * s), int(2048 * s), 1.0 / int(4096 * s))
+        rowptr, _ = m.csr_pattern(2)
+        nnz, G = int(rowptr[-1]), m.ngauss
+        Emod = torch.rand(G, dtype=torch.float64, device="cuda") + 0.5
+        nu = torch.rand(G, dtype=torch.float64, device="cuda") * 0.4
+        vals = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        dK = torch.rand(nnz, dtype=torch.float64, device="cuda") - 0.5
+        gE, gnu = torch.empty_like(Emod), torch.empty_like(nu)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        fwd = lambda: _lib.check(L.adfem_assemble_csr_plane(m.handle, 1, p(Emod), p(nu), p(vals), st))
+        adj = lambda: _lib.check(L.adfem_assemble_csr_plane_adjoint(m.handle, 1, p(Emod), p(nu), p(dK), p(gE), p(gnu), st))
+        tf, ta = timed(fwd, args.steps), timed(adj, args.steps)
+        b = 12 + 8 * 2 * m.nnode / m.nelem + 8 * 2 * m.gauss_per_elem + 8 * nnz / m.nelem      # connectivity + coordinates + (E, nu) + values
+        print(json.dumps({"case": "config3_fused_plane_stress", "elements": m.nelem, "nnz": nnz, "fwd_ms": tf, "adj_ms": ta,
+                          "Melem_per_s": m.nelem / ((tf + ta) * 1e-3) / 1e6, "alg_bytes_per_elem_per_direction": b,
+                          "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9}), flush=True)
+        del m
     if "4l" in cases or "4m" in cases:
         n = int(1000 * s)
         c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)

@@ -13,7 +13,7 @@ for P in 0 1; do
   timeout 600 python scripts/bench_configs.py --cases 3,5 --steps 10 --opt coef_presum=$P > gpurun_out/cfg35_presum${P}_$TAG.jsonl 2> gpurun_out/cfg35_presum${P}_$TAG.err
   echo "configs 3,5 coef_presum=$P rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg35_presum${P}_$TAG.jsonl
 done
-timeout 600 python scripts/bench_configs.py --cases gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
+timeout 600 python scripts/bench_configs.py --cases 3f,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
 echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
 # one full capture of the new kernels (scatter / Laplace term are the ones expected to need work)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gp_scatter|k_laplace_term|k_presum|k_expand" -c 8 -f -o gpurun_out/prof_gp_$TAG \

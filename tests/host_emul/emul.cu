@@ -137,6 +137,20 @@ void emul_quad_source_grad(const double* grad_rhs, int m, int n, double h, doubl
   for (long long t = 0; t < 4LL * m * n; t++) grad_f[t] = quad_source_bwd_body(t, grad_rhs, m, h);
 }
 
+// fused constitutive pre-step: k_presum_plane / k_expand_plane_grad of gauss_ops.cu (P1 triangles)
+int emul_presum_plane(int order, long long ne, int mode, const double* E, const double* nu, double* hbar) {
+  QuadRule r;
+  if (!triangle_rule(order, r)) return 1;
+  for (long long i = 0; i < ne * 9; i++) hbar[i] = presum_plane_body(r, r.n, mode, i, E, nu);
+  return 0;
+}
+int emul_expand_plane_grad(int order, long long ne, int mode, const double* E, const double* nu, const double* gbar, double* gE, double* gnu) {
+  QuadRule r;
+  if (!triangle_rule(order, r)) return 1;
+  for (long long t = 0; t < ne * r.n; t++) expand_plane_grad_body(r, r.n, mode, t, E, nu, gbar, gE, gnu);
+  return 0;
+}
+
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {
   for (long long i = 0; i < n; i++) plane_matrix_body(mode, E[i], nu[i], H + 9 * i);
 }

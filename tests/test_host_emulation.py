@@ -256,3 +256,25 @@ def test_quad_scalar_siblings(emul, oracle):
         gf = np.full(4 * m * n, np.nan)
         emul.emul_quad_source_grad(d(w), C.c_int(m), C.c_int(n), C.c_double(h), d(gf))
         close(gf, oracle.quad_source_bwd(w, m, n, h))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_plane_presum_bodies(emul, oracle, mode):
+    """adfem_assemble_csr_plane: pre-sum straight from (E, nu) == pre-sum of the materialised plane matrices; the gradient expansion equals
+    the oracle's plane-matrix adjoint applied to the expanded per-Gauss-point gradient."""
+    rng = np.random.default_rng(40 + mode)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ne, order, g = 37, 2, 3
+    E, nu = rng.random(ne * g) + 0.5, rng.random(ne * g) * 0.45
+    H = oracle.plane_matrix_fwd(E, nu, mode).reshape(-1)
+    ref, got = np.full(ne * 9, np.nan), np.full(ne * 9, np.nan)
+    assert emul.emul_presum_coef(C.c_int(2), C.c_int(order), C.c_longlong(ne), C.c_int(9), d(H), d(ref)) == 0
+    assert emul.emul_presum_plane(C.c_int(order), C.c_longlong(ne), C.c_int(mode), d(E), d(nu), d(got)) == 0
+    assert np.array_equal(got, ref)
+    gbar = rng.standard_normal(ne * 9)
+    gH = np.full(ne * g * 9, np.nan)
+    assert emul.emul_expand_grad(C.c_int(2), C.c_int(order), C.c_longlong(ne), C.c_int(9), d(gbar), d(gH)) == 0
+    rE, rnu = oracle.plane_matrix_bwd(gH, E, nu, mode)
+    gE, gnu = np.full(ne * g, np.nan), np.full(ne * g, np.nan)
+    assert emul.emul_expand_plane_grad(C.c_int(order), C.c_longlong(ne), C.c_int(mode), d(E), d(nu), d(gbar), d(gE), d(gnu)) == 0
+    close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)

@@ -253,3 +253,27 @@ def test_quad_scalar_siblings(oracle):
         (gf,) = torch.autograd.grad(rhs, ft, dev(w))
         close(npy(gf), oracle.quad_source_bwd(w, m, n, h))
         close(A.compute_fem_source_term1(f, m, n, h), oracle.quad_source_fwd(f, m, n, h))
+
+
+@pytest.mark.parametrize("plane,mode", [("strain", 0), ("stress", 1)])
+def test_fused_plane_stiffness(oracle, plane, mode):
+    """adfem_assemble_csr_plane[_adjoint]: same CSR values / (E, nu)-gradients as plane matrix -> stiffness through the oracle."""
+    rng = np.random.default_rng(50 + mode)
+    c, e = meshgen.jitter_unstructured(17, 13, 0.05, seed=8)
+    m, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    E, nu = rng.random(o.ngauss) + 0.5, rng.random(o.ngauss) * 0.4
+    n = 2 * o.ndof
+    H = oracle.plane_matrix_fwd(E, nu, mode)
+    ind, vv = o.stiffness_fwd(H.reshape(-1))
+    rp, ci, ref = oracle.canonical_csr(ind, vv, n)
+    Et, nt = dev(E).requires_grad_(True), dev(nu).requires_grad_(True)
+    T = A.compute_fem_stiffness_matrix_from_moduli(Et, nt, m, plane=plane)
+    assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+    close(npy(T.values), ref)
+    dv = rng.standard_normal(len(ref))
+    gE, gnu = torch.autograd.grad(T.values, [Et, nt], dev(dv))
+    rE, rnu = oracle.plane_matrix_bwd(o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, n)), E, nu, mode)
+    close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
+    m2 = A.Mesh(c, e, degree=2)
+    with pytest.raises(A.AdfemError):                                                                          # P1 only
+        A.compute_fem_stiffness_matrix_from_moduli(dev(np.ones(m2.ngauss)), dev(np.full(m2.ngauss, 0.3)), m2)
