@@ -125,6 +125,17 @@ class Partition:
         self.ghost_gcols = rk[~matched, 1]                     # global column ids
         self.ghost_vals = torch.zeros(int((~matched).sum()), dtype=torch.float64, device=self.device)
         self.interface_bytes = 8 * (sum(self.send_counts) + sum(self.recv_counts))
+        # ---- dof-vector exchange lists (source term, Laplace / strain-energy terms, dof fields): the dofs I hold but do not own go to their
+        # owner; the owner's list towards rank q is the dofs it shares with q and owns.  Both sides order by global id.
+        by_gid = lambda loc: loc[np.argsort(gid[loc], kind="stable")] if len(loc) else np.zeros(0, dtype=np.int64)
+        vsend = [by_gid(np.flatnonzero(owner == q)) if q != rank else np.zeros(0, dtype=np.int64) for q in range(world)]
+        vrecv = [by_gid(shared_with[q][owner[shared_with[q]] == rank]) if q in shared_with else np.zeros(0, dtype=np.int64) for q in range(world)]
+        self.vsend_counts, self.vrecv_counts = [len(a) for a in vsend], [len(a) for a in vrecv]
+        their = self._all_to_all([gid[a] for a in vsend])                      # what the others will send me, as global ids
+        for q in range(world):
+            assert np.array_equal(their[q], gid[vrecv[q]]), "dof-vector exchange lists of two ranks disagree"
+        self.vsend_idx = torch.from_numpy(np.concatenate(vsend)).to(self.device)
+        self.vrecv_idx = [torch.from_numpy(a).to(self.device) for a in vrecv]
 
     # ---- helpers ---------------------------------------------------------------------------------
     def local_of_gid(self, g, missing_ok=False):
@@ -194,6 +205,57 @@ class Partition:
         dist.all_to_all_single(got, back, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=self.group)
         dvals.index_copy_(0, self.send_pos, got)
         return dvals
+
+    def _comp_index(self, idx, ncomp):
+        """local dof indices -> indices into a component-blocked vector (dof + c*ndof), component-major"""
+        if ncomp == 1:
+            return idx
+        return torch.cat([idx + c * self.mesh.ndof for c in range(ncomp)])
+
+    def reduce_interface_vector(self, vec, ncomp=1):
+        """Forward of the scatter-type operators (source term, Laplace term, strain-energy term): the partial sums of the dofs
+        this rank holds but does not own go to their owners and are added there (in place; non-owned entries keep their partial sums and
+        are not part of this rank's result).  `vec` has ncomp*ndof entries, component-blocked like the reference (dof + c*ndof).
+        Contributions are added rank by rank in ascending order, so the result is reproducible."""
+        if self.world == 1:
+            return vec
+        send = vec.index_select(0, self._comp_index(self.vsend_idx, ncomp)) if ncomp == 1 else \
+            torch.cat([vec.index_select(0, self._comp_index(self.vsend_idx[o:o + c], ncomp)) for o, c in self._spans(self.vsend_counts)])
+        recv = torch.empty(ncomp * sum(self.vrecv_counts), dtype=vec.dtype, device=vec.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=[ncomp * c for c in self.vrecv_counts],
+                               input_split_sizes=[ncomp * c for c in self.vsend_counts], group=self.group)
+        o = 0
+        for q in range(self.world):
+            c = ncomp * self.vrecv_counts[q]
+            if c:
+                vec.index_add_(0, self._comp_index(self.vrecv_idx[q], ncomp), recv[o:o + c])
+            o += c
+        return vec
+
+    def replicate_interface_vector(self, vec, ncomp=1):
+        """The other direction: every owner sends its values of the shared dofs to the ranks that hold copies (in place).  Used for dof
+        fields that feed the gather-type operators (u at the Gauss points, strain, gradients) and for the upstream gradient of the
+        scatter-type operators in the adjoint."""
+        if self.world == 1:
+            return vec
+        back = torch.cat([vec.index_select(0, self._comp_index(self.vrecv_idx[q], ncomp)) for q in range(self.world)]) \
+            if sum(self.vrecv_counts) else torch.empty(0, dtype=vec.dtype, device=vec.device)
+        got = torch.empty(ncomp * sum(self.vsend_counts), dtype=vec.dtype, device=vec.device)
+        dist.all_to_all_single(got, back, output_split_sizes=[ncomp * c for c in self.vsend_counts],
+                               input_split_sizes=[ncomp * c for c in self.vrecv_counts], group=self.group)
+        o = 0
+        for off, c in self._spans(self.vsend_counts):
+            if c:
+                vec.index_copy_(0, self._comp_index(self.vsend_idx[off:off + c], ncomp), got[o:o + ncomp * c])
+            o += ncomp * c
+        return vec
+
+    @staticmethod
+    def _spans(counts):
+        o = 0
+        for c in counts:
+            yield o, c
+            o += c
 
     def owned_rows_coo(self, vals):
         """(global row, global col, value) triplets of the rows this rank owns — for tests / hand-off to a solver."""

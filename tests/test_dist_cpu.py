@@ -97,6 +97,34 @@ def _worker(rank, world, port, case, degree, ret):
             if len(part.ghost_rows) else torch.zeros(0, dtype=torch.float64)
         part.replicate_interface(dv, dghost)
         assert np.array_equal(dv.numpy(), want)
+        # ---- dof-vector exchange ("source term: same exchange on a vector"), scalar and component-blocked
+        f = rng.standard_normal(og.ngauss)
+        gsrc = og.source_fwd(f)
+        lsrc = torch.from_numpy(ol.source_fwd(f[e0 * g:e1 * g]))
+        part.reduce_interface_vector(lsrc)
+        assert np.abs(lsrc.numpy()[part.owned] - gsrc[owned_g]).max() < 1e-13 * max(1.0, np.abs(gsrc).max())
+        part.replicate_interface_vector(lsrc)                                   # now every local copy holds the global value
+        assert np.abs(lsrc.numpy() - gsrc[l2g]).max() < 1e-13 * max(1.0, np.abs(gsrc).max())
+        if case != "tet":
+            # matrix-free Laplace term (gather u -> scatter): u replicated from the owners, partial sums reduced to the owners
+            ug = rng.standard_normal(og.ndof)
+            ul = torch.from_numpy(np.where(part.owned, ug[l2g], np.nan))
+            part.replicate_interface_vector(ul)
+            assert np.array_equal(ul.numpy(), ug[l2g])
+            term = torch.from_numpy(ol.laplace_term_fwd(kappa[e0 * g:e1 * g], ul.numpy()))
+            part.reduce_interface_vector(term)
+            gterm = og.laplace_term_fwd(kappa, ug)
+            assert np.abs(term.numpy()[part.owned] - gterm[owned_g]).max() < 1e-12 * np.abs(gterm).max()
+            # two components (strain-energy term): vector of 2*ndof entries, dof + c*ndof
+            sig = rng.standard_normal(3 * og.ngauss)
+            ge_ = og.strain_energy_fwd(sig)
+            le_ = torch.from_numpy(ol.strain_energy_fwd(sig[3 * e0 * g:3 * e1 * g]))
+            part.reduce_interface_vector(le_, ncomp=2)
+            own2 = np.concatenate([part.owned, part.owned])
+            gsel = np.concatenate([owned_g, owned_g + og.ndof])
+            assert np.abs(le_.numpy()[own2] - ge_[gsel]).max() < 1e-12 * np.abs(ge_).max()
+            part.replicate_interface_vector(le_, ncomp=2)
+            assert np.abs(le_.numpy() - ge_[np.concatenate([l2g, l2g + og.ndof])]).max() < 1e-12 * np.abs(ge_).max()
         ret[rank] = "ok"
     except Exception as ex:  # surface the failure to the parent
         import traceback
