@@ -180,30 +180,68 @@ class Partition:
         return out
 
     # ---- per-step exchanges ------------------------------------------------------------------------
-    def reduce_interface(self, vals):
+    def _block_lists(self, ncomp):
+        """Index lists of the interface exchange for the ncomp x ncomp block operator (elasticity): scalar entry `pos` of row r (length len,
+        start rs, j = pos - rs) holds its ncomp^2 values at ncomp*(a*nnz + rs) + b*len + j (the layout of adfem_assemble_csr, = the
+        canonical CSR of the component-blocked matrix).  The exchange moves the ncomp^2 values of an entry together (entry-major)."""
+        cache = self.__dict__.setdefault("_block_cache", {})
+        if ncomp not in cache:
+            nc2, nnz = ncomp * ncomp, int(self.rowptr[-1])
+
+            def expand(pos_t):
+                pos = pos_t.cpu().numpy()
+                rows = np.searchsorted(self.rowptr, pos, side="right") - 1
+                rs, ln = self.rowptr[rows], self.rowptr[rows + 1] - self.rowptr[rows]
+                out = np.empty((len(pos), ncomp, ncomp), dtype=np.int64)
+                for a in range(ncomp):
+                    for b in range(ncomp):
+                        out[:, a, b] = ncomp * (a * nnz + rs) + b * ln + (pos - rs)
+                return torch.from_numpy(out.reshape(-1)).to(self.device)
+
+            def widen(idx_t):      # indices into the exchanged buffer: entry k -> k*nc2 .. k*nc2 + nc2 - 1
+                return (idx_t.reshape(-1, 1) * nc2 + torch.arange(nc2, device=idx_t.device).reshape(1, -1)).reshape(-1)
+
+            cache[ncomp] = dict(send_pos=expand(self.send_pos), match_pos=expand(self.recv_match_pos), match_idx=widen(self.recv_match_idx),
+                                ghost_idx=widen(self.ghost_idx), send_counts=[c * nc2 for c in self.send_counts],
+                                recv_counts=[c * nc2 for c in self.recv_counts])
+        return cache[ncomp]
+
+    def reduce_interface(self, vals, ncomp=1):
         """Forward: sum the partial interface rows into their owners (in place on `vals`, ghost-column part into
-        `self.ghost_vals`).  Rows this rank does not own keep their partial sums (they are not part of its result)."""
+        `self.ghost_vals`).  Rows this rank does not own keep their partial sums (they are not part of its result).
+        ncomp > 1: the component-blocked elasticity operator (vals in the layout of adfem_assemble_csr, ncomp^2 * nnz values;
+        ghost_vals then holds ncomp^2 values per ghost entry, (a, b)-minor)."""
         if self.world == 1:
             return vals
-        send = vals.index_select(0, self.send_pos)
-        recv = torch.empty(sum(self.recv_counts), dtype=vals.dtype, device=vals.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts, group=self.group)
-        vals.index_add_(0, self.recv_match_pos, recv.index_select(0, self.recv_match_idx))
-        self.ghost_vals = recv.index_select(0, self.ghost_idx)
+        if ncomp == 1:
+            L = dict(send_pos=self.send_pos, match_pos=self.recv_match_pos, match_idx=self.recv_match_idx, ghost_idx=self.ghost_idx,
+                     send_counts=self.send_counts, recv_counts=self.recv_counts)
+        else:
+            L = self._block_lists(ncomp)
+        send = vals.index_select(0, L["send_pos"])
+        recv = torch.empty(sum(L["recv_counts"]), dtype=vals.dtype, device=vals.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=L["recv_counts"], input_split_sizes=L["send_counts"], group=self.group)
+        vals.index_add_(0, L["match_pos"], recv.index_select(0, L["match_idx"]))
+        self.ghost_vals = recv.index_select(0, L["ghost_idx"])
         return vals
 
-    def replicate_interface(self, dvals, dghost=None):
+    def replicate_interface(self, dvals, dghost=None, ncomp=1):
         """Adjoint: owners send d loss / d K of the interface entries back, so `dvals` becomes valid on every entry
         this rank's elements contribute to (rows it does not own included)."""
         if self.world == 1:
             return dvals
-        back = torch.empty(sum(self.recv_counts), dtype=dvals.dtype, device=dvals.device)
-        back.index_copy_(0, self.recv_match_idx, dvals.index_select(0, self.recv_match_pos))
-        if len(self.ghost_idx):
-            back.index_copy_(0, self.ghost_idx, dghost if dghost is not None else torch.zeros_like(self.ghost_vals))
-        got = torch.empty(sum(self.send_counts), dtype=dvals.dtype, device=dvals.device)
-        dist.all_to_all_single(got, back, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=self.group)
-        dvals.index_copy_(0, self.send_pos, got)
+        if ncomp == 1:
+            L = dict(send_pos=self.send_pos, match_pos=self.recv_match_pos, match_idx=self.recv_match_idx, ghost_idx=self.ghost_idx,
+                     send_counts=self.send_counts, recv_counts=self.recv_counts)
+        else:
+            L = self._block_lists(ncomp)
+        back = torch.empty(sum(L["recv_counts"]), dtype=dvals.dtype, device=dvals.device)
+        back.index_copy_(0, L["match_idx"], dvals.index_select(0, L["match_pos"]))
+        if len(L["ghost_idx"]):
+            back.index_copy_(0, L["ghost_idx"], dghost if dghost is not None else torch.zeros(len(L["ghost_idx"]), dtype=dvals.dtype, device=dvals.device))
+        got = torch.empty(sum(L["send_counts"]), dtype=dvals.dtype, device=dvals.device)
+        dist.all_to_all_single(got, back, output_split_sizes=L["send_counts"], input_split_sizes=L["recv_counts"], group=self.group)
+        dvals.index_copy_(0, L["send_pos"], got)
         return dvals
 
     def _comp_index(self, idx, ncomp):
@@ -257,15 +295,31 @@ class Partition:
             yield o, c
             o += c
 
-    def owned_rows_coo(self, vals):
-        """(global row, global col, value) triplets of the rows this rank owns — for tests / hand-off to a solver."""
+    def owned_rows_coo(self, vals, ncomp=1):
+        """(global row, global col, value) triplets of the rows this rank owns — for tests / hand-off to a solver.  ncomp > 1: also the
+        component of the row and of the column, i.e. (gr, gc, gv, a, b)."""
         rows = np.repeat(np.arange(self.mesh.ndof), np.diff(self.rowptr))
         keep = self.owned[rows]
         v = vals.detach().cpu().numpy()
-        gr = np.concatenate([self.gid[rows[keep]], self.gid[self.ghost_rows]])
-        gc = np.concatenate([self.gid[self.colind[keep]], self.ghost_gcols])
-        gv = np.concatenate([v[keep], self.ghost_vals.cpu().numpy()])
-        return gr, gc, gv
+        if ncomp == 1:
+            gr = np.concatenate([self.gid[rows[keep]], self.gid[self.ghost_rows]])
+            gc = np.concatenate([self.gid[self.colind[keep]], self.ghost_gcols])
+            gv = np.concatenate([v[keep], self.ghost_vals.cpu().numpy()])
+            return gr, gc, gv
+        nnz = int(self.rowptr[-1])
+        pos = np.flatnonzero(keep)
+        rs, ln = self.rowptr[rows[pos]], self.rowptr[rows[pos] + 1] - self.rowptr[rows[pos]]
+        gh = self.ghost_vals.cpu().numpy().reshape(-1, ncomp, ncomp)
+        out = [[], [], [], [], []]
+        for a in range(ncomp):
+            for b in range(ncomp):
+                at = ncomp * (a * nnz + rs) + b * ln + (pos - rs)
+                out[0] += [self.gid[rows[pos]], self.gid[self.ghost_rows]]
+                out[1] += [self.gid[self.colind[pos]], self.ghost_gcols]
+                out[2] += [v[at], gh[:, a, b]]
+                out[3] += [np.full(len(pos) + len(self.ghost_rows), a)]
+                out[4] += [np.full(len(pos) + len(self.ghost_rows), b)]
+        return tuple(np.concatenate(o) for o in out)
 
 
 def partition_elements(coords, elems, rank, world, **kw):

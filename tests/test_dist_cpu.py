@@ -97,6 +97,38 @@ def _worker(rank, world, port, case, degree, ret):
             if len(part.ghost_rows) else torch.zeros(0, dtype=torch.float64)
         part.replicate_interface(dv, dghost)
         assert np.array_equal(dv.numpy(), want)
+        # ---- the component-blocked elasticity operator (configs 3 and 5): ncomp^2 values per scalar entry, layout of adfem_assemble_csr
+        if degree == 1:
+            nc = coords.shape[1]
+            ns2 = 9 if nc == 2 else 36
+            Hg = rng.random(og.ngauss * ns2) + 0.1
+            sgi, sgv = og.stiffness_fwd(Hg)
+            srp, sci, sref = O.canonical_csr(sgi, sgv, nc * og.ndof)
+            sli, slv = ol.stiffness_fwd(Hg[ns2 * e0 * g:ns2 * e1 * g])
+            lrp2, lci2, lsv = O.canonical_csr(sli, slv, nc * ol.ndof)
+            sv = torch.from_numpy(lsv.copy())
+            part.reduce_interface(sv, ncomp=nc)
+            gr, gc, gvv, ca, cb = part.owned_rows_coo(sv, ncomp=nc)
+            R = np.array([full[int(x)] for x in gr]) + ca * og.ndof
+            Cc = np.array([full[int(x)] for x in gc]) + cb * og.ndof
+            mine = sp.coo_matrix((gvv, (R, Cc)), shape=(nc * og.ndof, nc * og.ndof)).tocsr()
+            ref = sp.csr_matrix((sref, sci, srp), shape=(nc * og.ndof, nc * og.ndof))
+            own_rows = np.concatenate([owned_g + a * og.ndof for a in range(nc)])
+            assert abs(mine[own_rows] - ref[own_rows]).max() < 1e-12 * np.abs(sref).max()
+            # adjoint direction: dK of the global block matrix reaches every local entry
+            dKb = sp.csr_matrix((np.random.default_rng(2).standard_normal(len(sref)), sci, srp), shape=ref.shape)
+            lrows = np.repeat(np.arange(nc * m.ndof), np.diff(lrp2))
+            la, lr = lrows // m.ndof, lrows % m.ndof
+            lb, lc = lci2 // m.ndof, lci2 % m.ndof
+            want = np.asarray(dKb[l2g[lr] + la * og.ndof, l2g[lc] + lb * og.ndof]).reshape(-1)
+            dv2 = torch.from_numpy(np.where(part.owned[lr], want, np.nan))
+            if len(part.ghost_rows):
+                gR, gC = l2g[part.ghost_rows], np.array([full[int(x)] for x in part.ghost_gcols])
+                dgh = np.stack([np.asarray(dKb[gR + a * og.ndof, gC + b * og.ndof]).reshape(-1) for a in range(nc) for b in range(nc)], 1).reshape(-1)
+            else:
+                dgh = np.zeros(0)
+            part.replicate_interface(dv2, torch.from_numpy(dgh), ncomp=nc)
+            assert np.array_equal(dv2.numpy(), want)
         # ---- dof-vector exchange ("source term: same exchange on a vector"), scalar and component-blocked
         f = rng.standard_normal(og.ngauss)
         gsrc = og.source_fwd(f)
