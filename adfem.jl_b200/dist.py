@@ -342,3 +342,18 @@ def structured_slab(m, n_total, h, rank, world, **kw):
     coords[:, 1] += j0 * h
     gvid = np.arange(coords.shape[0], dtype=np.int64) + j0 * (m + 1)
     return Partition(coords, elems, gvid, (m + 1) * (n_total + 1), rank, world, **kw)
+
+
+def structured_slab3(n, l_total, h, rank, world, **kw):
+    """Rank `rank`'s z-slab of the tetrahedral grid Mesh3(n, n, l_total, h) (src/MFEM3/MFEM.jl:124-185: 5 tets per cube, the two splittings
+    alternate with the parity of i+j+k) without forming the global mesh: l_total/world layers of cubes per rank.  The layer count per rank
+    must be even so that every slab starts on the same parity and is tet_grid(n, n, l, h) shifted in z; the vertex numbering is k-major,
+    so a slab's vertices are a contiguous range of global ids."""
+    assert l_total % world == 0
+    l = l_total // world
+    assert world == 1 or l % 2 == 0, "layers per rank must be even (parity-alternating tetrahedral splitting)"
+    coords, elems = meshgen.tet_grid(n, n, l, h)
+    coords[:, 2] += rank * l * h
+    gvid = np.arange(coords.shape[0], dtype=np.int64) + rank * l * (n + 1) * (n + 1)
+    return Partition(coords, elems, gvid, (n + 1) * (n + 1) * (l_total + 1), rank, world, **kw)
+

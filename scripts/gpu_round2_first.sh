@@ -19,3 +19,9 @@ echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gp_scatter|k_laplace_term|k_presum|k_expand" -c 8 -f -o gpurun_out/prof_gp_$TAG \
   python scripts/bench_configs.py --cases gp --steps 1 --scale 0.5 > gpurun_out/prof_gp_$TAG.log 2>&1
 echo "ncu (gauss-point kernels) rc=$?"
+# multi-GPU (run with gpurun --gpus 2 or 8): configs 3-5 with the interface exchange, weak scaling
+if [ "${GPUS:-1}" -gt 1 ]; then
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $GPUS --master-addr 127.0.0.1 --master-port 29517 scripts/bench_dist_configs.py --cases 3,4l,5 --steps 10 \
+    > gpurun_out/dist_cfg_${GPUS}gpu_$TAG.jsonl 2> gpurun_out/dist_cfg_${GPUS}gpu_$TAG.err
+  echo "multi-GPU configs rc=$?"; cut -c1-400 gpurun_out/dist_cfg_${GPUS}gpu_$TAG.jsonl
+fi

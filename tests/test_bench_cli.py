@@ -41,3 +41,23 @@ def test_product_arm_needs_a_gpu():
         pytest.skip("a CUDA device is present")
     out = _run(["--steps", "1", "--warmup", "1", "--size", "8"])
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_multi_gpu_config_script_dry_run():
+    """scripts/bench_dist_configs.py --dry-run at world size 2 (gloo, host-only meshes): partitions of configs 3, 4 and 5 are built and both
+    interface exchanges run (block operator included); no kernel is launched and no rate is reported."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "scripts", "bench_dist_configs.py"), "--dry-run", "--scale", "0.02", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert [d["case"] for d in lines] == ["config3", "config4l", "config5"]
+    for d in lines:
+        assert d["n_gpus"] == 2 and d["dry_run"] is True and d["Melem_per_s"] is None and d["interface_bytes_per_step_total"] > 0
+    # without --dry-run and without a GPU the script refuses to run
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_dist_configs.py"), "--cases", "3", "--scale", "0.01"], capture_output=True, text=True, timeout=300)
+    import torch
+    if not torch.cuda.is_available():
+        assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)

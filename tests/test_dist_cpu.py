@@ -189,3 +189,23 @@ def test_structured_slab_matches_global_numbering():
         gv = np.arange(c.shape[0]) + rank * nl * (m + 1)
         blk = ge[2 * m * nl * rank:2 * m * nl * (rank + 1)]
         assert np.array_equal(gv[e], blk) and np.allclose(gc[gv], c)
+
+
+def test_structured_slab3_is_a_block_of_the_global_tet_grid():
+    """structured_slab3(): the z-slab of rank r is the set of tetrahedra of Mesh3(n, n, l_total, h) whose cubes lie in its layers, with the
+    same vertex coordinates and the same splitting (parity) — the local element order is the slab's own tet_grid order."""
+    n, l_total, h, world = 3, 8, 0.5, 4
+    gc, ge = meshgen.tet_grid(n, n, l_total, h)
+    gset = {tuple(sorted(t)) for t in ge.tolist()}
+    seen = set()
+    for rank in range(world):
+        l = l_total // world
+        c, e = meshgen.tet_grid(n, n, l, h)
+        c[:, 2] += rank * l * h
+        gv = np.arange(c.shape[0]) + rank * l * (n + 1) * (n + 1)
+        assert np.allclose(gc[gv], c)
+        mine = {tuple(sorted(t)) for t in gv[e].tolist()}
+        assert mine <= gset and not (mine & seen)
+        seen |= mine
+    assert seen == gset
+
