@@ -40,3 +40,22 @@ def test_error_reporting_without_gpu():
         A.Mesh(np.zeros((3, 2)), np.array([[0, 1, 5]]), host_only=True)        # vertex index out of range
     with pytest.raises(ValueError):
         A.Mesh(np.zeros((3, 2)), np.array([[0, 1, 2]]), degree=3, host_only=True)
+
+
+def test_gauss_op_lengths_on_host_only_handles():
+    """adfem_gauss_op_len is host arithmetic: input / output lengths of the five Gauss-point operators (include/adfem_cuda.h)."""
+    import ctypes as C
+    from adfem_jl_b200 import meshgen
+    L = A._lib.lib()
+    c, e = meshgen.jitter_unstructured(5, 4, 0.1, seed=0)
+    for mesh, dim, ns in ((A.Mesh(c, e, degree=2, host_only=True), 2, 3), (A.Mesh3(2, 2, 2, 0.5, host_only=True), 3, 6)):
+        G, n, nv = mesh.ngauss, mesh.ndof, mesh.nnode
+        want = {0: (nv, G), 1: (n, G), 2: (n, G * dim), 3: (dim * n, G * ns), 4: (G * ns, dim * n)}
+        for kind, (nin, nout) in want.items():
+            assert L.adfem_gauss_op_len(mesh.handle, C.c_int(kind), C.c_int(0)) == nin
+            assert L.adfem_gauss_op_len(mesh.handle, C.c_int(kind), C.c_int(1)) == nout
+        assert L.adfem_gauss_op_len(mesh.handle, C.c_int(7), C.c_int(0)) == -1
+        # compute entry points refuse host-only handles (no CPU path)
+        assert L.adfem_gauss_op(mesh.handle, C.c_int(1), None, None, None) != 0 and "no CPU fallback" in A._lib.last_error()
+        assert L.adfem_laplace_term(mesh.handle, None, None, None, None) != 0
+        assert L.adfem_assemble_csr_plane(mesh.handle, C.c_int(1), None, None, None, None) != 0
