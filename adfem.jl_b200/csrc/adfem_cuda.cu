@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "plan.h"
 #include "tri_grid.cuh"
+#include "grid_elast.cuh"
 
 using namespace adfem;
 
@@ -83,6 +84,7 @@ struct adfem_mesh {
   // structured triangulation Mesh(m, n, h) (tri_grid.cuh): detected from the arrays, no mesh-static index data is read
   bool grid_ok = false;
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
+  int opt_grid_elast = 0;                   // P1 elasticity on the structured triangulation: index-free kernels of grid_elast.cuh (off until measured on a GPU)
   DevBuf<double> grid_xs, grid_ys;
   // scratch and streams for the host-buffer calls (H2D, kernels, D2H)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -411,6 +413,33 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
   return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
 }
 
+// P1 elasticity on the structured triangulation (grid_elast.cuh): ~8 waves of resident warps, like the scalar kernels
+bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid(m) && m->hm.degree == 1; }
+int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
+  GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
+  if (m->num_sms == 0 && cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) m->num_sms = 148;
+  const int rows = adjoint ? gt.n : gt.n + 1;
+  const int strips = adjoint ? (gt.m + GE_COLS - 1) / GE_COLS : (gt.m + 1 + GE_COLS - 1) / GE_COLS;
+  const size_t smem = (size_t)GE_WARPS * (adjoint ? GE_ADJ_WARP_DOUBLES : GE_FWD_WARP_DOUBLES) * sizeof(double);
+  int rpw = m->opt_grid_rows;
+  if (rpw <= 0) {
+    const long long want_warps = 8LL * 3 * m->num_sms * GE_WARPS;
+    const int want_chunks = (int)std::max<long long>(1, want_warps / std::max(1, strips));
+    rpw = std::max(8, (rows + want_chunks - 1) / want_chunks);
+  }
+  const long long warps = (long long)strips * ((rows + rpw - 1) / rpw);
+  const unsigned blocks = (unsigned)((warps + GE_WARPS - 1) / GE_WARPS);
+  if (adjoint) {
+    CU_TRY(cudaFuncSetAttribute(k_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_elast_adj<<<blocks, GE_WARPS * 32, smem, st>>>(dev_mesh(m, m->opt_area_csr), gt, m->pat.nnz, rpw, in, out);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(k_grid_elast_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_elast_fwd<<<blocks, GE_WARPS * 32, smem, st>>>(dev_mesh(m, m->opt_area_csr), gt, m->pat.nnz, rpw, in, out);
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int rows = adjoint ? gt.n : gt.n + 1;
@@ -548,6 +577,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "coef_presum") m->opt_coef_presum = value != 0;
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
+  else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;
   else if (k == "host_chunks") m->opt_host_chunks = (int)value;
@@ -624,7 +654,8 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   if (int rc = check_op(m, op)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
-  if (op != ADFEM_OP_STIFFNESS && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
+  if ((op != ADFEM_OP_STIFFNESS || m->opt_grid_elast) && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
+  if (use_grid_elast(m, op)) return launch_grid_elast(m, false, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   FwdPlanDev* P = nullptr;
@@ -653,6 +684,7 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
   cudaStream_t st = (cudaStream_t)stream;
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
+  if (use_grid_elast(m, op)) return launch_grid_elast(m, true, dvals, grad_coef, st);
   if (use_presum(m, op)) {
     // one gradient block per element from the tile kernel, expanded to the g Gauss points by a streaming pass
     if (int rc = ensure_presum_buf(m)) return rc;

@@ -12,34 +12,13 @@
 // transpose buffer so that the 7 entries of 31 consecutive CSR rows leave (forward) or arrive (adjoint) as fully
 // coalesced 256-byte accesses.  Per-entry summation order is ascending element id, i.e. the order of the general path.
 #pragma once
+#include "grid_index.cuh"
 #include "kernels.cuh"
 
 namespace adfem {
 
-struct GridTri {
-  int m, n;                    // cells in x and y
-  const double* xs;            // m+1 node abscissae
-  const double* ys;            // n+1 node ordinates
-};
-
 constexpr int GRID_STRIP = 31;   // node columns per warp (lane 0 / lane 31 carry the neighbouring strip's cell / node column)
 constexpr int GRID_WARPS = 8;
-
-// CSR row pointer of node (i, j), j in [0, m+1] (j = m+1: end of node row i), closed form for the 7-point pattern
-//   row = [ (i-1,j), (i-1,j+1), (i,j-1), (i,j), (i,j+1), (i+1,j-1), (i+1,j) ]  restricted to existing nodes
-__host__ __device__ __forceinline__ long long grid_row_prefix(int j, int m, int A, int B) {
-  const int jm = j < m ? j : m, j1 = j > 0 ? j - 1 : 0;
-  return (long long)j * (1 + A + B) + (long long)(A + 1) * jm + (long long)(1 + B) * j1;
-}
-__host__ __device__ __forceinline__ long long grid_rowptr(int i, int j, int m, int n) {
-  const int A = i > 0, B = i < n;
-  long long before = 0;
-  if (i > 0) {
-    before = grid_row_prefix(m + 1, m, 0, n > 0);                                   // node row 0
-    if (i > 1) before += (long long)(i - 1) * grid_row_prefix(m + 1, m, 1, 1);      // node rows 1 .. i-1 (all have a row above and below)
-  }
-  return before + grid_row_prefix(j, m, A, B);
-}
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");

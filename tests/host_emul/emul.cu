@@ -8,6 +8,7 @@
 
 #include "gauss_ops.cuh"
 #include "quad_ops.cuh"
+#include "grid_elast.cuh"
 
 using namespace adfem;
 
@@ -148,6 +149,56 @@ int emul_expand_plane_grad(int order, long long ne, int mode, const double* E, c
   QuadRule r;
   if (!triangle_rule(order, r)) return 1;
   for (long long t = 0; t < ne * r.n; t++) expand_plane_grad_body(r, r.n, mode, t, E, nu, gbar, gE, gnu);
+  return 0;
+}
+
+// structured P1 elasticity (grid_elast.cuh): every warp of k_grid_elast_fwd / k_grid_elast_adj as three loops over its 32 lanes per row
+int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
+                        double* vals) {
+  QuadRule rule;
+  if (!triangle_rule(order, rule)) return 1;
+  const GridTri gt{m, n, xs, ys};
+  const int strips = (m + 1 + GE_COLS - 1) / GE_COLS, chunks = (n + 1 + rows_per_warp - 1) / rows_per_warp;
+  static double smem[GE_FWD_WARP_DOUBLES];
+  for (long long gw = 0; gw < (long long)strips * chunks; gw++) {
+    const int strip = (int)(gw % strips), chunk = (int)(gw / strips), j0 = strip * GE_COLS;
+    const int i0 = chunk * rows_per_warp, i1 = ge_min(i0 + rows_per_warp, n + 1);
+    for (int k = 0; k < GE_FWD_WARP_DOUBLES; k++) smem[k] = -7.0e300;           // poison: nothing may be read before it is written
+    double *P = smem, *C = P + GE_HROW, *stage = C + GE_HROW;
+    for (int lane = 0; lane < 32; lane++) ge_load_cell_row(lane, rule, rule.n, m, n, i0 - 1, j0, coef, P);
+    long long rowbase = grid_rowptr(i0, 0, m, n);
+    for (int i = i0; i < i1; i++) {
+      for (int lane = 0; lane < 32; lane++) ge_load_cell_row(lane, rule, rule.n, m, n, i, j0, coef, C);
+      for (int lane = 0; lane < 32; lane++) ge_node(lane, heron, gt, i, j0, P, C, stage);
+      for (int lane = 0; lane < 32; lane++) ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
+      rowbase += ge_prefix(m + 1, m, i > 0, i < n);
+      double* t = P; P = C; C = t;
+    }
+  }
+  return 0;
+}
+int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
+                        double* grad) {
+  QuadRule rule;
+  if (!triangle_rule(order, rule)) return 1;
+  const GridTri gt{m, n, xs, ys};
+  const int strips = (m + GE_COLS - 1) / GE_COLS, chunks = (n + rows_per_warp - 1) / rows_per_warp;
+  static double smem[GE_ADJ_WARP_DOUBLES];
+  for (long long gw = 0; gw < (long long)strips * chunks; gw++) {
+    const int strip = (int)(gw % strips), chunk = (int)(gw / strips), c0 = strip * GE_COLS;
+    const int r0 = chunk * rows_per_warp, r1 = ge_min(r0 + rows_per_warp, n);
+    for (int k = 0; k < GE_ADJ_WARP_DOUBLES; k++) smem[k] = -7.0e300;
+    double *lo = smem, *hi = lo + 2 * GE_NROW, *gst = hi + 2 * GE_NROW;
+    long long rowbase = grid_rowptr(r0, 0, m, n);
+    for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, r0, c0, rowbase, nnz, dvals, lo);
+    for (int ci = r0; ci < r1; ci++) {
+      rowbase += ge_prefix(m + 1, m, ci > 0, ci < n);
+      for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
+      for (int lane = 0; lane < 32; lane++) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
+      for (int lane = 0; lane < 32; lane++) ge_store_cell_row(lane, rule, rule.n, m, ci, c0, gst, grad);
+      double* t = lo; lo = hi; hi = t;
+    }
+  }
   return 0;
 }
 

@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_index.cuh", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -278,3 +278,29 @@ def test_fused_plane_presum_bodies(emul, oracle, mode):
     gE, gnu = np.full(ne * g, np.nan), np.full(ne * g, np.nan)
     assert emul.emul_expand_plane_grad(C.c_int(order), C.c_longlong(ne), C.c_int(mode), d(E), d(nu), d(gbar), d(gE), d(gnu)) == 0
     close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)
+
+
+@pytest.mark.parametrize("m,n,rpw,heron", [(5, 4, 8, 0), (1, 1, 3, 1), (33, 3, 2, 0), (70, 9, 4, 1), (32, 2, 100, 0), (31, 6, 1, 0)])
+def test_structured_elasticity_warp_phases(emul, oracle, m, n, rpw, heron):
+    """grid_elast.cuh: every warp of the structured P1-elasticity kernels run as loops over its lanes (shared memory poisoned first), on
+    rectilinear non-uniform grids with one or several strips / chunks, against the canonical CSR of the oracle's stiffness op."""
+    rng = np.random.default_rng(m * 100 + n)
+    xs = np.concatenate([[0.0], np.cumsum(rng.random(m) * 0.1 + 0.05)])
+    ys = np.concatenate([[0.3], 0.3 + np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    c, e = meshgen.tri_grid(m, n, 1.0)
+    c = np.stack([np.tile(xs, n + 1), np.repeat(ys, m + 1)], 1)
+    o = oracle.Mesh2D(c, e)
+    N2 = 2 * o.ndof
+    H = rng.random(o.ngauss * 9) + 0.1
+    ind, vv = o.stiffness_fwd(H)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, N2)
+    nnz_s = len(ref) // 4
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    vals = np.full(len(ref), np.nan)
+    assert emul.emul_grid_elast_fwd(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(H), d(vals)) == 0
+    close(vals, ref, rel=1e-12)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N2))
+    grad = np.full(o.ngauss * 9, np.nan)
+    assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(grad)) == 0
+    close(grad, expect, rel=1e-12)

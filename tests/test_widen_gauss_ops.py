@@ -277,3 +277,30 @@ def test_fused_plane_stiffness(oracle, plane, mode):
     m2 = A.Mesh(c, e, degree=2)
     with pytest.raises(A.AdfemError):                                                                          # P1 only
         A.compute_fem_stiffness_matrix_from_moduli(dev(np.ones(m2.ngauss)), dev(np.full(m2.ngauss, 0.3)), m2)
+
+
+@pytest.mark.parametrize("m,n", [(37, 29), (5, 3), (130, 21)])
+def test_structured_elasticity_kernels(oracle, m, n):
+    """Option "structured_elasticity": index-free P1 elasticity kernels (csrc/grid_elast.cuh) on Mesh(m, n, h) against the oracle and against
+    the general tile kernels, several rows-per-warp settings (one or many chunks), both area formulas."""
+    rng = np.random.default_rng(m + n)
+    ms, o = A.Mesh(m, n, 0.05), oracle.Mesh2D(*meshgen.tri_grid(m, n, 0.05))
+    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == 1
+    N2 = 2 * o.ndof
+    H = rng.random((o.ngauss, 3, 3)) + 0.1
+    ind, vv = o.stiffness_fwd(H.reshape(-1))
+    rp, ci, ref = oracle.canonical_csr(ind, vv, N2)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N2))
+    for on, rows, heron in ((1, 0, 0), (1, 1, 1), (1, 7, 0), (1, 1000, 0), (0, 0, 0)):
+        ms.set_option("structured_elasticity", on)
+        ms.set_option("grid_rows", rows)
+        ms.set_option("area_formula_csr", heron)
+        k = dev(H).requires_grad_(True)
+        T = A.compute_fem_stiffness_matrix(k, ms, mode="csr")
+        assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+        close(npy(T.values), ref)
+        (g,) = torch.autograd.grad(T.values, k, dev(dv))
+        close(npy(g).reshape(-1), expect)
+    ms.set_option("grid_rows", 0)
+    ms.set_option("area_formula_csr", 0)
