@@ -415,7 +415,10 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
 
 // P1 elasticity on the structured triangulation (grid_elast.cuh): ~8 waves of resident warps, like the scalar kernels
 bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid(m) && m->hm.degree == 1; }
-int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
+// plane_mode < 0: tangents H in / dH out (in = H or dvals, out = vals or grad_H).  plane_mode = 0 | 1: fused constitutive step — forward
+// (in = E, in2 = nu) -> out = vals; adjoint (in = dvals; E, nu) -> out = dE, out2 = dnu.
+int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st, int plane_mode = -1, const double* E = nullptr,
+                      const double* nu = nullptr, double* out2 = nullptr) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   if (m->num_sms == 0 && cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) m->num_sms = 148;
   const int rows = adjoint ? gt.n : gt.n + 1;
@@ -429,12 +432,16 @@ int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out
   }
   const long long warps = (long long)strips * ((rows + rpw - 1) / rpw);
   const unsigned blocks = (unsigned)((warps + GE_WARPS - 1) / GE_WARPS);
+  const DevMesh dm = dev_mesh(m, m->opt_area_csr);
+  const bool plane = plane_mode >= 0;
   if (adjoint) {
-    CU_TRY(cudaFuncSetAttribute(k_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_grid_elast_adj<<<blocks, GE_WARPS * 32, smem, st>>>(dev_mesh(m, m->opt_area_csr), gt, m->pat.nnz, rpw, in, out);
+    auto kern = plane ? k_grid_elast_adj<true> : k_grid_elast_adj<false>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, GE_WARPS * 32, smem, st>>>(dm, gt, m->pat.nnz, rpw, plane_mode, E, nu, in, out, out2);
   } else {
-    CU_TRY(cudaFuncSetAttribute(k_grid_elast_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_grid_elast_fwd<<<blocks, GE_WARPS * 32, smem, st>>>(dev_mesh(m, m->opt_area_csr), gt, m->pat.nnz, rpw, in, out);
+    auto kern = plane ? k_grid_elast_fwd<true> : k_grid_elast_fwd<false>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, GE_WARPS * 32, smem, st>>>(dm, gt, m->pat.nnz, rpw, plane_mode, plane ? E : in, nu, out);
   }
   CU_TRY(cudaGetLastError());
   return 0;
@@ -893,6 +900,9 @@ int adfem_assemble_csr_plane(adfem_mesh* m, int mode, const double* E, const dou
   if (int rc = need_device(m)) return rc;
   if (m->hm.dim != 2 || m->hm.degree != 1) return fail("adfem_assemble_csr_plane: P1 triangles only (use adfem_plane_matrix + adfem_assemble_csr otherwise)");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode != 0 && mode != 1) return fail("plane matrix: mode must be 0 (PlaneStrainMatrix) or 1 (PlaneStressMatrix)");
+  if (m->opt_grid_elast && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }
+  if (use_grid_elast(m, ADFEM_OP_STIFFNESS)) return launch_grid_elast(m, false, nullptr, vals, st, mode, E, nu);
   FwdPlanDev* P = nullptr;
   if (int rc = ensure_fwd_plan(m, 2, &P)) return rc;
   if (int rc = ensure_presum_buf(m)) return rc;
@@ -905,6 +915,8 @@ int adfem_assemble_csr_plane_adjoint(adfem_mesh* m, int mode, const double* E, c
   if (m->hm.dim != 2 || m->hm.degree != 1) return fail("adfem_assemble_csr_plane_adjoint: P1 triangles only");
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode != 0 && mode != 1) return fail("plane matrix: mode must be 0 (PlaneStrainMatrix) or 1 (PlaneStressMatrix)");
+  if (use_grid_elast(m, ADFEM_OP_STIFFNESS)) return launch_grid_elast(m, true, dvals, grad_E, st, mode, E, nu, grad_nu);
   if (int rc = ensure_presum_buf(m)) return rc;
   if (int rc = launch_adj<2, 1, OP_STIFFNESS>(m, dvals, m->presum_buf.p, st, true)) return rc;
   return launch_expand_plane_grad(dev_mesh(m, m->opt_area_csr), mode, E, nu, m->presum_buf.p, grad_E, grad_nu, st);

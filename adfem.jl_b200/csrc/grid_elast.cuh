@@ -17,6 +17,7 @@
 // the oracle where there is no GPU.
 #pragma once
 #include "device_fem.cuh"
+#include "gauss_ops.cuh"
 #include "grid_index.cuh"
 
 namespace adfem {
@@ -48,6 +49,29 @@ ADFEM_HD void ge_load_cell_row(int lane, const QuadRule& rule, int g, int m, int
       for (int k = 0; k < g; k++) s += ldg(p + 9 * k) * rule.w[k];
     }
     buf[idx] = s;
+  }
+}
+
+// phase 1, fused constitutive step: the same Gauss-summed tangents straight from the moduli, H_k = plane matrix(E_k, nu_k)
+// (gauss_ops.cuh); a lane owns whole triangles, so every plane matrix is evaluated once.  16 B per Gauss point are read instead of 72.
+ADFEM_HD void ge_load_cell_row_plane(int lane, const QuadRule& rule, int g, int m, int n, int ci, int j0, int mode, const double* E, const double* nu,
+                                     double* buf) {
+  for (int t = lane; t < GE_TRI; t += 32) {
+    const int cc = j0 - 1 + (t >> 1);
+    double s[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) s[c] = 0.0;
+    if (ci >= 0 && ci < n && cc >= 0 && cc < m) {
+      const size_t g0 = (size_t)(2 * ((size_t)ci * m + cc) + (t & 1)) * g;
+      for (int k = 0; k < g; k++) {
+        double H[9];
+        plane_matrix_body(mode, ldg(E + g0 + k), ldg(nu + g0 + k), H);
+#pragma unroll
+        for (int c = 0; c < 9; c++) s[c] += H[c] * rule.w[k];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) buf[t * 9 + c] = s[c];
   }
 }
 
@@ -203,10 +227,26 @@ ADFEM_HD void ge_store_cell_row(int lane, const QuadRule& rule, int g, int m, in
   }
 }
 
+// phase 3, fused constitutive step: (dE, dnu)[e*g + k] = d plane matrix / d(E, nu)^T (w_k gst[t]) over the contiguous run of the segment's Gauss points
+ADFEM_HD void ge_store_cell_row_plane(int lane, const QuadRule& rule, int g, int m, int ci, int c0, int mode, const double* E, const double* nu,
+                                      const double* gst, double* grad_E, double* grad_nu) {
+  const int ncell = ge_min(GE_COLS, m - c0), total = 2 * ncell * g;
+  const size_t g0 = (size_t)(2 * ((size_t)ci * m + c0)) * g;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int t = idx / g, k = idx - t * g;
+    double gk[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) gk[c] = gst[t * 9 + c] * rule.w[k];
+    plane_matrix_grad_body(mode, ldg(E + g0 + idx), ldg(nu + g0 + idx), gk, grad_E + g0 + idx, grad_nu + g0 + idx);
+  }
+}
+
 #ifdef __CUDACC__
 // Forward kernel: node rows [0, n], strips of 32 node columns; a warp handles `rows_per_warp` consecutive node rows of one strip.
-__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, const double* __restrict__ coef,
-                                                                  double* __restrict__ vals) {
+// PLANE: the tangents come from the moduli (coef = E, coef2 = nu, mode = 0 | 1) instead of from H (coef).
+template <bool PLANE>
+__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
+                                                                  const double* __restrict__ coef, const double* __restrict__ coef2, double* __restrict__ vals) {
   extern __shared__ __align__(16) double ge_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, m = gt.m, n = gt.n;
   const int strips = (m + 1 + GE_COLS - 1) / GE_COLS, chunks = (n + 1 + rows_per_warp - 1) / rows_per_warp;
@@ -217,10 +257,14 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, Gr
   double* P = ge_smem + (size_t)wib * GE_FWD_WARP_DOUBLES;
   double* C = P + GE_HROW;
   double* stage = C + GE_HROW;
-  ge_load_cell_row(lane, dm.rule, dm.g, m, n, i0 - 1, j0, coef, P);
+  auto load = [&](int ci, double* buf) {
+    if constexpr (PLANE) ge_load_cell_row_plane(lane, dm.rule, dm.g, m, n, ci, j0, mode, coef, coef2, buf);
+    else ge_load_cell_row(lane, dm.rule, dm.g, m, n, ci, j0, coef, buf);
+  };
+  load(i0 - 1, P);
   long long rowbase = grid_rowptr(i0, 0, m, n);
   for (int i = i0; i < i1; i++) {
-    ge_load_cell_row(lane, dm.rule, dm.g, m, n, i, j0, coef, C);
+    load(i, C);
     __syncwarp();
     ge_node(lane, dm.heron, gt, i, j0, P, C, stage);
     __syncwarp();
@@ -232,8 +276,11 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, Gr
 }
 
 // Adjoint kernel: cell rows [0, n), strips of 32 cell columns; a warp handles `rows_per_warp` consecutive cell rows of one strip.
-__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_adj(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, const double* __restrict__ dvals,
-                                                                  double* __restrict__ grad) {
+// PLANE: gradients with respect to the moduli (E, nu in; grad = dE, grad2 = dnu) instead of with respect to H.
+template <bool PLANE>
+__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_adj(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
+                                                                  const double* __restrict__ E, const double* __restrict__ nu,
+                                                                  const double* __restrict__ dvals, double* __restrict__ grad, double* __restrict__ grad2) {
   extern __shared__ __align__(16) double ge_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, m = gt.m, n = gt.n;
   const int strips = (m + GE_COLS - 1) / GE_COLS, chunks = (n + rows_per_warp - 1) / rows_per_warp;
@@ -252,7 +299,8 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_adj(DevMesh dm, Gr
     __syncwarp();
     ge_cell_adjoint(lane, dm.heron, gt, ci, c0, lo, hi, gst);
     __syncwarp();
-    ge_store_cell_row(lane, dm.rule, dm.g, m, ci, c0, gst, grad);
+    if constexpr (PLANE) ge_store_cell_row_plane(lane, dm.rule, dm.g, m, ci, c0, mode, E, nu, gst, grad, grad2);
+    else ge_store_cell_row(lane, dm.rule, dm.g, m, ci, c0, gst, grad);
     __syncwarp();
     double* t = lo; lo = hi; hi = t;
   }

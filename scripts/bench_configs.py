@@ -101,6 +101,8 @@ def main():
         # config 3 with the constitutive pre-step fused: E, nu per Gauss point in, H never materialised
         L = _lib.lib()
         m = A.Mesh(int(4096 * s), int(2048 * s), 1.0 / int(4096 * s))
+        for k, v in OPTS.items():
+            m.set_option(k, v)
         rowptr, _ = m.csr_pattern(2)
         nnz, G = int(rowptr[-1]), m.ngauss
         Emod = torch.rand(G, dtype=torch.float64, device="cuda") + 0.5
@@ -116,7 +118,7 @@ def main():
         b = 12 + 8 * 2 * m.nnode / m.nelem + 8 * 2 * m.gauss_per_elem + 8 * nnz / m.nelem      # connectivity + coordinates + (E, nu) + values
         print(json.dumps({"case": "config3_fused_plane_stress", "elements": m.nelem, "nnz": nnz, "fwd_ms": tf, "adj_ms": ta,
                           "Melem_per_s": m.nelem / ((tf + ta) * 1e-3) / 1e6, "alg_bytes_per_elem_per_direction": b,
-                          "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9}), flush=True)
+                          "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9, "options": dict(OPTS)}), flush=True)
         del m
     if "4l" in cases or "4m" in cases:
         n = int(1000 * s)

@@ -15,6 +15,8 @@ for P in 0 1; do
 done
 timeout 600 python scripts/bench_configs.py --cases 3 --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3_gridelast_$TAG.jsonl 2> gpurun_out/cfg3_gridelast_$TAG.err
 echo "config 3 structured elasticity kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3_gridelast_$TAG.jsonl
+timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3f_gridelast_$TAG.jsonl 2> gpurun_out/cfg3f_gridelast_$TAG.err
+echo "config 3 fused moduli, structured kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3f_gridelast_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
 echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
 # one full capture of the new kernels (scatter / Laplace term are the ones expected to need work)

@@ -153,8 +153,9 @@ int emul_expand_plane_grad(int order, long long ne, int mode, const double* E, c
 }
 
 // structured P1 elasticity (grid_elast.cuh): every warp of k_grid_elast_fwd / k_grid_elast_adj as three loops over its 32 lanes per row
+// plane_mode < 0: coef = H; plane_mode = 0 | 1: coef = E, coef2 = nu (fused constitutive step)
 int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
-                        double* vals) {
+                        double* vals, int plane_mode, const double* coef2) {
   QuadRule rule;
   if (!triangle_rule(order, rule)) return 1;
   const GridTri gt{m, n, xs, ys};
@@ -165,10 +166,14 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
     const int i0 = chunk * rows_per_warp, i1 = ge_min(i0 + rows_per_warp, n + 1);
     for (int k = 0; k < GE_FWD_WARP_DOUBLES; k++) smem[k] = -7.0e300;           // poison: nothing may be read before it is written
     double *P = smem, *C = P + GE_HROW, *stage = C + GE_HROW;
-    for (int lane = 0; lane < 32; lane++) ge_load_cell_row(lane, rule, rule.n, m, n, i0 - 1, j0, coef, P);
+    auto load = [&](int lane, int ci, double* buf) {
+      if (plane_mode >= 0) ge_load_cell_row_plane(lane, rule, rule.n, m, n, ci, j0, plane_mode, coef, coef2, buf);
+      else ge_load_cell_row(lane, rule, rule.n, m, n, ci, j0, coef, buf);
+    };
+    for (int lane = 0; lane < 32; lane++) load(lane, i0 - 1, P);
     long long rowbase = grid_rowptr(i0, 0, m, n);
     for (int i = i0; i < i1; i++) {
-      for (int lane = 0; lane < 32; lane++) ge_load_cell_row(lane, rule, rule.n, m, n, i, j0, coef, C);
+      for (int lane = 0; lane < 32; lane++) load(lane, i, C);
       for (int lane = 0; lane < 32; lane++) ge_node(lane, heron, gt, i, j0, P, C, stage);
       for (int lane = 0; lane < 32; lane++) ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
       rowbase += ge_prefix(m + 1, m, i > 0, i < n);
@@ -178,7 +183,7 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
   return 0;
 }
 int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
-                        double* grad) {
+                        double* grad, int plane_mode, const double* E, const double* nu, double* grad2) {
   QuadRule rule;
   if (!triangle_rule(order, rule)) return 1;
   const GridTri gt{m, n, xs, ys};
@@ -195,7 +200,10 @@ int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int or
       rowbase += ge_prefix(m + 1, m, ci > 0, ci < n);
       for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
       for (int lane = 0; lane < 32; lane++) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
-      for (int lane = 0; lane < 32; lane++) ge_store_cell_row(lane, rule, rule.n, m, ci, c0, gst, grad);
+      for (int lane = 0; lane < 32; lane++) {
+        if (plane_mode >= 0) ge_store_cell_row_plane(lane, rule, rule.n, m, ci, c0, plane_mode, E, nu, gst, grad, grad2);
+        else ge_store_cell_row(lane, rule, rule.n, m, ci, c0, gst, grad);
+      }
       double* t = lo; lo = hi; hi = t;
     }
   }

@@ -297,10 +297,27 @@ def test_structured_elasticity_warp_phases(emul, oracle, m, n, rpw, heron):
     nnz_s = len(ref) // 4
     d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     vals = np.full(len(ref), np.nan)
-    assert emul.emul_grid_elast_fwd(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(H), d(vals)) == 0
+    assert emul.emul_grid_elast_fwd(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(H), d(vals),
+                                    C.c_int(-1), None) == 0
     close(vals, ref, rel=1e-12)
     dv = rng.standard_normal(len(ref))
     expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N2))
     grad = np.full(o.ngauss * 9, np.nan)
-    assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(grad)) == 0
+    assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(grad),
+                                    C.c_int(-1), None, None, None) == 0
     close(grad, expect, rel=1e-12)
+    # fused constitutive step: tangents straight from the moduli, gradients with respect to the moduli
+    for mode in (0, 1):
+        E, nu = rng.random(o.ngauss) + 0.5, rng.random(o.ngauss) * 0.4
+        Hm = oracle.plane_matrix_fwd(E, nu, mode).reshape(-1)
+        _, vvm = o.stiffness_fwd(Hm)
+        _, _, refm = oracle.canonical_csr(ind, vvm, N2)
+        vals = np.full(len(ref), np.nan)
+        assert emul.emul_grid_elast_fwd(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(E), d(vals),
+                                        C.c_int(mode), d(nu)) == 0
+        close(vals, refm, rel=1e-12)
+        rE, rnu = oracle.plane_matrix_bwd(expect, E, nu, mode)
+        gE, gnu = np.full(o.ngauss, np.nan), np.full(o.ngauss, np.nan)
+        assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(gE),
+                                        C.c_int(mode), d(E), d(nu), d(gnu)) == 0
+        close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)

@@ -304,3 +304,16 @@ def test_structured_elasticity_kernels(oracle, m, n):
         close(npy(g).reshape(-1), expect)
     ms.set_option("grid_rows", 0)
     ms.set_option("area_formula_csr", 0)
+    # fused constitutive step on the structured kernels (tangents from the moduli, gradients with respect to the moduli)
+    E, nu = rng.random(o.ngauss) + 0.5, rng.random(o.ngauss) * 0.4
+    for mode, plane in ((0, "strain"), (1, "stress")):
+        _, vvm = o.stiffness_fwd(oracle.plane_matrix_fwd(E, nu, mode).reshape(-1))
+        _, _, refm = oracle.canonical_csr(ind, vvm, N2)
+        rE, rnu = oracle.plane_matrix_bwd(expect, E, nu, mode)
+        for on in (1, 0):
+            ms.set_option("structured_elasticity", on)
+            Et, nt = dev(E).requires_grad_(True), dev(nu).requires_grad_(True)
+            T = A.compute_fem_stiffness_matrix_from_moduli(Et, nt, ms, plane=plane)
+            close(npy(T.values), refm)
+            gE, gnu = torch.autograd.grad(T.values, [Et, nt], dev(dv))
+            close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
