@@ -14,7 +14,7 @@ def functions(path):
                 out[name] = hashlib.md5("".join(buf).encode()).hexdigest()
             name, buf = m.group(1), []
         elif name:
-            buf.append(line)
+            buf.append(" ".join(line.split()) + "\n")       # cuobjdump pads the columns to the longest instruction of the whole dump
     if name:
         out[name] = hashlib.md5("".join(buf).encode()).hexdigest()
     return out
