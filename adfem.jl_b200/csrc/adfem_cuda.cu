@@ -414,7 +414,7 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
 }
 
 // P1 elasticity on the structured triangulation (grid_elast.cuh): ~8 waves of resident warps, like the scalar kernels
-bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid(m) && m->hm.degree == 1; }
+bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid(m) && m->hm.degree == 1 && m->hm.g == GE_G; }
 // plane_mode < 0: tangents H in / dH out (in = H or dvals, out = vals or grad_H).  plane_mode = 0 | 1: fused constitutive step — forward
 // (in = E, in2 = nu) -> out = vals; adjoint (in = dvals; E, nu) -> out = dE, out2 = dnu.
 int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st, int plane_mode = -1, const double* E = nullptr,

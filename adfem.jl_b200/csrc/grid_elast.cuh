@@ -27,6 +27,7 @@ constexpr int GE_TRI = 2 * (GE_COLS + 1);                // triangles of one cel
 constexpr int GE_HROW = GE_TRI * 9;                      // doubles of Gauss-summed tangents per cell-row segment
 constexpr int GE_STAGE = GE_COLS * 14;                   // forward staging per component: <= 14 values per node
 constexpr int GE_WARPS = 4;
+constexpr int GE_G = 3;                                   // Gauss points per triangle: the structured layout is only detected for the order-2 rule
 constexpr int GE_FWD_WARP_DOUBLES = 2 * GE_HROW + 2 * GE_STAGE;
 constexpr int GE_NROW = (GE_COLS + 1) * 14;              // adjoint: staged CSR values of one node-row segment (33 nodes) per component
 constexpr int GE_ADJ_WARP_DOUBLES = 2 * 2 * GE_NROW + 2 * GE_COLS * 9;
@@ -40,13 +41,15 @@ ADFEM_HD int ge_min(int a, int b) { return a < b ? a : b; }
 // ---- forward ----------------------------------------------------------------------------------------------------------------------
 // phase 1: Gauss-summed tangents of cell row ci, cell columns j0-1 .. j0+31, into buf[t*9 + c] (t = 2*(cc - j0 + 1) + triangle); cells
 // outside the mesh give zeros
-ADFEM_HD void ge_load_cell_row(int lane, const QuadRule& rule, int g, int m, int n, int ci, int j0, const double* coef, double* buf) {
+template <int G>
+ADFEM_HD void ge_load_cell_row(int lane, const QuadRule& rule, int m, int n, int ci, int j0, const double* coef, double* buf) {
   for (int idx = lane; idx < GE_HROW; idx += 32) {
     const int t = idx / 9, c = idx - 9 * t, cc = j0 - 1 + (t >> 1);
     double s = 0.0;
     if (ci >= 0 && ci < n && cc >= 0 && cc < m) {
-      const double* p = coef + ((size_t)(2 * ((size_t)ci * m + cc) + (t & 1)) * g) * 9 + c;
-      for (int k = 0; k < g; k++) s += ldg(p + 9 * k) * rule.w[k];
+      const double* p = coef + ((size_t)(2 * ((size_t)ci * m + cc) + (t & 1)) * G) * 9 + c;
+#pragma unroll
+      for (int k = 0; k < G; k++) s += ldg(p + 9 * k) * rule.w[k];
     }
     buf[idx] = s;
   }
@@ -54,7 +57,8 @@ ADFEM_HD void ge_load_cell_row(int lane, const QuadRule& rule, int g, int m, int
 
 // phase 1, fused constitutive step: the same Gauss-summed tangents straight from the moduli, H_k = plane matrix(E_k, nu_k)
 // (gauss_ops.cuh); a lane owns whole triangles, so every plane matrix is evaluated once.  16 B per Gauss point are read instead of 72.
-ADFEM_HD void ge_load_cell_row_plane(int lane, const QuadRule& rule, int g, int m, int n, int ci, int j0, int mode, const double* E, const double* nu,
+template <int G>
+ADFEM_HD void ge_load_cell_row_plane(int lane, const QuadRule& rule, int m, int n, int ci, int j0, int mode, const double* E, const double* nu,
                                      double* buf) {
   for (int t = lane; t < GE_TRI; t += 32) {
     const int cc = j0 - 1 + (t >> 1);
@@ -62,8 +66,9 @@ ADFEM_HD void ge_load_cell_row_plane(int lane, const QuadRule& rule, int g, int 
 #pragma unroll
     for (int c = 0; c < 9; c++) s[c] = 0.0;
     if (ci >= 0 && ci < n && cc >= 0 && cc < m) {
-      const size_t g0 = (size_t)(2 * ((size_t)ci * m + cc) + (t & 1)) * g;
-      for (int k = 0; k < g; k++) {
+      const size_t g0 = (size_t)(2 * ((size_t)ci * m + cc) + (t & 1)) * G;
+#pragma unroll
+      for (int k = 0; k < G; k++) {
         double H[9];
         plane_matrix_body(mode, ldg(E + g0 + k), ldg(nu + g0 + k), H);
 #pragma unroll
@@ -218,8 +223,10 @@ ADFEM_HD void ge_cell_adjoint(int lane, int heron, const GridTri& gt, int ci, in
 }
 
 // phase 3: grad[(e*g + k)*9 + c] = gst[t*9 + c] * w_k over the contiguous run of the segment's elements (e = 2*(ci*m + c0) + t)
-ADFEM_HD void ge_store_cell_row(int lane, const QuadRule& rule, int g, int m, int ci, int c0, const double* gst, double* grad) {
-  const int ncell = ge_min(GE_COLS, m - c0), per = 9 * g, total = 2 * ncell * per;
+template <int G>
+ADFEM_HD void ge_store_cell_row(int lane, const QuadRule& rule, int m, int ci, int c0, const double* gst, double* grad) {
+  constexpr int per = 9 * G;
+  const int ncell = ge_min(GE_COLS, m - c0), total = 2 * ncell * per;
   double* out = grad + (size_t)(2 * ((size_t)ci * m + c0)) * per;
   for (int idx = lane; idx < total; idx += 32) {
     const int t = idx / per, r = idx - t * per, k = r / 9, c = r - 9 * k;
@@ -228,12 +235,13 @@ ADFEM_HD void ge_store_cell_row(int lane, const QuadRule& rule, int g, int m, in
 }
 
 // phase 3, fused constitutive step: (dE, dnu)[e*g + k] = d plane matrix / d(E, nu)^T (w_k gst[t]) over the contiguous run of the segment's Gauss points
-ADFEM_HD void ge_store_cell_row_plane(int lane, const QuadRule& rule, int g, int m, int ci, int c0, int mode, const double* E, const double* nu,
+template <int G>
+ADFEM_HD void ge_store_cell_row_plane(int lane, const QuadRule& rule, int m, int ci, int c0, int mode, const double* E, const double* nu,
                                       const double* gst, double* grad_E, double* grad_nu) {
-  const int ncell = ge_min(GE_COLS, m - c0), total = 2 * ncell * g;
-  const size_t g0 = (size_t)(2 * ((size_t)ci * m + c0)) * g;
+  const int ncell = ge_min(GE_COLS, m - c0), total = 2 * ncell * G;
+  const size_t g0 = (size_t)(2 * ((size_t)ci * m + c0)) * G;
   for (int idx = lane; idx < total; idx += 32) {
-    const int t = idx / g, k = idx - t * g;
+    const int t = idx / G, k = idx - t * G;
     double gk[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) gk[c] = gst[t * 9 + c] * rule.w[k];
@@ -258,8 +266,8 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, Gr
   double* C = P + GE_HROW;
   double* stage = C + GE_HROW;
   auto load = [&](int ci, double* buf) {
-    if constexpr (PLANE) ge_load_cell_row_plane(lane, dm.rule, dm.g, m, n, ci, j0, mode, coef, coef2, buf);
-    else ge_load_cell_row(lane, dm.rule, dm.g, m, n, ci, j0, coef, buf);
+    if constexpr (PLANE) ge_load_cell_row_plane<GE_G>(lane, dm.rule, m, n, ci, j0, mode, coef, coef2, buf);
+    else ge_load_cell_row<GE_G>(lane, dm.rule, m, n, ci, j0, coef, buf);
   };
   load(i0 - 1, P);
   long long rowbase = grid_rowptr(i0, 0, m, n);
@@ -299,8 +307,8 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_adj(DevMesh dm, Gr
     __syncwarp();
     ge_cell_adjoint(lane, dm.heron, gt, ci, c0, lo, hi, gst);
     __syncwarp();
-    if constexpr (PLANE) ge_store_cell_row_plane(lane, dm.rule, dm.g, m, ci, c0, mode, E, nu, gst, grad, grad2);
-    else ge_store_cell_row(lane, dm.rule, dm.g, m, ci, c0, gst, grad);
+    if constexpr (PLANE) ge_store_cell_row_plane<GE_G>(lane, dm.rule, m, ci, c0, mode, E, nu, gst, grad, grad2);
+    else ge_store_cell_row<GE_G>(lane, dm.rule, m, ci, c0, gst, grad);
     __syncwarp();
     double* t = lo; lo = hi; hi = t;
   }

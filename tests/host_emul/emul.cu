@@ -157,7 +157,7 @@ int emul_expand_plane_grad(int order, long long ne, int mode, const double* E, c
 int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
                         double* vals, int plane_mode, const double* coef2) {
   QuadRule rule;
-  if (!triangle_rule(order, rule)) return 1;
+  if (!triangle_rule(order, rule) || rule.n != GE_G) return 1;
   const GridTri gt{m, n, xs, ys};
   const int strips = (m + 1 + GE_COLS - 1) / GE_COLS, chunks = (n + 1 + rows_per_warp - 1) / rows_per_warp;
   static double smem[GE_FWD_WARP_DOUBLES];
@@ -167,8 +167,8 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
     for (int k = 0; k < GE_FWD_WARP_DOUBLES; k++) smem[k] = -7.0e300;           // poison: nothing may be read before it is written
     double *P = smem, *C = P + GE_HROW, *stage = C + GE_HROW;
     auto load = [&](int lane, int ci, double* buf) {
-      if (plane_mode >= 0) ge_load_cell_row_plane(lane, rule, rule.n, m, n, ci, j0, plane_mode, coef, coef2, buf);
-      else ge_load_cell_row(lane, rule, rule.n, m, n, ci, j0, coef, buf);
+      if (plane_mode >= 0) ge_load_cell_row_plane<GE_G>(lane, rule, m, n, ci, j0, plane_mode, coef, coef2, buf);
+      else ge_load_cell_row<GE_G>(lane, rule, m, n, ci, j0, coef, buf);
     };
     for (int lane = 0; lane < 32; lane++) load(lane, i0 - 1, P);
     long long rowbase = grid_rowptr(i0, 0, m, n);
@@ -185,7 +185,7 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
 int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
                         double* grad, int plane_mode, const double* E, const double* nu, double* grad2) {
   QuadRule rule;
-  if (!triangle_rule(order, rule)) return 1;
+  if (!triangle_rule(order, rule) || rule.n != GE_G) return 1;
   const GridTri gt{m, n, xs, ys};
   const int strips = (m + GE_COLS - 1) / GE_COLS, chunks = (n + rows_per_warp - 1) / rows_per_warp;
   static double smem[GE_ADJ_WARP_DOUBLES];
@@ -201,8 +201,8 @@ int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int or
       for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
       for (int lane = 0; lane < 32; lane++) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
       for (int lane = 0; lane < 32; lane++) {
-        if (plane_mode >= 0) ge_store_cell_row_plane(lane, rule, rule.n, m, ci, c0, plane_mode, E, nu, gst, grad, grad2);
-        else ge_store_cell_row(lane, rule, rule.n, m, ci, c0, gst, grad);
+        if (plane_mode >= 0) ge_store_cell_row_plane<GE_G>(lane, rule, m, ci, c0, plane_mode, E, nu, gst, grad, grad2);
+        else ge_store_cell_row<GE_G>(lane, rule, m, ci, c0, gst, grad);
       }
       double* t = lo; lo = hi; hi = t;
     }
