@@ -185,9 +185,11 @@ int ensure_pattern(adfem_mesh* m) {
 // doubles of shared memory per tile element in the forward kernel: the local matrix (packed symmetric for scalar operators) plus, for the
 // scalar operators that stage their coefficients asynchronously, two buffers of g coefficients
 bool coef_staged(const HostMesh& h) { return h.degree != 1 || h.g > PIPE_GMAX; }       // scalar operators that cannot use the register prefetch
-int slots_of(const HostMesh& h, int nc) {
+// presum3d: 3-D P1 elasticity with option "coef_presum": the Gauss-summed blocks (ns*ns doubles per element) are small enough to be staged too
+int slots_of(const HostMesh& h, int nc, bool presum3d = false) {
   if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? h.g : 0);                // + a staging buffer of g coefficients
   const int ns = h.dim == 2 ? 3 : 6;
+  if (presum3d) return (nc * h.d) * (nc * h.d) + ns * ns;
   // 2-D P1 elasticity stages the raw coefficient blocks (ns*ns*g doubles per element) asynchronously
   return (nc * h.d) * (nc * h.d) + ((h.dim == 2 && h.degree == 1) ? ns * ns * h.g : 0);
 }
@@ -201,10 +203,12 @@ size_t adj_smem_bytes(const AdjTiles& ap, int nc, int ns2) {
 int adj_ns2(const HostMesh& h, int nc) { return (nc > 1 && h.degree == 1) ? (h.dim == 2 ? 9 : 36) : 0; }
 constexpr size_t SMEM_LIMIT = 220 * 1024;
 
+bool presum3d_of(const adfem_mesh* m, int nc) { return m->opt_coef_presum && nc > 1 && m->hm.dim == 3 && m->hm.degree == 1 && m->hm.g > 1; }
+
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (int rc = ensure_pattern(m)) return rc;
   const HostMesh& h = m->hm;
-  const int slots = slots_of(h, nc), dd = h.d * h.d;
+  const int slots = slots_of(h, nc, presum3d_of(m, nc)), dd = h.d * h.d;
   auto it = m->fwd_plans.find(nc);
   if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
   auto P = std::make_unique<FwdPlanDev>();
@@ -334,7 +338,7 @@ int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int thr
 template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st, bool presum = false) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
-  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC));
+  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC, presum && presum3d_of(m, NC)));
   const int threads = tile_threads_of(m, NC);
   if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
   if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
@@ -347,6 +351,10 @@ int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* va
   }
   if constexpr (OP == OP_STIFFNESS && DIM == 2 && DEG == 1) {
     if (m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st, presum);
+  }
+  if constexpr (OP == OP_STIFFNESS && DIM == 3 && DEG == 1) {
+    // Gauss-summed blocks (option "coef_presum"): 36 doubles per element, staged with the flat coalesced index like the 2-D blocks
+    if (presum && presum3d_of(m, NC) && m->opt_coef_prefetch) return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, true>, P, smem, threads, coef, vals, st, presum);
   }
   return launch_fwd_kernel(m, k_tile_fwd<DIM, DEG, OP, false, false>, P, smem, threads, coef, vals, st, presum);
 }
@@ -581,7 +589,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }
   else if (k == "coef_prefetch") m->opt_coef_prefetch = value != 0;
-  else if (k == "coef_presum") m->opt_coef_presum = value != 0;
+  else if (k == "coef_presum") { if (m->opt_coef_presum != (value != 0) && m->hm.dim == 3) m->fwd_plans.clear(); m->opt_coef_presum = value != 0; }      // 3-D: the tile size depends on it
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;

@@ -227,6 +227,21 @@ def test_forward_plan_replay_elasticity(oracle, name, degree):
     assert _close(vals, ref)
 
 
+def test_forward_plan_replay_elasticity_3d_with_coef_presum(oracle):
+    """Option "coef_presum" changes the shared-memory slots per element of the 3-D P1 elasticity tiles (Gauss-summed blocks are staged): the
+    plan is rebuilt and must still replay to the oracle's matrix."""
+    m, o = make("tet", 1, oracle)
+    rng = np.random.default_rng(2)
+    H = rng.random(o.ngauss * 36)
+    ind, vv = o.stiffness_fwd(H)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, 3 * o.ndof)
+    local = vv.reshape(o.nelem, o.g, 144).sum(1)
+    v0, n0 = _fwd_replay(m, local, 3, len(ref))
+    m.set_option("coef_presum", 1)                             # clears the cached 3-D plan
+    v1, n1 = _fwd_replay(m, local, 3, len(ref))
+    assert _close(v0, ref) and _close(v1, ref) and n0 >= 1 and n1 >= 1
+
+
 @pytest.mark.parametrize("name,degree", CASES)
 def test_adjoint_plan_replay(oracle, name, degree):
     """Mirrors k_tile_adj: staged row segments + gidx must deliver dvals[slot_nnz[e,p,q]] to every owned element."""
