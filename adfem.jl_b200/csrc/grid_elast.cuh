@@ -250,10 +250,15 @@ ADFEM_HD void ge_store_cell_row_plane(int lane, const QuadRule& rule, int m, int
 }
 
 #ifdef __CUDACC__
+// L2 prefetch of a contiguous run of doubles [p, p + count), one 128-byte line per lane and step (no effect on results)
+__device__ __forceinline__ void ge_prefetch_run(int lane, const double* p, long long count) {
+  for (long long o = 16LL * lane; o < count; o += 16 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 // Forward kernel: node rows [0, n], strips of 32 node columns; a warp handles `rows_per_warp` consecutive node rows of one strip.
 // PLANE: the tangents come from the moduli (coef = E, coef2 = nu, mode = 0 | 1) instead of from H (coef).
 template <bool PLANE>
-__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
+__global__ void __launch_bounds__(GE_WARPS * 32, 3) k_grid_elast_fwd(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
                                                                   const double* __restrict__ coef, const double* __restrict__ coef2, double* __restrict__ vals) {
   extern __shared__ __align__(16) double ge_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, m = gt.m, n = gt.n;
@@ -271,8 +276,15 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, Gr
   };
   load(i0 - 1, P);
   long long rowbase = grid_rowptr(i0, 0, m, n);
+  const int pc0 = j0 > 0 ? j0 - 1 : 0, pc1 = ge_min(j0 + GE_COLS, m);            // cell columns of the strip that exist
+  const int per_cell = PLANE ? 2 * GE_G : 2 * GE_G * 9;                          // doubles per cell in coef (and coef2)
   for (int i = i0; i < i1; i++) {
     load(i, C);
+    if (i + 2 < n && i + 2 <= i1 && pc1 > pc0) {                                 // the run cell row i+2 will read: in L2 by the time it is needed
+      const size_t off = ((size_t)(i + 2) * m + pc0) * per_cell;
+      ge_prefetch_run(lane, coef + off, (long long)(pc1 - pc0) * per_cell);
+      if (PLANE) ge_prefetch_run(lane, coef2 + off, (long long)(pc1 - pc0) * per_cell);
+    }
     __syncwarp();
     ge_node(lane, dm.heron, gt, i, j0, P, C, stage);
     __syncwarp();
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_fwd(DevMesh dm, Gr
 // Adjoint kernel: cell rows [0, n), strips of 32 cell columns; a warp handles `rows_per_warp` consecutive cell rows of one strip.
 // PLANE: gradients with respect to the moduli (E, nu in; grad = dE, grad2 = dnu) instead of with respect to H.
 template <bool PLANE>
-__global__ void __launch_bounds__(GE_WARPS * 32) k_grid_elast_adj(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
+__global__ void __launch_bounds__(GE_WARPS * 32, 2) k_grid_elast_adj(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
                                                                   const double* __restrict__ E, const double* __restrict__ nu,
                                                                   const double* __restrict__ dvals, double* __restrict__ grad, double* __restrict__ grad2) {
   extern __shared__ __align__(16) double ge_smem[];
