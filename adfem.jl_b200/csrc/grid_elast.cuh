@@ -316,6 +316,13 @@ __global__ void __launch_bounds__(GE_WARPS * 32, 2) k_grid_elast_adj(DevMesh dm,
   for (int ci = r0; ci < r1; ci++) {
     rowbase += ge_prefix(m + 1, m, ci > 0, ci < n);          // CSR offset of node row ci + 1
     ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
+    if (ci + 2 <= n && ci + 2 <= r1) {                       // the two runs node row ci+2 will read (it has a row below: A = 1)
+      const int B2 = ci + 2 < n, pb = ge_prefix(c0, m, 1, B2);
+      const long long cnt = 2LL * (ge_prefix(ge_min(c0 + GE_COLS + 1, m + 1), m, 1, B2) - pb);
+      const long long rb2 = rowbase + ge_prefix(m + 1, m, 1, ci + 1 < n);      // CSR offset of node row ci + 2
+      ge_prefetch_run(lane, dvals + 2 * (rb2 + pb), cnt);
+      ge_prefetch_run(lane, dvals + 2 * (nnz + rb2 + pb), cnt);
+    }
     __syncwarp();
     ge_cell_adjoint(lane, dm.heron, gt, ci, c0, lo, hi, gst);
     __syncwarp();
