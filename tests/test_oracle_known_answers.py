@@ -416,3 +416,13 @@ def test_quad_scalar_siblings_known_answers(oracle):
     assert abs(oracle.quad_mass_bwd(g, m, n, h) @ K - g @ oracle.quad_mass_fwd(K, m, n, h)[2]) < 1e-12
     w = rng.standard_normal(N)
     assert abs(oracle.quad_source_bwd(w, m, n, h) @ f - w @ rhs) < 1e-12
+
+
+def test_plane_stress_matrix_published_value(oracle):
+    """docs/src/inverse.md:27 prints the reference H of the poroelasticity example, compute_plane_stress_matrix(E = 1, nu = 0.35), to six decimals:
+    [[1.604938, 0.864198, 0], [0.864198, 1.604938, 0], [0, 0, 0.37037]].  Pins mode 1 of the PlaneStrainAndStress op (and which of the two
+    reference formulas carries which name)."""
+    H = oracle.plane_matrix_fwd([1.0], [0.35], 1)[0]
+    ref = np.array([[1.604938, 0.864198, 0.0], [0.864198, 1.604938, 0.0], [0.0, 0.0, 0.37037]])
+    assert np.abs(H - ref).max() < 6e-7
+    assert np.abs(oracle.plane_matrix_fwd([1.0], [0.35], 0)[0] - ref).max() > 0.1          # mode 0 is the other matrix
