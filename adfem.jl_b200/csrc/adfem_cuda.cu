@@ -843,6 +843,8 @@ DofAdjacency dof_adjacency(const adfem_mesh* m) { return DofAdjacency{m->d_adj_p
 int gp_apply(adfem_mesh* m, const GpKind& k, bool to_gauss, const double* in, double* out, cudaStream_t st) {
   if (to_gauss) return launch_gp_gather(dev_mesh(m, m->opt_area_coo), m->hm.degree, k.basis, k.weighted, in, out, st);
   if (int rc = ensure_pattern(m)) return rc;
+  if (use_grid(m) && m->hm.degree == 1)      // structured triangulation: index arithmetic instead of the adjacency (grid_gauss.cuh)
+    return launch_grid_gp_scatter(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, k.basis, k.weighted, in, out, st);
   return launch_gp_scatter(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), k.basis, k.weighted, in, out, st);
 }
 }  // namespace
@@ -878,6 +880,8 @@ int adfem_gauss_op_adjoint(adfem_mesh* m, int kind, const double* grad_out, doub
 int adfem_laplace_term(adfem_mesh* m, const double* nu, const double* u, double* out, void* stream) {
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
+  if (use_grid(m) && m->hm.degree == 1)
+    return launch_grid_laplace_term(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, u, out, (cudaStream_t)stream);
   return launch_laplace_term(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), nu, u, out, (cudaStream_t)stream);
 }
 
@@ -888,7 +892,13 @@ int adfem_laplace_term_adjoint(adfem_mesh* m, const double* nu, const double* u,
   const DevMesh dm = dev_mesh(m, m->opt_area_coo);
   if (grad_nu) { if (int rc = launch_laplace_term_grad_nu(dm, m->hm.degree, u, grad_out, grad_nu, (cudaStream_t)stream)) return rc; }
   // the term is symmetric in (u, v): d/du of grad_out . K(nu) u is K(nu) grad_out
-  if (grad_u) { if (int rc = launch_laplace_term(dm, m->hm.degree, dof_adjacency(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc; }
+  if (grad_u) {
+    if (use_grid(m) && m->hm.degree == 1) {
+      if (int rc = launch_grid_laplace_term(dm, GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
+    } else {
+      if (int rc = launch_laplace_term(dm, m->hm.degree, dof_adjacency(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
+    }
+  }
   return 0;
 }
 

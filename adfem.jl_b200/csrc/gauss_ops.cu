@@ -6,6 +6,7 @@
 #include <string>
 
 #include "gauss_ops.cuh"
+#include "grid_gauss.cuh"
 #include "internal.h"
 
 namespace adfem {
@@ -54,6 +55,23 @@ __global__ void k_plane_matrix_grad(int mode, long long n, const double* __restr
                                     const double* __restrict__ gH, double* __restrict__ gE, double* __restrict__ gnu) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) plane_matrix_grad_body(mode, E[i], nu[i], gH + 9 * i, gE + i, gnu + i);
+}
+
+// structured triangulation: one thread per node, node id = i*(m+1) + j
+template <int B, bool W>
+__global__ void __launch_bounds__(GP_THREADS) k_grid_gp_scatter(DevMesh m, GridTri gt, const double* __restrict__ in, double* __restrict__ out) {
+  constexpr int NC = GpShape<2, 1, B>::NC;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, nn = (long long)(gt.m + 1) * (gt.n + 1);
+  if (r >= nn) return;
+  double acc[NC];
+  grid_scatter_node<B, W>(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), in, acc);
+#pragma unroll
+  for (int c = 0; c < NC; c++) out[r + c * nn] = acc[c];
+}
+__global__ void __launch_bounds__(GP_THREADS) k_grid_laplace_term(DevMesh m, GridTri gt, const double* __restrict__ nu, const double* __restrict__ u,
+                                                                   double* __restrict__ out) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, nn = (long long)(gt.m + 1) * (gt.n + 1);
+  if (r < nn) out[r] = grid_laplace_term_node(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), nu, u);
 }
 
 __global__ void k_presum_coef(DevMesh m, int ns2, long long n, const double* __restrict__ coef, double* __restrict__ hbar) {
@@ -155,6 +173,25 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
   if (n <= 0) return 0;
   k_plane_matrix_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mode, n, E, nu, grad_H, grad_E, grad_nu);
   return launched("plane matrix gradient kernel");
+}
+
+int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st) {
+  const long long nn = (long long)(gt.m + 1) * (gt.n + 1);
+  const unsigned nb = gp_blocks(nn);
+  if (basis < GB_P1SHAPE || basis > GB_STRAIN || (weighted && basis != GB_STRAIN)) return fail("gauss-point scatter: unknown operator");
+  switch (basis) {
+    case GB_P1SHAPE: k_grid_gp_scatter<GB_P1SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    case GB_SHAPE: k_grid_gp_scatter<GB_SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    case GB_GRAD: k_grid_gp_scatter<GB_GRAD, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    default:
+      if (weighted) k_grid_gp_scatter<GB_STRAIN, true><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
+      else k_grid_gp_scatter<GB_STRAIN, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
+  }
+  return launched("structured gauss-point scatter kernel");
+}
+int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st) {
+  k_grid_laplace_term<<<gp_blocks((long long)(gt.m + 1) * (gt.n + 1)), GP_THREADS, 0, st>>>(dm, gt, nu, u, out);
+  return launched("structured Laplace term kernel");
 }
 
 int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st) {

@@ -92,51 +92,79 @@ ADFEM_HD void gp_gather_body(const DevMesh& m, int e, const double* in, double* 
 }
 
 // ---- scatter: Gauss-point values -> ONE dof row (all NC components) ------------------------------------------------------
-// acc[c] = sum over incident (e, p), Gauss points k and values i of C_ic(p, k) * s[(e*g + k)*NQ + i] (* w_k)
+// contribution of element (geometry G, Gauss-point values se[k*NQ + i]) to the row of its local dof p:
+// acc[c] += sum over k, i of C_ic(p, k) * se[k*NQ + i] (* w_k)
 template <int DIM, int DEG, int B, bool W>
-ADFEM_HD void gp_scatter_row(const DevMesh& m, const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, int r,
-                             const double* s, double* acc) {
+ADFEM_HD void gp_scatter_elem(const Geom<DIM>& G, const QuadRule& rule, int g, int p, const double* se, double* acc) {
   using S = GpShape<DIM, DEG, B>;
   constexpr int D = S::D, NQ = S::NQ, NC = S::NC;
+  for (int k = 0; k < g; k++) {
+    double L[DIM + 1]; bary<DIM>(rule, k, L);
+    const double* sk = se + (size_t)k * NQ;
+    const double w = W ? rule.w[k] * G.wscale : 1.0;
+    if (B == GB_P1SHAPE) {
+      acc[0] += pick<DIM + 1>(L, p) * ldg(sk) * w;
+    } else if (B == GB_SHAPE) {
+      double phi[D]; basis_val<DIM, DEG>(L, phi);
+      acc[0] += pick<D>(phi, p) * ldg(sk) * w;
+    } else {
+      double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
+      double gs[DIM];
 #pragma unroll
-  for (int c = 0; c < NC; c++) acc[c] = 0.0;
-  for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
-    const int e = adj_elem[a], p = adj_loc[a];
-    Geom<DIM> G; load_geom(m, e, G);
-    for (int k = 0; k < m.g; k++) {
-      double L[DIM + 1]; bary<DIM>(m.rule, k, L);
-      const double* sk = s + ((size_t)e * m.g + k) * NQ;
-      const double w = W ? m.rule.w[k] * G.wscale : 1.0;
-      if (B == GB_P1SHAPE) {
-        acc[0] += pick<DIM + 1>(L, p) * ldg(sk) * w;
-      } else if (B == GB_SHAPE) {
-        double phi[D]; basis_val<DIM, DEG>(L, phi);
-        acc[0] += pick<D>(phi, p) * ldg(sk) * w;
+      for (int i = 0; i < DIM; i++) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) v = (q == p) ? gp[q][i] : v;
+        gs[i] = v;
+      }
+      double sv[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; i++) sv[i] = ldg(sk + i);
+      if (B == GB_GRAD) {
+        acc[0] += dotg<DIM>(gs, sv) * w;
       } else {
-        double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
-        double gs[DIM];
 #pragma unroll
-        for (int i = 0; i < DIM; i++) {
-          double v = 0.0;
-#pragma unroll
-          for (int q = 0; q < D; q++) v = (q == p) ? gp[q][i] : v;
-          gs[i] = v;
-        }
-        double sv[NQ];
-#pragma unroll
-        for (int i = 0; i < NQ; i++) sv[i] = ldg(sk + i);
-        if (B == GB_GRAD) {
-          acc[0] += dotg<DIM>(gs, sv) * w;
-        } else {
-#pragma unroll
-          for (int c = 0; c < NC; c++) acc[c] += bdot<DIM>(c, gs, sv) * w;
-        }
+        for (int c = 0; c < NC; c++) acc[c] += bdot<DIM>(c, gs, sv) * w;
       }
     }
   }
 }
 
+// acc[c] = sum over the incident (e, p) of row r, in ascending element order
+template <int DIM, int DEG, int B, bool W>
+ADFEM_HD void gp_scatter_row(const DevMesh& m, const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, int r,
+                             const double* s, double* acc) {
+  using S = GpShape<DIM, DEG, B>;
+#pragma unroll
+  for (int c = 0; c < S::NC; c++) acc[c] = 0.0;
+  for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
+    const int e = adj_elem[a], p = adj_loc[a];
+    Geom<DIM> G; load_geom(m, e, G);
+    gp_scatter_elem<DIM, DEG, B, W>(G, m.rule, m.g, p, s + (size_t)e * m.g * S::NQ, acc);
+  }
+}
+
 // ---- Laplace term: out[r] = sum over incident (e, p), k of nu[e,k] w_k grad phi_p . (sum_q grad phi_q u[dof_q]) -------------
+// contribution of one element (geometry G, coefficients nue[k], dof values ul[q]) to the row of its local dof p
+template <int DIM, int DEG>
+ADFEM_HD double laplace_term_elem(const Geom<DIM>& G, const QuadRule& rule, int g, int p, const double* nue, const double* ul) {
+  constexpr int D = ElemTraits<DIM, DEG>::D;
+  double acc = 0.0;
+  for (int k = 0; k < g; k++) {
+    double L[DIM + 1]; bary<DIM>(rule, k, L);
+    double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
+    double gu[DIM], gs[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+      double su = 0.0, v = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; q++) { su += gp[q][i] * ul[q]; v = (q == p) ? gp[q][i] : v; }
+      gu[i] = su; gs[i] = v;
+    }
+    acc += ldg(nue + k) * (rule.w[k] * G.wscale) * dotg<DIM>(gs, gu);
+  }
+  return acc;
+}
 template <int DIM, int DEG>
 ADFEM_HD double laplace_term_row(const DevMesh& m, const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, int r,
                                  const double* nu, const double* u) {
@@ -148,19 +176,7 @@ ADFEM_HD double laplace_term_row(const DevMesh& m, const long long* adj_ptr, con
     double ul[D];
 #pragma unroll
     for (int q = 0; q < D; q++) ul[q] = ldg(u + ldg(m.conn + (size_t)q * m.ne + e));
-    for (int k = 0; k < m.g; k++) {
-      double L[DIM + 1]; bary<DIM>(m.rule, k, L);
-      double gp[D][DIM]; basis_grad<DIM, DEG>(G, L, gp);
-      double gu[DIM], gs[DIM];
-#pragma unroll
-      for (int i = 0; i < DIM; i++) {
-        double su = 0.0, v = 0.0;
-#pragma unroll
-        for (int q = 0; q < D; q++) { su += gp[q][i] * ul[q]; v = (q == p) ? gp[q][i] : v; }
-        gu[i] = su; gs[i] = v;
-      }
-      acc += ldg(nu + (size_t)e * m.g + k) * (m.rule.w[k] * G.wscale) * dotg<DIM>(gs, gu);
-    }
+    acc += laplace_term_elem<DIM, DEG>(G, m.rule, m.g, p, nu + (size_t)e * m.g, ul);
   }
   return acc;
 }

@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "device_fem.cuh"
+#include "grid_index.cuh"
 
 namespace adfem {
 
@@ -25,6 +26,10 @@ int launch_laplace_term_grad_nu(const DevMesh& dm, int degree, const double* u, 
 int launch_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H, cudaStream_t st);
 int launch_plane_matrix_grad(int mode, long long n, const double* E, const double* nu, const double* grad_H, double* grad_E, double* grad_nu,
                              cudaStream_t st);
+
+// structured triangulation Mesh(m, n, h), P1 (grid_gauss.cuh): index-free versions of the scatter-type kernels
+int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st);
+int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st);
 
 // option "coef_presum" (P1 elasticity): hbar[ne*ns2] = sum_k w_k coef[(e*g+k)*ns2 + c]; grad[(e*g+k)*ns2 + c] = w_k gbar[e*ns2 + c]
 int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st);

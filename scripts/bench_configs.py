@@ -159,6 +159,8 @@ def main():
         n = int(1000 * s)
         c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)
         for tag, m in (("P2_unstructured", A.Mesh(c, e, degree=2)), ("P1_grid", A.Mesh(int(2048 * s), int(2048 * s), 1.0 / int(2048 * s)))):
+            for k, v in OPTS.items():
+                m.set_option(k, v)
             for kind, name in enumerate(("fem_to_gauss", "dof_to_gauss", "grad", "strain", "strain_energy")):
                 nin, nout = L.adfem_gauss_op_len(m.handle, kind, 0), L.adfem_gauss_op_len(m.handle, kind, 1)
                 x = torch.rand(nin, dtype=torch.float64, device="cuda")

@@ -19,6 +19,8 @@ timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structur
 echo "config 3 fused moduli, structured kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3f_gridelast_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
 echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
+timeout 600 python scripts/bench_configs.py --cases gp --steps 10 --opt structured=0 > gpurun_out/gp_general_$TAG.jsonl 2> gpurun_out/gp_general_$TAG.err
+echo "gauss-point ops, general kernels on the structured mesh rc=$?"; grep P1_grid gpurun_out/gp_general_$TAG.jsonl | cut -c1-260
 # one full capture of the new kernels (scatter / Laplace term are the ones expected to need work)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gp_scatter|k_laplace_term|k_presum|k_expand" -c 8 -f -o gpurun_out/prof_gp_$TAG \
   python scripts/bench_configs.py --cases gp --steps 1 --scale 0.5 > gpurun_out/prof_gp_$TAG.log 2>&1

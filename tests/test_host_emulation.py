@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_index.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -321,3 +321,33 @@ def test_structured_elasticity_warp_phases(emul, oracle, m, n, rpw, heron):
         assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(gE),
                                         C.c_int(mode), d(E), d(nu), d(gnu)) == 0
         close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)
+
+
+@pytest.mark.parametrize("m,n", [(5, 4), (1, 1), (9, 2)])
+def test_structured_scatter_operators(emul, oracle, m, n):
+    """grid_gauss.cuh: the scatter-type operators on Mesh(m, n, h) as one thread per node with index arithmetic — against the oracle, and
+    bit-identical to the general adjacency-walking bodies (same summation order, same geometry)."""
+    rng = np.random.default_rng(m * 10 + n)
+    xs = np.concatenate([[0.0], np.cumsum(rng.random(m) * 0.1 + 0.05)])
+    ys = np.concatenate([[0.3], 0.3 + np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    _, e = meshgen.tri_grid(m, n, 1.0)
+    c = np.stack([np.tile(xs, n + 1), np.repeat(ys, m + 1)], 1)
+    o = oracle.Mesh2D(c, e)
+    T = HostTables(o)
+    G, nd = o.ngauss, o.ndof
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    cases = [   # basis, weighted, input length, output length, oracle, general-path kind / adjoint flag
+        (0, 0, G, nd, o.fem_to_gauss_bwd, FEM_TO_GAUSS, True), (1, 0, G, nd, o.dof_to_gauss_bwd, DOF_TO_GAUSS, True),
+        (2, 0, 2 * G, nd, o.grad_bwd, GRAD, True), (3, 0, 3 * G, 2 * nd, o.strain_bwd, STRAIN, True),
+        (3, 1, 3 * G, 2 * nd, o.strain_energy_fwd, STRAIN_ENERGY, False)]
+    for basis, weighted, nin, nout, ref, kind, adjoint in cases:
+        x = rng.standard_normal(nin)
+        out = np.full(nout, np.nan)
+        assert emul.emul_grid_gp_scatter(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(1), C.c_int(basis), C.c_int(weighted), d(x), d(out)) == 0
+        close(out, ref(x))
+        assert np.array_equal(out, T.gauss_op(emul, kind, adjoint, x, nout))
+    nu, u = rng.random(G) + 0.5, rng.standard_normal(nd)
+    out = np.full(nd, np.nan)
+    assert emul.emul_grid_laplace_term(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(1), d(nu), d(u), d(out)) == 0
+    close(out, o.laplace_term_fwd(nu, u))
+    assert np.array_equal(out, T.laplace_term(emul, nu, u))

@@ -317,3 +317,36 @@ def test_structured_elasticity_kernels(oracle, m, n):
             close(npy(T.values), refm)
             gE, gnu = torch.autograd.grad(T.values, [Et, nt], dev(dv))
             close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
+
+
+def test_structured_scatter_operators(oracle):
+    """Scatter-type Gauss-point operators and the Laplace term on Mesh(m, n, h): the index-free one-thread-per-node kernels (grid_gauss.cuh,
+    option "structured" = 1, the default) against the oracle, and bit-identical to the general adjacency-walking kernels ("structured" = 0)."""
+    rng = np.random.default_rng(61)
+    m_, n_ = 45, 31
+    ms, o = A.Mesh(m_, n_, 0.05), oracle.Mesh2D(*meshgen.tri_grid(m_, n_, 0.05))
+    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == 1
+    G, nd = o.ngauss, o.ndof
+    nu, u, go, sig = rng.random(G) + 0.5, rng.standard_normal(nd), rng.standard_normal(nd), rng.standard_normal((G, 3))
+    w1, w2, w3 = rng.standard_normal(G), rng.standard_normal((G, 2)), rng.standard_normal((G, 3))
+    res = {}
+    for on in (1, 0):
+        ms.set_option("structured", on)
+        ut, nt = dev(u).requires_grad_(True), dev(nu).requires_grad_(True)
+        term = A.compute_fem_laplace_term1(ut, nt, ms)
+        gu, gnu = torch.autograd.grad(term, [ut, nt], dev(go))
+        se = A.compute_strain_energy_term(dev(sig), ms)
+        adj = []
+        for fn, x, w in ((A.fem_to_gauss_points, u, w1), (A.dof_to_gauss_points, u, w1), (A.eval_grad_on_gauss_pts1, u, w2),
+                         (A.eval_strain_on_gauss_pts, np.concatenate([u, go]), w3)):
+            xt = dev(x).requires_grad_(True)
+            (g,) = torch.autograd.grad(fn(xt, ms), xt, dev(w))
+            adj.append(npy(g))
+        res[on] = [npy(term), npy(gu), npy(gnu), npy(se)] + adj
+    ms.set_option("structured", 1)
+    rnu, ru = o.laplace_term_bwd(go, nu, u)
+    refs = [o.laplace_term_fwd(nu, u), ru, rnu, o.strain_energy_fwd(sig.reshape(-1)), o.fem_to_gauss_bwd(w1), o.dof_to_gauss_bwd(w1),
+            o.grad_bwd(w2.reshape(-1)), o.strain_bwd(w3.reshape(-1))]
+    for a, b, r in zip(res[1], res[0], refs):
+        close(a, r)
+        assert np.array_equal(a, b)
