@@ -321,7 +321,8 @@ def test_structured_elasticity_kernels(oracle, m, n):
 
 def test_structured_scatter_operators(oracle):
     """Scatter-type Gauss-point operators and the Laplace term on Mesh(m, n, h): the index-free one-thread-per-node kernels (grid_gauss.cuh,
-    option "structured" = 1, the default) against the oracle, and bit-identical to the general adjacency-walking kernels ("structured" = 0)."""
+    option "structured" = 1, the default) against the oracle and against the general adjacency-walking kernels ("structured" = 0; on the host the
+    two bodies are bit-identical, tests/test_host_emulation.py)."""
     rng = np.random.default_rng(61)
     m_, n_ = 45, 31
     ms, o = A.Mesh(m_, n_, 0.05), oracle.Mesh2D(*meshgen.tri_grid(m_, n_, 0.05))
@@ -349,4 +350,4 @@ def test_structured_scatter_operators(oracle):
             o.grad_bwd(w2.reshape(-1)), o.strain_bwd(w3.reshape(-1))]
     for a, b, r in zip(res[1], res[0], refs):
         close(a, r)
-        assert np.array_equal(a, b)
+        close(a, b, rel=1e-13)       # same summation order and geometry; only the compiler's FMA contraction may differ between the two kernels
