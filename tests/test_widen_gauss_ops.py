@@ -107,12 +107,12 @@ def test_plane_matrices(oracle):
     for mode, fn in ((0, A.compute_plane_strain_matrix), (1, A.compute_plane_stress_matrix)):
         Et, nt = dev(E).requires_grad_(True), dev(nu).requires_grad_(True)
         H = fn(Et, nt)
-        close(npy(H), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-15)
+        close(npy(H), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-14)
         g = rng.standard_normal((N, 3, 3))
         gE, gnu = torch.autograd.grad(H, [Et, nt], dev(g))
         rE, rnu = oracle.plane_matrix_bwd(g, E, nu, mode)
         close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
-        close(fn(E, nu), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-15)
+        close(fn(E, nu), oracle.plane_matrix_fwd(E, nu, mode), rel=1e-14)
     # fused pre-step + assembly: H(E, nu) feeds the stiffness operator and the gradient reaches E
     c, e = meshgen.jitter_unstructured(9, 8, 0.1, seed=1)
     m, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
@@ -166,8 +166,8 @@ def test_legacy_symbols_gauss_ops(oracle):
     g = np.zeros(3 * G); L.ComputeStrainEnergyTermMfem_backward(d(g), d(w4)); close(g, o.strain_energy_bwd(w4))
     N = 50
     E, pr = rng.random(N) + 0.5, rng.random(N) * 0.45
-    H = np.zeros(9 * N); L.PlaneStrainMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 0), rel=1e-15)
-    H = np.zeros(9 * N); L.PlaneStressMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 1), rel=1e-15)
+    H = np.zeros(9 * N); L.PlaneStrainMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 0), rel=1e-14)
+    H = np.zeros(9 * N); L.PlaneStressMatrix_forward(d(H), d(E), d(pr), C.c_int(N)); close(H.reshape(N, 3, 3), oracle.plane_matrix_fwd(E, pr, 1), rel=1e-14)
     gH = rng.standard_normal(9 * N)
     gn, gE = np.zeros(N), np.zeros(N)
     L.PlaneStressMatrix_backward(d(gn), d(gE), d(gH), d(E), d(pr), C.c_int(N))
