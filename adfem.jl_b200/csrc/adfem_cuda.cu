@@ -18,6 +18,7 @@
 #include "plan.h"
 #include "tri_grid.cuh"
 #include "grid_elast.cuh"
+#include "tet_grid.cuh"
 
 using namespace adfem;
 
@@ -86,6 +87,13 @@ struct adfem_mesh {
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 0;                   // P1 elasticity on the structured triangulation: index-free kernels of grid_elast.cuh (off until measured on a GPU)
   DevBuf<double> grid_xs, grid_ys;
+  // structured tetrahedral grid Mesh3(n, n, l, h) (tet_grid.cuh): detected from the arrays; used by the opt-in elasticity forward kernel
+  bool tet_ok = false;
+  int tet_n = 0, tet_l = 0;
+  std::vector<double> tet_axes[3];
+  TetGridTables tet_tab;
+  DevBuf<double> tet_xs, tet_ys, tet_zs;
+  DevBuf<TetGridTables> d_tet_tab;
   // scratch and streams for the host-buffer calls (H2D, kernels, D2H)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t hev[2] = {nullptr, nullptr};
@@ -142,6 +150,67 @@ bool detect_tri_grid(const HostMesh& h, int& m, int& n, std::vector<double>& xs,
 }
 
 // the closed-form row pointers of tri_grid.cuh must reproduce the symbolic pattern exactly
+// Is this the reference's structured tetrahedral grid (src/MFEM3/MFEM.jl:124-185: 5 tetrahedra per cube, TE1 / TE2 by the parity of the cube) on
+// rectilinear coordinates?  The element's vertex SETS are compared (MFEM's orientation fix may have swapped the first two vertices).
+bool detect_tet_grid(const HostMesh& h, int& n, int& l, std::vector<double> ax[3]) {
+  if (h.dim != 3 || h.degree != 1 || h.g != 4 || h.nv < 8 || h.ne < 5) return false;
+  const double* c = h.coords.data();
+  long long n1 = 0;
+  for (long long t = 1; t < h.nv; t++) if (c[3 * t + 1] != c[1]) { n1 = t; break; }
+  if (n1 < 2 || h.nv % (n1 * n1) != 0) return false;
+  const long long l1 = h.nv / (n1 * n1);
+  n = (int)n1 - 1; l = (int)l1 - 1;
+  if (l < 1 || (long long)h.ne != 5LL * n * n * l) return false;
+  ax[0].resize(n1); ax[1].resize(n1); ax[2].resize(l1);
+  for (long long i = 0; i < n1; i++) { ax[0][i] = c[3 * i]; ax[1][i] = c[3 * (i * n1) + 1]; }
+  for (long long k = 0; k < l1; k++) ax[2][k] = c[3 * (k * n1 * n1) + 2];
+  for (int d = 0; d < 3; d++)
+    for (size_t t = 0; t + 1 < ax[d].size(); t++) if (!(ax[d][t] < ax[d][t + 1])) return false;
+  for (long long k = 0; k < l1; k++)
+    for (long long j = 0; j < n1; j++)
+      for (long long i = 0; i < n1; i++) {
+        const double* p = c + 3 * ((k * n1 + j) * n1 + i);
+        if (p[0] != ax[0][i] || p[1] != ax[1][j] || p[2] != ax[2][k]) return false;
+      }
+  for (int ci = 0; ci < n; ci++)
+    for (int cj = 0; cj < n; cj++)
+      for (int ck = 0; ck < l; ck++) {
+        const int (*TE)[4] = tet_grid_split_of(ci, cj, ck);
+        const long long cube = ((long long)ci * n + cj) * l + ck;
+        for (int t = 0; t < 5; t++) {
+          int want[4], have[4];
+          for (int q = 0; q < 4; q++) {
+            const int v = TE[t][q];
+            want[q] = (int)(((long long)(ck + (v >> 2)) * n1 + (cj + ((v >> 1) & 1))) * n1 + (ci + (v & 1)));
+            have[q] = h.verts[(size_t)(5 * cube + t) * 4 + q];
+          }
+          std::sort(want, want + 4); std::sort(have, have + 4);
+          for (int q = 0; q < 4; q++) if (want[q] != have[q]) return false;
+        }
+      }
+  return true;
+}
+// the closed-form rows of tet_grid.cuh must be the rows of the symbolic pattern
+bool tet_pattern_matches(const ScalarPattern& pat, const TetGridTables& tab, int n, int l) {
+  const GridTet gt{n, l, nullptr, nullptr, nullptr, &tab};
+  const long long n1 = n + 1;
+  if ((long long)pat.n != n1 * n1 * (l + 1)) return false;
+  for (int k = 0; k <= l; k++)
+    for (int j = 0; j <= n; j++)
+      for (int i = 0; i <= n; i++) {
+        const long long r = ((long long)k * n1 + j) * n1 + i;
+        const int mask = tg_row_mask(gt, (i + j + k) & 1, i, j, k);
+        if (tg_popc(mask) != (int)(pat.rowptr[r + 1] - pat.rowptr[r])) return false;
+        long long at = pat.rowptr[r];
+        for (int s = 0; s < 27; s++)
+          if ((mask >> s) & 1) {
+            const long long col = r + (long long)(s / 9 - 1) * n1 * n1 + (long long)((s / 3) % 3 - 1) * n1 + (s % 3 - 1);
+            if (pat.colind[at++] != col) return false;
+          }
+      }
+  return true;
+}
+
 bool grid_pattern_matches(const ScalarPattern& pat, int m, int n) {
   if (pat.n != (m + 1) * (n + 1)) return false;
   for (int i = 0; i <= n; i++)
@@ -164,6 +233,7 @@ int ensure_pattern(adfem_mesh* m) {
   if (!err.empty()) return fail("symbolic: " + err);
   m->has_pattern = true;
   if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;
+  if (m->tet_ok && !tet_pattern_matches(m->pat, m->tet_tab, m->tet_n, m->tet_l)) m->tet_ok = false;
   if (!m->host_only) {
     const HostMesh& h = m->hm;
     const int dd = h.d * h.d;
@@ -455,6 +525,21 @@ int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out
   return 0;
 }
 
+// P1 tetrahedral elasticity forward on the structured grid Mesh3(n, n, l, h) (tet_grid.cuh): Gauss-sum pre-pass, then one warp per node
+bool use_tet_grid(adfem_mesh* m, int op) {
+  return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && m->opt_structured && m->tet_ok && !m->host_only && m->hm.degree == 1;
+}
+int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st) {
+  if (int rc = ensure_presum_buf(m)) return rc;
+  if (int rc = launch_presum_coef(dev_mesh(m, m->opt_area_csr), 36, coef, m->presum_buf.p, st)) return rc;
+  const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
+  const size_t smem = (size_t)TG_WARPS * TG_WARP_DOUBLES * sizeof(double);
+  CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tet_grid_elast_fwd<<<blocks_for(m->hm.nv, TG_WARPS), TG_WARPS * 32, smem, st>>>(gt, m->pat.nnz, m->d_rowptr.p, m->presum_buf.p, vals);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int rows = adjoint ? gt.n : gt.n + 1;
@@ -505,6 +590,8 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
   m->host_only = (flags & ADFEM_HOST_ONLY) != 0;
   std::vector<double> grid_xs, grid_ys;
   m->grid_ok = detect_tri_grid(m->hm, m->grid_m, m->grid_n, grid_xs, grid_ys);
+  m->tet_ok = detect_tet_grid(m->hm, m->tet_n, m->tet_l, m->tet_axes);
+  if (m->tet_ok) build_tet_grid_tables(m->tet_tab);
   if (!m->host_only) {
     if (adfem_device_count() == 0) return fail("no CUDA device available (libadfem_cuda has no CPU fallback)");
     CU_TRY(cudaGetDevice(&m->device));
@@ -521,6 +608,10 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
     m->dm.dim = h.dim; m->dm.ne = h.ne; m->dm.nv = h.nv; m->dm.d = h.d; m->dm.g = h.g; m->dm.ndof = h.ndof;
     m->dm.coords = m->coords.p; m->dm.verts = m->verts.p; m->dm.conn = m->conn.p; m->dm.rule = h.rule;
     if (m->grid_ok) { CU_TRY(upload(m->grid_xs, grid_xs)); CU_TRY(upload(m->grid_ys, grid_ys)); }
+    if (m->tet_ok) {
+      CU_TRY(upload(m->tet_xs, m->tet_axes[0])); CU_TRY(upload(m->tet_ys, m->tet_axes[1])); CU_TRY(upload(m->tet_zs, m->tet_axes[2]));
+      CU_TRY(upload(m->d_tet_tab, std::vector<TetGridTables>(1, m->tet_tab)));
+    }
   }
   *out = m.release();
   return 0;
@@ -549,7 +640,7 @@ long long adfem_mesh_info(const adfem_mesh* m, int what) {
       for (auto& kv : m->adj_plans) b += (long long)kv.second->bytes;
       return b;
     }
-    case ADFEM_INFO_STRUCTURED: return m->grid_ok ? 1 : 0;
+    case ADFEM_INFO_STRUCTURED: return m->grid_ok ? 1 : (m->tet_ok ? 2 : 0);
     default: return -1;
   }
 }
@@ -671,6 +762,8 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
   if ((op != ADFEM_OP_STIFFNESS || m->opt_grid_elast) && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
   if (use_grid_elast(m, op)) return launch_grid_elast(m, false, coef, vals, st);
+  if (m->tet_ok && m->opt_grid_elast && op == ADFEM_OP_STIFFNESS) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
+  if (use_tet_grid(m, op)) return launch_tet_grid_fwd(m, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   FwdPlanDev* P = nullptr;

@@ -1,0 +1,127 @@
+// Forward CSR assembly of the P1 tetrahedral ELASTICITY operator (3-D extension of ComputeFemStiffnessMatrixMfem, 6x6 Voigt tangent per Gauss
+// point) on the reference's structured grid `Mesh3(n, n, l, h)` — BASELINE config 5 — without tile blobs, connectivity or coordinates.
+//
+// Input: the Gauss-summed tangents Hbar_e = sum_k w_k H_{e,k} (36 doubles per tetrahedron) produced by the streaming pre-pass of option
+// "coef_presum" (gauss_ops.cu, k_presum_coef).  One WARP per node:
+//   phase 1  lane t evaluates the 3 x 12 row block of the node in its t-th incident tetrahedron (8 or 32 of them, by the parity of i+j+k,
+//            tet_grid_tables.h) from Hbar and the rectilinear coordinates, and parks it in shared memory;
+//   phase 2  the (up to) 19 x 9 values of the node's three CSR rows are gathered from those blocks in ascending element order (the summation
+//            order of the general tile kernels) into CSR order;
+//   phase 3  the three contiguous runs (component a = 0, 1, 2) are written with coalesced stores.
+// Row pointers are read from the scalar pattern (8 B per node); column positions are index arithmetic.
+// CSR layout as everywhere: scalar row r (start rs, length len) holds entry (a, b, j) at 3*(a*nnz + rs) + b*len + j.
+// All phases are __host__ __device__ functions of the lane index (tests/host_emul/).  The adjoint still runs through the general tile kernel.
+#pragma once
+#include "device_fem.cuh"
+#include "tet_grid_tables.h"
+
+namespace adfem {
+
+struct GridTet {
+  int n, l;                 // cubes in x and y (n) and in z (l); node (i, j, k) = k*(n+1)^2 + j*(n+1) + i, cube (ci, cj, ck) = (ci*n + cj)*l + ck
+  const double* xs;         // n+1, n+1, l+1 node coordinates per axis
+  const double* ys;
+  const double* zs;
+  const TetGridTables* tab;
+};
+
+constexpr int TG_BLK = 36;                        // row block of one tetrahedron: [a][q][b]
+constexpr int TG_WARP_DOUBLES = 32 * TG_BLK + 3 * 27 * 3;
+constexpr int TG_WARPS = 8;
+
+// 27-bit mask of the row slots of node (i, j, k) that exist: structurally present for its parity and inside the grid
+ADFEM_HD int tg_row_mask(const GridTet& gt, int par, int i, int j, int k) {
+  int mask = 0;
+  for (int s = 0; s < 27; s++) {
+    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+    const bool in = i + di >= 0 && i + di <= gt.n && j + dj >= 0 && j + dj <= gt.n && k + dk >= 0 && k + dk <= gt.l;
+    if (in && ((gt.tab->present[par] >> s) & 1)) mask |= 1 << s;
+  }
+  return mask;
+}
+ADFEM_HD int tg_popc(int x) { int c = 0; for (; x; x &= x - 1) c++; return c; }
+
+// phase 1: lane t -> tb[t*36 + (a*4 + q)*3 + b] = bvec(a, g_p)^T (Hbar |det|) bvec(b, g_q); zeros when the tetrahedron does not exist
+ADFEM_HD void tg_tet_block(int lane, const GridTet& gt, int par, int i, int j, int k, const double* hbar, double* tb) {
+  const TetGridTables& T = *gt.tab;
+  double* out = tb + lane * TG_BLK;
+  const int ci = i + T.inc[par][lane][0], cj = j + T.inc[par][lane][1], ck = k + T.inc[par][lane][2];
+  if (lane >= T.ninc[par] || ci < 0 || ci >= gt.n || cj < 0 || cj >= gt.n || ck < 0 || ck >= gt.l) {
+    for (int c = 0; c < TG_BLK; c++) out[c] = 0.0;
+    return;
+  }
+  double X[4][3];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    X[q][0] = ldg(gt.xs + i + T.voff[par][lane][q][0]);
+    X[q][1] = ldg(gt.ys + j + T.voff[par][lane][q][1]);
+    X[q][2] = ldg(gt.zs + k + T.voff[par][lane][q][2]);
+  }
+  Geom<3> G; geom_tet(X, G);
+  const double ws = G.wscale < 0 ? -G.wscale : G.wscale;          // the table order is the generator's, before MFEM's orientation fix
+  const double* he = hbar + ((size_t)5 * (((size_t)ci * gt.n + cj) * gt.l + ck) + T.inc[par][lane][3]) * 36;
+  double H[36];
+#pragma unroll
+  for (int c = 0; c < 36; c++) H[c] = ldg(he + c) * ws;
+  const int p = T.inc[par][lane][4];
+  double gp[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) v = (q == p) ? G.gL[q][c] : v;
+    gp[c] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      double hb[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) hb[r] = bdot<3>(b, G.gL[q], &H[6 * r]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[(a * 4 + q) * 3 + b] = bdot<3>(a, gp, hb);
+    }
+}
+
+// phase 2: the existing slots of the three rows into stage[a*81 + b*len + pos]
+ADFEM_HD void tg_gather_rows(int lane, const GridTet& gt, int par, int mask, const double* tb, double* stage) {
+  const TetGridTables& T = *gt.tab;
+  const int len = tg_popc(mask);
+  for (int idx = lane; idx < 27 * 9; idx += 32) {
+    const int s = idx / 9, ab = idx - 9 * s, a = ab / 3, b = ab - 3 * a;
+    if (!((mask >> s) & 1)) continue;
+    double v = 0.0;
+    for (int c = 0; c < T.nsrc[par][s]; c++) v += tb[T.src[par][s][c][0] * TG_BLK + (a * 4 + T.src[par][s][c][1]) * 3 + b];
+    stage[a * 81 + b * len + tg_popc(mask & ((1 << s) - 1))] = v;
+  }
+}
+
+// phase 3: three contiguous runs of 3*len values; rs = rowptr[node]
+ADFEM_HD void tg_store_rows(int lane, long long rs, int len, long long nnz, const double* stage, double* vals) {
+  for (int a = 0; a < 3; a++) {
+    double* out = vals + 3 * ((long long)a * nnz + rs);
+    for (int idx = lane; idx < 3 * len; idx += 32) out[idx] = stage[a * 81 + idx];
+  }
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt, long long nnz, const long long* __restrict__ rowptr,
+                                                                      const double* __restrict__ hbar, double* __restrict__ vals) {
+  extern __shared__ __align__(16) double tg_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long node = (long long)blockIdx.x * TG_WARPS + wib, n1 = gt.n + 1;
+  if (node >= n1 * n1 * (gt.l + 1)) return;
+  const int i = (int)(node % n1), j = (int)((node / n1) % n1), k = (int)(node / (n1 * n1)), par = (i + j + k) & 1;
+  double* tb = tg_smem + (size_t)wib * TG_WARP_DOUBLES;
+  double* stage = tb + 32 * TG_BLK;
+  tg_tet_block(lane, gt, par, i, j, k, hbar, tb);
+  const int mask = tg_row_mask(gt, par, i, j, k);
+  __syncwarp();
+  tg_gather_rows(lane, gt, par, mask, tb, stage);
+  __syncwarp();
+  tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
+}
+#endif
+
+}  // namespace adfem

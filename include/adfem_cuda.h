@@ -134,7 +134,9 @@ enum { ADFEM_INFO_DIM = 0, ADFEM_INFO_NV, ADFEM_INFO_NE, ADFEM_INFO_NDOF, ADFEM_
        ADFEM_INFO_NEDGES, ADFEM_INFO_GAUSS_PER_ELEM, ADFEM_INFO_NNZ_SCALAR, ADFEM_INFO_TILES_FWD, ADFEM_INFO_TILES_ADJ,
        ADFEM_INFO_PLAN_BYTES,
        ADFEM_INFO_STRUCTURED /* 1: the mesh is the structured triangulation Mesh(m,n,h) v1 on rectilinear nodes and the scalar CSR
-                                operators use the index-free kernels of csrc/tri_grid.cuh (option "structured" = 0 disables) */ };
+                                operators use the index-free kernels of csrc/tri_grid.cuh (option "structured" = 0 disables);
+                                2: the mesh is the structured tetrahedral grid Mesh3(n,n,l,h) on rectilinear nodes (csrc/tet_grid.cuh, used by
+                                the elasticity forward under option "structured_elasticity") */ };
 
 /* Replaces init_nnfem_mesh / init_nnfem_mesh3 (deps/MFEM/API.cpp:4, deps/MFEM3/API.cpp:4) without the
  * process-global singleton.  dim = 2|3; vertices: nv rows of `vertex_stride` doubles (first `dim` used);

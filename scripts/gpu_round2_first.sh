@@ -15,6 +15,8 @@ for P in 0 1; do
 done
 timeout 600 python scripts/bench_configs.py --cases 3 --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3_gridelast_$TAG.jsonl 2> gpurun_out/cfg3_gridelast_$TAG.err
 echo "config 3 structured elasticity kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3_gridelast_$TAG.jsonl
+timeout 600 python scripts/bench_configs.py --cases 5 --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg5_tetgrid_$TAG.jsonl 2> gpurun_out/cfg5_tetgrid_$TAG.err
+echo "config 5 structured tetrahedral forward rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg5_tetgrid_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3f_gridelast_$TAG.jsonl 2> gpurun_out/cfg3f_gridelast_$TAG.err
 echo "config 3 fused moduli, structured kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3f_gridelast_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
@@ -32,6 +34,6 @@ if [ "${GPUS:-1}" -gt 1 ]; then
   echo "multi-GPU configs rc=$?"; cut -c1-400 gpurun_out/dist_cfg_${GPUS}gpu_$TAG.jsonl
 fi
 # one full capture of the structured elasticity kernels (config 3 at half size)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_grid_elast -s 4 -c 2 -f -o gpurun_out/prof_gridelast_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_grid_elast|k_tet_grid" -s 4 -c 2 -f -o gpurun_out/prof_gridelast_$TAG \
   python scripts/bench_configs.py --cases 3 --steps 2 --scale 0.5 --opt structured_elasticity=1 > gpurun_out/prof_gridelast_$TAG.log 2>&1
 echo "ncu (structured elasticity kernels) rc=$?"

@@ -10,6 +10,7 @@
 #include "quad_ops.cuh"
 #include "grid_elast.cuh"
 #include "grid_gauss.cuh"
+#include "tet_grid.cuh"
 
 using namespace adfem;
 
@@ -241,6 +242,27 @@ int emul_grid_laplace_term(int m, int n, const double* xs, const double* ys, int
   if (!triangle_rule(order, rule)) return 1;
   const GridTri gt{m, n, xs, ys};
   for (long long r = 0; r < (long long)(m + 1) * (n + 1); r++) out[r] = grid_laplace_term_node(gt, heron, rule, rule.n, (int)(r / (m + 1)), (int)(r % (m + 1)), nu, u);
+  return 0;
+}
+
+// structured tetrahedral grid (tet_grid.cuh): every warp (= node) of k_tet_grid_elast_fwd as three loops over its lanes
+int emul_tet_grid_elast_fwd(int n, int l, const double* xs, const double* ys, const double* zs, long long nnz, const long long* rowptr, const double* hbar,
+                            double* vals) {
+  static TetGridTables tab;
+  build_tet_grid_tables(tab);
+  const GridTet gt{n, l, xs, ys, zs, &tab};
+  static double smem[TG_WARP_DOUBLES];
+  const long long n1 = n + 1, nn = n1 * n1 * (l + 1);
+  for (long long node = 0; node < nn; node++) {
+    const int i = (int)(node % n1), j = (int)((node / n1) % n1), k = (int)(node / (n1 * n1)), par = (i + j + k) & 1;
+    for (int c = 0; c < TG_WARP_DOUBLES; c++) smem[c] = -7.0e300;
+    double *tb = smem, *stage = tb + 32 * TG_BLK;
+    for (int lane = 0; lane < 32; lane++) tg_tet_block(lane, gt, par, i, j, k, hbar, tb);
+    const int mask = tg_row_mask(gt, par, i, j, k);
+    if (tg_popc(mask) != (int)(rowptr[node + 1] - rowptr[node])) return 2;          // the closed-form row must be the symbolic one
+    for (int lane = 0; lane < 32; lane++) tg_gather_rows(lane, gt, par, mask, tb, stage);
+    for (int lane = 0; lane < 32; lane++) tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
+  }
   return 0;
 }
 

@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "tet_grid.cuh", "tet_grid_tables.h", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -351,3 +351,34 @@ def test_structured_scatter_operators(emul, oracle, m, n):
     assert emul.emul_grid_laplace_term(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(1), d(nu), d(u), d(out)) == 0
     close(out, o.laplace_term_fwd(nu, u))
     assert np.array_equal(out, T.laplace_term(emul, nu, u))
+
+
+@pytest.mark.parametrize("n,l", [(2, 2), (3, 4), (1, 1), (4, 3)])
+def test_structured_tet_elasticity_warp_phases(emul, oracle, n, l):
+    """tet_grid.cuh: one warp per node of Mesh3(n, n, l, h) run as loops over its lanes (shared memory poisoned), rectilinear non-uniform
+    coordinates, against the canonical CSR of the oracle's 3-D stiffness op; the closed-form rows must equal the symbolic pattern."""
+    rng = np.random.default_rng(n * 10 + l)
+    xs = np.concatenate([[0.0], np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    ys = np.concatenate([[0.2], 0.2 + np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    zs = np.concatenate([[-0.1], -0.1 + np.cumsum(rng.random(l) * 0.1 + 0.05)])
+    _, e = meshgen.tet_grid(n, n, l, 1.0)
+    k, j, i = np.meshgrid(np.arange(l + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    c = np.stack([xs[i.reshape(-1)], ys[j.reshape(-1)], zs[k.reshape(-1)]], 1)
+    o = oracle.Mesh3D(c, e)
+    N3 = 3 * o.ndof
+    H = rng.random(o.ngauss * 36) + 0.1
+    ind, vv = o.stiffness_fwd(H)
+    _, _, ref = oracle.canonical_csr(ind, vv, N3)
+    li, lv = o.laplace_fwd(np.ones(o.ngauss))
+    rp, _, _ = oracle.canonical_csr(li, lv, o.ndof)
+    nnz_s = int(rp[-1])
+    assert 9 * nnz_s == len(ref)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    hbar = np.full(o.nelem * 36, np.nan)
+    assert emul.emul_presum_coef(C.c_int(3), C.c_int(o.order), C.c_longlong(o.nelem), C.c_int(36), d(H), d(hbar)) == 0
+    vals = np.full(len(ref), np.nan)
+    rp64 = np.ascontiguousarray(rp, dtype=np.int64)
+    rc = emul.emul_tet_grid_elast_fwd(C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_longlong(nnz_s), rp64.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                      d(hbar), d(vals))
+    assert rc == 0, rc
+    close(vals, ref)

@@ -47,6 +47,29 @@ def test_not_structured():
     assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
 
 
+@pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5)])
+def test_tet_grid_detection(n, l):
+    """Mesh3(n, n, l, h) (5 tetrahedra per cube, parity-alternating) is recognised from its arrays, also on rectilinear non-uniform coordinates;
+    the closed-form rows of csrc/tet_grid.cuh are validated against the symbolic pattern when it is built."""
+    c, e = meshgen.tet_grid(n, n, l, 0.25)
+    M = A.Mesh3(c, e, host_only=True)
+    assert _info(M, _lib.INFO_STRUCTURED) == 2
+    M.csr_pattern(1)
+    assert _info(M, _lib.INFO_STRUCTURED) == 2
+    rng = np.random.default_rng(n + l)
+    xs, ys, zs = (np.concatenate([[0.0], np.cumsum(rng.random(k) + 0.1)]) for k in (n, n, l))
+    kk, jj, ii = np.meshgrid(np.arange(l + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    c2 = np.stack([xs[ii.reshape(-1)], ys[jj.reshape(-1)], zs[kk.reshape(-1)]], 1)
+    assert _info(A.Mesh3(c2, e, host_only=True), _lib.INFO_STRUCTURED) == 2
+    c3 = c.copy(); c3[-1, 2] += 1e-13                                         # one node off the grid
+    assert _info(A.Mesh3(c3, e, host_only=True), _lib.INFO_STRUCTURED) == 0
+    if n * n * l > 1:
+        assert _info(A.Mesh3(c, e[::-1].copy(), host_only=True), _lib.INFO_STRUCTURED) == 0   # renumbered elements
+    assert _info(A.Mesh3(c, e, degree=2, host_only=True), _lib.INFO_STRUCTURED) == 0          # P2
+    e2 = e.copy(); e2[0] = e2[0][[1, 0, 2, 3]]                                               # another vertex order of the same tetrahedron is fine
+    assert _info(A.Mesh3(c, e2, host_only=True), _lib.INFO_STRUCTURED) == 2
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 def _close(a, b, rel=1e-12):
     a, b = np.asarray(a), np.asarray(b)

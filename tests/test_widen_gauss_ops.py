@@ -351,3 +351,27 @@ def test_structured_scatter_operators(oracle):
     for a, b, r in zip(res[1], res[0], refs):
         close(a, r)
         close(a, b, rel=1e-13)       # same summation order and geometry; only the compiler's FMA contraction may differ between the two kernels
+
+
+@pytest.mark.parametrize("n,l", [(3, 2), (5, 4), (1, 1)])
+def test_structured_tet_elasticity_forward(oracle, n, l):
+    """Option "structured_elasticity" on Mesh3(n, n, l, h): Gauss-sum pre-pass + one warp per node (csrc/tet_grid.cuh) for the forward, general
+    tile kernel for the adjoint; against the oracle and the general forward."""
+    rng = np.random.default_rng(70 + n + l)
+    c, e = meshgen.tet_grid(n, n, l, 0.2)
+    m, o = A.Mesh3(c, e), oracle.Mesh3D(c, e)
+    assert A._lib.lib().adfem_mesh_info(m.handle, A._lib.INFO_STRUCTURED) == 2
+    N3 = 3 * o.ndof
+    H = rng.random((o.ngauss, 6, 6)) + 0.1
+    ind, vv = o.stiffness_fwd(H.reshape(-1))
+    rp, ci, ref = oracle.canonical_csr(ind, vv, N3)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N3))
+    for on in (1, 0):
+        m.set_option("structured_elasticity", on)
+        k = dev(H).requires_grad_(True)
+        T = A.compute_fem_stiffness_matrix(k, m, mode="csr")
+        assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+        close(npy(T.values), ref)
+        (g,) = torch.autograd.grad(T.values, k, dev(dv))
+        close(npy(g).reshape(-1), expect)
