@@ -540,6 +540,16 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
   return 0;
 }
 
+int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
+  const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
+  const size_t smem = (size_t)TG_WARPS * TG_ADJ_WARP_DOUBLES * sizeof(double);
+  CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tet_grid_elast_adj<<<blocks_for(m->hm.ne, 32 * TG_WARPS), TG_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
+                                                                                        dvals, grad);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int rows = adjoint ? gt.n : gt.n + 1;
@@ -793,6 +803,7 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
   if (use_grid_elast(m, op)) return launch_grid_elast(m, true, dvals, grad_coef, st);
+  if (use_tet_grid(m, op)) return launch_tet_grid_adj(m, dvals, grad_coef, st);
   if (use_presum(m, op)) {
     // one gradient block per element from the tile kernel, expanded to the g Gauss points by a streaming pass
     if (int rc = ensure_presum_buf(m)) return rc;

@@ -10,7 +10,10 @@
 //   phase 3  the three contiguous runs (component a = 0, 1, 2) are written with coalesced stores.
 // Row pointers are read from the scalar pattern (8 B per node); column positions are index arithmetic.
 // CSR layout as everywhere: scalar row r (start rs, length len) holds entry (a, b, j) at 3*(a*nnz + rs) + b*len + j.
-// All phases are __host__ __device__ functions of the lane index (tests/host_emul/).  The adjoint still runs through the general tile kernel.
+// Adjoint: one warp per 32 consecutive tetrahedra (a contiguous run of the gradient array): lane t gathers the 144 upstream values of its
+// tetrahedron at computed CSR positions, forms B dK B^T |det| (36 values) into shared memory, and the warp writes the 32 x 4 x 36 gradients
+// (times the Gauss weights) coalesced.
+// All phases are __host__ __device__ functions of the lane index (tests/host_emul/).
 #pragma once
 #include "device_fem.cuh"
 #include "tet_grid_tables.h"
@@ -105,6 +108,77 @@ ADFEM_HD void tg_store_rows(int lane, long long rs, int len, long long nnz, cons
   }
 }
 
+// ---- adjoint ----------------------------------------------------------------------------------------------------------------------
+constexpr int TG_ADJ_WARP_DOUBLES = 32 * 36;
+
+// phase 1: lane -> tetrahedron e0 + lane: st[lane*36 + r*6 + c] = (B dK B^T)_{rc} |det|
+ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long long ne, long long nnz, const long long* rowptr, const double* dvals,
+                             double* st) {
+  const TetGridTables& T = *gt.tab;
+  const long long e = e0 + lane;
+  if (e >= ne) return;
+  const long long cube = e / 5, n1 = gt.n + 1;
+  const int t = (int)(e - 5 * cube), ck = (int)(cube % gt.l), cj = (int)((cube / gt.l) % gt.n), ci = (int)(cube / ((long long)gt.l * gt.n));
+  const int ev = ((ci + cj + ck + 3) & 1) == 0;
+  int vi[4], vj[4], vk[4], mask[4];
+  long long rs[4];
+  double X[4][3];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int v = T.te[ev][t][q];
+    vi[q] = ci + (v & 1); vj[q] = cj + ((v >> 1) & 1); vk[q] = ck + (v >> 2);
+    X[q][0] = ldg(gt.xs + vi[q]); X[q][1] = ldg(gt.ys + vj[q]); X[q][2] = ldg(gt.zs + vk[q]);
+    mask[q] = tg_row_mask(gt, (vi[q] + vj[q] + vk[q]) & 1, vi[q], vj[q], vk[q]);
+    rs[q] = rowptr[((long long)vk[q] * n1 + vj[q]) * n1 + vi[q]];
+  }
+  Geom<3> G; geom_tet(X, G);
+  const double ws = G.wscale < 0 ? -G.wscale : G.wscale;
+  double gH[36];
+#pragma unroll
+  for (int c = 0; c < 36; c++) gH[c] = 0.0;
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int len = tg_popc(mask[p]);
+    int pos[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int s = (vk[q] - vk[p] + 1) * 9 + (vj[q] - vj[p] + 1) * 3 + (vi[q] - vi[p] + 1);
+      pos[q] = tg_popc(mask[p] & ((1 << s) - 1));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const double* row = dvals + 3 * ((long long)a * nnz + rs[p]);
+      double tl[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) tl[c] = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) badd<3>(b, G.gL[q], ldg(row + b * len + pos[q]), tl);
+      double bl[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) bl[c] = 0.0;
+      badd<3>(a, G.gL[p], 1.0, bl);
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) gH[6 * r + c] += bl[r] * tl[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 36; c++) st[lane * 36 + c] = gH[c] * ws;
+}
+
+// phase 2: grad[(e*g + k)*36 + c] = st[t*36 + c] * w_k over the contiguous run of the warp's tetrahedra
+ADFEM_HD void tg_store_grad(int lane, const QuadRule& rule, int g, long long e0, long long ne, const double* st, double* grad) {
+  const int nt = (int)(ne - e0 < 32 ? ne - e0 : 32), per = 36 * g;
+  double* out = grad + (size_t)e0 * per;
+  for (int idx = lane; idx < nt * per; idx += 32) {
+    const int t = idx / per, r = idx - t * per, k = r / 36, c = r - 36 * k;
+    out[idx] = st[t * 36 + c] * rule.w[k];
+  }
+}
+
 #ifdef __CUDACC__
 __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt, long long nnz, const long long* __restrict__ rowptr,
                                                                       const double* __restrict__ hbar, double* __restrict__ vals) {
@@ -121,6 +195,19 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt
   tg_gather_rows(lane, gt, par, mask, tb, stage);
   __syncwarp();
   tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
+}
+
+__global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
+                                                                      const long long* __restrict__ rowptr, const double* __restrict__ dvals,
+                                                                      double* __restrict__ grad) {
+  extern __shared__ __align__(16) double tg_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long e0 = 32 * ((long long)blockIdx.x * TG_WARPS + wib);
+  if (e0 >= ne) return;
+  double* st = tg_smem + (size_t)wib * TG_ADJ_WARP_DOUBLES;
+  tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, st);
+  __syncwarp();
+  tg_store_grad(lane, rule, g, e0, ne, st, grad);
 }
 #endif
 

@@ -14,6 +14,7 @@ struct TetGridTables {
   int voff[2][32][4][3];    // offsets (di, dj, dk) of the four vertices relative to the node
   int vslot[2][32][4];      // their row slots: slot = (dk+1)*9 + (dj+1)*3 + (di+1), i.e. ascending node id
   int present[2];           // 27-bit masks of the slots that occur for the parity
+  int te[2][5][4];          // local cube vertices of the 5 tetrahedra: te[1] = TE1 (1-based cube index sum even), te[0] = TE2
   int nsrc[2][27];          // sources of a slot: (incident tetrahedron, local vertex) pairs in ascending element order
   int src[2][27][32][2];
 };
@@ -29,6 +30,9 @@ inline const int (*tet_grid_split_of(int ci, int cj, int ck))[4] { return tet_gr
 
 inline void build_tet_grid_tables(TetGridTables& T) {
   std::memset(&T, 0, sizeof(T));
+  for (int ev = 0; ev < 2; ev++)
+    for (int t = 0; t < 5; t++)
+      for (int q = 0; q < 4; q++) T.te[ev][t][q] = tet_grid_split(ev)[t][q];
   for (int par = 0; par < 2; par++) {
     const int i = 4 + par, j = 4, k = 4;                 // an interior node with (i + j + k) & 1 == par
     int n = 0;

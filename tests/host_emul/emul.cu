@@ -266,6 +266,23 @@ int emul_tet_grid_elast_fwd(int n, int l, const double* xs, const double* ys, co
   return 0;
 }
 
+int emul_tet_grid_elast_adj(int n, int l, const double* xs, const double* ys, const double* zs, int order, long long nnz, const long long* rowptr,
+                            const double* dvals, double* grad) {
+  static TetGridTables tab;
+  build_tet_grid_tables(tab);
+  QuadRule rule;
+  if (!tetrahedron_rule(order, rule)) return 1;
+  const GridTet gt{n, l, xs, ys, zs, &tab};
+  static double smem[TG_ADJ_WARP_DOUBLES];
+  const long long ne = 5LL * n * n * l;
+  for (long long e0 = 0; e0 < ne; e0 += 32) {
+    for (int c = 0; c < TG_ADJ_WARP_DOUBLES; c++) smem[c] = -7.0e300;
+    for (int lane = 0; lane < 32; lane++) tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, smem);
+    for (int lane = 0; lane < 32; lane++) tg_store_grad(lane, rule, rule.n, e0, ne, smem, grad);
+  }
+  return 0;
+}
+
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {
   for (long long i = 0; i < n; i++) plane_matrix_body(mode, E[i], nu[i], H + 9 * i);
 }

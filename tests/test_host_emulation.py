@@ -382,3 +382,10 @@ def test_structured_tet_elasticity_warp_phases(emul, oracle, n, l):
                                       d(hbar), d(vals))
     assert rc == 0, rc
     close(vals, ref)
+    rp3, ci3, _ = oracle.canonical_csr(ind, vv, N3)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp3, ci3, dv, ind, N3))
+    grad = np.full(o.ngauss * 36, np.nan)
+    assert emul.emul_tet_grid_elast_adj(C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_int(o.order), C.c_longlong(nnz_s),
+                                        rp64.ctypes.data_as(C.POINTER(C.c_longlong)), d(dv), d(grad)) == 0
+    close(grad, expect)

@@ -355,8 +355,8 @@ def test_structured_scatter_operators(oracle):
 
 @pytest.mark.parametrize("n,l", [(3, 2), (5, 4), (1, 1)])
 def test_structured_tet_elasticity_forward(oracle, n, l):
-    """Option "structured_elasticity" on Mesh3(n, n, l, h): Gauss-sum pre-pass + one warp per node (csrc/tet_grid.cuh) for the forward, general
-    tile kernel for the adjoint; against the oracle and the general forward."""
+    """Option "structured_elasticity" on Mesh3(n, n, l, h): Gauss-sum pre-pass + one warp per node for the forward, one warp per 32 tetrahedra
+    for the adjoint (csrc/tet_grid.cuh); against the oracle and the general tile kernels."""
     rng = np.random.default_rng(70 + n + l)
     c, e = meshgen.tet_grid(n, n, l, 0.2)
     m, o = A.Mesh3(c, e), oracle.Mesh3D(c, e)
