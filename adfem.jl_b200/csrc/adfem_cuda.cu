@@ -542,9 +542,9 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
 
 int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
   const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
-  const size_t smem = (size_t)TG_WARPS * TG_ADJ_WARP_DOUBLES * sizeof(double);
+  const size_t smem = (size_t)TG_ADJ_WARPS * TG_ADJ_WARP_DOUBLES * sizeof(double);
   CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tet_grid_elast_adj<<<blocks_for(m->hm.ne, 32 * TG_WARPS), TG_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
+  k_tet_grid_elast_adj<<<blocks_for(m->hm.ne, 32 * TG_ADJ_WARPS), TG_ADJ_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
                                                                                         dvals, grad);
   CU_TRY(cudaGetLastError());
   return 0;

@@ -32,17 +32,19 @@ constexpr int TG_BLK = 36;                        // row block of one tetrahedro
 constexpr int TG_WARP_DOUBLES = 32 * TG_BLK + 3 * 27 * 3;
 constexpr int TG_WARPS = 8;
 
-// 27-bit mask of the row slots of node (i, j, k) that exist: structurally present for its parity and inside the grid
+// 27-bit mask of the row slots of node (i, j, k) that exist: structurally present for its parity and inside the grid (slot = (dk+1)*9 + (dj+1)*3
+// + (di+1); the in-range part is a product of three 3-bit masks)
 ADFEM_HD int tg_row_mask(const GridTet& gt, int par, int i, int j, int k) {
-  int mask = 0;
-  for (int s = 0; s < 27; s++) {
-    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
-    const bool in = i + di >= 0 && i + di <= gt.n && j + dj >= 0 && j + dj <= gt.n && k + dk >= 0 && k + dk <= gt.l;
-    if (in && ((gt.tab->present[par] >> s) & 1)) mask |= 1 << s;
-  }
-  return mask;
+  const int mx = (i > 0 ? 1 : 0) | 2 | (i < gt.n ? 4 : 0), my = (j > 0 ? 1 : 0) | 2 | (j < gt.n ? 4 : 0), mz = (k > 0 ? 1 : 0) | 2 | (k < gt.l ? 4 : 0);
+  const int row9 = ((my & 1) ? mx : 0) | (mx << 3) | ((my & 4) ? mx << 6 : 0);
+  const int in27 = ((mz & 1) ? row9 : 0) | (row9 << 9) | ((mz & 4) ? row9 << 18 : 0);
+  return in27 & gt.tab->present[par];
 }
+#ifdef __CUDA_ARCH__
+ADFEM_HD int tg_popc(int x) { return __popc((unsigned)x); }
+#else
 ADFEM_HD int tg_popc(int x) { int c = 0; for (; x; x &= x - 1) c++; return c; }
+#endif
 
 // phase 1: lane t -> tb[t*36 + (a*4 + q)*3 + b] = bvec(a, g_p)^T (Hbar |det|) bvec(b, g_q); zeros when the tetrahedron does not exist
 ADFEM_HD void tg_tet_block(int lane, const GridTet& gt, int par, int i, int j, int k, const double* hbar, double* tb) {
@@ -110,6 +112,7 @@ ADFEM_HD void tg_store_rows(int lane, long long rs, int len, long long nnz, cons
 
 // ---- adjoint ----------------------------------------------------------------------------------------------------------------------
 constexpr int TG_ADJ_WARP_DOUBLES = 32 * 36;
+constexpr int TG_ADJ_WARPS = 4;
 
 // phase 1: lane -> tetrahedron e0 + lane: st[lane*36 + r*6 + c] = (B dK B^T)_{rc} |det|
 ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long long ne, long long nnz, const long long* rowptr, const double* dvals,
@@ -197,12 +200,12 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt
   tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
 }
 
-__global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
+__global__ void __launch_bounds__(TG_ADJ_WARPS * 32, 3) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
                                                                       const long long* __restrict__ rowptr, const double* __restrict__ dvals,
                                                                       double* __restrict__ grad) {
   extern __shared__ __align__(16) double tg_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long e0 = 32 * ((long long)blockIdx.x * TG_WARPS + wib);
+  const long long e0 = 32 * ((long long)blockIdx.x * TG_ADJ_WARPS + wib);
   if (e0 >= ne) return;
   double* st = tg_smem + (size_t)wib * TG_ADJ_WARP_DOUBLES;
   tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, st);
