@@ -3,7 +3,7 @@
 finishes in about a minute.  These are NOT bench.py lines (bench.py measures config 2); they record where the general tile
 kernels stand on the other operator / element families.  One JSON line per case on stdout.
 
-  python scripts/bench_configs.py [--steps 20] [--cases 3,4l,4m,5,src,gp] [--opt coef_presum=1]
+  python scripts/bench_configs.py [--steps 20] [--cases 3,3f,3q,4l,4m,5,src,gp] [--opt coef_presum=1]
 """
 import argparse
 import ctypes as C
@@ -120,6 +120,32 @@ def main():
                           "Melem_per_s": m.nelem / ((tf + ta) * 1e-3) / 1e6, "alg_bytes_per_elem_per_direction": b,
                           "fwd_GBps": b * m.nelem / (tf * 1e-3) / 1e9, "adj_GBps": b * m.nelem / (ta * 1e-3) / 1e9, "options": dict(OPTS)}), flush=True)
         del m
+    if "3q" in cases:
+        # config 3, second half: the literal structured compute_fem_stiffness_matrix1 (UnivariateFemStiffness) with SpatialVaryingTangentElastic type 1
+        L = _lib.lib()
+        mq = int(2896 * s)
+        G4 = 4 * mq * mq
+        mu = torch.rand(G4, dtype=torch.float64, device="cuda") + 0.5
+        hmat = torch.empty((G4, 2, 2), dtype=torch.float64, device="cuda")
+        vv = torch.empty(16 * G4, dtype=torch.float64, device="cuda")
+        gvv = torch.rand(16 * G4, dtype=torch.float64, device="cuda") - 0.5
+        gh, gmu = torch.empty_like(hmat), torch.empty_like(mu)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        h = 1.0 / mq
+
+        def fwd():
+            _lib.check(L.adfem_svt(p(mu), C.c_longlong(mq), C.c_longlong(mq), 1, p(hmat), st))
+            _lib.check(L.adfem_quad_stiffness1(p(hmat), 1, mq, mq, C.c_double(h), None, None, p(vv), st))
+
+        def adj():
+            _lib.check(L.adfem_quad_stiffness1_grad(p(gvv), 1, mq, mq, C.c_double(h), p(gh), st))
+            _lib.check(L.adfem_svt_grad(p(gh), C.c_longlong(mq), C.c_longlong(mq), 1, p(gmu), st))
+
+        tf, ta = timed(fwd, args.steps), timed(adj, args.steps)
+        b = 8 * (1 + 4 + 16) * 4          # per cell: mu in, hmat out + in, vv out (COO-compatible 64 slots per cell)
+        print(json.dumps({"case": "config3_quad_stiffness1_svt", "cells": mq * mq, "fwd_ms": tf, "adj_ms": ta, "bytes_per_cell_per_direction": b,
+                          "fwd_GBps": b * mq * mq / (tf * 1e-3) / 1e9, "adj_GBps": b * mq * mq / (ta * 1e-3) / 1e9}), flush=True)
     if "4l" in cases or "4m" in cases:
         n = int(1000 * s)
         c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)

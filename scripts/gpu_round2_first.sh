@@ -19,7 +19,7 @@ timeout 600 python scripts/bench_configs.py --cases 5 --steps 10 --opt structure
 echo "config 5 structured tetrahedral forward rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg5_tetgrid_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3f_gridelast_$TAG.jsonl 2> gpurun_out/cfg3f_gridelast_$TAG.err
 echo "config 3 fused moduli, structured kernels rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg3f_gridelast_$TAG.jsonl
-timeout 600 python scripts/bench_configs.py --cases 3f,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
+timeout 600 python scripts/bench_configs.py --cases 3f,3q,gp --steps 10 > gpurun_out/gp_$TAG.jsonl 2> gpurun_out/gp_$TAG.err
 echo "gauss-point ops rc=$?"; cut -c1-260 gpurun_out/gp_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases gp --steps 10 --opt structured=0 > gpurun_out/gp_general_$TAG.jsonl 2> gpurun_out/gp_general_$TAG.err
 echo "gauss-point ops, general kernels on the structured mesh rc=$?"; grep P1_grid gpurun_out/gp_general_$TAG.jsonl | cut -c1-260
