@@ -19,6 +19,7 @@
 #include "tri_grid.cuh"
 #include "grid_elast.cuh"
 #include "tet_grid.cuh"
+#include "row_gather.cuh"
 
 using namespace adfem;
 
@@ -76,6 +77,8 @@ struct adfem_mesh {
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
+  int opt_row_gather = 0;                   // scalar operators: one-thread-per-row forward (row_gather.cuh) instead of the row-tile kernel (off until measured)
+  bool rg_ok = false;                       // every CTA's 128 rows fit the shared-memory staging
   int opt_coef_presum = 0;                  // P1 elasticity: reduce the g coefficient blocks of an element to one in a streaming pre-pass (and expand the
                                             // adjoint's per-element block afterwards), so the tile kernels move NS*NS instead of g*NS*NS doubles per element
   DevBuf<double> presum_buf;                // ne * NS*NS doubles of scratch for it
@@ -234,6 +237,9 @@ int ensure_pattern(adfem_mesh* m) {
   m->has_pattern = true;
   if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;
   if (m->tet_ok && !tet_pattern_matches(m->pat, m->tet_tab, m->tet_n, m->tet_l)) m->tet_ok = false;
+  m->rg_ok = true;
+  for (long long r0 = 0; r0 < m->pat.n && m->rg_ok; r0 += RG_THREADS)
+    if (m->pat.rowptr[std::min<long long>(r0 + RG_THREADS, m->pat.n)] - m->pat.rowptr[r0] > RG_CAP) m->rg_ok = false;
   if (!m->host_only) {
     const HostMesh& h = m->hm;
     const int dd = h.d * h.d;
@@ -694,6 +700,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
+  else if (k == "row_gather") m->opt_row_gather = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;
   else if (k == "host_chunks") m->opt_host_chunks = (int)value;
@@ -776,6 +783,23 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   if (use_tet_grid(m, op)) return launch_tet_grid_fwd(m, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
+  if (op != ADFEM_OP_STIFFNESS && m->opt_row_gather) {
+    if (int rc = ensure_pattern(m)) return rc;
+    if (m->rg_ok) {
+      const unsigned nb = blocks_for(m->hm.ndof, RG_THREADS);
+#define CALL_RG(DIM, DEG)                                                                                                                              \
+  if (op == ADFEM_OP_LAPLACE)                                                                                                                          \
+    k_row_gather_fwd<DIM, DEG, OP_LAPLACE><<<nb, RG_THREADS, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,   \
+                                                                     m->d_rowptr.p, m->d_colind.p, coef, vals);                                        \
+  else                                                                                                                                                 \
+    k_row_gather_fwd<DIM, DEG, OP_MASS><<<nb, RG_THREADS, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,      \
+                                                                  m->d_rowptr.p, m->d_colind.p, coef, vals)
+      DISPATCH_ELEM(m, CALL_RG);
+#undef CALL_RG
+      CU_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
   FwdPlanDev* P = nullptr;
   if (int rc = ensure_fwd_plan(m, nc, &P)) return rc;
   const bool presum = use_presum(m, op);
