@@ -1,9 +1,14 @@
-"""GPU parity tests of the Gauss-point operators and matrix-free terms (csrc/gauss_ops.cu) against the oracle,
-through the C ABI (handle API via the Python mirror, and the reference's legacy host-pointer symbols).
+"""GPU parity tests of the widening rows and of the opt-in kernels written at the end of round 1: Gauss-point operators and
+matrix-free terms (csrc/gauss_ops.cu), structured Q1 siblings, coef_presum, the fused constitutive step, the structured-mesh elasticity kernels
+(grid_elast.cuh, tet_grid.cuh), the structured scatter kernels and row_gather — against the oracle, through the C ABI (handle API via the Python
+mirror, and the reference's legacy host-pointer symbols).
 
-The file name sorts after the core parity files on purpose: `pytest -x` reaches these widening rows (8(f)) only after rows (a)-(e).
-The kernel bodies tested here are also run on the host by tests/test_host_emulation.py."""
+NOT YET RUN ON A GPU: the session that wrote these tests had no GPU minutes left.  The arithmetic of every kernel tested here is checked on the
+host (tests/test_host_emulation.py), but the launch glue, the Python wrappers and the tests themselves have never executed on a device, so this
+module is skipped unless ADFEM_RUN_UNVERIFIED=1 — the first GPU call of round 2 (scripts/gpu_round2_first.sh) sets it — rather than let an
+untested test script decide the colour of the parity suite of rows (a)-(e).  The file name sorts after the core parity files for the same reason."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -12,7 +17,9 @@ import adfem_jl_b200 as A
 from adfem_jl_b200 import meshgen
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ADFEM_RUN_UNVERIFIED") != "1",
+                                 reason="written without GPU time at the end of round 1; set ADFEM_RUN_UNVERIFIED=1 (scripts/gpu_round2_first.sh does)")]
 
 
 def close(a, b, rel=1e-12):
