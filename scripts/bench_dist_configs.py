@@ -69,6 +69,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="exchanges on the kernels' stream (their time is then visible between forward and adjoint)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -101,24 +102,49 @@ def main():
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             pk, pv, pd, pg = (C.c_void_p(t.data_ptr()) for t in (coef, vals, dK, grad))
 
+        # Both interface exchanges run on a high-priority side stream, as in bench.py: replicate(dK) (input of the adjoint) overlaps the forward
+        # kernel, reduce(vals) overlaps the adjoint kernel; the streams join at the start of every step.  --no-overlap keeps everything on one stream
+        # (then the exchange time is what the events between forward and adjoint measure).
+        overlap = (not dry) and world > 1 and not args.no_overlap
+        main = torch.cuda.current_stream() if not dry else None
+        side = torch.cuda.Stream(priority=-1) if overlap else None
+
         def step(ev=None):
             nonlocal dghost
+            if dghost is None:
+                dghost = torch.zeros(len(part.ghost_idx) * nc * nc, dtype=torch.float64, device=dev)
+            if overlap:
+                side.wait_stream(main)
+                main.wait_stream(side)
+                with torch.cuda.stream(side):
+                    part.replicate_interface(dK, dghost, ncomp=nc)
             if ev:
                 ev[0].record()
             if not dry:
                 _lib.check(L.adfem_assemble_csr(mesh.handle, op, pk, pv, st))
             if ev:
                 ev[1].record()
-            part.reduce_interface(vals, ncomp=nc)                  # interface-row partial sums to their owners
-            if dghost is None:
-                dghost = torch.zeros_like(part.ghost_vals)
-            part.replicate_interface(dK, dghost, ncomp=nc)         # d loss / d K of the interface rows back to every contributor
+            if overlap:
+                fwd_done = torch.cuda.Event()
+                fwd_done.record(main)
+                main.wait_stream(side)                               # the adjoint needs the replicated dK
+            else:
+                part.reduce_interface(vals, ncomp=nc)                # interface-row partial sums to their owners
+                part.replicate_interface(dK, dghost, ncomp=nc)       # d loss / d K of the interface rows back to every contributor
             if ev:
                 ev[2].record()
             if not dry:
                 _lib.check(L.adfem_assemble_csr_adjoint(mesh.handle, op, pd, pg, st))
             if ev:
                 ev[3].record()
+            if overlap:
+                side.wait_event(fwd_done)
+                with torch.cuda.stream(side):
+                    part.reduce_interface(vals, ncomp=nc)
+
+        def join():
+            if overlap:
+                main.wait_stream(side)
 
         step()
         if not dry:
@@ -126,6 +152,7 @@ def main():
         setup = time.perf_counter() - t0
         for _ in range(args.warmup):
             step()
+        join()
         K = args.steps
         if dry:
             tw = time.perf_counter()
@@ -140,10 +167,13 @@ def main():
             torch.cuda.synchronize()
             for i in range(K):
                 step(ev[i])
+            join()
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            total_ms = ev[0][0].elapsed_time(ev[K - 1][3])
+            total_ms = ev[0][0].elapsed_time(end)
             fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
             xch_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
             adj_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / K
@@ -158,7 +188,7 @@ def main():
                               "elements_total": int(tsum[4].item()), "elements_per_gpu_max": int(tmax[4].item()),
                               "ms_per_step": ms, "Melem_per_s": tsum[4].item() / (ms * 1e-3) / 1e6 if not dry else None,
                               "fwd_ms_max": tmax[1].item(), "exchange_ms_max": tmax[2].item(), "adj_ms_max": tmax[3].item(),
-                              "interface_bytes_per_step_total": int(tsum[5].item()), "setup_s": round(setup, 1),
+                              "interface_bytes_per_step_total": int(tsum[5].item()), "setup_s": round(setup, 1), "overlap": bool(overlap),
                               "options": args.opt}), flush=True)
         del part, mesh
     if world > 1:

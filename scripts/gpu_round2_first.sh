@@ -42,6 +42,9 @@ if [ "${GPUS:-1}" -gt 1 ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $GPUS --master-addr 127.0.0.1 --master-port 29518 scripts/bench_dist_configs.py --cases 3,5 --steps 10 \
     --opt structured_elasticity=1 > gpurun_out/dist_cfg_struct_${GPUS}gpu_$TAG.jsonl 2> gpurun_out/dist_cfg_struct_${GPUS}gpu_$TAG.err
   echo "multi-GPU configs 3 and 5, structured elasticity kernels rc=$?"; cut -c1-400 gpurun_out/dist_cfg_struct_${GPUS}gpu_$TAG.jsonl
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $GPUS --master-addr 127.0.0.1 --master-port 29519 scripts/bench_dist_configs.py --cases 5 --steps 10 \
+    --opt structured_elasticity=1 --no-overlap > gpurun_out/dist_cfg5_noverlap_${GPUS}gpu_$TAG.jsonl 2> gpurun_out/dist_cfg5_noverlap_${GPUS}gpu_$TAG.err
+  echo "config 5 without exchange overlap rc=$?"; cut -c1-400 gpurun_out/dist_cfg5_noverlap_${GPUS}gpu_$TAG.jsonl
 fi
 # one full capture of the structured elasticity kernels (config 3 at half size)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_grid_elast|k_tet_grid" -s 4 -c 2 -f -o gpurun_out/prof_gridelast_$TAG \
