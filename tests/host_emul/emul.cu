@@ -15,6 +15,11 @@
 
 using namespace adfem;
 
+// Lanes of a warp phase run one after the other here; on the GPU they run together, so a phase must not depend on the order.  emul_set_reverse(1)
+// makes every phase visit its lanes 31..0 instead of 0..31: the tests require bit-identical results for both orders.
+static int g_reverse = 0;
+#define EMUL_LANES(lane) for (int lane##_i = 0, lane = g_reverse ? 31 : 0; lane##_i < 32; lane##_i++, lane = g_reverse ? 31 - lane##_i : lane##_i)
+
 namespace {
 
 DevMesh make_mesh(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn, bool& ok) {
@@ -95,13 +100,15 @@ static int run_row_gather(const DevMesh& m, const long long* ap, const int* ae, 
     const int total = (int)(rowptr[r1] - rs0);
     if (total > RG_CAP) return -1;
     for (int c = 0; c < RG_CAP; c++) acc[c] = -7.0e300;
-    for (int r = r0; r < r1; r++) rg_row<DIM, DEG, OP>(m, ap, ae, al, rowptr, colind, r, rs0, coef, acc);
+    for (int t = 0; t < r1 - r0; t++) { const int r = g_reverse ? r1 - 1 - t : r0 + t; rg_row<DIM, DEG, OP>(m, ap, ae, al, rowptr, colind, r, rs0, coef, acc); }
     for (int idx = 0; idx < total; idx++) vals[rs0 + idx] = acc[idx];
   }
   return 0;
 }
 
 extern "C" {
+
+void emul_set_reverse(int on) { g_reverse = on; }
 
 // kind / adjoint as adfem_gauss_op / adfem_gauss_op_adjoint (include/adfem_cuda.h); the kind -> (basis, weighted, direction) table is the one
 // of gp_kind() in adfem_cuda.cu
@@ -202,12 +209,12 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
       if (plane_mode >= 0) ge_load_cell_row_plane<GE_G>(lane, rule, m, n, ci, j0, plane_mode, coef, coef2, buf);
       else ge_load_cell_row<GE_G>(lane, rule, m, n, ci, j0, coef, buf);
     };
-    for (int lane = 0; lane < 32; lane++) load(lane, i0 - 1, P);
+    EMUL_LANES(lane) load(lane, i0 - 1, P);
     long long rowbase = grid_rowptr(i0, 0, m, n);
     for (int i = i0; i < i1; i++) {
-      for (int lane = 0; lane < 32; lane++) load(lane, i, C);
-      for (int lane = 0; lane < 32; lane++) ge_node(lane, heron, gt, i, j0, P, C, stage);
-      for (int lane = 0; lane < 32; lane++) ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
+      EMUL_LANES(lane) load(lane, i, C);
+      EMUL_LANES(lane) ge_node(lane, heron, gt, i, j0, P, C, stage);
+      EMUL_LANES(lane) ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
       rowbase += ge_prefix(m + 1, m, i > 0, i < n);
       double* t = P; P = C; C = t;
     }
@@ -227,12 +234,12 @@ int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int or
     for (int k = 0; k < GE_ADJ_WARP_DOUBLES; k++) smem[k] = -7.0e300;
     double *lo = smem, *hi = lo + 2 * GE_NROW, *gst = hi + 2 * GE_NROW;
     long long rowbase = grid_rowptr(r0, 0, m, n);
-    for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, r0, c0, rowbase, nnz, dvals, lo);
+    EMUL_LANES(lane) ge_load_node_row(lane, m, n, r0, c0, rowbase, nnz, dvals, lo);
     for (int ci = r0; ci < r1; ci++) {
       rowbase += ge_prefix(m + 1, m, ci > 0, ci < n);
-      for (int lane = 0; lane < 32; lane++) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
-      for (int lane = 0; lane < 32; lane++) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
-      for (int lane = 0; lane < 32; lane++) {
+      EMUL_LANES(lane) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
+      EMUL_LANES(lane) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
+      EMUL_LANES(lane) {
         if (plane_mode >= 0) ge_store_cell_row_plane<GE_G>(lane, rule, m, ci, c0, plane_mode, E, nu, gst, grad, grad2);
         else ge_store_cell_row<GE_G>(lane, rule, m, ci, c0, gst, grad);
       }
@@ -275,11 +282,11 @@ int emul_tet_grid_elast_fwd(int n, int l, const double* xs, const double* ys, co
     const int i = (int)(node % n1), j = (int)((node / n1) % n1), k = (int)(node / (n1 * n1)), par = (i + j + k) & 1;
     for (int c = 0; c < TG_WARP_DOUBLES; c++) smem[c] = -7.0e300;
     double *tb = smem, *stage = tb + 32 * TG_BLK;
-    for (int lane = 0; lane < 32; lane++) tg_tet_block(lane, gt, par, i, j, k, hbar, tb);
+    EMUL_LANES(lane) tg_tet_block(lane, gt, par, i, j, k, hbar, tb);
     const int mask = tg_row_mask(gt, par, i, j, k);
     if (tg_popc(mask) != (int)(rowptr[node + 1] - rowptr[node])) return 2;          // the closed-form row must be the symbolic one
-    for (int lane = 0; lane < 32; lane++) tg_gather_rows(lane, gt, par, mask, tb, stage);
-    for (int lane = 0; lane < 32; lane++) tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
+    EMUL_LANES(lane) tg_gather_rows(lane, gt, par, mask, tb, stage);
+    EMUL_LANES(lane) tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
   }
   return 0;
 }
@@ -295,8 +302,8 @@ int emul_tet_grid_elast_adj(int n, int l, const double* xs, const double* ys, co
   const long long ne = 5LL * n * n * l;
   for (long long e0 = 0; e0 < ne; e0 += 32) {
     for (int c = 0; c < TG_ADJ_WARP_DOUBLES; c++) smem[c] = -7.0e300;
-    for (int lane = 0; lane < 32; lane++) tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, smem);
-    for (int lane = 0; lane < 32; lane++) tg_store_grad(lane, rule, rule.n, e0, ne, smem, grad);
+    EMUL_LANES(lane) tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, smem);
+    EMUL_LANES(lane) tg_store_grad(lane, rule, rule.n, e0, ne, smem, grad);
   }
   return 0;
 }

@@ -416,3 +416,33 @@ def test_row_gather_forward(emul, oracle, dim, degree):
                                       ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(op), d(coef), d(vals))
         assert rc == 0, rc
         close(vals, ref)
+
+
+def test_warp_phases_do_not_depend_on_lane_order(emul, oracle):
+    """The emulator runs the lanes of a phase one after the other; with the lanes visited in reverse order the structured-elasticity, tetrahedral
+    and row-gather kernels must give the same bits (no lane reads what another lane writes in the same phase)."""
+    rng = np.random.default_rng(99)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    m, n = 37, 5
+    xs, ys = np.arange(m + 1) * 0.1, np.arange(n + 1) * 0.07
+    nnz_s = (oracle.canonical_csr(*oracle.Mesh2D(*meshgen.tri_grid(m, n, 0.1)).laplace_fwd(np.ones(6 * m * n)), (m + 1) * (n + 1))[0])[-1]
+    H, dv = rng.random(2 * m * n * 27), rng.standard_normal(4 * nnz_s)
+    nt, lt = 3, 2
+    c3, e3 = meshgen.tet_grid(nt, nt, lt, 0.5)
+    o3 = oracle.Mesh3D(c3, e3)
+    rp3 = np.ascontiguousarray(oracle.canonical_csr(*o3.laplace_fwd(np.ones(o3.ngauss)), o3.ndof)[0], dtype=np.int64)
+    hb, dv3 = rng.random(o3.nelem * 36), rng.standard_normal(9 * int(rp3[-1]))
+    ax = [np.arange(nt + 1) * 0.5, np.arange(nt + 1) * 0.5, np.arange(lt + 1) * 0.5]
+    out = {}
+    for rev in (0, 1):
+        emul.emul_set_reverse(C.c_int(rev))
+        v, g = np.full(4 * nnz_s, np.nan), np.full(2 * m * n * 27, np.nan)
+        assert emul.emul_grid_elast_fwd(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(0), C.c_int(3), C.c_longlong(nnz_s), d(H), d(v), C.c_int(-1), None) == 0
+        assert emul.emul_grid_elast_adj(C.c_int(m), C.c_int(n), d(xs), d(ys), C.c_int(2), C.c_int(0), C.c_int(3), C.c_longlong(nnz_s), d(dv), d(g), C.c_int(-1), None, None, None) == 0
+        v3, g3 = np.full(len(dv3), np.nan), np.full(o3.ngauss * 36, np.nan)
+        assert emul.emul_tet_grid_elast_fwd(C.c_int(nt), C.c_int(lt), d(ax[0]), d(ax[1]), d(ax[2]), C.c_longlong(int(rp3[-1])), rp3.ctypes.data_as(C.POINTER(C.c_longlong)), d(hb), d(v3)) == 0
+        assert emul.emul_tet_grid_elast_adj(C.c_int(nt), C.c_int(lt), d(ax[0]), d(ax[1]), d(ax[2]), C.c_int(2), C.c_longlong(int(rp3[-1])), rp3.ctypes.data_as(C.POINTER(C.c_longlong)), d(dv3), d(g3)) == 0
+        out[rev] = [v, g, v3, g3]
+    emul.emul_set_reverse(C.c_int(0))
+    for a, b in zip(out[0], out[1]):
+        assert not np.isnan(a).any() and np.array_equal(a, b)
