@@ -79,6 +79,7 @@ struct adfem_mesh {
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
   int opt_row_gather = 0;                   // scalar operators: one-thread-per-row forward (row_gather.cuh) instead of the row-tile kernel (off until measured)
   bool rg_ok = false;                       // every CTA's 128 rows fit the shared-memory staging
+  int rge_max_entries = 0;                  // elasticity variant: most CSR entries of any CTA's 64 rows (sizes its dynamic shared memory)
   int opt_coef_presum = 0;                  // P1 elasticity: reduce the g coefficient blocks of an element to one in a streaming pre-pass (and expand the
                                             // adjoint's per-element block afterwards), so the tile kernels move NS*NS instead of g*NS*NS doubles per element
   DevBuf<double> presum_buf;                // ne * NS*NS doubles of scratch for it
@@ -240,6 +241,9 @@ int ensure_pattern(adfem_mesh* m) {
   m->rg_ok = true;
   for (long long r0 = 0; r0 < m->pat.n && m->rg_ok; r0 += RG_THREADS)
     if (m->pat.rowptr[std::min<long long>(r0 + RG_THREADS, m->pat.n)] - m->pat.rowptr[r0] > RG_CAP) m->rg_ok = false;
+  m->rge_max_entries = 0;
+  for (long long r0 = 0; r0 < m->pat.n; r0 += RGE_THREADS)
+    m->rge_max_entries = std::max<long long>(m->rge_max_entries, m->pat.rowptr[std::min<long long>(r0 + RGE_THREADS, m->pat.n)] - m->pat.rowptr[r0]);
   if (!m->host_only) {
     const HostMesh& h = m->hm;
     const int dd = h.d * h.d;
@@ -796,6 +800,27 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
                                                                   m->d_rowptr.p, m->d_colind.p, coef, vals)
       DISPATCH_ELEM(m, CALL_RG);
 #undef CALL_RG
+      CU_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (op == ADFEM_OP_STIFFNESS && m->opt_row_gather && m->hm.degree == 1 && m->hm.g > 1) {
+    // P1 elasticity without a tile plan: Gauss-sum pre-pass, then one thread per scalar row (row_gather.cuh)
+    if (int rc = ensure_pattern(m)) return rc;
+    const size_t smem = (size_t)nc * nc * m->rge_max_entries * sizeof(double);
+    if (smem <= SMEM_LIMIT) {
+      if (int rc = ensure_presum_buf(m)) return rc;
+      if (int rc = launch_presum_coef(dev_mesh(m, m->opt_area_csr), coef_per_gauss(m, op), coef, m->presum_buf.p, st)) return rc;
+      const unsigned nb = blocks_for(m->hm.ndof, RGE_THREADS);
+      if (m->hm.dim == 2) {
+        CU_TRY(cudaFuncSetAttribute(k_row_gather_elast_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_row_gather_elast_fwd<2><<<nb, RGE_THREADS, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, m->d_rowptr.p,
+                                                                 m->d_colind.p, m->pat.nnz, m->presum_buf.p, vals);
+      } else {
+        CU_TRY(cudaFuncSetAttribute(k_row_gather_elast_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_row_gather_elast_fwd<3><<<nb, RGE_THREADS, smem, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, m->d_rowptr.p,
+                                                                 m->d_colind.p, m->pat.nnz, m->presum_buf.p, vals);
+      }
       CU_TRY(cudaGetLastError());
       return 0;
     }

@@ -72,6 +72,51 @@ ADFEM_HD void rg_row(const DevMesh& m, const long long* adj_ptr, const int* adj_
   }
 }
 
+// ---- P1 elasticity (any mesh): the same row walk for the NC x NC block operator, from the Gauss-summed tangents of option "coef_presum" ---------
+// hbar[e*NS*NS + ...] = sum_k w_k H_{e,k} (k_presum_coef).  Thread <-> scalar row r; it fills the NC*NC blocks of its row in the CTA's copy of
+// the NC component runs: acc[a*NC*T + NC*(rs - rs0) + b*len + j], T = CSR entries of the CTA's rows, i.e. the layout of adfem_assemble_csr.
+constexpr int RGE_THREADS = 64;
+
+template <int DIM>
+ADFEM_HD void rg_row_elast(const DevMesh& m, const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, const long long* rowptr,
+                           const int* colind, int r, long long rs0, int T, const double* hbar, double* acc) {
+  constexpr int NC = DIM, D = DIM + 1, NS = Voigt<DIM>::NS;
+  const long long rs = rowptr[r];
+  const int len = (int)(rowptr[r + 1] - rs), base = NC * (int)(rs - rs0);
+  for (int a = 0; a < NC; a++)
+    for (int t = 0; t < NC * len; t++) acc[a * NC * T + base + t] = 0.0;
+  const int* cols = colind + rs;
+  for (long long t = adj_ptr[r]; t < adj_ptr[r + 1]; t++) {
+    const int e = adj_elem[t], p = adj_loc[t];
+    Geom<DIM> G; load_geom(m, e, G);
+    double H[NS * NS];
+#pragma unroll
+    for (int c = 0; c < NS * NS; c++) H[c] = ldg(hbar + (size_t)e * (NS * NS) + c) * G.wscale;
+    double gp[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; c++) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; q++) v = (q == p) ? G.gL[q][c] : v;
+      gp[c] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < D; q++) {
+      const int c = ldg(m.conn + (size_t)q * m.ne + e);
+      int lo = 0, hi = len;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ldg(cols + mid) < c) lo = mid + 1; else hi = mid; }
+#pragma unroll
+      for (int b = 0; b < NC; b++) {
+        double hb[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) hb[i] = bdot<DIM>(b, G.gL[q], &H[NS * i]);
+#pragma unroll
+        for (int a = 0; a < NC; a++) acc[a * NC * T + base + b * len + lo] += bdot<DIM>(a, gp, hb);
+      }
+    }
+  }
+}
+
 #ifdef __CUDACC__
 template <int DIM, int DEG, int OP>
 __global__ void __launch_bounds__(RG_THREADS) k_row_gather_fwd(DevMesh m, const long long* __restrict__ adj_ptr, const int* __restrict__ adj_elem,
@@ -84,6 +129,24 @@ __global__ void __launch_bounds__(RG_THREADS) k_row_gather_fwd(DevMesh m, const 
   __syncthreads();
   const int total = (int)(rowptr[r1] - rs0);
   for (int idx = threadIdx.x; idx < total; idx += RG_THREADS) vals[rs0 + idx] = acc[idx];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(RGE_THREADS) k_row_gather_elast_fwd(DevMesh m, const long long* __restrict__ adj_ptr, const int* __restrict__ adj_elem,
+                                                                       const uint8_t* __restrict__ adj_loc, const long long* __restrict__ rowptr,
+                                                                       const int* __restrict__ colind, long long nnz, const double* __restrict__ hbar,
+                                                                       double* __restrict__ vals) {
+  extern __shared__ __align__(16) double rge_acc[];
+  constexpr int NC = DIM;
+  const int r0 = blockIdx.x * RGE_THREADS, r = r0 + threadIdx.x, r1 = min(r0 + RGE_THREADS, m.ndof);
+  const long long rs0 = rowptr[r0];
+  const int T = (int)(rowptr[r1] - rs0);
+  if (r < m.ndof) rg_row_elast<DIM>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, r, rs0, T, hbar, rge_acc);
+  __syncthreads();
+  for (int a = 0; a < NC; a++) {
+    double* out = vals + NC * ((long long)a * nnz + rs0);
+    for (int idx = threadIdx.x; idx < NC * T; idx += RGE_THREADS) out[idx] = rge_acc[a * NC * T + idx];
+  }
 }
 #endif
 

@@ -24,6 +24,8 @@ for R in 0 1; do
 done
 timeout 600 python scripts/bench_configs.py --cases 4l --steps 10 --opt row_gather=1 --opt adjoint_tiled=0 > gpurun_out/cfg4_rowgather_adjgather_$TAG.jsonl 2> gpurun_out/cfg4_rowgather_adjgather_$TAG.err
 echo "config 4 row_gather=1 + direct-gather adjoint rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg4_rowgather_adjgather_$TAG.jsonl
+timeout 600 python scripts/bench_configs.py --cases 3,5 --steps 10 --opt row_gather=1 > gpurun_out/cfg35_rowgather_$TAG.jsonl 2> gpurun_out/cfg35_rowgather_$TAG.err
+echo "configs 3,5 row_gather=1 (plan-free forward) rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg35_rowgather_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 5 --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg5_tetgrid_$TAG.jsonl 2> gpurun_out/cfg5_tetgrid_$TAG.err
 echo "config 5 structured tetrahedral forward rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg5_tetgrid_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3f_gridelast_$TAG.jsonl 2> gpurun_out/cfg3f_gridelast_$TAG.err

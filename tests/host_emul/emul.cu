@@ -106,6 +106,25 @@ static int run_row_gather(const DevMesh& m, const long long* ap, const int* ae, 
   return 0;
 }
 
+// k_row_gather_elast_fwd (row_gather.cuh)
+template <int DIM>
+static int run_row_gather_elast(const DevMesh& m, const long long* ap, const int* ae, const uint8_t* al, const long long* rowptr, const int* colind,
+                                long long nnz, const double* hbar, double* vals) {
+  constexpr int NC = DIM;
+  static double acc[9 * 8192];
+  for (int r0 = 0; r0 < m.ndof; r0 += RGE_THREADS) {
+    const int r1 = r0 + RGE_THREADS < m.ndof ? r0 + RGE_THREADS : m.ndof;
+    const long long rs0 = rowptr[r0];
+    const int T = (int)(rowptr[r1] - rs0);
+    if (T > 8192) return -1;
+    for (int c = 0; c < NC * NC * T; c++) acc[c] = -7.0e300;
+    for (int t = 0; t < r1 - r0; t++) { const int r = g_reverse ? r1 - 1 - t : r0 + t; rg_row_elast<DIM>(m, ap, ae, al, rowptr, colind, r, rs0, T, hbar, acc); }
+    for (int a = 0; a < NC; a++)
+      for (int idx = 0; idx < NC * T; idx++) vals[NC * ((long long)a * nnz + rs0) + idx] = acc[a * NC * T + idx];
+  }
+  return 0;
+}
+
 extern "C" {
 
 void emul_set_reverse(int on) { g_reverse = on; }
@@ -320,6 +339,16 @@ int emul_row_gather_fwd(int dim, int degree, int order, int nv, int ne, int ndof
   EMUL_DISPATCH(dim, degree, CALL_RG);
 #undef CALL_RG
   return rc;
+}
+
+int emul_row_gather_elast_fwd(int dim, int order, int nv, int ne, const double* coords, const int* verts, const int* conn, const long long* adj_ptr,
+                              const int* adj_elem, const uint8_t* adj_loc, const long long* rowptr, const int* colind, const double* hbar, double* vals) {
+  bool ok;
+  const DevMesh m = make_mesh(dim, 1, order, nv, ne, nv, coords, verts, conn, ok);
+  if (!ok) return 1;
+  const long long nnz = rowptr[nv];
+  return dim == 2 ? run_row_gather_elast<2>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, nnz, hbar, vals)
+                  : run_row_gather_elast<3>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, nnz, hbar, vals);
 }
 
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {

@@ -446,3 +446,38 @@ def test_warp_phases_do_not_depend_on_lane_order(emul, oracle):
     emul.emul_set_reverse(C.c_int(0))
     for a, b in zip(out[0], out[1]):
         assert not np.isnan(a).any() and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_row_gather_elasticity_forward(emul, oracle, dim):
+    """row_gather.cuh, P1 elasticity on unstructured meshes: one thread per scalar row fills its NC x NC blocks from the Gauss-summed tangents;
+    against the canonical CSR of the oracle's stiffness op, lanes in both orders."""
+    rng = np.random.default_rng(200 + dim)
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(15, 11, 0.05, seed=10)
+        o = oracle.Mesh2D(c, e)
+    else:
+        c, e = meshgen.tet_grid(4, 4, 3, 0.3)
+        o = oracle.Mesh3D(c + rng.uniform(-0.02, 0.02, c.shape), e)
+    T = HostTables(o)
+    ns2 = 9 if dim == 2 else 36
+    H = rng.random(o.ngauss * ns2) + 0.1
+    ind, vv = o.stiffness_fwd(H)
+    _, _, ref = oracle.canonical_csr(ind, vv, dim * o.ndof)
+    rp, ci, _ = oracle.canonical_csr(*o.laplace_fwd(np.ones(o.ngauss)), o.ndof)
+    rp64, ci32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(ci, dtype=np.int32)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    hbar = np.full(o.nelem * ns2, np.nan)
+    assert emul.emul_presum_coef(C.c_int(dim), C.c_int(o.order), C.c_longlong(o.nelem), C.c_int(ns2), d(H), d(hbar)) == 0
+    res = []
+    for rev in (0, 1):
+        emul.emul_set_reverse(C.c_int(rev))
+        vals = np.full(len(ref), np.nan)
+        rc = emul.emul_row_gather_elast_fwd(C.c_int(dim), C.c_int(o.order), C.c_int(o.nnode), C.c_int(o.nelem), d(T.coords),
+                                            T.verts.ctypes.data_as(C.POINTER(C.c_int)), T.conn.ctypes.data_as(C.POINTER(C.c_int)), *T._adj_args(),
+                                            rp64.ctypes.data_as(C.POINTER(C.c_longlong)), ci32.ctypes.data_as(C.POINTER(C.c_int)), d(hbar), d(vals))
+        assert rc == 0, rc
+        close(vals, ref)
+        res.append(vals)
+    emul.emul_set_reverse(C.c_int(0))
+    assert np.array_equal(res[0], res[1])

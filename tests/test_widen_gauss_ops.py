@@ -412,3 +412,32 @@ def test_row_gather_forward(oracle, dim, degree):
             mass_ref = M                                        # tile kernel (already checked against the oracle in test_gpu_parity.py)
         else:
             close(M, mass_ref)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_row_gather_elasticity_forward(oracle, dim):
+    """Option "row_gather" for P1 elasticity on unstructured meshes: Gauss-sum pre-pass + one thread per scalar row, no tile plan; the adjoint keeps
+    the tile kernel.  Against the oracle."""
+    rng = np.random.default_rng(90 + dim)
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(33, 29, 0.03, seed=13)
+        m, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+        ns = 3
+    else:
+        c, e = meshgen.tet_grid(5, 5, 4, 0.2)
+        c = c + rng.uniform(-0.02, 0.02, c.shape)
+        m, o = A.Mesh3(c, e), oracle.Mesh3D(c, e)
+        ns = 6
+    n = dim * o.ndof
+    H = rng.random((o.ngauss, ns, ns)) + 0.1
+    ind, vv = o.stiffness_fwd(H.reshape(-1))
+    rp, ci, ref = oracle.canonical_csr(ind, vv, n)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, n))
+    m.set_option("row_gather", 1)
+    k = dev(H).requires_grad_(True)
+    T = A.compute_fem_stiffness_matrix(k, m, mode="csr")
+    assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+    close(npy(T.values), ref)
+    (g,) = torch.autograd.grad(T.values, k, dev(dv))
+    close(npy(g).reshape(-1), expect)
