@@ -980,6 +980,8 @@ int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, 
 
 // ---- Gauss-point operators (gauss_ops.cu) ---------------------------------------------------------------------
 namespace {
+bool use_tet_gauss(const adfem_mesh* m) { return m->tet_ok && m->opt_structured && !m->host_only && m->hm.degree == 1; }
+GridTet grid_tet_of(const adfem_mesh* m) { return GridTet{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p}; }
 struct GpKind { int basis; bool weighted, scatter_fwd; };     // forward = gather (dof -> Gauss points) unless scatter_fwd
 bool gp_kind(int kind, GpKind& k) {
   switch (kind) {
@@ -996,6 +998,7 @@ DofAdjacency dof_adjacency(const adfem_mesh* m) { return DofAdjacency{m->d_adj_p
 int gp_apply(adfem_mesh* m, const GpKind& k, bool to_gauss, const double* in, double* out, cudaStream_t st) {
   if (to_gauss) return launch_gp_gather(dev_mesh(m, m->opt_area_coo), m->hm.degree, k.basis, k.weighted, in, out, st);
   if (int rc = ensure_pattern(m)) return rc;
+  if (use_tet_gauss(m)) return launch_tet_gp_scatter(dev_mesh(m, m->opt_area_coo), grid_tet_of(m), k.basis, k.weighted, in, out, st);
   if (use_grid(m) && m->hm.degree == 1)      // structured triangulation: index arithmetic instead of the adjacency (grid_gauss.cuh)
     return launch_grid_gp_scatter(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, k.basis, k.weighted, in, out, st);
   return launch_gp_scatter(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), k.basis, k.weighted, in, out, st);
@@ -1033,6 +1036,7 @@ int adfem_gauss_op_adjoint(adfem_mesh* m, int kind, const double* grad_out, doub
 int adfem_laplace_term(adfem_mesh* m, const double* nu, const double* u, double* out, void* stream) {
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
+  if (use_tet_gauss(m)) return launch_tet_laplace_term(dev_mesh(m, m->opt_area_coo), grid_tet_of(m), nu, u, out, (cudaStream_t)stream);
   if (use_grid(m) && m->hm.degree == 1)
     return launch_grid_laplace_term(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, u, out, (cudaStream_t)stream);
   return launch_laplace_term(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), nu, u, out, (cudaStream_t)stream);
@@ -1046,7 +1050,9 @@ int adfem_laplace_term_adjoint(adfem_mesh* m, const double* nu, const double* u,
   if (grad_nu) { if (int rc = launch_laplace_term_grad_nu(dm, m->hm.degree, u, grad_out, grad_nu, (cudaStream_t)stream)) return rc; }
   // the term is symmetric in (u, v): d/du of grad_out . K(nu) u is K(nu) grad_out
   if (grad_u) {
-    if (use_grid(m) && m->hm.degree == 1) {
+    if (use_tet_gauss(m)) {
+      if (int rc = launch_tet_laplace_term(dm, grid_tet_of(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
+    } else if (use_grid(m) && m->hm.degree == 1) {
       if (int rc = launch_grid_laplace_term(dm, GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
     } else {
       if (int rc = launch_laplace_term(dm, m->hm.degree, dof_adjacency(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;

@@ -7,6 +7,7 @@
 
 #include "gauss_ops.cuh"
 #include "grid_gauss.cuh"
+#include "tet_gauss.cuh"
 #include "internal.h"
 
 namespace adfem {
@@ -72,6 +73,23 @@ __global__ void __launch_bounds__(GP_THREADS) k_grid_laplace_term(DevMesh m, Gri
                                                                    double* __restrict__ out) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, nn = (long long)(gt.m + 1) * (gt.n + 1);
   if (r < nn) out[r] = grid_laplace_term_node(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), nu, u);
+}
+
+// structured tetrahedral grid: one thread per node, node id = (k*(n+1) + j)*(n+1) + i
+template <int B, bool W>
+__global__ void __launch_bounds__(GP_THREADS) k_tet_gp_scatter(DevMesh m, GridTet gt, const double* __restrict__ in, double* __restrict__ out) {
+  constexpr int NC = GpShape<3, 1, B>::NC;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, n1 = gt.n + 1, nn = n1 * n1 * (gt.l + 1);
+  if (r >= nn) return;
+  double acc[NC];
+  tg_scatter_node<B, W>(gt, m.rule, m.g, (int)(r % n1), (int)((r / n1) % n1), (int)(r / (n1 * n1)), in, acc);
+#pragma unroll
+  for (int c = 0; c < NC; c++) out[r + c * nn] = acc[c];
+}
+__global__ void __launch_bounds__(GP_THREADS) k_tet_laplace_term(DevMesh m, GridTet gt, const double* __restrict__ nu, const double* __restrict__ u,
+                                                                  double* __restrict__ out) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, n1 = gt.n + 1, nn = n1 * n1 * (gt.l + 1);
+  if (r < nn) out[r] = tg_laplace_term_node(gt, m.rule, m.g, (int)(r % n1), (int)((r / n1) % n1), (int)(r / (n1 * n1)), nu, u);
 }
 
 __global__ void k_presum_coef(DevMesh m, int ns2, long long n, const double* __restrict__ coef, double* __restrict__ hbar) {
@@ -192,6 +210,26 @@ int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool
 int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st) {
   k_grid_laplace_term<<<gp_blocks((long long)(gt.m + 1) * (gt.n + 1)), GP_THREADS, 0, st>>>(dm, gt, nu, u, out);
   return launched("structured Laplace term kernel");
+}
+
+int launch_tet_gp_scatter(const DevMesh& dm, const GridTet& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st) {
+  const long long n1 = gt.n + 1, nn = n1 * n1 * (gt.l + 1);
+  const unsigned nb = gp_blocks(nn);
+  if (basis < GB_P1SHAPE || basis > GB_STRAIN || (weighted && basis != GB_STRAIN)) return fail("gauss-point scatter: unknown operator");
+  switch (basis) {
+    case GB_P1SHAPE: k_tet_gp_scatter<GB_P1SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    case GB_SHAPE: k_tet_gp_scatter<GB_SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    case GB_GRAD: k_tet_gp_scatter<GB_GRAD, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    default:
+      if (weighted) k_tet_gp_scatter<GB_STRAIN, true><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
+      else k_tet_gp_scatter<GB_STRAIN, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
+  }
+  return launched("structured tetrahedral gauss-point scatter kernel");
+}
+int launch_tet_laplace_term(const DevMesh& dm, const GridTet& gt, const double* nu, const double* u, double* out, cudaStream_t st) {
+  const long long n1 = gt.n + 1;
+  k_tet_laplace_term<<<gp_blocks(n1 * n1 * (gt.l + 1)), GP_THREADS, 0, st>>>(dm, gt, nu, u, out);
+  return launched("structured tetrahedral Laplace term kernel");
 }
 
 int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st) {

@@ -6,6 +6,7 @@
 
 #include "device_fem.cuh"
 #include "grid_index.cuh"
+#include "tet_grid.cuh"
 
 namespace adfem {
 
@@ -30,6 +31,10 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
 // structured triangulation Mesh(m, n, h), P1 (grid_gauss.cuh): index-free versions of the scatter-type kernels
 int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st);
 int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st);
+
+// structured tetrahedral grid Mesh3(n, n, l, h), P1 (tet_gauss.cuh)
+int launch_tet_gp_scatter(const DevMesh& dm, const GridTet& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st);
+int launch_tet_laplace_term(const DevMesh& dm, const GridTet& gt, const double* nu, const double* u, double* out, cudaStream_t st);
 
 // option "coef_presum" (P1 elasticity): hbar[ne*ns2] = sum_k w_k coef[(e*g+k)*ns2 + c]; grad[(e*g+k)*ns2 + c] = w_k gbar[e*ns2 + c]
 int launch_presum_coef(const DevMesh& dm, int ns2, const double* coef, double* hbar, cudaStream_t st);

@@ -183,7 +183,7 @@ ADFEM_HD void tg_store_grad(int lane, const QuadRule& rule, int g, long long e0,
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt, long long nnz, const long long* __restrict__ rowptr,
+static __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt, long long nnz, const long long* __restrict__ rowptr,
                                                                       const double* __restrict__ hbar, double* __restrict__ vals) {
   extern __shared__ __align__(16) double tg_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(GridTet gt
   tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
 }
 
-__global__ void __launch_bounds__(TG_ADJ_WARPS * 32, 3) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
+static __global__ void __launch_bounds__(TG_ADJ_WARPS * 32, 3) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
                                                                       const long long* __restrict__ rowptr, const double* __restrict__ dvals,
                                                                       double* __restrict__ grad) {
   extern __shared__ __align__(16) double tg_smem[];

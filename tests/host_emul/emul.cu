@@ -12,6 +12,7 @@
 #include "grid_gauss.cuh"
 #include "tet_grid.cuh"
 #include "row_gather.cuh"
+#include "tet_gauss.cuh"
 
 using namespace adfem;
 
@@ -123,6 +124,18 @@ static int run_row_gather_elast(const DevMesh& m, const long long* ap, const int
       for (int idx = 0; idx < NC * T; idx++) vals[NC * ((long long)a * nnz + rs0) + idx] = acc[a * NC * T + idx];
   }
   return 0;
+}
+
+// one thread per node of k_tet_gp_scatter (gauss_ops.cu)
+template <int B, bool W>
+static void run_tet_scatter(const GridTet& gt, const QuadRule& rule, const double* in, double* out) {
+  constexpr int NC = GpShape<3, 1, B>::NC;
+  const long long n1 = gt.n + 1, nn = n1 * n1 * (gt.l + 1);
+  for (long long r = 0; r < nn; r++) {
+    double acc[NC];
+    tg_scatter_node<B, W>(gt, rule, rule.n, (int)(r % n1), (int)((r / n1) % n1), (int)(r / (n1 * n1)), in, acc);
+    for (int c = 0; c < NC; c++) out[r + c * nn] = acc[c];
+  }
 }
 
 extern "C" {
@@ -349,6 +362,32 @@ int emul_row_gather_elast_fwd(int dim, int order, int nv, int ne, const double* 
   const long long nnz = rowptr[nv];
   return dim == 2 ? run_row_gather_elast<2>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, nnz, hbar, vals)
                   : run_row_gather_elast<3>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, nnz, hbar, vals);
+}
+
+int emul_tet_gp_scatter(int n, int l, const double* xs, const double* ys, const double* zs, int order, int basis, int weighted, const double* in,
+                        double* out) {
+  static TetGridTables tab;
+  build_tet_grid_tables(tab);
+  QuadRule rule;
+  if (!tetrahedron_rule(order, rule)) return 1;
+  const GridTet gt{n, l, xs, ys, zs, &tab};
+  switch (basis) {
+    case GB_P1SHAPE: run_tet_scatter<GB_P1SHAPE, false>(gt, rule, in, out); return 0;
+    case GB_SHAPE: run_tet_scatter<GB_SHAPE, false>(gt, rule, in, out); return 0;
+    case GB_GRAD: run_tet_scatter<GB_GRAD, false>(gt, rule, in, out); return 0;
+    case GB_STRAIN: if (weighted) run_tet_scatter<GB_STRAIN, true>(gt, rule, in, out); else run_tet_scatter<GB_STRAIN, false>(gt, rule, in, out); return 0;
+  }
+  return 1;
+}
+int emul_tet_laplace_term(int n, int l, const double* xs, const double* ys, const double* zs, int order, const double* nu, const double* u, double* out) {
+  static TetGridTables tab;
+  build_tet_grid_tables(tab);
+  QuadRule rule;
+  if (!tetrahedron_rule(order, rule)) return 1;
+  const GridTet gt{n, l, xs, ys, zs, &tab};
+  const long long n1 = n + 1;
+  for (long long r = 0; r < n1 * n1 * (l + 1); r++) out[r] = tg_laplace_term_node(gt, rule, rule.n, (int)(r % n1), (int)((r / n1) % n1), (int)(r / (n1 * n1)), nu, u);
+  return 0;
 }
 
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {

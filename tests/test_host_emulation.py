@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "tet_grid.cuh", "tet_grid_tables.h", "row_gather.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "tet_grid.cuh", "tet_grid_tables.h", "row_gather.cuh", "tet_gauss.cuh", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -481,3 +481,32 @@ def test_row_gather_elasticity_forward(emul, oracle, dim):
         res.append(vals)
     emul.emul_set_reverse(C.c_int(0))
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("n,l", [(2, 2), (3, 1)])
+def test_structured_tet_scatter_operators(emul, oracle, n, l):
+    """tet_gauss.cuh: scatter-type Gauss-point operators and the Laplace term on Mesh3(n, n, l, h), one thread per node with index arithmetic and
+    the orientation fix replayed (Gauss points are indexed in the element's own vertex order) — bit-identical to the general adjacency-walking
+    bodies, and the Laplace term against the oracle (deps/MFEM3/ComputeLaplaceTermMfem)."""
+    rng = np.random.default_rng(300 + n + l)
+    xs = np.concatenate([[0.0], np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    ys = np.concatenate([[0.2], 0.2 + np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    zs = np.concatenate([[-0.1], -0.1 + np.cumsum(rng.random(l) * 0.1 + 0.05)])
+    _, e = meshgen.tet_grid(n, n, l, 1.0)
+    k, j, i = np.meshgrid(np.arange(l + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    c = np.stack([xs[i.reshape(-1)], ys[j.reshape(-1)], zs[k.reshape(-1)]], 1)
+    o = oracle.Mesh3D(c, e)
+    T = HostTables(o)
+    G, nd = o.ngauss, o.ndof
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for basis, weighted, nin, nout, kind, adjoint in ((0, 0, G, nd, FEM_TO_GAUSS, True), (1, 0, G, nd, DOF_TO_GAUSS, True), (2, 0, 3 * G, nd, GRAD, True),
+                                                      (3, 0, 6 * G, 3 * nd, STRAIN, True), (3, 1, 6 * G, 3 * nd, STRAIN_ENERGY, False)):
+        x = rng.standard_normal(nin)
+        out = np.full(nout, np.nan)
+        assert emul.emul_tet_gp_scatter(C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_int(o.order), C.c_int(basis), C.c_int(weighted), d(x), d(out)) == 0
+        assert np.array_equal(out, T.gauss_op(emul, kind, adjoint, x, nout))
+    nu, u = rng.random(G) + 0.5, rng.standard_normal(nd)
+    out = np.full(nd, np.nan)
+    assert emul.emul_tet_laplace_term(C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_int(o.order), d(nu), d(u), d(out)) == 0
+    close(out, o.laplace_term_fwd(nu, u))
+    assert np.array_equal(out, T.laplace_term(emul, nu, u))

@@ -441,3 +441,35 @@ def test_row_gather_elasticity_forward(oracle, dim):
     close(npy(T.values), ref)
     (g,) = torch.autograd.grad(T.values, k, dev(dv))
     close(npy(g).reshape(-1), expect)
+
+
+def test_structured_tet_scatter_operators(oracle):
+    """Scatter-type Gauss-point operators and the Laplace term on Mesh3(n, n, l, h): one-thread-per-node kernels with index arithmetic
+    (csrc/tet_gauss.cuh, option "structured" = 1) against the general adjacency-walking kernels and, for the Laplace term, the oracle."""
+    rng = np.random.default_rng(71)
+    n_, l_ = 5, 4
+    c, e = meshgen.tet_grid(n_, n_, l_, 0.2)
+    m, o = A.Mesh3(c, e), oracle.Mesh3D(c, e)
+    assert A._lib.lib().adfem_mesh_info(m.handle, A._lib.INFO_STRUCTURED) == 2
+    G, nd = o.ngauss, o.ndof
+    nu, u, go = rng.random(G) + 0.5, rng.standard_normal(nd), rng.standard_normal(nd)
+    sig, w1, w3, w6 = rng.standard_normal((G, 6)), rng.standard_normal(G), rng.standard_normal((G, 3)), rng.standard_normal((G, 6))
+    res = {}
+    for on in (1, 0):
+        m.set_option("structured", on)
+        ut, nt = dev(u).requires_grad_(True), dev(nu).requires_grad_(True)
+        term = A.compute_fem_laplace_term1(ut, nt, m)
+        gu, gnu = torch.autograd.grad(term, [ut, nt], dev(go))
+        se = A.compute_strain_energy_term(dev(sig), m)
+        adj = []
+        for fn, x, w in ((A.fem_to_gauss_points, u, w1), (A.dof_to_gauss_points, u, w1), (A.eval_grad_on_gauss_pts1, u, w3),
+                         (A.eval_strain_on_gauss_pts, np.concatenate([u, go, u]), w6)):
+            xt = dev(x).requires_grad_(True)
+            (g,) = torch.autograd.grad(fn(xt, m), xt, dev(w))
+            adj.append(npy(g))
+        res[on] = [npy(term), npy(gu), npy(gnu), npy(se)] + adj
+    m.set_option("structured", 1)
+    rnu, ru = o.laplace_term_bwd(go, nu, u)
+    close(res[1][0], o.laplace_term_fwd(nu, u)); close(res[1][1], ru); close(res[1][2], rnu)
+    for a, b in zip(res[1], res[0]):
+        close(a, b, rel=1e-13)
