@@ -12,7 +12,7 @@ def functions(path):
         if m:
             if name:
                 out[name] = hashlib.md5("".join(buf).encode()).hexdigest()
-            name, buf = m.group(1), []
+            name, buf = re.sub(r"_GLOBAL__N__[0-9a-f]+_(\d+_\w+?_cu)_[0-9a-f]+", r"_GLOBAL__N__\1", m.group(1)), []     # anonymous namespaces carry a per-path hash
         elif name:
             buf.append(" ".join(line.split()) + "\n")       # cuobjdump pads the columns to the longest instruction of the whole dump
     if name:
