@@ -20,6 +20,7 @@
 #include "grid_elast.cuh"
 #include "tet_grid.cuh"
 #include "row_gather.cuh"
+#include "tet_scalar.cuh"
 
 using namespace adfem;
 
@@ -560,6 +561,25 @@ int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaSt
   return 0;
 }
 
+// scalar P1 operators on the structured tetrahedral grid (tet_scalar.cuh), same opt-in switch as the elasticity kernels
+bool use_tet_scalar(adfem_mesh* m, int op) {
+  return op != ADFEM_OP_STIFFNESS && m->opt_grid_elast && m->opt_structured && m->tet_ok && !m->host_only && m->hm.degree == 1;
+}
+int launch_tet_scalar(adfem_mesh* m, int op, bool adjoint, const double* in, double* out, cudaStream_t st) {
+  const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
+  if (adjoint) {
+    const unsigned nb = blocks_for(m->hm.ne, 128);
+    if (op == ADFEM_OP_LAPLACE) k_tet_grid_scalar_adj<OP_LAPLACE><<<nb, 128, 0, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->d_rowptr.p, in, out);
+    else k_tet_grid_scalar_adj<OP_MASS><<<nb, 128, 0, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->d_rowptr.p, in, out);
+  } else {
+    const unsigned nb = blocks_for(m->hm.nv, RG_THREADS);
+    if (op == ADFEM_OP_LAPLACE) k_tet_grid_scalar_fwd<OP_LAPLACE><<<nb, RG_THREADS, 0, st>>>(gt, m->hm.rule, m->hm.g, m->d_rowptr.p, in, out);
+    else k_tet_grid_scalar_fwd<OP_MASS><<<nb, RG_THREADS, 0, st>>>(gt, m->hm.rule, m->hm.g, m->d_rowptr.p, in, out);
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st) {
   GridTri gt{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p};
   const int rows = adjoint ? gt.n : gt.n + 1;
@@ -783,8 +803,9 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
   if ((op != ADFEM_OP_STIFFNESS || m->opt_grid_elast) && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
   if (use_grid_elast(m, op)) return launch_grid_elast(m, false, coef, vals, st);
-  if (m->tet_ok && m->opt_grid_elast && op == ADFEM_OP_STIFFNESS) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
+  if (m->tet_ok && m->opt_grid_elast) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
   if (use_tet_grid(m, op)) return launch_tet_grid_fwd(m, coef, vals, st);
+  if (use_tet_scalar(m, op)) return launch_tet_scalar(m, op, false, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && m->opt_row_gather) {
@@ -853,6 +874,7 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
     return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
   if (use_grid_elast(m, op)) return launch_grid_elast(m, true, dvals, grad_coef, st);
   if (use_tet_grid(m, op)) return launch_tet_grid_adj(m, dvals, grad_coef, st);
+  if (use_tet_scalar(m, op)) return launch_tet_scalar(m, op, true, dvals, grad_coef, st);
   if (use_presum(m, op)) {
     // one gradient block per element from the tile kernel, expanded to the g Gauss points by a streaming pass
     if (int rc = ensure_presum_buf(m)) return rc;

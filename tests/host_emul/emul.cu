@@ -13,6 +13,7 @@
 #include "tet_grid.cuh"
 #include "row_gather.cuh"
 #include "tet_gauss.cuh"
+#include "tet_scalar.cuh"
 
 using namespace adfem;
 
@@ -387,6 +388,36 @@ int emul_tet_laplace_term(int n, int l, const double* xs, const double* ys, cons
   const GridTet gt{n, l, xs, ys, zs, &tab};
   const long long n1 = n + 1;
   for (long long r = 0; r < n1 * n1 * (l + 1); r++) out[r] = tg_laplace_term_node(gt, rule, rule.n, (int)(r % n1), (int)((r / n1) % n1), (int)(r / (n1 * n1)), nu, u);
+  return 0;
+}
+
+// structured tetrahedral grid, scalar operators (tet_scalar.cuh): CTAs of k_tet_grid_scalar_fwd, threads of k_tet_grid_scalar_adj
+int emul_tet_grid_scalar(int n, int l, const double* xs, const double* ys, const double* zs, int order, int op, int adjoint, const long long* rowptr,
+                         const double* in, double* out) {
+  static TetGridTables tab;
+  build_tet_grid_tables(tab);
+  QuadRule rule;
+  if (!tetrahedron_rule(order, rule) || (op != OP_LAPLACE && op != OP_MASS)) return 1;
+  const GridTet gt{n, l, xs, ys, zs, &tab};
+  const long long n1 = n + 1, nn = n1 * n1 * (l + 1), ne = 5LL * n * n * l;
+  if (adjoint) {
+    for (long long e = 0; e < ne; e++) {
+      if (op == OP_LAPLACE) tgs_tet_adjoint<OP_LAPLACE>(gt, rule, rule.n, e, rowptr, in, out); else tgs_tet_adjoint<OP_MASS>(gt, rule, rule.n, e, rowptr, in, out);
+    }
+    return 0;
+  }
+  static double acc[RG_CAP];
+  for (long long r0 = 0; r0 < nn; r0 += RG_THREADS) {
+    const long long r1 = r0 + RG_THREADS < nn ? r0 + RG_THREADS : nn, rs0 = rowptr[r0];
+    if (rowptr[r1] - rs0 > RG_CAP) return -1;
+    for (int c = 0; c < RG_CAP; c++) acc[c] = -7.0e300;
+    for (long long t = 0; t < r1 - r0; t++) {
+      const long long r = g_reverse ? r1 - 1 - t : r0 + t;
+      const int i = (int)(r % n1), j = (int)((r / n1) % n1), k = (int)(r / (n1 * n1));
+      if (op == OP_LAPLACE) tgs_row<OP_LAPLACE>(gt, rule, rule.n, i, j, k, rowptr[r], rs0, in, acc); else tgs_row<OP_MASS>(gt, rule, rule.n, i, j, k, rowptr[r], rs0, in, acc);
+    }
+    for (long long idx = 0; idx < rowptr[r1] - rs0; idx++) out[rs0 + idx] = acc[idx];
+  }
   return 0;
 }
 

@@ -29,7 +29,7 @@ def emul():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "tet_grid.cuh", "tet_grid_tables.h", "row_gather.cuh", "tet_gauss.cuh", "device_fem.cuh", "quadrature.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gauss_ops.cuh", "quad_ops.cuh", "grid_elast.cuh", "grid_gauss.cuh", "grid_index.cuh", "tet_grid.cuh", "tet_grid_tables.h", "row_gather.cuh", "tet_gauss.cuh", "tet_scalar.cuh", "device_fem.cuh", "quadrature.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
@@ -510,3 +510,42 @@ def test_structured_tet_scatter_operators(emul, oracle, n, l):
     assert emul.emul_tet_laplace_term(C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_int(o.order), d(nu), d(u), d(out)) == 0
     close(out, o.laplace_term_fwd(nu, u))
     assert np.array_equal(out, T.laplace_term(emul, nu, u))
+
+
+@pytest.mark.parametrize("n,l", [(2, 2), (3, 4), (1, 1)])
+def test_structured_tet_scalar_operators(emul, oracle, n, l):
+    """tet_scalar.cuh: CSR Laplace / mass and their adjoints on Mesh3(n, n, l, h) (the reference's own 3-D ops) by index arithmetic, against the
+    oracle; mass is checked through the general row-gather body (the oracle's 3-D mass has its own COO layout) and by transposition."""
+    rng = np.random.default_rng(400 + n + l)
+    xs = np.concatenate([[0.0], np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    ys = np.concatenate([[0.2], 0.2 + np.cumsum(rng.random(n) * 0.1 + 0.05)])
+    zs = np.concatenate([[-0.1], -0.1 + np.cumsum(rng.random(l) * 0.1 + 0.05)])
+    _, e = meshgen.tet_grid(n, n, l, 1.0)
+    k, j, i = np.meshgrid(np.arange(l + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    c = np.stack([xs[i.reshape(-1)], ys[j.reshape(-1)], zs[k.reshape(-1)]], 1)
+    o = oracle.Mesh3D(c, e)
+    T = HostTables(o)
+    coef = rng.random(o.ngauss) + 0.5
+    ind, vv = o.laplace_fwd(coef)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+    rp64, ci32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(ci, dtype=np.int32)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lp = rp64.ctypes.data_as(C.POINTER(C.c_longlong))
+    args = (C.c_int(n), C.c_int(l), d(xs), d(ys), d(zs), C.c_int(o.order))
+    vals = np.full(len(ref), np.nan)
+    assert emul.emul_tet_grid_scalar(*args, C.c_int(0), C.c_int(0), lp, d(coef), d(vals)) == 0
+    close(vals, ref)
+    dv = rng.standard_normal(len(ref))
+    g = np.full(o.ngauss, np.nan)
+    assert emul.emul_tet_grid_scalar(*args, C.c_int(0), C.c_int(1), lp, d(dv), d(g)) == 0
+    close(g, o.laplace_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, o.ndof)))
+    # mass: forward equals the general row-gather body bit for bit; adjoint is its transpose
+    mv, mref = np.full(len(ref), np.nan), np.full(len(ref), np.nan)
+    assert emul.emul_tet_grid_scalar(*args, C.c_int(1), C.c_int(0), lp, d(coef), d(mv)) == 0
+    assert emul.emul_row_gather_fwd(*T._mesh_args(), *T._adj_args(), lp, ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(1), d(coef), d(mref)) == 0
+    assert np.array_equal(mv, mref)
+    gm = np.full(o.ngauss, np.nan)
+    assert emul.emul_tet_grid_scalar(*args, C.c_int(1), C.c_int(1), lp, d(dv), d(gm)) == 0
+    lhs, rhs = mv @ dv, gm @ coef
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0)
+    assert abs(mv.sum() - (coef * o.weights).sum()) <= 1e-12 * abs(mv.sum())          # partition of unity: sum of M = int rho

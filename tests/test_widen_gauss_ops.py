@@ -473,3 +473,31 @@ def test_structured_tet_scatter_operators(oracle):
     close(res[1][0], o.laplace_term_fwd(nu, u)); close(res[1][1], ru); close(res[1][2], rnu)
     for a, b in zip(res[1], res[0]):
         close(a, b, rel=1e-13)
+
+
+@pytest.mark.parametrize("n,l", [(4, 3), (1, 1)])
+def test_structured_tet_scalar_operators(oracle, n, l):
+    """Option "structured_elasticity" also switches the scalar P1 operators on Mesh3(n, n, l, h) to the index-arithmetic kernels of
+    csrc/tet_scalar.cuh (FemLaplaceScalarT, mass; forward and adjoint): against the oracle and the general tile kernels."""
+    rng = np.random.default_rng(75 + n + l)
+    c, e = meshgen.tet_grid(n, n, l, 0.2)
+    m, o = A.Mesh3(c, e), oracle.Mesh3D(c, e)
+    coef = rng.random(o.ngauss) + 0.5
+    ind, vv = o.laplace_fwd(coef)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+    dv = rng.standard_normal(len(ref))
+    expect = o.laplace_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, o.ndof))
+    mass = {}
+    for on in (1, 0):
+        m.set_option("structured_elasticity", on)
+        k = dev(coef).requires_grad_(True)
+        T = A.compute_fem_laplace_matrix1(k, m, mode="csr")
+        assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+        close(npy(T.values), ref)
+        (g,) = torch.autograd.grad(T.values, k, dev(dv))
+        close(npy(g), expect)
+        k2 = dev(coef).requires_grad_(True)
+        M = A.compute_fem_mass_matrix1(k2, m, mode="csr")
+        (gm,) = torch.autograd.grad(M.values, k2, dev(dv))
+        mass[on] = (npy(M.values), npy(gm))
+    close(mass[1][0], mass[0][0]); close(mass[1][1], mass[0][1])
