@@ -3,7 +3,7 @@
 finishes in about a minute.  These are NOT bench.py lines (bench.py measures config 2); they record where the general tile
 kernels stand on the other operator / element families.  One JSON line per case on stdout.
 
-  python scripts/bench_configs.py [--steps 20] [--cases 3,3f,3q,4l,4m,5,src,gp] [--opt coef_presum=1]
+  python scripts/bench_configs.py [--steps 20] [--cases 3,3f,3q,4l,4m,5,5s,src,gp] [--opt coef_presum=1]
 """
 import argparse
 import ctypes as C
@@ -160,6 +160,13 @@ def main():
         c, e = meshgen.tet_grid(n, n, n, 1.0 / n)
         m = A.Mesh3(c, e)
         run_csr("config5_elasticity_P1_tet", m, 2, 36, args.steps, "Mesh3(%d,%d,%d,h) P1 tets, per-Gauss-point 6x6 Voigt H (3-D extension N2)" % (n, n, n))
+        del m
+    if "5s" in cases:
+        # the reference's own 3-D op (FemLaplaceScalarT) on the same tetrahedral grid
+        n = int(64 * s)
+        c, e = meshgen.tet_grid(n, n, n, 1.0 / n)
+        m = A.Mesh3(c, e)
+        run_csr("config5_laplace_P1_tet", m, 0, 1, args.steps, "Mesh3(%d,%d,%d,h) P1 tets, scalar Laplace (FemLaplaceScalarT)" % (n, n, n))
         del m
     if "src" in cases:
         L = _lib.lib()

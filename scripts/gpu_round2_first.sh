@@ -26,6 +26,10 @@ timeout 600 python scripts/bench_configs.py --cases 4l --steps 10 --opt row_gath
 echo "config 4 row_gather=1 + direct-gather adjoint rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg4_rowgather_adjgather_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3,5 --steps 10 --opt row_gather=1 > gpurun_out/cfg35_rowgather_$TAG.jsonl 2> gpurun_out/cfg35_rowgather_$TAG.err
 echo "configs 3,5 row_gather=1 (plan-free forward) rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg35_rowgather_$TAG.jsonl
+for S in 0 1; do
+  timeout 600 python scripts/bench_configs.py --cases 5s --steps 10 --opt structured_elasticity=$S > gpurun_out/cfg5s_struct${S}_$TAG.jsonl 2> gpurun_out/cfg5s_struct${S}_$TAG.err
+  echo "3-D scalar Laplace on Mesh3, structured_elasticity=$S rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg5s_struct${S}_$TAG.jsonl
+done
 timeout 600 python scripts/bench_configs.py --cases 5 --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg5_tetgrid_$TAG.jsonl 2> gpurun_out/cfg5_tetgrid_$TAG.err
 echo "config 5 structured tetrahedral forward rc=$?"; python scripts/cfg_line.py < gpurun_out/cfg5_tetgrid_$TAG.jsonl
 timeout 600 python scripts/bench_configs.py --cases 3f --steps 10 --opt structured_elasticity=1 > gpurun_out/cfg3f_gridelast_$TAG.jsonl 2> gpurun_out/cfg3f_gridelast_$TAG.err
