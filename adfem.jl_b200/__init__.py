@@ -10,4 +10,4 @@ from .ops import (CSRTensor, SparseTensor, compute_fem_laplace_matrix1, compute_
                   pcl_compute_fem_laplace_matrix1, pcl_impose_Dirichlet_boundary_conditions,
                   fem_to_gauss_points, dof_to_gauss_points, eval_grad_on_gauss_pts1, eval_strain_on_gauss_pts,
                   compute_strain_energy_term, compute_fem_laplace_term1, compute_plane_strain_matrix, compute_plane_stress_matrix,
-                  compute_fem_stiffness_matrix_from_moduli)
+                  compute_fem_stiffness_matrix_from_moduli, compute_fem_stiffness_matrix1_from_mu)

@@ -248,6 +248,15 @@ __global__ void k_quad_scalar_bwd(int op, const double* __restrict__ grad_vv, lo
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t < total) grad_coef[t] = quad_scalar_bwd_body(op, t, grad_vv, h);
 }
+__global__ void k_quad_stiff1_svt_fwd(const double* __restrict__ mu, int type, int m, int n, double h, long long* __restrict__ ii,
+                                      long long* __restrict__ jj, double* __restrict__ vv) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < 4LL * m * n) quad_stiff1_svt_fwd_body(t, mu, type, m, n, h, ii, jj, vv);
+}
+__global__ void k_quad_stiff1_svt_bwd(const double* __restrict__ grad_vv, int type, int m, int n, double h, double* __restrict__ grad_mu) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < 4LL * m * n) quad_stiff1_svt_bwd_body(t, grad_vv, type, m, n, h, grad_mu);
+}
 __global__ void k_quad_source_fwd(const double* __restrict__ f, int m, int n, double h, double* __restrict__ rhs) {
   const long long node = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (node < (long long)(m + 1) * (n + 1)) rhs[node] = quad_source_node(node, f, m, n, h);
@@ -333,6 +342,22 @@ int adfem_quad_source(const double* f, long long m, long long n, double h, doubl
 int adfem_quad_source_grad(const double* grad_rhs, long long m, long long n, double h, double* grad_f, void* stream) {
   if (int rc = check_grid((int)m, (int)n, h)) return rc;
   k_quad_source_bwd<<<nblk(4 * m * n, 128), 128, 0, (cudaStream_t)stream>>>(grad_rhs, (int)m, 4 * m * n, h, grad_f);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adfem_quad_stiffness1_svt(const double* mu, int type, int m, int n, double h, long long* ii, long long* jj, double* vv, void* stream) {
+  if (type < 1 || type > 3) return fail("SpatialVaryingTangentElastic: type must be 1, 2 or 3");
+  if (int rc = check_grid(m, n, h)) return rc;
+  if ((ii == nullptr) != (jj == nullptr)) return fail("ii and jj must both be given or both be NULL");
+  k_quad_stiff1_svt_fwd<<<nblk(4LL * m * n, 128), 128, 0, (cudaStream_t)stream>>>(mu, type, m, n, h, ii, jj, vv);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int adfem_quad_stiffness1_svt_grad(const double* grad_vv, int type, int m, int n, double h, double* grad_mu, void* stream) {
+  if (type < 1 || type > 3) return fail("SpatialVaryingTangentElastic: type must be 1, 2 or 3");
+  if (int rc = check_grid(m, n, h)) return rc;
+  k_quad_stiff1_svt_bwd<<<nblk(4LL * m * n, 128), 128, 0, (cudaStream_t)stream>>>(grad_vv, type, m, n, h, grad_mu);
   CU_TRY(cudaGetLastError());
   return 0;
 }

@@ -99,4 +99,52 @@ ADFEM_HD double quad_source_bwd_body(long long t, const double* grad_rhs, int m,
   return s;
 }
 
+// ---- SpatialVaryingTangentElastic fused into UnivariateFemStiffness ---------------------------------------------
+// compute_fem_stiffness_matrix1(compute_space_varying_tangent_elasticity_matrix(mu, m, n, h, type), m, n, h) in one pass: the 4mn x 2 x 2 tensor
+// is never written.  K of Gauss point gi (deps/SpatialVaryingTangentElastic/SpatialVaryingTangentElastic.h:1-31): type 1 mu_gi I,
+// type 2 diag(mu_gi, mu_{gi+4mn}), type 3 [[mu_gi, mu_{gi+8mn}], [mu_{gi+8mn}, mu_{gi+4mn}]].
+// Slot order and 1-BASED ii / jj of UnivariateFemStiffness (deps/FemStiffness1/UnivariateFemStiffness.h:29-43): t = 4*cs + (2*ei + ej), cell
+// sequence cs = i*n + j (i outer), xi = pts[ei], eta = pts[ej], K index gi = 4*(i + j*m) + ei + 2*ej.
+ADFEM_HD void quad_stiff1_svt_fwd_body(long long t, const double* mu, int type, int m, int n, double h, long long* ii, long long* jj, double* vv) {
+  const int gs = (int)(t & 3), ei = gs >> 1, ej = gs & 1;
+  const long long cs = t >> 2, off = 4LL * m * n;
+  const int i = (int)(cs / n), j = (int)(cs % n);
+  const long long gi = 4 * ((long long)i + (long long)j * m) + ei + 2 * ej;
+  const double k00 = ldg(mu + gi), k11 = type == 1 ? k00 : ldg(mu + gi + off), k01 = type == 3 ? ldg(mu + gi + 2 * off) : 0.0;
+  double r0[4], r1[4]; quad_grad_rows(h, quad_pt(ei), quad_pt(ej), r0, r1);
+  const double sc = 0.25 * h * h;
+  long long idx[4];
+  idx[0] = (long long)j * (m + 1) + i; idx[1] = idx[0] + 1; idx[2] = (long long)(j + 1) * (m + 1) + i; idx[3] = idx[2] + 1;
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double kb0 = k00 * r0[q] + k01 * r1[q], kb1 = k01 * r0[q] + k11 * r1[q];
+      vv[t * 16 + p * 4 + q] = (r0[p] * kb0 + r1[p] * kb1) * sc;
+      if (ii) { ii[t * 16 + p * 4 + q] = idx[p] + 1; jj[t * 16 + p * 4 + q] = idx[q] + 1; }
+    }
+}
+// adjoint: grad_mu (length 4mn * type), every entry written exactly once
+ADFEM_HD void quad_stiff1_svt_bwd_body(long long t, const double* grad_vv, int type, int m, int n, double h, double* grad_mu) {
+  const int gs = (int)(t & 3), ei = gs >> 1, ej = gs & 1;
+  const long long cs = t >> 2, off = 4LL * m * n;
+  const int i = (int)(cs / n), j = (int)(cs % n);
+  const long long gi = 4 * ((long long)i + (long long)j * m) + ei + 2 * ej;
+  double r0[4], r1[4]; quad_grad_rows(h, quad_pt(ei), quad_pt(ej), r0, r1);
+  double d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double v = ldg(grad_vv + t * 16 + p * 4 + q);
+      d00 += r0[p] * v * r0[q]; d01 += r0[p] * v * r1[q]; d10 += r1[p] * v * r0[q]; d11 += r1[p] * v * r1[q];
+    }
+  const double sc = 0.25 * h * h;
+  if (type == 1) grad_mu[gi] = (d00 + d11) * sc;
+  else {
+    grad_mu[gi] = d00 * sc; grad_mu[gi + off] = d11 * sc;
+    if (type == 3) grad_mu[gi + 2 * off] = (d01 + d10) * sc;
+  }
+}
+
 }  // namespace adfem

@@ -575,6 +575,40 @@ def compute_space_varying_tangent_elasticity_matrix(mu, m, n, h, type=1):   # no
     return out.cpu().numpy() if as_numpy else out
 
 
+class _QuadStiff1SVT(torch.autograd.Function):
+    """compute_fem_stiffness_matrix1(compute_space_varying_tangent_elasticity_matrix(mu, ...), ...) fused (adfem_quad_stiffness1_svt)."""
+
+    @staticmethod
+    def forward(ctx, mu, type_, m, n, h):
+        if mu.dtype != torch.float64 or not mu.is_cuda:
+            raise TypeError("mu must be a float64 CUDA tensor")
+        mu = mu.contiguous().view(-1)
+        assert mu.numel() == 4 * m * n * type_
+        vv = torch.empty(64 * m * n, dtype=torch.float64, device=mu.device)
+        check(lib().adfem_quad_stiffness1_svt(_ptr(mu), C.c_int(type_), C.c_int(m), C.c_int(n), C.c_double(h), None, None, _ptr(vv), _stream()))
+        ctx.args = (type_, m, n, h, mu.numel())
+        return vv
+
+    @staticmethod
+    def backward(ctx, grad_vv):
+        type_, m, n, h, nmu = ctx.args
+        g = torch.empty(nmu, dtype=torch.float64, device=grad_vv.device)
+        check(lib().adfem_quad_stiffness1_svt_grad(_ptr(grad_vv.contiguous()), C.c_int(type_), C.c_int(m), C.c_int(n), C.c_double(h), _ptr(g), _stream()))
+        return g, None, None, None, None
+
+
+def compute_fem_stiffness_matrix1_from_mu(mu, m, n, h, type=1):   # noqa: A002
+    """`compute_fem_stiffness_matrix1(compute_space_varying_tangent_elasticity_matrix(mu, m, n, h, type), m, n, h)` (src/InvCore.jl:67-76,
+    206-211) in one device pass: the 4mn x 2 x 2 tangent tensor is never materialised.  Same `SparseTensor` as the two ops."""
+    m, n, h, type = int(m), int(n), float(h), int(type)
+    as_numpy = isinstance(mu, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(mu, dtype=np.float64).reshape(-1)).cuda() if as_numpy else mu
+    vv = _QuadStiff1SVT.apply(t, type, m, n, h)
+    N = (m + 1) * (n + 1)
+    S = SparseTensor(_quad_indices(0, 1, m, n, h, vv.device), vv, N, N)
+    return S.to_scipy() if as_numpy else S
+
+
 class _Dirichlet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vv, rhs, bdval, indices, bd1):

@@ -267,6 +267,11 @@ int adfem_quad_scalar_grad(int op, const double* grad_vv, long long m, long long
 int adfem_quad_source(const double* f, long long m, long long n, double h, double* rhs, void* stream);
 int adfem_quad_source_grad(const double* grad_rhs, long long m, long long n, double h, double* grad_f, void* stream);
 
+/* SpatialVaryingTangentElastic fused into UnivariateFemStiffness: the same 64mn slots (and 1-based ii / jj) as
+ * adfem_svt followed by adfem_quad_stiffness1(rank3 = 1), without materialising the 4mn x 2 x 2 tensor; mu[4mn * type], grad_mu likewise. */
+int adfem_quad_stiffness1_svt(const double* mu, int type, int m, int n, double h, long long* ii, long long* jj, double* vv, void* stream);
+int adfem_quad_stiffness1_svt_grad(const double* grad_vv, int type, int m, int n, double h, double* grad_mu, void* stream);
+
 /* Host-buffer convenience calls (synchronous; H2D + kernel + D2H).  Used for end-to-end timing. */
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host);
 int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host);

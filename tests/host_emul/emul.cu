@@ -421,6 +421,14 @@ int emul_tet_grid_scalar(int n, int l, const double* xs, const double* ys, const
   return 0;
 }
 
+// k_quad_stiff1_svt_fwd / _bwd of grid_ops.cu
+void emul_quad_stiffness1_svt(const double* mu, int type, int m, int n, double h, long long* ii, long long* jj, double* vv) {
+  for (long long t = 0; t < 4LL * m * n; t++) quad_stiff1_svt_fwd_body(t, mu, type, m, n, h, ii, jj, vv);
+}
+void emul_quad_stiffness1_svt_grad(const double* grad_vv, int type, int m, int n, double h, double* grad_mu) {
+  for (long long t = 0; t < 4LL * m * n; t++) quad_stiff1_svt_bwd_body(t, grad_vv, type, m, n, h, grad_mu);
+}
+
 void emul_plane_matrix(int mode, long long n, const double* E, const double* nu, double* H) {
   for (long long i = 0; i < n; i++) plane_matrix_body(mode, E[i], nu[i], H + 9 * i);
 }

@@ -549,3 +549,26 @@ def test_structured_tet_scalar_operators(emul, oracle, n, l):
     lhs, rhs = mv @ dv, gm @ coef
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0)
     assert abs(mv.sum() - (coef * o.weights).sum()) <= 1e-12 * abs(mv.sum())          # partition of unity: sum of M = int rho
+
+
+@pytest.mark.parametrize("type_", [1, 2, 3])
+def test_fused_svt_quad_stiffness(emul, oracle, type_):
+    """quad_ops.cuh: SpatialVaryingTangentElastic fused into UnivariateFemStiffness == the two oracle ops chained (slot order, 1-based indices,
+    values), and the mu-gradient == the two oracle adjoints chained."""
+    rng = np.random.default_rng(500 + type_)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_longlong))
+    for m, n, h in ((5, 3, 0.1), (1, 1, 2.0), (2, 7, 0.37)):
+        mu = rng.random(4 * m * n * type_) + 0.5
+        hmat = oracle.svt_fwd(mu, m, n, type_).reshape(4 * m * n, 2, 2)
+        ri, rj, rv = oracle.univariate_stiffness_fwd(hmat, m, n, h)
+        N = 64 * m * n
+        ii, jj, vv = np.full(N, -1, dtype=np.int64), np.full(N, -1, dtype=np.int64), np.full(N, np.nan)
+        emul.emul_quad_stiffness1_svt(d(mu), C.c_int(type_), C.c_int(m), C.c_int(n), C.c_double(h), lp(ii), lp(jj), d(vv))
+        assert np.array_equal(ii, ri) and np.array_equal(jj, rj)
+        close(vv, rv)
+        g = rng.standard_normal(N)
+        ref = oracle.svt_bwd(oracle.univariate_stiffness_bwd(g, m, n, h, True), m, n, type_)
+        gmu = np.full(len(mu), np.nan)
+        emul.emul_quad_stiffness1_svt_grad(d(g), C.c_int(type_), C.c_int(m), C.c_int(n), C.c_double(h), d(gmu))
+        close(gmu, ref)

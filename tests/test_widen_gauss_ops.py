@@ -501,3 +501,24 @@ def test_structured_tet_scalar_operators(oracle, n, l):
         (gm,) = torch.autograd.grad(M.values, k2, dev(dv))
         mass[on] = (npy(M.values), npy(gm))
     close(mass[1][0], mass[0][0]); close(mass[1][1], mass[0][1])
+
+
+@pytest.mark.parametrize("type_", [1, 2, 3])
+def test_fused_svt_quad_stiffness(oracle, type_):
+    """adfem_quad_stiffness1_svt[_grad]: SpatialVaryingTangentElastic fused into the structured compute_fem_stiffness_matrix1 == the two ops chained
+    (on the device and through the oracle)."""
+    rng = np.random.default_rng(95 + type_)
+    m, n, h = 23, 17, 0.05
+    mu = rng.random(4 * m * n * type_) + 0.5
+    hmat = oracle.svt_fwd(mu, m, n, type_).reshape(4 * m * n, 2, 2)
+    ri, rj, rv = oracle.univariate_stiffness_fwd(hmat, m, n, h)
+    mt = dev(mu).requires_grad_(True)
+    S = A.compute_fem_stiffness_matrix1_from_mu(mt, m, n, h, type_)
+    idx = npy(S.indices)
+    assert np.array_equal(idx[:, 0], ri - 1) and np.array_equal(idx[:, 1], rj - 1)
+    close(npy(S.values), rv)
+    g = rng.standard_normal(len(rv))
+    (gm,) = torch.autograd.grad(S.values, mt, dev(g))
+    close(npy(gm), oracle.svt_bwd(oracle.univariate_stiffness_bwd(g, m, n, h, True), m, n, type_))
+    S2 = A.compute_fem_stiffness_matrix1(A.compute_space_varying_tangent_elasticity_matrix(dev(mu), m, n, h, type_), m, n, h)     # unfused
+    close(npy(S.values), npy(S2.values), rel=1e-13)
