@@ -146,6 +146,13 @@ def main():
         b = 8 * (1 + 4 + 16) * 4          # per cell: mu in, hmat out + in, vv out (COO-compatible 64 slots per cell)
         print(json.dumps({"case": "config3_quad_stiffness1_svt", "cells": mq * mq, "fwd_ms": tf, "adj_ms": ta, "bytes_per_cell_per_direction": b,
                           "fwd_GBps": b * mq * mq / (tf * 1e-3) / 1e9, "adj_GBps": b * mq * mq / (ta * 1e-3) / 1e9}), flush=True)
+        # the same pair fused: the 4mn x 2 x 2 tensor is never written
+        ffwd = lambda: _lib.check(L.adfem_quad_stiffness1_svt(p(mu), 1, mq, mq, C.c_double(h), None, None, p(vv), st))
+        fadj = lambda: _lib.check(L.adfem_quad_stiffness1_svt_grad(p(gvv), 1, mq, mq, C.c_double(h), p(gmu), st))
+        tf, ta = timed(ffwd, args.steps), timed(fadj, args.steps)
+        b = 8 * (1 + 16) * 4
+        print(json.dumps({"case": "config3_quad_stiffness1_svt_fused", "cells": mq * mq, "fwd_ms": tf, "adj_ms": ta, "bytes_per_cell_per_direction": b,
+                          "fwd_GBps": b * mq * mq / (tf * 1e-3) / 1e9, "adj_GBps": b * mq * mq / (ta * 1e-3) / 1e9}), flush=True)
     if "4l" in cases or "4m" in cases:
         n = int(1000 * s)
         c, e = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2)
