@@ -79,7 +79,7 @@ struct adfem_mesh {
   int opt_grid_limit = 0;                   // > 0: cap the persistent grid (tests: few CTAs walk many tiles)
   int opt_coef_prefetch = 1;                // forward: register prefetch of the next tile's coefficients (P1 scalar operators)
   int opt_row_gather = 0;                   // scalar operators: one-thread-per-row forward (row_gather.cuh) instead of the row-tile kernel (off until measured)
-  bool rg_ok = false;                       // every CTA's 128 rows fit the shared-memory staging
+  int rg_rows = 0;                          // rows per CTA of the row-gather forward: 128, 64 or 32, the largest whose CTAs all fit the staging; 0 = none does
   int rge_max_entries = 0;                  // elasticity variant: most CSR entries of any CTA's 64 rows (sizes its dynamic shared memory)
   int opt_coef_presum = 0;                  // P1 elasticity: reduce the g coefficient blocks of an element to one in a streaming pre-pass (and expand the
                                             // adjoint's per-element block afterwards), so the tile kernels move NS*NS instead of g*NS*NS doubles per element
@@ -239,9 +239,13 @@ int ensure_pattern(adfem_mesh* m) {
   m->has_pattern = true;
   if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;
   if (m->tet_ok && !tet_pattern_matches(m->pat, m->tet_tab, m->tet_n, m->tet_l)) m->tet_ok = false;
-  m->rg_ok = true;
-  for (long long r0 = 0; r0 < m->pat.n && m->rg_ok; r0 += RG_THREADS)
-    if (m->pat.rowptr[std::min<long long>(r0 + RG_THREADS, m->pat.n)] - m->pat.rowptr[r0] > RG_CAP) m->rg_ok = false;
+  m->rg_rows = 0;
+  for (int rows = RG_THREADS; rows >= 32 && !m->rg_rows; rows /= 2) {
+    bool fits = true;
+    for (long long r0 = 0; r0 < m->pat.n && fits; r0 += rows)
+      if (m->pat.rowptr[std::min<long long>(r0 + rows, m->pat.n)] - m->pat.rowptr[r0] > RG_CAP) fits = false;
+    if (fits) m->rg_rows = rows;
+  }
   m->rge_max_entries = 0;
   for (long long r0 = 0; r0 < m->pat.n; r0 += RGE_THREADS)
     m->rge_max_entries = std::max<long long>(m->rge_max_entries, m->pat.rowptr[std::min<long long>(r0 + RGE_THREADS, m->pat.n)] - m->pat.rowptr[r0]);
@@ -810,14 +814,15 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && m->opt_row_gather) {
     if (int rc = ensure_pattern(m)) return rc;
-    if (m->rg_ok) {
-      const unsigned nb = blocks_for(m->hm.ndof, RG_THREADS);
+    if (m->rg_rows) {
+      const int rgt = m->rg_rows;
+      const unsigned nb = blocks_for(m->hm.ndof, rgt);
 #define CALL_RG(DIM, DEG)                                                                                                                              \
   if (op == ADFEM_OP_LAPLACE)                                                                                                                          \
-    k_row_gather_fwd<DIM, DEG, OP_LAPLACE><<<nb, RG_THREADS, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,   \
+    k_row_gather_fwd<DIM, DEG, OP_LAPLACE><<<nb, rgt, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,   \
                                                                      m->d_rowptr.p, m->d_colind.p, coef, vals);                                        \
   else                                                                                                                                                 \
-    k_row_gather_fwd<DIM, DEG, OP_MASS><<<nb, RG_THREADS, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,      \
+    k_row_gather_fwd<DIM, DEG, OP_MASS><<<nb, rgt, 0, st>>>(dev_mesh(m, m->opt_area_csr), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p,      \
                                                                   m->d_rowptr.p, m->d_colind.p, coef, vals)
       DISPATCH_ELEM(m, CALL_RG);
 #undef CALL_RG

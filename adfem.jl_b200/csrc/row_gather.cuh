@@ -5,7 +5,8 @@
 // its rows — one contiguous run of the values array — with coalesced stores.  No tile plan is needed (the P2 tile blobs are 330 B per element,
 // more than the algorithmic traffic): the mesh-static inputs are the adjacency (5 B per incidence), the connectivity and the CSR pattern.
 // A local matrix row is evaluated once per dof of the element (d times the geometry / basis work of the tile kernels, ~3 kflop per P2 triangle,
-// far below the fp64 roof at this traffic).  Rows are limited by the shared-memory staging: RG_CAP values per CTA of RG_THREADS rows.
+// far below the fp64 roof at this traffic).  Rows are limited by the shared-memory staging: RG_CAP values per CTA of 128, 64 or 32 rows (the
+// host picks the largest count whose CTAs all fit; P2 tetrahedra run with 32).
 // Host + device bodies (tests/host_emul/).
 #pragma once
 #include "device_fem.cuh"
@@ -118,17 +119,18 @@ ADFEM_HD void rg_row_elast(const DevMesh& m, const long long* adj_ptr, const int
 }
 
 #ifdef __CUDACC__
+// blockDim.x = rows per CTA (128, 64 or 32: the largest whose CTAs all fit RG_CAP, chosen on the host from the pattern)
 template <int DIM, int DEG, int OP>
 __global__ void __launch_bounds__(RG_THREADS) k_row_gather_fwd(DevMesh m, const long long* __restrict__ adj_ptr, const int* __restrict__ adj_elem,
                                                                 const uint8_t* __restrict__ adj_loc, const long long* __restrict__ rowptr,
                                                                 const int* __restrict__ colind, const double* __restrict__ coef, double* __restrict__ vals) {
   __shared__ double acc[RG_CAP];
-  const int r0 = blockIdx.x * RG_THREADS, r = r0 + threadIdx.x, r1 = min(r0 + RG_THREADS, m.ndof);
+  const int rows = blockDim.x, r0 = blockIdx.x * rows, r = r0 + threadIdx.x, r1 = min(r0 + rows, m.ndof);
   const long long rs0 = rowptr[r0];
   if (r < m.ndof) rg_row<DIM, DEG, OP>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, r, rs0, coef, acc);
   __syncthreads();
   const int total = (int)(rowptr[r1] - rs0);
-  for (int idx = threadIdx.x; idx < total; idx += RG_THREADS) vals[rs0 + idx] = acc[idx];
+  for (int idx = threadIdx.x; idx < total; idx += rows) vals[rs0 + idx] = acc[idx];
 }
 
 template <int DIM>

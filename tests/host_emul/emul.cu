@@ -94,10 +94,10 @@ static void run_grid_scatter(const GridTri& gt, int heron, const QuadRule& rule,
 // k_row_gather_fwd (row_gather.cuh): every CTA as a loop over its threads (phase 1) and the flat copy (phase 2); -1 when a CTA's rows exceed RG_CAP
 template <int DIM, int DEG, int OP>
 static int run_row_gather(const DevMesh& m, const long long* ap, const int* ae, const uint8_t* al, const long long* rowptr, const int* colind,
-                          const double* coef, double* vals) {
+                          const double* coef, double* vals, int rows) {
   static double acc[RG_CAP];
-  for (int r0 = 0; r0 < m.ndof; r0 += RG_THREADS) {
-    const int r1 = r0 + RG_THREADS < m.ndof ? r0 + RG_THREADS : m.ndof;
+  for (int r0 = 0; r0 < m.ndof; r0 += rows) {
+    const int r1 = r0 + rows < m.ndof ? r0 + rows : m.ndof;
     const long long rs0 = rowptr[r0];
     const int total = (int)(rowptr[r1] - rs0);
     if (total > RG_CAP) return -1;
@@ -343,13 +343,13 @@ int emul_tet_grid_elast_adj(int n, int l, const double* xs, const double* ys, co
 
 int emul_row_gather_fwd(int dim, int degree, int order, int nv, int ne, int ndof, const double* coords, const int* verts, const int* conn,
                         const long long* adj_ptr, const int* adj_elem, const uint8_t* adj_loc, const long long* rowptr, const int* colind, int op,
-                        const double* coef, double* vals) {
+                        const double* coef, double* vals, int rows) {
   bool ok;
   const DevMesh m = make_mesh(dim, degree, order, nv, ne, ndof, coords, verts, conn, ok);
   if (!ok || (op != OP_LAPLACE && op != OP_MASS)) return 1;
   int rc = 1;
-#define CALL_RG(DIM, DEG) rc = op == OP_LAPLACE ? run_row_gather<DIM, DEG, OP_LAPLACE>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, coef, vals) \
-                                                  : run_row_gather<DIM, DEG, OP_MASS>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, coef, vals)
+#define CALL_RG(DIM, DEG) rc = op == OP_LAPLACE ? run_row_gather<DIM, DEG, OP_LAPLACE>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, coef, vals, rows) \
+                                                  : run_row_gather<DIM, DEG, OP_MASS>(m, adj_ptr, adj_elem, adj_loc, rowptr, colind, coef, vals, rows)
   EMUL_DISPATCH(dim, degree, CALL_RG);
 #undef CALL_RG
   return rc;

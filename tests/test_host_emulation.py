@@ -391,7 +391,7 @@ def test_structured_tet_elasticity_warp_phases(emul, oracle, n, l):
     close(grad, expect)
 
 
-@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1)])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 def test_row_gather_forward(emul, oracle, dim, degree):
     """row_gather.cuh: one thread per dof row (adjacency walk, local-matrix row in registers, binary search of the column positions, CTA-wide
     coalesced copy) for Laplace and mass against the canonical CSR of the oracle's COO."""
@@ -412,9 +412,14 @@ def test_row_gather_forward(emul, oracle, dim, degree):
         rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
         rp64, ci32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(ci, dtype=np.int32)
         vals = np.full(len(ref), np.nan)
-        rc = emul.emul_row_gather_fwd(*T._mesh_args(), *T._adj_args(), rp64.ctypes.data_as(C.POINTER(C.c_longlong)),
-                                      ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(op), d(coef), d(vals))
+        for rows in (128, 64, 32):                     # the host picks the largest row count whose CTAs fit the staging (P2 tetrahedra: 32)
+            vals = np.full(len(ref), np.nan)
+            rc = emul.emul_row_gather_fwd(*T._mesh_args(), *T._adj_args(), rp64.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                          ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(op), d(coef), d(vals), C.c_int(rows))
+            if rc == 0:
+                break
         assert rc == 0, rc
+        assert rows == (32 if (dim, degree) == (3, 2) else 128) or dim == 3
         close(vals, ref)
 
 
@@ -542,7 +547,7 @@ def test_structured_tet_scalar_operators(emul, oracle, n, l):
     # mass: forward equals the general row-gather body bit for bit; adjoint is its transpose
     mv, mref = np.full(len(ref), np.nan), np.full(len(ref), np.nan)
     assert emul.emul_tet_grid_scalar(*args, C.c_int(1), C.c_int(0), lp, d(coef), d(mv)) == 0
-    assert emul.emul_row_gather_fwd(*T._mesh_args(), *T._adj_args(), lp, ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(1), d(coef), d(mref)) == 0
+    assert emul.emul_row_gather_fwd(*T._mesh_args(), *T._adj_args(), lp, ci32.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(1), d(coef), d(mref), C.c_int(128)) == 0
     assert np.array_equal(mv, mref)
     gm = np.full(o.ngauss, np.nan)
     assert emul.emul_tet_grid_scalar(*args, C.c_int(1), C.c_int(1), lp, d(dv), d(gm)) == 0

@@ -386,8 +386,8 @@ def test_structured_tet_elasticity_forward(oracle, n, l):
 
 @pytest.mark.parametrize("dim,degree", [(2, 2), (2, 1), (3, 1), (3, 2)])
 def test_row_gather_forward(oracle, dim, degree):
-    """Option "row_gather": one-thread-per-row forward for Laplace and mass (csrc/row_gather.cuh) against the oracle; P2 tetrahedra have rows too
-    long for its staging and silently keep the tile kernel."""
+    """Option "row_gather": one-thread-per-row forward for Laplace and mass (csrc/row_gather.cuh) against the oracle; the rows per CTA adapt to the
+    row lengths (128 for triangles and P1 tetrahedra, fewer for P2 tetrahedra)."""
     rng = np.random.default_rng(80 + 10 * dim + degree)
     if dim == 2:
         c, e = meshgen.jitter_unstructured(41, 37, 0.02, seed=12)
