@@ -90,7 +90,8 @@ struct adfem_mesh {
   // structured triangulation Mesh(m, n, h) (tri_grid.cuh): detected from the arrays, no mesh-static index data is read
   bool grid_ok = false;
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
-  int opt_grid_elast = 0;                   // P1 elasticity on the structured triangulation: index-free kernels of grid_elast.cuh (off until measured on a GPU)
+  int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
+  int opt_tet_scalar = 0;                   // scalar P1 operators on Mesh3(n,n,l,h) through tet_scalar.cuh: measured slower than the tile kernels (0.358 vs 0.151 ms), kept opt-in
   DevBuf<double> grid_xs, grid_ys;
   // structured tetrahedral grid Mesh3(n, n, l, h) (tet_grid.cuh): detected from the arrays; used by the opt-in elasticity forward kernel
   bool tet_ok = false;
@@ -567,7 +568,7 @@ int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaSt
 
 // scalar P1 operators on the structured tetrahedral grid (tet_scalar.cuh), same opt-in switch as the elasticity kernels
 bool use_tet_scalar(adfem_mesh* m, int op) {
-  return op != ADFEM_OP_STIFFNESS && m->opt_grid_elast && m->opt_structured && m->tet_ok && !m->host_only && m->hm.degree == 1;
+  return op != ADFEM_OP_STIFFNESS && m->opt_tet_scalar && m->opt_structured && m->tet_ok && !m->host_only && m->hm.degree == 1;
 }
 int launch_tet_scalar(adfem_mesh* m, int op, bool adjoint, const double* in, double* out, cudaStream_t st) {
   const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
@@ -728,6 +729,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
+  else if (k == "structured_tet_scalar") m->opt_tet_scalar = value != 0;
   else if (k == "row_gather") m->opt_row_gather = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;
   else if (k == "grid_occupancy") m->opt_grid_occupancy = (int)value;
@@ -807,7 +809,7 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   const int nc = op == ADFEM_OP_STIFFNESS ? m->hm.dim : 1;
   if ((op != ADFEM_OP_STIFFNESS || m->opt_grid_elast) && m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }      // validates the closed-form row pointers
   if (use_grid_elast(m, op)) return launch_grid_elast(m, false, coef, vals, st);
-  if (m->tet_ok && m->opt_grid_elast) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
+  if (m->tet_ok && (m->opt_tet_scalar || (m->opt_grid_elast && op == ADFEM_OP_STIFFNESS))) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
   if (use_tet_grid(m, op)) return launch_tet_grid_fwd(m, coef, vals, st);
   if (use_tet_scalar(m, op)) return launch_tet_scalar(m, op, false, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && use_grid(m))

@@ -688,6 +688,11 @@ def pcl_impose_Dirichlet_boundary_conditions(indices, bdnode, outdof):
     bd = torch.as_tensor(np.asarray(bdnode), dtype=torch.int64, device="cuda") + 1
     sN = ind.shape[0]
     N = int(max(ind.max().item() if sN else -1, (bd.max().item() - 1) if bd.numel() else -1)) + 1
+    need = int(lib().adfem_impose_dirichlet_count(_ptr(ind), C.c_longlong(sN), _ptr(bd), C.c_longlong(bd.numel()), C.c_longlong(N), _stream()))
+    if need < 0:
+        raise _lib.AdfemError(_lib.last_error())
+    if int(outdof) < need:      # the kernel writes column kpos[k] < nkeep of every kept slot: a smaller J would be written out of bounds
+        raise ValueError("outdof = %d is smaller than the %d output slots of impose_Dirichlet_boundary_conditions" % (int(outdof), need))
     Jt = torch.zeros(int(outdof), sN, dtype=torch.float64, device="cuda")  # column-major sN x outdof
     check(lib().adfem_pcl_impose_dirichlet(_ptr(ind), C.c_longlong(sN), _ptr(bd), C.c_longlong(bd.numel()), C.c_longlong(N), _ptr(Jt), _stream()))
     return Jt.t()

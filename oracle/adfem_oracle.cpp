@@ -6,15 +6,24 @@
 // and bench.py's cpu_baseline / --impl reference legs may load this library; it is the checker
 // and the reported CPU baseline, never part of the product path (libadfem_cuda.so).
 //
-// PARITY STATUS: "parity unpinned" for matrix/gradient VALUES.  The reference cannot be built in
+// PARITY STATUS: pinned by INDEPENDENT EXACT GOLDENS, not by reference-made files.  The reference cannot be built in
 // this environment (needs TensorFlow-1.x headers, MFEM, Eigen, Julia) and the golden files its own
-// tests read (fenics/A.txt, A2.txt, edges.txt) are not shipped.  What IS pinned against the
-// reference's tests (tests/test_oracle_known_answers.py):
+// tests read (fenics/A.txt, A2.txt, edges.txt of deps/MFEM/FemLaplace1/ftest.jl:6-33) are not shipped, so
+// tests/golden/make_exact_goldens.py recomputes those matrices — and their mass / source / elasticity / tetrahedral
+// siblings — in rational arithmetic (sympy) from the mesh arrays alone, on the reference's own test mesh Mesh(8,8,1/8)
+// (P1, P2), a distorted renumbered triangulation, Mesh3(2,2,2,1/2) and a distorted tetrahedral cube; the oracle and the
+// CUDA library both match them to 1e-12 (tests/test_exact_goldens.py), edge dofs matched through the `edges` table as
+// ftest.jl:28-31 does.  Also pinned against the reference's tests (tests/test_oracle_known_answers.py):
 //   * test/MFEM2.jl:7-27         Mesh(2,2,0.5): ngauss==24, area==0.125
 //   * test/MFEM/MCore.jl:1-14    4-point segment rule values (lorder=6)
 //   * deps/MFEM/FemSource1/ftest.jl:4-16   source(c) == mass(c)*1
-//   * hand-derivable 5-point stencil of UnitSquareMesh(8,8,"left") P1 Laplace
+//   * quadrature exactness degrees (triangle order 2/4, tetrahedron order 2/4 incl. the negative weight)
 //   * polynomial exactness / K*1=0 / sum(M)=area / finite-difference gradient convergence
+// What stays UNVERIFIABLE without MFEM itself: (1) the ORDER of the Gauss points inside an element (coefficient arrays are
+// indexed e*g+k) — every operator is invariant to it as long as coefficients are sampled at `gauss_nodes`, which is the
+// only way the reference's API produces them, and the exact goldens test exactly that; (2) the NUMBERS MFEM gives to
+// edges (DSTable order) — observable only through `mesh.edges`, which is returned consistently with the P2 dofs.
+// The COO slot ORDER (which duplicate comes first) follows the reference's loops by reading, not by execution.
 //
 // Third-party arithmetic that is NOT under /root/reference and is restated from its published
 // algorithm (MFEM, version unpinned by the reference — src/ToolChain.jl:8 calls install_mfem()):

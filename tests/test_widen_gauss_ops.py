@@ -3,10 +3,7 @@ matrix-free terms (csrc/gauss_ops.cu), structured Q1 siblings, coef_presum, the 
 (grid_elast.cuh, tet_grid.cuh), the structured scatter kernels and row_gather — against the oracle, through the C ABI (handle API via the Python
 mirror, and the reference's legacy host-pointer symbols).
 
-NOT YET RUN ON A GPU: the session that wrote these tests had no GPU minutes left.  The arithmetic of every kernel tested here is checked on the
-host (tests/test_host_emulation.py), but the launch glue, the Python wrappers and the tests themselves have never executed on a device, so this
-module is skipped unless ADFEM_RUN_UNVERIFIED=1 — the first GPU call of round 2 (scripts/gpu_round2_first.sh) sets it — rather than let an
-untested test script decide the colour of the parity suite of rows (a)-(e).  The file name sorts after the core parity files for the same reason."""
+First run on a B200 in round 2 (profiles/pytest_gpu_r02_first.log: 34 passed); part of the normal `-m gpu` suite since."""
 import ctypes as C
 import os
 
@@ -17,9 +14,7 @@ import adfem_jl_b200 as A
 from adfem_jl_b200 import meshgen
 
 torch = pytest.importorskip("torch")
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ADFEM_RUN_UNVERIFIED") != "1",
-                                 reason="written without GPU time at the end of round 1; set ADFEM_RUN_UNVERIFIED=1 (scripts/gpu_round2_first.sh does)")]
+pytestmark = pytest.mark.gpu
 
 
 def close(a, b, rel=1e-12):
@@ -477,7 +472,7 @@ def test_structured_tet_scatter_operators(oracle):
 
 @pytest.mark.parametrize("n,l", [(4, 3), (1, 1)])
 def test_structured_tet_scalar_operators(oracle, n, l):
-    """Option "structured_elasticity" also switches the scalar P1 operators on Mesh3(n, n, l, h) to the index-arithmetic kernels of
+    """Option "structured_tet_scalar" (opt-in: measured slower than the tile kernels) switches the scalar P1 operators on Mesh3(n, n, l, h) to the index-arithmetic kernels of
     csrc/tet_scalar.cuh (FemLaplaceScalarT, mass; forward and adjoint): against the oracle and the general tile kernels."""
     rng = np.random.default_rng(75 + n + l)
     c, e = meshgen.tet_grid(n, n, l, 0.2)
@@ -489,7 +484,7 @@ def test_structured_tet_scalar_operators(oracle, n, l):
     expect = o.laplace_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, o.ndof))
     mass = {}
     for on in (1, 0):
-        m.set_option("structured_elasticity", on)
+        m.set_option("structured_tet_scalar", on)
         k = dev(coef).requires_grad_(True)
         T = A.compute_fem_laplace_matrix1(k, m, mode="csr")
         assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
