@@ -50,6 +50,8 @@ def lib():
         L.adfem_plan_array.restype = C.c_longlong
         L.adfem_gauss_op_len.restype = C.c_longlong
         L.adfem_impose_dirichlet_count.restype = C.c_longlong
+        L.adfem_dist_info.restype = C.c_longlong
+        L.adfem_dist_destroy.restype = None
         L.init_nnfem_mesh.restype = c_lp
         L.init_nnfem_mesh3.restype = c_lp
         L.adfem_mesh_info.argtypes = [C.c_void_p, C.c_int]

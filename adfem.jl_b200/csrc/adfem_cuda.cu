@@ -19,6 +19,7 @@
 #include "tri_grid.cuh"
 #include "grid_elast.cuh"
 #include "tet_grid.cuh"
+#include "tet_node.cuh"
 #include "row_gather.cuh"
 #include "tet_scalar.cuh"
 
@@ -91,6 +92,9 @@ struct adfem_mesh {
   bool grid_ok = false;
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
+  int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh)
+  bool tet_const_ready = false;
+  DevBuf<double> tet_spacing;              // [1/hx | 1/hy | 1/hz | hx | hy | hz] per cube and axis (tet_node.cuh)
   int opt_tet_scalar = 0;                   // scalar P1 operators on Mesh3(n,n,l,h) through tet_scalar.cuh: measured slower than the tile kernels (0.358 vs 0.151 ms), kept opt-in
   DevBuf<double> grid_xs, grid_ys;
   // structured tetrahedral grid Mesh3(n, n, l, h) (tet_grid.cuh): detected from the arrays; used by the opt-in elasticity forward kernel
@@ -231,7 +235,7 @@ int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_thread
 // fits the register file (seen in ncu: occupancy limit 1, 15 % achieved), so they run 256 threads x 2 CTAs with 110 KB tiles.
 bool heavy_kernel(const adfem_mesh* m, int nc) { return m->hm.degree == 2 || (nc > 1 && m->hm.dim == 3); }
 int tile_threads_of(const adfem_mesh* m, int nc) { return m->opt_tile_threads > 0 ? m->opt_tile_threads : (heavy_kernel(m, nc) ? 256 : 320); }
-size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : (heavy_kernel(m, nc) ? 110 * 1024 : 72 * 1024); }
+size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : (heavy_kernel(m, nc) ? ((m->hm.degree == 2 && nc == 1) ? 104 : 110) * 1024 : 72 * 1024); }   // P2 scalar kernels keep up to 5 KB of static moment tables
 
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
@@ -546,6 +550,29 @@ bool use_tet_grid(adfem_mesh* m, int op) {
   return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && m->opt_structured && m->tet_ok && !m->host_only && m->hm.degree == 1;
 }
 int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStream_t st) {
+  if (m->opt_tet_node) {
+    const size_t need = tn_scratch_doubles(m->tet_n, m->tet_l);
+    if (m->presum_buf.n < need) CU_TRY(m->presum_buf.alloc(need));
+    if (!m->tet_const_ready) {
+      TetNodeConst C; build_tet_node_const(m->tet_tab, C);
+      CU_TRY(cudaMemcpyToSymbol(c_tn, &C, sizeof(C)));
+      CU_TRY(cudaFuncSetAttribute(k_tet_node_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+      std::vector<double> spc;
+      for (int inv = 1; inv >= 0; inv--)
+        for (int a = 0; a < 3; a++)
+          for (size_t c = 0; c + 1 < m->tet_axes[a].size(); c++) { const double hc = m->tet_axes[a][c + 1] - m->tet_axes[a][c]; spc.push_back(inv ? 1.0 / hc : hc); }
+      CU_TRY(upload(m->tet_spacing, spc));
+      m->tet_const_ready = true;
+    }
+    const int n = m->tet_n, l = m->tet_l, nxb = (n + TPX_CUBES - 1) / TPX_CUBES;
+    k_tet_presum_x<<<(unsigned)((size_t)n * l * nxb * 5), TPX_THREADS, 0, st>>>(n, l, m->hm.rule, m->hm.g, coef, m->presum_buf.p);
+    const GridTet gt{n, l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
+    const double* q = m->tet_spacing.p;
+    const TetSpacing sp{q, q + n, q + 2 * n, q + 2 * n + l, q + 3 * n + l, q + 4 * n + l};
+    k_tet_node_fwd<<<blocks_for(m->hm.nv, TN_NODES), TN_THREADS, TN_SMEM_BYTES, st>>>(gt, sp, m->pat.nnz, m->d_rowptr.p, m->presum_buf.p, vals);
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
   if (int rc = ensure_presum_buf(m)) return rc;
   if (int rc = launch_presum_coef(dev_mesh(m, m->opt_area_csr), 36, coef, m->presum_buf.p, st)) return rc;
   const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
@@ -729,6 +756,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
+  else if (k == "tet_node") m->opt_tet_node = value != 0;
   else if (k == "structured_tet_scalar") m->opt_tet_scalar = value != 0;
   else if (k == "row_gather") m->opt_row_gather = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;

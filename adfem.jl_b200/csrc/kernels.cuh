@@ -460,6 +460,148 @@ __device__ __forceinline__ void local_matrix(const DevMesh& m, const Geom<DIM>& 
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// P2 scalar operators in MOMENT FORM (round 2).  On an affine simplex grad phi_p = sum_a (d phi_p / d lambda_a) grad lambda_a, so with
+// S_ab = grad lambda_a . grad lambda_b |det| the P2 Laplace matrix needs only NV(2NV+1) coefficient moments (21 on triangles, 36 on
+// tetrahedra) against mesh-independent tables instead of D(D+1)/2 gradient products per Gauss point:
+//   vertex p, vertex q        : S_pq MV(p,q)                                MV(p,q) = sum_k c_k w_k alpha_p alpha_q,  alpha_p = 4 L_p - 1
+//   vertex p, edge (a,b)      : 4 (S_pb AV[p][a] + S_pa AV[p][b])           AV[p][i] = sum_k c_k w_k alpha_p L_i
+//   edge (a,b), edge (c,d)    : 16 (S_bd BL(a,c) + S_bc BL(a,d) + S_ad BL(b,c) + S_ac BL(b,d)),   BL(i,m) = sum_k c_k w_k L_i L_m
+// (552 -> ~200 fp64 operations per P2 triangle, 3300 -> ~600 per P2 tetrahedron; same sums, different association: agreement with the
+// per-point form is ~1e-15 relative).  The mass matrix uses the table phi_p(k) phi_q(k) w_k the same way.  Tables are built by every CTA
+// in its prologue from the quadrature rule into shared memory, layout tab[k * NM + m].
+template <int DIM> struct P2M {
+  static constexpr int NV = DIM + 1, NE = NV * (NV - 1) / 2, D = NV + NE, NS = NV * (NV + 1) / 2;
+  static constexpr int NM = 2 * NS + NV * NV;        // Laplace moments: MV (NS) | AV (NV*NV) | BL (NS)
+  static constexpr int NA = D * (D + 1) / 2;         // packed upper triangle of the local matrix
+  __host__ __device__ static constexpr int sym(int i, int j) { return i <= j ? i * NV - i * (i - 1) / 2 + (j - i) : j * NV - j * (j - 1) / 2 + (i - j); }
+};
+template <int DIM, int OP> __host__ __device__ constexpr int p2_table_rows() { return OP == OP_LAPLACE ? P2M<DIM>::NM : P2M<DIM>::NA; }
+
+template <int DIM, int OP> ADFEM_HD void p2_build_table(const QuadRule& rule, int g, int tid, int nth, double* tab) {
+  using M = P2M<DIM>;
+  constexpr int R = p2_table_rows<DIM, OP>();
+  for (int idx = tid; idx < R * g; idx += nth) {
+    const int k = idx / R, mm = idx - R * k;
+    double L[DIM + 1]; bary<DIM>(rule, k, L);
+    double v;
+    if (OP == OP_LAPLACE) {
+      int i = 0, j = 0, kind = 0, c = 0;                 // decode mm -> (kind, i, j)
+      for (int a = 0; a < M::NV; a++) for (int b = a; b < M::NV; b++) { if (c == mm) { kind = 0; i = a; j = b; } c++; }
+      for (int a = 0; a < M::NV; a++) for (int b = 0; b < M::NV; b++) { if (c == mm) { kind = 1; i = a; j = b; } c++; }
+      for (int a = 0; a < M::NV; a++) for (int b = a; b < M::NV; b++) { if (c == mm) { kind = 2; i = a; j = b; } c++; }
+      double Li = 0, Lj = 0;
+      for (int a = 0; a <= DIM; a++) { Li = a == i ? L[a] : Li; Lj = a == j ? L[a] : Lj; }
+      v = kind == 0 ? (4.0 * Li - 1.0) * (4.0 * Lj - 1.0) : (kind == 1 ? (4.0 * Li - 1.0) * Lj : Li * Lj);
+    } else {
+      double phi[M::D]; basis_val<DIM, 2>(L, phi);
+      int c = 0; v = 0.0;
+      for (int a = 0; a < M::D; a++) for (int b = a; b < M::D; b++) { if (c == mm) v = phi[a] * phi[b]; c++; }
+    }
+    tab[idx] = v * rule.w[k];
+  }
+}
+
+// S_ab = grad lambda_a . grad lambda_b * wscale, packed symmetric (P2M::sym)
+template <int DIM> __device__ __forceinline__ void p2_metric(const Geom<DIM>& G, double* S) {
+  int i = 0;
+#pragma unroll
+  for (int a = 0; a <= DIM; a++)
+#pragma unroll
+    for (int b = a; b <= DIM; b++) S[i++] = dotg<DIM>(G.gL[a], G.gL[b]) * G.wscale;
+}
+
+// forward: packed upper triangle of the P2 local matrix (same slot order as local_matrix_scalar) from the staged coefficients cf(k)
+template <int DIM, int OP, typename Coef, typename Put>
+__device__ __forceinline__ void p2_local_matrix(int g, const Geom<DIM>& G, const double* __restrict__ tab, Coef cf, Put put) {
+  using M = P2M<DIM>;
+  constexpr int R = p2_table_rows<DIM, OP>(), NV = M::NV, NE = M::NE;
+  double mom[R];
+#pragma unroll
+  for (int i = 0; i < R; i++) mom[i] = 0.0;
+  for (int k = 0; k < g; k++) {
+    const double c = cf(k);
+    const double* t = tab + k * R;
+#pragma unroll
+    for (int i = 0; i < R; i++) mom[i] += c * t[i];
+  }
+  if (OP == OP_MASS) {
+#pragma unroll
+    for (int i = 0; i < R; i++) put(i, mom[i] * G.wscale);
+    return;
+  }
+  double S[M::NS]; p2_metric<DIM>(G, S);
+  const double* MV = mom; const double* AV = mom + M::NS; const double* BL = mom + M::NS + NV * NV;
+  int i = 0;
+#pragma unroll
+  for (int p = 0; p < NV; p++) {
+#pragma unroll
+    for (int q = p; q < NV; q++) put(i++, S[M::sym(p, q)] * MV[M::sym(p, q)]);
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+      int a, b; edge_ends<DIM>(j, a, b);
+      put(i++, 4.0 * (S[M::sym(p, b)] * AV[p * NV + a] + S[M::sym(p, a)] * AV[p * NV + b]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NE; j++) {
+    int a, b; edge_ends<DIM>(j, a, b);
+#pragma unroll
+    for (int j2 = j; j2 < NE; j2++) {
+      int c, d; edge_ends<DIM>(j2, c, d);
+      put(i++, 16.0 * (S[M::sym(b, d)] * BL[M::sym(a, c)] + S[M::sym(b, c)] * BL[M::sym(a, d)] + S[M::sym(a, d)] * BL[M::sym(b, c)] +
+                       S[M::sym(a, c)] * BL[M::sym(b, d)]));
+    }
+  }
+}
+
+// adjoint: gs = packed, symmetrised upstream gradient of the local matrix; out(k, d loss / d c_k)
+template <int DIM, int OP, typename Out>
+__device__ __forceinline__ void p2_local_adjoint(int g, const Geom<DIM>& G, const double* __restrict__ tab, const double* gs, Out out) {
+  using M = P2M<DIM>;
+  constexpr int R = p2_table_rows<DIM, OP>(), NV = M::NV, NE = M::NE;
+  double cm[R];
+  if (OP == OP_MASS) {
+#pragma unroll
+    for (int i = 0; i < R; i++) cm[i] = gs[i] * G.wscale;
+  } else {
+#pragma unroll
+    for (int i = 0; i < R; i++) cm[i] = 0.0;
+    double S[M::NS]; p2_metric<DIM>(G, S);
+    double* MV = cm; double* AV = cm + M::NS; double* BL = cm + M::NS + NV * NV;
+    int i = 0;
+#pragma unroll
+    for (int p = 0; p < NV; p++) {
+#pragma unroll
+      for (int q = p; q < NV; q++) MV[M::sym(p, q)] += gs[i++] * S[M::sym(p, q)];
+#pragma unroll
+      for (int j = 0; j < NE; j++) {
+        int a, b; edge_ends<DIM>(j, a, b);
+        const double v = 4.0 * gs[i++];
+        AV[p * NV + a] += v * S[M::sym(p, b)]; AV[p * NV + b] += v * S[M::sym(p, a)];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+      int a, b; edge_ends<DIM>(j, a, b);
+#pragma unroll
+      for (int j2 = j; j2 < NE; j2++) {
+        int c, d; edge_ends<DIM>(j2, c, d);
+        const double v = 16.0 * gs[i++];
+        BL[M::sym(a, c)] += v * S[M::sym(b, d)]; BL[M::sym(a, d)] += v * S[M::sym(b, c)];
+        BL[M::sym(b, c)] += v * S[M::sym(a, d)]; BL[M::sym(b, d)] += v * S[M::sym(a, c)];
+      }
+    }
+  }
+  for (int k = 0; k < g; k++) {
+    const double* t = tab + k * R;
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) v += cm[i] * t[i];
+    out(k, v);
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Scalar operators: contract the upstream gradients `g(p, q)` of one element's local matrix with its shape tables and
@@ -705,6 +847,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   // and the copies for tile i+1 are issued after the barrier that ends phase A of tile i, so one buffer suffices
   // P1 elasticity (CST): the raw coefficient blocks [nel][cpe] of the tile, copied with a flat (coalesced) index by all threads.
   double* cst_all = loc + (size_t)(OP == OP_STIFFNESS ? Dt * Dt : D * (D + 1) / 2) * tp.max_elems;
+  // P2 scalar operators: moment tables of the quadrature rule (p2_local_matrix), built once per CTA
+  constexpr bool P2TAB = DEG == 2 && OP != OP_STIFFNESS;
+  __shared__ double p2tab[P2TAB ? p2_table_rows<DIM, P2TAB ? OP : OP_LAPLACE>() * MAX_QP : 1];
+  if constexpr (P2TAB) p2_build_table<DIM, OP>(m.rule, g, tid, nth, p2tab);
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
@@ -781,7 +927,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
       const double* cs = cst_all;
       for (int le = tid; le < V.nel; le += nth) {
         Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
-        local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+        if constexpr (P2TAB) p2_local_matrix<DIM, OP>(g, G, p2tab, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+        else local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
       }
     } else {
       for (int le = tid; le < V.nel; le += nth) {
@@ -866,6 +1013,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
   const size_t sd_stride = (size_t)NC * NC * ap.max_nnz;
   double* gacc = sd_all + 2 * sd_stride;                   // P1 elasticity only: [NS*NS][nel] gradient matrices of the tile's elements
   (void)gacc;
+  constexpr bool P2TAB = DEG == 2 && OP != OP_STIFFNESS;
+  __shared__ double p2tab[P2TAB ? p2_table_rows<DIM, P2TAB ? OP : OP_LAPLACE>() * MAX_QP : 1];
+  if constexpr (P2TAB) p2_build_table<DIM, OP>(m.rule, m.g, tid, nth, p2tab);
   if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
   __syncthreads();
   if (R.count == 0) return;
@@ -905,7 +1055,19 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_adj(DevMesh m, long l
 #pragma unroll
           for (int w = 0; w < W; w++) pk[p][w] = V.gpk[(p * W + w) * V.nel + le];
         }
-        local_adjoint<DIM, DEG, OP>(m, G, e, [&](int p, int q) { return sd[rb[p] + ((pk[p][q >> 2] >> (8 * (q & 3))) & 0xffu)]; }, grad_coef);
+        auto dK = [&](int p, int q) { return sd[rb[p] + ((pk[p][q >> 2] >> (8 * (q & 3))) & 0xffu)]; };
+        if constexpr (P2TAB) {
+          double gs[D * (D + 1) / 2];
+          { int i = 0;
+#pragma unroll
+            for (int p = 0; p < D; p++)
+#pragma unroll
+              for (int q = p; q < D; q++) gs[i++] = (q == p) ? dK(p, p) : dK(p, q) + dK(q, p); }
+          double* ge = grad_coef + (size_t)e * m.g;
+          p2_local_adjoint<DIM, OP>(m.g, G, p2tab, gs, [&](int k, double v) { ge[k] = v; });
+        } else {
+          local_adjoint<DIM, DEG, OP>(m, G, e, dK, grad_coef);
+        }
       } else {
         auto dK = [&](int l, int s) {
           const int a = l / D, p = l % D, b = s / D, q = s % D;

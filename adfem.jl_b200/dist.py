@@ -15,12 +15,29 @@ The reference has no parallelism at all; this is the new 
 Setup (numpy + one collective of index lists) is mesh-static.  The per-step exchange works on any
 `torch.distributed` backend: NCCL on the GPUs, gloo in the CPU unit tests (which inject oracle values).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import meshgen
+from . import _lib, meshgen
 from .mesh import Mesh, Mesh3, bcedge, get_edge_dof
+
+
+def make_nccl_comm(rank, world, group=None):
+    """An `ncclComm_t` owned by libadfem_cuda (adfem_dist_comm_create): rank 0 draws the ncclUniqueId, torch.distributed carries its
+    128 bytes to the other ranks (any backend), every rank then joins with ncclCommInitRank on its current CUDA device."""
+    L = _lib.lib()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        _lib.check(L.adfem_dist_nccl_unique_id(buf))
+    box = [bytes(buf)]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    comm = C.c_void_p()
+    _lib.check(L.adfem_dist_comm_create(C.byref(comm), box[0], C.c_int(rank), C.c_int(world)))
+    return comm
 
 
 def _boundary_faces(elems):
@@ -36,7 +53,7 @@ class Partition:
     coords/elems: the rank's own elements in LOCAL vertex numbering; gvid[i] = global id of local vertex i
     (ascending); nv_global = number of global vertices.  `mesh_kwargs` go to Mesh/Mesh3 (degree, order, host_only)."""
 
-    def __init__(self, coords, elems, gvid, nv_global, rank, world, group=None, device=None, **mesh_kwargs):
+    def __init__(self, coords, elems, gvid, nv_global, rank, world, group=None, device=None, interface_vertices=None, **mesh_kwargs):
         self.rank, self.world, self.group = rank, world, group
         dim = coords.shape[1]
         self.mesh = (Mesh if dim == 2 else Mesh3)(coords, elems, **mesh_kwargs)
@@ -52,8 +69,11 @@ class Partition:
         self.gid = gid
         self._gid_order = np.argsort(gid, kind="stable")
         self._gid_sorted = gid[self._gid_order]
-        # dofs that can be shared: those on facets of the block boundary
-        if dim == 2:
+        # dofs that can be shared: those on facets of the block boundary (`interface_vertices`: the caller knows the candidate
+        # vertices, e.g. the two end planes of a structured slab — skips the facet sort, which dominates the setup of large P1 meshes)
+        if interface_vertices is not None and m.ndof == m.nnode:
+            cand = np.unique(np.asarray(interface_vertices, dtype=np.int64))
+        elif dim == 2:
             bd = bcedge(m)
             cand = np.unique(bd.reshape(-1))
             if m.ndof > m.nnode:
@@ -95,6 +115,8 @@ class Partition:
             send_pos.append(pos)
             send_keys.append(keys.reshape(-1))
         self.send_counts = [len(p) for p in send_pos]
+        self._send_pos_np = np.ascontiguousarray(np.concatenate(send_pos), dtype=np.int64)
+        self._dist = None                                      # adfem_dist handle once use_library() was called (GPU runs)
         self.send_pos = torch.from_numpy(np.concatenate(send_pos)).to(self.device)
         recv_keys = self._all_to_all([k for k in send_keys])
         self.recv_counts = [len(k) // 2 for k in recv_keys]
@@ -118,6 +140,7 @@ class Partition:
             ph[hit] = ent[at[hit]]
             pos[have] = ph
         matched = pos >= 0
+        self._recv_pos_np = np.ascontiguousarray(pos, dtype=np.int64)
         self.recv_match_idx = torch.from_numpy(np.flatnonzero(matched)).to(self.device)
         self.recv_match_pos = torch.from_numpy(pos[matched]).to(self.device)
         self.ghost_idx = torch.from_numpy(np.flatnonzero(~matched)).to(self.device)
@@ -136,6 +159,34 @@ class Partition:
             assert np.array_equal(their[q], gid[vrecv[q]]), "dof-vector exchange lists of two ranks disagree"
         self.vsend_idx = torch.from_numpy(np.concatenate(vsend)).to(self.device)
         self.vrecv_idx = [torch.from_numpy(a).to(self.device) for a in vrecv]
+
+    # ---- exchange inside the library (include/adfem_cuda.h group 3) ------------------------------------------
+    def use_library(self, comm=None, max_ncomp=None):
+        """Route reduce_interface / replicate_interface through libadfem_cuda's own pack / ncclSend+ncclRecv / unpack path
+        (csrc/dist.cu, deterministic owner sums).  `comm`: an ncclComm_t as c_void_p, default one made by make_nccl_comm()."""
+        if self.world == 1 or self.mesh.host_only:
+            return self
+        L = _lib.lib()
+        self._comm = comm if comm is not None else make_nccl_comm(self.rank, self.world, self.group)
+        sc = np.asarray(self.send_counts, dtype=np.int64)
+        rc = np.asarray(self.recv_counts, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(L.adfem_dist_create(C.byref(h), self.mesh.handle, self._comm, C.c_int(self.rank), C.c_int(self.world),
+                                       C.c_int(max_ncomp or self.mesh.dim), sc.ctypes.data_as(_lib.c_lp), self._send_pos_np.ctypes.data_as(_lib.c_lp),
+                                       rc.ctypes.data_as(_lib.c_lp), self._recv_pos_np.ctypes.data_as(_lib.c_lp)))
+        self._dist = h
+        self._ghost_bufs = {}
+        return self
+
+    def _ghost_buf(self, ncomp, dtype, device):
+        if ncomp not in self._ghost_bufs:
+            self._ghost_bufs[ncomp] = torch.zeros(len(self.ghost_idx) * ncomp * ncomp, dtype=dtype, device=device)
+        return self._ghost_bufs[ncomp]
+
+    def __del__(self):
+        if getattr(self, "_dist", None) is not None and _lib._lib is not None:
+            _lib._lib.adfem_dist_destroy(self._dist)
+            self._dist = None
 
     # ---- helpers ---------------------------------------------------------------------------------
     def local_of_gid(self, g, missing_ok=False):
@@ -213,6 +264,11 @@ class Partition:
         ghost_vals then holds ncomp^2 values per ghost entry, (a, b)-minor)."""
         if self.world == 1:
             return vals
+        if self._dist is not None:
+            self.ghost_vals = self._ghost_buf(ncomp, vals.dtype, vals.device)
+            _lib.check(_lib.lib().adfem_dist_reduce(self._dist, C.c_int(ncomp), C.c_void_p(vals.data_ptr()), C.c_void_p(self.ghost_vals.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return vals
         if ncomp == 1:
             L = dict(send_pos=self.send_pos, match_pos=self.recv_match_pos, match_idx=self.recv_match_idx, ghost_idx=self.ghost_idx,
                      send_counts=self.send_counts, recv_counts=self.recv_counts)
@@ -229,6 +285,11 @@ class Partition:
         """Adjoint: owners send d loss / d K of the interface entries back, so `dvals` becomes valid on every entry
         this rank's elements contribute to (rows it does not own included)."""
         if self.world == 1:
+            return dvals
+        if self._dist is not None:
+            _lib.check(_lib.lib().adfem_dist_replicate(self._dist, C.c_int(ncomp), C.c_void_p(dvals.data_ptr()),
+                                                       C.c_void_p(dghost.data_ptr()) if dghost is not None and dghost.numel() else None,
+                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
             return dvals
         if ncomp == 1:
             L = dict(send_pos=self.send_pos, match_pos=self.recv_match_pos, match_idx=self.recv_match_idx, ghost_idx=self.ghost_idx,
@@ -341,7 +402,8 @@ def structured_slab(m, n_total, h, rank, world, **kw):
     coords, elems = meshgen.tri_grid(m, nl, h)
     coords[:, 1] += j0 * h
     gvid = np.arange(coords.shape[0], dtype=np.int64) + j0 * (m + 1)
-    return Partition(coords, elems, gvid, (m + 1) * (n_total + 1), rank, world, **kw)
+    iface = np.concatenate([np.arange(m + 1), np.arange(m + 1) + nl * (m + 1)])          # first and last node row of the slab
+    return Partition(coords, elems, gvid, (m + 1) * (n_total + 1), rank, world, interface_vertices=iface, **kw)
 
 
 def structured_slab3(n, l_total, h, rank, world, **kw):
@@ -355,5 +417,7 @@ def structured_slab3(n, l_total, h, rank, world, **kw):
     coords, elems = meshgen.tet_grid(n, n, l, h)
     coords[:, 2] += rank * l * h
     gvid = np.arange(coords.shape[0], dtype=np.int64) + rank * l * (n + 1) * (n + 1)
-    return Partition(coords, elems, gvid, (n + 1) * (n + 1) * (l_total + 1), rank, world, **kw)
+    plane = (n + 1) * (n + 1)
+    iface = np.concatenate([np.arange(plane), np.arange(plane) + l * plane])          # bottom and top node planes of the slab
+    return Partition(coords, elems, gvid, (n + 1) * (n + 1) * (l_total + 1), rank, world, interface_vertices=iface, **kw)
 

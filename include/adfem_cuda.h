@@ -276,6 +276,32 @@ int adfem_quad_stiffness1_svt_grad(const double* grad_vv, int type, int m, int n
 int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, double* vals_host);
 int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_host, double* grad_coef_host);
 
+/* ============================ (3) multi-GPU interface exchange ================================
+ * SURVEY 8(e).  The reference has no parallel path (no file:line to mirror); this group is what a Julia / C++ / Python host binds to run
+ * the assembly path on element blocks, one process per GPU.  The host computes the mesh-static lists once (which CSR entries of rows it
+ * does not own go to which owner; for every entry it will receive, the position of the same (row, col) in its own pattern or -1 when it
+ * does not hold the column) and hands them over; every exchange is then pack kernel -> one ncclGroup of ncclSend/ncclRecv -> unpack
+ * kernel on the caller's stream.  No atomics: an entry receiving from several ranks sums them in ascending source-rank order.
+ * NCCL is bound at run time (dlopen libnccl.so.2). */
+typedef struct adfem_dist adfem_dist;
+int adfem_dist_nccl_unique_id(void* id128 /* out: 128-byte ncclUniqueId, call on one rank and broadcast it */);
+int adfem_dist_comm_create(void** nccl_comm /* out: ncclComm_t */, const void* id128, int rank, int world);    /* ncclCommInitRank, current device */
+int adfem_dist_comm_destroy(void* nccl_comm);
+/* send_pos: positions (in the scalar CSR of `m`) of the entries this rank sends, concatenated by destination rank (send_counts[world]);
+ * recv_pos: for the entries it receives, concatenated by source rank (recv_counts[world]), its own position of that entry or -1 (ghost
+ * column).  max_ncomp: largest block size the handle will be used with (1 scalar, dim elasticity).  nccl_comm may be an existing
+ * ncclComm_t of the host (NCCL.jl, torch) or one made by adfem_dist_comm_create; NULL is accepted for world == 1. */
+int adfem_dist_create(adfem_dist** out, adfem_mesh* m, void* nccl_comm, int rank, int world, int max_ncomp, const long long* send_counts,
+                      const long long* send_pos, const long long* recv_counts, const long long* recv_pos);
+void adfem_dist_destroy(adfem_dist* d);
+long long adfem_dist_info(const adfem_dist* d, int what /* 0 entries sent, 1 received, 2 ghost entries, 3 distinct destinations, 4 bytes per scalar exchange */);
+/* forward: vals (layout of adfem_assemble_csr, ncomp^2 * nnz) — partial interface rows are summed into their owners in place; ghost_vals
+ * [nghost * ncomp^2] (may be NULL) receives the blocks whose column the owner does not hold.  Rows a rank does not own keep their partial sums. */
+int adfem_dist_reduce(adfem_dist* d, int ncomp, double* vals, double* ghost_vals, void* stream);
+/* adjoint: owners send d loss / d K of the interface entries back (dghost: gradient of the ghost block or NULL = 0), so dvals becomes valid
+ * on every entry this rank's elements contribute to; adfem_assemble_csr_adjoint then runs rank-local. */
+int adfem_dist_replicate(adfem_dist* d, int ncomp, double* dvals, const double* dghost, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

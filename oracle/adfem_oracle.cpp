@@ -43,6 +43,7 @@
 #include <cstring>
 #include <map>
 #include <set>
+#include <thread>
 #include <vector>
 
 typedef long long int64;
@@ -424,10 +425,12 @@ void mfem_get_element_to_vertices3(long long* elems) {
 // 2-D ops
 // =====================================================================================
 // deps/MFEM/FemLaplace1/FemLaplaceScalar.h:3-26 (and :59-61)
-void FemLaplaceScalar_forward_Julia(int64* indices, double* vv, const double* kappa) {
-  size_t s = 0, nz = 0;
+// element range [e0, e1): the reference's loop body unchanged; slot / Gauss-point counters start where the full loop would be at e0
+static void laplace2_forward_range(int e0, int e1, int64* indices, double* vv, const double* kappa) {
   int d = mmesh.elem_ndof;
-  for (int i = 0; i < mmesh.nelem; i++) {
+  size_t s = 0, nz = 0;
+  for (int i = 0; i < e0; i++) { s += mmesh.elements[i]->ngauss; nz += (size_t)mmesh.elements[i]->ngauss * d * d; }
+  for (int i = e0; i < e1; i++) {
     Element2* elem = mmesh.elements[i];
     std::vector<double> D(d * 2);                       // Eigen::MatrixXd D(elem_ndof,2) per element (:9)
     for (int k = 0; k < elem->ngauss; k++) {
@@ -441,11 +444,13 @@ void FemLaplaceScalar_forward_Julia(int64* indices, double* vv, const double* ka
     }
   }
 }
+void FemLaplaceScalar_forward_Julia(int64* indices, double* vv, const double* kappa) { laplace2_forward_range(0, mmesh.nelem, indices, vv, kappa); }
 // FemLaplaceScalar.h:28-54
-void oracle_FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv) {
-  size_t nz = 0, s = 0;
+static void laplace2_backward_range(int e0, int e1, double* grad_kappa, const double* grad_vv) {
   int d = mmesh.elem_ndof;
-  for (int i = 0; i < mmesh.nelem; i++) {
+  size_t nz = 0, s = 0;
+  for (int i = 0; i < e0; i++) { s += mmesh.elements[i]->ngauss; nz += (size_t)mmesh.elements[i]->ngauss * d * d; }
+  for (int i = e0; i < e1; i++) {
     Element2* elem = mmesh.elements[i];
     std::vector<double> D(d * 2);
     for (int k = 0; k < elem->ngauss; k++) {
@@ -458,6 +463,18 @@ void oracle_FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv)
       grad_kappa[s++] = v;
     }
   }
+}
+void oracle_FemLaplaceScalar_backward(double* grad_kappa, const double* grad_vv) { laplace2_backward_range(0, mmesh.nelem, grad_kappa, grad_vv); }
+// bench.py's CPU arm only: the same two loops split over `nthreads` contiguous element blocks (the reference itself has no threading; every
+// slot is written by exactly one thread, so the outputs are bit-identical to the serial call).
+void oracle_FemLaplaceScalar_forward_backward_mt(int nthreads, int64* indices, double* vv, const double* kappa, double* grad_kappa, const double* grad_vv) {
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    const int e0 = (int)((long long)mmesh.nelem * t / nthreads), e1 = (int)((long long)mmesh.nelem * (t + 1) / nthreads);
+    th.emplace_back([=] { laplace2_forward_range(e0, e1, indices, vv, kappa); laplace2_backward_range(e0, e1, grad_kappa, grad_vv); });
+  }
+  for (auto& x : th) x.join();
 }
 // FemLaplaceScalar.h:65-92 — dense column-major ngauss x N Jacobian
 void pcl_FemLaplaceScalar_Jacobian(double* H) {

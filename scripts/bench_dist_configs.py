@@ -54,6 +54,11 @@ def build_case(case, scale, rank, world, host_only):
         part, _ = adist.partition_elements(coords, elems, rank, world, degree=2, **kw)
         return part, 0 if case == "4l" else 1, 1, "config 4: P2 %s, Morton element blocks of a jittered, randomly renumbered %d x %d grid" % (
             "Laplace" if case == "4l" else "mass", n, n * world)
+    if case == "5g":
+        # STRONG scaling: the global mesh Mesh3(160, 160, 160, h) (20.5 M tetrahedra) is fixed, every rank takes 160 / world cube layers
+        n = max(2, int(160 * scale)) // (2 * world) * (2 * world)
+        part = adist.structured_slab3(n, n, 1.0 / n, rank, world, **kw)
+        return part, 2, 36, "config 5, strong scaling: P1 tetrahedral elasticity, z-slabs of the fixed global Mesh3(%d, %d, %d, h)" % (n, n, n)
     if case == "5":
         n = max(2, int(215 * scale))
         l = max(2, int(26 * scale)) // 2 * 2
@@ -71,6 +76,8 @@ def main():
     ap.add_argument("--dry-run", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="exchanges on the kernels' stream (their time is then visible between forward and adjoint)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE")
+    ap.add_argument("--library", type=int, default=1, help="1: interface exchange inside libadfem_cuda (adfem_dist_*: pack kernel, ncclSend/Recv group, "
+                    "deterministic unpack); 0: the torch.distributed reference path (index_select / all_to_all_single / index_add_)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dry = args.dry_run
@@ -86,6 +93,8 @@ def main():
         t0 = time.perf_counter()
         part, op, cpg, note = build_case(case, args.scale, rank, world, dry)
         mesh = part.mesh
+        if args.library and not dry and world > 1:
+            part.use_library()
         for kv in args.opt:
             k, v = kv.split("=")
             mesh.set_option(k, int(v))
@@ -184,7 +193,8 @@ def main():
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         if rank == 0:
             ms = tmax[0].item() / K
-            print(json.dumps({"case": "config" + case, "note": note, "n_gpus": world, "scaling": "weak", "dry_run": dry,
+            print(json.dumps({"case": "config" + case, "note": note, "n_gpus": world, "scaling": "strong" if case == "5g" else "weak", "dry_run": dry,
+                              "exchange": "library (adfem_dist_*)" if (args.library and not dry and world > 1) else "torch.distributed",
                               "elements_total": int(tsum[4].item()), "elements_per_gpu_max": int(tmax[4].item()),
                               "ms_per_step": ms, "Melem_per_s": tsum[4].item() / (ms * 1e-3) / 1e6 if not dry else None,
                               "fwd_ms_max": tmax[1].item(), "exchange_ms_max": tmax[2].item(), "adj_ms_max": tmax[3].item(),
