@@ -93,6 +93,9 @@ struct adfem_mesh {
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
   int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh)
+  int opt_tet_chunks = 0;                   // z-chunks of the two-stream forward pipeline (0 or 1 = off: measured no gain)
+  cudaStream_t tet_side_stream = nullptr;
+  std::vector<cudaEvent_t> tet_events;
   bool tet_const_ready = false;
   DevBuf<double> tet_spacing;              // [1/hx | 1/hy | 1/hz | hx | hy | hz] per cube and axis (tet_node.cuh)
   int opt_tet_scalar = 0;                   // scalar P1 operators on Mesh3(n,n,l,h) through tet_scalar.cuh: measured slower than the tile kernels (0.358 vs 0.151 ms), kept opt-in
@@ -111,6 +114,8 @@ struct adfem_mesh {
   ~adfem_mesh() {
     for (auto& s : hs) if (s) cudaStreamDestroy(s);
     for (auto& e : hev) if (e) cudaEventDestroy(e);
+    for (auto e : tet_events) cudaEventDestroy(e);
+    if (tet_side_stream) cudaStreamDestroy(tet_side_stream);
   }
   DevBuf<double> s_in, s_out;
 };
@@ -565,11 +570,34 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
       m->tet_const_ready = true;
     }
     const int n = m->tet_n, l = m->tet_l, nxb = (n + TPX_CUBES - 1) / TPX_CUBES;
-    k_tet_presum_x<<<(unsigned)((size_t)n * l * nxb * 5), TPX_THREADS, 0, st>>>(n, l, m->hm.rule, m->hm.g, coef, m->presum_buf.p);
     const GridTet gt{n, l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
     const double* q = m->tet_spacing.p;
     const TetSpacing sp{q, q + n, q + 2 * n, q + 2 * n + l, q + 3 * n + l, q + 4 * n + l};
-    k_tet_node_fwd<<<blocks_for(m->hm.nv, TN_NODES), TN_THREADS, TN_SMEM_BYTES, st>>>(gt, sp, m->pat.nnz, m->d_rowptr.p, m->presum_buf.p, vals);
+    const long long plane = (long long)(n + 1) * (n + 1);
+    // z-chunks: the Gauss pre-sum of cube layers [z0, z1) runs on the caller's stream, the node kernel of node planes [z0, z1) (the last chunk also
+    // takes plane l) follows on a side stream as soon as its layers are summed, so the DRAM-bound pass of chunk c + 1 overlaps the
+    // instruction-bound pass of chunk c.  One chunk = plain back-to-back launches on the caller's stream.
+    int nchunk = m->opt_tet_chunks > 0 ? m->opt_tet_chunks : 1;      // measured (gpurun r2g, 10.5 M tetrahedra): 1 / 4 / 8 / 16 chunks = 5.55 / 5.68 / 5.65 / 5.61 ms: no gain, so off by default
+    nchunk = std::max(1, std::min(nchunk, l));
+    if (nchunk > 1 && !m->tet_side_stream) {
+      CU_TRY(cudaStreamCreateWithFlags(&m->tet_side_stream, cudaStreamNonBlocking));
+      m->tet_events.resize(34);
+      for (auto& e : m->tet_events) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    nchunk = std::min(nchunk, 32);
+    cudaStream_t s2 = nchunk > 1 ? m->tet_side_stream : st;
+    if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[32], st)); CU_TRY(cudaStreamWaitEvent(s2, m->tet_events[32], 0)); }   // the side stream starts after the caller's earlier work (vals may still be read)
+    for (int c = 0; c < nchunk; c++) {
+      const int z0 = (int)((long long)l * c / nchunk), z1 = (int)((long long)l * (c + 1) / nchunk), nz = z1 - z0;
+      const unsigned grid = (unsigned)((size_t)n * nz * nxb * 5);
+      if (m->hm.g == 4) k_tet_presum_xg<4><<<grid, TPX_THREADS, 0, st>>>(n, l, z0, nz, m->hm.rule, coef, m->presum_buf.p);
+      else k_tet_presum_x<<<grid, TPX_THREADS, 0, st>>>(n, l, z0, nz, m->hm.rule, m->hm.g, coef, m->presum_buf.p);
+      if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[c], st)); CU_TRY(cudaStreamWaitEvent(s2, m->tet_events[c], 0)); }
+      // node plane k needs cube layers k - 1 and k: planes [z0, z1) are complete once layers < z1 are summed (plane z1 waits for the next chunk)
+      const long long node0 = plane * z0, node1 = (c + 1 == nchunk) ? (long long)m->hm.nv : plane * z1;
+      k_tet_node_fwd<<<blocks_for(node1 - node0, TN_NODES), TN_THREADS, TN_SMEM_BYTES, s2>>>(gt, sp, m->pat.nnz, node0, node1, m->d_rowptr.p, m->presum_buf.p, vals);
+    }
+    if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[33], s2)); CU_TRY(cudaStreamWaitEvent(st, m->tet_events[33], 0)); }
     CU_TRY(cudaGetLastError());
     return 0;
   }
@@ -587,7 +615,8 @@ int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaSt
   const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
   const size_t smem = (size_t)TG_ADJ_WARPS * TG_ADJ_WARP_DOUBLES * sizeof(double);
   CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tet_grid_elast_adj<<<blocks_for(m->hm.ne, 32 * TG_ADJ_WARPS), TG_ADJ_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
+  const long long units = (long long)m->tet_n * m->tet_n * ((5 * m->tet_l + 31) / 32);      // (cube column, chunk of 32 tetrahedra)
+  k_tet_grid_elast_adj<<<blocks_for(units, TG_ADJ_WARPS), TG_ADJ_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
                                                                                         dvals, grad);
   CU_TRY(cudaGetLastError());
   return 0;
@@ -757,6 +786,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
   else if (k == "tet_node") m->opt_tet_node = value != 0;
+  else if (k == "tet_chunks") m->opt_tet_chunks = (int)value;
   else if (k == "structured_tet_scalar") m->opt_tet_scalar = value != 0;
   else if (k == "row_gather") m->opt_row_gather = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;

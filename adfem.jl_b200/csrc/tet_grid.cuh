@@ -111,7 +111,9 @@ ADFEM_HD void tg_store_rows(int lane, long long rs, int len, long long nnz, cons
 }
 
 // ---- adjoint ----------------------------------------------------------------------------------------------------------------------
-constexpr int TG_ADJ_WARP_DOUBLES = 32 * 36;
+constexpr int TG_ADJ_LD = 37;                     // odd leading dimension: the 32 lanes' stores of entry c hit 16 distinct 64-bit banks
+constexpr int TG_ADJ_WARP_DOUBLES = 32 * TG_ADJ_LD + 1;
+struct alignas(16) TgPair { double x, y; };
 constexpr int TG_ADJ_WARPS = 4;
 
 // phase 1: lane -> tetrahedron e0 + lane: st[lane*36 + r*6 + c] = (B dK B^T)_{rc} |det|
@@ -158,27 +160,45 @@ ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long lon
       for (int b = 0; b < 3; b++)
 #pragma unroll
         for (int q = 0; q < 4; q++) badd<3>(b, G.gL[q], ldg(row + b * len + pos[q]), tl);
-      double bl[6];
+      // b(a, grad lambda_p) has three non-zero Voigt rows (device_fem.cuh badd<3>): only those rows of the outer product are formed
+      constexpr int ROW[3][3] = {{0, 4, 5}, {1, 3, 5}, {2, 3, 4}}, AX[3][3] = {{0, 2, 1}, {1, 2, 0}, {2, 1, 0}};
 #pragma unroll
-      for (int c = 0; c < 6; c++) bl[c] = 0.0;
-      badd<3>(a, G.gL[p], 1.0, bl);
+      for (int i = 0; i < 3; i++) {
+        const double bl = G.gL[p][AX[a][i]];
 #pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) gH[6 * r + c] += bl[r] * tl[c];
+        for (int c = 0; c < 6; c++) gH[6 * ROW[a][i] + c] += bl * tl[c];
+      }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 36; c++) st[lane * 36 + c] = gH[c] * ws;
+  for (int c = 0; c < 36; c++) st[lane * TG_ADJ_LD + c] = gH[c] * ws;
 }
 
 // phase 2: grad[(e*g + k)*36 + c] = st[t*36 + c] * w_k over the contiguous run of the warp's tetrahedra
 ADFEM_HD void tg_store_grad(int lane, const QuadRule& rule, int g, long long e0, long long ne, const double* st, double* grad) {
   const int nt = (int)(ne - e0 < 32 ? ne - e0 : 32), per = 36 * g;
   double* out = grad + (size_t)e0 * per;
+  if (g == 4 && nt == 32 && (reinterpret_cast<size_t>(out) & 15) == 0) {
+    // full warp, 4 Gauss points: 16-byte stores; pair q = lane + 32*it covers tetrahedron q / 72, Gauss point (q % 72) / 18, entries 2*(q % 18), +1.
+    // 32 * 9 pairs = 4 tetrahedra, so the decomposition of an iteration repeats every 9 iterations with the tetrahedron advanced by 4.
+    int off[9]; double w[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const int q = lane + 32 * j, t = q / 72, r = q - 72 * t, k = r / 18, c2 = r - 18 * k;
+      off[j] = t * TG_ADJ_LD + 2 * c2; w[j] = rule.w[k];
+    }
+    TgPair* o2 = reinterpret_cast<TgPair*>(out) + lane;
+#pragma unroll 1
+    for (int tt = 0; tt < 8; tt++) {
+      const double* s4 = st + tt * 4 * TG_ADJ_LD;
+#pragma unroll
+      for (int j = 0; j < 9; j++) o2[(tt * 9 + j) * 32] = TgPair{s4[off[j]] * w[j], s4[off[j] + 1] * w[j]};
+    }
+    return;
+  }
   for (int idx = lane; idx < nt * per; idx += 32) {
     const int t = idx / per, r = idx - t * per, k = r / 36, c = r - 36 * k;
-    out[idx] = st[t * 36 + c] * rule.w[k];
+    out[idx] = st[t * TG_ADJ_LD + c] * rule.w[k];
   }
 }
 
@@ -200,17 +220,24 @@ static __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(Gri
   tg_store_rows(lane, rowptr[node], tg_popc(mask), nnz, stage, vals);
 }
 
+// Work unit = (cube column (ci, cj), chunk c of 32 consecutive tetrahedra of that column): the warp's gradients stay one contiguous run, and units
+// are rasterised chunk-slowest / ci-fastest, u = (c*n + cj)*n + ci, so that the warps in flight at any time cover a slab of ~6 cube layers over
+// a few rows of columns — a working set of upstream values that fits L2 at any mesh size.  (In element order a wave of warps covers a whole
+// (cj, ck) plane at fixed ci, 250 MB of CSR rows for Mesh3(215,215,208): the adjoint fell from 0.39 ns per tetrahedron at 1.3 M to 0.60 ns at 48 M.)
 static __global__ void __launch_bounds__(TG_ADJ_WARPS * 32, 3) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
                                                                       const long long* __restrict__ rowptr, const double* __restrict__ dvals,
                                                                       double* __restrict__ grad) {
   extern __shared__ __align__(16) double tg_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long e0 = 32 * ((long long)blockIdx.x * TG_ADJ_WARPS + wib);
-  if (e0 >= ne) return;
+  const long long u = (long long)blockIdx.x * TG_ADJ_WARPS + wib, ncol = (long long)gt.n * gt.n;
+  const int per_col = 5 * gt.l, nchunk = (per_col + 31) / 32;
+  if (u >= ncol * nchunk) return;
+  const int c = (int)(u / ncol), cj = (int)((u / gt.n) % gt.n), ci = (int)(u % gt.n);
+  const long long col0 = ((long long)ci * gt.n + cj) * per_col, e0 = col0 + 32 * c, e1 = min(col0 + per_col, ne);
   double* st = tg_smem + (size_t)wib * TG_ADJ_WARP_DOUBLES;
-  tg_tet_adjoint(lane, gt, e0, ne, nnz, rowptr, dvals, st);
+  tg_tet_adjoint(lane, gt, e0, e1, nnz, rowptr, dvals, st);
   __syncwarp();
-  tg_store_grad(lane, rule, g, e0, ne, st, grad);
+  tg_store_grad(lane, rule, g, e0, e1, st, grad);
 }
 #endif
 

@@ -93,11 +93,11 @@ static __constant__ TetNodeConst c_tn;
 constexpr int TPX_CUBES = 64, TPX_THREADS = 256;
 // grid: ((cj*l + ck) * nxb + xb) * 5 + t — one CTA per (grid line, block of 64 cubes, tetrahedron of the cube): load + sum, one barrier, transposed
 // store.  No loop over t inside the CTA: the loads of one CTA overlap the stores of the others resident on the SM (8 CTAs of 18.7 KB).
-static __global__ void __launch_bounds__(TPX_THREADS) k_tet_presum_x(int n, int l, QuadRule rule, int g, const double* __restrict__ coef,
+static __global__ void __launch_bounds__(TPX_THREADS) k_tet_presum_x(int n, int l, int z0, int nz, QuadRule rule, int g, const double* __restrict__ coef,
                                                                      double* __restrict__ hx) {
   __shared__ double tile[36 * (TPX_CUBES + 1)];
   const int nxb = (n + TPX_CUBES - 1) / TPX_CUBES;
-  const int t = blockIdx.x % 5, rest = blockIdx.x / 5, xb = rest % nxb, line = rest / nxb, ck = line % l, cj = line / l;
+  const int t = blockIdx.x % 5, rest = blockIdx.x / 5, xb = rest % nxb, lz = rest / nxb, ck = z0 + lz % nz, cj = lz / nz, line = cj * l + ck;
   const int ci0 = xb * TPX_CUBES, ncx = min(TPX_CUBES, n - ci0), half = tn_half(n), nblk = tn_nblk(n);
   const int tid = threadIdx.x;
   for (int idx = tid; idx < ncx * 36; idx += TPX_THREADS) {
@@ -113,6 +113,61 @@ static __global__ void __launch_bounds__(TPX_THREADS) k_tet_presum_x(int n, int 
     const int c = idx / TPX_CUBES, r = idx - TPX_CUBES * c, hh = r >> 5, xx = r & 31, cil = 2 * xx + hh;     // ci0 is even: px = hh*half + ci0/2 + xx
     const int px = hh * half + (ci0 >> 1) + xx;
     if (cil < ncx) hx[((((size_t)line * 5 + t) * nblk + (px >> 5)) * 36 + c) * 32 + (px & 31)] = tile[c * (TPX_CUBES + 1) + cil];
+  }
+}
+
+// The same pass for a compile-time number of Gauss points: 16-byte loads (two adjacent tangent entries, 18 lanes per tetrahedron), all loads of a
+// batch of three items in flight before the first is used (12 x 16 B per thread), no per-item 64-bit index arithmetic.  The generic kernel above
+// needed 125 warp instructions per tetrahedron (profiles/ncu_r02_cfg5_tet_node_v2.md: issue slots 35 % busy, DRAM at 54 %).
+template <int G>
+static __global__ void __launch_bounds__(TPX_THREADS) k_tet_presum_xg(int n, int l, int z0, int nz, QuadRule rule, const double* __restrict__ coef,
+                                                                      double* __restrict__ hx) {
+  __shared__ double tile[36 * (TPX_CUBES + 1)];
+  const int nxb = (n + TPX_CUBES - 1) / TPX_CUBES;
+  const int t = blockIdx.x % 5, rest = blockIdx.x / 5, xb = rest % nxb, lz = rest / nxb, ck = z0 + lz % nz, cj = lz / nz;
+  const int line = cj * l + ck;
+  const int ci0 = xb * TPX_CUBES, ncx = min(TPX_CUBES, n - ci0), half = tn_half(n), nblk = tn_nblk(n);
+  const int tid = threadIdx.x;
+  double w[G];
+#pragma unroll
+  for (int k = 0; k < G; k++) w[k] = rule.w[k];
+  const size_t cube_stride = (size_t)5 * n * l * G * 36;                      // doubles between the tetrahedra t of cubes ci and ci + 1
+  const double2* base = reinterpret_cast<const double2*>(coef + ((size_t)5 * (((size_t)ci0 * n + cj) * l + ck) + t) * G * 36);
+  const int nitem = ncx * 18;
+  constexpr int NIT = (TPX_CUBES * 18 + TPX_THREADS - 1) / TPX_THREADS, NB = 3;
+#pragma unroll
+  for (int it0 = 0; it0 < NIT; it0 += NB) {
+    double2 v[NB][G];
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+      const int idx = tid + (it0 + u) * TPX_THREADS;
+      if (it0 + u < NIT && idx < nitem) {
+        const int cil = idx / 18, c2 = idx - 18 * cil;
+        const double2* p = base + (cil * cube_stride) / 2 + c2;
+#pragma unroll
+        for (int k = 0; k < G; k++) v[u][k] = __ldg(p + 18 * k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+      const int idx = tid + (it0 + u) * TPX_THREADS;
+      if (it0 + u < NIT && idx < nitem) {
+        const int cil = idx / 18, c2 = idx - 18 * cil;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < G; k++) { s0 += v[u][k].x * w[k]; s1 += v[u][k].y * w[k]; }
+        tile[(2 * c2) * (TPX_CUBES + 1) + cil] = s0;
+        tile[(2 * c2 + 1) * (TPX_CUBES + 1) + cil] = s1;
+      }
+    }
+  }
+  __syncthreads();
+  double* out = hx + ((size_t)line * 5 + t) * nblk * (36 * 32);
+#pragma unroll 3
+  for (int idx = tid; idx < 36 * TPX_CUBES; idx += TPX_THREADS) {
+    const int c = idx / TPX_CUBES, r = idx - TPX_CUBES * c, hh = r >> 5, xx = r & 31, cil = 2 * xx + hh;     // ci0 is even: px = hh*half + ci0/2 + xx
+    const int px = hh * half + (ci0 >> 1) + xx;
+    if (cil < ncx) out[((size_t)(px >> 5) * 36 + c) * 32 + (px & 31)] = tile[c * (TPX_CUBES + 1) + cil];
   }
 }
 
@@ -197,14 +252,15 @@ __device__ __forceinline__ void tn_accumulate(const GridTet& gt, const TetSpacin
   }
 }
 
-static __global__ void __launch_bounds__(TN_THREADS, 3) k_tet_node_fwd(GridTet gt, TetSpacing sp, long long nnz, const long long* __restrict__ rowptr,
-                                                                       const double* __restrict__ hx, double* __restrict__ vals) {
+// nodes [node0, node1) (flat ids; whole node planes when the forward runs in z-chunks on two streams)
+static __global__ void __launch_bounds__(TN_THREADS, 3) k_tet_node_fwd(GridTet gt, TetSpacing sp, long long nnz, long long node0, long long node1,
+                                                                       const long long* __restrict__ rowptr, const double* __restrict__ hx, double* __restrict__ vals) {
   extern __shared__ __align__(16) double tn_acc[];
   __shared__ long long s_rs[TN_NODES];
   __shared__ int s_mask[TN_NODES], s_src[TN_NODES];
   __shared__ unsigned char s_slot27[2][19];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, heavy = c_tn.heavy, par = warp < 3 ? heavy : 1 - heavy, b = warp < 3 ? warp : warp - 3;
-  const long long n1 = gt.n + 1, nn = n1 * n1 * (gt.l + 1), f0 = (long long)blockIdx.x * TN_NODES;
+  const long long n1 = gt.n + 1, nn = node1, f0 = node0 + (long long)blockIdx.x * TN_NODES;
   // the lane's node: the one of the flat pair (f0 + 2*lane, f0 + 2*lane + 1) whose index parity (i + j + k) & 1 is `par`
   long long f = f0 + 2 * lane;
   {

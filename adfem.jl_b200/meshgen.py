@@ -71,3 +71,16 @@ def jitter_unstructured(m, n, h, seed=2, jitter=0.3, permute=True):
         elems = inv[elems]
         elems = elems[rng.permutation(elems.shape[0])]
     return coords, elems
+
+
+def morton_element_order(coords, elems):
+    """Element permutation that sorts the centroids along a Morton curve: contiguous element blocks become spatially compact
+    (used before an element-block partition of a mesh whose element numbering has no locality)."""
+    c = coords[elems].mean(1)
+    lo, hi = c.min(0), c.max(0)
+    q = np.minimum(((c - lo) / np.maximum(hi - lo, 1e-300) * 65535).astype(np.uint64), 65535)
+    key = np.zeros(len(c), dtype=np.uint64)
+    for b in range(16):
+        for d in range(c.shape[1]):
+            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(c.shape[1] * b + d)
+    return np.argsort(key, kind="stable")

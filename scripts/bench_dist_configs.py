@@ -29,16 +29,7 @@ from adfem_jl_b200 import _lib, meshgen
 from adfem_jl_b200 import dist as adist
 
 
-def morton_order(coords, elems):
-    """element permutation that sorts the centroids along a Morton curve: contiguous element blocks become spatially compact"""
-    c = coords[elems].mean(1)
-    lo, hi = c.min(0), c.max(0)
-    q = np.minimum(((c - lo) / np.maximum(hi - lo, 1e-300) * 65535).astype(np.uint64), 65535)
-    key = np.zeros(len(c), dtype=np.uint64)
-    for b in range(16):
-        for d in range(c.shape[1]):
-            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(c.shape[1] * b + d)
-    return np.argsort(key, kind="stable")
+morton_order = meshgen.morton_element_order
 
 
 def build_case(case, scale, rank, world, host_only):

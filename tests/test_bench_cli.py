@@ -17,7 +17,7 @@ def _run(args, env=None):
 
 
 def test_reference_arm_line():
-    out = _run(["--impl", "reference", "--cpu-size", "48", "--steps", "2", "--warmup", "1", "--gpus", "1"])
+    out = _run(["--impl", "reference", "--size", "48", "--steps", "2", "--warmup", "1", "--gpus", "1"])
     assert out.returncode == 0, out.stderr
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -26,13 +26,38 @@ def test_reference_arm_line():
     assert d["dtype"] == "f64" and d["steps"] == 2 and d["warmup"] == 1 and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "48" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "Mesh(48,48,1/48)" in cb["sample"]
+    assert d["config"]["same_mesh_as_gpu_arm"] is True
     assert d["e2e"] == {"value": d["value"], "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 def test_reference_arm_other_ranks_exit_quietly():
-    out = _run(["--impl", "reference", "--cpu-size", "16", "--steps", "1", "--warmup", "0", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    out = _run(["--impl", "reference", "--size", "16", "--steps", "1", "--warmup", "0", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_bounds_its_sample():
+    """a large step count shrinks the sample to a row slab of the same mesh (stated in the line) instead of running for hours"""
+    out = _run(["--impl", "reference", "--size", "256", "--steps", "3", "--warmup", "0", "--cpu-budget-s", "0.05"])
+    assert out.returncode == 0, out.stderr
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"]["same_mesh_as_gpu_arm"] is False and "row slab" in d["cpu_baseline"]["sample"]
+
+
+def test_bench_cases_host_logic():
+    """bench.py's case builder on host-only meshes: element counts of the BASELINE configs scale as stated and SURVEY 8(d)'s
+    algorithmic bytes per element come out at 72 / 348 / 264 / ~1363 B."""
+    sys.path.insert(0, ROOT)
+    import bench
+    want = {"2": (72, 1), "3": (348, 9), "4l": (264, 1), "5": (1363, 36)}
+    for case, (b, cpg) in want.items():
+        mesh, part, op, c, note, scaling = bench.build_case(case, 0, 1, scale=0.01 if case != "5" else 0.06, size=40, host_only=True)
+        assert part is None and c == cpg and ("config " + case[0]) in note
+        nc = mesh.dim if op == 2 else 1
+        rowptr, _ = mesh.csr_pattern(1)
+        got = bench.alg_bytes_per_elem(mesh, nc * nc * int(rowptr[-1]), cpg)
+        assert abs(got - b) / b < 0.12, (case, got)     # small meshes: boundary effects in nnz/E and nnode/E
+        assert scaling == ("strong" if case in ("4l", "5") else "weak")
 
 
 def test_product_arm_needs_a_gpu():

@@ -355,8 +355,8 @@ def test_structured_scatter_operators(oracle):
         close(a, b, rel=1e-13)       # same summation order and geometry; only the compiler's FMA contraction may differ between the two kernels
 
 
-@pytest.mark.parametrize("n,l", [(3, 2), (5, 4), (1, 1)])
-def test_structured_tet_elasticity_forward(oracle, n, l):
+@pytest.mark.parametrize("n,l,chunks,node", [(3, 2, 1, 1), (5, 4, 1, 1), (1, 1, 1, 1), (5, 6, 3, 1), (70, 5, 5, 1), (4, 4, 1, 0), (33, 34, 0, 1)])
+def test_structured_tet_elasticity_forward(oracle, n, l, chunks, node):
     """Option "structured_elasticity" on Mesh3(n, n, l, h): Gauss-sum pre-pass + one warp per node for the forward, one warp per 32 tetrahedra
     for the adjoint (csrc/tet_grid.cuh); against the oracle and the general tile kernels."""
     rng = np.random.default_rng(70 + n + l)
@@ -369,7 +369,9 @@ def test_structured_tet_elasticity_forward(oracle, n, l):
     rp, ci, ref = oracle.canonical_csr(ind, vv, N3)
     dv = rng.standard_normal(len(ref))
     expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N3))
-    for on in (1, 0):
+    m.set_option("tet_chunks", chunks)      # > 1: Gauss pre-sum and node kernel pipelined over z-chunks on two streams (0 = automatic)
+    m.set_option("tet_node", node)          # 0: first-generation one-warp-per-node forward
+    for on in ((1, 0) if n < 30 else (1,)):
         m.set_option("structured_elasticity", on)
         k = dev(H).requires_grad_(True)
         T = A.compute_fem_stiffness_matrix(k, m, mode="csr")
@@ -377,6 +379,9 @@ def test_structured_tet_elasticity_forward(oracle, n, l):
         close(npy(T.values), ref)
         (g,) = torch.autograd.grad(T.values, k, dev(dv))
         close(npy(g).reshape(-1), expect)
+        if on == 1 and chunks != 1:          # a second pass must find the side stream ordered behind the first one's readers
+            T2 = A.compute_fem_stiffness_matrix(k, m, mode="csr")
+            assert torch.equal(T2.values, T.values)
 
 
 @pytest.mark.parametrize("dim,degree", [(2, 2), (2, 1), (3, 1), (3, 2)])
