@@ -93,6 +93,7 @@ struct adfem_mesh {
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
   int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh)
+  int opt_tet_adj_blocks = 3;               // resident CTAs per SM the tetrahedral adjoint kernel is compiled for (register cap 168 / 128 / 96): measured 3.77 / 3.87 / 4.75 ms at 10.5 M tetrahedra
   int opt_tet_chunks = 0;                   // z-chunks of the two-stream forward pipeline (0 or 1 = off: measured no gain)
   cudaStream_t tet_side_stream = nullptr;
   std::vector<cudaEvent_t> tet_events;
@@ -595,6 +596,8 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
       if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[c], st)); CU_TRY(cudaStreamWaitEvent(s2, m->tet_events[c], 0)); }
       // node plane k needs cube layers k - 1 and k: planes [z0, z1) are complete once layers < z1 are summed (plane z1 waits for the next chunk)
       const long long node0 = plane * z0, node1 = (c + 1 == nchunk) ? (long long)m->hm.nv : plane * z1;
+      // (measured and dropped, gpurun r2i: one CTA per parity — 3 warps, no barrier between the 32- and the 8-tetrahedron warps — 5.55 -> 6.79 ms at
+      // 10.5 M tetrahedra, 6.03 ms as two launches: the two parities of a span share their tangent blocks through L1)
       k_tet_node_fwd<<<blocks_for(node1 - node0, TN_NODES), TN_THREADS, TN_SMEM_BYTES, s2>>>(gt, sp, m->pat.nnz, node0, node1, m->d_rowptr.p, m->presum_buf.p, vals);
     }
     if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[33], s2)); CU_TRY(cudaStreamWaitEvent(st, m->tet_events[33], 0)); }
@@ -614,10 +617,18 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
 int launch_tet_grid_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st) {
   const GridTet gt{m->tet_n, m->tet_l, m->tet_xs.p, m->tet_ys.p, m->tet_zs.p, m->d_tet_tab.p};
   const size_t smem = (size_t)TG_ADJ_WARPS * TG_ADJ_WARP_DOUBLES * sizeof(double);
-  CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long units = (long long)m->tet_n * m->tet_n * ((5 * m->tet_l + 31) / 32);      // (cube column, chunk of 32 tetrahedra)
-  k_tet_grid_elast_adj<<<blocks_for(units, TG_ADJ_WARPS), TG_ADJ_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, m->pat.nnz, m->d_rowptr.p,
-                                                                                        dvals, grad);
+  // resident CTAs per SM the kernel is compiled for: 3 = 168 registers, 4 = 128, 5 = 96 (a few spills)
+#define ADFEM_TET_ADJ(MINB)                                                                                                                  \
+  do {                                                                                                                                       \
+    CU_TRY(cudaFuncSetAttribute(k_tet_grid_elast_adj<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+    k_tet_grid_elast_adj<MINB><<<blocks_for(units, TG_ADJ_WARPS), TG_ADJ_WARPS * 32, smem, st>>>(gt, m->hm.rule, m->hm.g, (long long)m->hm.ne, \
+                                                                                             m->pat.nnz, m->d_rowptr.p, dvals, grad);       \
+  } while (0)
+  if (m->opt_tet_adj_blocks == 4) ADFEM_TET_ADJ(4);
+  else if (m->opt_tet_adj_blocks == 5) ADFEM_TET_ADJ(5);
+  else ADFEM_TET_ADJ(3);
+#undef ADFEM_TET_ADJ
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -787,6 +798,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
   else if (k == "tet_node") m->opt_tet_node = value != 0;
   else if (k == "tet_chunks") m->opt_tet_chunks = (int)value;
+  else if (k == "tet_adj_blocks") m->opt_tet_adj_blocks = (int)value;
   else if (k == "structured_tet_scalar") m->opt_tet_scalar = value != 0;
   else if (k == "row_gather") m->opt_row_gather = value != 0;
   else if (k == "grid_rows") m->opt_grid_rows = (int)value;

@@ -138,20 +138,33 @@ ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long lon
   }
   Geom<3> G; geom_tet(X, G);
   const double ws = G.wscale < 0 ? -G.wscale : G.wscale;
-  double gH[36];
-#pragma unroll
-  for (int c = 0; c < 36; c++) gH[c] = 0.0;
+  // CSR positions of the four vertex columns inside each vertex row, one byte each (rows have at most 19 entries)
+  unsigned pos4[4]; int len[4];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int len = tg_popc(mask[p]);
-    int pos[4];
+    len[p] = tg_popc(mask[p]);
+    unsigned pk = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int s = (vk[q] - vk[p] + 1) * 9 + (vj[q] - vj[p] + 1) * 3 + (vi[q] - vi[p] + 1);
-      pos[q] = tg_popc(mask[p] & ((1 << s) - 1));
+      pk |= (unsigned)tg_popc(mask[p] & ((1 << s) - 1)) << (8 * q);
     }
+    pos4[p] = pk;
+  }
+  // grad H = sum over (row component a, vertex p) of b(a, grad lambda_p) (x) t(a, p),  t = sum over (b, q) of dK[(p,a),(q,b)] b(b, grad lambda_q).
+  // b(a, .) has three non-zero Voigt rows (device_fem.cuh badd<3>), so component a only touches rows ROW[a]: 18 accumulators live at a
+  // time instead of 36 (the kernel ran 12 warps per SM at 168 registers).  Rows 3, 4, 5 receive two components: the second one adds in place.
+  constexpr int ROW[3][3] = {{0, 4, 5}, {1, 3, 5}, {2, 3, 4}}, AX[3][3] = {{0, 2, 1}, {1, 2, 0}, {2, 1, 0}};
+  double* out = st + lane * TG_ADJ_LD;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
+  for (int a = 0; a < 3; a++) {
+    double acc[3][6];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) acc[i][c] = 0.0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
       const double* row = dvals + 3 * ((long long)a * nnz + rs[p]);
       double tl[6];
 #pragma unroll
@@ -159,19 +172,25 @@ ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long lon
 #pragma unroll
       for (int b = 0; b < 3; b++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) badd<3>(b, G.gL[q], ldg(row + b * len + pos[q]), tl);
-      // b(a, grad lambda_p) has three non-zero Voigt rows (device_fem.cuh badd<3>): only those rows of the outer product are formed
-      constexpr int ROW[3][3] = {{0, 4, 5}, {1, 3, 5}, {2, 3, 4}}, AX[3][3] = {{0, 2, 1}, {1, 2, 0}, {2, 1, 0}};
+        for (int q = 0; q < 4; q++) badd<3>(b, G.gL[q], ldg(row + b * len[p] + (int)((pos4[p] >> (8 * q)) & 0xffu)), tl);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         const double bl = G.gL[p][AX[a][i]];
 #pragma unroll
-        for (int c = 0; c < 6; c++) gH[6 * ROW[a][i] + c] += bl * tl[c];
+        for (int c = 0; c < 6; c++) acc[i][c] += bl * tl[c];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int r = ROW[a][i];
+      const bool first = (r < 3) || (a == 0) || (a == 1 && r == 3);      // rows 3, 4, 5 are first written by components 1, 0, 0
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        if (first) out[6 * r + c] = acc[i][c] * ws;
+        else out[6 * r + c] += acc[i][c] * ws;
       }
     }
   }
-#pragma unroll
-  for (int c = 0; c < 36; c++) st[lane * TG_ADJ_LD + c] = gH[c] * ws;
 }
 
 // phase 2: grad[(e*g + k)*36 + c] = st[t*36 + c] * w_k over the contiguous run of the warp's tetrahedra
@@ -224,7 +243,8 @@ static __global__ void __launch_bounds__(TG_WARPS * 32) k_tet_grid_elast_fwd(Gri
 // are rasterised chunk-slowest / ci-fastest, u = (c*n + cj)*n + ci, so that the warps in flight at any time cover a slab of ~6 cube layers over
 // a few rows of columns — a working set of upstream values that fits L2 at any mesh size.  (In element order a wave of warps covers a whole
 // (cj, ck) plane at fixed ci, 250 MB of CSR rows for Mesh3(215,215,208): the adjoint fell from 0.39 ns per tetrahedron at 1.3 M to 0.60 ns at 48 M.)
-static __global__ void __launch_bounds__(TG_ADJ_WARPS * 32, 3) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
+template <int MINB>
+static __global__ void __launch_bounds__(TG_ADJ_WARPS * 32, MINB) k_tet_grid_elast_adj(GridTet gt, QuadRule rule, int g, long long ne, long long nnz,
                                                                       const long long* __restrict__ rowptr, const double* __restrict__ dvals,
                                                                       double* __restrict__ grad) {
   extern __shared__ __align__(16) double tg_smem[];

@@ -668,6 +668,52 @@ def impose_Dirichlet_boundary_conditions(A, rhs=None, bdnode=None, bdval=None):
     return B if helper else (B, orhs)
 
 
+class _DirichletBd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vv, ii, jj, bd, m, n):
+        vv = vv.contiguous()
+        N, L = vv.numel(), lib()
+        n1, n2 = C.c_longlong(0), C.c_longlong(0)
+        check(L.adfem_dirichlet_bd_count(_ptr(ii), _ptr(jj), C.c_longlong(N), _ptr(bd), C.c_int(bd.numel()), C.c_int(m), C.c_int(n), C.byref(n1), C.byref(n2),
+                                         _stream()))
+        i64 = lambda k: torch.empty(k, dtype=torch.int64, device=vv.device)
+        f64 = lambda k: torch.empty(k, dtype=torch.float64, device=vv.device)
+        ii1, jj1, vv1, ii2, jj2, vv2 = i64(n1.value), i64(n1.value), f64(n1.value), i64(n2.value), i64(n2.value), f64(n2.value)
+        check(L.adfem_dirichlet_bd(_ptr(ii), _ptr(jj), _ptr(vv), C.c_longlong(N), _ptr(bd), C.c_int(bd.numel()), C.c_int(m), C.c_int(n), _ptr(ii1), _ptr(jj1),
+                                   _ptr(vv1), _ptr(ii2), _ptr(jj2), _ptr(vv2), _stream()))
+        ctx.save_for_backward(ii, jj, bd)
+        ctx.mn = (m, n, n1.value, n2.value)
+        ctx.mark_non_differentiable(ii1, jj1, ii2, jj2)
+        return vv1, vv2, ii1, jj1, ii2, jj2
+
+    @staticmethod
+    def backward(ctx, g1, g2, *_):
+        ii, jj, bd = ctx.saved_tensors
+        m, n, n1, n2 = ctx.mn
+        g1 = torch.zeros(n1, dtype=torch.float64, device=ii.device) if g1 is None else g1.contiguous()
+        g2 = torch.zeros(n2, dtype=torch.float64, device=ii.device) if g2 is None else g2.contiguous()
+        g = torch.empty(ii.numel(), dtype=torch.float64, device=ii.device)
+        check(lib().adfem_dirichlet_bd_grad(_ptr(ii), _ptr(jj), C.c_longlong(ii.numel()), _ptr(bd), C.c_int(bd.numel()), C.c_int(m), C.c_int(n), _ptr(g1),
+                                            _ptr(g2), _ptr(g), _stream()))
+        return g, None, None, None, None, None
+
+
+def fem_impose_Dirichlet_boundary_condition_experimental(A, bdnode, m, n, h=None, coupled=False):
+    """`fem_impose_Dirichlet_boundary_condition_experimental(A, bdnode, m, n, h)` — src/InvCore.jl:14-23 (op DirichletBd,
+    deps/DirichletBd/DirichletBd.h:8-60); `coupled=True` is `fem_impose_coupled_Dirichlet_boundary_condition` (:6-12, m*n extra dofs).
+    `A`: SparseTensor with the 2(m+1)(n+1) component-blocked dofs; `bdnode`: boundary NODES in the index base of A's indices (the op
+    compares integers only).  Returns (A1, A2): A1 = A with the rows and columns of the boundary dofs (bdnode and bdnode + (m+1)(n+1))
+    replaced by the identity, A2 = the free-row / boundary-column block with columns numbered 1..2|bdnode| in list order."""
+    assert isinstance(A, SparseTensor)
+    dev_ = A.values.device
+    ind = A.indices
+    ii, jj = ind[:, 0].contiguous(), ind[:, 1].contiguous()
+    bd = torch.as_tensor(np.asarray(bdnode), dtype=torch.int32, device=dev_).contiguous()
+    vv1, vv2, ii1, jj1, ii2, jj2 = _DirichletBd.apply(A.values, ii, jj, bd, int(m), int(n))
+    nd = 2 * (m + 1) * (n + 1) + (m * n if coupled else 0)
+    return SparseTensor(torch.stack([ii1, jj1], 1), vv1, nd, nd), SparseTensor(torch.stack([ii2, jj2], 1), vv2, nd, 2 * bd.numel())
+
+
 # ------------------------------------------------------------------------------------------ PCL Jacobians (src/pcl.jl)
 def pcl_compute_fem_laplace_matrix1(mesh):
     """`pcl_compute_fem_laplace_matrix1(mmesh)` — src/pcl.jl:35-39 (kernel pcl_FemLaplaceScalar_Jacobian,

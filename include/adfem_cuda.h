@@ -236,6 +236,20 @@ int adfem_impose_dirichlet_grad(const double* grad_ov, const double* grad_orhs, 
                                 long long sN, const long long* bd, const double* bdval, long long bdN, long long N,
                                 double* grad_vv, double* grad_rhs, double* grad_bdval, void* stream);
 
+/* DirichletBd — the op "dirichlet_bd" (deps/DirichletBd/DirichletBd.h:8-60, DirichletBd.cpp:19-33) behind
+ * fem_impose_Dirichlet_boundary_condition_experimental / fem_impose_coupled_Dirichlet_boundary_condition (src/InvCore.jl:6-23): COO
+ * triplets (ii, jj, vv)[N] of a two-component operator on the m x n grid, boundary NODES bd[bdn] (int32 like the op input, same index
+ * base as ii / jj); the boundary dof set is bd and bd + (m+1)(n+1).  Output 1: the triplets with both indices free, in input order,
+ * then one (b, b, 1.0) per boundary dof in ascending order; output 2: the triplets with a free row and a boundary column, the column
+ * replaced by the 1-based position of that dof in [bd, bd + (m+1)(n+1)] (last duplicate wins).  All pointers are DEVICE pointers;
+ * lengths are data dependent: call _count first.  _grad (backward(), DirichletBd.h:96-112) overwrites grad_vv[N]. */
+int adfem_dirichlet_bd_count(const long long* ii, const long long* jj, long long N, const int* bd, int bdn, int m, int n, long long* n1, long long* n2,
+                             void* stream);
+int adfem_dirichlet_bd(const long long* ii, const long long* jj, const double* vv, long long N, const int* bd, int bdn, int m, int n, long long* ii1,
+                       long long* jj1, double* vv1, long long* ii2, long long* jj2, double* vv2, void* stream);
+int adfem_dirichlet_bd_grad(const long long* ii, const long long* jj, long long N, const int* bd, int bdn, int m, int n, const double* grad_vv1,
+                            const double* grad_vv2, double* grad_vv, void* stream);
+
 /* Device versions of the two PCL Jacobians: H / J are DEVICE pointers, caller-zeroed; indices 0-based interleaved like adfem_impose_dirichlet. */
 int adfem_pcl_laplace_jacobian(adfem_mesh* m, double* H /* G x G*d*d column-major */, void* stream);
 int adfem_pcl_impose_dirichlet(const long long* indices, long long sN, const long long* bd, long long bdN, long long N, double* J /* sN x S column-major */,

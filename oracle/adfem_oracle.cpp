@@ -847,6 +847,40 @@ void oracle_ImposeDirichlet_copy(int64* oindices, double* ov, double* orhs) {   
   for (size_t i = 0; i < g_dir.rhs.size(); i++) orhs[i] = g_dir.rhs[i];
   for (size_t i = 0; i < g_dir.ii.size(); i++) { oindices[2 * i] = g_dir.ii[i]; oindices[2 * i + 1] = g_dir.jj[i]; ov[i] = g_dir.vv[i]; }
 }
+// DirichletBd (deps/DirichletBd/DirichletBd.h:8-60): two calls like the op shell (count, then copy).  bdset = bd and bd + (m+1)(n+1);
+// a boundary dof's column in the second matrix is its 1-based position in that concatenated list (std::map assignment: last wins).
+struct DirichletBdState { std::vector<int64> ii1, jj1, ii2, jj2; std::vector<double> vv1, vv2; } g_dbd;
+void oracle_DirichletBd_forward(const int64* ii, const int64* jj, const double* vv, int N, const int* bd, int bdn, int m, int n, long long* n1, long long* n2) {
+  g_dbd = DirichletBdState();
+  const int off = (m + 1) * (n + 1);
+  std::set<int> bdset;
+  std::map<int, int> position;
+  for (int half = 0, k = 1; half < 2; half++)
+    for (int i = 0; i < bdn; i++) { const int dof = bd[i] + half * off; bdset.insert(dof); position[dof] = k++; }      // :17-29
+  for (int s = 0; s < N; s++) {                                                                                         // :31-41
+    const bool rb = bdset.count((int)ii[s]) > 0, cb = bdset.count((int)jj[s]) > 0;
+    if (!rb && !cb) { g_dbd.ii1.push_back(ii[s]); g_dbd.jj1.push_back(jj[s]); g_dbd.vv1.push_back(vv[s]); }
+    if (!rb && cb) { g_dbd.ii2.push_back(ii[s]); g_dbd.jj2.push_back(position[(int)jj[s]]); g_dbd.vv2.push_back(vv[s]); }
+  }
+  for (int dof : bdset) { g_dbd.ii1.push_back(dof); g_dbd.jj1.push_back(dof); g_dbd.vv1.push_back(1.0); }               // :42-44
+  *n1 = (long long)g_dbd.vv1.size(); *n2 = (long long)g_dbd.vv2.size();
+}
+void oracle_DirichletBd_copy(int64* ii1, int64* jj1, double* vv1, int64* ii2, int64* jj2, double* vv2) {                // fill(), :47-92
+  for (size_t i = 0; i < g_dbd.vv1.size(); i++) { ii1[i] = g_dbd.ii1[i]; jj1[i] = g_dbd.jj1[i]; vv1[i] = g_dbd.vv1[i]; }
+  for (size_t i = 0; i < g_dbd.vv2.size(); i++) { ii2[i] = g_dbd.ii2[i]; jj2[i] = g_dbd.jj2[i]; vv2[i] = g_dbd.vv2[i]; }
+}
+void oracle_DirichletBd_backward(double* grad_vv, const int64* ii, const int64* jj, const double* grad_vv1, const double* grad_vv2, int N, const int* bd,
+                                 int bdn, int m, int n) {                                                                  // :96-112
+  std::set<int> bdset(bd, bd + bdn);
+  for (int i = 0; i < bdn; i++) bdset.insert(bd[i] + (m + 1) * (n + 1));
+  size_t k1 = 0, k2 = 0;
+  for (int s = 0; s < N; s++) {
+    grad_vv[s] = 0.0;
+    const bool rb = bdset.count((int)ii[s]) > 0, cb = bdset.count((int)jj[s]) > 0;
+    if (!rb && !cb) grad_vv[s] += grad_vv1[k1++];
+    if (!rb && cb) grad_vv[s] += grad_vv2[k2++];
+  }
+}
 // ImposeDirichlet.h:63-93; outputs are zero-filled first like the Grad op shell (.cpp:229-232)
 void oracle_ImposeDirichlet_backward(double* grad_vv_ipt, double* grad_rhs_ipt, double* grad_bdval, const double* grad_vv,
                                      const double* grad_rhs, const int64* indices, const double* v_ipt, const int64* bd,

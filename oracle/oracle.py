@@ -324,6 +324,28 @@ class Mesh3D(_MeshBase):
 
 
 # --- mesh-free ops -----------------------------------------------------------------------
+def dirichlet_bd_fwd(ii, jj, vv, bd, m, n):
+    """deps/DirichletBd/DirichletBd.h:8-60 -> (ii1, jj1, vv1, ii2, jj2, vv2); bd int32 in the index base of ii / jj."""
+    ii, jj = np.ascontiguousarray(ii, dtype=np.int64), np.ascontiguousarray(jj, dtype=np.int64)
+    vv, bd = _f64(vv), np.ascontiguousarray(bd, dtype=np.int32)
+    n1, n2 = C.c_longlong(0), C.c_longlong(0)
+    lib().oracle_DirichletBd_forward(_l(ii), _l(jj), _d(vv), C.c_int(len(vv)), bd.ctypes.data_as(c_ip), C.c_int(len(bd)), C.c_int(m), C.c_int(n),
+                                     C.byref(n1), C.byref(n2))
+    out = [np.zeros(n1.value, dtype=np.int64), np.zeros(n1.value, dtype=np.int64), np.zeros(n1.value),
+           np.zeros(n2.value, dtype=np.int64), np.zeros(n2.value, dtype=np.int64), np.zeros(n2.value)]
+    lib().oracle_DirichletBd_copy(_l(out[0]), _l(out[1]), _d(out[2]), _l(out[3]), _l(out[4]), _d(out[5]))
+    return out
+
+
+def dirichlet_bd_bwd(ii, jj, g1, g2, bd, m, n):
+    ii, jj = np.ascontiguousarray(ii, dtype=np.int64), np.ascontiguousarray(jj, dtype=np.int64)
+    bd = np.ascontiguousarray(bd, dtype=np.int32)
+    g = np.zeros(len(ii))
+    lib().oracle_DirichletBd_backward(_d(g), _l(ii), _l(jj), _d(_f64(g1)), _d(_f64(g2)), C.c_int(len(ii)), bd.ctypes.data_as(c_ip), C.c_int(len(bd)),
+                                      C.c_int(m), C.c_int(n))
+    return g
+
+
 def impose_dirichlet_fwd(indices, vv, bd0, rhs, bdval):
     """deps/MFEM/ImposeDirichlet/ImposeDirichlet.h:27-60. `bd0` is 0-based here (the C symbol takes 1-based)."""
     indices = np.ascontiguousarray(indices, dtype=np.int64)

@@ -51,6 +51,68 @@ def test_impose_dirichlet_coo(oracle, dup):
     close(gv.cpu().numpy(), egv); close(gr.cpu().numpy(), egr); close(gb.cpu().numpy(), egb)
 
 
+def test_impose_dirichlet_is_bit_reproducible(oracle):
+    """rhs correction and grad_bdval are segmented reductions in slot order (no atomics): identical bits run to run, and the rhs is
+    bit-identical to the oracle's sequential loop when every product is formed the same way (values chosen exactly representable)."""
+    c, e = meshgen.jitter_unstructured(40, 30, 0.1, seed=3)
+    m, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    rng = np.random.default_rng(5)
+    ind, _ = o.laplace_fwd(np.ones(o.ngauss))
+    vv = rng.integers(-8, 9, len(ind)).astype(np.float64) / 4          # dyadic values: products and partial sums are exact in any association
+    rhs = rng.integers(-8, 9, o.ndof).astype(np.float64)
+    bd = rng.permutation(A.bcnode(m))
+    bdval = rng.integers(-8, 9, len(bd)).astype(np.float64) / 2
+    oi, ov, orhs = oracle.impose_dirichlet_fwd(ind, vv, bd, rhs, bdval)
+    outs = []
+    for _ in range(3):
+        v_t, r_t, b_t = dev(vv).requires_grad_(True), dev(rhs).requires_grad_(True), dev(bdval).requires_grad_(True)
+        B, r2 = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), v_t, o.ndof, o.ndof), r_t, bd, b_t)
+        w = torch.arange(o.ndof, dtype=torch.float64, device="cuda") / 16
+        (gb,) = torch.autograd.grad(r2, b_t, w)
+        outs.append((r2.detach().cpu().numpy(), gb.cpu().numpy()))
+    assert np.array_equal(outs[0][0], orhs)
+    for r, g in outs[1:]:
+        assert np.array_equal(r, outs[0][0]) and np.array_equal(g, outs[0][1])
+    # irrational values: still bit-identical run to run
+    vv2 = rng.standard_normal(len(ind))
+    res = [A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), dev(vv2), o.ndof, o.ndof), dev(rhs), bd, dev(bdval))[1].cpu().numpy() for _ in range(3)]
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+    close(res[0], oracle.impose_dirichlet_fwd(ind, vv2, bd, rhs, bdval)[2])
+
+
+@pytest.mark.parametrize("base,dup", [(1, False), (0, False), (1, True)])
+def test_dirichlet_bd_op(oracle, base, dup):
+    """DirichletBd (deps/DirichletBd/DirichletBd.h:8-60): both outputs bit-exact in order, indices and values (values are copies or 1.0), and
+    the gradient; the COO input is the structured two-component stiffness operator (UnivariateFemStiffness slots, duplicates included)."""
+    m, n, h = 7, 5, 0.2
+    rng = np.random.default_rng(3 + base)
+    nn = (m + 1) * (n + 1)
+    # a two-component COO operator with duplicates: every cell couples its 4 nodes in both components
+    cells = np.arange(m * n)
+    ci, cj = cells % m, cells // m
+    nodes = np.stack([cj * (m + 1) + ci, cj * (m + 1) + ci + 1, (cj + 1) * (m + 1) + ci, (cj + 1) * (m + 1) + ci + 1], 1)
+    dofs = np.concatenate([nodes, nodes + nn], 1)                                   # 8 dofs per cell
+    ii = np.repeat(dofs, 8, axis=1).reshape(-1) + base
+    jj = np.tile(dofs, (1, 8)).reshape(-1) + base
+    vv = rng.standard_normal(len(ii))
+    bnode = np.unique(np.concatenate([np.arange(m + 1), np.arange(n + 1) * (m + 1), np.arange(n + 1) * (m + 1) + m]))   # bottom, left, right
+    bd = rng.permutation(bnode) + base
+    if dup:
+        bd = np.concatenate([bd, bd[:4]])
+    ref = oracle.dirichlet_bd_fwd(ii, jj, vv, bd, m, n)
+    Acoo = A.SparseTensor(dev(np.stack([ii, jj], 1)), dev(vv).requires_grad_(True), 2 * nn + base, 2 * nn + base)
+    A1, A2 = A.fem_impose_Dirichlet_boundary_condition_experimental(Acoo, bd, m, n, h)
+    got = [A1.indices[:, 0], A1.indices[:, 1], A1.values, A2.indices[:, 0], A2.indices[:, 1], A2.values]
+    for g, r in zip(got, ref):
+        assert np.array_equal(g.detach().cpu().numpy(), r)
+    assert A2.shape[1] == 2 * len(bd) and int(A2.indices[:, 1].max()) <= 2 * len(bd) and int(A2.indices[:, 1].min()) >= 1
+    w1, w2 = rng.standard_normal(len(ref[2])), rng.standard_normal(len(ref[5]))
+    (g,) = torch.autograd.grad([A1.values, A2.values], Acoo.values, [dev(w1), dev(w2)])
+    assert np.array_equal(g.cpu().numpy(), oracle.dirichlet_bd_bwd(ii, jj, w1, w2, bd, m, n))
+    with pytest.raises(A.AdfemError):
+        A.fem_impose_Dirichlet_boundary_condition_experimental(Acoo, np.array([10 ** 6]), m, n, h)
+
+
 def test_impose_dirichlet_eager_matches_dense_julia_version():
     """test/mfem.jl:78-88: the op equals the dense slicing implementation (src/MFEM/MUtils.jl:184-199)."""
     rng = np.random.default_rng(1)

@@ -426,3 +426,24 @@ def test_plane_stress_matrix_published_value(oracle):
     ref = np.array([[1.604938, 0.864198, 0.0], [0.864198, 1.604938, 0.0], [0.0, 0.0, 0.37037]])
     assert np.abs(H - ref).max() < 6e-7
     assert np.abs(oracle.plane_matrix_fwd([1.0], [0.35], 0)[0] - ref).max() > 0.1          # mode 0 is the other matrix
+
+
+def test_dirichlet_bd_known_answer(oracle):
+    """DirichletBd on a 1 x 1 cell, two components (8 dofs, 1-based like Julia's find(A)): node 1 on the boundary -> dofs 1 and 5.
+    Dense check against the slicing definition: A1 = A with rows / columns {1, 5} replaced by the identity, A2 = A[free, (1, 5)]."""
+    m = n = 1
+    N = 8
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((N, N))
+    ii, jj = np.nonzero(np.ones((N, N)))
+    vv = D[ii, jj]
+    ii1, jj1, vv1, ii2, jj2, vv2 = oracle.dirichlet_bd_fwd(ii + 1, jj + 1, vv, np.array([1]), m, n)
+    A1 = np.zeros((N, N)); np.add.at(A1, (ii1 - 1, jj1 - 1), vv1)
+    A2 = np.zeros((N, 2)); np.add.at(A2, (ii2 - 1, jj2 - 1), vv2)
+    E = D.copy(); E[[0, 4], :] = 0; E[:, [0, 4]] = 0; E[0, 0] = E[4, 4] = 1
+    F = D[:, [0, 4]].copy(); F[[0, 4], :] = 0
+    assert np.array_equal(A1, E) and np.array_equal(A2, F)
+    assert list(ii1[-2:]) == [1, 5] and list(vv1[-2:]) == [1.0, 1.0]           # unit diagonal appended in ascending dof order
+    g = oracle.dirichlet_bd_bwd(ii + 1, jj + 1, np.arange(len(vv1), dtype=float), 100 + np.arange(len(vv2), dtype=float), np.array([1]), m, n)
+    free = ~np.isin(ii, [0, 4])
+    assert np.all(g[~free] == 0) and np.count_nonzero(g[free & np.isin(jj, [0, 4])] >= 100) == 12
