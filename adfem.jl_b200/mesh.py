@@ -46,16 +46,29 @@ class _MeshBase:
         self.gauss_per_elem = info(_lib.INFO_GAUSS_PER_ELEM)
         self.elem_type = P1 if degree == 1 else P2
         self.degree = degree
-        edges = np.zeros(2 * max(self.nedge, 1), dtype=np.int64)
-        check(L.adfem_mesh_edges(h, edges.ctypes.data_as(_lib.c_lp)))
-        self.edges = edges[:2 * self.nedge].reshape(2, self.nedge).T - 1
-        conn = np.zeros(self.nelem * self.elem_ndof, dtype=np.int64)
-        check(L.adfem_mesh_connectivity(h, conn.ctypes.data_as(_lib.c_lp)))
-        self.conn = conn.reshape(self.nelem, self.elem_ndof) - 1
-        ev = np.zeros(self.nelem * (self.dim + 1), dtype=np.int64)
-        check(L.adfem_mesh_element_to_vertices(h, ev.ctypes.data_as(_lib.c_lp)))
-        self.elems = ev.reshape(self.dim + 1, self.nelem).T - 1     # post orientation fix, like src/MFEM/MFEM.jl:106
+        self._lazy = {}                                            # edges / conn / elems: ne x d int64 copies, fetched on first use only
         self._csr = {}
+
+    def _fetch(self, name):
+        if name not in self._lazy:
+            L, h = lib(), self.handle
+            if name == "edges":
+                edges = np.zeros(2 * max(self.nedge, 1), dtype=np.int64)
+                check(L.adfem_mesh_edges(h, edges.ctypes.data_as(_lib.c_lp)))
+                self._lazy[name] = edges[:2 * self.nedge].reshape(2, self.nedge).T - 1
+            elif name == "conn":
+                conn = np.zeros(self.nelem * self.elem_ndof, dtype=np.int64)
+                check(L.adfem_mesh_connectivity(h, conn.ctypes.data_as(_lib.c_lp)))
+                self._lazy[name] = conn.reshape(self.nelem, self.elem_ndof) - 1
+            else:
+                ev = np.zeros(self.nelem * (self.dim + 1), dtype=np.int64)
+                check(L.adfem_mesh_element_to_vertices(h, ev.ctypes.data_as(_lib.c_lp)))
+                self._lazy[name] = ev.reshape(self.dim + 1, self.nelem).T - 1     # post orientation fix, like src/MFEM/MFEM.jl:106
+        return self._lazy[name]
+
+    edges = property(lambda self: self._fetch("edges"))            # nedge x 2, 0-based (src/MFEM/MFEM.jl:99-100)
+    conn = property(lambda self: self._fetch("conn"))              # ne x d global dofs, 0-based
+    elems = property(lambda self: self._fetch("elems"))            # ne x (dim+1) vertices after the orientation fix
 
     def __del__(self):
         h = getattr(self, "handle", None)

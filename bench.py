@@ -243,13 +243,18 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
         what = {"4": "Laplace and mass", "4l": "Laplace", "4m": "mass"}[case]
         coords, elems = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2, permute=(numbering == "random"))
         note = (f"config 4: P2 {what}, jittered triangulation with random diagonals, {n} x {n} cells ({2 * n * n} triangles), "
-                + ("nodes and elements randomly renumbered (worst case for locality)" if numbering == "random" else "generator (row-major) numbering"))
+                + ("nodes randomly renumbered (worst case for the locality of the CSR rows), elements in Morton order of their centroids (what a partitioner "
+                   "delivers; the element blocks of the N-GPU runs are contiguous ranges of this order)" if numbering == "random" else
+                   "generator (row-major) numbering of nodes and elements"))
+        if numbering == "random":
+            elems = elems[meshgen.morton_element_order(coords, elems)]         # same element order at every N, so the strong-scaling curve compares like with like
         op = 1 if case == "4m" else 0
         if world == 1:
             return A.Mesh(coords, elems, degree=2, **kw), None, op, 1, note, "strong"
-        elems = elems[meshgen.morton_element_order(coords, elems)]             # element blocks are made spatially compact first; the node numbering stays
+        if numbering != "random":
+            elems = elems[meshgen.morton_element_order(coords, elems)]
         part, _ = adist.partition_elements(coords, elems, rank, world, degree=2, **kw)
-        return part.mesh, part, op, 1, note + "; Morton element blocks, one per GPU", "strong"
+        return part.mesh, part, op, 1, note + "; one contiguous element block per GPU", "strong"
     if case == "5":
         n = max(2, int(215 * scale))
         l = max(2 * world, int(208 * scale) // (2 * world) * (2 * world))
@@ -261,6 +266,34 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
         part = adist.structured_slab3(n, l, 1.0 / n, rank, world, **kw)
         return part.mesh, part, 2, 36, note, "strong"
     raise SystemExit("unknown case " + case)
+
+
+def link_probe(world, nbytes=1 << 29, reps=4):
+    """What the box's host <-> device path gives when every rank copies at once: `reps` x (H2D + D2H of `nbytes` each, concurrently on two
+    streams, pinned host memory).  Context for the end-to-end number: the host-buffer calls cannot be faster than this."""
+    import torch
+    import torch.distributed as dist
+    h_in, h_out = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory(), torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+    h_in.fill_(1.0)
+    d_in, d_out = torch.empty_like(h_in, device="cuda"), torch.ones(nbytes // 8, dtype=torch.float64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for timed in (False, True):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps if timed else 1):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"duplex_GBps_all_ranks": world * 2 * reps * nbytes / t.item() / 1e9, "bytes_each_way_per_rank": reps * nbytes,
+            "how": "all ranks at once, H2D and D2H concurrently, pinned memory, max time over ranks"}
 
 
 class DeviceStep:
@@ -334,6 +367,28 @@ class DeviceStep:
         if self.part is not None:
             self.main.wait_stream(self.side)
 
+    def exchange_alone_ms(self, reps=10):
+        """the two interface exchanges of a step by themselves on the main stream (no kernel to hide behind): pack kernel -> ncclSend/ncclRecv
+        group -> unpack kernel, once for reduce(vals) and once for replicate(dK); max over ranks"""
+        if self.part is None:
+            return None
+        import torch.distributed as dist
+        torch = self.torch
+        self.join()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for timed in (False, True):
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps if timed else 2):
+                self.part.reduce_interface(self.vals, ncomp=self.nc)
+                self.part.replicate_interface(self.dK, self.dghost, ncomp=self.nc)
+            ev1.record()
+            torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
 
 def time_steps(step, K, warmup, world, sampler=None):
     """W untimed steps, then exactly K steps between barrier + synchronize on both sides; CUDA events on the launching stream;
@@ -389,6 +444,7 @@ def case_records(case, rank, world, steps, warmup, scale, peak, traffic, library
         torch.cuda.synchronize()
         setup = time.perf_counter() - t0
         ms, f_ms, a_ms, x_ms = time_steps(step, steps, warmup, world)
+        xa_ms = step.exchange_alone_ms()
         E = mesh.nelem
         b = alg_bytes_per_elem(mesh, step.nnz, cpg)
         cnt = torch.tensor([float(E), float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0, b * E], dtype=torch.float64, device="cuda")
@@ -410,7 +466,8 @@ def case_records(case, rank, world, steps, warmup, scale, peak, traffic, library
                                   "traffic": {"fwd": (sum(tr_f) if all(t is not None for t in tr_f) else None), "adj": (sum(tr_a) if all(t is not None for t in tr_a) else None),
                                               "alg_bytes_per_launch": b * E}},
                      "plan_bytes_per_elem": L.adfem_mesh_info(mesh.handle, _lib.INFO_PLAN_BYTES) / E, "setup_s_untimed": round(setup, 1),
-                     "exchange": step.exchange, "interface_bytes_per_step_total": int(ibytes), "steps": steps, "warmup": warmup})
+                     "exchange": step.exchange, "interface_bytes_per_step_total": int(ibytes), "exchange_alone_ms": xa_ms,
+                     "steps": steps, "warmup": warmup})
         del step
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
@@ -496,6 +553,7 @@ def main():
     if world > 1:
         dist.all_reduce(cnt)
     Etot = cnt.item()
+    xa_ms = step.exchange_alone_ms()
     value = Etot / (ms_per_step * 1e-3) / 1e6
     h = mesh.handle
 
@@ -537,9 +595,10 @@ def main():
         bi, bo = 8 * (G * cpg + nnz), 8 * (nnz + G * cpg)
         e2e = {"value": Etot / te.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
                "ms_per_step": te.item() * 1e3, "api": "adfem_assemble_csr_host + adfem_assemble_csr_adjoint_host (pinned host buffers)",
-               "host_link_GBps_all_ranks": world * (bi + bo) / te.item() / 1e9,
-               "note": "bound by PCIe at N=1 and by the host memory system shared by all ranks at N>1 (one NUMA node on this box); "
-                       "interface rows of the multi-rank step stay partial sums on the host copy (the exchange runs on device buffers)"}
+               "host_link_GBps_all_ranks": world * (bi + bo) / te.item() / 1e9, "link_probe": link_probe(world),
+               "note": "bound by the host <-> device path: compare host_link_GBps_all_ranks (what the step moved) with link_probe (plain copies of all "
+                       "ranks at once); at N>1 the ranks share one host memory system / PCIe root (one NUMA node on this box).  Interface rows of the "
+                       "multi-rank step stay partial sums on the host copy (the exchange runs on device buffers)"}
         if part is None:
             assert torch.equal(hv.cuda(), step.vals), "host-buffer path and device path disagree"
         del hk, hv, hd, hg
@@ -616,7 +675,7 @@ def main():
                        "parallelism": ("element blocks; interface rows: " + str(headline_exchange) + " on a high-priority side stream (reduce(vals) overlaps the adjoint "
                                        "kernel, replicate(dK) the forward kernel); %d interface bytes per step on rank 0" % int(ibytes)) if world > 1 else "single GPU"},
             "roofline": roofline, "general_path": general, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches * K, "clocks": sampler.result(),
-            "extra": {"configs": extras, "wait_for_exchange_ms": xch_ms}}
+            "extra": {"configs": extras, "wait_for_exchange_ms": xch_ms, "exchange_alone_ms": xa_ms}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

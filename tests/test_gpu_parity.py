@@ -322,9 +322,11 @@ def test_empty_and_tiny_meshes(oracle):
             close(S.data, ref)
 
 
-def test_device_resident_csr_pattern():
-    """adfem_csr_pattern_device hands out the handle's device copies of rowptr / colind (solver hand-off): identical to the
-    host pattern, and together with adfem_assemble_csr's values a complete device CSR matrix."""
+@pytest.mark.parametrize("degree", [1, 2])
+def test_device_resident_csr_pattern(oracle, degree):
+    """adfem_csr_pattern_device hands out the handle's device copies of rowptr / colind (solver hand-off): bit-identical to the
+    ORACLE's canonical CSR pattern (sorted, duplicates summed, from the reference's COO output), and together with adfem_assemble_csr's
+    values a complete device CSR matrix whose dense form equals the oracle's; a device-side solve with it reproduces the oracle's solution."""
     import ctypes as C
 
     class _Dev:                                    # wrap a raw device pointer for torch (CUDA array interface)
@@ -332,7 +334,7 @@ def test_device_resident_csr_pattern():
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
     c, e = meshgen.jitter_unstructured(13, 11, 0.1, seed=9)
-    m = A.Mesh(c, e)
+    m, o = A.Mesh(c, e, degree=degree), oracle.Mesh2D(c, e, degree=degree)
     rowptr, colind = m.csr_pattern(1)
     prp, pci = C.c_void_p(), C.c_void_p()
     A._lib.check(A._lib.lib().adfem_csr_pattern_device(m.handle, C.byref(prp), C.byref(pci)))
@@ -340,6 +342,20 @@ def test_device_resident_csr_pattern():
     d_ci = torch.as_tensor(_Dev(pci.value, len(colind), "<i4"), device="cuda")
     assert np.array_equal(d_rp.cpu().numpy(), rowptr) and np.array_equal(d_ci.cpu().numpy(), colind)
     k = torch.rand(m.ngauss, dtype=torch.float64, device="cuda") + 0.5
+    ind, vv = o.laplace_fwd(k.cpu().numpy())
+    rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+    assert np.array_equal(d_rp.cpu().numpy(), rp) and np.array_equal(d_ci.cpu().numpy().astype(np.int64), ci)          # device pattern == oracle pattern
     T = ops.compute_fem_laplace_matrix1(k, m, mode="csr")
     K = torch.sparse_csr_tensor(d_rp, d_ci.to(torch.int64), T.values, size=(m.ndof, m.ndof))
-    assert (K.to_dense() @ torch.ones(m.ndof, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-10       # K 1 = 0
+    import scipy.sparse as sps
+    Kref = sps.csr_matrix((ref, ci, rp), shape=(o.ndof, o.ndof)).toarray()
+    close(K.to_dense().cpu().numpy(), Kref)
+    # solver hand-off: K + M is SPD; solve on the device from the device CSR, compare with the oracle matrices solved on the host
+    Mv = ops.compute_fem_mass_matrix1(torch.ones_like(k), m, mode="csr").values
+    indm, vm = o.mass_fwd(np.ones(o.ngauss))
+    _, _, refm = oracle.canonical_csr(indm, vm, o.ndof)
+    Aref = Kref + sps.csr_matrix((refm, ci, rp), shape=(o.ndof, o.ndof)).toarray()
+    b = np.random.default_rng(0).standard_normal(o.ndof)
+    Ad = torch.sparse_csr_tensor(d_rp, d_ci.to(torch.int64), T.values + Mv, size=(m.ndof, m.ndof)).to_dense()
+    x = torch.linalg.solve(Ad, torch.from_numpy(b).cuda())
+    close(x.cpu().numpy(), np.linalg.solve(Aref, b), rel=1e-9)
