@@ -9,18 +9,27 @@ import numpy as np
 
 def tri_grid(m, n, h, version=1, rng=None):
     """(m+1)(n+1) nodes, 2mn triangles. version 1/2 = the two diagonal directions, 3 = random per cell."""
-    jj, ii = np.meshgrid(np.arange(m, dtype=np.int64), np.arange(n, dtype=np.int64))   # ii: row (y), jj: col (x)
-    a = (ii * (m + 1) + jj).reshape(-1)
-    v1 = np.stack([np.stack([a, a + 1, a + m + 1], 1), np.stack([a + 1, a + m + 1, a + m + 2], 1)], 1)     # MFEM.jl:143-145
-    v2 = np.stack([np.stack([a, a + m + 2, a + m + 1], 1), np.stack([a, a + 1, a + m + 2], 1)], 1)         # MFEM.jl:146-148
+    a = (np.arange(n, dtype=np.int64)[:, None] * (m + 1) + np.arange(m, dtype=np.int64)[None, :]).reshape(-1)   # lower-left node of cell (row ii, col jj)
+
+    def fill(el, mask, tris):          # el[cells, 2, 3] <- the two triangles `tris` (offsets from a) of the cells in `mask`, without temporaries
+        for t in range(2):
+            for k in range(3):
+                if mask is None:
+                    np.add(a, tris[t][k], out=el[:, t, k])
+                else:
+                    el[mask, t, k] = a[mask] + tris[t][k]
+    v1 = ((0, 1, m + 1), (1, m + 1, m + 2))                                                                # MFEM.jl:143-145
+    v2 = ((0, m + 2, m + 1), (0, 1, m + 2))                                                                # MFEM.jl:146-148
+    el = np.empty((m * n, 2, 3), dtype=np.int64)
     if version == 1:
-        el = v1
+        fill(el, None, v1)
     elif version == 2:
-        el = v2
+        fill(el, None, v2)
     elif version == 3:
         rng = np.random.default_rng(0) if rng is None else rng
         pick = rng.random(m * n) > 0.5                                                                     # MFEM.jl:149-156
-        el = np.where(pick[:, None, None], v1, v2)
+        fill(el, pick, v1)
+        fill(el, ~pick, v2)
     else:
         raise ValueError("version must be 1, 2 or 3")
     elems = el.reshape(2 * m * n, 3)
