@@ -90,6 +90,7 @@ struct adfem_mesh {
   int opt_area_csr = 0, opt_area_coo = 1;   // 2-D weight scale: 0 = det/2, 1 = Heron (reference formula)
   // structured triangulation Mesh(m, n, h) (tri_grid.cuh): detected from the arrays, no mesh-static index data is read
   bool grid_ok = false;
+  bool grid_mapped = false;                 // structured connectivity, non-rectilinear node positions: scalar CSR kernels only (MAPPED)
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
   int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh)
@@ -138,7 +139,10 @@ int need_device(const adfem_mesh* m) {
 }
 
 // Is this the reference's structured triangulation (src/MFEM/MFEM.jl:134-146, version 1) on rectilinear coordinates?
-bool detect_tri_grid(const HostMesh& h, int& m, int& n, std::vector<double>& xs, std::vector<double>& ys) {
+// `mapped` = the connectivity is the generator's but the node positions are not rectilinear (a jittered / mapped grid): the scalar CSR
+// kernels then read the positions from the coordinate array (tri_grid.cuh, MAPPED), every other structured kernel is not used.
+bool detect_tri_grid(const HostMesh& h, int& m, int& n, std::vector<double>& xs, std::vector<double>& ys, bool& mapped) {
+  mapped = false;
   if (h.dim != 2 || h.degree != 1 || h.g != 3 || h.ne < 2 || h.nv < 4) return false;
   const int* v = h.verts.data();
   if (v[0] != 0 || v[1] != 1 || v[2] < 2) return false;
@@ -155,13 +159,14 @@ bool detect_tri_grid(const HostMesh& h, int& m, int& n, std::vector<double>& xs,
   xs.resize(m + 1); ys.resize(n + 1);
   for (int j = 0; j <= m; j++) xs[j] = h.coords[2 * (size_t)j];
   for (int i = 0; i <= n; i++) ys[i] = h.coords[2 * (size_t)i * (m + 1) + 1];
-  for (int j = 0; j < m; j++) if (!(xs[j] < xs[j + 1])) return false;
-  for (int i = 0; i < n; i++) if (!(ys[i] < ys[i + 1])) return false;
-  for (int i = 0; i <= n; i++)
+  for (int j = 0; j < m && !mapped; j++) if (!(xs[j] < xs[j + 1])) mapped = true;
+  for (int i = 0; i < n && !mapped; i++) if (!(ys[i] < ys[i + 1])) mapped = true;
+  for (int i = 0; i <= n && !mapped; i++)
     for (int j = 0; j <= m; j++) {
       const double* c = &h.coords[2 * ((size_t)i * (m + 1) + j)];
-      if (c[0] != xs[j] || c[1] != ys[i]) return false;       // bitwise: the kernels recompute nothing, they index xs / ys
+      if (c[0] != xs[j] || c[1] != ys[i]) { mapped = true; break; }       // bitwise: the rectilinear kernels recompute nothing, they index xs / ys
     }
+  // the vertex order above is the one AFTER the orientation fix, so every triangle is positively oriented in either case
   return true;
 }
 
@@ -480,7 +485,8 @@ int ensure_host_streams(adfem_mesh* m) {
   return 0;
 }
 
-bool use_grid(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }
+bool use_grid_any(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }      // scalar CSR operators: rectilinear or mapped
+bool use_grid(adfem_mesh* m) { return use_grid_any(m) && !m->grid_mapped; }                        // everything else: rectilinear only
 
 int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
   if (m->opt_grid_rows > 0) return m->opt_grid_rows;
@@ -504,6 +510,7 @@ template <int OP> int launch_grid_fwd(adfem_mesh* m, const double* coef, double*
   if (r1 < 0) r1 = gt.n + 1;
   const int strips = (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, r1 - r0), chunks = (r1 - r0 + H - 1) / H;
   const long long warps = (long long)strips * chunks;
+  if (m->grid_mapped) return launch_grid(k_grid_fwd<OP, 2, true>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, coef, vals);
   if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_fwd<OP, 3>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, coef, vals);
   return launch_grid(k_grid_fwd<OP, 2>, GRID_FWD_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, coef, vals);
 }
@@ -513,6 +520,7 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
   if (r1 < 0) r1 = gt.n;
   const int strips = (gt.m + GRID_STRIP - 1) / GRID_STRIP, H = grid_rows_per_warp(m, strips, r1 - r0), chunks = (r1 - r0 + H - 1) / H;
   const long long warps = (long long)strips * chunks;
+  if (m->grid_mapped) return launch_grid(k_grid_adj<OP, 2, true>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
   if (m->opt_grid_occupancy >= 3) return launch_grid(k_grid_adj<OP, 3>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
   return launch_grid(k_grid_adj<OP, 2>, GRID_ADJ_SMEM, warps, st, dev_mesh(m, m->opt_area_csr), gt, r0, r1, H, dvals, grad);
 }
@@ -701,7 +709,7 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
   if (!err.empty()) return fail(err);
   m->host_only = (flags & ADFEM_HOST_ONLY) != 0;
   std::vector<double> grid_xs, grid_ys;
-  m->grid_ok = detect_tri_grid(m->hm, m->grid_m, m->grid_n, grid_xs, grid_ys);
+  m->grid_ok = detect_tri_grid(m->hm, m->grid_m, m->grid_n, grid_xs, grid_ys, m->grid_mapped);
   m->tet_ok = detect_tet_grid(m->hm, m->tet_n, m->tet_l, m->tet_axes);
   if (m->tet_ok) build_tet_grid_tables(m->tet_tab);
   if (!m->host_only) {
@@ -752,7 +760,7 @@ long long adfem_mesh_info(const adfem_mesh* m, int what) {
       for (auto& kv : m->adj_plans) b += (long long)kv.second->bytes;
       return b;
     }
-    case ADFEM_INFO_STRUCTURED: return m->grid_ok ? 1 : (m->tet_ok ? 2 : 0);
+    case ADFEM_INFO_STRUCTURED: return m->grid_ok ? (m->grid_mapped ? 3 : 1) : (m->tet_ok ? 2 : 0);
     default: return -1;
   }
 }
@@ -882,7 +890,7 @@ int adfem_assemble_csr(adfem_mesh* m, int op, const double* coef, double* vals, 
   if (m->tet_ok && (m->opt_tet_scalar || (m->opt_grid_elast && op == ADFEM_OP_STIFFNESS))) { if (int rc = ensure_pattern(m)) return rc; }    // validates the closed-form rows
   if (use_tet_grid(m, op)) return launch_tet_grid_fwd(m, coef, vals, st);
   if (use_tet_scalar(m, op)) return launch_tet_scalar(m, op, false, coef, vals, st);
-  if (op != ADFEM_OP_STIFFNESS && use_grid(m))
+  if (op != ADFEM_OP_STIFFNESS && use_grid_any(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_fwd<OP_LAPLACE>(m, coef, vals, st) : launch_grid_fwd<OP_MASS>(m, coef, vals, st);
   if (op != ADFEM_OP_STIFFNESS && m->opt_row_gather) {
     if (int rc = ensure_pattern(m)) return rc;
@@ -947,7 +955,7 @@ int adfem_assemble_csr_adjoint(adfem_mesh* m, int op, const double* dvals, doubl
   if (int rc = check_op(m, op)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (op != ADFEM_OP_STIFFNESS && use_grid(m))
+  if (op != ADFEM_OP_STIFFNESS && use_grid_any(m))
     return op == ADFEM_OP_LAPLACE ? launch_grid_adj<OP_LAPLACE>(m, dvals, grad_coef, st) : launch_grid_adj<OP_MASS>(m, dvals, grad_coef, st);
   if (use_grid_elast(m, op)) return launch_grid_elast(m, true, dvals, grad_coef, st);
   if (use_tet_grid(m, op)) return launch_tet_grid_adj(m, dvals, grad_coef, st);
@@ -1207,7 +1215,7 @@ int adfem_assemble_csr_host(adfem_mesh* m, int op, const double* coef_host, doub
   if (nout < 0) return 1;
   if (m->s_in.n < (size_t)nin) CU_TRY(m->s_in.alloc(nin));
   if (m->s_out.n < (size_t)nout) CU_TRY(m->s_out.alloc(nout));
-  if (op != ADFEM_OP_STIFFNESS && use_grid(m) && m->opt_host_chunks > 1) {
+  if (op != ADFEM_OP_STIFFNESS && use_grid_any(m) && m->opt_host_chunks > 1) {
     // structured mesh: node-row chunks flow through three streams, so the H2D copy of chunk c+1, the kernel of chunk c and the
     // D2H copy of chunk c-1 overlap (PCIe is full duplex).  Chunk c needs the coefficients of cell rows < R[c+1] and writes the
     // contiguous CSR range of node rows [R[c], R[c+1]).
@@ -1245,7 +1253,7 @@ int adfem_assemble_csr_adjoint_host(adfem_mesh* m, int op, const double* dvals_h
   if (nin < 0) return 1;
   if (m->s_out.n < (size_t)nin) CU_TRY(m->s_out.alloc(nin));
   if (m->s_in.n < (size_t)nout) CU_TRY(m->s_in.alloc(nout));
-  if (op != ADFEM_OP_STIFFNESS && use_grid(m) && m->opt_host_chunks > 1) {
+  if (op != ADFEM_OP_STIFFNESS && use_grid_any(m) && m->opt_host_chunks > 1) {
     // cell-row chunks [C[c], C[c+1]) need the upstream CSR rows of node rows <= C[c+1] and write a contiguous gradient range
     if (int rc = ensure_host_streams(m)) return rc;
     const int gm = m->grid_m, gn = m->grid_n, C = std::min(m->opt_host_chunks, gn);

@@ -68,6 +68,17 @@ __device__ __forceinline__ void grid_cell_matrices(const DevMesh& m, double x0, 
   }
 }
 
+// the same for a cell with ARBITRARY corner positions (structured connectivity on mapped / jittered coordinates, template flag MAPPED below)
+template <int OP>
+__device__ __forceinline__ void grid_cell_matrices_pts(const DevMesh& m, double2 BL, double2 BR, double2 TL, double2 TR, const double kap[6], double T0[6],
+                                                       double T1[6]) {
+  Geom<2> G;
+  geom_tri(BL, BR, TL, m.heron, G);
+  local_matrix_scalar<2, 1, OP, 3>(m, G, [&](int k) { return kap[k]; }, [&](int s, double v) { T0[s] = v; });
+  geom_tri(TL, BR, TR, m.heron, G);
+  local_matrix_scalar<2, 1, OP, 3>(m, G, [&](int k) { return kap[3 + k]; }, [&](int s, double v) { T1[s] = v; });
+}
+
 // per-warp shared memory of k_grid_fwd: the output transpose buffer
 constexpr int GRID_FWD_WARP_DOUBLES = GRID_STRIP * 7 + 1;
 constexpr int GRID_FWD_SMEM = GRID_WARPS * GRID_FWD_WARP_DOUBLES * 8;
@@ -75,7 +86,9 @@ constexpr int GRID_FWD_SMEM = GRID_WARPS * GRID_FWD_WARP_DOUBLES * 8;
 // Forward: vals[nnz] of the scalar operator OP on the structured triangulation (3 Gauss points per element).
 // Node rows [r0, r1); grid: ceil(strips * chunks / GRID_WARPS) CTAs of GRID_WARPS warps; `rows_per_warp` node rows per warp.
 // The coefficients of cell row i+2 are loaded into registers while row i is processed (three rotating buffers).
-template <int OP, int MINB>
+// MAPPED: structured connectivity, arbitrary node positions — the corner positions of the lane's cell column come from the coordinate array
+// (16 B per node and strip, loaded one node row ahead) instead of xs / ys; everything else (index arithmetic, shuffles, stores) is unchanged.
+template <int OP, int MINB, bool MAPPED = false>
 __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp,
                                                                     const double* __restrict__ coef, double* __restrict__ vals) {
   extern __shared__ __align__(16) double grid_smem[];
@@ -88,7 +101,15 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, G
   const int i0 = r0 + chunk * rows_per_warp, i1 = min(i0 + rows_per_warp, r1);
   double* stage = grid_smem + (size_t)wib * GRID_FWD_WARP_DOUBLES;
   const bool colok = cj >= 0 && cj < gt.m;                           // this lane's cell column exists
-  const double x0 = colok ? __ldg(gt.xs + cj) : 0.0, x1 = colok ? __ldg(gt.xs + cj + 1) : 1.0;
+  const double x0 = (!MAPPED && colok) ? __ldg(gt.xs + cj) : 0.0, x1 = (!MAPPED && colok) ? __ldg(gt.xs + cj + 1) : 1.0;
+  // MAPPED: positions of nodes (r, cj) and (r, cj + 1)
+  auto points = [&](int r, double2& a, double2& b) {
+    if (colok && r >= 0 && r <= gt.n) {
+      const double2* p = reinterpret_cast<const double2*>(m.coords) + ((size_t)r * (gt.m + 1) + cj);
+      a = __ldg(p); b = __ldg(p + 1);
+    }
+  };
+  double2 qb0 = make_double2(0.0, 0.0), qb1 = make_double2(1.0, 0.0), qt0 = make_double2(0.0, 1.0), qt1 = make_double2(1.0, 1.0);   // node rows i and i + 1
   const bool has_node = lane >= 1 && cj <= gt.m;                     // lanes 1..31 write node column cj
   const bool jl = cj > 0, jr = cj < gt.m;
   const int jend = min(j0 + GRID_STRIP, gt.m + 1);                   // one past the last node column of the strip
@@ -108,11 +129,19 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, G
   double kA[6], kB[6], kC[6], pT0[6], pT1[6], cT0[6], cT1[6];
 #pragma unroll
   for (int s = 0; s < 6; s++) { pT0[s] = pT1[s] = 0.0; kA[s] = kB[s] = kC[s] = 0.0; }
-  double ya = __ldg(gt.ys + i0), yb = __ldg(gt.ys + min(i0 + 1, gt.n));   // ordinates of node rows i, i+1 (loaded one row ahead)
+  double ya = 0.0, yb = 1.0;
+  if constexpr (!MAPPED) { ya = __ldg(gt.ys + i0); yb = __ldg(gt.ys + min(i0 + 1, gt.n)); }   // ordinates of node rows i, i+1 (loaded one row ahead)
+  else { points(i0, qb0, qb1); points(min(i0 + 1, gt.n), qt0, qt1); }
   if (i0 > 0) {                                                      // cell row i0-1 (below the first node row of the chunk)
-    const double ym = __ldg(gt.ys + i0 - 1);
     load(i0 - 1, kC);
-    if (colok) grid_cell_matrices<OP>(m, x0, x1, ym, ya, 1.0 / ((x1 - x0) * (ya - ym)), kC, pT0, pT1);
+    if constexpr (!MAPPED) {
+      const double ym = __ldg(gt.ys + i0 - 1);
+      if (colok) grid_cell_matrices<OP>(m, x0, x1, ym, ya, 1.0 / ((x1 - x0) * (ya - ym)), kC, pT0, pT1);
+    } else {
+      double2 qm0 = qb0, qm1 = qb1;
+      points(i0 - 1, qm0, qm1);
+      if (colok) grid_cell_matrices_pts<OP>(m, qm0, qm1, qb0, qb1, kC, pT0, pT1);
+    }
   }
   load(i0, kA);
   if (i0 + 1 < i1) load(i0 + 1, kB);
@@ -120,10 +149,18 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, G
   double inv = 1.0 / ((x1 - x0) * (yb - ya));                        // 1 / det of cell row i, computed one row ahead
   auto row = [&](int i, const double kcur[6], double kfill[6]) {
     if (i + 2 < i1) load(i + 2, kfill);                              // two cell rows ahead: in flight while rows i, i+1 are computed
-    const double yc = __ldg(gt.ys + min(i + 2, gt.n));               // used by the next row
-    const double inv_next = 1.0 / ((x1 - x0) * (yc - yb));          // independent of this row's dependency chain
-    if (colok && i < gt.n) grid_cell_matrices<OP>(m, x0, x1, ya, yb, inv, kcur, cT0, cT1);
-    else {
+    double yc = 0.0, inv_next = 0.0;
+    double2 qn0 = qt0, qn1 = qt1;
+    if constexpr (!MAPPED) {
+      yc = __ldg(gt.ys + min(i + 2, gt.n));                          // used by the next row
+      inv_next = 1.0 / ((x1 - x0) * (yc - yb));                      // independent of this row's dependency chain
+    } else {
+      points(min(i + 2, gt.n), qn0, qn1);                            // node row i + 2: used by the next row
+    }
+    if (colok && i < gt.n) {
+      if constexpr (!MAPPED) grid_cell_matrices<OP>(m, x0, x1, ya, yb, inv, kcur, cT0, cT1);
+      else grid_cell_matrices_pts<OP>(m, qb0, qb1, qt0, qt1, kcur, cT0, cT1);
+    } else {
 #pragma unroll
       for (int s = 0; s < 6; s++) cT0[s] = cT1[s] = 0.0;
     }
@@ -158,6 +195,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_fwd(DevMesh m, G
     __syncwarp();
     rowbase += grid_row_prefix32(gt.m + 1, gt.m, A, B);
     ya = yb; yb = yc; inv = inv_next;
+    if constexpr (MAPPED) { qb0 = qt0; qb1 = qt1; qt0 = qn0; qt1 = qn1; }
 #pragma unroll
     for (int s = 0; s < 6; s++) { pT0[s] = cT0[s]; pT1[s] = cT1[s]; }
   };
@@ -190,6 +228,16 @@ __device__ __forceinline__ void grid_cell_adjoint(const DevMesh& m, double x0, d
   }
 }
 
+template <int OP>
+__device__ __forceinline__ void grid_cell_adjoint_pts(const DevMesh& m, double2 BL, double2 BR, double2 TL, double2 TR, const double t0[9], const double t1[9],
+                                                      double gk[6]) {
+  Geom<2> G;
+  geom_tri(BL, BR, TL, m.heron, G);
+  local_adjoint_scalar<2, 1, OP, 3>(m, G, [&](int p, int q) { return t0[p * 3 + q]; }, [&](int k, double v) { gk[k] = v; });
+  geom_tri(TL, BR, TR, m.heron, G);
+  local_adjoint_scalar<2, 1, OP, 3>(m, G, [&](int p, int q) { return t1[p * 3 + q]; }, [&](int k, double v) { gk[3 + k] = v; });
+}
+
 // per-warp shared memory of k_grid_adj: a ring of 3 raw node rows (up to 32*7 CSR entries each) + the output transpose buffer
 constexpr int GRID_ADJ_WARP_DOUBLES = 4 * 32 * 7;
 constexpr int GRID_ADJ_SMEM = GRID_WARPS * GRID_ADJ_WARP_DOUBLES * 8;
@@ -197,7 +245,7 @@ constexpr int GRID_ADJ_SMEM = GRID_WARPS * GRID_ADJ_WARP_DOUBLES * 8;
 // Adjoint: grad_coef[e*3 + k] from upstream dvals[nnz].  Lane l owns node column j0+l (32 columns, the last one only feeds
 // its left neighbour) and cell column j0+l for l < 31.  The CSR entries of node row ci+3 (one contiguous run per strip) are
 // requested with asynchronous copies while cell row ci is processed.
-template <int OP, int MINB>
+template <int OP, int MINB, bool MAPPED = false>
 __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp,
                                                                     const double* __restrict__ dvals, double* __restrict__ grad_coef) {
   extern __shared__ __align__(16) double grid_smem[];
@@ -212,7 +260,14 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
   double* stage = ring + 3 * 32 * 7;
   const bool node_ok = j <= gt.m, cell_ok = lane < GRID_STRIP && j < gt.m;
   const bool jl = j > 0, jr = j < gt.m;
-  const double x0 = cell_ok ? __ldg(gt.xs + j) : 0.0, x1 = cell_ok ? __ldg(gt.xs + j + 1) : 1.0;
+  const double x0 = (!MAPPED && cell_ok) ? __ldg(gt.xs + j) : 0.0, x1 = (!MAPPED && cell_ok) ? __ldg(gt.xs + j + 1) : 1.0;
+  auto points = [&](int r, double2& a, double2& b) {                 // MAPPED: positions of nodes (r, j) and (r, j + 1)
+    if (cell_ok && r >= 0 && r <= gt.n) {
+      const double2* p = reinterpret_cast<const double2*>(m.coords) + ((size_t)r * (gt.m + 1) + j);
+      a = __ldg(p); b = __ldg(p + 1);
+    }
+  };
+  double2 qb0 = make_double2(0.0, 0.0), qb1 = make_double2(1.0, 0.0), qt0 = make_double2(0.0, 1.0), qt1 = make_double2(1.0, 1.0);
   const int jend = min(j0 + 32, gt.m + 1);
   const int ncell6 = 6 * min(GRID_STRIP, gt.m - j0);
 
@@ -257,12 +312,16 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
   unpack(c0, 0, lo);
   double* out = grad_coef + 6 * ((size_t)c0 * gt.m + j0) + lane;
   const size_t ostride = (size_t)6 * gt.m;
-  double ya = __ldg(gt.ys + c0), yb = __ldg(gt.ys + c0 + 1);         // ordinates of node rows ci, ci+1 (loaded one row ahead)
+  double ya = 0.0, yb = 1.0;
+  if constexpr (!MAPPED) { ya = __ldg(gt.ys + c0); yb = __ldg(gt.ys + c0 + 1); }   // ordinates of node rows ci, ci+1 (loaded one row ahead)
+  else { points(c0, qb0, qb1); points(c0 + 1, qt0, qt1); }
   int slot = 0;                                                      // ring slot of node row ci
   double inv = 1.0 / ((x1 - x0) * (yb - ya));                        // 1 / det of cell row ci, computed one row ahead
   for (int ci = c0; ci < c1; ci++, out += ostride) {
-    const double yc = __ldg(gt.ys + min(ci + 2, gt.n));
-    const double inv_next = 1.0 / ((x1 - x0) * (yc - yb));
+    double yc = 0.0, inv_next = 0.0;
+    double2 qn0 = qt0, qn1 = qt1;
+    if constexpr (!MAPPED) { yc = __ldg(gt.ys + min(ci + 2, gt.n)); inv_next = 1.0 / ((x1 - x0) * (yc - yb)); }
+    else points(min(ci + 2, gt.n), qn0, qn1);
     const int slot1 = slot == 2 ? 0 : slot + 1;
     cp_async_wait<1>();                                              // node row ci+1 has landed (row ci+2 may be in flight)
     __syncwarp();                                                    // ... for every lane; every lane is also done reading slot (row ci)
@@ -278,7 +337,8 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
       // T0 = [BL, BR, TL], T1 = [TL, BR, TR]: dK(p,q) = entry (row of local p, column of local q)
       const double t0[9] = {lo[3], lo[4], lo[6], br_L, br_C, br_UL, hi[0], hi[1], hi[3]};
       const double t1[9] = {hi[3], hi[1], hi[4], br_UL, br_C, br_U, tr_L, tr_D, tr_C};
-      grid_cell_adjoint<OP>(m, x0, x1, ya, yb, inv, t0, t1, gk);
+      if constexpr (!MAPPED) grid_cell_adjoint<OP>(m, x0, x1, ya, yb, inv, t0, t1, gk);
+      else grid_cell_adjoint_pts<OP>(m, qb0, qb1, qt0, qt1, t0, t1, gk);
     }
     // the 6 gradients of every cell of the strip leave through the transpose buffer as one contiguous, coalesced run
     if (lane < GRID_STRIP) {
@@ -292,6 +352,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
 #pragma unroll
     for (int k = 0; k < 7; k++) lo[k] = hi[k];
     ya = yb; yb = yc; inv = inv_next;
+    if constexpr (MAPPED) { qb0 = qt0; qb1 = qt1; qt0 = qn0; qt1 = qn1; }
     slot = slot1;
   }
 }

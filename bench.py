@@ -72,6 +72,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.armed, self.samples, self.reasons, self.max_mhz, self.err = index, False, False, [], set(), None, None
+        self.timed = False          # inside the K timed steps (a subset of `armed`, which also covers the warm-up steps right before them)
+        self.n_timed = 0
         self.ready = threading.Event()
 
     def run(self):
@@ -86,6 +88,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 if self.armed:
                     self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    self.n_timed += 1 if self.timed else 0
                     try:
                         r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                     except Exception:
@@ -93,7 +96,7 @@ class ClockSampler(threading.Thread):
                     for k, bit in names.items():
                         if r & bit:
                             self.reasons.add(k)
-                time.sleep(0.001)
+                time.sleep(0.0005)
         except Exception as ex:  # NVML missing: report it, do not fail the bench
             self.err = type(ex).__name__
             self.reasons.add("nvml_unavailable:" + self.err)
@@ -102,7 +105,8 @@ class ClockSampler(threading.Thread):
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "samples_in_timed_region": self.n_timed,
+                "window": "warm-up steps + the K timed steps of the headline config (same kernels back to back; an NVML query takes 1-20 ms, the timed region 60 ms)"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -210,11 +214,12 @@ def bind_to_gpu_numa_node(local):
 CASE_KERNELS = {          # (forward kernels, adjoint kernels) of the default path, names as ncu prints them (keys of profiles/traffic.json)
     "2": (["k_grid_fwd<LAPLACE>"], ["k_grid_adj<LAPLACE>"]),
     "2g": (["k_tile_fwd<2,1,LAPLACE,1,0>"], ["k_tile_adj<2,1,LAPLACE>"]),
+    "2m": (["k_grid_fwd<LAPLACE,MAPPED>"], ["k_grid_adj<LAPLACE,MAPPED>"]),
     "3": (["k_grid_elast_fwd<LAPLACE>"], ["k_grid_elast_adj<LAPLACE>"]),
     "4l": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4m": (["k_tile_fwd<2,2,MASS,0,1>"], ["k_tile_adj<2,2,MASS>"]),
-    "5": (["k_tet_presum_x", "k_tet_node_fwd"], ["k_tet_grid_elast_adj"]),
+    "5": (["k_tet_presum_xg<4>", "k_tet_node_fwd"], ["k_tet_grid_elast_adj<3>"]),
 }
 
 
@@ -230,6 +235,16 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
             return A.Mesh(n, n, 1.0 / n, **kw), None, 0, 1, f"config 2: structured P1 Laplace fwd+adjoint (CSR mode), Mesh({n},{n},1/{n}) per GPU", "weak"
         part = adist.structured_slab(n, n * world, 1.0 / n, rank, world, **kw)
         return part.mesh, part, 0, 1, f"config 2: structured P1 Laplace fwd+adjoint (CSR mode), Mesh({n},{n},1/{n}) per GPU", "weak"
+    if case == "2m":
+        # config 2's connectivity on mapped + jittered node positions: what one moved node does to the structured fast path (index-free kernels
+        # with positions from the coordinate array instead of the general tile kernels)
+        import numpy as np
+        n = size or max(4, int(4096 * scale))
+        coords, elems = meshgen.tri_grid(n, n, 1.0 / n)
+        rng = np.random.default_rng(3)
+        coords = np.stack([coords[:, 0] + 0.02 * np.sin(3.0 * coords[:, 1]), coords[:, 1] + 0.02 * np.cos(2.0 * coords[:, 0])], 1) + rng.uniform(-0.2 / n, 0.2 / n, coords.shape)
+        note = f"config 2 connectivity, Mesh({n},{n},1/{n}), on mapped + jittered node positions (structured kernels, positions from the coordinate array)"
+        return A.Mesh(coords, elems, **kw), None, 0, 1, note, "weak"
     if case == "3":
         m, nl = max(4, int(4096 * scale)), max(2, int(2048 * scale))
         note = f"config 3: P1 linear elasticity, per-Gauss-point 3x3 tangent H, Mesh({m},{nl},1/{m}) per GPU ({2 * m * nl} triangles)"
@@ -395,7 +410,9 @@ def time_steps(step, K, warmup, world, sampler=None):
     returns (ms per step = max over ranks, forward ms, adjoint ms, wait-for-exchange ms) — the last three averaged on this rank."""
     import torch
     import torch.distributed as dist
-    for _ in range(warmup):
+    if sampler is not None:
+        sampler.armed = True
+    for _ in range(max(warmup, 50 if sampler is not None else 0)):      # the headline run warms up for at least 50 steps so that the clock sampler sees the load
         step()
     step.join()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
@@ -404,7 +421,7 @@ def time_steps(step, K, warmup, world, sampler=None):
         dist.barrier()
     torch.cuda.synchronize()
     if sampler is not None:
-        sampler.armed = True
+        sampler.timed = True
     ev_begin.record()
     for i in range(K):
         step(ev[i])
@@ -412,7 +429,7 @@ def time_steps(step, K, warmup, world, sampler=None):
     ev_end.record()
     torch.cuda.synchronize()
     if sampler is not None:
-        sampler.armed = False
+        sampler.armed = sampler.timed = False
     if world > 1:
         dist.barrier()
     total_ms = ev_begin.elapsed_time(ev_end)
@@ -447,6 +464,8 @@ def case_records(case, rank, world, steps, warmup, scale, peak, traffic, library
         xa_ms = step.exchange_alone_ms()
         E = mesh.nelem
         b = alg_bytes_per_elem(mesh, step.nnz, cpg)
+        if case == "2m":
+            b -= 4 * mesh.elem_ndof        # structured connectivity is index arithmetic: coordinates (8 B), coefficients (24 B) and values (28 B) per element are what moves
         cnt = torch.tensor([float(E), float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0, b * E], dtype=torch.float64, device="cuda")
         mx = torch.tensor([float(E)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -483,7 +502,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", choices=["2", "3", "4", "4l", "4m", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
-    ap.add_argument("--extra-configs", default="3,4,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
+    ap.add_argument("--extra-configs", default="2m,3,4,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
     ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the edge counts of configs 3-5 (smoke runs)")
     ap.add_argument("--numbering", default="random", choices=["random", "generator"], help="config 4: node / element numbering of the synthetic unstructured mesh")
@@ -610,7 +629,7 @@ def main():
     nnode = mesh.nnode
     b_general = alg_bytes_per_elem(mesh, nnz, cpg)
     ibytes = float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0
-    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m"))]
+    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m")) and not (c == "2m" and world > 1)]
     if xc:
         del step, part, mesh
         torch.cuda.empty_cache()
@@ -664,12 +683,13 @@ def main():
                          f"{ne_cpu} triangles (a row slab of the config-2 mesh), best of 3, {threads} host threads over element blocks",
                "single_thread_value": ne_cpu / min(single) / 1e6,
                "single_thread_note": "the reference op as it is (no threading), same sample, one pass"}
-    launches = {"2": 2, "2g": 2, "3": 2, "4": 2, "4l": 2, "4m": 2, "5": 3}[key] + (4 if world > 1 else 0)
+    launches = {"2": 2, "2g": 2, "2m": 2, "3": 2, "4": 2, "4l": 2, "4m": 2, "5": 3}[key] + (4 if world > 1 else 0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": note, "elements_per_gpu": E, "nodes_per_gpu": nnode, "nnz_per_gpu": nnz, "gauss_points_per_gpu": G,
                        "l2_policy": "inputs larger than L2 (coefficients %.2f GB, values %.2f GB per pass; no flush needed)" % (8 * G * cpg / 1e9, 8 * nnz / 1e9),
                        "setup_s_untimed": round(t_setup, 1), "numa_node_rank0": numa, "numa_note": numa_why,
+                       "untimed_steps_before_timing": max(args.warmup, 50),
                        "path": "structured triangulation kernels (tri_grid.cuh): no mesh-static index data" if structured else "default kernels of this config",
                        "plan_bytes_per_elem": 0.0 if structured else plan_bytes,
                        "parallelism": ("element blocks; interface rows: " + str(headline_exchange) + " on a high-priority side stream (reduce(vals) overlaps the adjoint "

@@ -23,6 +23,16 @@ def rectilinear(m, n, seed):
     return c, e
 
 
+def mapped(m, n, seed):
+    """Mesh(m, n, h) connectivity on a smoothly mapped AND jittered grid: no two nodes share an abscissa or ordinate, every triangle keeps its
+    orientation (jitter below a quarter of the local spacing)."""
+    rng = np.random.default_rng(seed)
+    c, e = rectilinear(m, n, seed)
+    x, y = c[:, 0].copy(), c[:, 1].copy()
+    c = np.stack([x + 0.08 * np.sin(0.7 * y), y + 0.06 * np.cos(0.9 * x)], 1) + rng.uniform(-0.1, 0.1, c.shape)
+    return c, e
+
+
 GRIDS = [(1, 1), (2, 1), (1, 3), (5, 4), (31, 2), (32, 3), (63, 5), (70, 33)]
 
 
@@ -39,8 +49,10 @@ def test_not_structured():
     c, e = meshgen.tri_grid(6, 5, 0.1, version=2)                # other diagonal
     assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
     c, e = meshgen.tri_grid(6, 5, 0.1)
-    c2 = c.copy(); c2[9, 0] += 1e-13                             # one node off the rectilinear grid
-    assert _info(A.Mesh(c2, e, host_only=True), _lib.INFO_STRUCTURED) == 0
+    c2 = c.copy(); c2[9, 0] += 1e-13                             # one node off the rectilinear grid: structured connectivity, MAPPED coordinates (3)
+    assert _info(A.Mesh(c2, e, host_only=True), _lib.INFO_STRUCTURED) == 3
+    c3 = c.copy(); c3[9] = c3[9 + 7 + 1] + 0.01                   # a node pushed across its cell: a triangle flips, the orientation fix reorders it
+    assert _info(A.Mesh(c3, e, host_only=True), _lib.INFO_STRUCTURED) == 0
     assert _info(A.Mesh(c, e[::-1].copy(), host_only=True), _lib.INFO_STRUCTURED) == 0      # renumbered elements
     assert _info(A.Mesh(c, e, degree=2, host_only=True), _lib.INFO_STRUCTURED) == 0          # P2
     c, e = meshgen.jitter_unstructured(6, 5, 0.1)
@@ -78,15 +90,26 @@ def _close(a, b, rel=1e-12):
     assert err.max() <= rel, f"max rel err {err.max():.3e} at {err.argmax()}"
 
 
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 4), (70, 33)])
+def test_mapped_grid_detection(m, n):
+    """structured connectivity on mapped / jittered node positions: recognised as kind 3 (scalar CSR operators take the index-free kernels with
+    positions from the coordinate array), the closed-form row pointers still validate"""
+    c, e = mapped(m, n, 5)
+    M = A.Mesh(c, e, host_only=True)
+    assert _info(M, _lib.INFO_STRUCTURED) == 3
+    M.csr_pattern(1)
+    assert _info(M, _lib.INFO_STRUCTURED) == 3
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear", "mapped"])
 @pytest.mark.parametrize("m,n", GRIDS)
 def test_structured_parity(oracle, m, n, kind):
     import torch
     from adfem_jl_b200 import ops
-    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else rectilinear(m, n, 2)
+    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else (rectilinear(m, n, 2) if kind == "rectilinear" else mapped(m, n, 3))
     M, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
-    assert _info(M, _lib.INFO_STRUCTURED) == 1
+    assert _info(M, _lib.INFO_STRUCTURED) == (3 if kind == "mapped" else 1)
     rng = np.random.default_rng(7)
     coef = rng.random(o.ngauss) + 0.5
     rowptr, colind = M.csr_pattern(1)
@@ -150,13 +173,14 @@ def test_structured_large_properties():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["rectilinear", "mapped"])
 @pytest.mark.parametrize("m,n", [(1, 1), (5, 4), (63, 5), (70, 33)])
-def test_structured_host_buffer_pipeline(m, n):
+def test_structured_host_buffer_pipeline(m, n, kind):
     """adfem_assemble_csr_host / _adjoint_host on a structured mesh stream node-row chunks through three CUDA streams; any chunking
     must give exactly the device-pointer result."""
     import torch
     from adfem_jl_b200 import ops
-    c, e = rectilinear(m, n, 3)
+    c, e = rectilinear(m, n, 3) if kind == "rectilinear" else mapped(m, n, 3)
     M = A.Mesh(c, e)
     L = _lib.lib()
     rng = np.random.default_rng(11)
@@ -178,13 +202,14 @@ def test_structured_host_buffer_pipeline(m, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear", "mapped"])
 @pytest.mark.parametrize("m,n", GRIDS)
 def test_structured_source_term(oracle, m, n, kind):
-    """compute_fem_source_term1 and its adjoint on the structured path vs the oracle and vs the general kernels."""
+    """compute_fem_source_term1 and its adjoint on the structured path vs the oracle and vs the general kernels (mapped grids: the source
+    term has no index-free kernel, both settings run the general one)."""
     import torch
     from adfem_jl_b200 import ops
-    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else rectilinear(m, n, 4)
+    c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else (rectilinear(m, n, 4) if kind == "rectilinear" else mapped(m, n, 4))
     M, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
     rng = np.random.default_rng(13)
     f, gr = rng.standard_normal(o.ngauss), rng.standard_normal(o.ndof)
