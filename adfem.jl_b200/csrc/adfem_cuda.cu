@@ -570,7 +570,8 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
     if (!m->tet_const_ready) {
       TetNodeConst C; build_tet_node_const(m->tet_tab, C);
       CU_TRY(cudaMemcpyToSymbol(c_tn, &C, sizeof(C)));
-      CU_TRY(cudaFuncSetAttribute(k_tet_node_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+      CU_TRY(cudaFuncSetAttribute(k_tet_node_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+      CU_TRY(cudaFuncSetAttribute(k_tet_node_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES2));
       std::vector<double> spc;
       for (int inv = 1; inv >= 0; inv--)
         for (int a = 0; a < 3; a++)
@@ -606,7 +607,8 @@ int launch_tet_grid_fwd(adfem_mesh* m, const double* coef, double* vals, cudaStr
       const long long node0 = plane * z0, node1 = (c + 1 == nchunk) ? (long long)m->hm.nv : plane * z1;
       // (measured and dropped, gpurun r2i: one CTA per parity — 3 warps, no barrier between the 32- and the 8-tetrahedron warps — 5.55 -> 6.79 ms at
       // 10.5 M tetrahedra, 6.03 ms as two launches: the two parities of a span share their tangent blocks through L1)
-      k_tet_node_fwd<<<blocks_for(node1 - node0, TN_NODES), TN_THREADS, TN_SMEM_BYTES, s2>>>(gt, sp, m->pat.nnz, node0, node1, m->d_rowptr.p, m->presum_buf.p, vals);
+      if (m->opt_tet_node == 2) k_tet_node_fwd<2><<<blocks_for(node1 - node0, TN_NODES), 9 * 32, TN_SMEM_BYTES2, s2>>>(gt, sp, m->pat.nnz, node0, node1, m->d_rowptr.p, m->presum_buf.p, vals);
+      else k_tet_node_fwd<1><<<blocks_for(node1 - node0, TN_NODES), 6 * 32, TN_SMEM_BYTES, s2>>>(gt, sp, m->pat.nnz, node0, node1, m->d_rowptr.p, m->presum_buf.p, vals);
     }
     if (nchunk > 1) { CU_TRY(cudaEventRecord(m->tet_events[33], s2)); CU_TRY(cudaStreamWaitEvent(st, m->tet_events[33], 0)); }
     CU_TRY(cudaGetLastError());
@@ -804,7 +806,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
-  else if (k == "tet_node") m->opt_tet_node = value != 0;
+  else if (k == "tet_node") m->opt_tet_node = (int)value;
   else if (k == "tet_chunks") m->opt_tet_chunks = (int)value;
   else if (k == "tet_adj_blocks") m->opt_tet_adj_blocks = (int)value;
   else if (k == "structured_tet_scalar") m->opt_tet_scalar = value != 0;

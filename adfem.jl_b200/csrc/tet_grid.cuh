@@ -111,8 +111,11 @@ ADFEM_HD void tg_store_rows(int lane, long long rs, int len, long long nnz, cons
 }
 
 // ---- adjoint ----------------------------------------------------------------------------------------------------------------------
-constexpr int TG_ADJ_LD = 37;                     // odd leading dimension: the 32 lanes' stores of entry c hit 16 distinct 64-bit banks
-constexpr int TG_ADJ_WARP_DOUBLES = 32 * TG_ADJ_LD + 1;
+// leading dimension of the per-warp gradient staging: 38 doubles = 19 16-byte units (odd), so that BOTH phases move 16-byte pairs without bank
+// conflicts — the lanes' pair stores of phase 1 (lane stride 19 units) and the consecutive-pair loads of phase 2.  The kernel runs at 94 % of the
+// L1 data-pipe wavefront peak (profiles/ncu_r02_cfg5_v3.md: 8-byte accesses with a leading dimension of 37 took a quarter of it).
+constexpr int TG_ADJ_LD = 38;
+constexpr int TG_ADJ_WARP_DOUBLES = 32 * TG_ADJ_LD;
 struct alignas(16) TgPair { double x, y; };
 constexpr int TG_ADJ_WARPS = 4;
 
@@ -184,10 +187,12 @@ ADFEM_HD void tg_tet_adjoint(int lane, const GridTet& gt, long long e0, long lon
     for (int i = 0; i < 3; i++) {
       const int r = ROW[a][i];
       const bool first = (r < 3) || (a == 0) || (a == 1 && r == 3);      // rows 3, 4, 5 are first written by components 1, 0, 0
+      TgPair* o2 = reinterpret_cast<TgPair*>(out + 6 * r);          // 16-byte aligned: lane * 38 + 6 r is even
 #pragma unroll
-      for (int c = 0; c < 6; c++) {
-        if (first) out[6 * r + c] = acc[i][c] * ws;
-        else out[6 * r + c] += acc[i][c] * ws;
+      for (int c = 0; c < 3; c++) {
+        TgPair v{acc[i][2 * c] * ws, acc[i][2 * c + 1] * ws};
+        if (!first) { const TgPair w = o2[c]; v.x += w.x; v.y += w.y; }
+        o2[c] = v;
       }
     }
   }
@@ -211,7 +216,10 @@ ADFEM_HD void tg_store_grad(int lane, const QuadRule& rule, int g, long long e0,
     for (int tt = 0; tt < 8; tt++) {
       const double* s4 = st + tt * 4 * TG_ADJ_LD;
 #pragma unroll
-      for (int j = 0; j < 9; j++) o2[(tt * 9 + j) * 32] = TgPair{s4[off[j]] * w[j], s4[off[j] + 1] * w[j]};
+      for (int j = 0; j < 9; j++) {
+        const TgPair v = *reinterpret_cast<const TgPair*>(s4 + off[j]);      // t * 38 + 2 c2: 16-byte aligned
+        o2[(tt * 9 + j) * 32] = TgPair{v.x * w[j], v.y * w[j]};
+      }
     }
     return;
   }

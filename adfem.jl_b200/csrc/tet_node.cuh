@@ -174,16 +174,16 @@ static __global__ void __launch_bounds__(TPX_THREADS) k_tet_presum_xg(int n, int
 constexpr int TN_NODES = 64, TN_THREADS = 192;
 constexpr int TN_SLOT = 97;                                                  // 3 x 32 accumulators per slot + 1: the store phase walks the slots (odd stride: no bank conflicts)
 constexpr int TN_ACC1 = 19 * TN_SLOT, TN_ACC0 = 7 * TN_SLOT;                  // doubles per warp of the 19-slot / 7-slot parity
-constexpr int TN_SMEM_BYTES = (3 * TN_ACC1 + 3 * TN_ACC0) * 8;
+constexpr int TN_SMEM_BYTES = (3 * TN_ACC1 + 3 * TN_ACC0) * 8, TN_SMEM_BYTES2 = (6 * TN_ACC1 + 3 * TN_ACC0) * 8;
 
 template <int B>
 __device__ __forceinline__ void tn_accumulate(const GridTet& gt, const TetSpacing& sp, int par, bool valid, int i, int j, int k, int lane,
-                                              const double* __restrict__ hx, double* __restrict__ acc) {
+                                              const double* __restrict__ hx, double* __restrict__ acc, int t0 = 0, int t1 = 64) {
   // columns of the tangent that component B of a strain-displacement column touches (device_fem.cuh bdot<3>)
   constexpr int COL[3][3] = {{0, 4, 5}, {1, 3, 5}, {2, 3, 4}};
   const int n = gt.n, l = gt.l, half = tn_half(n), nblk = tn_nblk(n);
-  const int ninc = c_tn.ninc[par];
-  for (int t = 0; t < ninc; t++) {
+  const int ninc = min(c_tn.ninc[par], t1);
+  for (int t = t0; t < ninc; t++) {
     const int ci = i + c_tn.inc[par][t][0], cj = j + c_tn.inc[par][t][1], ck = k + c_tn.inc[par][t][2];
     if (!valid || ci < 0 || ci >= n || cj < 0 || cj >= n || ck < 0 || ck >= l) continue;
     const double ihx = __ldg(sp.ihx + ci), ihy = __ldg(sp.ihy + cj), ihz = __ldg(sp.ihz + ck);
@@ -252,14 +252,21 @@ __device__ __forceinline__ void tn_accumulate(const GridTet& gt, const TetSpacin
   }
 }
 
-// nodes [node0, node1) (flat ids; whole node planes when the forward runs in z-chunks on two streams)
-static __global__ void __launch_bounds__(TN_THREADS, 3) k_tet_node_fwd(GridTet gt, TetSpacing sp, long long nnz, long long node0, long long node1,
+// nodes [node0, node1) (flat ids; whole node planes when the forward runs in z-chunks on two streams).
+// HS = warps per column component of the 32-tetrahedron parity.  HS = 1 (first version, 6 warps): its three warps walk all 32 incident tetrahedra while
+// the three warps of the 8-tetrahedron parity wait at the barrier three quarters of the time (profiles/ncu_r02_cfg5_v3.md: 32 % of the warp
+// samples).  HS = 2 (9 warps): warps 0-2 take tetrahedra [0, 16), warps 3-5 tetrahedra [16, 32) of the same nodes into accumulators of their own,
+// summed when the rows are stored; the longest warp then runs 16 iterations instead of 32 (105 KB of accumulators, two CTAs per SM).
+template <int HS>
+static __global__ void __launch_bounds__((3 * HS + 3) * 32, HS == 1 ? 3 : 2) k_tet_node_fwd(GridTet gt, TetSpacing sp, long long nnz, long long node0, long long node1,
                                                                        const long long* __restrict__ rowptr, const double* __restrict__ hx, double* __restrict__ vals) {
+  constexpr int NTH = (3 * HS + 3) * 32, HW = 3 * HS;              // threads, warps of the heavy parity
   extern __shared__ __align__(16) double tn_acc[];
   __shared__ long long s_rs[TN_NODES];
   __shared__ int s_mask[TN_NODES], s_src[TN_NODES];
   __shared__ unsigned char s_slot27[2][19];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, heavy = c_tn.heavy, par = warp < 3 ? heavy : 1 - heavy, b = warp < 3 ? warp : warp - 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, heavy = c_tn.heavy, par = warp < HW ? heavy : 1 - heavy;
+  const int b = warp < HW ? warp % 3 : warp - HW, part = warp < HW ? warp / 3 : 0;
   const long long n1 = gt.n + 1, nn = node1, f0 = node0 + (long long)blockIdx.x * TN_NODES;
   // the lane's node: the one of the flat pair (f0 + 2*lane, f0 + 2*lane + 1) whose index parity (i + j + k) & 1 is `par`
   long long f = f0 + 2 * lane;
@@ -269,11 +276,11 @@ static __global__ void __launch_bounds__(TN_THREADS, 3) k_tet_node_fwd(GridTet g
   }
   const bool valid = f < nn;
   const int i = (int)(f % n1), j = (int)((f / n1) % n1), k = (int)(f / (n1 * n1));
-  double* acc = tn_acc + (warp < 3 ? b * TN_ACC1 : 3 * TN_ACC1 + b * TN_ACC0);
-  const int nslot = warp < 3 ? 19 : 7;
+  double* acc = tn_acc + (warp < HW ? warp * TN_ACC1 : HW * TN_ACC1 + b * TN_ACC0);
+  const int nslot = warp < HW ? 19 : 7;
   if (tid < 38) s_slot27[tid / 19][tid % 19] = c_tn.slot27[tid / 19][tid % 19];
   for (int s = 0; s < nslot; s++) { acc[s * TN_SLOT + lane] = 0.0; acc[s * TN_SLOT + 32 + lane] = 0.0; acc[s * TN_SLOT + 64 + lane] = 0.0; }
-  if (b == 0) {
+  if (b == 0 && part == 0) {
     const int fpos = (int)(f - f0);
     int mask = 0;
     if (valid) {      // structurally present for the parity and inside the grid (27-neighbourhood id = (dk+1)*9 + (dj+1)*3 + (di+1))
@@ -283,22 +290,28 @@ static __global__ void __launch_bounds__(TN_THREADS, 3) k_tet_node_fwd(GridTet g
     }
     s_mask[fpos] = mask; s_src[fpos] = par * 32 + lane; s_rs[fpos] = valid ? rowptr[f] : 0;
   }
-  if (b == 0) tn_accumulate<0>(gt, sp, par, valid, i, j, k, lane, hx, acc);
-  else if (b == 1) tn_accumulate<1>(gt, sp, par, valid, i, j, k, lane, hx, acc);
-  else tn_accumulate<2>(gt, sp, par, valid, i, j, k, lane, hx, acc);
+  // tetrahedra of this warp: the heavy parity's incidence list is cut into HS ascending pieces
+  const int per = (c_tn.ninc[heavy] + HS - 1) / HS, t0 = warp < HW ? part * per : 0, t1 = warp < HW ? t0 + per : 64;
+  if (b == 0) tn_accumulate<0>(gt, sp, par, valid, i, j, k, lane, hx, acc, t0, t1);
+  else if (b == 1) tn_accumulate<1>(gt, sp, par, valid, i, j, k, lane, hx, acc, t0, t1);
+  else tn_accumulate<2>(gt, sp, par, valid, i, j, k, lane, hx, acc, t0, t1);
   __syncthreads();
   // store: item (node position nd, column component bb, compact slot cs); the three row components a share the lookups
-  for (int idx = tid; idx < TN_NODES * 57; idx += TN_THREADS) {
+  for (int idx = tid; idx < TN_NODES * 57; idx += NTH) {
     const int nd = idx / 57, r = idx - 57 * nd, bb = r / 19, cs = r - 19 * bb;
     const int mask = s_mask[nd], src = s_src[nd], pn = src >> 5, ln = src & 31;
     if (cs >= (pn == heavy ? 19 : 7)) continue;
     const int s27 = s_slot27[pn][cs];
     if (!((mask >> s27) & 1)) continue;
     const int len = __popc((unsigned)mask), jpos = __popc((unsigned)(mask & ((1 << s27) - 1)));
-    const double* a0 = tn_acc + (pn == heavy ? bb * TN_ACC1 : 3 * TN_ACC1 + bb * TN_ACC0) + cs * TN_SLOT + ln;
+    const double* a0 = tn_acc + (pn == heavy ? bb * TN_ACC1 : HW * TN_ACC1 + bb * TN_ACC0) + cs * TN_SLOT + ln;
     double* out = vals + 3 * s_rs[nd] + bb * len + jpos;
 #pragma unroll
-    for (int a = 0; a < 3; a++) out[3 * (long long)a * nnz] = a0[a * 32];
+    for (int a = 0; a < 3; a++) {
+      double v = a0[a * 32];
+      if (HS == 2 && pn == heavy) v += a0[3 * TN_ACC1 + a * 32];      // second piece of the incidence list (ascending element order inside each piece)
+      out[3 * (long long)a * nnz] = v;
+    }
   }
 }
 #endif

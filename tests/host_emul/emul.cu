@@ -331,7 +331,7 @@ int emul_tet_grid_elast_adj(int n, int l, const double* xs, const double* ys, co
   QuadRule rule;
   if (!tetrahedron_rule(order, rule)) return 1;
   const GridTet gt{n, l, xs, ys, zs, &tab};
-  static double smem[TG_ADJ_WARP_DOUBLES];
+  alignas(16) static double smem[TG_ADJ_WARP_DOUBLES];
   const long long ne = 5LL * n * n * l;
   for (long long e0 = 0; e0 < ne; e0 += 32) {
     for (int c = 0; c < TG_ADJ_WARP_DOUBLES; c++) smem[c] = -7.0e300;

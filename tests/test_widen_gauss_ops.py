@@ -355,7 +355,8 @@ def test_structured_scatter_operators(oracle):
         close(a, b, rel=1e-13)       # same summation order and geometry; only the compiler's FMA contraction may differ between the two kernels
 
 
-@pytest.mark.parametrize("n,l,chunks,node", [(3, 2, 1, 1), (5, 4, 1, 1), (1, 1, 1, 1), (5, 6, 3, 1), (70, 5, 5, 1), (4, 4, 1, 0), (33, 34, 0, 1)])
+@pytest.mark.parametrize("n,l,chunks,node", [(3, 2, 1, 1), (5, 4, 1, 1), (1, 1, 1, 1), (5, 6, 3, 1), (70, 5, 5, 1), (4, 4, 1, 0), (33, 34, 0, 1),
+                                             (3, 2, 1, 2), (5, 4, 1, 2), (1, 1, 1, 2), (5, 6, 3, 2), (70, 5, 1, 2), (33, 34, 0, 2)])
 def test_structured_tet_elasticity_forward(oracle, n, l, chunks, node):
     """Option "structured_elasticity" on Mesh3(n, n, l, h): Gauss-sum pre-pass + one warp per node for the forward, one warp per 32 tetrahedra
     for the adjoint (csrc/tet_grid.cuh); against the oracle and the general tile kernels."""
@@ -370,7 +371,7 @@ def test_structured_tet_elasticity_forward(oracle, n, l, chunks, node):
     dv = rng.standard_normal(len(ref))
     expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N3))
     m.set_option("tet_chunks", chunks)      # > 1: Gauss pre-sum and node kernel pipelined over z-chunks on two streams (0 = automatic)
-    m.set_option("tet_node", node)          # 0: first-generation one-warp-per-node forward
+    m.set_option("tet_node", node)          # 0: first-generation one-warp-per-node forward; 2: incidence list of the 32-tetrahedron parity split over two warps
     for on in ((1, 0) if n < 30 else (1,)):
         m.set_option("structured_elasticity", on)
         k = dev(H).requires_grad_(True)
