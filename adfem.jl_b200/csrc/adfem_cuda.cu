@@ -93,7 +93,8 @@ struct adfem_mesh {
   bool grid_mapped = false;                 // structured connectivity, non-rectilinear node positions: scalar CSR kernels only (MAPPED)
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
-  int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh)
+  int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh),
+                                            // 2 = as 1 with the 32-tetrahedron incidence list split over two warps (measured: 5.55 -> 5.75 ms at 10.5 M tetrahedra, no gain)
   int opt_tet_adj_blocks = 3;               // resident CTAs per SM the tetrahedral adjoint kernel is compiled for (register cap 168 / 128 / 96): measured 3.77 / 3.87 / 4.75 ms at 10.5 M tetrahedra
   int opt_tet_chunks = 0;                   // z-chunks of the two-stream forward pipeline (0 or 1 = off: measured no gain)
   cudaStream_t tet_side_stream = nullptr;
