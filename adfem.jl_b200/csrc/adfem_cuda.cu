@@ -486,7 +486,7 @@ int ensure_host_streams(adfem_mesh* m) {
   return 0;
 }
 
-bool use_grid_any(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }      // scalar CSR operators: rectilinear or mapped
+bool use_grid_any(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }      // scalar CSR operators and source term: rectilinear or mapped
 bool use_grid(adfem_mesh* m) { return use_grid_any(m) && !m->grid_mapped; }                        // everything else: rectilinear only
 
 int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
@@ -669,8 +669,11 @@ int launch_grid_source(adfem_mesh* m, bool adjoint, const double* in, double* ou
   const int strips = adjoint ? (gt.m + GRID_STRIP - 1) / GRID_STRIP : (gt.m + 1 + GRID_STRIP - 1) / GRID_STRIP;
   const int H = grid_rows_per_warp(m, strips, rows), chunks = (rows + H - 1) / H;
   const unsigned blocks = (unsigned)(((long long)strips * chunks + GRID_WARPS - 1) / GRID_WARPS);
-  if (adjoint) k_grid_source_adj<<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
-  else k_grid_source_fwd<<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+  if (m->grid_mapped) {
+    if (adjoint) k_grid_source_adj<true><<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+    else k_grid_source_fwd<true><<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+  } else if (adjoint) k_grid_source_adj<false><<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
+  else k_grid_source_fwd<false><<<blocks, GRID_WARPS * 32, 0, st>>>(dev_mesh(m, m->opt_area_coo), gt, 0, rows, H, in, out);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -1067,7 +1070,7 @@ int adfem_source(adfem_mesh* m, const double* f, double* rhs, void* stream) {
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_grid(m)) return launch_grid_source(m, false, f, rhs, st);
+  if (use_grid_any(m)) return launch_grid_source(m, false, f, rhs, st);
 #define CALL_SRC(DIM, DEG) \
   k_source_fwd<DIM, DEG><<<blocks_for(m->hm.ndof, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), m->d_adj_ptr.p, m->d_adj_elem.p, m->d_adj_loc.p, f, rhs)
   DISPATCH_ELEM(m, CALL_SRC);
@@ -1080,7 +1083,7 @@ int adfem_source_adjoint(adfem_mesh* m, const double* grad_rhs, double* grad_f, 
   if (int rc = need_device(m)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (m->grid_ok) { if (int rc = ensure_pattern(m)) return rc; }
-  if (use_grid(m)) return launch_grid_source(m, true, grad_rhs, grad_f, st);
+  if (use_grid_any(m)) return launch_grid_source(m, true, grad_rhs, grad_f, st);
 #define CALL_SRCB(DIM, DEG) k_source_bwd<DIM, DEG><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(dev_mesh(m, m->opt_area_coo), grad_rhs, grad_f)
   DISPATCH_ELEM(m, CALL_SRCB);
 #undef CALL_SRCB

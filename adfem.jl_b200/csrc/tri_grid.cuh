@@ -359,8 +359,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, MINB) k_grid_adj(DevMesh m, G
 
 // ---- source term on the structured triangulation (FemSourceScalar_forward/_backward, deps/MFEM/FemSource1/FemSourceScalar.h:4-32) -------------
 // per-vertex load integrals of both triangles of a VALID cell: v[r] = sum_k f_k lambda_r(x_k) w_k
-__device__ __forceinline__ void grid_cell_loads(const DevMesh& m, double x0, double x1, double y0, double y1, const double f[6], double T0[3], double T1[3]) {
-  const double2 BL = make_double2(x0, y0), BR = make_double2(x1, y0), TL = make_double2(x0, y1), TR = make_double2(x1, y1);
+__device__ __forceinline__ void grid_cell_loads_pts(const DevMesh& m, double2 BL, double2 BR, double2 TL, double2 TR, const double f[6], double T0[3], double T1[3]) {
   Geom<2> G0, G1;
   geom_tri(BL, BR, TL, m.heron, G0);
   geom_tri(TL, BR, TR, m.heron, G1);
@@ -374,9 +373,13 @@ __device__ __forceinline__ void grid_cell_loads(const DevMesh& m, double x0, dou
     for (int r = 0; r < 3; r++) { T0[r] += L[r] * w0; T1[r] += L[r] * w1; }
   }
 }
+__device__ __forceinline__ void grid_cell_loads(const DevMesh& m, double x0, double x1, double y0, double y1, const double f[6], double T0[3], double T1[3]) {
+  grid_cell_loads_pts(m, make_double2(x0, y0), make_double2(x1, y0), make_double2(x0, y1), make_double2(x1, y1), f, T0, T1);
+}
 
 // rhs[node] for node rows [r0, r1): lane l owns cell column / node column j0-1+l as in k_grid_fwd; one value per node, so
 // consecutive lanes write consecutive addresses and no transpose is needed
+template <bool MAPPED = false>
 __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp, const double* __restrict__ f,
                                                                      double* __restrict__ rhs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -387,7 +390,14 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, 
   const int j0 = strip * GRID_STRIP, cj = j0 - 1 + lane;
   const int i0 = r0 + chunk * rows_per_warp, i1 = min(i0 + rows_per_warp, r1);
   const bool colok = cj >= 0 && cj < gt.m, has_node = lane >= 1 && cj <= gt.m;
-  const double x0 = colok ? __ldg(gt.xs + cj) : 0.0, x1 = colok ? __ldg(gt.xs + cj + 1) : 1.0;
+  const double x0 = (!MAPPED && colok) ? __ldg(gt.xs + cj) : 0.0, x1 = (!MAPPED && colok) ? __ldg(gt.xs + cj + 1) : 1.0;
+  auto points = [&](int r, double2& a, double2& b) {                 // MAPPED: positions of nodes (r, cj) and (r, cj + 1)
+    if (colok && r >= 0 && r <= gt.n) {
+      const double2* p = reinterpret_cast<const double2*>(m.coords) + ((size_t)r * (gt.m + 1) + cj);
+      a = __ldg(p); b = __ldg(p + 1);
+    }
+  };
+  double2 qb0 = make_double2(0.0, 0.0), qb1 = make_double2(1.0, 0.0), qt0 = make_double2(0.0, 1.0), qt1 = make_double2(1.0, 1.0);
   const size_t kstride = (size_t)6 * gt.m;
   const double* kcol = f + 6 * (size_t)max(cj, 0);
   auto load = [&](int ci, double k[6]) {
@@ -402,18 +412,30 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, 
   for (int s = 0; s < 6; s++) kA[s] = kB[s] = kC[s] = 0.0;
 #pragma unroll
   for (int s = 0; s < 3; s++) pT0[s] = pT1[s] = 0.0;
-  double ya = __ldg(gt.ys + i0), yb = __ldg(gt.ys + min(i0 + 1, gt.n));
+  double ya = 0.0, yb = 1.0;
+  if constexpr (!MAPPED) { ya = __ldg(gt.ys + i0); yb = __ldg(gt.ys + min(i0 + 1, gt.n)); }
+  else { points(i0, qb0, qb1); points(min(i0 + 1, gt.n), qt0, qt1); }
   if (i0 > 0) {
     load(i0 - 1, kC);
-    if (colok) grid_cell_loads(m, x0, x1, __ldg(gt.ys + i0 - 1), ya, kC, pT0, pT1);
+    if constexpr (!MAPPED) { if (colok) grid_cell_loads(m, x0, x1, __ldg(gt.ys + i0 - 1), ya, kC, pT0, pT1); }
+    else {
+      double2 qm0 = qb0, qm1 = qb1;
+      points(i0 - 1, qm0, qm1);
+      if (colok) grid_cell_loads_pts(m, qm0, qm1, qb0, qb1, kC, pT0, pT1);
+    }
   }
   load(i0, kA);
   if (i0 + 1 < i1) load(i0 + 1, kB);
   auto row = [&](int i, const double kcur[6], double kfill[6]) {
     if (i + 2 < i1) load(i + 2, kfill);
-    const double yc = __ldg(gt.ys + min(i + 2, gt.n));
-    if (colok && i < gt.n) grid_cell_loads(m, x0, x1, ya, yb, kcur, cT0, cT1);
-    else {
+    double yc = 0.0;
+    double2 qn0 = qt0, qn1 = qt1;
+    if constexpr (!MAPPED) yc = __ldg(gt.ys + min(i + 2, gt.n));
+    else points(min(i + 2, gt.n), qn0, qn1);
+    if (colok && i < gt.n) {
+      if constexpr (!MAPPED) grid_cell_loads(m, x0, x1, ya, yb, kcur, cT0, cT1);
+      else grid_cell_loads_pts(m, qb0, qb1, qt0, qt1, kcur, cT0, cT1);
+    } else {
 #pragma unroll
       for (int s = 0; s < 3; s++) cT0[s] = cT1[s] = 0.0;
     }
@@ -422,6 +444,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, 
     const double v = ((((l_p + pT0[2]) + pT1[0]) + l_c0) + l_c1) + cT0[0];
     if (has_node) rhs[(size_t)i * (gt.m + 1) + cj] = v;
     ya = yb; yb = yc;
+    if constexpr (MAPPED) { qb0 = qt0; qb1 = qt1; qt0 = qn0; qt1 = qn1; }
 #pragma unroll
     for (int s = 0; s < 3; s++) { pT0[s] = cT0[s]; pT1[s] = cT1[s]; }
   };
@@ -433,6 +456,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_fwd(DevMesh m, 
 }
 
 // grad_f[e*3 + k] = sum_r lambda_r(x_k) w_k grad_rhs[node_r] for cell rows [r0, r1): lane l owns node column = cell column j0+l (l < 31)
+template <bool MAPPED = false>
 __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_adj(DevMesh m, GridTri gt, int r0, int r1, int rows_per_warp, const double* __restrict__ grad_rhs,
                                                                      double* __restrict__ grad_f) {
   __shared__ double stage_all[GRID_WARPS][GRID_STRIP * 7];
@@ -445,21 +469,35 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_adj(DevMesh m, 
   const int c0 = r0 + chunk * rows_per_warp, c1 = min(c0 + rows_per_warp, r1);
   double* stage = stage_all[wib];
   const bool node_ok = j <= gt.m, cell_ok = lane < GRID_STRIP && j < gt.m;
-  const double x0 = cell_ok ? __ldg(gt.xs + j) : 0.0, x1 = cell_ok ? __ldg(gt.xs + j + 1) : 1.0;
+  const double x0 = (!MAPPED && cell_ok) ? __ldg(gt.xs + j) : 0.0, x1 = (!MAPPED && cell_ok) ? __ldg(gt.xs + j + 1) : 1.0;
+  auto points = [&](int r, double2& a, double2& b) {                 // MAPPED: positions of nodes (r, j) and (r, j + 1)
+    if (cell_ok && r >= 0 && r <= gt.n) {
+      const double2* p = reinterpret_cast<const double2*>(m.coords) + ((size_t)r * (gt.m + 1) + j);
+      a = __ldg(p); b = __ldg(p + 1);
+    }
+  };
+  double2 qb0 = make_double2(0.0, 0.0), qb1 = make_double2(1.0, 0.0), qt0 = make_double2(0.0, 1.0), qt1 = make_double2(1.0, 1.0);
   const int ncell6 = 6 * min(GRID_STRIP, gt.m - j0);
   auto node = [&](int i) { return (node_ok && i <= gt.n) ? __ldg(grad_rhs + (size_t)i * (gt.m + 1) + j) : 0.0; };
   double glo = node(c0), ghi = node(c0 + 1), gnx = node(c0 + 2);     // node rows ci, ci+1, ci+2 (one row ahead)
-  double ya = __ldg(gt.ys + c0), yb = __ldg(gt.ys + c0 + 1);
+  double ya = 0.0, yb = 1.0;
+  if constexpr (!MAPPED) { ya = __ldg(gt.ys + c0); yb = __ldg(gt.ys + c0 + 1); }
+  else { points(c0, qb0, qb1); points(c0 + 1, qt0, qt1); }
   double* out = grad_f + 6 * ((size_t)c0 * gt.m + j0) + lane;
   const size_t ostride = (size_t)6 * gt.m;
   for (int ci = c0; ci < c1; ci++, out += ostride) {
-    const double gn2 = node(ci + 3), yc = __ldg(gt.ys + min(ci + 2, gt.n));
+    const double gn2 = node(ci + 3);
+    double yc = 0.0;
+    double2 qn0 = qt0, qn1 = qt1;
+    if constexpr (!MAPPED) yc = __ldg(gt.ys + min(ci + 2, gt.n));
+    else points(min(ci + 2, gt.n), qn0, qn1);
     const double g_br = shfl_down1(glo), g_tr = shfl_down1(ghi);
     double gk[6];
 #pragma unroll
     for (int s = 0; s < 6; s++) gk[s] = 0.0;
     if (cell_ok) {
-      const double2 BL = make_double2(x0, ya), BR = make_double2(x1, ya), TL = make_double2(x0, yb), TR = make_double2(x1, yb);
+      const double2 BL = MAPPED ? qb0 : make_double2(x0, ya), BR = MAPPED ? qb1 : make_double2(x1, ya), TL = MAPPED ? qt0 : make_double2(x0, yb),
+                    TR = MAPPED ? qt1 : make_double2(x1, yb);
       Geom<2> G0, G1;
       geom_tri(BL, BR, TL, m.heron, G0);
       geom_tri(TL, BR, TR, m.heron, G1);
@@ -483,6 +521,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) k_grid_source_adj(DevMesh m, 
     for (int k = 0; k < 6; k++) { const int t = lane + 32 * k; if (t < ncell6) out[32 * k] = stage[(t / 6) * 7 + t % 6]; }
     glo = ghi; ghi = gnx; gnx = gn2;
     ya = yb; yb = yc;
+    if constexpr (MAPPED) { qb0 = qt0; qb1 = qt1; qt0 = qn0; qt1 = qn1; }
   }
 }
 

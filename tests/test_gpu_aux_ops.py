@@ -113,6 +113,48 @@ def test_dirichlet_bd_op(oracle, base, dup):
         A.fem_impose_Dirichlet_boundary_condition_experimental(Acoo, np.array([10 ** 6]), m, n, h)
 
 
+def test_edge_cases_empty_boundary_and_single_elements(oracle):
+    """Degenerate inputs the reference accepts: an empty boundary list (both Dirichlet ops return the matrix unchanged, in order), a
+    boundary list covering every dof, and meshes of a single triangle / a single tetrahedron through the CSR and COO paths."""
+    rng = np.random.default_rng(8)
+    c, e = meshgen.tri_grid(3, 2, 0.5)
+    o = oracle.Mesh2D(c, e)
+    ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+    rhs = rng.standard_normal(o.ndof)
+    none = np.zeros(0, dtype=np.int64)
+    B, r = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), dev(vv), o.ndof, o.ndof), dev(rhs), none, dev(np.zeros(0)))
+    assert np.array_equal(B.indices.cpu().numpy(), ind) and np.array_equal(B.values.cpu().numpy(), vv) and np.array_equal(r.cpu().numpy(), rhs)
+    allbd = np.arange(o.ndof)
+    bv = rng.standard_normal(o.ndof)
+    B, r = A.impose_Dirichlet_boundary_conditions(A.SparseTensor(dev(ind), dev(vv), o.ndof, o.ndof), dev(rhs), allbd, dev(bv))
+    oi, ov, orhs = oracle.impose_dirichlet_fwd(ind, vv, allbd, rhs, bv)
+    assert np.array_equal(B.indices.cpu().numpy(), oi) and np.array_equal(B.values.cpu().numpy(), ov) and np.array_equal(r.cpu().numpy(), orhs)
+    assert len(ov) == o.ndof and np.all(ov == 1.0)
+    ii, jj = ind[:, 0] + 1, ind[:, 1] + 1
+    Acoo = A.SparseTensor(dev(np.stack([ii, jj], 1)), dev(vv), 2 * 12 + 1, 2 * 12 + 1)
+    A1, A2 = A.fem_impose_Dirichlet_boundary_condition_experimental(Acoo, np.zeros(0, dtype=np.int32), 3, 2, 0.5)
+    assert np.array_equal(A1.indices.cpu().numpy(), np.stack([ii, jj], 1)) and np.array_equal(A1.values.cpu().numpy(), vv) and A2.values.numel() == 0
+    for dim, coords, elems in ((2, np.array([[0.0, 0.0], [1.0, 0.2], [0.3, 0.9]]), np.array([[0, 1, 2]])),
+                               (2, np.array([[0.0, 0.0], [1.0, 0.2], [0.3, 0.9]]), np.array([[1, 0, 2]])),          # negatively oriented: the fix swaps v0, v1
+                               (3, np.array([[0.0, 0.0, 0.0], [1.0, 0.1, 0.0], [0.2, 0.9, 0.1], [0.1, 0.2, 0.8]]), np.array([[0, 1, 2, 3]]))):
+        for degree in (1, 2):
+            m = (A.Mesh if dim == 2 else A.Mesh3)(coords, elems, degree=degree)
+            om = (oracle.Mesh2D if dim == 2 else oracle.Mesh3D)(coords, elems, degree=degree)
+            kap = rng.random(om.ngauss) + 0.5
+            ind1, vv1 = om.laplace_fwd(kap)
+            rp, ci, ref = oracle.canonical_csr(ind1, vv1, om.ndof)
+            kt = dev(kap).requires_grad_(True)
+            T = A.compute_fem_laplace_matrix1(kt, m, mode="csr")
+            assert np.array_equal(T.rowptr, rp) and np.array_equal(T.colind, ci)
+            close(T.values.detach().cpu().numpy(), ref)
+            dv = rng.standard_normal(len(ref))
+            (g,) = torch.autograd.grad(T.values, kt, dev(dv))
+            close(g.cpu().numpy(), om.laplace_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind1, om.ndof)))
+            S = A.compute_fem_laplace_matrix1(dev(kap), m, mode="coo")
+            assert np.array_equal(S.indices.cpu().numpy(), ind1)
+            close(S.values.cpu().numpy(), vv1)
+
+
 def test_impose_dirichlet_eager_matches_dense_julia_version():
     """test/mfem.jl:78-88: the op equals the dense slicing implementation (src/MFEM/MUtils.jl:184-199)."""
     rng = np.random.default_rng(1)

@@ -70,7 +70,7 @@ def test_coo_scalar_ops(oracle, name, degree):
         close(g.cpu().numpy(), bwd(gv))
 
 
-@pytest.mark.parametrize("name,degree", [c for c in CASES if not (c[0] == "tet" and c[1] == 2)])
+@pytest.mark.parametrize("name,degree", CASES)          # incl. P2 tetrahedra (3-D extension N2: 30 x 30 local matrix, 6 x 6 Voigt tangent)
 def test_coo_stiffness(oracle, name, degree):
     m, o = make(name, degree, oracle)
     ns = 3 if m.dim == 2 else 6
@@ -185,6 +185,16 @@ def test_csr_stiffness(oracle, name, degree):
     rng = np.random.default_rng(6)
     H = rng.random((o.ngauss, ns, ns))
     _csr_check(m, o, oracle, 2, H, o.stiffness_fwd, o.stiffness_bwd, m.dim, None)
+
+
+def test_csr_stiffness_p2_tets_is_refused_cleanly(oracle):
+    """P2 tetrahedral elasticity (a 30 x 30 local matrix per element; the reference has no 3-D elasticity operator at all, extension N2) works in
+    the COO-compatible mode (test_coo_stiffness[tet-2]); the CSR tile kernels cannot hold the elements of a single vertex row in shared memory, and
+    the library says so instead of producing anything."""
+    m, o = make("tet", 2, oracle)
+    H = np.random.default_rng(6).random((o.ngauss, 6, 6))
+    with pytest.raises(A.AdfemError, match="tile too large"):
+        ops.compute_fem_stiffness_matrix(dev(H), m, mode="csr")
 
 
 # ------------------------------------------------------------------------------------------ legacy symbols

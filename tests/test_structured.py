@@ -205,8 +205,7 @@ def test_structured_host_buffer_pipeline(m, n, kind):
 @pytest.mark.parametrize("kind", ["uniform", "rectilinear", "mapped"])
 @pytest.mark.parametrize("m,n", GRIDS)
 def test_structured_source_term(oracle, m, n, kind):
-    """compute_fem_source_term1 and its adjoint on the structured path vs the oracle and vs the general kernels (mapped grids: the source
-    term has no index-free kernel, both settings run the general one)."""
+    """compute_fem_source_term1 and its adjoint on the structured path (rectilinear and mapped grids) vs the oracle and vs the general kernels."""
     import torch
     from adfem_jl_b200 import ops
     c, e = meshgen.tri_grid(m, n, 0.37) if kind == "uniform" else (rectilinear(m, n, 4) if kind == "rectilinear" else mapped(m, n, 4))
