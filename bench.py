@@ -218,6 +218,7 @@ CASE_KERNELS = {          # (forward kernels, adjoint kernels) of the default pa
     "3": (["k_grid_elast_fwd<LAPLACE>"], ["k_grid_elast_adj<LAPLACE>"]),
     "4l": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
+    "4o": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4m": (["k_tile_fwd<2,2,MASS,0,1>"], ["k_tile_adj<2,2,MASS>"]),
     "5": (["k_tet_presum_xg<4>", "k_tet_node_fwd"], ["k_tet_grid_elast_adj<3>"]),
 }
@@ -252,22 +253,23 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
             return A.Mesh(m, nl, 1.0 / m, **kw), None, 2, 9, note, "weak"
         part = adist.structured_slab(m, nl * world, 1.0 / m, rank, world, **kw)
         return part.mesh, part, 2, 9, note, "weak"
-    if case in ("4", "4l", "4m"):
-        # the mesh is fixed (16 M triangles); N ranks take Morton-compact element blocks of it: "element-partitioned across 2/4/8 GPUs" = strong scaling
+    if case in ("4", "4l", "4m", "4o"):
+        # jittered grid, random diagonals, nodes AND elements randomly renumbered, 16 M triangles.  On N > 1 GPUs (and in case
+        # "4o" on one GPU) the elements are first put in Morton order of their centroids — SURVEY 8(e)'s space-filling-curve renumbering that makes
+        # contiguous element blocks compact; the node numbering stays random.  The mesh is fixed, N ranks take one block each: strong scaling.
         n = max(4, int(2828 * scale))
-        what = {"4": "Laplace and mass", "4l": "Laplace", "4m": "mass"}[case]
+        what = {"4": "Laplace and mass", "4l": "Laplace", "4m": "mass", "4o": "Laplace"}[case]
         coords, elems = meshgen.jitter_unstructured(n, n, 1.0 / n, seed=2, permute=(numbering == "random"))
+        morton = world > 1 or case == "4o"
         note = (f"config 4: P2 {what}, jittered triangulation with random diagonals, {n} x {n} cells ({2 * n * n} triangles), "
-                + ("nodes randomly renumbered (worst case for the locality of the CSR rows), elements in Morton order of their centroids (what a partitioner "
-                   "delivers; the element blocks of the N-GPU runs are contiguous ranges of this order)" if numbering == "random" else
-                   "generator (row-major) numbering of nodes and elements"))
-        if numbering == "random":
-            elems = elems[meshgen.morton_element_order(coords, elems)]         # same element order at every N, so the strong-scaling curve compares like with like
+                + ("nodes randomly renumbered" if numbering == "random" else "generator (row-major) node numbering") + ", elements "
+                + ("in Morton order of their centroids (SURVEY 8e: compact contiguous element blocks)" if morton else
+                   ("randomly renumbered" if numbering == "random" else "in generator order")))
+        if morton:
+            elems = elems[meshgen.morton_element_order(coords, elems)]
         op = 1 if case == "4m" else 0
         if world == 1:
             return A.Mesh(coords, elems, degree=2, **kw), None, op, 1, note, "strong"
-        if numbering != "random":
-            elems = elems[meshgen.morton_element_order(coords, elems)]
         part, _ = adist.partition_elements(coords, elems, rank, world, degree=2, **kw)
         return part.mesh, part, op, 1, note + "; one contiguous element block per GPU", "strong"
     if case == "5":
@@ -501,8 +503,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="2", choices=["2", "3", "4", "4l", "4m", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
-    ap.add_argument("--extra-configs", default="2m,3,4,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
+    ap.add_argument("--config", default="2", choices=["2", "3", "4", "4l", "4m", "4o", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
+    ap.add_argument("--extra-configs", default="2m,3,4,4o,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
     ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the edge counts of configs 3-5 (smoke runs)")
     ap.add_argument("--numbering", default="random", choices=["random", "generator"], help="config 4: node / element numbering of the synthetic unstructured mesh")
@@ -629,7 +631,7 @@ def main():
     nnode = mesh.nnode
     b_general = alg_bytes_per_elem(mesh, nnz, cpg)
     ibytes = float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0
-    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m")) and not (c == "2m" and world > 1)]
+    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m")) and not (c in ("2m", "4o") and world > 1)]
     if xc:
         del step, part, mesh
         torch.cuda.empty_cache()
@@ -660,7 +662,8 @@ def main():
     dom = "fwd" if fwd_ms >= adj_ms else "adj"
     tr = [traffic_of(traffic, k, E) for k in (fnames if dom == "fwd" else anames)]
     roofline = {"bound": "hbm", "kernel": kern[dom]["name"], "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peak, "traffic": (sum(tr) if all(t is not None for t in tr) else None), "peak_source": peak_src,
+                "frac": kern[dom]["GBps"] / peak, "frac_of_nominal_8TBps": kern[dom]["GBps"] / 8000.0,
+                "traffic": (sum(tr) if all(t is not None for t in tr) else None), "peak_source": peak_src,
                 "alg_bytes_per_elem": {"fwd": bf, "adj": ba}, "step_frac": (bf + ba) * E / (ms_per_step * 1e-3) / 1e9 / peak,
                 "kernels": kern}
     if structured:
@@ -683,7 +686,7 @@ def main():
                          f"{ne_cpu} triangles (a row slab of the config-2 mesh), best of 3, {threads} host threads over element blocks",
                "single_thread_value": ne_cpu / min(single) / 1e6,
                "single_thread_note": "the reference op as it is (no threading), same sample, one pass"}
-    launches = {"2": 2, "2g": 2, "2m": 2, "3": 2, "4": 2, "4l": 2, "4m": 2, "5": 3}[key] + (4 if world > 1 else 0)
+    launches = {"2": 2, "2g": 2, "2m": 2, "3": 2, "4": 2, "4l": 2, "4m": 2, "4o": 2, "5": 3}[key] + (4 if world > 1 else 0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": note, "elements_per_gpu": E, "nodes_per_gpu": nnode, "nnz_per_gpu": nnz, "gauss_points_per_gpu": G,
