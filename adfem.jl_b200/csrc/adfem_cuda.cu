@@ -74,6 +74,9 @@ struct adfem_mesh {
   std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
+  int opt_tile_overlap = -1;                // scalar tile forward with one barrier per tile (double-buffered local matrices, kernels.cuh k_tile_fwd_ov): -1 = P2 only.
+                                            // Measured (gpurun r2p): P2 forward, 16 M triangles, 5.84 -> 5.15 ms (random numbering), 3.21 -> 2.98 ms (Morton elements);
+                                            // P1 forward on the 33.5 M-triangle mesh 0.730 -> 0.950 ms (smaller tiles, more halo): stays on the two-barrier kernel
   int opt_smem_budget = 0;                  // dynamic shared memory per CTA (3 head + 2 body buffers + staging); 0 = per-operator default
   int opt_tile_threads = 0;                 // threads per CTA of the tile kernels; 0 = per-operator default
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
@@ -288,8 +291,9 @@ int ensure_pattern(adfem_mesh* m) {
 // scalar operators that stage their coefficients asynchronously, two buffers of g coefficients
 bool coef_staged(const HostMesh& h) { return h.degree != 1 || h.g > PIPE_GMAX; }       // scalar operators that cannot use the register prefetch
 // presum3d: 3-D P1 elasticity with option "coef_presum": the Gauss-summed blocks (ns*ns doubles per element) are small enough to be staged too
-int slots_of(const HostMesh& h, int nc, bool presum3d = false) {
-  if (nc == 1) return h.d * (h.d + 1) / 2 + (coef_staged(h) ? h.g : 0);                // + a staging buffer of g coefficients
+bool tile_overlap_of(const adfem_mesh* m) { return m->opt_tile_overlap > 0 || (m->opt_tile_overlap < 0 && m->hm.degree == 2); }
+int slots_of(const HostMesh& h, int nc, bool presum3d = false, bool overlap = false) {
+  if (nc == 1) return (overlap ? 2 : 1) * (h.d * (h.d + 1) / 2) + (coef_staged(h) ? h.g : 0);     // + a staging buffer of g coefficients; overlap: two local-matrix buffers
   const int ns = h.dim == 2 ? 3 : 6;
   if (presum3d) return (nc * h.d) * (nc * h.d) + ns * ns;
   // 2-D P1 elasticity stages the raw coefficient blocks (ns*ns*g doubles per element) asynchronously
@@ -310,7 +314,7 @@ bool presum3d_of(const adfem_mesh* m, int nc) { return m->opt_coef_presum && nc 
 int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
   if (int rc = ensure_pattern(m)) return rc;
   const HostMesh& h = m->hm;
-  const int slots = slots_of(h, nc, presum3d_of(m, nc)), dd = h.d * h.d;
+  const int slots = slots_of(h, nc, presum3d_of(m, nc), nc == 1 && tile_overlap_of(m)), dd = h.d * h.d;
   auto it = m->fwd_plans.find(nc);
   if (it != m->fwd_plans.end()) { *out = it->second.get(); return 0; }
   auto P = std::make_unique<FwdPlanDev>();
@@ -440,9 +444,18 @@ int launch_fwd_kernel(adfem_mesh* m, K kern, FwdPlanDev* P, size_t smem, int thr
 template <int DIM, int DEG, int OP>
 int launch_tile_fwd(adfem_mesh* m, FwdPlanDev* P, const double* coef, double* vals, cudaStream_t st, bool presum = false) {
   constexpr int NC = OP == OP_STIFFNESS ? DIM : 1;
-  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC, presum && presum3d_of(m, NC)));
+  const bool overlap = NC == 1 && tile_overlap_of(m);
+  const size_t smem = fwd_smem_bytes(P->host, slots_of(m->hm, NC, presum && presum3d_of(m, NC), overlap));
   const int threads = tile_threads_of(m, NC);
   if (smem > SMEM_LIMIT) return fail("forward tile needs more shared memory than an SM has");
+  if constexpr (OP != OP_STIFFNESS) {
+    if (overlap && m->opt_coef_prefetch) {
+      if constexpr (DEG == 1) {
+        if (m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads) return launch_fwd_kernel(m, k_tile_fwd_ov<DIM, DEG, OP, true>, P, smem, threads, coef, vals, st);
+      }
+      if (coef_staged(m->hm)) return launch_fwd_kernel(m, k_tile_fwd_ov<DIM, DEG, OP, false>, P, smem, threads, coef, vals, st);
+    }
+  }
   if constexpr (DEG == 1 && OP != OP_STIFFNESS) {
     // register prefetch of the next tile's coefficients
     if (m->opt_coef_prefetch && m->hm.g <= PIPE_GMAX && P->host.max_elems <= PIPE_EPT * threads)
@@ -802,6 +815,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
+  else if (k == "tile_overlap") { if (m->opt_tile_overlap != (int)value) m->fwd_plans.clear(); m->opt_tile_overlap = (int)value; }      // -1 auto, 0 off, 1 on; the tile size depends on it
   else if (k == "tile_threads" && value == 0) { m->opt_tile_threads = 0; m->adj_plans.clear(); }          // back to the per-operator default
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
   else if (k == "pipeline") { if (value < 0 || value > 1) return fail("pipeline must be 0 (one CTA per tile) or 1 (persistent, software-pipelined)"); m->opt_pipeline = (int)value; }

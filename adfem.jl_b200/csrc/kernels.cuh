@@ -973,6 +973,96 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd(DevMesh m, long l
   }
 }
 
+// Forward, scalar operators, ONE CTA-wide barrier per tile ("tile_overlap"): the local matrices are double-buffered, and an iteration runs
+// phase B of tile i (gather from loc[i & 1]) followed by phase A of tile i + 1 (local matrices into loc[(i + 1) & 1]) with no barrier in
+// between, so warps drift apart — some still gather while others already evaluate elements — instead of all meeting twice per tile.  Phase B
+// comes first so that the body of tile i + 2 (requested when tile i is released) has the whole of phase B of tile i + 1 to arrive: the ring of
+// two bodies suffices.  Costs D (D + 1) / 2 more doubles of shared memory per tile element (smaller tiles); same blobs, same summation order,
+// bit-identical values.
+template <int DIM, int DEG, int OP, bool KPRE>
+__global__ void __launch_bounds__(TILE_MAX_THREADS) k_tile_fwd_ov(DevMesh m, long long nnz_s, DevTiles tp, const double* __restrict__ coef,
+                                                                  double* __restrict__ vals) {
+  static_assert(OP != OP_STIFFNESS, "scalar operators only");
+  static_assert(!KPRE || DEG == 1, "register prefetch is for P1 scalar operators");
+  constexpr int D = ElemTraits<DIM, DEG>::D, NVL = DIM + 1, LS = D * (D + 1) / 2;
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ __align__(8) uint64_t mbar[5];
+  const int tid = threadIdx.x, nth = blockDim.x, g = m.g;
+  TileRing R{smem_all, smem_all + (size_t)3 * tp.max_head, mbar, tp.max_head, tp.max_body, tp.blob_ptr, tp.blob,
+             (int)blockIdx.x, (int)gridDim.x, ((int)blockIdx.x < tp.ntiles) ? (tp.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0};
+  double* loc_all = reinterpret_cast<double*>(R.bodies + (size_t)2 * tp.max_body);      // two buffers of LS * max_elems doubles
+  const size_t loc_stride = (size_t)LS * tp.max_elems;
+  double* cst_all = loc_all + 2 * loc_stride;                                           // staging [g][nel] of the tile whose phase A comes next (not KPRE)
+  constexpr bool P2TAB = DEG == 2;
+  __shared__ double p2tab[P2TAB ? p2_table_rows<DIM, OP>() * MAX_QP : 1];
+  if constexpr (P2TAB) p2_build_table<DIM, OP>(m.rule, g, tid, nth, p2tab);
+  if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&mbar[i], 1); }
+  __syncthreads();
+  if (R.count == 0) return;
+  if (tid == 0) R.prologue();
+  double kr[KPRE ? PIPE_EPT : 1][KPRE ? PIPE_GMAX : 1];
+  auto fetch_coef = [&](const unsigned char* head) {
+    const int* hdr = reinterpret_cast<const int*>(head);
+    const int nel = hdr[1];
+    const int* elems = hdr + 8;
+    if constexpr (KPRE) {
+#pragma unroll
+      for (int s = 0; s < PIPE_EPT; s++) {
+        const int le = tid + s * nth;
+        if (le < nel) {
+          const double* p = coef + (size_t)elems[le] * g;
+#pragma unroll
+          for (int k = 0; k < PIPE_GMAX; k++) if (k < g) kr[s][k] = __ldg(p + k);
+        }
+      }
+    } else {
+      for (int le = tid; le < nel; le += nth) {
+        const double* p = coef + (size_t)elems[le] * g;
+        for (int k = 0; k < g; k++) cp_async8(cst_all + k * nel + le, p + k);
+      }
+    }
+  };
+  auto phase_a = [&](const FwdView& V, double* loc) {
+    if constexpr (KPRE) {
+#pragma unroll
+      for (int s = 0; s < PIPE_EPT; s++) {
+        const int le = tid + s * nth;
+        if (le < V.nel) {
+          Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+          local_matrix_scalar<DIM, DEG, OP, PIPE_GMAX>(m, G, [&](int k) { return kr[s][k]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+        }
+      }
+    } else {
+      cp_async_wait_all();                                 // this thread's copies (it reads only what it copied)
+      const double* cs = cst_all;
+      for (int le = tid; le < V.nel; le += nth) {
+        Geom<DIM> G; tile_geom(V.tv, V.xy, V.nel, le, m.heron, G);
+        if constexpr (P2TAB) p2_local_matrix<DIM, OP>(g, G, p2tab, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+        else local_matrix_scalar<DIM, DEG, OP, 0>(m, G, [&](int k) { return cs[k * V.nel + le]; }, [&](int slot, double v) { loc[slot * V.nel + le] = v; });
+      }
+    }
+  };
+  // prologue: local matrices of the first tile
+  R.wait_head(0);
+  fetch_coef(R.head(0));
+  R.wait_body(0);
+  { const FwdView V0(R.head(0), R.body(0), NVL, DIM, false); phase_a(V0, loc_all); }
+  __syncthreads();
+  for (int i = 0; i < R.count; i++) {
+    const FwdView V(R.head(i), R.body(i), NVL, DIM, false);
+    const bool more = i + 1 < R.count;
+    if (more) { R.wait_head(i + 1); fetch_coef(R.head(i + 1)); }      // in flight during phase B
+    fwd_gather_scalar(V, loc_all + (size_t)(i & 1) * loc_stride, vals, tid, nth);
+    if (more) {
+      R.wait_body(i + 1);
+      const FwdView Vn(R.head(i + 1), R.body(i + 1), NVL, DIM, false);
+      phase_a(Vn, loc_all + (size_t)((i + 1) & 1) * loc_stride);
+    }
+    __syncthreads();                                       // loc[(i+1)&1] complete; loc[i&1], body(i), head(i) free
+    if (tid == 0) R.refill_after(i);
+  }
+}
+
 // decoded view of an adjoint tile
 struct AdjView {
   int nrows, nel, nvt, nnz_t, lrow16;

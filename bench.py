@@ -516,7 +516,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--structured", type=int, default=1, help="0: force the general tile kernels on the structured mesh")
     ap.add_argument("--general-steps", type=int, default=20, help="extra timed steps of the general (unstructured-mesh) tile kernels, N=1 only")
-    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="adfem_set_option on the headline mesh")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="adfem_set_option on the headline mesh (and on the extra configs)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -637,7 +637,7 @@ def main():
         torch.cuda.empty_cache()
         for c in xc:
             try:
-                recs = case_records(c, rank, world, args.extra_steps, 3, args.scale, peak, traffic, bool(args.library_exchange), args.numbering)
+                recs = case_records(c, rank, world, args.extra_steps, 3, args.scale, peak, traffic, bool(args.library_exchange), args.numbering, opts)
             except Exception as ex:          # an extra config must not cost the headline line
                 recs = [{"case": "config" + c, "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}] if rank == 0 else []
                 torch.cuda.empty_cache()

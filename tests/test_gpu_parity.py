@@ -155,6 +155,31 @@ def test_csr_scalar_ops(oracle, name, degree, tiles):
 
 
 @pytest.mark.parametrize("name,degree", CASES)
+def test_csr_scalar_tile_overlap(oracle, name, degree):
+    """Option "tile_overlap": scalar tile forward with one barrier per tile (double-buffered local matrices, kernels.cuh k_tile_fwd_ov): bit-identical
+    to the two-barrier kernel, against the oracle, for several tile sizes, CTA sizes and persistent launches that walk all tiles."""
+    m, o = make(name, degree, oracle)
+    m.set_option("structured", 0)
+    rng = np.random.default_rng(12)
+    coef = rng.random(o.ngauss) + 0.5
+    for op, fn, ofwd in ((0, ops.compute_fem_laplace_matrix1, o.laplace_fwd), (1, ops.compute_fem_mass_matrix1, o.mass_fwd)):
+        ind, vv = ofwd(coef)
+        rp, ci, ref = oracle.canonical_csr(ind, vv, o.ndof)
+        for rows, threads, glim in ((0, 0, 0), (16, 128, 1), (40, 320, 2), (7, 64, 3)):
+            m.set_option("rows_per_tile", rows)
+            m.set_option("tile_threads", threads)
+            m.set_option("grid_limit", glim)
+            m.set_option("tile_overlap", 0)
+            base = fn(dev(coef), m, mode="csr").values.cpu().numpy()
+            m.set_option("tile_overlap", 1)
+            got = fn(dev(coef), m, mode="csr").values.cpu().numpy()
+            close(got, ref)
+            assert np.array_equal(got, base)
+    for k_, v_ in (("tile_overlap", -1), ("rows_per_tile", 0), ("tile_threads", 0), ("grid_limit", 0)):
+        m.set_option(k_, v_)
+
+
+@pytest.mark.parametrize("name,degree", CASES)
 def test_csr_mass_3d(oracle, name, degree):
     if MESHES[name][0] != 3:
         pytest.skip("3-D only")
