@@ -77,6 +77,7 @@ struct adfem_mesh {
   int opt_tile_overlap = -1;                // scalar tile forward with one barrier per tile (double-buffered local matrices, kernels.cuh k_tile_fwd_ov): -1 = P2 only.
                                             // Measured (gpurun r2p): P2 forward, 16 M triangles, 5.84 -> 5.15 ms (random numbering), 3.21 -> 2.98 ms (Morton elements);
                                             // P1 forward on the 33.5 M-triangle mesh 0.730 -> 0.950 ms (smaller tiles, more halo): stays on the two-barrier kernel
+  int opt_smem_budget_adj = 0;              // the same for the adjoint tile kernels only (0 = opt_smem_budget / per-operator default)
   int opt_smem_budget = 0;                  // dynamic shared memory per CTA (3 head + 2 body buffers + staging); 0 = per-operator default
   int opt_tile_threads = 0;                 // threads per CTA of the tile kernels; 0 = per-operator default
   int opt_pipeline = 1;                     // 1 = persistent CTAs (software pipeline across tiles), 0 = one CTA per tile
@@ -250,7 +251,17 @@ int nthreads_of(const adfem_mesh* m) { return m->opt_threads > 0 ? m->opt_thread
 // fits the register file (seen in ncu: occupancy limit 1, 15 % achieved), so they run 256 threads x 2 CTAs with 110 KB tiles.
 bool heavy_kernel(const adfem_mesh* m, int nc) { return m->hm.degree == 2 || (nc > 1 && m->hm.dim == 3); }
 int tile_threads_of(const adfem_mesh* m, int nc) { return m->opt_tile_threads > 0 ? m->opt_tile_threads : (heavy_kernel(m, nc) ? 256 : 320); }
-size_t smem_budget_of(const adfem_mesh* m, int nc) { return m->opt_smem_budget > 0 ? (size_t)m->opt_smem_budget : (heavy_kernel(m, nc) ? ((m->hm.degree == 2 && nc == 1) ? 104 : 110) * 1024 : 72 * 1024); }   // P2 scalar kernels keep up to 5 KB of static moment tables
+// adjoint = true: the P2 scalar adjoint runs one CTA of 200 KB per SM.  Measured (gpurun r2q / r2r / r2t), adjoint of the P2 Laplace operator:
+//   2 M triangles, random numbering:        104 KB 0.406 ms, 72 KB 0.329 ms, 200 KB 0.335 ms (the forward is flat over all shapes)
+//   16 M triangles, random numbering:       104 KB 3.15 ms,  72 KB 2.95 ms,  200 KB 2.71 ms
+//   16 M triangles, Morton element order:   104 KB 2.23 ms,  72 KB 2.61 ms,  148 KB 2.64 ms, 200 KB 2.24 ms
+size_t smem_budget_of(const adfem_mesh* m, int nc, bool adjoint = false) {
+  if (adjoint && m->opt_smem_budget_adj > 0) return (size_t)m->opt_smem_budget_adj;
+  if (m->opt_smem_budget > 0) return (size_t)m->opt_smem_budget;
+  if (!heavy_kernel(m, nc)) return 72 * 1024;
+  if (m->hm.degree == 2 && nc == 1) return (adjoint ? 200 : 104) * 1024;    // P2 scalar kernels keep up to 5 KB of static moment tables
+  return 110 * 1024;
+}
 
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
@@ -357,7 +368,7 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
   if (it != m->adj_plans.end()) { *out = it->second.get(); return 0; }
   if (m->adj_untileable) return 0;
   auto P = std::make_unique<AdjPlanDev>();
-  size_t budget = smem_budget_of(m, nc);
+  size_t budget = smem_budget_of(m, nc, true);
   std::string err = "tile too large";
   for (int attempt = 0; attempt < 4 && !err.empty(); attempt++, budget = std::min(SMEM_LIMIT, budget * 2)) {
     const int dd = h.d * h.d;
@@ -815,6 +826,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "adjoint_tiled") m->opt_adjoint_tiled = (int)value;
   else if (k == "host_threads") m->opt_threads = (int)value;
   else if (k == "smem_budget") { m->opt_smem_budget = (int)value; m->fwd_plans.clear(); m->adj_plans.clear(); }
+  else if (k == "smem_budget_adj") { m->opt_smem_budget_adj = (int)value; m->adj_plans.clear(); }
   else if (k == "tile_overlap") { if (m->opt_tile_overlap != (int)value) m->fwd_plans.clear(); m->opt_tile_overlap = (int)value; }      // -1 auto, 0 off, 1 on; the tile size depends on it
   else if (k == "tile_threads" && value == 0) { m->opt_tile_threads = 0; m->adj_plans.clear(); }          // back to the per-operator default
   else if (k == "tile_threads") { if (value < 32 || value > TILE_MAX_THREADS || value % 32) return fail("tile_threads must be a multiple of 32 in [32, 512]"); if (m->opt_tile_threads != (int)value && m->opt_elems_per_tile <= 0) m->adj_plans.clear(); m->opt_tile_threads = (int)value; }
