@@ -123,6 +123,10 @@ void PlaneStressMatrix_forward(double* out, const double* E, const double* nu, i
 void PlaneStressMatrix_backward(double* grad_nu, double* grad_E, const double* grad_out, const double* E, const double* nu, int N);
 
 /* ============================ (2) handle API ================================================= */
+/* Threading / streams: a mesh handle owns scratch that its calls share (the Gauss-summed tangents of the P1 elasticity kernels, the
+ * staging buffers of the *_host calls, the side stream of the optional z-chunk pipeline).  Calls on ONE handle must therefore be issued
+ * on one stream at a time, or be ordered by events; different handles are independent.  Every call is asynchronous on the stream it is
+ * given (the first call of an operator also builds its mesh-static plan, which synchronises once). */
 typedef struct adfem_mesh adfem_mesh;
 
 const char* adfem_last_error(void);
@@ -135,8 +139,11 @@ enum { ADFEM_INFO_DIM = 0, ADFEM_INFO_NV, ADFEM_INFO_NE, ADFEM_INFO_NDOF, ADFEM_
        ADFEM_INFO_PLAN_BYTES,
        ADFEM_INFO_STRUCTURED /* 1: the mesh is the structured triangulation Mesh(m,n,h) v1 on rectilinear nodes and the scalar CSR
                                 operators use the index-free kernels of csrc/tri_grid.cuh (option "structured" = 0 disables);
-                                2: the mesh is the structured tetrahedral grid Mesh3(n,n,l,h) on rectilinear nodes (csrc/tet_grid.cuh, used by
-                                the elasticity forward under option "structured_elasticity") */ };
+                                2: the mesh is the structured tetrahedral grid Mesh3(n,n,l,h) on rectilinear nodes (csrc/tet_node.cuh / tet_grid.cuh,
+                                used by the elasticity kernels under option "structured_elasticity");
+                                3: structured connectivity of Mesh(m,n,h) on NON-rectilinear (mapped / jittered) node positions: the scalar CSR
+                                operators and the source term use the MAPPED instantiations of the index-free kernels, everything else the
+                                general kernels */ };
 
 /* Replaces init_nnfem_mesh / init_nnfem_mesh3 (deps/MFEM/API.cpp:4, deps/MFEM3/API.cpp:4) without the
  * process-global singleton.  dim = 2|3; vertices: nv rows of `vertex_stride` doubles (first `dim` used);
