@@ -340,7 +340,13 @@ class DeviceStep:
         self.main = torch.cuda.current_stream()
         self.st = C.c_void_p(self.main.cuda_stream)
         self.p = [C.c_void_p(t.data_ptr()) for t in (self.coef, self.vals, self.dK, self.grad)]
-        self.side = torch.cuda.Stream(priority=-1) if part is not None else None
+        # The exchanges overlap the kernels only on the structured paths (many short CTAs: the high-priority side stream's kernels slip in
+        # between them).  The tile kernels are PERSISTENT (every SM slot is held for the whole launch), so a concurrent ncclSend/ncclRecv
+        # kernel either waits for them to end or sits on an SM waiting for a peer whose own NCCL kernel cannot start — measured on config 4 at
+        # N = 8: forward 0.38 -> 0.63 ms and the adjoint waiting 0.29 ms for an exchange that takes 0.06 ms alone.  There the exchanges run on
+        # the main stream between the kernels.
+        self.overlap = part is not None and int(self.L.adfem_mesh_info(mesh.handle, _lib.INFO_STRUCTURED)) != 0
+        self.side = torch.cuda.Stream(priority=-1) if self.overlap else None
         self.dghost = None
         if part is not None:
             if library:
@@ -356,6 +362,20 @@ class DeviceStep:
 
     def __call__(self, ev=None):
         torch, part, main, side = self.torch, self.part, self.main, self.side
+        if part is not None and not self.overlap:       # in order on the main stream
+            if ev:
+                ev[0].record()
+            self.forward()
+            if ev:
+                ev[1].record()
+            part.reduce_interface(self.vals, ncomp=self.nc)
+            part.replicate_interface(self.dK, self.dghost, ncomp=self.nc)
+            if ev:
+                ev[2].record()
+            self.adjoint()
+            if ev:
+                ev[3].record()
+            return
         if part is not None:
             side.wait_stream(main)             # previous step's adjoint has read dK; previous reduce has finished with vals
             main.wait_stream(side)
@@ -381,7 +401,7 @@ class DeviceStep:
                 part.reduce_interface(self.vals, ncomp=self.nc)
 
     def join(self):
-        if self.part is not None:
+        if self.side is not None:
             self.main.wait_stream(self.side)
 
     def exchange_alone_ms(self, reps=10):
@@ -487,7 +507,7 @@ def case_records(case, rank, world, steps, warmup, scale, peak, traffic, library
                                   "traffic": {"fwd": (sum(tr_f) if all(t is not None for t in tr_f) else None), "adj": (sum(tr_a) if all(t is not None for t in tr_a) else None),
                                               "alg_bytes_per_launch": b * E}},
                      "plan_bytes_per_elem": L.adfem_mesh_info(mesh.handle, _lib.INFO_PLAN_BYTES) / E, "setup_s_untimed": round(setup, 1),
-                     "exchange": step.exchange, "interface_bytes_per_step_total": int(ibytes), "exchange_alone_ms": xa_ms,
+                     "exchange": step.exchange, "exchange_overlaps_kernels": bool(step.overlap), "interface_bytes_per_step_total": int(ibytes), "exchange_alone_ms": xa_ms,
                      "steps": steps, "warmup": warmup})
         del step
         torch.cuda.empty_cache()
