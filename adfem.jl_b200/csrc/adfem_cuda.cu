@@ -74,9 +74,10 @@ struct adfem_mesh {
   std::map<int, std::unique_ptr<AdjPlanDev>> adj_plans;   // keyed by nc
   // options
   int opt_rows_per_tile = 0, opt_elems_per_tile = 0, opt_adjoint_tiled = 1, opt_threads = 0;
-  int opt_tile_overlap = -1;                // scalar tile forward with one barrier per tile (double-buffered local matrices, kernels.cuh k_tile_fwd_ov): -1 = P2 only.
-                                            // Measured (gpurun r2p): P2 forward, 16 M triangles, 5.84 -> 5.15 ms (random numbering), 3.21 -> 2.98 ms (Morton elements);
-                                            // P1 forward on the 33.5 M-triangle mesh 0.730 -> 0.950 ms (smaller tiles, more halo): stays on the two-barrier kernel
+  int opt_tile_overlap = 0;                 // scalar tile forward with one barrier per tile (double-buffered local matrices, kernels.cuh k_tile_fwd_ov): 1 = on, -1 = P2 only.
+                                            // Off: the gain is not robust.  Measured P2 forward, one GPU: 16 M triangles 5.84 -> 5.15 ms (random numbering), 3.21 -> 2.98 ms
+                                            // (Morton elements), 2 M triangles 0.354 -> 0.376 ms; element blocks under torchrun: 8 M per GPU 1.52 -> 2.02 ms, 2 M per GPU
+                                            // 0.50 -> 0.63 ms.  P1 forward on 33.5 M triangles 0.730 -> 0.950 ms (smaller tiles, more halo).
   int opt_smem_budget_adj = 0;              // the same for the adjoint tile kernels only (0 = opt_smem_budget / per-operator default)
   int opt_smem_budget = 0;                  // dynamic shared memory per CTA (3 head + 2 body buffers + staging); 0 = per-operator default
   int opt_tile_threads = 0;                 // threads per CTA of the tile kernels; 0 = per-operator default

@@ -175,7 +175,7 @@ def test_csr_scalar_tile_overlap(oracle, name, degree):
             got = fn(dev(coef), m, mode="csr").values.cpu().numpy()
             close(got, ref)
             assert np.array_equal(got, base)
-    for k_, v_ in (("tile_overlap", -1), ("rows_per_tile", 0), ("tile_threads", 0), ("grid_limit", 0)):
+    for k_, v_ in (("tile_overlap", 0), ("rows_per_tile", 0), ("tile_threads", 0), ("grid_limit", 0)):
         m.set_option(k_, v_)
 
 
