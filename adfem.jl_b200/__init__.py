@@ -2,7 +2,7 @@
 over libadfem_cuda.so (include/adfem_cuda.h).  Import as `adfem_jl_b200` (see the shim at the repo root)."""
 from . import _lib, meshgen  # noqa: F401
 from ._lib import AdfemError, build  # noqa: F401
-from .mesh import (P1, P2, Mesh, Mesh3, bcedge, bcnode, fem_nodes, gauss_nodes, gauss_weights, get_area,  # noqa: F401
+from .mesh import (P1, P2, Mesh, Mesh3, bcedge, bcnode, fem_nodes, gauss_nodes, gauss_nodes_soa, gauss_weights, get_area,  # noqa: F401
                    get_edge_dof, get_ngauss, get_volume, read_mesh_file)
 from .ops import (CSRTensor, SparseTensor, compute_fem_laplace_matrix1, compute_fem_mass_matrix1,  # noqa: F401,E402
                   compute_fem_source_term, compute_fem_source_term1, compute_fem_stiffness_matrix, compute_fem_stiffness_matrix1,

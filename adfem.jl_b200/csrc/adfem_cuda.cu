@@ -780,7 +780,7 @@ long long adfem_mesh_info(const adfem_mesh* m, int what) {
     case ADFEM_INFO_NDOF: return h.ndof;
     case ADFEM_INFO_NGAUSS: return (long long)h.ne * h.g;
     case ADFEM_INFO_ELEM_NDOF: return h.d;
-    case ADFEM_INFO_NEDGES: return h.nedges;
+    case ADFEM_INFO_NEDGES: h.ensure_edges(); return h.nedges;
     case ADFEM_INFO_GAUSS_PER_ELEM: return h.g;
     case ADFEM_INFO_NNZ_SCALAR: return m->has_pattern ? m->pat.nnz : -1;
     case ADFEM_INFO_TILES_FWD: { long long t = 0; for (auto& kv : m->fwd_plans) t = kv.second->host.ntiles; return t; }
@@ -798,6 +798,7 @@ long long adfem_mesh_info(const adfem_mesh* m, int what) {
 
 int adfem_mesh_edges(const adfem_mesh* m, long long* edges) {
   if (!m) return fail("null mesh handle");
+  m->hm.ensure_edges();
   const long long ne = m->hm.nedges;
   for (long long i = 0; i < ne; i++) { edges[i] = m->hm.edge_lo[i] + 1; edges[ne + i] = m->hm.edge_hi[i] + 1; }
   return 0;
@@ -1331,6 +1332,7 @@ long long* legacy_init(adfem_mesh*& slot, int dim, double* vertices, int nv, int
                        long long* nedges) {
   if (slot) { printf("WARNING: Internal mesh is being overwritten!\n"); adfem_mesh_destroy(slot); slot = nullptr; }   // API.cpp:6-10
   if (adfem_mesh_create(&slot, dim, vertices, 3, nv, elems, ne, order, degree, lorder, 0)) { legacy_fail("init_nnfem_mesh"); return nullptr; }
+  slot->hm.ensure_edges();
   *nedges = slot->hm.nedges;
   long long* edges = (long long*)malloc(sizeof(long long) * 2 * (size_t)std::max<long long>(1, slot->hm.nedges));
   adfem_mesh_edges(slot, edges);

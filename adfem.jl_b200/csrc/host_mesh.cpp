@@ -1,10 +1,28 @@
 #include "host_mesh.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <thread>
 
 namespace adfem {
 
 namespace {
+// static block partition of [0, n) over host threads (ADFEM_HOST_THREADS, default: the hardware's); element loops below are independent per element
+template <class F> void par_elems(long long n, F fn) {
+  int nt = 0;
+  if (const char* s = getenv("ADFEM_HOST_THREADS")) nt = atoi(s);
+  if (nt <= 0) { unsigned h = std::thread::hardware_concurrency(); nt = h == 0 ? 4 : (int)std::min(h, 64u); }
+  if (nt <= 1 || n < 65536) { fn(0LL, n); return; }
+  std::vector<std::thread> th;
+  const long long chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    const long long a = t * chunk, b = std::min(n, a + chunk);
+    if (a < b) th.emplace_back([=] { fn(a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
 // local edges in MFEM geometry order (Geometry::Constants<TRIANGLE/TETRAHEDRON>::Edges)
 const int kTriEdges[3][2] = {{0, 1}, {1, 2}, {2, 0}};
 const int kTetEdges[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
@@ -42,7 +60,8 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   for (size_t i = 0; i < verts.size(); i++)
     if (verts[i] < 0 || verts[i] >= nv) return "element vertex index out of range";
   // orientation fix (quirk Q3)
-  for (int e = 0; e < ne; e++) {
+  par_elems(ne, [&](long long e0, long long e1) {
+  for (long long e = e0; e < e1; e++) {
     int* vi = &verts[(size_t)e * nvl];
     const double* X = coords.data();
     double det;
@@ -57,26 +76,47 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
     }
     if (det < 0.0) { int t = vi[0]; vi[0] = vi[1]; vi[1] = t; }
   }
-  // edges + connectivity
-  EdgeNumbering en(nv);
+  });
+  // edges + connectivity.  P1: the connectivity is the vertex list and the edge numbering (an output of the mesh constructor only) is left to
+  // ensure_edges(): its sequential first-appearance walk costs more than every other table together on large meshes.
   conn.resize((size_t)ne * d);
-  for (int e = 0; e < ne; e++) {
-    const int* vi = &verts[(size_t)e * nvl];
-    int* ce = &conn[(size_t)e * d];
-    for (int k = 0; k < nvl; k++) ce[k] = vi[k];
-    for (int j = 0; j < nel; j++) {
-      int a = dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0], b = dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1];
-      int id = en.id(vi[a], vi[b]);
-      if (degree == 2) ce[nvl + j] = nv + id;
+  edges_built = false; nedges = 0; edge_lo.clear(); edge_hi.clear();
+  if (degree == 1) {
+    conn = verts;
+  } else {
+    EdgeNumbering en(nv);
+    for (int e = 0; e < ne; e++) {
+      const int* vi = &verts[(size_t)e * nvl];
+      int* ce = &conn[(size_t)e * d];
+      for (int k = 0; k < nvl; k++) ce[k] = vi[k];
+      for (int j = 0; j < nel; j++) {
+        int a = dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0], b = dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1];
+        ce[nvl + j] = nv + en.id(vi[a], vi[b]);
+      }
     }
+    nedges = (long long)en.hi.size();
+    edge_lo.swap(en.lo);
+    edge_hi.swap(en.hi);
+    edges_built = true;
   }
-  nedges = (long long)en.hi.size();
-  edge_lo.swap(en.lo);
-  edge_hi.swap(en.hi);
   long long nd = degree == 1 ? (long long)nv : (long long)nv + nedges;
   if (nd > 2147483647LL) return "too many dofs for 32-bit dof ids";
   ndof = (int)nd;
   return "";
+}
+
+void HostMesh::ensure_edges() const {
+  if (edges_built) return;
+  const int nvl = dim + 1, nel = dim == 2 ? 3 : 6;
+  EdgeNumbering en(nv);
+  for (int e = 0; e < ne; e++) {
+    const int* vi = &verts[(size_t)e * nvl];
+    for (int j = 0; j < nel; j++) en.id(vi[dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0]], vi[dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1]]);
+  }
+  nedges = (long long)en.hi.size();
+  edge_lo.swap(en.lo);
+  edge_hi.swap(en.hi);
+  edges_built = true;
 }
 
 void HostMesh::dof_position(int dof, double* x) const {
@@ -108,37 +148,43 @@ double tet_volume(const double* v0, const double* v1, const double* v2, const do
 
 void HostMesh::measure(double* a) const {
   const int nvl = dim + 1;
-  for (int e = 0; e < ne; e++) {
-    const int* vi = &verts[(size_t)e * nvl];
-    const double* X = coords.data();
-    a[e] = dim == 2 ? tri_area_heron(X + 2 * (size_t)vi[0], X + 2 * (size_t)vi[1], X + 2 * (size_t)vi[2])
-                    : tet_volume(X + 3 * (size_t)vi[0], X + 3 * (size_t)vi[1], X + 3 * (size_t)vi[2], X + 3 * (size_t)vi[3]);
-  }
+  par_elems(ne, [&](long long e0, long long e1) {
+    for (long long e = e0; e < e1; e++) {
+      const int* vi = &verts[(size_t)e * nvl];
+      const double* X = coords.data();
+      a[e] = dim == 2 ? tri_area_heron(X + 2 * (size_t)vi[0], X + 2 * (size_t)vi[1], X + 2 * (size_t)vi[2])
+                      : tet_volume(X + 3 * (size_t)vi[0], X + 3 * (size_t)vi[1], X + 3 * (size_t)vi[2], X + 3 * (size_t)vi[3]);
+    }
+  });
 }
 
 void HostMesh::gauss_weights(double* w) const {
   std::vector<double> a(ne);
   measure(a.data());
-  for (int e = 0; e < ne; e++)
-    for (int k = 0; k < g; k++) w[(size_t)e * g + k] = dim == 2 ? rule.w[k] * a[e] / 0.5 : rule.w[k] * a[e] * 6.0;
+  par_elems(ne, [&](long long e0, long long e1) {
+    for (long long e = e0; e < e1; e++)
+      for (int k = 0; k < g; k++) w[(size_t)e * g + k] = dim == 2 ? rule.w[k] * a[e] / 0.5 : rule.w[k] * a[e] * 6.0;
+  });
 }
 
 void HostMesh::gauss_points(double* xyz) const {
   const int nvl = dim + 1;
   const size_t G = (size_t)ne * g;
-  for (int e = 0; e < ne; e++) {
-    const int* vi = &verts[(size_t)e * nvl];
-    for (int k = 0; k < g; k++) {
-      double L[4];
-      if (dim == 2) { L[0] = 1 - rule.x[k] - rule.y[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; }
-      else { L[0] = 1 - rule.x[k] - rule.y[k] - rule.z[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; L[3] = rule.z[k]; }
-      for (int c = 0; c < dim; c++) {
-        double s = 0;
-        for (int j = 0; j < nvl; j++) s += coords[(size_t)vi[j] * dim + c] * L[j];
-        xyz[c * G + (size_t)e * g + k] = s;
+  par_elems(ne, [&](long long e0, long long e1) {
+    for (long long e = e0; e < e1; e++) {
+      const int* vi = &verts[(size_t)e * nvl];
+      for (int k = 0; k < g; k++) {
+        double L[4];
+        if (dim == 2) { L[0] = 1 - rule.x[k] - rule.y[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; }
+        else { L[0] = 1 - rule.x[k] - rule.y[k] - rule.z[k]; L[1] = rule.x[k]; L[2] = rule.y[k]; L[3] = rule.z[k]; }
+        for (int c = 0; c < dim; c++) {
+          double s = 0;
+          for (int j = 0; j < nvl; j++) s += coords[(size_t)vi[j] * dim + c] * L[j];
+          xyz[c * G + (size_t)e * g + k] = s;
+        }
       }
     }
-  }
+  });
 }
 
 }  // namespace adfem

@@ -19,12 +19,15 @@ struct HostMesh {
   int d = 0;            // dofs per element: 3/6 (tri P1/P2), 4/10 (tet P1/P2)
   int g = 0;            // Gauss points per element
   int ndof = 0;         // nv (P1) or nv + nedges (P2)
-  long long nedges = 0;
+  mutable long long nedges = 0;   // P1 meshes: filled by ensure_edges() (the edge list is only an output there, not needed by any kernel)
+  mutable bool edges_built = false;
   QuadRule rule;
   std::vector<double> coords;     // nv x dim, packed
   std::vector<int> verts;         // ne x (dim+1) after the orientation fix (det<0 => swap local 0,1)
   std::vector<int> conn;          // ne x d, 0-based dofs: vertices then (P2) nv + edge id, geometry edge order
-  std::vector<int> edge_lo, edge_hi;   // edge i joins edge_lo[i] < edge_hi[i] (first-appearance numbering)
+  mutable std::vector<int> edge_lo, edge_hi;   // edge i joins edge_lo[i] < edge_hi[i] (first-appearance numbering)
+  // P1: numbers the edges on first use (nedges, edge_lo, edge_hi); P2 meshes have them from build().  Not thread-safe (setup-time getter).
+  void ensure_edges() const;
 
   // builds all tables; returns "" or an error message
   std::string build(int dim, const double* vertices, int vstride, int nv, const int* elems, int ne, int order,

@@ -42,7 +42,7 @@ class _MeshBase:
         info = lambda w: int(L.adfem_mesh_info(h, w))
         self.nodes = coords
         self.nnode, self.nelem, self.ndof = info(_lib.INFO_NV), info(_lib.INFO_NE), info(_lib.INFO_NDOF)
-        self.nedge, self.elem_ndof, self.ngauss = info(_lib.INFO_NEDGES), info(_lib.INFO_ELEM_NDOF), info(_lib.INFO_NGAUSS)
+        self.elem_ndof, self.ngauss = info(_lib.INFO_ELEM_NDOF), info(_lib.INFO_NGAUSS)
         self.gauss_per_elem = info(_lib.INFO_GAUSS_PER_ELEM)
         self.elem_type = P1 if degree == 1 else P2
         self.degree = degree
@@ -66,6 +66,7 @@ class _MeshBase:
                 self._lazy[name] = ev.reshape(self.dim + 1, self.nelem).T - 1     # post orientation fix, like src/MFEM/MFEM.jl:106
         return self._lazy[name]
 
+    nedge = property(lambda self: int(lib().adfem_mesh_info(self.handle, _lib.INFO_NEDGES)))      # P1 meshes number their edges on first use
     edges = property(lambda self: self._fetch("edges"))            # nedge x 2, 0-based (src/MFEM/MFEM.jl:99-100)
     conn = property(lambda self: self._fetch("conn"))              # ne x d global dofs, 0-based
     elems = property(lambda self: self._fetch("elems"))            # ne x (dim+1) vertices after the orientation fix
@@ -188,6 +189,14 @@ def gauss_nodes(mesh):
     out = np.zeros(mesh.dim * mesh.ngauss)
     check(lib().adfem_mesh_gauss(mesh.handle, out.ctypes.data_as(_lib.c_dp)))
     return out.reshape(mesh.dim, mesh.ngauss).T.copy()
+
+
+def gauss_nodes_soa(mesh):
+    """(dim, ngauss) array: row c = coordinate c of every Gauss point — the layout of mfem_get_gauss(x, y) itself, without the transposed copy
+    that `gauss_nodes` makes for the Julia-shaped (ngauss, dim) result."""
+    out = np.zeros(mesh.dim * mesh.ngauss)
+    check(lib().adfem_mesh_gauss(mesh.handle, out.ctypes.data_as(_lib.c_dp)))
+    return out.reshape(mesh.dim, mesh.ngauss)
 
 
 def gauss_weights(mesh):

@@ -331,7 +331,8 @@ class DeviceStep:
         G = mesh.ngauss
         gen = torch.Generator(device="cuda").manual_seed(seed)
         if coef_h is not None:
-            self.coef, self.dK = torch.from_numpy(coef_h).cuda(), torch.from_numpy(dK_h).cuda()
+            self.coef = coef_h if torch.is_tensor(coef_h) else torch.from_numpy(coef_h).cuda()
+            self.dK = dK_h if torch.is_tensor(dK_h) else torch.from_numpy(dK_h).cuda()
         else:
             self.coef = torch.rand(G * cpg, dtype=torch.float64, device="cuda", generator=gen) + 0.5
             self.dK = torch.rand(self.nnz, dtype=torch.float64, device="cuda", generator=gen) - 0.5
@@ -578,9 +579,10 @@ def main():
     coef_h = dK_h = None
     if case == "2":
         rowptr, _ = mesh.csr_pattern(1)
-        xy = A.gauss_nodes(mesh)
-        coef_h = 1 + 0.5 * np.sin(2 * np.pi * xy[:, 0]) * np.cos(2 * np.pi * xy[:, 1])
-        del xy
+        xy = A.gauss_nodes_soa(mesh)                              # (2, G): kappa(x, y) = 1 + sin(2 pi x) cos(2 pi y) / 2 is evaluated on the device (setup time)
+        gx, gy = torch.from_numpy(xy[0]).cuda(), torch.from_numpy(xy[1]).cuda()
+        coef_h = 1 + 0.5 * torch.sin(2 * np.pi * gx) * torch.cos(2 * np.pi * gy)
+        del xy, gx, gy
         dK_h = np.random.default_rng(rank).uniform(-1, 1, int(rowptr[-1]))
     step = DeviceStep(mesh, part, op, cpg, coef_h, dK_h, seed=rank, library=bool(args.library_exchange))
     nnz = step.nnz
