@@ -264,6 +264,19 @@ size_t smem_budget_of(const adfem_mesh* m, int nc, bool adjoint = false) {
   return 110 * 1024;
 }
 
+// device copy of the slot -> nnz map (SoA [d*d][ne]) for k_csr_adj_gather, built on first use
+int ensure_dev_slot_nnz(adfem_mesh* m) {
+  if (m->dpat.slot_nnz) return 0;
+  const HostMesh& h = m->hm;
+  const int dd = h.d * h.d;
+  std::vector<uint32_t> soa((size_t)h.ne * dd);
+  for (int e = 0; e < h.ne; e++)
+    for (int s = 0; s < dd; s++) soa[(size_t)s * h.ne + e] = m->pat.slot_nnz[(size_t)e * dd + s];
+  CU_TRY(upload(m->d_slot_nnz, soa));
+  m->dpat.slot_nnz = m->d_slot_nnz.p;
+  return 0;
+}
+
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
   std::string err = m->pat.build(m->hm, nthreads_of(m));
@@ -289,12 +302,9 @@ int ensure_pattern(adfem_mesh* m) {
     CU_TRY(upload(m->d_adj_ptr, m->pat.adj_ptr));
     CU_TRY(upload(m->d_adj_elem, m->pat.adj_elem));
     CU_TRY(upload(m->d_adj_loc, m->pat.adj_loc));
-    std::vector<uint32_t> soa((size_t)h.ne * dd);
-    for (int e = 0; e < h.ne; e++)
-      for (int s = 0; s < dd; s++) soa[(size_t)s * h.ne + e] = m->pat.slot_nnz[(size_t)e * dd + s];
-    CU_TRY(upload(m->d_slot_nnz, soa));
+    (void)dd;       // the slot -> nnz map goes to the device only when the direct-gather adjoint needs it (ensure_dev_slot_nnz): 4 d^2 bytes per element
     m->dpat.n = m->pat.n; m->dpat.nnz = m->pat.nnz;
-    m->dpat.rowptr = m->d_rowptr.p; m->dpat.colind = m->d_colind.p; m->dpat.slot_nnz = m->d_slot_nnz.p;
+    m->dpat.rowptr = m->d_rowptr.p; m->dpat.colind = m->d_colind.p; m->dpat.slot_nnz = nullptr;
   }
   return 0;
 }
@@ -498,6 +508,7 @@ int launch_adj(adfem_mesh* m, const double* dvals, double* grad, cudaStream_t st
     if (int rc = tile_grid(m, kern, tile_threads_of(m, NC), smem, P->dev.ntiles, &grid)) return rc;
     kern<<<grid, tile_threads_of(m, NC), smem, st>>>(presum ? dev_mesh_presum(m, m->opt_area_csr) : dev_mesh(m, m->opt_area_csr), m->pat.nnz, P->dev, dvals, grad);
   } else {
+    if (int rc = ensure_dev_slot_nnz(m)) return rc;
     k_csr_adj_gather<DIM, DEG, OP><<<blocks_for(m->hm.ne, 128), 128, 0, st>>>(presum ? dev_mesh_presum(m, m->opt_area_csr) : dev_mesh(m, m->opt_area_csr), m->dpat, dvals, grad);
   }
   CU_TRY(cudaGetLastError());
