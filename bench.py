@@ -524,7 +524,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="2", choices=["2", "3", "4", "4l", "4m", "4o", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
+    ap.add_argument("--config", default="2", choices=["2", "2m", "3", "4", "4l", "4m", "4o", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
     ap.add_argument("--extra-configs", default="2m,3,4,4o,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
     ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the edge counts of configs 3-5 (smoke runs)")
@@ -675,6 +675,8 @@ def main():
         # the structured-mesh kernels take connectivity and coordinates as index arithmetic (they are implicit inputs of
         # Mesh(m,n,h)), so their compulsory streams are the coefficients and the values only: 8*g + 8*nnz/E per element
         bf = ba = 8 * 3 + 8 * nnz / E
+    elif case == "2m":
+        bf = ba = b_general - 12           # mapped grid: the connectivity is index arithmetic, coordinates + coefficients + values move
     else:
         bf = ba = b_general
     key = case if (case != "2" or structured) else "2g"

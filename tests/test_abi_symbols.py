@@ -22,6 +22,27 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_reference_side_bindings_name_real_symbols():
+    """julia/AdFemCUDA.jl (ccall) and integration/tf_ops/FemLaplaceScalar.cpp (the TF op shell) cannot be executed here (no Julia, no
+    TensorFlow): check at least that every library symbol they bind is exported, and with the argument count the header declares."""
+    L = A._lib.lib()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "adfem_cuda.h")).read(), flags=re.S)
+    nargs = {}
+    for name, args in re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(([^;{}]*)\)\s*;", hdr):
+        nargs[name] = 0 if args.strip() in ("", "void") else args.count(",") + 1
+    jl = open(os.path.join(ROOT, "julia", "AdFemCUDA.jl")).read()
+    calls = re.findall(r"ccall\(\(:(\w+), LIB\[\]\),\s*\w+,\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 15
+    for name, argtypes in calls:
+        assert hasattr(L, name), name
+        n = len([a for a in argtypes.split(",") if a.strip()])
+        assert n == nargs[name], (name, n, nargs[name])
+    cpp = open(os.path.join(ROOT, "integration", "tf_ops", "FemLaplaceScalar.cpp")).read()
+    for name in ("FemLaplaceScalar_forward", "FemLaplaceScalar_backward", "mfem_get_ngauss", "mfem_get_elem_ndof"):
+        assert name + "(" in cpp and hasattr(L, name)
+    assert 'REGISTER_OP("FemLaplaceScalar")' in cpp and 'REGISTER_OP("FemLaplaceScalarGrad")' in cpp      # the names ADCME's load_op_and_grad looks up
+
+
 def test_error_reporting_without_gpu():
     L = A._lib.lib()
     if L.adfem_device_count() == 0:
