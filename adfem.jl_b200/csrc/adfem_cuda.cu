@@ -563,7 +563,7 @@ template <int OP> int launch_grid_adj(adfem_mesh* m, const double* dvals, double
 }
 
 // P1 elasticity on the structured triangulation (grid_elast.cuh): ~8 waves of resident warps, like the scalar kernels
-bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid(m) && m->hm.degree == 1 && m->hm.g == GE_G; }
+bool use_grid_elast(adfem_mesh* m, int op) { return op == ADFEM_OP_STIFFNESS && m->opt_grid_elast && use_grid_any(m) && m->hm.degree == 1 && m->hm.g == GE_G; }
 // plane_mode < 0: tangents H in / dH out (in = H or dvals, out = vals or grad_H).  plane_mode = 0 | 1: fused constitutive step — forward
 // (in = E, in2 = nu) -> out = vals; adjoint (in = dvals; E, nu) -> out = dE, out2 = dnu.
 int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out, cudaStream_t st, int plane_mode = -1, const double* E = nullptr,
@@ -583,12 +583,13 @@ int launch_grid_elast(adfem_mesh* m, bool adjoint, const double* in, double* out
   const unsigned blocks = (unsigned)((warps + GE_WARPS - 1) / GE_WARPS);
   const DevMesh dm = dev_mesh(m, m->opt_area_csr);
   const bool plane = plane_mode >= 0;
+  const bool mp = m->grid_mapped;      // node positions from the coordinate array (structured connectivity on a mapped / jittered grid)
   if (adjoint) {
-    auto kern = plane ? k_grid_elast_adj<true> : k_grid_elast_adj<false>;
+    auto kern = plane ? (mp ? k_grid_elast_adj<true, true> : k_grid_elast_adj<true, false>) : (mp ? k_grid_elast_adj<false, true> : k_grid_elast_adj<false, false>);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, GE_WARPS * 32, smem, st>>>(dm, gt, m->pat.nnz, rpw, plane_mode, E, nu, in, out, out2);
   } else {
-    auto kern = plane ? k_grid_elast_fwd<true> : k_grid_elast_fwd<false>;
+    auto kern = plane ? (mp ? k_grid_elast_fwd<true, true> : k_grid_elast_fwd<true, false>) : (mp ? k_grid_elast_fwd<false, true> : k_grid_elast_fwd<false, false>);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, GE_WARPS * 32, smem, st>>>(dm, gt, m->pat.nnz, rpw, plane_mode, plane ? E : in, nu, out);
   }

@@ -103,7 +103,10 @@ ADFEM_HD void ge_add_triangle(const double* Hb, double2 v0, double2 v1, double2 
 
 // phase 2: node (i, j0 + lane).  Pattern slots: 0 (i-1,j)  1 (i-1,j+1)  2 (i,j-1)  3 (i,j)  4 (i,j+1)  5 (i+1,j-1)  6 (i+1,j).
 // P / C = tangents of cell rows i-1 / i (ge_load_cell_row).  Writes stage[a*GE_STAGE + 2*o + b*len + pos].
-ADFEM_HD void ge_node(int lane, int heron, const GridTri& gt, int i, int j0, const double* P, const double* C, double* stage) {
+// MAPPED (structured connectivity on arbitrary node positions): the positions of the seven stencil nodes come from the coordinate array `xy`
+// ([node][2]) instead of the axis tables.
+template <bool MAPPED = false>
+ADFEM_HD void ge_node(int lane, int heron, const GridTri& gt, int i, int j0, const double* P, const double* C, double* stage, const double* xy = nullptr) {
   const int m = gt.m, n = gt.n, jn = j0 + lane;
   if (jn > m) return;
   const int A = i > 0, B = i < n, jl = jn > 0, jr = jn < m;
@@ -112,6 +115,28 @@ ADFEM_HD void ge_node(int lane, int heron, const GridTri& gt, int i, int j0, con
   for (int s = 0; s < 7; s++)
 #pragma unroll
     for (int ab = 0; ab < 4; ab++) acc[s][ab] = 0.0;
+  if constexpr (MAPPED) {
+    auto Pt = [&](int di, int dj) { const double* p = xy + 2 * ((size_t)(i + di) * (m + 1) + (jn + dj)); return make_double2(ldg(p), ldg(p + 1)); };
+    const double2 pc = Pt(0, 0);
+    if (A) {                                                 // cell row i-1
+      const double2 pd = Pt(-1, 0);
+      if (jl) ge_add_triangle<2, 2, 0, 3>(P + (2 * lane + 1) * 9, Pt(0, -1), pd, pc, heron, acc);                                                     // T1(i-1, j-1) = [TL BR TR], node = TR
+      if (jr) {
+        const double2 pdr = Pt(-1, 1);
+        ge_add_triangle<2, 0, 1, 3>(P + (2 * lane + 2) * 9, pd, pdr, pc, heron, acc);                                                                   // T0(i-1, j)   = [BL BR TL], node = TL
+        ge_add_triangle<0, 3, 1, 4>(P + (2 * lane + 3) * 9, pc, pdr, Pt(0, 1), heron, acc);                                                             // T1(i-1, j)   = [TL BR TR], node = TL
+      }
+    }
+    if (B) {                                                 // cell row i
+      const double2 pu = Pt(1, 0);
+      if (jl) {
+        const double2 pl = Pt(0, -1), pul = Pt(1, -1);
+        ge_add_triangle<1, 2, 3, 5>(C + (2 * lane) * 9, pl, pc, pul, heron, acc);                                                                       // T0(i, j-1)   = [BL BR TL], node = BR
+        ge_add_triangle<1, 5, 3, 6>(C + (2 * lane + 1) * 9, pul, pc, pu, heron, acc);                                                                   // T1(i, j-1)   = [TL BR TR], node = BR
+      }
+      if (jr) ge_add_triangle<0, 3, 4, 6>(C + (2 * lane + 2) * 9, pc, Pt(0, 1), pu, heron, acc);                                                       // T0(i, j)     = [BL BR TL], node = BL
+    }
+  } else {
   const double xc = ldg(gt.xs + jn), xl = jl ? ldg(gt.xs + jn - 1) : 0.0, xr = jr ? ldg(gt.xs + jn + 1) : 0.0;
   const double yc = ldg(gt.ys + i);
   if (A) {                                                   // cell row i-1: this node is on its top side
@@ -129,6 +154,7 @@ ADFEM_HD void ge_node(int lane, int heron, const GridTri& gt, int i, int j0, con
       ge_add_triangle<1, 5, 3, 6>(C + (2 * lane + 1) * 9, make_double2(xl, yu), make_double2(xc, yc), make_double2(xc, yu), heron, acc);               // T1(i, j-1)   = [TL BR TR], node = BR
     }
     if (jr) ge_add_triangle<0, 3, 4, 6>(C + (2 * lane + 2) * 9, make_double2(xc, yc), make_double2(xr, yc), make_double2(xc, yu), heron, acc);         // T0(i, j)     = [BL BR TL], node = BL
+  }
   }
   const int ex[7] = {A, A && jr, jl, 1, jr, B && jl, B};
   const int len = ex[0] + ex[1] + ex[2] + 1 + ex[4] + ex[5] + ex[6];
@@ -208,17 +234,27 @@ ADFEM_HD void ge_triangle_adjoint(const double* lo, const double* hi, int m, int
 }
 
 // phase 2: both triangles of cell (ci, c0 + lane) -> gst[(2*lane + t)*9 + c]
-ADFEM_HD void ge_cell_adjoint(int lane, int heron, const GridTri& gt, int ci, int c0, const double* lo, const double* hi, double* gst) {
+template <bool MAPPED = false>
+ADFEM_HD void ge_cell_adjoint(int lane, int heron, const GridTri& gt, int ci, int c0, const double* lo, const double* hi, double* gst, const double* xy = nullptr) {
   const int m = gt.m, n = gt.n, cc = c0 + lane;
   if (cc >= m) return;
-  const double x0 = ldg(gt.xs + cc), x1 = ldg(gt.xs + cc + 1), y0 = ldg(gt.ys + ci), y1 = ldg(gt.ys + ci + 1);
+  double2 BL, BR, TL, TR;
+  if constexpr (MAPPED) {
+    const double* p0 = xy + 2 * ((size_t)ci * (m + 1) + cc);
+    const double* p1 = xy + 2 * ((size_t)(ci + 1) * (m + 1) + cc);
+    BL = make_double2(ldg(p0), ldg(p0 + 1)); BR = make_double2(ldg(p0 + 2), ldg(p0 + 3));
+    TL = make_double2(ldg(p1), ldg(p1 + 1)); TR = make_double2(ldg(p1 + 2), ldg(p1 + 3));
+  } else {
+    const double x0 = ldg(gt.xs + cc), x1 = ldg(gt.xs + cc + 1), y0 = ldg(gt.ys + ci), y1 = ldg(gt.ys + ci + 1);
+    BL = make_double2(x0, y0); BR = make_double2(x1, y0); TL = make_double2(x0, y1); TR = make_double2(x1, y1);
+  }
   {                                                          // T0 = [BL BR TL]
     const int iv[3] = {ci, ci, ci + 1}, jv[3] = {cc, cc + 1, cc};
-    ge_triangle_adjoint(lo, hi, m, n, c0, ci, iv, jv, make_double2(x0, y0), make_double2(x1, y0), make_double2(x0, y1), heron, gst + (2 * lane) * 9);
+    ge_triangle_adjoint(lo, hi, m, n, c0, ci, iv, jv, BL, BR, TL, heron, gst + (2 * lane) * 9);
   }
   {                                                          // T1 = [TL BR TR]
     const int iv[3] = {ci + 1, ci, ci + 1}, jv[3] = {cc, cc + 1, cc + 1};
-    ge_triangle_adjoint(lo, hi, m, n, c0, ci, iv, jv, make_double2(x0, y1), make_double2(x1, y0), make_double2(x1, y1), heron, gst + (2 * lane + 1) * 9);
+    ge_triangle_adjoint(lo, hi, m, n, c0, ci, iv, jv, TL, BR, TR, heron, gst + (2 * lane + 1) * 9);
   }
 }
 
@@ -257,7 +293,7 @@ __device__ __forceinline__ void ge_prefetch_run(int lane, const double* p, long 
 
 // Forward kernel: node rows [0, n], strips of 32 node columns; a warp handles `rows_per_warp` consecutive node rows of one strip.
 // PLANE: the tangents come from the moduli (coef = E, coef2 = nu, mode = 0 | 1) instead of from H (coef).
-template <bool PLANE>
+template <bool PLANE, bool MAPPED = false>
 __global__ void __launch_bounds__(GE_WARPS * 32, 3) k_grid_elast_fwd(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
                                                                   const double* __restrict__ coef, const double* __restrict__ coef2, double* __restrict__ vals) {
   extern __shared__ __align__(16) double ge_smem[];
@@ -286,7 +322,7 @@ __global__ void __launch_bounds__(GE_WARPS * 32, 3) k_grid_elast_fwd(DevMesh dm,
       if (PLANE) ge_prefetch_run(lane, coef2 + off, (long long)(pc1 - pc0) * per_cell);
     }
     __syncwarp();
-    ge_node(lane, dm.heron, gt, i, j0, P, C, stage);
+    ge_node<MAPPED>(lane, dm.heron, gt, i, j0, P, C, stage, dm.coords);
     __syncwarp();
     ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
     __syncwarp();
@@ -297,7 +333,7 @@ __global__ void __launch_bounds__(GE_WARPS * 32, 3) k_grid_elast_fwd(DevMesh dm,
 
 // Adjoint kernel: cell rows [0, n), strips of 32 cell columns; a warp handles `rows_per_warp` consecutive cell rows of one strip.
 // PLANE: gradients with respect to the moduli (E, nu in; grad = dE, grad2 = dnu) instead of with respect to H.
-template <bool PLANE>
+template <bool PLANE, bool MAPPED = false>
 __global__ void __launch_bounds__(GE_WARPS * 32, 2) k_grid_elast_adj(DevMesh dm, GridTri gt, long long nnz, int rows_per_warp, int mode,
                                                                   const double* __restrict__ E, const double* __restrict__ nu,
                                                                   const double* __restrict__ dvals, double* __restrict__ grad, double* __restrict__ grad2) {
@@ -324,7 +360,7 @@ __global__ void __launch_bounds__(GE_WARPS * 32, 2) k_grid_elast_adj(DevMesh dm,
       ge_prefetch_run(lane, dvals + 2 * (nnz + rb2 + pb), cnt);
     }
     __syncwarp();
-    ge_cell_adjoint(lane, dm.heron, gt, ci, c0, lo, hi, gst);
+    ge_cell_adjoint<MAPPED>(lane, dm.heron, gt, ci, c0, lo, hi, gst, dm.coords);
     __syncwarp();
     if constexpr (PLANE) ge_store_cell_row_plane<GE_G>(lane, dm.rule, m, ci, c0, mode, E, nu, gst, grad, grad2);
     else ge_store_cell_row<GE_G>(lane, dm.rule, m, ci, c0, gst, grad);

@@ -216,6 +216,7 @@ CASE_KERNELS = {          # (forward kernels, adjoint kernels) of the default pa
     "2g": (["k_tile_fwd<2,1,LAPLACE,1,0>"], ["k_tile_adj<2,1,LAPLACE>"]),
     "2m": (["k_grid_fwd<LAPLACE,MAPPED>"], ["k_grid_adj<LAPLACE,MAPPED>"]),
     "3": (["k_grid_elast_fwd<LAPLACE>"], ["k_grid_elast_adj<LAPLACE>"]),
+    "3m": (["k_grid_elast_fwd<MAPPED>"], ["k_grid_elast_adj<MAPPED>"]),
     "4l": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
     "4o": (["k_tile_fwd<2,2,LAPLACE,0,1>"], ["k_tile_adj<2,2,LAPLACE>"]),
@@ -246,6 +247,15 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
         coords = np.stack([coords[:, 0] + 0.02 * np.sin(3.0 * coords[:, 1]), coords[:, 1] + 0.02 * np.cos(2.0 * coords[:, 0])], 1) + rng.uniform(-0.2 / n, 0.2 / n, coords.shape)
         note = f"config 2 connectivity, Mesh({n},{n},1/{n}), on mapped + jittered node positions (structured kernels, positions from the coordinate array)"
         return A.Mesh(coords, elems, **kw), None, 0, 1, note, "weak"
+    if case == "3m":
+        # config 3's connectivity on mapped + jittered node positions (MAPPED instantiations of the structured elasticity kernels)
+        import numpy as np
+        m, nl = max(4, int(4096 * scale)), max(2, int(2048 * scale))
+        coords, elems = meshgen.tri_grid(m, nl, 1.0 / m)
+        rng = np.random.default_rng(4)
+        coords = np.stack([coords[:, 0] + 0.02 * np.sin(3.0 * coords[:, 1]), coords[:, 1] + 0.02 * np.cos(2.0 * coords[:, 0])], 1) + rng.uniform(-0.2 / m, 0.2 / m, coords.shape)
+        note = f"config 3 connectivity, Mesh({m},{nl},1/{m}), on mapped + jittered node positions (structured elasticity kernels, positions from the coordinate array)"
+        return A.Mesh(coords, elems, **kw), None, 2, 9, note, "weak"
     if case == "3":
         m, nl = max(4, int(4096 * scale)), max(2, int(2048 * scale))
         note = f"config 3: P1 linear elasticity, per-Gauss-point 3x3 tangent H, Mesh({m},{nl},1/{m}) per GPU ({2 * m * nl} triangles)"
@@ -487,7 +497,7 @@ def case_records(case, rank, world, steps, warmup, scale, peak, traffic, library
         xa_ms = step.exchange_alone_ms()
         E = mesh.nelem
         b = alg_bytes_per_elem(mesh, step.nnz, cpg)
-        if case == "2m":
+        if case in ("2m", "3m"):
             b -= 4 * mesh.elem_ndof        # structured connectivity is index arithmetic: coordinates (8 B), coefficients (24 B) and values (28 B) per element are what moves
         cnt = torch.tensor([float(E), float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0, b * E], dtype=torch.float64, device="cuda")
         mx = torch.tensor([float(E)], dtype=torch.float64, device="cuda")
@@ -524,8 +534,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="2", choices=["2", "2m", "3", "4", "4l", "4m", "4o", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
-    ap.add_argument("--extra-configs", default="2m,3,4,4o,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
+    ap.add_argument("--config", default="2", choices=["2", "2m", "3", "3m", "4", "4l", "4m", "4o", "5"], help="BASELINE config of the headline line (default 2, the metric's config)")
+    ap.add_argument("--extra-configs", default="2m,3,3m,4,4o,5", help="comma list of the other configs timed into extra.configs ('none' to skip)")
     ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the edge counts of configs 3-5 (smoke runs)")
     ap.add_argument("--numbering", default="random", choices=["random", "generator"], help="config 4: node / element numbering of the synthetic unstructured mesh")
@@ -653,7 +663,7 @@ def main():
     nnode = mesh.nnode
     b_general = alg_bytes_per_elem(mesh, nnz, cpg)
     ibytes = float(part.interface_bytes * step.nc * step.nc) if part is not None else 0.0
-    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m")) and not (c in ("2m", "4o") and world > 1)]
+    xc = [c for c in args.extra_configs.split(",") if c and c != "none" and c != case and not (c == "4" and case in ("4l", "4m")) and not (c in ("2m", "3m", "4o") and world > 1)]
     if xc:
         del step, part, mesh
         torch.cuda.empty_cache()
@@ -675,7 +685,7 @@ def main():
         # the structured-mesh kernels take connectivity and coordinates as index arithmetic (they are implicit inputs of
         # Mesh(m,n,h)), so their compulsory streams are the coefficients and the values only: 8*g + 8*nnz/E per element
         bf = ba = 8 * 3 + 8 * nnz / E
-    elif case == "2m":
+    elif case in ("2m", "3m"):
         bf = ba = b_general - 12           # mapped grid: the connectivity is index arithmetic, coordinates + coefficients + values move
     else:
         bf = ba = b_general
@@ -710,7 +720,7 @@ def main():
                          f"{ne_cpu} triangles (a row slab of the config-2 mesh), best of 3, {threads} host threads over element blocks",
                "single_thread_value": ne_cpu / min(single) / 1e6,
                "single_thread_note": "the reference op as it is (no threading), same sample, one pass"}
-    launches = {"2": 2, "2g": 2, "2m": 2, "3": 2, "4": 2, "4l": 2, "4m": 2, "4o": 2, "5": 3}[key] + (4 if world > 1 else 0)
+    launches = {"2": 2, "2g": 2, "2m": 2, "3": 2, "3m": 2, "4": 2, "4l": 2, "4m": 2, "4o": 2, "5": 3}[key] + (4 if world > 1 else 0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": note, "elements_per_gpu": E, "nodes_per_gpu": nnode, "nnz_per_gpu": nnz, "gauss_points_per_gpu": G,

@@ -226,8 +226,9 @@ int emul_expand_plane_grad(int order, long long ne, int mode, const double* E, c
 
 // structured P1 elasticity (grid_elast.cuh): every warp of k_grid_elast_fwd / k_grid_elast_adj as three loops over its 32 lanes per row
 // plane_mode < 0: coef = H; plane_mode = 0 | 1: coef = E, coef2 = nu (fused constitutive step)
-int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
-                        double* vals, int plane_mode, const double* coef2) {
+// xy != nullptr: MAPPED instantiation (node positions from the coordinate array [node][2]; xs / ys are not read)
+static int emul_grid_elast_fwd_impl(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
+                                    double* vals, int plane_mode, const double* coef2, const double* xy) {
   QuadRule rule;
   if (!triangle_rule(order, rule) || rule.n != GE_G) return 1;
   const GridTri gt{m, n, xs, ys};
@@ -246,7 +247,8 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
     long long rowbase = grid_rowptr(i0, 0, m, n);
     for (int i = i0; i < i1; i++) {
       EMUL_LANES(lane) load(lane, i, C);
-      EMUL_LANES(lane) ge_node(lane, heron, gt, i, j0, P, C, stage);
+      if (xy) { EMUL_LANES(lane) ge_node<true>(lane, heron, gt, i, j0, P, C, stage, xy); }
+      else { EMUL_LANES(lane) ge_node(lane, heron, gt, i, j0, P, C, stage); }
       EMUL_LANES(lane) ge_store_node_row(lane, m, n, i, j0, rowbase, nnz, stage, vals);
       rowbase += ge_prefix(m + 1, m, i > 0, i < n);
       double* t = P; P = C; C = t;
@@ -254,8 +256,15 @@ int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int or
   }
   return 0;
 }
-int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
-                        double* grad, int plane_mode, const double* E, const double* nu, double* grad2) {
+int emul_grid_elast_fwd(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* coef,
+                        double* vals, int plane_mode, const double* coef2) {
+  return emul_grid_elast_fwd_impl(m, n, xs, ys, order, heron, rows_per_warp, nnz, coef, vals, plane_mode, coef2, nullptr);
+}
+int emul_grid_elast_fwd_mapped(int m, int n, const double* xy, int order, int heron, int rows_per_warp, long long nnz, const double* coef, double* vals) {
+  return emul_grid_elast_fwd_impl(m, n, nullptr, nullptr, order, heron, rows_per_warp, nnz, coef, vals, -1, nullptr, xy);
+}
+static int emul_grid_elast_adj_impl(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
+                                    double* grad, int plane_mode, const double* E, const double* nu, double* grad2, const double* xy) {
   QuadRule rule;
   if (!triangle_rule(order, rule) || rule.n != GE_G) return 1;
   const GridTri gt{m, n, xs, ys};
@@ -271,7 +280,8 @@ int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int or
     for (int ci = r0; ci < r1; ci++) {
       rowbase += ge_prefix(m + 1, m, ci > 0, ci < n);
       EMUL_LANES(lane) ge_load_node_row(lane, m, n, ci + 1, c0, rowbase, nnz, dvals, hi);
-      EMUL_LANES(lane) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst);
+      if (xy) { EMUL_LANES(lane) ge_cell_adjoint<true>(lane, heron, gt, ci, c0, lo, hi, gst, xy); }
+      else { EMUL_LANES(lane) ge_cell_adjoint(lane, heron, gt, ci, c0, lo, hi, gst); }
       EMUL_LANES(lane) {
         if (plane_mode >= 0) ge_store_cell_row_plane<GE_G>(lane, rule, m, ci, c0, plane_mode, E, nu, gst, grad, grad2);
         else ge_store_cell_row<GE_G>(lane, rule, m, ci, c0, gst, grad);
@@ -280,6 +290,14 @@ int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int or
     }
   }
   return 0;
+}
+
+int emul_grid_elast_adj(int m, int n, const double* xs, const double* ys, int order, int heron, int rows_per_warp, long long nnz, const double* dvals,
+                        double* grad, int plane_mode, const double* E, const double* nu, double* grad2) {
+  return emul_grid_elast_adj_impl(m, n, xs, ys, order, heron, rows_per_warp, nnz, dvals, grad, plane_mode, E, nu, grad2, nullptr);
+}
+int emul_grid_elast_adj_mapped(int m, int n, const double* xy, int order, int heron, int rows_per_warp, long long nnz, const double* dvals, double* grad) {
+  return emul_grid_elast_adj_impl(m, n, nullptr, nullptr, order, heron, rows_per_warp, nnz, dvals, grad, -1, nullptr, nullptr, nullptr, xy);
 }
 
 // structured scatter-type Gauss-point operators (grid_gauss.cuh): k_grid_gp_scatter / k_grid_laplace_term of gauss_ops.cu

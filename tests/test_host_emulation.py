@@ -323,6 +323,33 @@ def test_structured_elasticity_warp_phases(emul, oracle, m, n, rpw, heron):
         close(gE, rE, rel=1e-11); close(gnu, rnu, rel=1e-11)
 
 
+@pytest.mark.parametrize("m,n,rpw,heron", [(5, 4, 3, 0), (1, 1, 8, 1), (33, 3, 2, 0), (70, 9, 4, 1)])
+def test_structured_elasticity_warp_phases_mapped_grid(emul, oracle, m, n, rpw, heron):
+    """The MAPPED instantiation of the same phases: structured connectivity on smoothly mapped + jittered node positions, the seven stencil
+    positions read from the coordinate array; against the canonical CSR of the oracle's stiffness op and its adjoint."""
+    rng = np.random.default_rng(m * 100 + n + 7)
+    c, e = meshgen.tri_grid(m, n, 1.0)
+    x, y = c[:, 0], c[:, 1]
+    c = np.stack([x + 0.08 * np.sin(0.7 * y), y + 0.06 * np.cos(0.9 * x)], 1) + rng.uniform(-0.1, 0.1, c.shape)
+    c = np.ascontiguousarray(c)
+    o = oracle.Mesh2D(c, e)
+    assert np.array_equal(o.elems, oracle.Mesh2D(*meshgen.tri_grid(m, n, 1.0)).elems)       # no triangle flipped: same connectivity after the orientation fix
+    N2 = 2 * o.ndof
+    H = rng.random(o.ngauss * 9) + 0.1
+    ind, vv = o.stiffness_fwd(H)
+    rp, ci, ref = oracle.canonical_csr(ind, vv, N2)
+    nnz_s = len(ref) // 4
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    vals = np.full(len(ref), np.nan)
+    assert emul.emul_grid_elast_fwd_mapped(C.c_int(m), C.c_int(n), d(c), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(H), d(vals)) == 0
+    close(vals, ref, rel=1e-12)
+    dv = rng.standard_normal(len(ref))
+    expect = o.stiffness_bwd(oracle.csr_adjoint_to_slots(rp, ci, dv, ind, N2))
+    grad = np.full(o.ngauss * 9, np.nan)
+    assert emul.emul_grid_elast_adj_mapped(C.c_int(m), C.c_int(n), d(c), C.c_int(2), C.c_int(heron), C.c_int(rpw), C.c_longlong(nnz_s), d(dv), d(grad)) == 0
+    close(grad, expect, rel=1e-12)
+
+
 @pytest.mark.parametrize("m,n", [(5, 4), (1, 1), (9, 2)])
 def test_structured_scatter_operators(emul, oracle, m, n):
     """grid_gauss.cuh: the scatter-type operators on Mesh(m, n, h) as one thread per node with index arithmetic — against the oracle, and

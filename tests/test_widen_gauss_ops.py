@@ -281,13 +281,18 @@ def test_fused_plane_stiffness(oracle, plane, mode):
         A.compute_fem_stiffness_matrix_from_moduli(dev(np.ones(m2.ngauss)), dev(np.full(m2.ngauss, 0.3)), m2)
 
 
+@pytest.mark.parametrize("mapped", [False, True])
 @pytest.mark.parametrize("m,n", [(37, 29), (5, 3), (130, 21)])
-def test_structured_elasticity_kernels(oracle, m, n):
+def test_structured_elasticity_kernels(oracle, m, n, mapped):
     """Option "structured_elasticity": index-free P1 elasticity kernels (csrc/grid_elast.cuh) on Mesh(m, n, h) against the oracle and against
-    the general tile kernels, several rows-per-warp settings (one or many chunks), both area formulas."""
+    the general tile kernels, several rows-per-warp settings (one or many chunks), both area formulas; `mapped`: the same connectivity on
+    smoothly mapped + jittered node positions (MAPPED instantiations, positions from the coordinate array)."""
     rng = np.random.default_rng(m + n)
-    ms, o = A.Mesh(m, n, 0.05), oracle.Mesh2D(*meshgen.tri_grid(m, n, 0.05))
-    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == 1
+    c, e = meshgen.tri_grid(m, n, 0.05)
+    if mapped:
+        c = np.stack([c[:, 0] + 0.004 * np.sin(14.0 * c[:, 1]), c[:, 1] + 0.003 * np.cos(18.0 * c[:, 0])], 1) + rng.uniform(-0.005, 0.005, c.shape)
+    ms, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == (3 if mapped else 1)
     N2 = 2 * o.ndof
     H = rng.random((o.ngauss, 3, 3)) + 0.1
     ind, vv = o.stiffness_fwd(H.reshape(-1))
