@@ -361,9 +361,14 @@ class DeviceStep:
         self.dghost = None
         if part is not None:
             if library:
-                part.use_library()
+                try:
+                    part.use_library()
+                except Exception as ex:        # e.g. libnccl.so.2 cannot be bound: keep measuring, through torch.distributed, and say so
+                    library = False
+                    self.exchange_note = "library exchange unavailable (%s: %s)" % (type(ex).__name__, str(ex)[:120])
             self.dghost = torch.zeros(len(part.ghost_idx) * self.nc * self.nc, dtype=torch.float64, device="cuda")
-        self.exchange = None if part is None else ("library (adfem_dist_*: pack kernel, ncclSend/ncclRecv group, deterministic unpack)" if library else "torch.distributed all_to_all_single")
+        self.exchange = None if part is None else ("library (adfem_dist_*: pack kernel, ncclSend/ncclRecv group, deterministic unpack)" if library else
+                                                   "torch.distributed all_to_all_single" + ("; " + self.exchange_note if getattr(self, "exchange_note", None) else ""))
 
     def forward(self):
         self._lib.check(self.L.adfem_assemble_csr(self.mesh.handle, self.op, self.p[0], self.p[1], self.st))
