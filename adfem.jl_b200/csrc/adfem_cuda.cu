@@ -528,7 +528,7 @@ int ensure_host_streams(adfem_mesh* m) {
 }
 
 bool use_grid_any(adfem_mesh* m) { return m->grid_ok && m->opt_structured && !m->host_only; }      // scalar CSR operators and source term: rectilinear or mapped
-bool use_grid(adfem_mesh* m) { return use_grid_any(m) && !m->grid_mapped; }                        // everything else: rectilinear only
+bool use_grid(adfem_mesh* m) { return use_grid_any(m) && !m->grid_mapped; }                        // rectilinear only (no caller left: every structured kernel has a MAPPED form)
 
 int grid_rows_per_warp(adfem_mesh* m, int strips, int rows) {
   if (m->opt_grid_rows > 0) return m->opt_grid_rows;
@@ -1157,8 +1157,9 @@ int gp_apply(adfem_mesh* m, const GpKind& k, bool to_gauss, const double* in, do
   if (to_gauss) return launch_gp_gather(dev_mesh(m, m->opt_area_coo), m->hm.degree, k.basis, k.weighted, in, out, st);
   if (int rc = ensure_pattern(m)) return rc;
   if (use_tet_gauss(m)) return launch_tet_gp_scatter(dev_mesh(m, m->opt_area_coo), grid_tet_of(m), k.basis, k.weighted, in, out, st);
-  if (use_grid(m) && m->hm.degree == 1)      // structured triangulation: index arithmetic instead of the adjacency (grid_gauss.cuh)
-    return launch_grid_gp_scatter(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, k.basis, k.weighted, in, out, st);
+  if (use_grid_any(m) && m->hm.degree == 1)      // structured triangulation (rectilinear or mapped): index arithmetic instead of the adjacency (grid_gauss.cuh)
+    return launch_grid_gp_scatter(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, k.basis, k.weighted, in, out, st,
+                                  m->grid_mapped ? m->coords.p : nullptr);
   return launch_gp_scatter(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), k.basis, k.weighted, in, out, st);
 }
 }  // namespace
@@ -1195,8 +1196,9 @@ int adfem_laplace_term(adfem_mesh* m, const double* nu, const double* u, double*
   if (int rc = need_device(m)) return rc;
   if (int rc = ensure_pattern(m)) return rc;
   if (use_tet_gauss(m)) return launch_tet_laplace_term(dev_mesh(m, m->opt_area_coo), grid_tet_of(m), nu, u, out, (cudaStream_t)stream);
-  if (use_grid(m) && m->hm.degree == 1)
-    return launch_grid_laplace_term(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, u, out, (cudaStream_t)stream);
+  if (use_grid_any(m) && m->hm.degree == 1)
+    return launch_grid_laplace_term(dev_mesh(m, m->opt_area_coo), GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, u, out, (cudaStream_t)stream,
+                                    m->grid_mapped ? m->coords.p : nullptr);
   return launch_laplace_term(dev_mesh(m, m->opt_area_coo), m->hm.degree, dof_adjacency(m), nu, u, out, (cudaStream_t)stream);
 }
 
@@ -1210,8 +1212,9 @@ int adfem_laplace_term_adjoint(adfem_mesh* m, const double* nu, const double* u,
   if (grad_u) {
     if (use_tet_gauss(m)) {
       if (int rc = launch_tet_laplace_term(dm, grid_tet_of(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
-    } else if (use_grid(m) && m->hm.degree == 1) {
-      if (int rc = launch_grid_laplace_term(dm, GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
+    } else if (use_grid_any(m) && m->hm.degree == 1) {
+      if (int rc = launch_grid_laplace_term(dm, GridTri{m->grid_m, m->grid_n, m->grid_xs.p, m->grid_ys.p}, nu, grad_out, grad_u, (cudaStream_t)stream,
+                                            m->grid_mapped ? m->coords.p : nullptr)) return rc;
     } else {
       if (int rc = launch_laplace_term(dm, m->hm.degree, dof_adjacency(m), nu, grad_out, grad_u, (cudaStream_t)stream)) return rc;
     }

@@ -60,19 +60,19 @@ __global__ void k_plane_matrix_grad(int mode, long long n, const double* __restr
 
 // structured triangulation: one thread per node, node id = i*(m+1) + j
 template <int B, bool W>
-__global__ void __launch_bounds__(GP_THREADS) k_grid_gp_scatter(DevMesh m, GridTri gt, const double* __restrict__ in, double* __restrict__ out) {
+__global__ void __launch_bounds__(GP_THREADS) k_grid_gp_scatter(DevMesh m, GridTri gt, const double* __restrict__ xy, const double* __restrict__ in, double* __restrict__ out) {
   constexpr int NC = GpShape<2, 1, B>::NC;
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, nn = (long long)(gt.m + 1) * (gt.n + 1);
   if (r >= nn) return;
   double acc[NC];
-  grid_scatter_node<B, W>(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), in, acc);
+  grid_scatter_node<B, W>(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), in, acc, xy);
 #pragma unroll
   for (int c = 0; c < NC; c++) out[r + c * nn] = acc[c];
 }
-__global__ void __launch_bounds__(GP_THREADS) k_grid_laplace_term(DevMesh m, GridTri gt, const double* __restrict__ nu, const double* __restrict__ u,
+__global__ void __launch_bounds__(GP_THREADS) k_grid_laplace_term(DevMesh m, GridTri gt, const double* __restrict__ xy, const double* __restrict__ nu, const double* __restrict__ u,
                                                                    double* __restrict__ out) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x, nn = (long long)(gt.m + 1) * (gt.n + 1);
-  if (r < nn) out[r] = grid_laplace_term_node(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), nu, u);
+  if (r < nn) out[r] = grid_laplace_term_node(gt, m.heron, m.rule, m.g, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), nu, u, xy);
 }
 
 // structured tetrahedral grid: one thread per node, node id = (k*(n+1) + j)*(n+1) + i
@@ -193,22 +193,22 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
   return launched("plane matrix gradient kernel");
 }
 
-int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st) {
+int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st, const double* xy) {
   const long long nn = (long long)(gt.m + 1) * (gt.n + 1);
   const unsigned nb = gp_blocks(nn);
   if (basis < GB_P1SHAPE || basis > GB_STRAIN || (weighted && basis != GB_STRAIN)) return fail("gauss-point scatter: unknown operator");
   switch (basis) {
-    case GB_P1SHAPE: k_grid_gp_scatter<GB_P1SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
-    case GB_SHAPE: k_grid_gp_scatter<GB_SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
-    case GB_GRAD: k_grid_gp_scatter<GB_GRAD, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out); break;
+    case GB_P1SHAPE: k_grid_gp_scatter<GB_P1SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, xy, in, out); break;
+    case GB_SHAPE: k_grid_gp_scatter<GB_SHAPE, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, xy, in, out); break;
+    case GB_GRAD: k_grid_gp_scatter<GB_GRAD, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, xy, in, out); break;
     default:
-      if (weighted) k_grid_gp_scatter<GB_STRAIN, true><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
-      else k_grid_gp_scatter<GB_STRAIN, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, in, out);
+      if (weighted) k_grid_gp_scatter<GB_STRAIN, true><<<nb, GP_THREADS, 0, st>>>(dm, gt, xy, in, out);
+      else k_grid_gp_scatter<GB_STRAIN, false><<<nb, GP_THREADS, 0, st>>>(dm, gt, xy, in, out);
   }
   return launched("structured gauss-point scatter kernel");
 }
-int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st) {
-  k_grid_laplace_term<<<gp_blocks((long long)(gt.m + 1) * (gt.n + 1)), GP_THREADS, 0, st>>>(dm, gt, nu, u, out);
+int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st, const double* xy) {
+  k_grid_laplace_term<<<gp_blocks((long long)(gt.m + 1) * (gt.n + 1)), GP_THREADS, 0, st>>>(dm, gt, xy, nu, u, out);
   return launched("structured Laplace term kernel");
 }
 

@@ -29,8 +29,9 @@ int launch_plane_matrix_grad(int mode, long long n, const double* E, const doubl
                              cudaStream_t st);
 
 // structured triangulation Mesh(m, n, h), P1 (grid_gauss.cuh): index-free versions of the scatter-type kernels
-int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st);
-int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st);
+// xy: nullptr on rectilinear grids; the coordinate array ([node][2]) for structured connectivity on mapped / jittered node positions
+int launch_grid_gp_scatter(const DevMesh& dm, const GridTri& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st, const double* xy = nullptr);
+int launch_grid_laplace_term(const DevMesh& dm, const GridTri& gt, const double* nu, const double* u, double* out, cudaStream_t st, const double* xy = nullptr);
 
 // structured tetrahedral grid Mesh3(n, n, l, h), P1 (tet_gauss.cuh)
 int launch_tet_gp_scatter(const DevMesh& dm, const GridTet& gt, int basis, bool weighted, const double* in, double* out, cudaStream_t st);

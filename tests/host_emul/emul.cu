@@ -81,12 +81,12 @@ int run_kind(const DevMesh& m, const long long* ap, const int* ae, const uint8_t
 
 // one thread per node of k_grid_gp_scatter (gauss_ops.cu)
 template <int B, bool W>
-static void run_grid_scatter(const GridTri& gt, int heron, const QuadRule& rule, const double* in, double* out) {
+static void run_grid_scatter(const GridTri& gt, int heron, const QuadRule& rule, const double* in, double* out, const double* xy = nullptr) {
   constexpr int NC = GpShape<2, 1, B>::NC;
   const long long nn = (long long)(gt.m + 1) * (gt.n + 1);
   for (long long r = 0; r < nn; r++) {
     double acc[NC];
-    grid_scatter_node<B, W>(gt, heron, rule, rule.n, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), in, acc);
+    grid_scatter_node<B, W>(gt, heron, rule, rule.n, (int)(r / (gt.m + 1)), (int)(r % (gt.m + 1)), in, acc, xy);
     for (int c = 0; c < NC; c++) out[r + c * nn] = acc[c];
   }
 }
@@ -301,23 +301,38 @@ int emul_grid_elast_adj_mapped(int m, int n, const double* xy, int order, int he
 }
 
 // structured scatter-type Gauss-point operators (grid_gauss.cuh): k_grid_gp_scatter / k_grid_laplace_term of gauss_ops.cu
-int emul_grid_gp_scatter(int m, int n, const double* xs, const double* ys, int order, int heron, int basis, int weighted, const double* in, double* out) {
+// xy != nullptr: mapped grid (positions from the coordinate array, xs / ys unused)
+static int emul_grid_gp_scatter_impl(int m, int n, const double* xs, const double* ys, int order, int heron, int basis, int weighted, const double* in, double* out,
+                                     const double* xy) {
   QuadRule rule;
   if (!triangle_rule(order, rule)) return 1;
   const GridTri gt{m, n, xs, ys};
   switch (basis) {
-    case GB_P1SHAPE: run_grid_scatter<GB_P1SHAPE, false>(gt, heron, rule, in, out); return 0;
-    case GB_SHAPE: run_grid_scatter<GB_SHAPE, false>(gt, heron, rule, in, out); return 0;
-    case GB_GRAD: run_grid_scatter<GB_GRAD, false>(gt, heron, rule, in, out); return 0;
-    case GB_STRAIN: if (weighted) run_grid_scatter<GB_STRAIN, true>(gt, heron, rule, in, out); else run_grid_scatter<GB_STRAIN, false>(gt, heron, rule, in, out); return 0;
+    case GB_P1SHAPE: run_grid_scatter<GB_P1SHAPE, false>(gt, heron, rule, in, out, xy); return 0;
+    case GB_SHAPE: run_grid_scatter<GB_SHAPE, false>(gt, heron, rule, in, out, xy); return 0;
+    case GB_GRAD: run_grid_scatter<GB_GRAD, false>(gt, heron, rule, in, out, xy); return 0;
+    case GB_STRAIN: if (weighted) run_grid_scatter<GB_STRAIN, true>(gt, heron, rule, in, out, xy); else run_grid_scatter<GB_STRAIN, false>(gt, heron, rule, in, out, xy); return 0;
   }
   return 1;
+}
+int emul_grid_gp_scatter(int m, int n, const double* xs, const double* ys, int order, int heron, int basis, int weighted, const double* in, double* out) {
+  return emul_grid_gp_scatter_impl(m, n, xs, ys, order, heron, basis, weighted, in, out, nullptr);
+}
+int emul_grid_gp_scatter_mapped(int m, int n, const double* xy, int order, int heron, int basis, int weighted, const double* in, double* out) {
+  return emul_grid_gp_scatter_impl(m, n, nullptr, nullptr, order, heron, basis, weighted, in, out, xy);
 }
 int emul_grid_laplace_term(int m, int n, const double* xs, const double* ys, int order, int heron, const double* nu, const double* u, double* out) {
   QuadRule rule;
   if (!triangle_rule(order, rule)) return 1;
   const GridTri gt{m, n, xs, ys};
   for (long long r = 0; r < (long long)(m + 1) * (n + 1); r++) out[r] = grid_laplace_term_node(gt, heron, rule, rule.n, (int)(r / (m + 1)), (int)(r % (m + 1)), nu, u);
+  return 0;
+}
+int emul_grid_laplace_term_mapped(int m, int n, const double* xy, int order, int heron, const double* nu, const double* u, double* out) {
+  QuadRule rule;
+  if (!triangle_rule(order, rule)) return 1;
+  const GridTri gt{m, n, nullptr, nullptr};
+  for (long long r = 0; r < (long long)(m + 1) * (n + 1); r++) out[r] = grid_laplace_term_node(gt, heron, rule, rule.n, (int)(r / (m + 1)), (int)(r % (m + 1)), nu, u, xy);
   return 0;
 }
 

@@ -380,6 +380,33 @@ def test_structured_scatter_operators(emul, oracle, m, n):
     assert np.array_equal(out, T.laplace_term(emul, nu, u))
 
 
+@pytest.mark.parametrize("m,n", [(5, 4), (1, 1), (9, 2)])
+def test_structured_scatter_operators_mapped_grid(emul, oracle, m, n):
+    """the same node bodies with the corner positions read from the coordinate array (structured connectivity on mapped + jittered node
+    positions): against the oracle and bit-identical to the general adjacency-walking bodies"""
+    rng = np.random.default_rng(m * 10 + n + 3)
+    c, e = meshgen.tri_grid(m, n, 1.0)
+    c = np.ascontiguousarray(np.stack([c[:, 0] + 0.08 * np.sin(0.7 * c[:, 1]), c[:, 1] + 0.06 * np.cos(0.9 * c[:, 0])], 1) + rng.uniform(-0.1, 0.1, c.shape))
+    o = oracle.Mesh2D(c, e)
+    T = HostTables(o)
+    G, nd = o.ngauss, o.ndof
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    cases = [(0, 0, G, nd, o.fem_to_gauss_bwd, FEM_TO_GAUSS, True), (1, 0, G, nd, o.dof_to_gauss_bwd, DOF_TO_GAUSS, True),
+             (2, 0, 2 * G, nd, o.grad_bwd, GRAD, True), (3, 0, 3 * G, 2 * nd, o.strain_bwd, STRAIN, True),
+             (3, 1, 3 * G, 2 * nd, o.strain_energy_fwd, STRAIN_ENERGY, False)]
+    for basis, weighted, nin, nout, ref, kind, adjoint in cases:
+        x = rng.standard_normal(nin)
+        out = np.full(nout, np.nan)
+        assert emul.emul_grid_gp_scatter_mapped(C.c_int(m), C.c_int(n), d(c), C.c_int(2), C.c_int(1), C.c_int(basis), C.c_int(weighted), d(x), d(out)) == 0
+        close(out, ref(x))
+        assert np.array_equal(out, T.gauss_op(emul, kind, adjoint, x, nout))
+    nu, u = rng.random(G) + 0.5, rng.standard_normal(nd)
+    out = np.full(nd, np.nan)
+    assert emul.emul_grid_laplace_term_mapped(C.c_int(m), C.c_int(n), d(c), C.c_int(2), C.c_int(1), d(nu), d(u), d(out)) == 0
+    close(out, o.laplace_term_fwd(nu, u))
+    assert np.array_equal(out, T.laplace_term(emul, nu, u))
+
+
 @pytest.mark.parametrize("n,l", [(2, 2), (3, 4), (1, 1), (4, 3)])
 def test_structured_tet_elasticity_warp_phases(emul, oracle, n, l):
     """tet_grid.cuh: one warp per node of Mesh3(n, n, l, h) run as loops over its lanes (shared memory poisoned), rectilinear non-uniform

@@ -326,14 +326,20 @@ def test_structured_elasticity_kernels(oracle, m, n, mapped):
             close(npy(gE), rE, rel=1e-11); close(npy(gnu), rnu, rel=1e-11)
 
 
-def test_structured_scatter_operators(oracle):
+@pytest.mark.parametrize("mapped", [False, True])
+def test_structured_scatter_operators(oracle, mapped):
     """Scatter-type Gauss-point operators and the Laplace term on Mesh(m, n, h): the index-free one-thread-per-node kernels (grid_gauss.cuh,
     option "structured" = 1, the default) against the oracle and against the general adjacency-walking kernels ("structured" = 0; on the host the
-    two bodies are bit-identical, tests/test_host_emulation.py)."""
+    two bodies are bit-identical, tests/test_host_emulation.py).  `mapped`: the same connectivity on smoothly mapped + jittered node positions
+    (corner positions from the coordinate array instead of the two axis arrays)."""
     rng = np.random.default_rng(61)
     m_, n_ = 45, 31
-    ms, o = A.Mesh(m_, n_, 0.05), oracle.Mesh2D(*meshgen.tri_grid(m_, n_, 0.05))
-    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == 1
+    c, e = meshgen.tri_grid(m_, n_, 0.05)
+    if mapped:
+        c = np.ascontiguousarray(np.stack([c[:, 0] + 0.004 * np.sin(14.0 * c[:, 1]), c[:, 1] + 0.003 * np.cos(18.0 * c[:, 0])], 1)
+                                 + rng.uniform(-0.005, 0.005, c.shape))
+    ms, o = A.Mesh(c, e), oracle.Mesh2D(c, e)
+    assert A._lib.lib().adfem_mesh_info(ms.handle, A._lib.INFO_STRUCTURED) == (3 if mapped else 1)
     G, nd = o.ngauss, o.ndof
     nu, u, go, sig = rng.random(G) + 0.5, rng.standard_normal(nd), rng.standard_normal(nd), rng.standard_normal((G, 3))
     w1, w2, w3 = rng.standard_normal(G), rng.standard_normal((G, 2)), rng.standard_normal((G, 3))
