@@ -142,8 +142,8 @@ enum { ADFEM_INFO_DIM = 0, ADFEM_INFO_NV, ADFEM_INFO_NE, ADFEM_INFO_NDOF, ADFEM_
                                 2: the mesh is the structured tetrahedral grid Mesh3(n,n,l,h) on rectilinear nodes (csrc/tet_node.cuh / tet_grid.cuh,
                                 used by the elasticity kernels under option "structured_elasticity");
                                 3: structured connectivity of Mesh(m,n,h) on NON-rectilinear (mapped / jittered) node positions: the scalar CSR
-                                operators, the source term and P1 elasticity use the MAPPED instantiations of the index-free kernels, the
-                                Gauss-point operators the general kernels */ };
+                                operators, the source term, P1 elasticity and the scatter-type Gauss-point operators / Laplace term use the
+                                index-free kernels with node positions read from the coordinate array (MAPPED instantiations) */ };
 
 /* Replaces init_nnfem_mesh / init_nnfem_mesh3 (deps/MFEM/API.cpp:4, deps/MFEM3/API.cpp:4) without the
  * process-global singleton.  dim = 2|3; vertices: nv rows of `vertex_stride` doubles (first `dim` used);
