@@ -323,11 +323,13 @@ int slots_of(const HostMesh& h, int nc, bool presum3d = false, bool overlap = fa
 }
 
 // dynamic shared memory of the tile kernels: 3 head buffers + 2 body buffers + local matrices / 2 staging buffers
-size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return 3 * align16(tp.max_head) + 2 * align16(tp.max_body) + (size_t)8 * slots * tp.max_elems; }
+size_t fwd_smem_of(size_t max_head, size_t max_body, int max_elems, int slots) { return 3 * align16(max_head) + 2 * align16(max_body) + (size_t)8 * slots * max_elems; }
+size_t fwd_smem_bytes(const FwdTiles& tp, int slots) { return fwd_smem_of(tp.max_head, tp.max_body, tp.max_elems, slots); }
 // ns2: NS*NS for P1 elasticity (gradient matrices parked in shared memory for the coalesced store), else 0
-size_t adj_smem_bytes(const AdjTiles& ap, int nc, int ns2) {
-  return 3 * align16(ap.max_head) + 2 * align16(ap.max_body) + (size_t)2 * 8 * nc * nc * ap.max_nnz + (size_t)8 * ns2 * ap.max_elems;
+size_t adj_smem_of(size_t max_head, size_t max_body, int max_elems, int max_nnz, int nc, int ns2) {
+  return 3 * align16(max_head) + 2 * align16(max_body) + (size_t)2 * 8 * nc * nc * max_nnz + (size_t)8 * ns2 * max_elems;
 }
+size_t adj_smem_bytes(const AdjTiles& ap, int nc, int ns2) { return adj_smem_of(ap.max_head, ap.max_body, ap.max_elems, ap.max_nnz, nc, ns2); }
 int adj_ns2(const HostMesh& h, int nc) { return (nc > 1 && h.degree == 1) ? (h.dim == 2 ? 9 : 36) : 0; }
 constexpr size_t SMEM_LIMIT = 220 * 1024;
 
@@ -353,6 +355,9 @@ int ensure_fwd_plan(adfem_mesh* m, int nc, FwdPlanDev** out) {
     // renumbered meshes), and each try is a full plan build — 2/3 of the 40 s the 16 M-triangle P2 plan took.  Start where the sequence ends up.
     if (m->opt_rows_per_tile <= 0 && h.dim == 2 && attempt == 0)
       for (int skip = (h.degree == 2 || nc > 1) ? 2 : 1; skip > 0; skip--) R = std::max(4, (int)(R * 0.8));
+    // a plan over the limit below is rejected after the build: let the build stop at the first tile that shows it
+    const size_t limit = std::max(budget, m->opt_rows_per_tile > 0 ? SMEM_LIMIT : budget);
+    P->host.too_big = [=](size_t hd, size_t bd, int me, int) { return fwd_smem_of(hd, bd, me, slots) > limit; };
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, R, max_elems, nc == 1 ? 1 : 0, nthreads_of(m));
       if (getenv("ADFEM_DEBUG_PLAN")) fprintf(stderr, "fwd plan try %d: R=%d max_elems=%d -> '%s' smem %zu (budget %zu) tiles %d\n", tries, R, max_elems, err.c_str(), err.empty() ? fwd_smem_bytes(P->host, slots) : (size_t)0, budget, P->host.ntiles);
@@ -396,8 +401,12 @@ int ensure_adj_plan(adfem_mesh* m, int nc, AdjPlanDev** out) {
     // every thread of the CTA gets the same number of elements
     if (m->opt_elems_per_tile <= 0 && EPT >= tile_threads_of(m, nc)) EPT -= EPT % tile_threads_of(m, nc);
     const int max_nnz = 65535;
+    const size_t limit = std::max(budget, m->opt_elems_per_tile > 0 ? SMEM_LIMIT : budget);
+    const int ns2 = adj_ns2(h, nc);
+    P->host.too_big = [=](size_t hd, size_t bd, int me, int mn) { return adj_smem_of(hd, bd, me, mn, nc, ns2) > limit; };
     for (int tries = 0; tries < 16; tries++) {
       err = P->host.build(h, m->pat, EPT, max_nnz, nthreads_of(m));
+      if (getenv("ADFEM_DEBUG_PLAN")) fprintf(stderr, "adj plan try %d: EPT=%d -> '%s' smem %zu (budget %zu) tiles %d\n", tries, EPT, err.c_str(), err.empty() ? adj_smem_bytes(P->host, nc, adj_ns2(h, nc)) : (size_t)0, budget, P->host.ntiles);
       if (err == "row longer than 255 entries") { m->adj_untileable = true; return 0; }
       if (err.empty() && adj_smem_bytes(P->host, nc, adj_ns2(h, nc)) > std::max(budget, m->opt_elems_per_tile > 0 ? SMEM_LIMIT : budget)) err = "tile too large";
       if (err.empty() || EPT <= 4) break;

@@ -1,8 +1,10 @@
 #include "host_mesh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 namespace adfem {
@@ -22,6 +24,9 @@ template <class F> void par_elems(long long n, F fn) {
   }
   for (auto& x : th) x.join();
 }
+
+// zero reserved (not yet constructed) storage of plain data: maps its pages from the calling thread; the resize that follows finds them mapped
+template <class T> void prefault(T* p, size_t n) { if (n) memset(static_cast<void*>(p), 0, n * sizeof(T)); }
 
 // local edges in MFEM geometry order (Geometry::Constants<TRIANGLE/TETRAHEDRON>::Edges)
 const int kTriEdges[3][2] = {{0, 1}, {1, 2}, {2, 0}};
@@ -53,12 +58,24 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   g = rule.n;
   const int nvl = dim + 1, nel = dim == 2 ? 3 : 6;
   d = degree == 1 ? nvl : nvl + nel;
+  // copies and the range check in element / vertex blocks over the host threads (the first touch of the new arrays is most of their cost)
+  coords.clear(); coords.reserve((size_t)nv * dim);
+  verts.clear(); verts.reserve((size_t)ne * nvl);
+  par_elems(nv, [&](long long i0, long long i1) { prefault(coords.data() + (size_t)i0 * dim, (size_t)(i1 - i0) * dim); });
+  par_elems(ne, [&](long long e0, long long e1) { prefault(verts.data() + (size_t)e0 * nvl, (size_t)(e1 - e0) * nvl); });
   coords.resize((size_t)nv * dim);
-  for (int i = 0; i < nv; i++)
-    for (int c = 0; c < dim; c++) coords[(size_t)i * dim + c] = vertices[(size_t)i * vstride + c];
-  verts.assign(elems, elems + (size_t)ne * nvl);
-  for (size_t i = 0; i < verts.size(); i++)
-    if (verts[i] < 0 || verts[i] >= nv) return "element vertex index out of range";
+  verts.resize((size_t)ne * nvl);
+  par_elems(nv, [&](long long i0, long long i1) {
+    for (long long i = i0; i < i1; i++)
+      for (int c = 0; c < dim; c++) coords[(size_t)i * dim + c] = vertices[(size_t)i * vstride + c];
+  });
+  std::atomic<bool> bad(false);
+  par_elems(ne, [&](long long e0, long long e1) {
+    bool b = false;
+    for (size_t i = (size_t)e0 * nvl; i < (size_t)e1 * nvl; i++) { const int v = elems[i]; verts[i] = v; b |= v < 0 || v >= nv_; }
+    if (b) bad.store(true);
+  });
+  if (bad.load()) return "element vertex index out of range";
   // orientation fix (quirk Q3)
   par_elems(ne, [&](long long e0, long long e1) {
   for (long long e = e0; e < e1; e++) {
@@ -79,10 +96,12 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   });
   // edges + connectivity.  P1: the connectivity is the vertex list and the edge numbering (an output of the mesh constructor only) is left to
   // ensure_edges(): its sequential first-appearance walk costs more than every other table together on large meshes.
+  conn.clear(); conn.reserve((size_t)ne * d);
+  par_elems(ne, [&](long long e0, long long e1) { prefault(conn.data() + (size_t)e0 * d, (size_t)(e1 - e0) * d); });
   conn.resize((size_t)ne * d);
   edges_built = false; nedges = 0; edge_lo.clear(); edge_hi.clear();
   if (degree == 1) {
-    conn = verts;
+    par_elems(ne, [&](long long e0, long long e1) { memcpy(conn.data() + (size_t)e0 * d, verts.data() + (size_t)e0 * d, (size_t)(e1 - e0) * d * sizeof(int)); });
   } else {
     EdgeNumbering en(nv);
     for (int e = 0; e < ne; e++) {

@@ -1,10 +1,14 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
+#include <type_traits>
 #include <utility>
 
 namespace adfem {
@@ -17,6 +21,35 @@ int default_threads() {
 
 namespace {
 
+// ADFEM_DEBUG_PLAN=1: wall time of each host phase on stderr
+struct PhaseTimer {
+  const bool on = getenv("ADFEM_DEBUG_PLAN") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "  [plan] %-34s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+// v = n zeros, with the first touch of the pages spread over the worker threads: a fresh multi-GB array costs a page fault per 4 KB, which a single
+// thread pays at 1-2 GB/s.  The threads zero the reserved storage, the resize that follows value-initialises pages that are already mapped.
+template <class T> void assign_parallel(std::vector<T>& v, size_t n, int nthreads) {
+  static_assert(std::is_trivially_copyable<T>::value, "plain data only");
+  v.clear();
+  const size_t bytes = n * sizeof(T);
+  if (nthreads > 1 && bytes >= ((size_t)8 << 20)) {
+    v.reserve(n);
+    char* p = reinterpret_cast<char*>(v.data());
+    std::vector<std::thread> th;
+    const size_t chunk = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+    for (size_t b = 0; b < bytes; b += chunk) th.emplace_back([=] { memset(p + b, 0, std::min(chunk, bytes - b)); });
+    for (auto& x : th) x.join();
+  }
+  v.resize(n);
+}
+
 // static block partition of [0,n) over worker threads
 void parallel_for(long long n, int nthreads, const std::function<void(long long, long long, int)>& fn) {
   if (nthreads <= 1 || n < 4096) { fn(0, n, 0); return; }
@@ -28,21 +61,6 @@ void parallel_for(long long n, int nthreads, const std::function<void(long long,
     th.emplace_back(fn, b, e, t);
   }
   for (auto& x : th) x.join();
-}
-
-typedef std::pair<int, uint64_t> ColSlot;   // (column, global slot id (e*d+p)*d+q)
-
-// all local entries that land in row r, sorted by (col, slot): the fixed summation order of every nnz
-inline void row_pairs(const HostMesh& m, const ScalarPattern& pat, int r, std::vector<ColSlot>& out) {
-  out.clear();
-  const int d = m.d;
-  for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) {
-    int e = pat.adj_elem[a], p = pat.adj_loc[a];
-    const int* ce = &m.conn[(size_t)e * d];
-    uint64_t base = ((uint64_t)e * d + p) * d;
-    for (int q = 0; q < d; q++) out.emplace_back(ce[q], base + q);
-  }
-  std::sort(out.begin(), out.end());
 }
 
 inline uint64_t spread2(uint64_t x) {   // 21 bits -> every 2nd bit
@@ -109,47 +127,129 @@ void morton_order(long long n, int nthreads, const std::function<uint64_t(long l
 std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
   n = m.ndof;
   const int d = m.d;
+  PhaseTimer pt;
   const long long nslot_rows = (long long)m.ne * d;
   if (nslot_rows > 2147483647LL) return "ne*elem_ndof exceeds 32-bit";
-  // dof -> (element, local) adjacency by counting sort (element order preserved inside a row)
-  adj_ptr.assign((size_t)n + 1, 0);
-  for (long long i = 0; i < nslot_rows; i++) adj_ptr[m.conn[i] + 1]++;
-  for (int r = 0; r < n; r++) adj_ptr[r + 1] += adj_ptr[r];
-  adj_elem.resize(nslot_rows); adj_loc.resize(nslot_rows);
-  {
-    std::vector<long long> cur(adj_ptr.begin(), adj_ptr.end() - 1);
-    for (int e = 0; e < m.ne; e++)
-      for (int p = 0; p < d; p++) { long long at = cur[m.conn[(size_t)e * d + p]]++; adj_elem[at] = e; adj_loc[at] = (uint8_t)p; }
-  }
-  // pass 1: row lengths
-  std::vector<int> rowlen(n);
-  parallel_for(n, nthreads, [&](long long b, long long e, int) {
-    std::vector<ColSlot> ps;
-    for (long long r = b; r < e; r++) {
-      row_pairs(m, *this, (int)r, ps);
-      int cnt = 0;
-      for (size_t i = 0; i < ps.size(); i++) if (i == 0 || ps[i].first != ps[i - 1].first) cnt++;
-      rowlen[r] = cnt;
-    }
+  // dof -> (element, local) adjacency, ascending element inside a row.  Threads take element blocks: counts and fill positions are claimed with
+  // relaxed atomic increments, which leaves the order inside a row to the scheduler — so every row (a handful of entries) is sorted afterwards.
+  assign_parallel(adj_ptr, (size_t)n + 1, nthreads);
+  parallel_for(nslot_rows, nthreads, [&](long long b, long long e, int) {
+    long long* cnt = adj_ptr.data() + 1;
+    const int* c = m.conn.data();
+    for (long long i = b; i < e; i++) __atomic_fetch_add(&cnt[c[i]], 1LL, __ATOMIC_RELAXED);
   });
-  rowptr.assign((size_t)n + 1, 0);
-  for (int r = 0; r < n; r++) rowptr[r + 1] = rowptr[r] + rowlen[r];
-  nnz = rowptr[n];
-  if (nnz > 4294967295LL) return "scalar nnz exceeds 32-bit slot map";
-  colind.resize(nnz);
-  slot_nnz.resize((size_t)m.ne * d * d);
-  // pass 2: columns + slot map
+  for (int r = 0; r < n; r++) adj_ptr[r + 1] += adj_ptr[r];
+  assign_parallel(adj_elem, (size_t)nslot_rows, nthreads); assign_parallel(adj_loc, (size_t)nslot_rows, nthreads);
+  {
+    std::vector<long long> cur;
+    assign_parallel(cur, (size_t)n, nthreads);
+    parallel_for(n, nthreads, [&](long long b, long long e, int) { memcpy(cur.data() + b, adj_ptr.data() + b, (size_t)(e - b) * sizeof(long long)); });
+    parallel_for(m.ne, nthreads, [&](long long b, long long e, int) {
+      const int* c = m.conn.data() + (size_t)b * d;
+      for (long long el = b; el < e; el++)
+        for (int p = 0; p < d; p++, c++) { const long long at = __atomic_fetch_add(&cur[*c], 1LL, __ATOMIC_RELAXED); adj_elem[at] = (int)el; adj_loc[at] = (uint8_t)p; }
+    });
+  }
   parallel_for(n, nthreads, [&](long long b, long long e, int) {
-    std::vector<ColSlot> ps;
+    std::vector<uint64_t> key;
     for (long long r = b; r < e; r++) {
-      row_pairs(m, *this, (int)r, ps);
-      long long at = rowptr[r] - 1;
-      for (size_t i = 0; i < ps.size(); i++) {
-        if (i == 0 || ps[i].first != ps[i - 1].first) colind[++at] = ps[i].first;
-        slot_nnz[ps[i].second] = (uint32_t)at;
+      const long long r0 = adj_ptr[r], len = adj_ptr[r + 1] - r0;
+      int* el = adj_elem.data() + r0;
+      uint8_t* lo = adj_loc.data() + r0;
+      if (len <= 32) {                          // insertion sort of the (element, local) pairs by element (an element meets a dof once)
+        for (long long i = 1; i < len; i++) {
+          const int ke = el[i]; const uint8_t kl = lo[i];
+          long long j = i - 1;
+          for (; j >= 0 && el[j] > ke; j--) { el[j + 1] = el[j]; lo[j + 1] = lo[j]; }
+          el[j + 1] = ke; lo[j + 1] = kl;
+        }
+      } else {
+        key.resize((size_t)len);
+        for (long long i = 0; i < len; i++) key[i] = (uint64_t)(uint32_t)el[i] << 8 | lo[i];
+        std::sort(key.begin(), key.end());
+        for (long long i = 0; i < len; i++) { el[i] = (int)(key[i] >> 8); lo[i] = (uint8_t)(key[i] & 0xff); }
       }
     }
   });
+  pt.lap("pattern: adjacency");
+  if (pt.on) {      // FNV-1a over the adjacency: lets two builds of the host code be compared
+    uint64_t hsh = 1469598103934665603ULL;
+    auto mix = [&](uint64_t v) { hsh = (hsh ^ v) * 1099511628211ULL; };
+    for (long long v : adj_ptr) mix((uint64_t)v);
+    for (long long i = 0; i < nslot_rows; i++) mix(((uint64_t)(uint32_t)adj_elem[i] << 8) | adj_loc[i]);
+    fprintf(stderr, "  [plan] adjacency checksum %016llx\n", (unsigned long long)hsh);
+    pt.lap("pattern: (checksum)");
+  }
+  // pass 1: the distinct columns of every row, ascending (one sort of the row's column ids); a thread appends the rows of its range to a buffer of
+  // its own, which is copied to its place once the row pointers are known
+  std::vector<int> rowlen;
+  assign_parallel(rowlen, (size_t)n, nthreads);
+  const int nbuf = std::max(1, nthreads);
+  std::vector<std::vector<int>> colbuf(nbuf);
+  std::vector<long long> buf_first(nbuf, -1);
+  parallel_for(n, nthreads, [&](long long b, long long e, int tid) {
+    std::vector<int> cols;
+    std::vector<int>& out = colbuf[tid];
+    buf_first[tid] = b;
+    out.reserve((size_t)((e - b) * (m.dim == 2 ? (m.degree == 1 ? 8 : 13) : (m.degree == 1 ? 16 : 32))));
+    for (long long r = b; r < e; r++) {
+      const long long deg = adj_ptr[r + 1] - adj_ptr[r];
+      if (deg * d <= 40) {                      // the usual row: insert into a small sorted set
+        int uq[160], cnt = 0;
+        for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
+          const int* ce = &m.conn[(size_t)adj_elem[a] * d];
+          for (int q = 0; q < d; q++) {
+            const int c = ce[q];
+            int i = cnt;
+            while (i > 0 && uq[i - 1] > c) i--;
+            if (i > 0 && uq[i - 1] == c) continue;
+            for (int k = cnt; k > i; k--) uq[k] = uq[k - 1];
+            uq[i] = c; cnt++;
+          }
+        }
+        out.insert(out.end(), uq, uq + cnt);
+        rowlen[r] = cnt;
+        continue;
+      }
+      cols.clear();
+      for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
+        const int* ce = &m.conn[(size_t)adj_elem[a] * d];
+        cols.insert(cols.end(), ce, ce + d);
+      }
+      std::sort(cols.begin(), cols.end());
+      const size_t before = out.size();
+      for (size_t i = 0; i < cols.size(); i++) if (i == 0 || cols[i] != cols[i - 1]) out.push_back(cols[i]);
+      rowlen[r] = (int)(out.size() - before);
+    }
+  });
+  assign_parallel(rowptr, (size_t)n + 1, nthreads);
+  for (int r = 0; r < n; r++) rowptr[r + 1] = rowptr[r] + rowlen[r];
+  nnz = rowptr[n];
+  if (nnz > 4294967295LL) return "scalar nnz exceeds 32-bit slot map";
+  pt.lap("pattern: columns of every row");
+  assign_parallel(colind, (size_t)nnz, nthreads);
+  assign_parallel(slot_nnz, (size_t)m.ne * d * d, nthreads);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nbuf; t++)
+      if (buf_first[t] >= 0 && !colbuf[t].empty())
+        th.emplace_back([&, t] { memcpy(colind.data() + rowptr[buf_first[t]], colbuf[t].data(), colbuf[t].size() * sizeof(int)); std::vector<int>().swap(colbuf[t]); });
+    for (auto& x : th) x.join();
+  }
+  // pass 2: slot map — local entry (e, p, q) lands in row conn[e][p] at the position of conn[e][q] among the row's columns
+  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+    for (long long r = b; r < e; r++) {
+      const int* cb = colind.data() + rowptr[r];
+      const int* cend = colind.data() + rowptr[r + 1];
+      for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
+        const int el = adj_elem[a], p = adj_loc[a];
+        const int* ce = &m.conn[(size_t)el * d];
+        uint32_t* dst = &slot_nnz[((size_t)el * d + p) * d];
+        for (int q = 0; q < d; q++) dst[q] = (uint32_t)(rowptr[r] + (std::lower_bound(cb, cend, ce[q]) - cb));
+      }
+    }
+  });
+  pt.lap("pattern: columns + slot map");
   return "";
 }
 
@@ -184,18 +284,35 @@ void tile_vertices(const HostMesh& m, const std::vector<int>& te, std::vector<in
     for (int c = 0; c < m.dim; c++) xy[i * m.dim + c] = m.coords[(size_t)tvert[i] * m.dim + c];
 }
 
-struct PartOut { std::vector<uint8_t> blob; std::vector<long long> sizes; std::string err; int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0; long long tot_a = 0; };
+struct PartOut {
+  std::vector<uint8_t> blob; std::vector<long long> sizes; std::string err;
+  int max_rows = 0, max_elems = 0, max_nnz = 0, max_src = 0, max_verts = 0;
+  size_t max_head = 0, max_body = 0;
+  long long tot_a = 0;
+};
 
 // per_tile appends the tile's head and body to P.blob and pushes their two sizes to P.sizes
-template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<PartOut>& parts, F per_tile) {
+// A failure in one part (a tile that cannot be built, or too_big() of the part's running maxima — the plan's maxima can only be larger) stops the
+// other parts at their next tile.
+template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<PartOut>& parts,
+                                         const std::function<bool(size_t, size_t, int, int)>& too_big, F per_tile) {
   int nparts = std::max(1, std::min(nthreads, ntiles));
   parts.assign(nparts, PartOut());
   std::vector<long long> pcut(nparts + 1);
   for (int i = 0; i <= nparts; i++) pcut[i] = (long long)ntiles * i / nparts;
+  std::atomic<bool> stop(false);
   std::vector<std::thread> th;
   for (int pi = 0; pi < nparts; pi++) th.emplace_back([&, pi] {
     PartOut& P = parts[pi];
-    for (long long t = pcut[pi]; t < pcut[pi + 1] && P.err.empty(); t++) per_tile((int)t, P);
+    for (long long t = pcut[pi]; t < pcut[pi + 1] && P.err.empty() && !stop.load(std::memory_order_relaxed); t++) {
+      per_tile((int)t, P);
+      if (P.err.empty() && P.sizes.size() >= 2) {
+        P.max_head = std::max(P.max_head, (size_t)P.sizes[P.sizes.size() - 2]);
+        P.max_body = std::max(P.max_body, (size_t)P.sizes[P.sizes.size() - 1]);
+        if (too_big && too_big(P.max_head, P.max_body, P.max_elems, P.max_nnz)) P.err = "tile too large";
+      }
+      if (!P.err.empty()) stop.store(true, std::memory_order_relaxed);
+    }
   });
   for (auto& t : th) t.join();
   for (auto& P : parts) if (!P.err.empty()) return P.err;
@@ -203,20 +320,22 @@ template <class F> std::string run_parts(int ntiles, int nthreads, std::vector<P
 }
 
 // concatenate the per-thread outputs: blob, blob_ptr (2 offsets per tile + end), largest head / body
-void merge_parts(std::vector<PartOut>& parts, std::vector<long long>& blob_ptr, std::vector<uint8_t>& blob, size_t& max_head, size_t& max_body) {
-  blob_ptr.assign(1, 0); blob.clear(); max_head = max_body = 0;
+void merge_parts(std::vector<PartOut>& parts, std::vector<long long>& blob_ptr, std::vector<uint8_t>& blob, size_t& max_head, size_t& max_body, int nthreads) {
+  blob_ptr.assign(1, 0); max_head = max_body = 0;
   size_t total = 0;
-  for (auto& P : parts) total += P.blob.size();
-  blob.reserve(total);
-  for (auto& P : parts) {
+  std::vector<size_t> at;
+  for (auto& P : parts) { at.push_back(total); total += P.blob.size(); }
+  assign_parallel(blob, total, nthreads);
+  for (auto& P : parts)
     for (size_t i = 0; i < P.sizes.size(); i++) {
       blob_ptr.push_back(blob_ptr.back() + P.sizes[i]);
       size_t& mx = (i & 1) ? max_body : max_head;
       mx = std::max(mx, (size_t)P.sizes[i]);
     }
-    blob.insert(blob.end(), P.blob.begin(), P.blob.end());
-    std::vector<uint8_t>().swap(P.blob);
-  }
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < parts.size(); i++)
+    th.emplace_back([&, i] { if (!parts[i].blob.empty()) memcpy(blob.data() + at[i], parts[i].blob.data(), parts[i].blob.size()); std::vector<uint8_t>().swap(parts[i].blob); });
+  for (auto& x : th) x.join();
 }
 }  // namespace
 
@@ -224,9 +343,13 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   rows_per_tile = R; sym = sym_;
   const int d = m.d, dd = d * d, n = pat.n;
   const int nslot = sym ? d * (d + 1) / 2 : dd;
-  Morton mc(m);
-  std::vector<int> order;
-  morton_order(n, nthreads, [&](long long i) { double x[3]; m.dof_position((int)i, x); return mc.code(x); }, order);
+  PhaseTimer pt;
+  if ((long long)morton_cache.size() != n) {
+    Morton mc(m);
+    morton_order(n, nthreads, [&](long long i) { double x[3]; m.dof_position((int)i, x); return mc.code(x); }, morton_cache);
+  }
+  std::vector<int> order(morton_cache);
+  pt.lap("fwd tiles: morton order of rows");
   ntiles = (n + R - 1) / R;
   std::vector<int> row_ptr(ntiles + 1);
   for (int t = 0; t <= ntiles; t++) row_ptr[t] = (int)std::min<long long>((long long)t * R, n);
@@ -241,14 +364,14 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   std::vector<int> symidx(dd);
   for (int p = 0; p < d; p++) for (int q = 0; q < d; q++) { int a = std::min(p, q), b = std::max(p, q); symidx[p * d + q] = a * d - a * (a - 1) / 2 + (b - a); }
 
+  pt.lap("fwd tiles: tile sort, max row");
   std::vector<PartOut> parts;
-  std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
-    std::vector<ColSlot> ps;
-    std::vector<int> te, tvert;
-    std::vector<uint16_t> tv, rlen;
+  std::string err = run_parts(ntiles, nthreads, parts, too_big, [&](int t, PartOut& P) {
+    std::vector<int> te, tvert, jitem;
+    std::vector<uint16_t> tv, rlen, pool;
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
-    struct Item { uint32_t d0, d1; int paired; std::vector<uint16_t> src; };
+    struct Item { uint32_t d0, d1; int paired; uint32_t off, cnt; };     // sources: pool[off .. off + cnt)
     std::vector<Item> items;
     const int* trow = rows.data() + row_ptr[t];
     const int nrows = row_ptr[t + 1] - row_ptr[t];
@@ -263,44 +386,51 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     size_t nsrc = 0, nnz_t = 0;
     for (int lr = 0; lr < nrows; lr++) {
       const int r = trow[lr];
-      rstart.push_back((uint32_t)pat.rowptr[r]);
-      rlen.push_back((uint16_t)(pat.rowptr[r + 1] - pat.rowptr[r]));
-      nnz_t += rlen.back();
-      row_pairs(m, pat, r, ps);
-      int j = -1;
-      bool skip = false;
-      for (size_t k = 0; k < ps.size(); k++) {
-        if (k == 0 || ps[k].first != ps[k - 1].first) {
-          j++;
-          const int c = ps[k].first;
-          skip = false;
-          int paired = 0; uint32_t d1 = 0;
-          if (sym && c != r) {                       // is the mirrored entry (c, r) produced by this tile too?
-            const int* it = std::lower_bound(trow, trow + nrows, c);
-            if (it != trow + nrows && *it == c) {
-              const int lc = (int)(it - trow);
-              if (lc < lr) skip = true;               // already emitted from the other side
-              else {
-                const int* cb = &pat.colind[pat.rowptr[c]];
-                const int* ce = &pat.colind[pat.rowptr[c + 1]];
-                paired = 1; d1 = code(lc, (int)(std::lower_bound(cb, ce, r) - cb));
-              }
-            }
+      const long long rs = pat.rowptr[r];
+      const int len = (int)(pat.rowptr[r + 1] - rs), deg = (int)(pat.adj_ptr[r + 1] - pat.adj_ptr[r]);
+      rstart.push_back((uint32_t)rs);
+      rlen.push_back((uint16_t)len);
+      nnz_t += (size_t)len;
+      // one item per CSR entry of the row (ascending column) unless its mirror image was emitted from the other row of the pair; an entry
+      // receives at most one contribution per incident element, so item j owns pool[base + j*deg .. + deg)
+      jitem.assign(len, -1);
+      const size_t base = pool.size();
+      pool.resize(base + (size_t)len * deg);
+      for (int j = 0; j < len; j++) {
+        const int c = pat.colind[rs + j];
+        int paired = 0; uint32_t d1 = 0;
+        if (sym && c != r) {                       // is the mirrored entry (c, r) produced by this tile too?
+          const int* it = std::lower_bound(trow, trow + nrows, c);
+          if (it != trow + nrows && *it == c) {
+            const int lc = (int)(it - trow);
+            if (lc < lr) continue;                  // already emitted from the other side
+            const int* cb = &pat.colind[pat.rowptr[c]];
+            const int* ce = &pat.colind[pat.rowptr[c + 1]];
+            paired = 1; d1 = code(lc, (int)(std::lower_bound(cb, ce, r) - cb));
           }
-          if (!skip) items.push_back(Item{code(lr, j), d1, paired, {}});
         }
-        if (skip) continue;
-        int el = (int)(ps[k].second / dd), pq = (int)(ps[k].second % dd);
-        int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
-        items.back().src.push_back((uint16_t)(sym ? symidx[pq] * nel + le : le * dd + pq));
-        nsrc++;
+        jitem[j] = (int)items.size();
+        items.push_back(Item{code(lr, j), d1, paired, (uint32_t)(base + (size_t)j * deg), 0u});
+      }
+      // contributions in ascending (element, local column) order = ascending slot id: the fixed summation order of every entry
+      for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) {
+        const int el = pat.adj_elem[a], pl = pat.adj_loc[a];
+        const int le = (int)(std::lower_bound(te.begin(), te.end(), el) - te.begin());
+        const uint32_t* sn = &pat.slot_nnz[((size_t)el * d + pl) * d];
+        for (int q = 0; q < d; q++) {
+          const int it = jitem[(size_t)(sn[q] - (uint32_t)rs)];
+          if (it < 0) continue;
+          Item& I = items[it];
+          pool[I.off + I.cnt++] = (uint16_t)(sym ? symidx[pl * d + q] * nel + le : le * dd + pl * d + q);
+          nsrc++;
+        }
       }
     }
     if (nsrc > 65535 * 4 || nnz_t > 65535) { P.err = "tile too large"; return; }
     // classes of equal (source count, paired), ascending; tile order kept inside a class (coalesced stores)
     std::vector<int> ord(items.size());
     for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
-    auto key = [&](int a) { return (int)items[a].src.size() | items[a].paired << 16; };
+    auto key = [&](int a) { return (int)items[a].cnt | items[a].paired << 16; };
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key(a) < key(b); });
     std::vector<int> cls;            // {count | paired << 16, items, src offset, dst offset} per class
     std::vector<uint16_t> src, dst16;
@@ -311,7 +441,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
       const int kk = key(ord[a]), cnt = kk & 0xffff;
       while (b < ord.size() && key(ord[b]) == kk) b++;
       cls.push_back(kk); cls.push_back((int)(b - a)); cls.push_back((int)src.size()); cls.push_back((int)(ent32 ? dst32.size() : dst16.size()));
-      for (int k = 0; k < cnt; k++) for (size_t i = a; i < b; i++) src.push_back(items[ord[i]].src[k]);
+      for (int k = 0; k < cnt; k++) for (size_t i = a; i < b; i++) src.push_back(pool[items[ord[i]].off + k]);
       for (size_t i = a; i < b; i++) push_dst(items[ord[i]].d0);
       if (kk >> 16) for (size_t i = a; i < b; i++) push_dst(items[ord[i]].d1);
       a = b;
@@ -331,6 +461,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     P.max_src = std::max(P.max_src, (int)src.size()); P.max_verts = std::max(P.max_verts, (int)tvert.size());
     P.tot_a += nel;
   });
+  pt.lap("fwd tiles: per-tile blobs");
   if (!err.empty()) return err;
   max_rows = max_elems = max_nnz = max_src = max_verts = 0;
   long long tot = 0;
@@ -339,7 +470,9 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     max_src = std::max(max_src, P.max_src); max_verts = std::max(max_verts, P.max_verts);
     tot += P.tot_a;
   }
-  merge_parts(parts, blob_ptr, blob, max_head, max_body);
+  merge_parts(parts, blob_ptr, blob, max_head, max_body, nthreads);
+  std::vector<int>().swap(morton_cache);
+  pt.lap("fwd tiles: merge");
   elem_redundancy = m.ne > 0 ? (double)tot / m.ne : 0;
   return "";
 }
@@ -349,14 +482,17 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
   elems_per_tile = EPT;
   const int d = m.d, dd = d * d, nvl = m.dim + 1;
   for (int r = 0; r < pat.n; r++) if (pat.rowptr[r + 1] - pat.rowptr[r] > 255) return "row longer than 255 entries";
-  Morton mc(m);
-  std::vector<int> order;
-  morton_order(m.ne, nthreads, [&](long long e) {
-    double c[3] = {0, 0, 0};
-    for (int k = 0; k < nvl; k++) for (int a = 0; a < m.dim; a++) c[a] += m.coords[(size_t)m.verts[(size_t)e * nvl + k] * m.dim + a];
-    for (int a = 0; a < m.dim; a++) c[a] /= nvl;
-    return mc.code(c);
-  }, order);
+  PhaseTimer pt;
+  if ((long long)morton_cache.size() != m.ne) {
+    Morton mc(m);
+    morton_order(m.ne, nthreads, [&](long long e) {
+      double c[3] = {0, 0, 0};
+      for (int k = 0; k < nvl; k++) for (int a = 0; a < m.dim; a++) c[a] += m.coords[(size_t)m.verts[(size_t)e * nvl + k] * m.dim + a];
+      for (int a = 0; a < m.dim; a++) c[a] /= nvl;
+      return mc.code(c);
+    }, morton_cache);
+  }
+  std::vector<int> order(morton_cache);
   ntiles = (m.ne + EPT - 1) / EPT;
   std::vector<int> elem_ptr(ntiles + 1);
   for (int t = 0; t <= ntiles; t++) elem_ptr[t] = (int)std::min<long long>((long long)t * EPT, m.ne);
@@ -364,8 +500,9 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
   parallel_for(ntiles, nthreads, [&](long long b, long long e, int) {
     for (long long t = b; t < e; t++) std::sort(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]);
   });
+  pt.lap("adj tiles: morton order, tile sort");
   std::vector<PartOut> parts;
-  std::string err = run_parts(ntiles, nthreads, parts, [&](int t, PartOut& P) {
+  std::string err = run_parts(ntiles, nthreads, parts, too_big, [&](int t, PartOut& P) {
     std::vector<int> tr, te(elems.begin() + elem_ptr[t], elems.begin() + elem_ptr[t + 1]), tvert;
     std::vector<uint16_t> tv, roff, lrow16, td;
     std::vector<uint8_t> lrow8;
@@ -419,6 +556,7 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     P.max_verts = std::max(P.max_verts, (int)tvert.size());
     P.tot_a += nrows;
   });
+  pt.lap("adj tiles: per-tile blobs");
   if (!err.empty()) return err;
   max_rows = max_elems = max_nnz = max_verts = 0;
   long long tot = 0;
@@ -427,7 +565,9 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     max_verts = std::max(max_verts, P.max_verts);
     tot += P.tot_a;
   }
-  merge_parts(parts, blob_ptr, blob, max_head, max_body);
+  merge_parts(parts, blob_ptr, blob, max_head, max_body, nthreads);
+  std::vector<int>().swap(morton_cache);
+  pt.lap("adj tiles: merge");
   row_redundancy = pat.n > 0 ? (double)tot / pat.n : 0;
   return "";
 }

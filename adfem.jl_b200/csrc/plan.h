@@ -17,6 +17,7 @@
 // into one contiguous, 16-byte aligned blob that TMA bulk copies bring on chip (two copies: head, body).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -68,6 +69,11 @@ struct FwdTiles {
   std::vector<long long> blob_ptr;    // 2*ntiles+1 byte offsets
   std::vector<uint8_t> blob;
   double elem_redundancy = 0;
+  // optional, set by the caller before build(): true when a plan whose largest head / body / element count / entry count are these cannot be
+  // launched (shared-memory budget).  build() then gives up with "tile too large" at the first tile that shows it instead of finishing a plan
+  // the caller is going to reject (the caller's tile-size search shrinks the tiles and builds again).
+  std::function<bool(size_t max_head, size_t max_body, int max_elems, int max_nnz)> too_big;
+  std::vector<int> morton_cache;      // rows in Morton order: kept from a rejected build for the next try of the tile-size search, dropped on success
   std::string build(const HostMesh& m, const ScalarPattern& pat, int rows_per_tile, int max_tile_elems, int sym, int nthreads);
 };
 
@@ -93,6 +99,8 @@ struct AdjTiles {
   std::vector<long long> blob_ptr;    // 2*ntiles+1
   std::vector<uint8_t> blob;
   double row_redundancy = 0;
+  std::function<bool(size_t max_head, size_t max_body, int max_elems, int max_nnz)> too_big;      // as in FwdTiles
+  std::vector<int> morton_cache;      // elements in Morton order, as in FwdTiles
   std::string build(const HostMesh& m, const ScalarPattern& pat, int elems_per_tile, int max_tile_nnz, int nthreads);
 };
 

@@ -269,6 +269,43 @@ def test_adjoint_plan_replay(oracle, name, degree):
     assert (seen == 1).all()
 
 
+@pytest.mark.parametrize("dim,degree,ncomp", [(2, 2, 1), (2, 1, 2), (3, 1, 3), (3, 2, 1)])
+def test_symbolic_phase_is_thread_count_independent(oracle, dim, degree, ncomp):
+    """The threaded symbolic phase (adjacency claimed with atomic increments and sorted per row, per-thread column buffers, per-thread tile
+    blobs, early stop of rejected tile sizes) on meshes large enough to be split over the host threads (>= 4096 rows / tiles of 65536+
+    elements), randomly renumbered: pattern, slot map and both tile plans are the same bytes for 1, 2 and 7 threads, and the pattern is the
+    oracle's."""
+    rng = np.random.default_rng(11)
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(190, 180, 1.0 / 190, seed=4, permute=True)
+        mk, o = (lambda: A.Mesh(c, e, degree=degree, host_only=True)), oracle.Mesh2D(c, e, degree=degree)
+    else:
+        c, e = meshgen.tet_grid(26, 26, 22, 1.0 / 24)
+        c = c + rng.uniform(-0.1 / 24, 0.1 / 24, c.shape)
+        perm = rng.permutation(len(c))
+        inv = np.empty_like(perm); inv[perm] = np.arange(len(c))
+        c, e = np.ascontiguousarray(c[perm]), np.ascontiguousarray(inv[e][rng.permutation(len(e))]).astype(e.dtype)
+        mk, o = (lambda: A.Mesh3(c, e, degree=degree, host_only=True)), oracle.Mesh3D(c, e, degree=degree)
+    assert o.nelem >= 65536 and o.ndof >= 4096
+    got = []
+    for threads in (1, 2, 7):
+        m = mk()
+        m.set_option("host_threads", threads)
+        rowptr, colind = m.csr_pattern(1)
+        got.append([rowptr, colind, m.slot_to_nnz()] + [m.plan_array(which, ncomp, a, np.int64 if a == 0 else np.uint8) for which in (0, 1) for a in (0, 1)])
+    for other in got[1:]:
+        for a, b in zip(got[0], other):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+    rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
+    assert np.array_equal(got[0][0], rp) and np.array_equal(got[0][1], ci)
+    dd = o.elem_ndof ** 2
+    blk = ind.reshape(o.nelem, o.g, dd, 2)[:, 0]
+    rows_of_nnz = np.repeat(np.arange(o.ndof), np.diff(rp))
+    s2n = got[0][2].reshape(o.nelem, dd)
+    assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
+
+
 def test_product_has_no_cpu_compute_path():
     """A host-only handle (and any box without CUDA) must refuse to compute: no CPU fallback."""
     import ctypes as C
