@@ -7,7 +7,19 @@
 #include <cstring>
 #include <thread>
 
+#include <sys/mman.h>
+
 namespace adfem {
+
+void advise_huge_pages(void* p, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+  const uintptr_t huge = (uintptr_t)2 << 20;
+  const uintptr_t a = ((uintptr_t)p + huge - 1) & ~(huge - 1), e = ((uintptr_t)p + bytes) & ~(huge - 1);
+  if (p && e > a) (void)madvise((void*)a, e - a, MADV_HUGEPAGE);
+#else
+  (void)p; (void)bytes;
+#endif
+}
 
 namespace {
 // static block partition of [0, n) over host threads (ADFEM_HOST_THREADS, default: the hardware's); element loops below are independent per element
@@ -37,7 +49,12 @@ const int kTetEdges[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
 // through `edges` and `dof[k+nv]` (deps/MFEM/Common.cpp:70-74,133-140).
 struct EdgeNumbering {
   std::vector<int> head, next, hi, lo;
-  explicit EdgeNumbering(int nv) : head(nv, -1) {}
+  // `expect`: a guess of the edge count (the lists are reserved and advised for huge pages: the walk below is one dependent random access after
+  // the other on renumbered meshes; a wrong guess only means the vectors grow the usual way)
+  EdgeNumbering(int nv, size_t expect) {
+    head.reserve(nv); advise_huge_pages(head.data(), (size_t)nv * sizeof(int)); head.assign(nv, -1);
+    for (std::vector<int>* v : {&next, &hi, &lo}) { v->reserve(expect); advise_huge_pages(v->data(), expect * sizeof(int)); }
+  }
   int id(int a, int b) {
     int r = a <= b ? a : b, c = a <= b ? b : a;
     for (int n = head[r]; n >= 0; n = next[n])
@@ -61,6 +78,8 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   // copies and the range check in element / vertex blocks over the host threads (the first touch of the new arrays is most of their cost)
   coords.clear(); coords.reserve((size_t)nv * dim);
   verts.clear(); verts.reserve((size_t)ne * nvl);
+  advise_huge_pages(coords.data(), coords.capacity() * sizeof(double));
+  advise_huge_pages(verts.data(), verts.capacity() * sizeof(int));
   par_elems(nv, [&](long long i0, long long i1) { prefault(coords.data() + (size_t)i0 * dim, (size_t)(i1 - i0) * dim); });
   par_elems(ne, [&](long long e0, long long e1) { prefault(verts.data() + (size_t)e0 * nvl, (size_t)(e1 - e0) * nvl); });
   coords.resize((size_t)nv * dim);
@@ -97,13 +116,14 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   // edges + connectivity.  P1: the connectivity is the vertex list and the edge numbering (an output of the mesh constructor only) is left to
   // ensure_edges(): its sequential first-appearance walk costs more than every other table together on large meshes.
   conn.clear(); conn.reserve((size_t)ne * d);
+  advise_huge_pages(conn.data(), conn.capacity() * sizeof(int));
   par_elems(ne, [&](long long e0, long long e1) { prefault(conn.data() + (size_t)e0 * d, (size_t)(e1 - e0) * d); });
   conn.resize((size_t)ne * d);
   edges_built = false; nedges = 0; edge_lo.clear(); edge_hi.clear();
   if (degree == 1) {
     par_elems(ne, [&](long long e0, long long e1) { memcpy(conn.data() + (size_t)e0 * d, verts.data() + (size_t)e0 * d, (size_t)(e1 - e0) * d * sizeof(int)); });
   } else {
-    EdgeNumbering en(nv);
+    EdgeNumbering en(nv, expected_edges());
     for (int e = 0; e < ne; e++) {
       const int* vi = &verts[(size_t)e * nvl];
       int* ce = &conn[(size_t)e * d];
@@ -124,10 +144,13 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   return "";
 }
 
+// Euler: E = V + F - 1 for a simply connected triangulation; tetrahedral grids have about 7 edges per vertex, 1.2-1.4 per element
+size_t HostMesh::expected_edges() const { return dim == 2 ? (size_t)nv + ne + 64 : (size_t)nv + (size_t)ne * 3 / 2 + 64; }
+
 void HostMesh::ensure_edges() const {
   if (edges_built) return;
   const int nvl = dim + 1, nel = dim == 2 ? 3 : 6;
-  EdgeNumbering en(nv);
+  EdgeNumbering en(nv, expected_edges());
   for (int e = 0; e < ne; e++) {
     const int* vi = &verts[(size_t)e * nvl];
     for (int j = 0; j < nel; j++) en.id(vi[dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0]], vi[dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1]]);

@@ -3,6 +3,7 @@
 // per element.  Everything here is computed once per mesh; the per-Gauss-point shape tables (h, hx, hy,
 // w) are NOT stored — the kernels recompute them from the vertex coordinates.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -10,6 +11,10 @@
 #include "quadrature.h"
 
 namespace adfem {
+
+// Ask for transparent huge pages on freshly reserved, not yet touched storage of a large host array (this image runs THP in "madvise" mode): the
+// symbolic phase walks multi-GB arrays at random addresses on renumbered meshes, where 4 KB pages mean a TLB miss per access.  Advice only.
+void advise_huge_pages(void* p, size_t bytes);
 
 struct HostMesh {
   int dim = 0;          // 2 (triangles) or 3 (tetrahedra)
@@ -26,6 +31,7 @@ struct HostMesh {
   std::vector<int> verts;         // ne x (dim+1) after the orientation fix (det<0 => swap local 0,1)
   std::vector<int> conn;          // ne x d, 0-based dofs: vertices then (P2) nv + edge id, geometry edge order
   mutable std::vector<int> edge_lo, edge_hi;   // edge i joins edge_lo[i] < edge_hi[i] (first-appearance numbering)
+  size_t expected_edges() const;     // reservation guess for the edge numbering
   // P1: numbers the edges on first use (nedges, edge_lo, edge_hi); P2 meshes have them from build().  Not thread-safe (setup-time getter).
   void ensure_edges() const;
 

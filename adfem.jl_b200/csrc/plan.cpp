@@ -21,6 +21,24 @@ int default_threads() {
 
 namespace {
 
+// blocks [cut[t], cut[t+1]) of [0,n) with equal shares of the weight whose running sum is prefix(i) (non-decreasing, prefix(0) = 0): P2 dofs are
+// numbered vertices first, and a vertex row costs three times an edge row
+template <class W> void parallel_for_weighted(long long n, int nthreads, W prefix, const std::function<void(long long, long long, int)>& fn) {
+  if (nthreads <= 1 || n < 4096) { fn(0, n, 0); return; }
+  std::vector<long long> cut(nthreads + 1, n);
+  cut[0] = 0;
+  const long long total = prefix(n);
+  for (int t = 1; t < nthreads; t++) {
+    const long long want = (long long)((double)total * t / nthreads);
+    long long lo = cut[t - 1], hi = n;
+    while (lo < hi) { const long long mid = (lo + hi) / 2; if (prefix(mid) < want) lo = mid + 1; else hi = mid; }
+    cut[t] = lo;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) if (cut[t] < cut[t + 1]) th.emplace_back(fn, cut[t], cut[t + 1], t);
+  for (auto& x : th) x.join();
+}
+
 // ADFEM_DEBUG_PLAN=1: wall time of each host phase on stderr
 struct PhaseTimer {
   const bool on = getenv("ADFEM_DEBUG_PLAN") != nullptr;
@@ -42,6 +60,7 @@ template <class T> void assign_parallel(std::vector<T>& v, size_t n, int nthread
   if (nthreads > 1 && bytes >= ((size_t)8 << 20)) {
     v.reserve(n);
     char* p = reinterpret_cast<char*>(v.data());
+    advise_huge_pages(p, bytes);
     std::vector<std::thread> th;
     const size_t chunk = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
     for (size_t b = 0; b < bytes; b += chunk) th.emplace_back([=] { memset(p + b, 0, std::min(chunk, bytes - b)); });
@@ -187,12 +206,18 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
   const int nbuf = std::max(1, nthreads);
   std::vector<std::vector<int>> colbuf(nbuf);
   std::vector<long long> buf_first(nbuf, -1);
-  parallel_for(n, nthreads, [&](long long b, long long e, int tid) {
+  auto row_work = [&](long long r) { return adj_ptr[r] + r; };       // running sum of (incident elements + 1) per row
+  parallel_for_weighted(n, nthreads, row_work, [&](long long b, long long e, int tid) {
     std::vector<int> cols;
     std::vector<int>& out = colbuf[tid];
     buf_first[tid] = b;
-    out.reserve((size_t)((e - b) * (m.dim == 2 ? (m.degree == 1 ? 8 : 13) : (m.degree == 1 ? 16 : 32))));
+    // untouched reserve (virtual memory only): a row has at most one column per gathered dof; twice the usual row length of the element family
+    out.reserve((size_t)std::min<long long>((adj_ptr[e] - adj_ptr[b]) * d, (e - b) * (m.dim == 2 ? (m.degree == 1 ? 16 : 40) : (m.degree == 1 ? 32 : 64))));
+    advise_huge_pages(out.data(), out.capacity() * sizeof(int));
+    constexpr long long AHEAD = 12;      // rows: on a renumbered mesh every incident element's connectivity is a cache miss; ask for it early
     for (long long r = b; r < e; r++) {
+      if (r + AHEAD < e)
+        for (long long a = adj_ptr[r + AHEAD]; a < adj_ptr[r + AHEAD + 1]; a++) __builtin_prefetch(&m.conn[(size_t)adj_elem[a] * d]);
       const long long deg = adj_ptr[r + 1] - adj_ptr[r];
       if (deg * d <= 40) {                      // the usual row: insert into a small sorted set
         int uq[160], cnt = 0;
@@ -237,8 +262,14 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
     for (auto& x : th) x.join();
   }
   // pass 2: slot map — local entry (e, p, q) lands in row conn[e][p] at the position of conn[e][q] among the row's columns
-  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+  parallel_for_weighted(n, nthreads, row_work, [&](long long b, long long e, int) {
+    constexpr long long AHEAD = 12;
     for (long long r = b; r < e; r++) {
+      if (r + AHEAD < e)
+        for (long long a = adj_ptr[r + AHEAD]; a < adj_ptr[r + AHEAD + 1]; a++) {
+          __builtin_prefetch(&m.conn[(size_t)adj_elem[a] * d]);
+          __builtin_prefetch(&slot_nnz[((size_t)adj_elem[a] * d + adj_loc[a]) * d], 1);
+        }
       const int* cb = colind.data() + rowptr[r];
       const int* cend = colind.data() + rowptr[r + 1];
       for (long long a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
@@ -280,6 +311,7 @@ void tile_vertices(const HostMesh& m, const std::vector<int>& te, std::vector<in
     for (int k = 0; k < nvl; k++)
       tv[(size_t)k * nel + le] = (uint16_t)(std::lower_bound(tvert.begin(), tvert.end(), m.verts[(size_t)te[le] * nvl + k]) - tvert.begin());
   xy.resize(tvert.size() * m.dim);
+  for (size_t i = 0; i < tvert.size(); i++) __builtin_prefetch(&m.coords[(size_t)tvert[i] * m.dim]);
   for (size_t i = 0; i < tvert.size(); i++)
     for (int c = 0; c < m.dim; c++) xy[i * m.dim + c] = m.coords[(size_t)tvert[i] * m.dim + c];
 }
@@ -375,11 +407,23 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     std::vector<Item> items;
     const int* trow = rows.data() + row_ptr[t];
     const int nrows = row_ptr[t + 1] - row_ptr[t];
+    // The rows of a tile are neighbours in space, not in memory: on a renumbered mesh every row and every element below is a cache miss of its
+    // own.  Ask for them a whole tile at a time (the loads are independent) instead of meeting them one after the other.
+    for (int i = 0; i < nrows; i++) { __builtin_prefetch(&pat.adj_ptr[trow[i]]); __builtin_prefetch(&pat.rowptr[trow[i]]); }
+    for (int i = 0; i < nrows; i++) {
+      const int r = trow[i];
+      __builtin_prefetch(&pat.adj_elem[pat.adj_ptr[r]]); __builtin_prefetch(&pat.adj_loc[pat.adj_ptr[r]]);
+      __builtin_prefetch(&pat.colind[pat.rowptr[r]]); __builtin_prefetch(&pat.colind[pat.rowptr[r + 1] - 1]);
+    }
     for (int i = 0; i < nrows; i++) { int r = trow[i]; for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) te.push_back(pat.adj_elem[a]); }
     std::sort(te.begin(), te.end());
     te.erase(std::unique(te.begin(), te.end()), te.end());
     const int nel = (int)te.size();
     if (nel > max_tile_elems || (long long)nel * (sym ? nslot : dd) > 65535) { P.err = "tile too large"; return; }
+    for (int el : te) {
+      __builtin_prefetch(&m.verts[(size_t)el * (m.dim + 1)]);
+      for (int b = 0; b < dd * 4; b += 64) __builtin_prefetch(reinterpret_cast<const char*>(&pat.slot_nnz[(size_t)el * dd]) + b);
+    }
     tile_vertices(m, te, tvert, tv, xy);
     if (tvert.size() > 65535) { P.err = "tile too large"; return; }
     auto code = [&](int lr, int j) { return ent32 ? ((uint32_t)lr | (uint32_t)j << 16) : ((uint32_t)lr | (uint32_t)j << 8); };
@@ -429,9 +473,15 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     if (nsrc > 65535 * 4 || nnz_t > 65535) { P.err = "tile too large"; return; }
     // classes of equal (source count, paired), ascending; tile order kept inside a class (coalesced stores)
     std::vector<int> ord(items.size());
-    for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
     auto key = [&](int a) { return (int)items[a].cnt | items[a].paired << 16; };
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key(a) < key(b); });
+    {   // stable counting sort by (paired, source count): a handful of distinct keys for thousands of items
+      uint32_t maxc = 0;
+      for (const Item& I : items) maxc = std::max(maxc, I.cnt);
+      std::vector<int> start(2 * ((size_t)maxc + 1) + 1, 0);
+      for (const Item& I : items) start[(size_t)I.paired * (maxc + 1) + I.cnt + 1]++;
+      for (size_t b = 1; b < start.size(); b++) start[b] += start[b - 1];
+      for (size_t i = 0; i < items.size(); i++) ord[start[(size_t)items[i].paired * (maxc + 1) + items[i].cnt]++] = (int)i;
+    }
     std::vector<int> cls;            // {count | paired << 16, items, src offset, dst offset} per class
     std::vector<uint16_t> src, dst16;
     std::vector<uint32_t> dst32;
@@ -510,10 +560,15 @@ std::string AdjTiles::build(const HostMesh& m, const ScalarPattern& pat, int EPT
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
     const int nel = (int)te.size();
+    for (int e : te) {          // as in the forward tiles: independent misses, requested together
+      __builtin_prefetch(&m.conn[(size_t)e * d]); __builtin_prefetch(&m.verts[(size_t)e * nvl]);
+      for (int b = 0; b < dd * 4; b += 64) __builtin_prefetch(reinterpret_cast<const char*>(&pat.slot_nnz[(size_t)e * dd]) + b);
+    }
     for (int e : te) { const int* ce = &m.conn[(size_t)e * d]; tr.insert(tr.end(), ce, ce + d); }
     std::sort(tr.begin(), tr.end());
     tr.erase(std::unique(tr.begin(), tr.end()), tr.end());
     const int nrows = (int)tr.size();
+    for (int r : tr) __builtin_prefetch(&pat.rowptr[r]);
     const int lrow_wide = nrows > 256;
     long long acc = 0;
     roff.push_back(0);
