@@ -12,12 +12,12 @@ def tri_grid(m, n, h, version=1, rng=None):
     a = (np.arange(n, dtype=np.int64)[:, None] * (m + 1) + np.arange(m, dtype=np.int64)[None, :]).reshape(-1)   # lower-left node of cell (row ii, col jj)
 
     def fill(el, mask, tris):          # el[cells, 2, 3] <- the two triangles `tris` (offsets from a) of the cells in `mask`, without temporaries
+        if mask is None:               # one contiguous pass over the output
+            np.add(a[:, None, None], np.asarray(tris, dtype=np.int64)[None], out=el)
+            return
         for t in range(2):
             for k in range(3):
-                if mask is None:
-                    np.add(a, tris[t][k], out=el[:, t, k])
-                else:
-                    el[mask, t, k] = a[mask] + tris[t][k]
+                el[mask, t, k] = a[mask] + tris[t][k]
     v1 = ((0, 1, m + 1), (1, m + 1, m + 2))                                                                # MFEM.jl:143-145
     v2 = ((0, m + 2, m + 1), (0, 1, m + 2))                                                                # MFEM.jl:146-148
     el = np.empty((m * n, 2, 3), dtype=np.int64)
@@ -33,9 +33,10 @@ def tri_grid(m, n, h, version=1, rng=None):
     else:
         raise ValueError("version must be 1, 2 or 3")
     elems = el.reshape(2 * m * n, 3)
-    y, x = np.meshgrid(np.arange(n + 1) * float(h), np.arange(m + 1) * float(h), indexing="ij")
-    coords = np.stack([x.reshape(-1), y.reshape(-1)], 1)
-    return coords, elems
+    coords = np.empty((n + 1, m + 1, 2))
+    coords[:, :, 0] = (np.arange(m + 1) * float(h))[None, :]
+    coords[:, :, 1] = (np.arange(n + 1) * float(h))[:, None]
+    return coords.reshape(-1, 2), elems
 
 
 _TE1 = np.array([[1, 2, 3, 5], [2, 3, 4, 8], [3, 5, 7, 8], [2, 3, 5, 8], [2, 5, 6, 8]]) - 1   # MFEM.jl:131-137
