@@ -46,22 +46,22 @@ _TE2 = np.array([[1, 2, 4, 6], [1, 5, 6, 7], [4, 6, 7, 8], [1, 4, 6, 7], [1, 3, 
 def tet_grid(m, n, l, h):
     """(m+1)(n+1)(l+1) nodes, 5mnl tets. Only consistent for m == n (reference quirk Q9)."""
     # coords: for k; for j in 1:m+1; for i in 1:n+1  -> x=(i-1)h fastest
-    k, j, i = np.meshgrid(np.arange(l + 1), np.arange(m + 1), np.arange(n + 1), indexing="ij")
-    coords = np.stack([i.reshape(-1) * float(h), j.reshape(-1) * float(h), k.reshape(-1) * float(h)], 1)
-
-    def ID(i, j, k):   # 1-based in, 0-based out ; MFEM.jl:128-130
-        return (k - 1) * (n + 1) * (m + 1) + (j - 1) * (m + 1) + i - 1
-
-    ii, jj, kk = np.meshgrid(np.arange(1, n + 1, dtype=np.int64), np.arange(1, m + 1, dtype=np.int64),
-                             np.arange(1, l + 1, dtype=np.int64), indexing="ij")   # loops: for i; for j; for k
-    ii, jj, kk = ii.reshape(-1), jj.reshape(-1), kk.reshape(-1)
-    IDX = np.stack([ID(ii, jj, kk), ID(ii + 1, jj, kk), ID(ii, jj + 1, kk), ID(ii + 1, jj + 1, kk),
-                    ID(ii, jj, kk + 1), ID(ii + 1, jj, kk + 1), ID(ii, jj + 1, kk + 1), ID(ii + 1, jj + 1, kk + 1)], 1)
-    even = ((ii + jj + kk) % 2 == 0)
-    e1 = IDX[:, _TE1]          # ncell x 5 x 4
-    e2 = IDX[:, _TE2]
-    elems = np.where(even[:, None, None], e1, e2).reshape(-1, 4)
-    return coords, elems
+    coords = np.empty((l + 1, m + 1, n + 1, 3))
+    coords[..., 0] = (np.arange(n + 1) * float(h))[None, None, :]
+    coords[..., 1] = (np.arange(m + 1) * float(h))[None, :, None]
+    coords[..., 2] = (np.arange(l + 1) * float(h))[:, None, None]
+    # 0-based id of node (i, j, k), 1-based arguments: (k-1)(n+1)(m+1) + (j-1)(m+1) + i-1 (MFEM.jl:128-130); cells in the order of the loops
+    # `for i; for j; for k`.  A cell's 8 corners are its first node plus fixed offsets, its 5 tetrahedra pick 4 corners each (TE1 / TE2 by the
+    # parity of i+j+k): one gather of the 5 x 4 offset table per cell and one in-place add of the cell's first node.
+    sj, sk = m + 1, (n + 1) * (m + 1)
+    i0, j0, k0 = np.arange(n, dtype=np.int64)[:, None, None], np.arange(m, dtype=np.int64)[None, :, None], np.arange(l, dtype=np.int64)[None, None, :]
+    base = (i0 + j0 * sj + k0 * sk).reshape(-1)
+    even = ((i0 + j0 + k0) % 2 == 1).reshape(-1)                 # 1-based (i + j + k) even
+    corner = np.array([0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1], dtype=np.int64)
+    table = np.stack([corner[_TE2], corner[_TE1]])               # [parity][tet][vertex]
+    elems = table[even.astype(np.intp)]                          # ncell x 5 x 4
+    elems += base[:, None, None]
+    return coords.reshape(-1, 3), elems.reshape(-1, 4)
 
 
 def jitter_unstructured(m, n, h, seed=2, jitter=0.3, permute=True):

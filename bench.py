@@ -335,8 +335,9 @@ class DeviceStep:
         self.torch, self._lib, self.L = torch, _lib, _lib.lib()
         self.mesh, self.part, self.op, self.cpg = mesh, part, op, cpg
         self.nc = mesh.dim if op == 2 else 1
-        rowptr, _ = mesh.csr_pattern(1)
-        self.nnz_s = int(rowptr[-1])
+        self.nnz_s = int(self.L.adfem_csr_nnz(mesh.handle, 1))       # builds the symbolic pattern; no host copy of rowptr / colind
+        if self.nnz_s < 0:
+            raise RuntimeError(_lib.last_error())
         self.nnz = self.nc * self.nc * self.nnz_s
         G = mesh.ngauss
         gen = torch.Generator(device="cuda").manual_seed(seed)
@@ -593,12 +594,14 @@ def main():
     E, G = mesh.nelem, mesh.ngauss
     coef_h = dK_h = None
     if case == "2":
-        rowptr, _ = mesh.csr_pattern(1)
+        nnz_scalar = int(L.adfem_csr_nnz(mesh.handle, 1))
+        if nnz_scalar < 0:
+            raise RuntimeError(_lib.last_error())
         xy = A.gauss_nodes_soa(mesh)                              # (2, G): kappa(x, y) = 1 + sin(2 pi x) cos(2 pi y) / 2 is evaluated on the device (setup time)
         gx, gy = torch.from_numpy(xy[0]).cuda(), torch.from_numpy(xy[1]).cuda()
         coef_h = 1 + 0.5 * torch.sin(2 * np.pi * gx) * torch.cos(2 * np.pi * gy)
         del xy, gx, gy
-        dK_h = np.random.default_rng(rank).uniform(-1, 1, int(rowptr[-1]))
+        dK_h = np.random.default_rng(rank).uniform(-1, 1, nnz_scalar)
     step = DeviceStep(mesh, part, op, cpg, coef_h, dK_h, seed=rank, library=bool(args.library_exchange))
     nnz = step.nnz
     step()                                     # builds the mesh-static plans (untimed, reused by every later call)
