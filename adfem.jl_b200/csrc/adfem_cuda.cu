@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -199,23 +200,28 @@ bool detect_tet_grid(const HostMesh& h, int& n, int& l, std::vector<double> ax[3
         const double* p = c + 3 * ((k * n1 + j) * n1 + i);
         if (p[0] != ax[0][i] || p[1] != ax[1][j] || p[2] != ax[2][k]) return false;
       }
-  for (int ci = 0; ci < n; ci++)
-    for (int cj = 0; cj < n; cj++)
-      for (int ck = 0; ck < l; ck++) {
-        const int (*TE)[4] = tet_grid_split_of(ci, cj, ck);
-        const long long cube = ((long long)ci * n + cj) * l + ck;
-        for (int t = 0; t < 5; t++) {
-          int want[4], have[4];
-          for (int q = 0; q < 4; q++) {
-            const int v = TE[t][q];
-            want[q] = (int)(((long long)(ck + (v >> 2)) * n1 + (cj + ((v >> 1) & 1))) * n1 + (ci + (v & 1)));
-            have[q] = h.verts[(size_t)(5 * cube + t) * 4 + q];
+  // every tetrahedron against the generator's: slabs of cube index ci over the host threads (48 M tetrahedra in config 5)
+  std::atomic<bool> same(true);
+  const int nn = n, ll = l;
+  host_parallel_for(n, 0, [&](long long c0, long long c1) {
+    for (int ci = (int)c0; ci < (int)c1 && same.load(std::memory_order_relaxed); ci++)
+      for (int cj = 0; cj < nn; cj++)
+        for (int ck = 0; ck < ll; ck++) {
+          const int (*TE)[4] = tet_grid_split_of(ci, cj, ck);
+          const long long cube = ((long long)ci * nn + cj) * ll + ck;
+          for (int t = 0; t < 5; t++) {
+            int want[4], have[4];
+            for (int q = 0; q < 4; q++) {
+              const int v = TE[t][q];
+              want[q] = (int)(((long long)(ck + (v >> 2)) * n1 + (cj + ((v >> 1) & 1))) * n1 + (ci + (v & 1)));
+              have[q] = h.verts[(size_t)(5 * cube + t) * 4 + q];
+            }
+            std::sort(want, want + 4); std::sort(have, have + 4);
+            for (int q = 0; q < 4; q++) if (want[q] != have[q]) { same.store(false, std::memory_order_relaxed); return; }
           }
-          std::sort(want, want + 4); std::sort(have, have + 4);
-          for (int q = 0; q < 4; q++) if (want[q] != have[q]) return false;
         }
-      }
-  return true;
+  });
+  return same.load();
 }
 // the closed-form rows of tet_grid.cuh must be the rows of the symbolic pattern
 bool tet_pattern_matches(const ScalarPattern& pat, const TetGridTables& tab, int n, int l) {

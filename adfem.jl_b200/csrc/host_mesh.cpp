@@ -21,6 +21,20 @@ void advise_huge_pages(void* p, size_t bytes) {
 #endif
 }
 
+void host_parallel_for(long long n, int nthreads, const std::function<void(long long, long long)>& fn, long long serial_below) {
+  int nt = nthreads;
+  if (nt <= 0) { if (const char* s = getenv("ADFEM_HOST_THREADS")) nt = atoi(s); }
+  if (nt <= 0) { unsigned h = std::thread::hardware_concurrency(); nt = h == 0 ? 4 : (int)std::min(h, 64u); }
+  if (nt <= 1 || n < serial_below) { fn(0LL, n); return; }
+  std::vector<std::thread> th;
+  const long long chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    const long long a = t * chunk, b = std::min(n, a + chunk);
+    if (a < b) th.emplace_back([=, &fn] { fn(a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
 namespace {
 // static block partition of [0, n) over host threads (ADFEM_HOST_THREADS, default: the hardware's); element loops below are independent per element
 template <class F> void par_elems(long long n, F fn) {

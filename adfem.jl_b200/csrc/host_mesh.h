@@ -5,6 +5,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,9 @@ namespace adfem {
 // Ask for transparent huge pages on freshly reserved, not yet touched storage of a large host array (this image runs THP in "madvise" mode): the
 // symbolic phase walks multi-GB arrays at random addresses on renumbered meshes, where 4 KB pages mean a TLB miss per access.  Advice only.
 void advise_huge_pages(void* p, size_t bytes);
+
+// fn(begin, end) on equal blocks of [0, n) over `nthreads` host threads (0: ADFEM_HOST_THREADS, else the hardware's); fn(0, n) when n is small
+void host_parallel_for(long long n, int nthreads, const std::function<void(long long, long long)>& fn, long long serial_below = 16);
 
 struct HostMesh {
   int dim = 0;          // 2 (triangles) or 3 (tetrahedra)

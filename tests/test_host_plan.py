@@ -306,6 +306,22 @@ def test_symbolic_phase_is_thread_count_independent(oracle, dim, degree, ncomp):
     assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
 
 
+def test_plan_manifest_unchanged():
+    """The symbolic phase is a byte-exact contract with the kernels (tile blobs are decoded on the device): digests of pattern, slot map and
+    both tile plans over every element family / numbering / plan kind (scripts/host_plan_manifest.py) against the manifest committed when
+    the kernels were last validated on B200 (tests/golden/host_plan_manifest.txt).  A deliberate change of the blob layout regenerates the
+    manifest together with a GPU validation pass."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "host_plan_manifest.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    want = open(os.path.join(root, "tests", "golden", "host_plan_manifest.txt")).read().split("\n")
+    got = out.stdout.split("\n")
+    assert [l for l in got if l.strip()] == [l for l in want if l.strip()]
+
+
 def test_product_has_no_cpu_compute_path():
     """A host-only handle (and any box without CUDA) must refuse to compute: no CPU fallback."""
     import ctypes as C

@@ -59,7 +59,7 @@ def test_not_structured():
     assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
 
 
-@pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5)])
+@pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5), (20, 9)])
 def test_tet_grid_detection(n, l):
     """Mesh3(n, n, l, h) (5 tetrahedra per cube, parity-alternating) is recognised from its arrays, also on rectilinear non-uniform coordinates;
     the closed-form rows of csrc/tet_grid.cuh are validated against the symbolic pattern when it is built."""
@@ -80,6 +80,10 @@ def test_tet_grid_detection(n, l):
     assert _info(A.Mesh3(c, e, degree=2, host_only=True), _lib.INFO_STRUCTURED) == 0          # P2
     e2 = e.copy(); e2[0] = e2[0][[1, 0, 2, 3]]                                               # another vertex order of the same tetrahedron is fine
     assert _info(A.Mesh3(c, e2, host_only=True), _lib.INFO_STRUCTURED) == 2
+    if n >= 16:                                    # the element check runs in slabs over the host threads: one foreign tetrahedron in any slab is found
+        for at in (3, len(e) // 2 + 7, len(e) - 2):
+            e4 = e.copy(); e4[at, 3] = (e4[at, 3] + 2 * (n + 1)) % len(c)
+            assert _info(A.Mesh3(c, e4, host_only=True), _lib.INFO_STRUCTURED) == 0
 
 
 # ---------------------------------------------------------------------------------------------- GPU
