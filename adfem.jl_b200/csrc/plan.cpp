@@ -116,28 +116,61 @@ struct Morton {
   }
 };
 
-// ids sorted by Morton code of their position
+struct KeyId {
+  uint64_t key; int id;
+  bool operator<(const KeyId& o) const { return key != o.key ? key < o.key : id < o.id; }
+};
+
+// Stable LSD radix sort by key, 11 bits per pass, blocks of the input over the threads (per-thread histograms, exclusive offsets per
+// (digit, thread)); passes whose digit is the same for every key are skipped.  The input is in ascending id order, so equal keys stay in
+// ascending id order: the result is the (key, id)-lexicographic order a comparison sort of the pairs gives.
+void radix_sort_by_key(std::vector<KeyId>& a, int nthreads) {
+  const long long n = (long long)a.size();
+  constexpr int BITS = 11, NB = 1 << BITS;
+  const int T = std::max(1, nthreads);
+  uint64_t any = 0, all = ~0ULL;
+  for (const KeyId& p : a) { any |= p.key; all &= p.key; }
+  const uint64_t varying = any ^ all;
+  std::vector<KeyId> b;
+  assign_parallel(b, (size_t)n, nthreads);
+  std::vector<long long> cut(T + 1);
+  for (int t = 0; t <= T; t++) cut[t] = n * t / T;
+  std::vector<std::vector<long long>> hist(T, std::vector<long long>(NB));
+  for (int shift = 0; shift < 64; shift += BITS) {
+    if (((varying >> shift) & (NB - 1)) == 0) continue;
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
+        std::vector<long long>& h = hist[t];
+        std::fill(h.begin(), h.end(), 0);
+        for (long long i = cut[t]; i < cut[t + 1]; i++) h[(a[i].key >> shift) & (NB - 1)]++;
+      });
+      for (auto& x : th) x.join();
+    }
+    long long run = 0;
+    for (int dgt = 0; dgt < NB; dgt++)
+      for (int t = 0; t < T; t++) { const long long c = hist[t][dgt]; hist[t][dgt] = run; run += c; }
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
+        std::vector<long long>& h = hist[t];
+        for (long long i = cut[t]; i < cut[t + 1]; i++) b[h[(a[i].key >> shift) & (NB - 1)]++] = a[i];
+      });
+      for (auto& x : th) x.join();
+    }
+    a.swap(b);
+  }
+}
+
+// ids sorted by (Morton code of their position, id)
 void morton_order(long long n, int nthreads, const std::function<uint64_t(long long)>& code, std::vector<int>& order) {
-  std::vector<std::pair<uint64_t, int>> keyed(n);
-  parallel_for(n, nthreads, [&](long long b, long long e, int) { for (long long i = b; i < e; i++) keyed[i] = {code(i), (int)i}; });
-  // sort blocks in parallel, then merge pairwise
-  int nb = 1;
-  while (nb < nthreads && n / (nb * 2) > 65536) nb *= 2;
-  std::vector<long long> cut(nb + 1);
-  for (int i = 0; i <= nb; i++) cut[i] = n * i / nb;
-  {
-    std::vector<std::thread> th;
-    for (int i = 0; i < nb; i++) th.emplace_back([&, i] { std::sort(keyed.begin() + cut[i], keyed.begin() + cut[i + 1]); });
-    for (auto& t : th) t.join();
-  }
-  for (int w = 1; w < nb; w *= 2) {
-    std::vector<std::thread> th;
-    for (int i = 0; i + w < nb; i += 2 * w)
-      th.emplace_back([&, i, w] { std::inplace_merge(keyed.begin() + cut[i], keyed.begin() + cut[i + w], keyed.begin() + cut[std::min(nb, i + 2 * w)]); });
-    for (auto& t : th) t.join();
-  }
-  order.resize(n);
-  for (long long i = 0; i < n; i++) order[i] = keyed[i].second;
+  std::vector<KeyId> keyed;
+  assign_parallel(keyed, (size_t)n, nthreads);
+  parallel_for(n, nthreads, [&](long long b, long long e, int) { for (long long i = b; i < e; i++) keyed[i] = KeyId{code(i), (int)i}; });
+  if (nthreads > 1 && n >= 65536) radix_sort_by_key(keyed, nthreads);
+  else std::sort(keyed.begin(), keyed.end());
+  assign_parallel(order, (size_t)n, nthreads);
+  parallel_for(n, nthreads, [&](long long b, long long e, int) { for (long long i = b; i < e; i++) order[i] = keyed[i].id; });
 }
 
 }  // namespace
