@@ -141,6 +141,10 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
     for (int e = 0; e < ne; e++) {
       const int* vi = &verts[(size_t)e * nvl];
       int* ce = &conn[(size_t)e * d];
+      if (e + 8 < ne) {          // the chain heads of the vertices a few elements ahead (random addresses on a renumbered mesh)
+        const int* vn = &verts[(size_t)(e + 8) * nvl];
+        for (int k = 0; k < nvl; k++) __builtin_prefetch(&en.head[vn[k]]);
+      }
       for (int k = 0; k < nvl; k++) ce[k] = vi[k];
       for (int j = 0; j < nel; j++) {
         int a = dim == 2 ? kTriEdges[j][0] : kTetEdges[j][0], b = dim == 2 ? kTriEdges[j][1] : kTetEdges[j][1];

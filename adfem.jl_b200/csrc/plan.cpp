@@ -188,7 +188,10 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
   parallel_for(nslot_rows, nthreads, [&](long long b, long long e, int) {
     long long* cnt = adj_ptr.data() + 1;
     const int* c = m.conn.data();
-    for (long long i = b; i < e; i++) __atomic_fetch_add(&cnt[c[i]], 1LL, __ATOMIC_RELAXED);
+    for (long long i = b; i < e; i++) {
+      if (i + 24 < e) __builtin_prefetch(&cnt[c[i + 24]], 1);
+      __atomic_fetch_add(&cnt[c[i]], 1LL, __ATOMIC_RELAXED);
+    }
   });
   for (int r = 0; r < n; r++) adj_ptr[r + 1] += adj_ptr[r];
   assign_parallel(adj_elem, (size_t)nslot_rows, nthreads); assign_parallel(adj_loc, (size_t)nslot_rows, nthreads);
@@ -198,8 +201,12 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
     parallel_for(n, nthreads, [&](long long b, long long e, int) { memcpy(cur.data() + b, adj_ptr.data() + b, (size_t)(e - b) * sizeof(long long)); });
     parallel_for(m.ne, nthreads, [&](long long b, long long e, int) {
       const int* c = m.conn.data() + (size_t)b * d;
+      const int* cend = m.conn.data() + (size_t)e * d;
       for (long long el = b; el < e; el++)
-        for (int p = 0; p < d; p++, c++) { const long long at = __atomic_fetch_add(&cur[*c], 1LL, __ATOMIC_RELAXED); adj_elem[at] = (int)el; adj_loc[at] = (uint8_t)p; }
+        for (int p = 0; p < d; p++, c++) {
+          if (c + 24 < cend) __builtin_prefetch(&cur[c[24]], 1);
+          const long long at = __atomic_fetch_add(&cur[*c], 1LL, __ATOMIC_RELAXED); adj_elem[at] = (int)el; adj_loc[at] = (uint8_t)p;
+        }
     });
   }
   parallel_for(n, nthreads, [&](long long b, long long e, int) {
