@@ -439,7 +439,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
   pt.lap("fwd tiles: tile sort, max row");
   std::vector<PartOut> parts;
   std::string err = run_parts(ntiles, nthreads, parts, too_big, [&](int t, PartOut& P) {
-    std::vector<int> te, tvert, jitem;
+    std::vector<int> te, tvert, jitem, hkey, hval;
     std::vector<uint16_t> tv, rlen, pool;
     std::vector<double> xy;
     std::vector<uint32_t> rstart;
@@ -467,6 +467,24 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
     tile_vertices(m, te, tvert, tv, xy);
     if (tvert.size() > 65535) { P.err = "tile too large"; return; }
     auto code = [&](int lr, int j) { return ent32 ? ((uint32_t)lr | (uint32_t)j << 16) : ((uint32_t)lr | (uint32_t)j << 8); };
+    // dof id -> tile row (scalar plans ask it for every CSR entry): open addressing, at most half full
+    int hbits = 4;
+    while ((1 << hbits) < 2 * nrows) hbits++;
+    hkey.assign((size_t)1 << hbits, -1); hval.resize((size_t)1 << hbits);
+    const uint32_t hmask = (1u << hbits) - 1;
+    auto hslot = [&](int c) { return ((uint32_t)c * 2654435761u) >> (32 - hbits); };
+    if (sym)
+      for (int lr = 0; lr < nrows; lr++) {
+        uint32_t at = hslot(trow[lr]);
+        while (hkey[at] >= 0) at = (at + 1) & hmask;
+        hkey[at] = trow[lr]; hval[at] = lr;
+      }
+    auto tile_row_of = [&](int c) {          // -1: not a row of this tile
+      for (uint32_t at = hslot(c);; at = (at + 1) & hmask) {
+        if (hkey[at] == c) return hval[at];
+        if (hkey[at] < 0) return -1;
+      }
+    };
     size_t nsrc = 0, nnz_t = 0;
     for (int lr = 0; lr < nrows; lr++) {
       const int r = trow[lr];
@@ -484,9 +502,8 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
         const int c = pat.colind[rs + j];
         int paired = 0; uint32_t d1 = 0;
         if (sym && c != r) {                       // is the mirrored entry (c, r) produced by this tile too?
-          const int* it = std::lower_bound(trow, trow + nrows, c);
-          if (it != trow + nrows && *it == c) {
-            const int lc = (int)(it - trow);
+          const int lc = tile_row_of(c);
+          if (lc >= 0) {
             if (lc < lr) continue;                  // already emitted from the other side
             const int* cb = &pat.colind[pat.rowptr[c]];
             const int* ce = &pat.colind[pat.rowptr[c + 1]];
