@@ -781,13 +781,14 @@ int adfem_mesh_create(adfem_mesh** out, int dim, const double* vertices, int ver
     const HostMesh& h = m->hm;
     CU_TRY(upload(m->coords, h.coords));
     const int nvl = h.dim + 1;
-    std::vector<int> vs((size_t)h.ne * nvl), cs((size_t)h.ne * h.d);
-    for (int e = 0; e < h.ne; e++) {
-      for (int k = 0; k < nvl; k++) vs[(size_t)k * h.ne + e] = h.verts[(size_t)e * nvl + k];
-      for (int k = 0; k < h.d; k++) cs[(size_t)k * h.ne + e] = h.conn[(size_t)e * h.d + k];
+    {
+      const std::vector<int> vs = soa_copy(h.verts, h.ne, nvl);       // [k][e]: what the kernels read
+      CU_TRY(upload(m->verts, vs));
     }
-    CU_TRY(upload(m->verts, vs));
-    CU_TRY(upload(m->conn, cs));
+    {
+      const std::vector<int> cs = soa_copy(h.conn, h.ne, h.d);
+      CU_TRY(upload(m->conn, cs));
+    }
     m->dm.dim = h.dim; m->dm.ne = h.ne; m->dm.nv = h.nv; m->dm.d = h.d; m->dm.g = h.g; m->dm.ndof = h.ndof;
     m->dm.coords = m->coords.p; m->dm.verts = m->verts.p; m->dm.conn = m->conn.p; m->dm.rule = h.rule;
     if (m->grid_ok) { CU_TRY(upload(m->grid_xs, grid_xs)); CU_TRY(upload(m->grid_ys, grid_ys)); }

@@ -35,6 +35,23 @@ void host_parallel_for(long long n, int nthreads, const std::function<void(long 
   for (auto& x : th) x.join();
 }
 
+std::vector<int> soa_copy(const std::vector<int>& aos, long long ne, int kcount) {
+  std::vector<int> out;
+  const size_t total = (size_t)ne * kcount;
+  out.reserve(total);
+  advise_huge_pages(out.data(), total * sizeof(int));
+  int* o = out.data();
+  host_parallel_for((long long)total, 0, [&](long long a, long long b) { memset(static_cast<void*>(o + a), 0, (size_t)(b - a) * sizeof(int)); }, 1 << 20);
+  out.resize(total);
+  o = out.data();
+  const int* in = aos.data();
+  host_parallel_for(ne, 0, [&](long long e0, long long e1) {
+    for (long long e = e0; e < e1; e++)
+      for (int k = 0; k < kcount; k++) o[(size_t)k * ne + e] = in[(size_t)e * kcount + k];
+  }, 1 << 16);
+  return out;
+}
+
 namespace {
 // static block partition of [0, n) over host threads (ADFEM_HOST_THREADS, default: the hardware's); element loops below are independent per element
 template <class F> void par_elems(long long n, F fn) {

@@ -20,6 +20,10 @@ void advise_huge_pages(void* p, size_t bytes);
 // fn(begin, end) on equal blocks of [0, n) over `nthreads` host threads (0: ADFEM_HOST_THREADS, else the hardware's); fn(0, n) when n is small
 void host_parallel_for(long long n, int nthreads, const std::function<void(long long, long long)>& fn, long long serial_below = 16);
 
+// Struct-of-arrays copy of an element table for the device: out[k * ne + e] = aos[e * kcount + k] (the kernels read index k of 32 consecutive
+// elements with one coalesced load).  Element blocks over the host threads, pages of the copy first touched by them.
+std::vector<int> soa_copy(const std::vector<int>& aos, long long ne, int kcount);
+
 struct HostMesh {
   int dim = 0;          // 2 (triangles) or 3 (tetrahedra)
   int nv = 0;           // vertices

@@ -123,7 +123,7 @@ class Mesh(_MeshBase):
                 lorder = 2
         elif len(args) >= 3 and np.isscalar(args[0]) and np.isscalar(args[1]):
             m, n, h = int(args[0]), int(args[1]), float(args[2])
-            coords, elems = meshgen.tri_grid(m, n, h, version=version)
+            coords, elems = meshgen.tri_grid(m, n, h, version=version, dtype=np.int32 if (m + 1) * (n + 1) < 2 ** 31 else np.int64)
         else:
             coords, elems = args[0], args[1]
             if len(args) > 2:
@@ -143,7 +143,7 @@ class Mesh3(_MeshBase):
     def __init__(self, *args, order=-1, degree=1, lorder=-1, host_only=False):
         if len(args) >= 4 and np.isscalar(args[0]):
             m, n, l, h = int(args[0]), int(args[1]), int(args[2]), float(args[3])
-            coords, elems = meshgen.tet_grid(m, n, l, h)
+            coords, elems = meshgen.tet_grid(m, n, l, h, dtype=np.int32 if (m + 1) * (n + 1) * (l + 1) < 2 ** 31 else np.int64)
         else:
             coords, elems = args[0], args[1]
             if len(args) > 2:

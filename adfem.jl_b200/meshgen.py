@@ -7,20 +7,22 @@ Returned connectivity is 0-based (the Julia arrays are 1-based).
 import numpy as np
 
 
-def tri_grid(m, n, h, version=1, rng=None):
-    """(m+1)(n+1) nodes, 2mn triangles. version 1/2 = the two diagonal directions, 3 = random per cell."""
-    a = (np.arange(n, dtype=np.int64)[:, None] * (m + 1) + np.arange(m, dtype=np.int64)[None, :]).reshape(-1)   # lower-left node of cell (row ii, col jj)
+def tri_grid(m, n, h, version=1, rng=None, dtype=np.int64):
+    """(m+1)(n+1) nodes, 2mn triangles. version 1/2 = the two diagonal directions, 3 = random per cell.  `dtype`: integer type of the
+    connectivity (the mesh constructors ask for int32, what the library takes, when the node ids fit)."""
+    assert np.dtype(dtype) == np.int64 or (m + 1) * (n + 1) < 2 ** 31
+    a = (np.arange(n, dtype=dtype)[:, None] * (m + 1) + np.arange(m, dtype=dtype)[None, :]).reshape(-1)   # lower-left node of cell (row ii, col jj)
 
     def fill(el, mask, tris):          # el[cells, 2, 3] <- the two triangles `tris` (offsets from a) of the cells in `mask`, without temporaries
         if mask is None:               # one contiguous pass over the output
-            np.add(a[:, None, None], np.asarray(tris, dtype=np.int64)[None], out=el)
+            np.add(a[:, None, None], np.asarray(tris, dtype=dtype)[None], out=el)
             return
         for t in range(2):
             for k in range(3):
                 el[mask, t, k] = a[mask] + tris[t][k]
     v1 = ((0, 1, m + 1), (1, m + 1, m + 2))                                                                # MFEM.jl:143-145
     v2 = ((0, m + 2, m + 1), (0, 1, m + 2))                                                                # MFEM.jl:146-148
-    el = np.empty((m * n, 2, 3), dtype=np.int64)
+    el = np.empty((m * n, 2, 3), dtype=dtype)
     if version == 1:
         fill(el, None, v1)
     elif version == 2:
@@ -43,8 +45,9 @@ _TE1 = np.array([[1, 2, 3, 5], [2, 3, 4, 8], [3, 5, 7, 8], [2, 3, 5, 8], [2, 5, 
 _TE2 = np.array([[1, 2, 4, 6], [1, 5, 6, 7], [4, 6, 7, 8], [1, 4, 6, 7], [1, 3, 4, 7]]) - 1   # MFEM.jl:138-144
 
 
-def tet_grid(m, n, l, h):
-    """(m+1)(n+1)(l+1) nodes, 5mnl tets. Only consistent for m == n (reference quirk Q9)."""
+def tet_grid(m, n, l, h, dtype=np.int64):
+    """(m+1)(n+1)(l+1) nodes, 5mnl tets. Only consistent for m == n (reference quirk Q9).  `dtype`: integer type of the connectivity."""
+    assert np.dtype(dtype) == np.int64 or (m + 1) * (n + 1) * (l + 1) < 2 ** 31
     # coords: for k; for j in 1:m+1; for i in 1:n+1  -> x=(i-1)h fastest
     coords = np.empty((l + 1, m + 1, n + 1, 3))
     coords[..., 0] = (np.arange(n + 1) * float(h))[None, None, :]
@@ -54,10 +57,10 @@ def tet_grid(m, n, l, h):
     # `for i; for j; for k`.  A cell's 8 corners are its first node plus fixed offsets, its 5 tetrahedra pick 4 corners each (TE1 / TE2 by the
     # parity of i+j+k): one gather of the 5 x 4 offset table per cell and one in-place add of the cell's first node.
     sj, sk = m + 1, (n + 1) * (m + 1)
-    i0, j0, k0 = np.arange(n, dtype=np.int64)[:, None, None], np.arange(m, dtype=np.int64)[None, :, None], np.arange(l, dtype=np.int64)[None, None, :]
+    i0, j0, k0 = np.arange(n, dtype=dtype)[:, None, None], np.arange(m, dtype=dtype)[None, :, None], np.arange(l, dtype=dtype)[None, None, :]
     base = (i0 + j0 * sj + k0 * sk).reshape(-1)
     even = ((i0 + j0 + k0) % 2 == 1).reshape(-1)                 # 1-based (i + j + k) even
-    corner = np.array([0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1], dtype=np.int64)
+    corner = np.array([0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1], dtype=dtype)
     table = np.stack([corner[_TE2], corner[_TE1]])               # [parity][tet][vertex]
     elems = table[even.astype(np.intp)]                          # ncell x 5 x 4
     elems += base[:, None, None]

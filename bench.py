@@ -288,8 +288,7 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
         note = (f"config 5: P1 tetrahedral elasticity, per-Gauss-point 6x6 Voigt tangent, the fixed global mesh Mesh3({n},{n},{l},1/{n}) = {5 * n * n * l} tetrahedra "
                 f"in z-slabs of {l // world} cube layers per GPU")
         if world == 1:
-            c, e = meshgen.tet_grid(n, n, l, 1.0 / n)
-            return A.Mesh3(c, e, **kw), None, 2, 36, note, "strong"
+            return A.Mesh3(n, n, l, 1.0 / n, **kw), None, 2, 36, note, "strong"
         part = adist.structured_slab3(n, l, 1.0 / n, rank, world, **kw)
         return part.mesh, part, 2, 36, note, "strong"
     raise SystemExit("unknown case " + case)

@@ -306,6 +306,40 @@ def test_symbolic_phase_is_thread_count_independent(oracle, dim, degree, ncomp):
     assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
 
 
+def test_device_path_host_helpers(tmp_path):
+    """Host helpers the library only reaches with a GPU (adfem_mesh_create's struct-of-arrays copies of the element tables), built for the host
+    with g++ from the product's own source (tests/host_emul/host_check.cpp + csrc/host_mesh.cpp) and checked against numpy, below and above the
+    size where they split the work over threads, for 1 and 5 threads."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    so = str(tmp_path / "libhost_check.so")
+    csrc = os.path.join(root, "adfem.jl_b200", "csrc")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-I", csrc, os.path.join(root, "tests", "host_emul", "host_check.cpp"),
+                           os.path.join(csrc, "host_mesh.cpp"), "-o", so])
+    L = C.CDLL(so)
+    rng = np.random.default_rng(3)
+    old = os.environ.get("ADFEM_HOST_THREADS")
+    try:
+        for threads in ("1", "5"):
+            os.environ["ADFEM_HOST_THREADS"] = threads
+            for ne, k in ((0, 3), (1, 4), (1000, 3), (70001, 6), (400003, 4), (150000, 10)):
+                aos = rng.integers(0, 2 ** 31 - 1, size=(ne, k), dtype=np.int32)
+                out = np.full(ne * k, -7, dtype=np.int32)
+                assert L.check_soa_copy(aos.ctypes.data_as(C.c_void_p), C.c_longlong(ne), C.c_int(k), out.ctypes.data_as(C.c_void_p)) == 0
+                assert np.array_equal(out.reshape(k, ne), aos.T)
+    finally:
+        if old is None:
+            os.environ.pop("ADFEM_HOST_THREADS", None)
+        else:
+            os.environ["ADFEM_HOST_THREADS"] = old
+
+
 def test_plan_manifest_unchanged():
     """The symbolic phase is a byte-exact contract with the kernels (tile blobs are decoded on the device): digests of pattern, slot map and
     both tile plans over every element family / numbering / plan kind (scripts/host_plan_manifest.py) against the manifest committed when
