@@ -98,6 +98,7 @@ struct adfem_mesh {
   bool grid_ok = false;
   bool grid_mapped = false;                 // structured connectivity, non-rectilinear node positions: scalar CSR kernels only (MAPPED)
   int grid_m = 0, grid_n = 0, opt_structured = 1, opt_grid_rows = 0, opt_grid_occupancy = 2;
+  bool opt_grid_pattern = true;              // symbolic tables of the structured triangulation in closed form (ScalarPattern::build_tri_grid)
   int opt_grid_elast = 1;                   // P1 elasticity on Mesh(m,n,h) / Mesh3(n,n,l,h): index-free kernels of grid_elast.cuh / tet_grid.cuh (measured round 2: 0.63 / 0.24 of roofline against 0.46 / 0.11)
   int opt_tet_node = 1;                     // config 5 forward: 1 = x-fastest Gauss pre-sum + one thread per (node, component) (tet_node.cuh), 0 = one warp per node (tet_grid.cuh),
                                             // 2 = as 1 with the 32-tetrahedron incidence list split over two warps (measured: 5.55 -> 5.75 ms at 10.5 M tetrahedra, no gain)
@@ -285,7 +286,8 @@ int ensure_dev_slot_nnz(adfem_mesh* m) {
 
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
-  std::string err = m->pat.build(m->hm, nthreads_of(m));
+  // the structured triangulation (rectilinear or mapped) gets its tables from index arithmetic; option "structured_pattern" = 0: the general build
+  std::string err = (m->grid_ok && m->opt_grid_pattern) ? m->pat.build_tri_grid(m->hm, m->grid_m, m->grid_n, nthreads_of(m)) : m->pat.build(m->hm, nthreads_of(m));
   if (!err.empty()) return fail("symbolic: " + err);
   m->has_pattern = true;
   if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;
@@ -870,6 +872,7 @@ int adfem_set_option(adfem_mesh* m, const char* key, long long value) {
   else if (k == "coef_presum") { if (m->opt_coef_presum != (value != 0) && m->hm.dim == 3) m->fwd_plans.clear(); m->opt_coef_presum = value != 0; }      // 3-D: the tile size depends on it
   else if (k == "grid_limit") m->opt_grid_limit = (int)value;
   else if (k == "structured") m->opt_structured = value != 0;
+  else if (k == "structured_pattern") { if (m->has_pattern) return fail("structured_pattern must be set before the symbolic phase has run"); m->opt_grid_pattern = value != 0; }
   else if (k == "structured_elasticity") m->opt_grid_elast = value != 0;
   else if (k == "tet_node") m->opt_tet_node = (int)value;
   else if (k == "tet_chunks") m->opt_tet_chunks = (int)value;

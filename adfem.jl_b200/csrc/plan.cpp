@@ -326,6 +326,76 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
 
 // ------------------------------------------------------------------------------------------------
 namespace {
+// node (i, j) of Mesh(gm, gn, h): incident (element, local vertex) pairs in ascending element order and the ascending columns of its row
+struct GridNode {
+  int nadj = 0, ncol = 0;
+  int elem[6]; uint8_t loc[6]; int col[7];
+  GridNode(int i, int j, int gm, int gn) {
+    const long long r = (long long)i * (gm + 1) + j;
+    auto cell = [&](int ci, int cj) { return 2 * ((long long)ci * gm + cj); };
+    if (i >= 1 && j >= 1) { elem[nadj] = (int)(cell(i - 1, j - 1) + 1); loc[nadj++] = 2; }            // top-right corner of the cell below-left
+    if (i >= 1 && j < gm) { elem[nadj] = (int)cell(i - 1, j); loc[nadj++] = 2; elem[nadj] = (int)(cell(i - 1, j) + 1); loc[nadj++] = 0; }    // top-left corner
+    if (i < gn && j >= 1) { elem[nadj] = (int)cell(i, j - 1); loc[nadj++] = 1; elem[nadj] = (int)(cell(i, j - 1) + 1); loc[nadj++] = 1; }    // bottom-right corner
+    if (i < gn && j < gm) { elem[nadj] = (int)cell(i, j); loc[nadj++] = 0; }                            // bottom-left corner
+    if (i >= 1) col[ncol++] = (int)(r - (gm + 1));
+    if (i >= 1 && j < gm) col[ncol++] = (int)(r - (gm + 1) + 1);
+    if (j >= 1) col[ncol++] = (int)(r - 1);
+    col[ncol++] = (int)r;
+    if (j < gm) col[ncol++] = (int)(r + 1);
+    if (i < gn && j >= 1) col[ncol++] = (int)(r + (gm + 1) - 1);
+    if (i < gn) col[ncol++] = (int)(r + (gm + 1));
+  }
+  int position(int c) const { int p = 0; while (p < ncol && col[p] != c) p++; return p; }
+};
+}  // namespace
+
+std::string ScalarPattern::build_tri_grid(const HostMesh& m, int gm, int gn, int nthreads) {
+  if (m.dim != 2 || m.degree != 1 || m.d != 3 || gm < 1 || gn < 1 || (long long)(gm + 1) * (gn + 1) != m.ndof || 2LL * gm * gn != m.ne)
+    return "not the structured triangulation";
+  PhaseTimer pt;
+  n = m.ndof;
+  const long long nslot_rows = 3LL * m.ne, w = gm + 1;
+  if (nslot_rows > 2147483647LL) return "ne*elem_ndof exceeds 32-bit";
+  assign_parallel(adj_ptr, (size_t)n + 1, nthreads);
+  assign_parallel(rowptr, (size_t)n + 1, nthreads);
+  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+    for (long long r = b; r < e; r++) { const GridNode g((int)(r / w), (int)(r % w), gm, gn); adj_ptr[r + 1] = g.nadj; rowptr[r + 1] = g.ncol; }
+  });
+  for (long long r = 0; r < n; r++) { adj_ptr[r + 1] += adj_ptr[r]; rowptr[r + 1] += rowptr[r]; }
+  nnz = rowptr[n];
+  if (adj_ptr[n] != nslot_rows) return "structured triangulation: incidence count mismatch";
+  if (nnz > 4294967295LL) return "scalar nnz exceeds 32-bit slot map";
+  assign_parallel(adj_elem, (size_t)nslot_rows, nthreads); assign_parallel(adj_loc, (size_t)nslot_rows, nthreads);
+  assign_parallel(colind, (size_t)nnz, nthreads);
+  assign_parallel(slot_nnz, (size_t)m.ne * 9, nthreads);
+  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+    for (long long r = b; r < e; r++) {
+      const GridNode g((int)(r / w), (int)(r % w), gm, gn);
+      for (int a = 0; a < g.nadj; a++) { adj_elem[adj_ptr[r] + a] = g.elem[a]; adj_loc[adj_ptr[r] + a] = g.loc[a]; }
+      for (int c = 0; c < g.ncol; c++) colind[rowptr[r] + c] = g.col[c];
+    }
+  });
+  pt.lap("pattern (structured): adjacency, columns");
+  // slot map: local entry (p, q) of a triangle lands in the row of its vertex p at the position of its vertex q
+  parallel_for((long long)gn * gm, nthreads, [&](long long b, long long e, int) {
+    for (long long c = b; c < e; c++) {
+      const int ci = (int)(c / gm), cj = (int)(c % gm);
+      const GridNode bl(ci, cj, gm, gn), br(ci, cj + 1, gm, gn), tl(ci + 1, cj, gm, gn), tr(ci + 1, cj + 1, gm, gn);
+      const long long a = (long long)ci * w + cj;
+      const GridNode* node[2][3] = {{&bl, &br, &tl}, {&tl, &br, &tr}};
+      const long long vert[2][3] = {{a, a + 1, a + w}, {a + w, a + 1, a + w + 1}};
+      for (int t = 0; t < 2; t++)
+        for (int p = 0; p < 3; p++)
+          for (int q = 0; q < 3; q++)
+            slot_nnz[((size_t)(2 * c + t) * 3 + p) * 3 + q] = (uint32_t)(rowptr[vert[t][p]] + node[t][p]->position((int)vert[t][q]));
+    }
+  });
+  pt.lap("pattern (structured): slot map");
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
 struct BlobWriter {
   std::vector<uint8_t>& out;
   size_t base;

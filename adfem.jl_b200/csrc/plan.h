@@ -35,6 +35,10 @@ struct ScalarPattern {
   std::vector<int> adj_elem;        // ne*d
   std::vector<uint8_t> adj_loc;     // ne*d
   std::string build(const HostMesh& m, int nthreads);
+  // The same tables for the structured triangulation Mesh(gm, gn, h), version 1, P1 (connectivity as detect_tri_grid of adfem_cuda.cu verifies
+  // it: cell (ci, cj) with first node a = ci (gm+1) + cj holds the triangles (a, a+1, a+gm+1) and (a+gm+1, a+1, a+gm+2)), from index arithmetic:
+  // no counting sort, no per-row sets, no searches in the connectivity.  Byte-identical to build() (tests/test_structured.py).
+  std::string build_tri_grid(const HostMesh& m, int gm, int gn, int nthreads);
 };
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }

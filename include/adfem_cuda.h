@@ -159,7 +159,7 @@ int adfem_mesh_element_to_vertices(const adfem_mesh* m, long long* elems);    /*
 int adfem_mesh_gauss(const adfem_mesh* m, double* xyz);                       /* dim blocks of ngauss (column-major) */
 int adfem_mesh_gauss_weights(const adfem_mesh* m, double* w);
 int adfem_mesh_measure(const adfem_mesh* m, double* a);                       /* Heron area (2-D) / volume (3-D) */
-int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads", "smem_budget", "tile_threads", "pipeline", "coef_prefetch", "coef_presum", "structured", "structured_elasticity", "structured_tet_scalar", "row_gather", "grid_rows", "grid_limit", "area_formula_csr", "area_formula_coo" */
+int adfem_set_option(adfem_mesh* m, const char* key, long long value);        /* "rows_per_tile", "elems_per_tile", "adjoint_tiled", "host_threads", "smem_budget", "tile_threads", "pipeline", "coef_prefetch", "coef_presum", "structured", "structured_pattern", "structured_elasticity", "structured_tet_scalar", "row_gather", "grid_rows", "grid_limit", "area_formula_csr", "area_formula_coo" */
 
 /* Mesh-static symbolic phase (what Julia's sparse() / TF's sparse ops redo on every call downstream of the
  * reference's COO, src/MFEM/MCore.jl:118-119).  ncomp = 1: scalar operators, n = ndof.  ncomp = dim: the

@@ -59,6 +59,38 @@ def test_not_structured():
     assert _info(A.Mesh(c, e, host_only=True), _lib.INFO_STRUCTURED) == 0
 
 
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 6), (6, 1), (2, 2), (7, 5), (70, 64), (300, 3)])
+@pytest.mark.parametrize("mapped", [False, True])
+def test_closed_form_symbolic_tables(oracle, m, n, mapped):
+    """Mesh(m, n, h): the symbolic tables from index arithmetic (ScalarPattern::build_tri_grid, the default on the structured triangulation) are
+    the bytes the general build produces (option structured_pattern = 0) — pattern, slot map, both tile plans (which read the dof -> element
+    adjacency) — for 1 and 3 host threads, and the pattern is the oracle's."""
+    c, e = meshgen.tri_grid(m, n, 0.25)
+    if mapped:
+        rng = np.random.default_rng(m * 31 + n)
+        c = np.ascontiguousarray(np.stack([c[:, 0] + 0.02 * np.sin(3.0 * c[:, 1]), c[:, 1] + 0.02 * np.cos(2.0 * c[:, 0])], 1) + rng.uniform(-0.02, 0.02, c.shape))
+    got = {}
+    for closed in (1, 0):
+        for threads in (1, 3):
+            M = A.Mesh(c, e, host_only=True)
+            assert _info(M, _lib.INFO_STRUCTURED) == (3 if mapped else 1)
+            M.set_option("structured_pattern", closed)
+            M.set_option("host_threads", threads)
+            rowptr, colind = M.csr_pattern(1)
+            got[closed, threads] = [rowptr, colind, M.slot_to_nnz()] + [M.plan_array(w, nc, a, np.int64 if a == 0 else np.uint8) for nc in (1, 2) for w in (0, 1) for a in (0, 1)]
+            assert _info(M, _lib.INFO_STRUCTURED) == (3 if mapped else 1)         # the closed-form row pointers of the kernels still validate
+    ref = got[0, 1]
+    for key, arrs in got.items():
+        for x, y in zip(ref, arrs):
+            assert x.shape == y.shape and np.array_equal(x, y), key
+    o = oracle.Mesh2D(c, e)
+    ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+    rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
+    assert np.array_equal(ref[0], rp) and np.array_equal(ref[1], ci)
+    with pytest.raises(_lib.AdfemError):
+        M.set_option("structured_pattern", 1)                                   # too late: the tables exist
+
+
 @pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5), (20, 9)])
 def test_tet_grid_detection(n, l):
     """Mesh3(n, n, l, h) (5 tetrahedra per cube, parity-alternating) is recognised from its arrays, also on rectilinear non-uniform coordinates;
