@@ -229,20 +229,23 @@ bool tet_pattern_matches(const ScalarPattern& pat, const TetGridTables& tab, int
   const GridTet gt{n, l, nullptr, nullptr, nullptr, &tab};
   const long long n1 = n + 1;
   if ((long long)pat.n != n1 * n1 * (l + 1)) return false;
-  for (int k = 0; k <= l; k++)
-    for (int j = 0; j <= n; j++)
-      for (int i = 0; i <= n; i++) {
-        const long long r = ((long long)k * n1 + j) * n1 + i;
-        const int mask = tg_row_mask(gt, (i + j + k) & 1, i, j, k);
-        if (tg_popc(mask) != (int)(pat.rowptr[r + 1] - pat.rowptr[r])) return false;
-        long long at = pat.rowptr[r];
-        for (int s = 0; s < 27; s++)
-          if ((mask >> s) & 1) {
-            const long long col = r + (long long)(s / 9 - 1) * n1 * n1 + (long long)((s / 3) % 3 - 1) * n1 + (s % 3 - 1);
-            if (pat.colind[at++] != col) return false;
-          }
-      }
-  return true;
+  std::atomic<bool> same(true);
+  host_parallel_for(l + 1, 0, [&](long long k0, long long k1) {          // node planes over the host threads
+    for (int k = (int)k0; k < (int)k1 && same.load(std::memory_order_relaxed); k++)
+      for (int j = 0; j <= n; j++)
+        for (int i = 0; i <= n; i++) {
+          const long long r = ((long long)k * n1 + j) * n1 + i;
+          const int mask = tg_row_mask(gt, (i + j + k) & 1, i, j, k);
+          if (tg_popc(mask) != (int)(pat.rowptr[r + 1] - pat.rowptr[r])) { same.store(false, std::memory_order_relaxed); return; }
+          long long at = pat.rowptr[r];
+          for (int s = 0; s < 27; s++)
+            if ((mask >> s) & 1) {
+              const long long col = r + (long long)(s / 9 - 1) * n1 * n1 + (long long)((s / 3) % 3 - 1) * n1 + (s % 3 - 1);
+              if (pat.colind[at++] != col) { same.store(false, std::memory_order_relaxed); return; }
+            }
+        }
+  });
+  return same.load();
 }
 
 bool grid_pattern_matches(const ScalarPattern& pat, int m, int n) {
@@ -287,7 +290,9 @@ int ensure_dev_slot_nnz(adfem_mesh* m) {
 int ensure_pattern(adfem_mesh* m) {
   if (m->has_pattern) return 0;
   // the structured triangulation (rectilinear or mapped) gets its tables from index arithmetic; option "structured_pattern" = 0: the general build
-  std::string err = (m->grid_ok && m->opt_grid_pattern) ? m->pat.build_tri_grid(m->hm, m->grid_m, m->grid_n, nthreads_of(m)) : m->pat.build(m->hm, nthreads_of(m));
+  std::string err = (m->grid_ok && m->opt_grid_pattern) ? m->pat.build_tri_grid(m->hm, m->grid_m, m->grid_n, nthreads_of(m))
+                    : (m->tet_ok && m->opt_grid_pattern) ? m->pat.build_tet_grid(m->hm, m->tet_n, m->tet_l, nthreads_of(m))
+                                                         : m->pat.build(m->hm, nthreads_of(m));
   if (!err.empty()) return fail("symbolic: " + err);
   m->has_pattern = true;
   if (m->grid_ok && !grid_pattern_matches(m->pat, m->grid_m, m->grid_n)) m->grid_ok = false;

@@ -1,4 +1,5 @@
 #include "plan.h"
+#include "tet_grid_tables.h"
 
 #include <algorithm>
 #include <atomic>
@@ -391,6 +392,98 @@ std::string ScalarPattern::build_tri_grid(const HostMesh& m, int gm, int gn, int
     }
   });
   pt.lap("pattern (structured): slot map");
+  return "";
+}
+
+std::string ScalarPattern::build_tet_grid(const HostMesh& m, int gn, int gl, int nthreads) {
+  const long long n1 = gn + 1, plane = n1 * n1;
+  if (m.dim != 3 || m.degree != 1 || m.d != 4 || gn < 1 || gl < 1 || plane * (gl + 1) != m.ndof || 5LL * gn * gn * gl != m.ne)
+    return "not the structured tetrahedral grid";
+  PhaseTimer pt;
+  TetGridTables T;
+  build_tet_grid_tables(T);
+  n = m.ndof;
+  const long long nslot_rows = 4LL * m.ne;
+  if (nslot_rows > 2147483647LL) return "ne*elem_ndof exceeds 32-bit";
+  // incident tetrahedra (table entries whose cube exists) and the 27-bit mask of the row entries of node (i, j, k)
+  auto node = [&](long long r, int& i, int& j, int& k) { i = (int)(r % n1); j = (int)((r / n1) % n1); k = (int)(r / plane); };
+  auto exists = [&](const int* inc, int i, int j, int k) {
+    const int ci = i + inc[0], cj = j + inc[1], ck = k + inc[2];
+    return ci >= 0 && ci < gn && cj >= 0 && cj < gn && ck >= 0 && ck < gl;
+  };
+  auto popc = [](unsigned v) { return __builtin_popcount(v); };
+  assign_parallel(adj_ptr, (size_t)n + 1, nthreads);
+  assign_parallel(rowptr, (size_t)n + 1, nthreads);
+  std::vector<uint32_t> maskv;
+  assign_parallel(maskv, (size_t)n, nthreads);
+  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+    for (long long r = b; r < e; r++) {
+      int i, j, k;
+      node(r, i, j, k);
+      const int par = (i + j + k) & 1;
+      int cnt = 0; unsigned mask = 0;
+      for (int t = 0; t < T.ninc[par]; t++)
+        if (exists(T.inc[par][t], i, j, k)) { cnt++; for (int q = 0; q < 4; q++) mask |= 1u << T.vslot[par][t][q]; }
+      adj_ptr[r + 1] = cnt; rowptr[r + 1] = popc(mask); maskv[r] = mask;
+    }
+  });
+  for (long long r = 0; r < n; r++) { adj_ptr[r + 1] += adj_ptr[r]; rowptr[r + 1] += rowptr[r]; }
+  nnz = rowptr[n];
+  if (adj_ptr[n] != nslot_rows) return "structured tetrahedral grid: incidence count mismatch";
+  if (nnz > 4294967295LL) return "scalar nnz exceeds 32-bit slot map";
+  pt.lap("pattern (structured tetrahedra): counts");
+  assign_parallel(adj_elem, (size_t)nslot_rows, nthreads); assign_parallel(adj_loc, (size_t)nslot_rows, nthreads);
+  assign_parallel(colind, (size_t)nnz, nthreads);
+  assign_parallel(slot_nnz, (size_t)m.ne * 16, nthreads);
+  pt.lap("pattern (structured tetrahedra): allocation");
+  std::atomic<bool> bad(false);
+  // per node: columns from the mask, incident tetrahedra from the table (the node's local position is read from the mesh)
+  parallel_for(n, nthreads, [&](long long b, long long e, int) {
+    for (long long r = b; r < e; r++) {
+      int i, j, k;
+      node(r, i, j, k);
+      const int par = (i + j + k) & 1;
+      const unsigned mask = maskv[r];
+      long long at = rowptr[r];
+      for (int s = 0; s < 27; s++)
+        if ((mask >> s) & 1) colind[at++] = (int)(r + (long long)(s / 9 - 1) * plane + (long long)((s / 3) % 3 - 1) * n1 + (s % 3 - 1));
+      long long a = adj_ptr[r];
+      for (int t = 0; t < T.ninc[par]; t++) {
+        const int* inc = T.inc[par][t];
+        if (!exists(inc, i, j, k)) continue;
+        const long long cube = ((long long)(i + inc[0]) * gn + (j + inc[1])) * gl + (k + inc[2]);
+        const long long el = 5 * cube + inc[3];
+        const int* v = &m.conn[(size_t)el * 4];
+        int p = -1;
+        for (int q = 0; q < 4; q++) if (v[q] == r) p = q;
+        if (p < 0) { bad.store(true); return; }
+        adj_elem[a] = (int)el; adj_loc[a] = (uint8_t)p; a++;
+      }
+    }
+  });
+  pt.lap("pattern (structured tetrahedra): adjacency, columns");
+  // per element (one cache line of the slot map each): local entry (p, q) lands in the row of vertex p at the position of vertex q among the row
+  // entries — its 27-neighbourhood slot (dk+1) 9 + (dj+1) 3 + (di+1), counted through the row's mask
+  parallel_for(m.ne, nthreads, [&](long long b, long long e, int) {
+    for (long long el = b; el < e; el++) {
+      const int* v = &m.conn[(size_t)el * 4];
+      int c[4][3];
+      for (int q = 0; q < 4; q++) node(v[q], c[q][0], c[q][1], c[q][2]);
+      for (int p = 0; p < 4; p++) {
+        const unsigned mask = maskv[v[p]];
+        const long long rs = rowptr[v[p]];
+        for (int q = 0; q < 4; q++) {
+          const int di = c[q][0] - c[p][0], dj = c[q][1] - c[p][1], dk = c[q][2] - c[p][2];
+          if (di < -1 || di > 1 || dj < -1 || dj > 1 || dk < -1 || dk > 1) { bad.store(true); return; }
+          const int slot = (dk + 1) * 9 + (dj + 1) * 3 + (di + 1);
+          if (!((mask >> slot) & 1)) { bad.store(true); return; }
+          slot_nnz[((size_t)el * 4 + p) * 4 + q] = (uint32_t)(rs + popc(mask & ((1u << slot) - 1)));
+        }
+      }
+    }
+  });
+  if (bad.load()) return "structured tetrahedral grid: an element does not hold the generator's vertices";
+  pt.lap("pattern (structured tetrahedra): slot map");
   return "";
 }
 

@@ -39,6 +39,10 @@ struct ScalarPattern {
   // it: cell (ci, cj) with first node a = ci (gm+1) + cj holds the triangles (a, a+1, a+gm+1) and (a+gm+1, a+1, a+gm+2)), from index arithmetic:
   // no counting sort, no per-row sets, no searches in the connectivity.  Byte-identical to build() (tests/test_structured.py).
   std::string build_tri_grid(const HostMesh& m, int gm, int gn, int nthreads);
+  // The same for the structured tetrahedral grid Mesh3(gn, gn, gl, h), P1 (element 5 * cube + t holds the vertex SET of tetrahedron t of the cube's
+  // splitting, as detect_tet_grid verifies; the local position of a vertex inside its element is read from the mesh, the orientation fix may have
+  // swapped the first two): incident tetrahedra and row entries of a node from the two parity neighbourhoods of tet_grid_tables.h.
+  std::string build_tet_grid(const HostMesh& m, int gn, int gl, int nthreads);
 };
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }

@@ -91,6 +91,38 @@ def test_closed_form_symbolic_tables(oracle, m, n, mapped):
         M.set_option("structured_pattern", 1)                                   # too late: the tables exist
 
 
+@pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5), (17, 16), (3, 40)])
+def test_closed_form_symbolic_tables_tetrahedra(oracle, n, l):
+    """Mesh3(n, n, l, h): the symbolic tables from the two parity neighbourhoods (ScalarPattern::build_tet_grid, the default on the structured
+    tetrahedral grid) are the bytes of the general build (structured_pattern = 0) — pattern, slot map, tile plans — for 1 and 3 host threads,
+    also when elements list their vertices in another order (the local positions are read from the mesh), and the pattern is the oracle's."""
+    c, e = meshgen.tet_grid(n, n, l, 0.25)
+    rng = np.random.default_rng(n * 7 + l)
+    e2 = e.copy()
+    for at in rng.choice(len(e2), size=max(1, len(e2) // 3), replace=False):
+        e2[at] = e2[at][rng.permutation(4)]
+    for conn in (e, e2):
+        got = {}
+        for closed in (1, 0):
+            for threads in (1, 3):
+                M = A.Mesh3(c, conn, host_only=True)
+                assert _info(M, _lib.INFO_STRUCTURED) == 2
+                M.set_option("structured_pattern", closed)
+                M.set_option("host_threads", threads)
+                rowptr, colind = M.csr_pattern(1)
+                got[closed, threads] = [rowptr, colind, M.slot_to_nnz()] + [M.plan_array(w, nc, a, np.int64 if a == 0 else np.uint8) for nc in (1, 3) for w in (0, 1) for a in (0, 1)]
+                assert _info(M, _lib.INFO_STRUCTURED) == 2
+        ref = got[0, 1]
+        for key, arrs in got.items():
+            for x, y in zip(ref, arrs):
+                assert x.shape == y.shape and np.array_equal(x, y), key
+        if n * n * l <= 5 ** 3:
+            o = oracle.Mesh3D(c, conn)
+            ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+            rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
+            assert np.array_equal(ref[0], rp) and np.array_equal(ref[1], ci)
+
+
 @pytest.mark.parametrize("n,l", [(1, 1), (2, 3), (4, 2), (5, 5), (20, 9)])
 def test_tet_grid_detection(n, l):
     """Mesh3(n, n, l, h) (5 tetrahedra per cube, parity-alternating) is recognised from its arrays, also on rectilinear non-uniform coordinates;
