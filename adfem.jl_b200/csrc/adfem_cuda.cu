@@ -909,13 +909,15 @@ int adfem_csr_pattern(adfem_mesh* m, int ncomp, long long* rowptr, int* colind) 
   const ScalarPattern& p = m->pat;
   const long long n = p.n;
   if ((long long)ncomp * n > 2147483647LL) return fail("ncomp*ndof exceeds 32-bit column ids");
-  for (int a = 0; a < ncomp; a++)
-    for (long long r = 0; r < n; r++) {
-      const long long rs = p.rowptr[r], len = p.rowptr[r + 1] - rs, base = ncomp * (a * p.nnz + rs);
-      rowptr[a * n + r] = base;
-      for (int b = 0; b < ncomp; b++)
-        for (long long j = 0; j < len; j++) colind[base + b * len + j] = (int)(p.colind[rs + j] + b * n);
-    }
+  host_parallel_for(n, nthreads_of(m), [&](long long r0, long long r1) {         // row blocks over the host threads (the caller's arrays are first touched here)
+    for (int a = 0; a < ncomp; a++)
+      for (long long r = r0; r < r1; r++) {
+        const long long rs = p.rowptr[r], len = p.rowptr[r + 1] - rs, base = ncomp * (a * p.nnz + rs);
+        rowptr[a * n + r] = base;
+        for (int b = 0; b < ncomp; b++)
+          for (long long j = 0; j < len; j++) colind[base + b * len + j] = (int)(p.colind[rs + j] + b * n);
+      }
+  }, 1 << 16);
   rowptr[ncomp * n] = p.nnz * ncomp * ncomp;
   return 0;
 }

@@ -296,6 +296,17 @@ def test_symbolic_phase_is_thread_count_independent(oracle, dim, degree, ncomp):
     for other in got[1:]:
         for a, b in zip(got[0], other):
             assert a.shape == b.shape and np.array_equal(a, b)
+    # the component-blocked pattern handed to the caller (row blocks over the threads) is the documented expansion of the scalar one
+    rowptr, colind = got[0][0], got[0][1]
+    nd, nnz, lens = o.ndof, len(colind), np.diff(rowptr)
+    rp_v, ci_v = m.csr_pattern(dim)
+    within = np.arange(nnz) - np.repeat(rowptr[:-1], lens)
+    want = np.empty(dim * dim * nnz, dtype=np.int64)
+    for a in range(dim):
+        assert np.array_equal(rp_v[a * nd:(a + 1) * nd], dim * (a * nnz + rowptr[:-1]))
+        for b in range(dim):
+            want[np.repeat(dim * (a * nnz + rowptr[:-1]) + b * lens, lens) + within] = colind + b * nd
+    assert rp_v[-1] == dim * dim * nnz and np.array_equal(ci_v, want)
     ind, vv = o.laplace_fwd(np.ones(o.ngauss))
     rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
     assert np.array_equal(got[0][0], rp) and np.array_equal(got[0][1], ci)
