@@ -35,6 +35,50 @@ void host_parallel_for(long long n, int nthreads, const std::function<void(long 
   for (auto& x : th) x.join();
 }
 
+void radix_sort_by_key(std::vector<KeyId>& a, int nthreads) {
+  const long long n = (long long)a.size();
+  constexpr int BITS = 11, NB = 1 << BITS;
+  const int T = std::max(1, nthreads);
+  uint64_t any = 0, all = ~0ULL;
+  for (const KeyId& p : a) { any |= p.key; all &= p.key; }
+  const uint64_t varying = any ^ all;
+  std::vector<KeyId> b;
+  b.reserve((size_t)n);
+  advise_huge_pages(b.data(), (size_t)n * sizeof(KeyId));
+  {
+    KeyId* p = b.data();
+    host_parallel_for(n, T, [&](long long i0, long long i1) { memset(static_cast<void*>(p + i0), 0, (size_t)(i1 - i0) * sizeof(KeyId)); }, 1 << 16);
+  }
+  b.resize((size_t)n);
+  std::vector<long long> cut(T + 1);
+  for (int t = 0; t <= T; t++) cut[t] = n * t / T;
+  std::vector<std::vector<long long>> hist(T, std::vector<long long>(NB));
+  for (int shift = 0; shift < 64; shift += BITS) {
+    if (((varying >> shift) & (NB - 1)) == 0) continue;
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
+        std::vector<long long>& h = hist[t];
+        std::fill(h.begin(), h.end(), 0);
+        for (long long i = cut[t]; i < cut[t + 1]; i++) h[(a[i].key >> shift) & (NB - 1)]++;
+      });
+      for (auto& x : th) x.join();
+    }
+    long long run = 0;
+    for (int dgt = 0; dgt < NB; dgt++)
+      for (int t = 0; t < T; t++) { const long long c = hist[t][dgt]; hist[t][dgt] = run; run += c; }
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
+        std::vector<long long>& h = hist[t];
+        for (long long i = cut[t]; i < cut[t + 1]; i++) b[h[(a[i].key >> shift) & (NB - 1)]++] = a[i];
+      });
+      for (auto& x : th) x.join();
+    }
+    a.swap(b);
+  }
+}
+
 std::vector<int> soa_copy(const std::vector<int>& aos, long long ne, int kcount) {
   std::vector<int> out;
   const size_t total = (size_t)ne * kcount;
@@ -78,6 +122,63 @@ const int kTetEdges[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
 // Global edge ids in first-appearance order while walking elements 0..E-1 and their local edges in
 // geometry order — the numbering MFEM's GetElementToEdgeTable produces and the reference exposes
 // through `edges` and `dof[k+nv]` (deps/MFEM/Common.cpp:70-74,133-140).
+int host_threads() {
+  int nt = 0;
+  if (const char* s = getenv("ADFEM_HOST_THREADS")) nt = atoi(s);
+  if (nt <= 0) { unsigned h = std::thread::hardware_concurrency(); nt = h == 0 ? 4 : (int)std::min(h, 64u); }
+  return nt;
+}
+
+// The numbering of EdgeNumbering below (edge ids in order of first appearance over (element, local edge)) without the sequential walk: sort the
+// (edge key, appearance) records by key — the first record of a key is its first appearance —, then rank the edges by that first appearance.
+// ids[e * nel + j] = edge id of local edge j of element e; lo / hi = end points per edge id.  Same arrays as the walk (tests/test_host_plan.py).
+void number_edges_sorted(const std::vector<int>& verts, int ne, int nvl, int nel, const int (*local)[2], int nt, std::vector<int>& ids,
+                         std::vector<int>& lo, std::vector<int>& hi) {
+  const long long nrec = (long long)ne * nel;
+  std::vector<KeyId> rec;
+  rec.reserve((size_t)nrec);
+  advise_huge_pages(rec.data(), (size_t)nrec * sizeof(KeyId));
+  {
+    KeyId* p = rec.data();
+    host_parallel_for(nrec, nt, [&](long long a, long long b) { memset(static_cast<void*>(p + a), 0, (size_t)(b - a) * sizeof(KeyId)); }, 1 << 16);
+  }
+  rec.resize((size_t)nrec);
+  host_parallel_for(ne, nt, [&](long long e0, long long e1) {
+    for (long long e = e0; e < e1; e++) {
+      const int* vi = &verts[(size_t)e * nvl];
+      for (int j = 0; j < nel; j++) {
+        const int a = vi[local[j][0]], b = vi[local[j][1]];
+        const uint64_t l = (uint64_t)(a <= b ? a : b), h = (uint64_t)(a <= b ? b : a);
+        rec[(size_t)e * nel + j] = KeyId{l << 32 | h, (int)(e * nel + j)};
+      }
+    }
+  }, 1 << 14);
+  radix_sort_by_key(rec, nt);
+  // groups of equal keys; group g starts at record start[g], which carries the smallest appearance index of the edge
+  std::vector<KeyId> first;             // (first appearance, group)
+  std::vector<long long> start;
+  for (long long i = 0; i < nrec; i++)
+    if (i == 0 || rec[i].key != rec[i - 1].key) { first.push_back(KeyId{(uint64_t)rec[i].id, (int)start.size()}); start.push_back(i); }
+  const long long nedge = (long long)start.size();
+  start.push_back(nrec);
+  radix_sort_by_key(first, nt);         // by first appearance: position = edge id
+  std::vector<int> id_of_group((size_t)nedge);
+  lo.resize((size_t)nedge); hi.resize((size_t)nedge);
+  host_parallel_for(nedge, nt, [&](long long a, long long b) {
+    for (long long id = a; id < b; id++) {
+      const int g = first[id].id;
+      id_of_group[g] = (int)id;
+      const uint64_t key = rec[start[g]].key;
+      lo[id] = (int)(key >> 32); hi[id] = (int)(key & 0xffffffffu);
+    }
+  }, 1 << 14);
+  ids.resize((size_t)nrec);
+  host_parallel_for(nedge, nt, [&](long long a, long long b) {
+    for (long long g = a; g < b; g++)
+      for (long long i = start[g]; i < start[g + 1]; i++) ids[rec[i].id] = id_of_group[g];
+  }, 1 << 14);
+}
+
 struct EdgeNumbering {
   std::vector<int> head, next, hi, lo;
   // `expect`: a guess of the edge count (the lists are reserved and advised for huge pages: the walk below is one dependent random access after
@@ -154,6 +255,21 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
   if (degree == 1) {
     par_elems(ne, [&](long long e0, long long e1) { memcpy(conn.data() + (size_t)e0 * d, verts.data() + (size_t)e0 * d, (size_t)(e1 - e0) * d * sizeof(int)); });
   } else {
+    const int nt = host_threads();
+    if (nt > 1 && ne >= 32768 && (long long)ne * nel < 1500000000LL) {          // threaded, sort-based (3 x 16 B per record of scratch)
+      std::vector<int> ids;
+      number_edges_sorted(verts, ne, nvl, nel, dim == 2 ? kTriEdges : kTetEdges, nt, ids, edge_lo, edge_hi);
+      nedges = (long long)edge_lo.size();
+      host_parallel_for(ne, nt, [&](long long e0, long long e1) {
+        for (long long e = e0; e < e1; e++) {
+          const int* vi = &verts[(size_t)e * nvl];
+          int* ce = &conn[(size_t)e * d];
+          for (int k = 0; k < nvl; k++) ce[k] = vi[k];
+          for (int j = 0; j < nel; j++) ce[nvl + j] = nv + ids[(size_t)e * nel + j];
+        }
+      }, 1 << 14);
+      edges_built = true;
+    } else {
     EdgeNumbering en(nv, expected_edges());
     for (int e = 0; e < ne; e++) {
       const int* vi = &verts[(size_t)e * nvl];
@@ -172,6 +288,7 @@ std::string HostMesh::build(int dim_, const double* vertices, int vstride, int n
     edge_lo.swap(en.lo);
     edge_hi.swap(en.hi);
     edges_built = true;
+    }
   }
   long long nd = degree == 1 ? (long long)nv : (long long)nv + nedges;
   if (nd > 2147483647LL) return "too many dofs for 32-bit dof ids";

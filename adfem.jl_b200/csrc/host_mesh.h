@@ -24,6 +24,15 @@ void host_parallel_for(long long n, int nthreads, const std::function<void(long 
 // elements with one coalesced load).  Element blocks over the host threads, pages of the copy first touched by them.
 std::vector<int> soa_copy(const std::vector<int>& aos, long long ne, int kcount);
 
+struct KeyId {
+  uint64_t key; int id;
+  bool operator<(const KeyId& o) const { return key != o.key ? key < o.key : id < o.id; }
+};
+// Stable LSD radix sort by key, 11 bits per pass, blocks of the input over the threads (per-thread histograms, exclusive offsets per
+// (digit, thread)); passes whose digit is the same for every key are skipped.  With the input in ascending id order equal keys stay in
+// ascending id order: the result is the (key, id)-lexicographic order a comparison sort of the pairs gives.
+void radix_sort_by_key(std::vector<KeyId>& a, int nthreads);
+
 struct HostMesh {
   int dim = 0;          // 2 (triangles) or 3 (tetrahedra)
   int nv = 0;           // vertices

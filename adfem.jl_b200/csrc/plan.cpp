@@ -117,52 +117,6 @@ struct Morton {
   }
 };
 
-struct KeyId {
-  uint64_t key; int id;
-  bool operator<(const KeyId& o) const { return key != o.key ? key < o.key : id < o.id; }
-};
-
-// Stable LSD radix sort by key, 11 bits per pass, blocks of the input over the threads (per-thread histograms, exclusive offsets per
-// (digit, thread)); passes whose digit is the same for every key are skipped.  The input is in ascending id order, so equal keys stay in
-// ascending id order: the result is the (key, id)-lexicographic order a comparison sort of the pairs gives.
-void radix_sort_by_key(std::vector<KeyId>& a, int nthreads) {
-  const long long n = (long long)a.size();
-  constexpr int BITS = 11, NB = 1 << BITS;
-  const int T = std::max(1, nthreads);
-  uint64_t any = 0, all = ~0ULL;
-  for (const KeyId& p : a) { any |= p.key; all &= p.key; }
-  const uint64_t varying = any ^ all;
-  std::vector<KeyId> b;
-  assign_parallel(b, (size_t)n, nthreads);
-  std::vector<long long> cut(T + 1);
-  for (int t = 0; t <= T; t++) cut[t] = n * t / T;
-  std::vector<std::vector<long long>> hist(T, std::vector<long long>(NB));
-  for (int shift = 0; shift < 64; shift += BITS) {
-    if (((varying >> shift) & (NB - 1)) == 0) continue;
-    {
-      std::vector<std::thread> th;
-      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
-        std::vector<long long>& h = hist[t];
-        std::fill(h.begin(), h.end(), 0);
-        for (long long i = cut[t]; i < cut[t + 1]; i++) h[(a[i].key >> shift) & (NB - 1)]++;
-      });
-      for (auto& x : th) x.join();
-    }
-    long long run = 0;
-    for (int dgt = 0; dgt < NB; dgt++)
-      for (int t = 0; t < T; t++) { const long long c = hist[t][dgt]; hist[t][dgt] = run; run += c; }
-    {
-      std::vector<std::thread> th;
-      for (int t = 0; t < T; t++) th.emplace_back([&, t] {
-        std::vector<long long>& h = hist[t];
-        for (long long i = cut[t]; i < cut[t + 1]; i++) b[h[(a[i].key >> shift) & (NB - 1)]++] = a[i];
-      });
-      for (auto& x : th) x.join();
-    }
-    a.swap(b);
-  }
-}
-
 // ids sorted by (Morton code of their position, id)
 void morton_order(long long n, int nthreads, const std::function<uint64_t(long long)>& code, std::vector<int>& order) {
   std::vector<KeyId> keyed;

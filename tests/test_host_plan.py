@@ -317,6 +317,40 @@ def test_symbolic_phase_is_thread_count_independent(oracle, dim, degree, ncomp):
     assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_threaded_edge_numbering_is_the_sequential_walk(oracle, dim):
+    """P2 meshes of 32768+ elements number their edges by sorting (edge, appearance) records instead of walking the elements; ids, end points and
+    the P2 connectivity must be those of the first-appearance walk (deps/MFEM/Common.cpp:70-74,133-140): against the oracle's walk and
+    against the library's own sequential path (ADFEM_HOST_THREADS=1), on a randomly renumbered mesh."""
+    import os
+    rng = np.random.default_rng(dim)
+    if dim == 2:
+        c, e = meshgen.jitter_unstructured(140, 130, 1.0 / 140, seed=6, permute=True)
+        mk, o = (lambda: A.Mesh(c, e, degree=2, host_only=True)), oracle.Mesh2D(c, e, degree=2)
+    else:
+        c, e = meshgen.tet_grid(19, 19, 20, 1.0 / 19)
+        c = c + rng.uniform(-0.1 / 19, 0.1 / 19, c.shape)
+        perm = rng.permutation(len(c))
+        inv = np.empty_like(perm); inv[perm] = np.arange(len(c))
+        c, e = np.ascontiguousarray(c[perm]), np.ascontiguousarray(inv[e][rng.permutation(len(e))]).astype(e.dtype)
+        mk, o = (lambda: A.Mesh3(c, e, degree=2, host_only=True)), oracle.Mesh3D(c, e, degree=2)
+    assert o.nelem >= 32768
+    old = os.environ.get("ADFEM_HOST_THREADS")
+    try:
+        got = []
+        for threads in ("1", "4", "7"):
+            os.environ["ADFEM_HOST_THREADS"] = threads
+            m = mk()
+            got.append((m.nedge, m.edges.copy(), m.conn.copy()))
+    finally:
+        if old is None:
+            os.environ.pop("ADFEM_HOST_THREADS", None)
+        else:
+            os.environ["ADFEM_HOST_THREADS"] = old
+    for nedge, edges, conn in got:
+        assert nedge == o.nedge and np.array_equal(edges, o.edges) and np.array_equal(conn, o.conn)
+
+
 def test_device_path_host_helpers(tmp_path):
     """Host helpers the library only reaches with a GPU (adfem_mesh_create's struct-of-arrays copies of the element tables), built for the host
     with g++ from the product's own source (tests/host_emul/host_check.cpp + csrc/host_mesh.cpp) and checked against numpy, below and above the
