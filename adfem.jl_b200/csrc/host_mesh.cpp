@@ -302,6 +302,14 @@ size_t HostMesh::expected_edges() const { return dim == 2 ? (size_t)nv + ne + 64
 void HostMesh::ensure_edges() const {
   if (edges_built) return;
   const int nvl = dim + 1, nel = dim == 2 ? 3 : 6;
+  const int nt = host_threads();
+  if (nt > 1 && ne >= 32768 && (long long)ne * nel < 1500000000LL) {
+    std::vector<int> ids;
+    number_edges_sorted(verts, ne, nvl, nel, dim == 2 ? kTriEdges : kTetEdges, nt, ids, edge_lo, edge_hi);
+    nedges = (long long)edge_lo.size();
+    edges_built = true;
+    return;
+  }
   EdgeNumbering en(nv, expected_edges());
   for (int e = 0; e < ne; e++) {
     const int* vi = &verts[(size_t)e * nvl];

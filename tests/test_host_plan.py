@@ -327,6 +327,7 @@ def test_threaded_edge_numbering_is_the_sequential_walk(oracle, dim):
     if dim == 2:
         c, e = meshgen.jitter_unstructured(140, 130, 1.0 / 140, seed=6, permute=True)
         mk, o = (lambda: A.Mesh(c, e, degree=2, host_only=True)), oracle.Mesh2D(c, e, degree=2)
+        mk1 = lambda: A.Mesh(c, e, host_only=True)
     else:
         c, e = meshgen.tet_grid(19, 19, 20, 1.0 / 19)
         c = c + rng.uniform(-0.1 / 19, 0.1 / 19, c.shape)
@@ -334,6 +335,7 @@ def test_threaded_edge_numbering_is_the_sequential_walk(oracle, dim):
         inv = np.empty_like(perm); inv[perm] = np.arange(len(c))
         c, e = np.ascontiguousarray(c[perm]), np.ascontiguousarray(inv[e][rng.permutation(len(e))]).astype(e.dtype)
         mk, o = (lambda: A.Mesh3(c, e, degree=2, host_only=True)), oracle.Mesh3D(c, e, degree=2)
+        mk1 = lambda: A.Mesh3(c, e, host_only=True)
     assert o.nelem >= 32768
     old = os.environ.get("ADFEM_HOST_THREADS")
     try:
@@ -342,6 +344,8 @@ def test_threaded_edge_numbering_is_the_sequential_walk(oracle, dim):
             os.environ["ADFEM_HOST_THREADS"] = threads
             m = mk()
             got.append((m.nedge, m.edges.copy(), m.conn.copy()))
+            m1 = mk1()                       # P1: the edge list is numbered on first use, the same way
+            assert m1.nedge == o.nedge and np.array_equal(m1.edges, o.edges)
     finally:
         if old is None:
             os.environ.pop("ADFEM_HOST_THREADS", None)
