@@ -92,8 +92,19 @@ def morton_element_order(coords, elems):
     c = coords[elems].mean(1)
     lo, hi = c.min(0), c.max(0)
     q = np.minimum(((c - lo) / np.maximum(hi - lo, 1e-300) * 65535).astype(np.uint64), 65535)
+    dim = c.shape[1]
     key = np.zeros(len(c), dtype=np.uint64)
-    for b in range(16):
-        for d in range(c.shape[1]):
-            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(c.shape[1] * b + d)
+    # bit b of coordinate d goes to bit dim*b + d: spread the 16 bits of a coordinate with the usual shift-and-mask cascade
+    cascade = {2: ((8, 0x00FF00FF), (4, 0x0F0F0F0F), (2, 0x33333333), (1, 0x55555555)),
+               3: ((32, 0x1F00000000FFFF), (16, 0x1F0000FF0000FF), (8, 0x100F00F00F00F00F), (4, 0x10C30C30C30C30C3), (2, 0x1249249249249249))}
+    if dim in cascade:
+        for d in range(dim):
+            x = q[:, d].copy()
+            for sh, mask in cascade[dim]:
+                x = (x | (x << np.uint64(sh))) & np.uint64(mask)
+            key |= x << np.uint64(d)
+    else:
+        for b in range(16):
+            for d in range(dim):
+                key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(dim * b + d)
     return np.argsort(key, kind="stable")
