@@ -30,8 +30,8 @@ def tri_grid(m, n, h, version=1, rng=None, dtype=np.int64):
     elif version == 3:
         rng = np.random.default_rng(0) if rng is None else rng
         pick = rng.random(m * n) > 0.5                                                                     # MFEM.jl:149-156
-        fill(el, pick, v1)
-        fill(el, ~pick, v2)
+        np.take(np.asarray((v2, v1), dtype=dtype), pick.astype(np.intp), axis=0, out=el)                  # the cell's pair of triangles, by its coin
+        el += a[:, None, None]
     else:
         raise ValueError("version must be 1, 2 or 3")
     elems = el.reshape(2 * m * n, 3)
