@@ -949,6 +949,7 @@ long long adfem_plan_array(adfem_mesh* m, int which_plan, int ncomp, int array_i
   } else {
     AdjPlanDev* P = nullptr;
     if (ensure_adj_plan(m, ncomp, &P)) return -1;
+    if (!P) { fail("no adjoint tile plan: the mesh has rows longer than 255 entries (the adjoint uses the gather kernel)"); return -1; }
     ptr = &P->host.blob_ptr; blob = &P->host.blob;
   }
   if (array_id == 0) { if (out) memcpy(out, ptr->data(), ptr->size() * sizeof(long long)); return (long long)ptr->size(); }

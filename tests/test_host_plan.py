@@ -389,6 +389,34 @@ def test_device_path_host_helpers(tmp_path):
             os.environ["ADFEM_HOST_THREADS"] = old
 
 
+@pytest.mark.parametrize("degree", [1, 2])
+def test_high_valence_vertex(oracle, degree):
+    """A fan of 3000 triangles around one vertex: rows far longer than the small-row fast paths of the symbolic phase (sorted adjacency rows,
+    sorted column sets).  Pattern and slot map are the oracle's for 1 and 4 host threads; the tile plans refuse such a mesh with an error
+    (a row of 3001 entries fits no tile; the COO-compatible kernels and the gather adjoint take it) — never with a crash."""
+    K = 3000
+    th = np.linspace(0, 2 * np.pi, K, endpoint=False)
+    c = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(th), np.sin(th)], 1)])
+    e = np.stack([np.zeros(K, dtype=np.int64), 1 + np.arange(K), 1 + (np.arange(K) + 1) % K], 1)
+    e = e[np.random.default_rng(0).permutation(K)]
+    o = oracle.Mesh2D(c, e, degree=degree)
+    ind, vv = o.laplace_fwd(np.ones(o.ngauss))
+    rp, ci, _ = oracle.canonical_csr(ind, vv, o.ndof)
+    dd = o.elem_ndof ** 2
+    blk = ind.reshape(o.nelem, o.g, dd, 2)[:, 0]
+    rows_of_nnz = np.repeat(np.arange(o.ndof), np.diff(rp))
+    for threads in (1, 4):
+        m = A.Mesh(c, e, degree=degree, host_only=True)
+        m.set_option("host_threads", threads)
+        rowptr, colind = m.csr_pattern(1)
+        assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci) and np.diff(rp).max() >= K
+        s2n = m.slot_to_nnz().reshape(o.nelem, dd)
+        assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
+        for which in (0, 1):
+            with pytest.raises(A._lib.AdfemError):
+                m.plan_array(which, 1, 0, np.int64)
+
+
 def test_plan_manifest_unchanged():
     """The symbolic phase is a byte-exact contract with the kernels (tile blobs are decoded on the device): digests of pattern, slot map and
     both tile plans over every element family / numbering / plan kind (scripts/host_plan_manifest.py) against the manifest committed when
