@@ -170,11 +170,11 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
       const long long r0 = adj_ptr[r], len = adj_ptr[r + 1] - r0;
       int* el = adj_elem.data() + r0;
       uint8_t* lo = adj_loc.data() + r0;
-      if (len <= 32) {                          // insertion sort of the (element, local) pairs by element (an element meets a dof once)
+      if (len <= 32) {                          // insertion sort of the (element, local) pairs (local decides only inside a degenerate element)
         for (long long i = 1; i < len; i++) {
           const int ke = el[i]; const uint8_t kl = lo[i];
           long long j = i - 1;
-          for (; j >= 0 && el[j] > ke; j--) { el[j + 1] = el[j]; lo[j + 1] = lo[j]; }
+          for (; j >= 0 && (el[j] > ke || (el[j] == ke && lo[j] > kl)); j--) { el[j + 1] = el[j]; lo[j + 1] = lo[j]; }
           el[j + 1] = ke; lo[j + 1] = kl;
         }
       } else {
@@ -185,6 +185,18 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
       }
     }
   });
+  {
+    std::atomic<bool> rep(false);
+    parallel_for(m.ne, nthreads, [&](long long b, long long e, int) {
+      bool r = false;
+      for (long long el = b; el < e; el++) {
+        const int* ce = &m.conn[(size_t)el * d];
+        for (int p = 1; p < d; p++) for (int q = 0; q < p; q++) r |= ce[p] == ce[q];
+      }
+      if (r) rep.store(true);
+    });
+    repeated_dofs = rep.load();
+  }
   pt.lap("pattern: adjacency");
   if (pt.on) {      // FNV-1a over the adjacency: lets two builds of the host code be compared
     uint64_t hsh = 1469598103934665603ULL;
@@ -611,10 +623,11 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
       rlen.push_back((uint16_t)len);
       nnz_t += (size_t)len;
       // one item per CSR entry of the row (ascending column) unless its mirror image was emitted from the other row of the pair; an entry
-      // receives at most one contribution per incident element, so item j owns pool[base + j*deg .. + deg)
+      // receives at most one contribution per incident element (d of them if elements repeat dofs), so item j owns pool[base + j*cap .. + cap)
       jitem.assign(len, -1);
       const size_t base = pool.size();
-      pool.resize(base + (size_t)len * deg);
+      const int cap = pat.repeated_dofs ? deg * d : deg;       // a degenerate element can feed an entry from several of its local columns
+      pool.resize(base + (size_t)len * cap);
       for (int j = 0; j < len; j++) {
         const int c = pat.colind[rs + j];
         int paired = 0; uint32_t d1 = 0;
@@ -628,7 +641,7 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
           }
         }
         jitem[j] = (int)items.size();
-        items.push_back(Item{code(lr, j), d1, paired, (uint32_t)(base + (size_t)j * deg), 0u});
+        items.push_back(Item{code(lr, j), d1, paired, (uint32_t)(base + (size_t)j * cap), 0u});
       }
       // contributions in ascending (element, local column) order = ascending slot id: the fixed summation order of every entry
       for (long long a = pat.adj_ptr[r]; a < pat.adj_ptr[r + 1]; a++) {

@@ -34,6 +34,8 @@ struct ScalarPattern {
   std::vector<long long> adj_ptr;   // n+1: dof -> incident (element, local index) pairs
   std::vector<int> adj_elem;        // ne*d
   std::vector<uint8_t> adj_loc;     // ne*d
+  bool repeated_dofs = false;       // some element lists a dof twice (a degenerate element): a CSR entry can then receive more than one
+                                    // contribution per incident (element, local dof) pair, which the forward tile builder sizes its lists for
   std::string build(const HostMesh& m, int nthreads);
   // The same tables for the structured triangulation Mesh(gm, gn, h), version 1, P1 (connectivity as detect_tri_grid of adfem_cuda.cu verifies
   // it: cell (ci, cj) with first node a = ci (gm+1) + cj holds the triangles (a, a+1, a+gm+1) and (a+gm+1, a+1, a+gm+2)), from index arithmetic:

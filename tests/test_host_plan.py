@@ -417,6 +417,32 @@ def test_high_valence_vertex(oracle, degree):
                 m.plan_array(which, 1, 0, np.int64)
 
 
+def test_degenerate_elements_do_not_break_the_symbolic_phase(oracle):
+    """Elements that list a vertex twice (zero area: their values are meaningless, as in the reference) must not corrupt the symbolic phase:
+    a CSR entry then receives several contributions from one (element, local dof) pair.  Pattern = the oracle's index set; slot map consistent;
+    plans build and are the same bytes for 1 and 4 threads."""
+    c, e = meshgen.jitter_unstructured(40, 30, 0.1, seed=5)
+    e = e.copy()
+    for at in (0, 17, len(e) // 2, len(e) - 1):
+        e[at, 1] = e[at, 0]
+    o = oracle.Mesh2D(c, e)
+    ind, _ = o.laplace_fwd(np.ones(o.ngauss))
+    rp, ci, _ = oracle.canonical_csr(ind, np.zeros(len(ind)), o.ndof)
+    blk = ind.reshape(o.nelem, o.g, 9, 2)[:, 0]
+    rows_of_nnz = np.repeat(np.arange(o.ndof), np.diff(rp))
+    got = []
+    for threads in (1, 4):
+        m = A.Mesh(c, e, host_only=True)
+        m.set_option("host_threads", threads)
+        rowptr, colind = m.csr_pattern(1)
+        assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+        s2n = m.slot_to_nnz().reshape(o.nelem, 9)
+        assert np.array_equal(rows_of_nnz[s2n], blk[..., 0]) and np.array_equal(ci[s2n], blk[..., 1])
+        got.append([m.plan_array(w, nc, a, np.int64 if a == 0 else np.uint8) for nc in (1, 2) for w in (0, 1) for a in (0, 1)])
+    for x, y in zip(*got):
+        assert np.array_equal(x, y)
+
+
 def test_plan_manifest_unchanged():
     """The symbolic phase is a byte-exact contract with the kernels (tile blobs are decoded on the device): digests of pattern, slot map and
     both tile plans over every element family / numbering / plan kind (scripts/host_plan_manifest.py) against the manifest committed when
