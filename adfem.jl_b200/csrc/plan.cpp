@@ -283,7 +283,17 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
         const int el = adj_elem[a], p = adj_loc[a];
         const int* ce = &m.conn[(size_t)el * d];
         uint32_t* dst = &slot_nnz[((size_t)el * d + p) * d];
-        for (int q = 0; q < d; q++) dst[q] = (uint32_t)(rowptr[r] + (std::lower_bound(cb, cend, ce[q]) - cb));
+        const int len = (int)(cend - cb);
+        if (len <= 64) {          // short row: count the smaller columns (no branches, vectorised) instead of a search with unpredictable ones
+          for (int q = 0; q < d; q++) {
+            const int c = ce[q];
+            int pos = 0;
+            for (int k = 0; k < len; k++) pos += cb[k] < c;
+            dst[q] = (uint32_t)(rowptr[r] + pos);
+          }
+        } else {
+          for (int q = 0; q < d; q++) dst[q] = (uint32_t)(rowptr[r] + (std::lower_bound(cb, cend, ce[q]) - cb));
+        }
       }
     }
   });
@@ -637,7 +647,10 @@ std::string FwdTiles::build(const HostMesh& m, const ScalarPattern& pat, int R, 
             if (lc < lr) continue;                  // already emitted from the other side
             const int* cb = &pat.colind[pat.rowptr[c]];
             const int* ce = &pat.colind[pat.rowptr[c + 1]];
-            paired = 1; d1 = code(lc, (int)(std::lower_bound(cb, ce, r) - cb));
+            int pos = 0;
+            if (ce - cb <= 64) { for (const int* k = cb; k < ce; k++) pos += *k < r; }      // short row: branch-free count
+            else pos = (int)(std::lower_bound(cb, ce, r) - cb);
+            paired = 1; d1 = code(lc, pos);
           }
         }
         jitem[j] = (int)items.size();
