@@ -232,9 +232,9 @@ std::string ScalarPattern::build(const HostMesh& m, int nthreads) {
           const int* ce = &m.conn[(size_t)adj_elem[a] * d];
           for (int q = 0; q < d; q++) {
             const int c = ce[q];
-            int i = cnt;
-            while (i > 0 && uq[i - 1] > c) i--;
-            if (i > 0 && uq[i - 1] == c) continue;
+            int i = 0, dup = 0;                       // position and presence by branch-free counts over the (short) set
+            for (int k = 0; k < cnt; k++) { i += uq[k] < c; dup += uq[k] == c; }
+            if (dup) continue;
             for (int k = cnt; k > i; k--) uq[k] = uq[k - 1];
             uq[i] = c; cnt++;
           }
