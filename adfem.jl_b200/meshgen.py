@@ -89,7 +89,7 @@ def jitter_unstructured(m, n, h, seed=2, jitter=0.3, permute=True):
 def morton_element_order(coords, elems):
     """Element permutation that sorts the centroids along a Morton curve: contiguous element blocks become spatially compact
     (used before an element-block partition of a mesh whose element numbering has no locality)."""
-    c = coords[elems].mean(1)
+    c = np.take(coords, elems, axis=0).mean(1)
     lo, hi = c.min(0), c.max(0)
     q = np.minimum(((c - lo) / np.maximum(hi - lo, 1e-300) * 65535).astype(np.uint64), 65535)
     dim = c.shape[1]

@@ -227,6 +227,8 @@ CASE_KERNELS = {          # (forward kernels, adjoint kernels) of the default pa
 
 def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host_only=False):
     """-> (mesh, partition or None, op, coefficients per Gauss point, description, scaling).  world > 1: element blocks, one per rank."""
+    import numpy as np
+
     import adfem_jl_b200 as A
     from adfem_jl_b200 import dist as adist
     from adfem_jl_b200 import meshgen
@@ -276,7 +278,7 @@ def build_case(case, rank, world, scale=1.0, size=None, numbering="random", host
                 + ("in Morton order of their centroids (SURVEY 8e: compact contiguous element blocks)" if morton else
                    ("randomly renumbered" if numbering == "random" else "in generator order")))
         if morton:
-            elems = elems[meshgen.morton_element_order(coords, elems)]
+            elems = np.take(elems, meshgen.morton_element_order(coords, elems), axis=0)
         op = 1 if case == "4m" else 0
         if world == 1:
             return A.Mesh(coords, elems, degree=2, **kw), None, op, 1, note, "strong"

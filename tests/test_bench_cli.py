@@ -58,6 +58,10 @@ def test_bench_cases_host_logic():
         got = bench.alg_bytes_per_elem(mesh, nc * nc * int(rowptr[-1]), cpg)
         assert abs(got - b) / b < 0.12, (case, got)     # small meshes: boundary effects in nnz/E and nnode/E
         assert scaling == ("strong" if case in ("4l", "5") else "weak")
+    # every other case name of the default run builds too (mapped grids, mass matrix, Morton-ordered elements)
+    for case, nelem in (("2m", 2 * 40 * 40), ("3m", None), ("4m", None), ("4o", None), ("4", None)):
+        mesh, part, op, c, note, scaling = bench.build_case(case, 0, 1, scale=0.01, size=40 if case == "2m" else None, host_only=True)
+        assert part is None and mesh.nelem > 0 and (nelem is None or mesh.nelem == nelem)
 
 
 def test_product_arm_needs_a_gpu():
