@@ -42,9 +42,15 @@ def make_nccl_comm(rank, world, group=None):
 
 def _boundary_faces(elems):
     f = np.concatenate([elems[:, [0, 1, 2]], elems[:, [0, 1, 3]], elems[:, [0, 2, 3]], elems[:, [1, 2, 3]]], 0)
-    f = np.sort(f, 1)
-    u, cnt = np.unique(f, axis=0, return_counts=True)
-    return u[cnt == 1]
+    f = np.sort(f, 1).astype(np.int64, copy=False)
+    # rows as integer keys (a 1-D unique is several times faster than the row-wise one): first (a, b) -> its rank among the distinct pairs, then
+    # rank * nv + c; ascending keys are the rows in (a, b, c) order
+    nv = np.int64(int(f.max()) + 1 if f.size else 1)
+    ab, rank_ab = np.unique(f[:, 0] * nv + f[:, 1], return_inverse=True)
+    key, cnt = np.unique(rank_ab.reshape(-1).astype(np.int64) * nv + f[:, 2], return_counts=True)
+    key = key[cnt == 1]
+    k_ab = ab[key // nv]
+    return np.stack([k_ab // nv, k_ab % nv, key % nv], 1).astype(elems.dtype, copy=False)
 
 
 class Partition:

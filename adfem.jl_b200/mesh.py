@@ -228,8 +228,12 @@ def bcedge(mesh):
     e = mesh.elems
     pairs = np.concatenate([e[:, [0, 1]], e[:, [2, 1]], e[:, [0, 2]]], 0)
     pairs = np.sort(pairs, 1)
-    uniq, cnt = np.unique(pairs, axis=0, return_counts=True)
-    return uniq[cnt % 2 == 1]
+    # rows as one integer key lo * nnode + hi: the ascending keys are the rows in (lo, hi) order, and a 1-D unique is several times faster than
+    # the row-wise one (this is most of the setup of an element-block partition of a 16 M-triangle mesh)
+    nn = np.int64(max(int(mesh.nnode), 1))
+    key, cnt = np.unique(pairs[:, 0].astype(np.int64) * nn + pairs[:, 1], return_counts=True)
+    key = key[cnt % 2 == 1]
+    return np.stack([key // nn, key % nn], 1).astype(pairs.dtype, copy=False)
 
 
 def get_edge_dof(edges, mesh):
