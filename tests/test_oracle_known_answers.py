@@ -447,3 +447,32 @@ def test_dirichlet_bd_known_answer(oracle):
     g = oracle.dirichlet_bd_bwd(ii + 1, jj + 1, np.arange(len(vv1), dtype=float), 100 + np.arange(len(vv2), dtype=float), np.array([1]), m, n)
     free = ~np.isin(ii, [0, 4])
     assert np.all(g[~free] == 0) and np.count_nonzero(g[free & np.isin(jj, [0, 4])] >= 100) == 12
+
+
+def test_boundary_edges_and_nodes_known_answers():
+    """`bcedge` / `bcnode` (src/MFEM/MCore.jl:385-450): Mesh(2, 2, h) has 8 boundary edges and every node but the centre on the boundary; on a
+    jittered, renumbered triangulation the boundary edges are the (lo, hi) pairs counted once by a dictionary walk over the elements, in
+    ascending (lo, hi) order; P2 adds the dofs of those edges."""
+    import collections
+    import adfem_jl_b200 as A
+    from adfem_jl_b200 import meshgen
+    m = A.Mesh(2, 2, 0.5, host_only=True)
+    assert len(A.bcedge(m)) == 8 and np.array_equal(A.bcnode(m), [0, 1, 2, 3, 5, 6, 7, 8])
+    c, e = meshgen.jitter_unstructured(13, 9, 0.1, seed=7)
+    for degree in (1, 2):
+        m = A.Mesh(c, e, degree=degree, host_only=True)
+        seen = collections.Counter()
+        for t in m.elems:
+            for a, b in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])):
+                seen[(min(a, b), max(a, b))] += 1
+        want = np.array(sorted(k for k, v in seen.items() if v == 1), dtype=np.int64)
+        bd = A.bcedge(m)
+        assert bd.dtype == np.int64 and np.array_equal(bd, want) and len(want) == 2 * (13 + 9)
+        nodes = np.unique(want.reshape(-1))
+        got = A.bcnode(m)
+        assert np.array_equal(got[:len(nodes)], nodes)
+        if degree == 2:
+            edge_of = {(min(a, b), max(a, b)): i for i, (a, b) in enumerate(m.edges)}
+            assert np.array_equal(got[len(nodes):], np.sort([edge_of[tuple(k)] for k in want]) + m.nnode)
+        else:
+            assert len(got) == len(nodes)
